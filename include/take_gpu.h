@@ -1,0 +1,200 @@
+/* take_gpu.h -- C ABI of the B200 rendering core that replaces TaKe's CPU hot path.
+ *
+ * The reference (TaKeTube/TaKe) has no plugin / FFI seam: `render()` (src/render.cpp:9-87) parses the
+ * scene, builds the BVH and runs the per-pixel path-tracing loop in one statically linked C++ function.
+ * This library replaces everything `render()` does AFTER `parse_scene` (src/render.cpp:28): BVH
+ * construction, ray-scene intersection and the Monte-Carlo path-integration loop.  A maintainer keeps
+ * the reference's front end (Mitsuba XML / PLY / OBJ / textures), flattens the parsed `Scene`
+ * (src/scene.h:13-33) into a `TakeSceneDesc`, and calls the functions below (INTEGRATION.md shows the
+ * ~80-line adapter).
+ *
+ * Conventions: plain C, no C++ types, no exceptions across the boundary.  Every function returns
+ * 0 on success or a negative TAKE_E_* code, with a human-readable message available from
+ * take_gpu_last_error() (thread-local).  The caller owns every host buffer; the library owns all
+ * device memory behind the opaque TakeScene handle.  A handle is bound to one CUDA device and is
+ * not thread-safe; different handles may be used from different host threads.  All calls are
+ * complete when they return.  There is NO CPU fallback: without a usable CUDA device every call
+ * fails with TAKE_E_CUDA.
+ *
+ * All reference arithmetic is IEEE double (src/take.h:27) and so are the data here.
+ */
+#ifndef TAKE_GPU_H
+#define TAKE_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TAKE_OK 0
+#define TAKE_E_INVALID (-1) /* bad argument / inconsistent scene description            */
+#define TAKE_E_CUDA (-2)    /* CUDA runtime error or no device (there is no CPU path)    */
+#define TAKE_E_NOMEM (-3)   /* host or device allocation failed                          */
+
+/* Material::index() of the reference's std::variant (src/material.h:82-93). */
+enum {
+    TAKE_MAT_DIFFUSE = 0,
+    TAKE_MAT_MIRROR = 1,
+    TAKE_MAT_PLASTIC = 2,
+    TAKE_MAT_PHONG = 3,
+    TAKE_MAT_BLINN_PHONG = 4,
+    TAKE_MAT_BLINN_MICROFACET = 5,
+    TAKE_MAT_DISNEY_DIFFUSE = 6,
+    TAKE_MAT_DISNEY_METAL = 7,     /* 7,8,10,11 evaluate as Lambertian in the reference   */
+    TAKE_MAT_DISNEY_GLASS = 8,     /* (src/materials/disney_metal.inl:1-28 and siblings)  */
+    TAKE_MAT_DISNEY_CLEARCOAT = 9, /* cosine sampling, eval == 0 (disney_clearcoat.inl:22-27) */
+    TAKE_MAT_DISNEY_SHEEN = 10,
+    TAKE_MAT_DISNEY_BSDF = 11
+};
+
+enum { TAKE_LIGHT_POINT = 0, TAKE_LIGHT_AREA = 1 }; /* src/light.h:9-19 */
+
+/* prim_flags bits */
+enum { TAKE_PRIM_HAS_NORMALS = 1, TAKE_PRIM_HAS_UVS = 2, TAKE_PRIM_SPHERE = 4 };
+
+/* Which of the reference's integrators to run (src/integrator/path_tracing.h). */
+enum {
+    TAKE_INTEGRATOR_MIS = 0,           /* path_tracing                :5-111  (what render.cpp:76 calls) */
+    TAKE_INTEGRATOR_RAW = 1,           /* path_tracing_raw            :114-157 */
+    TAKE_INTEGRATOR_ONE_SAMPLE_MIS = 2 /* path_tracing_one_sample_MIS :161-271 */
+};
+
+/* take_gpu_intersect flags */
+enum {
+    TAKE_ISECT_FAST = 0, /* SAH tree, conservative FP32 boxes, FP64 leaf test; ties -> larger reference DFS rank */
+    TAKE_ISECT_EXACT = 1 /* the reference's own tree topology, FP64 slab test and tmax updates (bvh.cpp:86-109) */
+};
+
+typedef struct TakeCamera { /* src/camera.h:5-11 */
+    int32_t width, height;
+    double lookfrom[3], lookat[3], up[3];
+    double vfov; /* vertical field of view in degrees (already converted, parse_scene.cpp:366-377) */
+} TakeCamera;
+
+typedef struct TakeTextureDesc { /* one Image3 of the TexturePool (src/texture.h:8-14, src/image.h:13-39) */
+    int32_t width, height;
+    const double *rgb; /* height*width*3, row-major, row 0 first */
+} TakeTextureDesc;
+
+typedef struct TakeMaterialDesc { /* POD image of one `Material` alternative (src/material.h:7-80) */
+    int32_t type;                 /* TAKE_MAT_*                                                          */
+    int32_t tex_id;               /* >= 0: ImageTexture into textures[]; -1: ConstTexture `color`       */
+    double color[3];              /* ConstTexture::value (src/texture.h:22-25)                          */
+    double uscale, vscale, uoffset, voffset; /* ImageTexture (src/texture.h:16-20)                      */
+    double p[2];                  /* eta (mirror, plastic) | exponent (phong, blinn*) | roughness, subsurface (disney diffuse) */
+} TakeMaterialDesc;
+
+typedef struct TakeLightDesc { /* src/light.h:9-19 */
+    int32_t kind;              /* TAKE_LIGHT_*                                             */
+    int32_t prim_id;           /* DiffuseAreaLight::shape_id (primitive id), -1 for points */
+    double intensity[3];
+    double position[3];        /* PointLight only */
+} TakeLightDesc;
+
+/* Flattened `Scene` (src/scene.h:13-33).  Primitive id == index into the reference's scene.shapes:
+ * one entry per mesh face in parse order (src/parse/parse_scene.cpp:937-945) or per sphere. */
+typedef struct TakeSceneDesc {
+    TakeCamera camera;
+    double background[3];          /* Scene::background_color */
+    int64_t num_vertices;          /* all meshes' vertex arrays concatenated (src/shape.h:13-18) */
+    const double *positions;       /* 3*num_vertices */
+    const double *normals;         /* 3*num_vertices (zeros where the mesh has none) */
+    const double *uvs;             /* 2*num_vertices (zeros where the mesh has none) */
+    int64_t num_prims;
+    const int32_t *indices;        /* 3*num_prims global vertex indices; for a sphere: {sphere index, 0, 0} */
+    const int32_t *prim_material;  /* material id the hit reports (mesh.material_id, src/shape.cpp:85)     */
+    const int32_t *prim_light;     /* area_light_id or -1 (src/shape.h:8-11)                               */
+    const uint8_t *prim_flags;     /* TAKE_PRIM_* */
+    int64_t num_spheres;
+    const double *spheres;         /* 4*num_spheres: center xyz, radius (src/shape.h:20-23) */
+    int32_t num_materials, num_textures, num_lights, reserved;
+    const TakeMaterialDesc *materials;
+    const TakeTextureDesc *textures;
+    const TakeLightDesc *lights;
+} TakeSceneDesc;
+
+/* A ray exactly as the reference's `Ray` (src/ray.h:4-9): 8 doubles. */
+typedef struct TakeRay {
+    double origin[3];
+    double dir[3];
+    double tmin, tmax;
+} TakeRay;
+
+/* Closest hit: what scene_intersect() (src/scene.cpp:25-47) determines, plus the primitive id that
+ * `Intersection` lacks (src/intersection.h:4-12). */
+typedef struct TakeHit {
+    int32_t prim_id; /* -1 = miss */
+    int32_t pad;
+    double t;        /* bit-identical to the reference's Intersection::t */
+    double u, v;     /* Moller-Trumbore barycentrics (src/shape.cpp:63,69); 0 for spheres */
+} TakeHit;
+
+typedef struct TakeRenderOpts {
+    int32_t integrator;   /* TAKE_INTEGRATOR_* */
+    int32_t max_depth;    /* `-max_depth` (src/render.cpp:14-23); the loop runs max_depth+1 bounces */
+    int64_t spp_begin;    /* sample-index range [spp_begin, spp_end) of EVERY pixel: the unit of   */
+    int64_t spp_end;      /* multi-GPU sharding.  Results depend only on (seed, pixel, index).     */
+    uint64_t seed;
+    int32_t flags;        /* TAKE_RENDER_* */
+    int32_t reserved;
+} TakeRenderOpts;
+
+enum {
+    TAKE_RENDER_DEFAULT = 0,
+    TAKE_RENDER_NO_SORT = 1 /* disable the per-bounce material sort (A/B measurements) */
+};
+
+typedef struct TakeStats {
+    int64_t samples;        /* path samples started                               */
+    int64_t extend_rays;    /* closest-hit rays traced (primary + bounce)         */
+    int64_t shadow_rays;    /* any-hit rays traced                                */
+    int64_t shaded;         /* path vertices shaded                               */
+    int64_t box_tests;      /* filled only by the instrumented (TAKE_STATS) build */
+    int64_t tri_tests;
+    int64_t kernel_launches;
+    double ms_total;        /* device time of the whole call (CUDA events)        */
+    double ms_generate, ms_extend, ms_shade, ms_shadow, ms_sort, ms_other;
+} TakeStats;
+
+typedef struct TakeScene TakeScene; /* opaque */
+
+/* Number of usable CUDA devices. */
+int take_gpu_device_count(int *count);
+
+/* Build the acceleration structures on the host (replaces build_bvh / construct_bvh,
+ * src/scene.cpp:4-23, src/bvh.cpp:8-45) and upload the scene to `device` once. */
+int take_gpu_scene_create(int device, const TakeSceneDesc *desc, TakeScene **out);
+int take_gpu_scene_destroy(TakeScene *scene);
+
+/* Closest hit for `n` host rays (replaces scene_intersect, src/scene.cpp:25-47).  `flags` = TAKE_ISECT_*. */
+int take_gpu_intersect(TakeScene *scene, const TakeRay *rays, int64_t n, TakeHit *hits, int flags);
+/* Boolean occlusion for `n` host rays (replaces scene_occluded, src/scene.cpp:49-64). */
+int take_gpu_occluded(TakeScene *scene, const TakeRay *rays, int64_t n, uint8_t *occluded);
+/* Same, with rays / results already resident on the scene's device (no copies; async on the scene's stream
+ * followed by a stream synchronise). */
+int take_gpu_intersect_device(TakeScene *scene, const TakeRay *d_rays, int64_t n, TakeHit *d_hits, int flags);
+
+/* The render loop (replaces the tile lambda of src/render.cpp:59-82 and the integrators of
+ * src/integrator/path_tracing.h).  Adds, for every pixel, the radiance of samples
+ * [spp_begin, spp_end) to sum_rgb and its square to sumsq_rgb (may be NULL): height*width*3 doubles in image
+ * layout (row 0 = top, the layout src/render.cpp:78 writes).  Host buffers are overwritten, not accumulated. */
+int take_gpu_render(TakeScene *scene, const TakeRenderOpts *opts, double *sum_rgb, double *sumsq_rgb, TakeStats *stats);
+/* Same with DEVICE output buffers, which are accumulated into (zero them first). */
+int take_gpu_render_device(TakeScene *scene, const TakeRenderOpts *opts, double *d_sum_rgb, double *d_sumsq_rgb,
+                           TakeStats *stats);
+
+/* Radiance of `n` individual path samples (pixel x, image row y from the top, sample index s): 3 doubles each. */
+int take_gpu_radiance_samples(TakeScene *scene, const TakeRenderOpts *opts, int64_t n, const int32_t *px,
+                              const int32_t *py, const int64_t *s, double *rgb);
+
+/* Raw CUDA stream the scene's work is issued on (a cudaStream_t), for callers that time with events. */
+void *take_gpu_scene_stream(TakeScene *scene);
+
+const char *take_gpu_last_error(void);
+const char *take_gpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAKE_GPU_H */

@@ -1,0 +1,361 @@
+"""Procedural scenes for the BASELINE.json configs.
+
+Every generator produces the SAME scene twice:
+  * `SceneBuilder.flat()`    -> `FlatScene` (numpy arrays) for the GPU core's C-ABI, and
+  * `SceneBuilder.write(dir)` -> Mitsuba-style `scene.xml` + binary PLY meshes that the reference's own
+    front end parses (src/parse/parse_scene.cpp, src/parse/parse_ply.cpp).
+The two are bit-identical by construction (tests/test_scenes.py checks it against the reference
+parser): all XML scalars are float32 values because the reference reads them with std::stof
+(parse_scene.cpp:52-58,98-104); mesh data are float32 in world space under an identity toWorld, so
+xform_point (src/transform.cpp:79-87) is exact; normals go through xform_normal = normalize() in
+double (transform.cpp:95-100, src/vector.h:249-257), restated below in numpy with the same op order.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import sceneio as sio
+from .sceneio import FlatScene
+
+_BSDF_XML = {
+    sio.MAT_DIFFUSE: ("diffuse", "reflectance"), sio.MAT_MIRROR: ("mirror", "reflectance"),
+    sio.MAT_PLASTIC: ("plastic", "reflectance"), sio.MAT_PHONG: ("phong", "reflectance"),
+    sio.MAT_BLINN_PHONG: ("blinn", "reflectance"), sio.MAT_BLINN_MICROFACET: ("blinn_microfacet", "reflectance"),
+    sio.MAT_DISNEY_DIFFUSE: ("disneydiffuse", "baseColor"), sio.MAT_DISNEY_METAL: ("disneymetal", "baseColor"),
+    sio.MAT_DISNEY_GLASS: ("disneyglass", "baseColor"), sio.MAT_DISNEY_SHEEN: ("disneysheen", "baseColor"),
+    sio.MAT_DISNEY_BSDF: ("disneybsdf", "baseColor"),
+}
+
+
+def f32(x):
+    """Round to float32 and widen back: what std::stof / a float PLY property hands the reference."""
+    return np.asarray(x, dtype=np.float32).astype(np.float64)
+
+
+def _fmt(x) -> str:
+    return "%.9g" % float(np.float32(x))
+
+
+def _vec(v) -> str:
+    return ", ".join(_fmt(c) for c in v)
+
+
+def ref_normalize(v: np.ndarray) -> np.ndarray:
+    """normalize() of src/vector.h:249-257: l = sqrt((x*x + y*y) + z*z); l <= 0 -> 0; else v * (1/l)."""
+    v = np.asarray(v, dtype=np.float64)
+    l = np.sqrt((v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1]) + v[:, 2] * v[:, 2])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv = 1.0 / l
+        out = v * inv[:, None]
+    out[l <= 0] = 0.0
+    return out
+
+
+class SceneBuilder:
+    def __init__(self, width, height, lookfrom, lookat, up=(0, 1, 0), vfov=45.0, spp=16, background=(0, 0, 0)):
+        self.width, self.height, self.spp = int(width), int(height), int(spp)
+        self.lookfrom, self.lookat, self.up = f32(lookfrom), f32(lookat), f32(up)
+        self.vfov = float(f32(vfov))
+        self.background = f32(background)
+        self.materials = []   # (type, color|None, tex|None, params dict)
+        self.textures = []    # (name, rgbe uint8 [h,w,4])
+        self.meshes = []      # dicts
+
+    # -- materials ----------------------------------------------------------------------------
+    def material(self, mtype, color=(0.5, 0.5, 0.5), texture=None, uvscale=(1, 1), uvoffset=(0, 0), **params) -> int:
+        """params: eta (plastic), exponent (phong/blinn/blinn_microfacet), roughness/subsurface (disneydiffuse)."""
+        self.materials.append(dict(type=mtype, color=f32(color), texture=texture, uvscale=f32(uvscale),
+                                   uvoffset=f32(uvoffset), params={k: float(f32(v)) for k, v in params.items()}))
+        return len(self.materials) - 1
+
+    def texture_rgbe(self, rgbe: np.ndarray) -> int:
+        """Image texture given as Radiance RGBE bytes [h,w,4]; texel = mantissa * 2^(e-136) exactly
+        (stb_image's stbi__hdr_convert, which the reference's imread3 calls for .hdr: src/image.cpp:92-104)."""
+        rgbe = np.ascontiguousarray(rgbe, dtype=np.uint8)
+        assert rgbe.ndim == 3 and rgbe.shape[2] == 4
+        self.textures.append(rgbe)
+        return len(self.textures) - 1
+
+    # -- geometry -----------------------------------------------------------------------------
+    def mesh(self, positions, indices, normals, uvs=None, material=0, radiance=None):
+        """World-space triangle mesh.  `normals` are required (the reference would otherwise run
+        compute_normals, and emitters need them: src/shape.cpp:163-165)."""
+        self.meshes.append(dict(
+            positions=np.asarray(positions, dtype=np.float32).reshape(-1, 3),
+            indices=np.asarray(indices, dtype=np.int32).reshape(-1, 3),
+            normals=np.asarray(normals, dtype=np.float32).reshape(-1, 3),
+            uvs=None if uvs is None else np.asarray(uvs, dtype=np.float32).reshape(-1, 2),
+            material=int(material), radiance=None if radiance is None else f32(radiance)))
+        return len(self.meshes) - 1
+
+    def quad(self, p0, p1, p2, p3, material=0, radiance=None, normal=None):
+        """Quad p0..p3 (counter-clockwise seen from the side the normal points to), split (0,1,2),(0,2,3)."""
+        p = np.array([p0, p1, p2, p3], dtype=np.float64)
+        if normal is None:
+            normal = np.cross(p[1] - p[0], p[3] - p[0])
+            normal = normal / np.linalg.norm(normal)
+        n = np.tile(np.asarray(normal, dtype=np.float64), (4, 1))
+        uv = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], dtype=np.float64)
+        return self.mesh(p, [[0, 1, 2], [0, 2, 3]], n, uv, material, radiance)
+
+    def box(self, center, half, yaw_deg, material=0, bottom=False):
+        """Axis box rotated about +y, 5 faces (6 with bottom), outward normals."""
+        c, s = np.cos(np.radians(yaw_deg)), np.sin(np.radians(yaw_deg))
+        R = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+        hx, hy, hz = half
+        corners = lambda pts: [R @ np.array(p) + np.array(center) for p in pts]
+        faces = [
+            [(-hx, -hy, hz), (hx, -hy, hz), (hx, hy, hz), (-hx, hy, hz)],        # +z
+            [(hx, -hy, -hz), (-hx, -hy, -hz), (-hx, hy, -hz), (hx, hy, -hz)],    # -z
+            [(hx, -hy, hz), (hx, -hy, -hz), (hx, hy, -hz), (hx, hy, hz)],        # +x
+            [(-hx, -hy, -hz), (-hx, -hy, hz), (-hx, hy, hz), (-hx, hy, -hz)],    # -x
+            [(-hx, hy, hz), (hx, hy, hz), (hx, hy, -hz), (-hx, hy, -hz)],        # +y
+        ]
+        if bottom:
+            faces.append([(-hx, -hy, -hz), (hx, -hy, -hz), (hx, -hy, hz), (-hx, -hy, hz)])
+        for f in faces:
+            self.quad(*corners(f), material=material)
+
+    # -- outputs ------------------------------------------------------------------------------
+    def flat(self) -> FlatScene:
+        pos, nrm, uv, idx, pmat, plight, pflags, lights = [], [], [], [], [], [], [], []
+        base = 0
+        n_prims = 0
+        for m in self.meshes:
+            nv, nf = len(m["positions"]), len(m["indices"])
+            pos.append(m["positions"].astype(np.float64))
+            nrm.append(ref_normalize(m["normals"].astype(np.float64)))
+            uv.append(np.zeros((nv, 2)) if m["uvs"] is None else m["uvs"].astype(np.float64))
+            idx.append(m["indices"] + base)
+            pmat.append(np.full(nf, m["material"], np.int32))
+            pflags.append(np.full(nf, sio.PRIM_HAS_NORMALS | (0 if m["uvs"] is None else sio.PRIM_HAS_UVS), np.uint8))
+            if m["radiance"] is not None:
+                # one DiffuseAreaLight per face, in shape order (parse_scene.cpp:940-943)
+                first = len(lights)
+                for f in range(nf):
+                    lights.append((sio.LIGHT_AREA, n_prims + f, tuple(m["radiance"]), (0.0, 0.0, 0.0)))
+                plight.append(np.arange(first, first + nf, dtype=np.int32))
+            else:
+                plight.append(np.full(nf, -1, np.int32))
+            base += nv
+            n_prims += nf
+        mats = np.zeros(len(self.materials), sio.MAT_DTYPE)
+        for i, m in enumerate(self.materials):
+            mats[i]["type"] = m["type"]
+            mats[i]["tex_id"] = -1 if m["texture"] is None else m["texture"]
+            mats[i]["color"] = 0.0 if m["texture"] is not None else m["color"]
+            mats[i]["uv"] = [1, 1, 0, 0] if m["texture"] is None else [*m["uvscale"], *m["uvoffset"]]
+            p = m["params"]
+            t = m["type"]
+            if t in (sio.MAT_MIRROR,):
+                mats[i]["p"][0] = 1.0                      # Mirror::eta default (material.h:11-14); parser never sets it
+            elif t == sio.MAT_PLASTIC:
+                mats[i]["p"][0] = p.get("eta", 1.5)
+            elif t in (sio.MAT_PHONG, sio.MAT_BLINN_PHONG, sio.MAT_BLINN_MICROFACET):
+                mats[i]["p"][0] = p.get("exponent", 5.0)
+            elif t == sio.MAT_DISNEY_DIFFUSE:
+                mats[i]["p"][0] = p.get("roughness", 0.5)
+                mats[i]["p"][1] = p.get("subsurface", 0.0)
+        textures = []
+        for rgbe in self.textures:
+            scale = np.ldexp(np.float32(1.0), rgbe[..., 3].astype(np.int32) - 136).astype(np.float32)
+            rgb = (rgbe[..., :3].astype(np.float32) * scale[..., None]).astype(np.float64)
+            rgb[rgbe[..., 3] == 0] = 0.0
+            textures.append(rgb)
+        cat = lambda xs, shape, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(shape, dt)
+        return FlatScene(
+            self.width, self.height, self.lookfrom, self.lookat, self.up, self.vfov, self.background,
+            cat(pos, (0, 3), np.float64), cat(nrm, (0, 3), np.float64), cat(uv, (0, 2), np.float64),
+            cat(idx, (0, 3), np.int32), cat(pmat, (0,), np.int32), cat(plight, (0,), np.int32),
+            cat(pflags, (0,), np.uint8), np.zeros((0, 4)), mats,
+            np.array(lights, dtype=sio.LIGHT_DTYPE) if lights else np.zeros(0, sio.LIGHT_DTYPE), textures,
+            self.spp)._canon()
+
+    def write(self, directory) -> str:
+        """Write scene.xml + meshes + textures under `directory`; returns the XML path."""
+        os.makedirs(directory, exist_ok=True)
+        x = ['<?xml version="1.0" encoding="utf-8"?>', '<scene version="0.5.0">']
+        x.append('<sensor type="perspective">')
+        x.append(f'  <float name="fov" value="{_fmt(self.vfov)}"/><string name="fovAxis" value="y"/>')
+        x.append(f'  <transform name="toWorld"><lookat origin="{_vec(self.lookfrom)}" target="{_vec(self.lookat)}" '
+                 f'up="{_vec(self.up)}"/></transform>')
+        x.append(f'  <sampler type="independent"><integer name="sampleCount" value="{self.spp}"/></sampler>')
+        x.append(f'  <film type="hdrfilm"><integer name="width" value="{self.width}"/>'
+                 f'<integer name="height" value="{self.height}"/></film>')
+        x.append('</sensor>')
+        x.append(f'<background><rgb name="radiance" value="{_vec(self.background)}"/></background>')
+        for i, rgbe in enumerate(self.textures):
+            write_hdr(os.path.join(directory, f"tex{i}.hdr"), rgbe)
+        for i, m in enumerate(self.materials):
+            tname, cname = _BSDF_XML[m["type"]]
+            x.append(f'<bsdf type="{tname}" id="m{i}">')
+            if m["texture"] is None:
+                x.append(f'  <rgb name="{cname}" value="{_vec(m["color"])}"/>')
+            else:
+                x.append(f'  <texture type="bitmap" name="{cname}"><string name="filename" value="tex{m["texture"]}.hdr"/>'
+                         f'<float name="uscale" value="{_fmt(m["uvscale"][0])}"/><float name="vscale" value="{_fmt(m["uvscale"][1])}"/>'
+                         f'<float name="uoffset" value="{_fmt(m["uvoffset"][0])}"/><float name="voffset" value="{_fmt(m["uvoffset"][1])}"/></texture>')
+            for k, v in m["params"].items():
+                x.append(f'  <float name="{k}" value="{_fmt(v)}"/>')
+            x.append('</bsdf>')
+        for i, m in enumerate(self.meshes):
+            write_ply(os.path.join(directory, f"mesh{i}.ply"), m["positions"], m["indices"], m["normals"], m["uvs"])
+            x.append(f'<shape type="ply"><string name="filename" value="mesh{i}.ply"/><ref id="m{m["material"]}"/>')
+            if m["radiance"] is not None:
+                x.append(f'  <emitter type="area"><rgb name="radiance" value="{_vec(m["radiance"])}"/></emitter>')
+            x.append('</shape>')
+        x.append('</scene>')
+        path = os.path.join(directory, "scene.xml")
+        with open(path, "w") as f:
+            f.write("\n".join(x) + "\n")
+        return path
+
+
+def write_ply(path, positions, indices, normals, uvs=None):
+    """binary_little_endian PLY in the form src/parse/parse_ply.cpp:16-31,83-120 reads."""
+    nv, nf = len(positions), len(indices)
+    props = ["x", "y", "z", "nx", "ny", "nz"] + (["u", "v"] if uvs is not None else [])
+    hdr = ["ply", "format binary_little_endian 1.0", f"element vertex {nv}"]
+    hdr += [f"property float {p}" for p in props]
+    hdr += [f"element face {nf}", "property list uchar int vertex_indices", "end_header"]
+    cols = [positions.astype("<f4"), normals.astype("<f4")] + ([uvs.astype("<f4")] if uvs is not None else [])
+    verts = np.ascontiguousarray(np.concatenate(cols, axis=1))
+    faces = np.zeros(nf, dtype=np.dtype([("n", "u1"), ("i", "<i4", 3)]))
+    faces["n"] = 3
+    faces["i"] = indices
+    with open(path, "wb") as f:
+        f.write(("\n".join(hdr) + "\n").encode("ascii"))
+        verts.tofile(f)
+        faces.tofile(f)
+
+
+def write_hdr(path, rgbe):
+    """Flat (non-RLE) Radiance .hdr; stb_image falls back to flat decoding when a scanline does not
+    start with the RLE marker, so give every row's first pixel a mantissa that cannot be mistaken for it."""
+    h, w, _ = rgbe.shape
+    data = rgbe.copy()
+    if 8 <= w < 32768:
+        clash = (data[:, 0, 0] == 2) & (data[:, 0, 1] == 2) & (data[:, 0, 2] < 128)
+        assert not clash.any(), "first texel of a row looks like an RLE marker"
+    with open(path, "wb") as f:
+        f.write(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n" + f"-Y {h} +X {w}\n".encode("ascii"))
+        data.tofile(f)
+
+
+# =============================================================================================
+# BASELINE.json configs
+# =============================================================================================
+def cornell_box(width=512, height=512, spp=64, materials="diffuse") -> SceneBuilder:
+    """Config 1: Cornell box, 32 triangles (5 walls, ceiling light, two rotated boxes), 2 area lights
+    (each light triangle is its own light, parse_scene.cpp:940-943).  SURVEY.md Appendix D geometry."""
+    b = SceneBuilder(width, height, (0, 1, 3.8), (0, 1, 0), (0, 1, 0), 39.3, spp, (0, 0, 0))
+    if materials == "diffuse":
+        white = b.material(sio.MAT_DIFFUSE, (0.73, 0.73, 0.73))
+        red = b.material(sio.MAT_DIFFUSE, (0.65, 0.05, 0.05))
+        green = b.material(sio.MAT_DIFFUSE, (0.12, 0.45, 0.15))
+        tall = short = white
+    else:  # "mixed": one of every implemented BSDF, for shading parity
+        white = b.material(sio.MAT_DIFFUSE, (0.73, 0.73, 0.73))
+        red = b.material(sio.MAT_PHONG, (0.65, 0.05, 0.05), exponent=20)
+        green = b.material(sio.MAT_BLINN_PHONG, (0.12, 0.45, 0.15), exponent=30)
+        tall = b.material(sio.MAT_MIRROR, (0.9, 0.9, 0.9))
+        short = b.material(sio.MAT_PLASTIC, (0.2, 0.3, 0.7), eta=1.5)
+    black = b.material(sio.MAT_DIFFUSE, (0, 0, 0))
+    if materials != "diffuse":
+        floor = b.material(sio.MAT_BLINN_MICROFACET, (0.6, 0.6, 0.5), exponent=50)
+        back = b.material(sio.MAT_DISNEY_DIFFUSE, (0.7, 0.6, 0.5), roughness=0.7, subsurface=0.4)
+    else:
+        floor = back = white
+    b.quad((-1, 0, 1), (1, 0, 1), (1, 0, -1), (-1, 0, -1), floor)          # floor  y=0, normal +y
+    b.quad((-1, 2, -1), (1, 2, -1), (1, 2, 1), (-1, 2, 1), white)          # ceiling y=2, normal -y
+    b.quad((-1, 0, -1), (1, 0, -1), (1, 2, -1), (-1, 2, -1), back)         # back   z=-1, normal +z
+    b.quad((-1, 0, 1), (-1, 0, -1), (-1, 2, -1), (-1, 2, 1), red)          # left   x=-1, normal +x
+    b.quad((1, 0, -1), (1, 0, 1), (1, 2, 1), (1, 2, -1), green)            # right  x=+1, normal -x
+    b.quad((-0.25, 1.98, -0.25), (0.25, 1.98, -0.25), (0.25, 1.98, 0.25), (-0.25, 1.98, 0.25), black,
+           radiance=(17, 12, 4))                                           # light, normal -y
+    b.box((-0.35, 0.6, -0.3), (0.3, 0.6, 0.3), 18, tall)
+    b.box((0.35, 0.3, 0.35), (0.3, 0.3, 0.3), -17, short)
+    return b
+
+
+def _grid_mesh(n, extent, height_fn):
+    """(n+1)^2 vertices on [-extent,extent]^2 in xz, y = height_fn(x,z); 2 n^2 triangles; smooth normals
+    from central differences; uv = grid parameter."""
+    g = np.linspace(-extent, extent, n + 1)
+    X, Z = np.meshgrid(g, g, indexing="xy")          # row = z index, col = x index
+    Y = height_fn(X, Z)
+    step = 2.0 * extent / n
+    dYdx = np.gradient(Y, step, axis=1)
+    dYdz = np.gradient(Y, step, axis=0)
+    N = np.stack([-dYdx, np.ones_like(Y), -dYdz], axis=-1)
+    N /= np.linalg.norm(N, axis=-1, keepdims=True)
+    P = np.stack([X, Y, Z], axis=-1).reshape(-1, 3)
+    UV = np.stack([(X + extent) / (2 * extent), (Z + extent) / (2 * extent)], axis=-1).reshape(-1, 2)
+    i, j = np.meshgrid(np.arange(n), np.arange(n), indexing="xy")   # i: x cell, j: z cell
+    v00 = (j * (n + 1) + i).ravel()
+    v10, v01, v11 = v00 + 1, v00 + (n + 1), v00 + (n + 2)
+    # counter-clockwise seen from +y: (x,z) -> (x,z+1) -> (x+1,z+1)
+    tris = np.empty((2 * n * n, 3), np.int32)
+    tris[0::2] = np.stack([v00, v01, v11], axis=1)
+    tris[1::2] = np.stack([v00, v11, v10], axis=1)
+    return P, tris, N.reshape(-1, 3), UV
+
+
+def heightfield(n=708, width=1920, height=1080, spp=256, seed=1234, mtype=sio.MAT_BLINN_MICROFACET) -> SceneBuilder:
+    """Config 2: displaced grid, n=708 -> 1 002 528 triangles on [-100,100]^2 (+ a 2-triangle quad light),
+    blinn_microfacet (the reference's only microfacet BRDF: SURVEY.md section 0 gap 1), one-sample MIS."""
+    rng = np.random.default_rng(seed)
+    noise = rng.normal(0.0, 1.0, size=(n + 1, n + 1))
+    P, T, N, UV = _grid_mesh(n, 100.0, lambda X, Z: 15.0 * np.sin(0.06 * X) * np.cos(0.05 * Z) + noise)
+    b = SceneBuilder(width, height, (0, 160, 240), (0, 0, 0), (0, 1, 0), 45.0, spp, (0.05, 0.05, 0.08))
+    if mtype == sio.MAT_BLINN_MICROFACET:
+        m = b.material(mtype, (0.7, 0.6, 0.4), exponent=100)
+    else:
+        m = b.material(mtype, (0.7, 0.6, 0.4))
+    black = b.material(sio.MAT_DIFFUSE, (0, 0, 0))
+    b.mesh(P, T, N, UV, m)
+    b.quad((-50, 200, -50), (50, 200, -50), (50, 200, 50), (-50, 200, 50), black, radiance=(20, 20, 20))  # normal -y
+    return b
+
+
+def multi_light(width=1920, height=1080, spp=1024, n_side=20, seed=3) -> SceneBuilder:
+    """Config 4: Cornell-style room scaled x50 with n_side^2 small emissive triangles under the ceiling
+    (each its own light), plus diffuse / glossy blockers; multi-sample MIS."""
+    S = 50.0
+    rng = np.random.default_rng(seed)
+    b = SceneBuilder(width, height, (0, S, 3.8 * S), (0, S, 0), (0, 1, 0), 39.3, spp, (0, 0, 0))
+    white = b.material(sio.MAT_DIFFUSE, (0.73, 0.73, 0.73))
+    red = b.material(sio.MAT_DIFFUSE, (0.65, 0.05, 0.05))
+    green = b.material(sio.MAT_DIFFUSE, (0.12, 0.45, 0.15))
+    black = b.material(sio.MAT_DIFFUSE, (0, 0, 0))
+    glossy = b.material(sio.MAT_BLINN_MICROFACET, (0.8, 0.7, 0.5), exponent=60)
+    phong = b.material(sio.MAT_PHONG, (0.5, 0.5, 0.6), exponent=40)
+    q = lambda *p, **k: b.quad(*[tuple(S * np.array(v)) for v in p], **k)
+    q((-1, 0, 1), (1, 0, 1), (1, 0, -1), (-1, 0, -1), material=white)
+    q((-1, 2, -1), (1, 2, -1), (1, 2, 1), (-1, 2, 1), material=white)
+    q((-1, 0, -1), (1, 0, -1), (1, 2, -1), (-1, 2, -1), material=white)
+    q((-1, 0, 1), (-1, 0, -1), (-1, 2, -1), (-1, 2, 1), material=red)
+    q((1, 0, -1), (1, 0, 1), (1, 2, 1), (1, 2, -1), material=green)
+    # emissive triangles: one mesh per light so that each can carry its own radiance
+    cell = 1.6 * S / n_side
+    for j in range(n_side):
+        for i in range(n_side):
+            cx = -0.8 * S + (i + 0.5) * cell + rng.uniform(-0.15, 0.15) * cell
+            cz = -0.8 * S + (j + 0.5) * cell + rng.uniform(-0.15, 0.15) * cell
+            y = 1.96 * S - rng.uniform(0, 0.02) * S
+            r = 0.3 * cell
+            a = rng.uniform(0, 2 * np.pi)
+            pts = [(cx + r * np.cos(a + k * 2 * np.pi / 3), y, cz + r * np.sin(a + k * 2 * np.pi / 3)) for k in range(3)]
+            rad = rng.uniform(5, 50)
+            # wind so that the geometric normal is -y (facing the room); shading normals -y
+            b.mesh(pts, [[0, 1, 2]], [(0, -1, 0)] * 3, None, black, radiance=(rad, rad, rad))
+    b.box((-0.35 * S, 0.6 * S, -0.3 * S), (0.3 * S, 0.6 * S, 0.3 * S), 18, glossy)
+    b.box((0.35 * S, 0.3 * S, 0.35 * S), (0.3 * S, 0.3 * S, 0.3 * S), -17, phong)
+    b.box((0.0, 1.2 * S, -0.6 * S), (0.5 * S, 0.02 * S, 0.2 * S), 5, white, bottom=True)
+    return b
+
+
+def build(name: str, **kw) -> SceneBuilder:
+    return {"cornell": cornell_box, "heightfield": heightfield, "multi_light": multi_light}[name](**kw)
