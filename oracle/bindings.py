@@ -146,3 +146,125 @@ def run_stock_cli(xml_path, max_depth=5, threads=None, timeout=3600):
     g = lambda pat: float(re.search(pat, out).group(1))
     return (g(r"Finish building rendering\. Took ([0-9.eE+-]+) seconds"), g(r"Finish building BVH\. Took ([0-9.eE+-]+) seconds"),
             g(r"Scene parsing done\. Took ([0-9.eE+-]+) seconds"), threads)
+
+
+class OracleScene:
+    """A FlatScene loaded into the CPU restatement (oracle/take_oracle.cpp)."""
+
+    def __init__(self, lib, flat):
+        self.lib, self.flat = lib, flat
+        self._desc = flat.to_desc()
+        self.h = lib.oracle_scene_create(C.byref(self._desc))
+        self.width, self.height = flat.width, flat.height
+        self.num_prims = flat.num_prims
+
+    def close(self):
+        if self.h:
+            self.lib.oracle_scene_free(self.h)
+            self.h = None
+
+    def bvh(self):
+        n = self.lib.oracle_bvh_size(self.h)
+        box = np.empty((n, 6), np.float64)
+        links = np.empty((n, 3), np.int32)
+        self.lib.oracle_bvh_dump(self.h, _ptr(box, np.float64), _ptr(links, np.int32))
+        return box, links, self.lib.oracle_bvh_root(self.h)
+
+    def dfs_rank(self):
+        rank = np.full(self.num_prims, -1, np.int32)
+        self.lib.oracle_dfs_rank(self.h, _ptr(rank, np.int32))
+        return rank
+
+    def intersect(self, rays, records=False, counters=False, threads=8):
+        rays = _rays(rays)
+        n = len(rays)
+        prim = np.empty(n, np.int32)
+        t = np.empty(n, np.float64)
+        uv = np.empty((n, 2), np.float64)
+        rec = np.empty((n, 16), np.float64) if records else None
+        cnt = np.zeros(2, np.int64)
+        self.lib.oracle_intersect(self.h, _ptr(rays, np.float64), n, _ptr(prim, np.int32), _ptr(t, np.float64),
+                                  _ptr(uv, np.float64), _ptr(rec, np.float64), _ptr(cnt, np.int64), threads)
+        out = (prim, t, uv) + ((rec,) if records else ()) + ((cnt,) if counters else ())
+        return out
+
+    def occluded(self, rays, threads=8):
+        rays = _rays(rays)
+        occ = np.empty(len(rays), np.uint8)
+        self.lib.oracle_occluded(self.h, _ptr(rays, np.float64), len(rays), _ptr(occ, np.uint8), threads)
+        return occ
+
+    def render(self, integrator="mis", max_depth=5, spp_begin=0, spp_end=1, seed=0, threads=8, sumsq=True,
+               stats=False):
+        s = np.zeros((self.height, self.width, 3), np.float64)
+        s2 = np.zeros_like(s) if sumsq else None
+        st = np.zeros(6, np.int64)
+        rc = self.lib.oracle_render(self.h, INTEGRATORS[integrator], max_depth, spp_begin, spp_end, seed, threads,
+                                    _ptr(s, np.float64), _ptr(s2, np.float64), _ptr(st, np.int64))
+        assert rc == 0
+        return (s, s2, st) if stats else (s, s2)
+
+    def radiance_samples(self, px, py, s, integrator="mis", max_depth=5, seed=0, threads=8):
+        px = np.ascontiguousarray(px, np.int32); py = np.ascontiguousarray(py, np.int32)
+        s = np.ascontiguousarray(s, np.int64)
+        out = np.empty((len(px), 3), np.float64)
+        rc = self.lib.oracle_radiance_samples(self.h, INTEGRATORS[integrator], max_depth, seed, len(px),
+                                              _ptr(px, np.int32), _ptr(py, np.int32), _ptr(s, np.int64),
+                                              _ptr(out, np.float64), threads)
+        assert rc == 0
+        return out
+
+    def primary_rays(self, px, py, s=None, seed=0, jitter=True):
+        px = np.ascontiguousarray(px, np.int32); py = np.ascontiguousarray(py, np.int32)
+        s = np.zeros(len(px), np.int64) if s is None else np.ascontiguousarray(s, np.int64)
+        rays = np.empty((len(px), 8), np.float64)
+        self.lib.oracle_primary_rays(self.h, seed, len(px), _ptr(px, np.int32), _ptr(py, np.int32),
+                                     _ptr(s, np.int64), int(jitter), _ptr(rays, np.float64))
+        return rays
+
+
+class OracleLib:
+    def __init__(self, path=ORACLE_SO):
+        L = self.lib = C.CDLL(path)
+        vp, i64, u64, i32, u32 = C.c_void_p, C.c_int64, C.c_uint64, C.c_int, C.c_uint32
+        L.oracle_scene_create.restype = vp
+        L.oracle_scene_create.argtypes = [vp]
+        L.oracle_scene_free.argtypes = [vp]
+        L.oracle_bvh_size.restype = i64
+        L.oracle_bvh_size.argtypes = [vp]
+        L.oracle_bvh_root.argtypes = [vp]
+        L.oracle_bvh_dump.argtypes = [vp, vp, vp]
+        L.oracle_dfs_rank.argtypes = [vp, vp]
+        L.oracle_intersect.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, i32]
+        L.oracle_occluded.argtypes = [vp, vp, i64, vp, i32]
+        L.oracle_render.argtypes = [vp, i32, i32, i64, i64, u64, i32, vp, vp, vp]
+        L.oracle_radiance_samples.argtypes = [vp, i32, i32, u64, i64, vp, vp, vp, vp, i32]
+        L.oracle_primary_rays.argtypes = [vp, u64, i64, vp, vp, vp, i32, vp]
+        L.oracle_stream_real.restype = C.c_double
+        L.oracle_stream_real.argtypes = [u64, u32, u64, u32]
+        L.oracle_philox.argtypes = [vp, vp, vp]
+
+    def load(self, flat) -> OracleScene:
+        return OracleScene(self.lib, flat)
+
+    def philox(self, ctr, key):
+        ctr = np.ascontiguousarray(ctr, np.uint32); key = np.ascontiguousarray(key, np.uint32)
+        out = np.empty(4, np.uint32)
+        self.lib.oracle_philox(_ptr(ctr, np.uint32), _ptr(key, np.uint32), _ptr(out, np.uint32))
+        return out
+
+    def stream_real(self, seed, pixel, sample, k) -> float:
+        return self.lib.oracle_stream_real(seed, pixel, sample, k)
+
+
+def secondary_rays(rays, t, prim, seed=0):
+    """Random secondary rays leaving the hit points of `rays` (for hits only): uniform directions on the sphere,
+    tmin = 1e-7, tmax = inf -- the shape of ray the integrators spawn (path_tracing.h:79)."""
+    rng = np.random.default_rng(seed)
+    hit = prim >= 0
+    o = rays[hit, 0:3] + rays[hit, 3:6] * t[hit, None]
+    d = rng.normal(size=o.shape)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    out = np.empty((len(o), 8))
+    out[:, 0:3], out[:, 3:6], out[:, 6], out[:, 7] = o, d, 1e-7, np.inf
+    return out
