@@ -191,6 +191,10 @@ int take_gpu_radiance_samples(TakeScene *scene, const TakeRenderOpts *opts, int6
 /* Raw CUDA stream the scene's work is issued on (a cudaStream_t), for callers that time with events. */
 void *take_gpu_scene_stream(TakeScene *scene);
 
+/* Diagnostics: out[0..5] = reference-order tree build ms, fast tree build ms, fast tree depth, SAH cost,
+ * number of fast-tree nodes, SM count of the device. */
+int take_gpu_scene_info(TakeScene *scene, double *out);
+
 const char *take_gpu_last_error(void);
 const char *take_gpu_version(void);
 

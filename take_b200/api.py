@@ -1,0 +1,206 @@
+"""Host-side mirror of the reference's render interface, over the C-ABI library (include/take_gpu.h).
+
+Reference call stack being replaced:
+    main (src/main.cpp:8) -> render(params) (src/render.cpp:9) -> parse_scene -> build_bvh -> tile loop
+    -> path_tracing (src/integrator/path_tracing.h) -> scene_intersect / scene_occluded (src/scene.cpp:25-64)
+
+`GpuScene` = the reference's `Scene` after `build_bvh` (acceleration structures built, data resident on one
+B200); its methods carry the reference's names: `intersect` = scene_intersect, `occluded` = scene_occluded,
+`render` = the body of render() after parsing.  There is no CPU path: if libtake_gpu.so is missing or no CUDA
+device is usable, everything here raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .sceneio import FlatScene, TakeSceneDesc
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtake_gpu.so")
+
+INTEGRATORS = {"mis": 0, "raw": 1, "one_sample_mis": 2}
+ISECT_FAST, ISECT_EXACT = 0, 1
+RENDER_NO_SORT = 1
+
+EXPORTS = [
+    "take_gpu_device_count", "take_gpu_scene_create", "take_gpu_scene_destroy", "take_gpu_intersect",
+    "take_gpu_occluded", "take_gpu_intersect_device", "take_gpu_render", "take_gpu_render_device",
+    "take_gpu_radiance_samples", "take_gpu_scene_stream", "take_gpu_scene_info", "take_gpu_last_error",
+    "take_gpu_version",
+]
+
+RAY_DTYPE = np.dtype([("origin", "<f8", 3), ("dir", "<f8", 3), ("tmin", "<f8"), ("tmax", "<f8")])
+HIT_DTYPE = np.dtype([("prim_id", "<i4"), ("pad", "<i4"), ("t", "<f8"), ("u", "<f8"), ("v", "<f8")])
+assert RAY_DTYPE.itemsize == 64 and HIT_DTYPE.itemsize == 32
+
+
+class TakeRenderOpts(C.Structure):
+    _fields_ = [("integrator", C.c_int32), ("max_depth", C.c_int32), ("spp_begin", C.c_int64), ("spp_end", C.c_int64),
+                ("seed", C.c_uint64), ("flags", C.c_int32), ("reserved", C.c_int32)]
+
+
+class TakeStats(C.Structure):
+    _fields_ = [("samples", C.c_int64), ("extend_rays", C.c_int64), ("shadow_rays", C.c_int64), ("shaded", C.c_int64),
+                ("box_tests", C.c_int64), ("tri_tests", C.c_int64), ("kernel_launches", C.c_int64),
+                ("ms_total", C.c_double), ("ms_generate", C.c_double), ("ms_extend", C.c_double),
+                ("ms_shade", C.c_double), ("ms_shadow", C.c_double), ("ms_sort", C.c_double), ("ms_other", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class TakeGpuError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path: str = LIB_PATH):
+    """dlopen the C-ABI library.  Raises if it has not been built (python __graft_entry__.py / make -C take_b200/csrc)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise TakeGpuError(f"{path} not found: build the CUDA extension first (there is no CPU fallback)")
+    L = C.CDLL(path)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+    L.take_gpu_last_error.restype = C.c_char_p
+    L.take_gpu_version.restype = C.c_char_p
+    L.take_gpu_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.take_gpu_scene_create.argtypes = [i32, C.POINTER(TakeSceneDesc), C.POINTER(vp)]
+    L.take_gpu_scene_destroy.argtypes = [vp]
+    L.take_gpu_intersect.argtypes = [vp, vp, i64, vp, i32]
+    L.take_gpu_intersect_device.argtypes = [vp, vp, i64, vp, i32]
+    L.take_gpu_occluded.argtypes = [vp, vp, i64, vp]
+    L.take_gpu_render.argtypes = [vp, C.POINTER(TakeRenderOpts), vp, vp, C.POINTER(TakeStats)]
+    L.take_gpu_render_device.argtypes = [vp, C.POINTER(TakeRenderOpts), vp, vp, C.POINTER(TakeStats)]
+    L.take_gpu_radiance_samples.argtypes = [vp, C.POINTER(TakeRenderOpts), i64, vp, vp, vp, vp]
+    L.take_gpu_scene_stream.restype = vp
+    L.take_gpu_scene_stream.argtypes = [vp]
+    L.take_gpu_scene_info.argtypes = [vp, vp]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise TakeGpuError(f"take_gpu error {rc}: {load_library().take_gpu_last_error().decode()}")
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    _check(load_library().take_gpu_device_count(C.byref(n)))
+    return n.value
+
+
+def make_rays(origin, direction, tmin=1e-7, tmax=np.inf) -> np.ndarray:
+    """Pack rays as the reference's `Ray` (src/ray.h:4-9): n x 8 doubles."""
+    origin = np.asarray(origin, np.float64); direction = np.asarray(direction, np.float64)
+    n = max(origin.reshape(-1, 3).shape[0], direction.reshape(-1, 3).shape[0])
+    rays = np.empty((n, 8), np.float64)
+    rays[:, 0:3], rays[:, 3:6], rays[:, 6], rays[:, 7] = origin, direction, tmin, tmax
+    return rays
+
+
+class GpuScene:
+    def __init__(self, flat: FlatScene, device: int = 0):
+        self.lib = load_library()
+        self.flat = flat
+        self.width, self.height = flat.width, flat.height
+        self._desc = flat.to_desc()
+        h = C.c_void_p()
+        _check(self.lib.take_gpu_scene_create(device, C.byref(self._desc), C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.take_gpu_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> dict:
+        out = (C.c_double * 6)()
+        _check(self.lib.take_gpu_scene_info(self.h, out))
+        keys = ["build_ms_reference_tree", "build_ms_fast_tree", "fast_tree_depth", "sah_cost", "fast_nodes", "sm_count"]
+        return dict(zip(keys, out))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.take_gpu_scene_stream(self.h) or 0)
+
+    # scene_intersect (src/scene.cpp:25-47)
+    def intersect(self, rays, exact: bool = False):
+        rays = np.ascontiguousarray(rays, np.float64).reshape(-1, 8)
+        hits = np.empty(len(rays), HIT_DTYPE)
+        _check(self.lib.take_gpu_intersect(self.h, rays.ctypes.data, len(rays), hits.ctypes.data,
+                                           ISECT_EXACT if exact else ISECT_FAST))
+        return hits["prim_id"].copy(), hits["t"].copy(), np.stack([hits["u"], hits["v"]], axis=1)
+
+    # scene_occluded (src/scene.cpp:49-64)
+    def occluded(self, rays):
+        rays = np.ascontiguousarray(rays, np.float64).reshape(-1, 8)
+        occ = np.empty(len(rays), np.uint8)
+        _check(self.lib.take_gpu_occluded(self.h, rays.ctypes.data, len(rays), occ.ctypes.data))
+        return occ
+
+    def _opts(self, integrator, max_depth, spp_begin, spp_end, seed, flags=0):
+        return TakeRenderOpts(INTEGRATORS[integrator], max_depth, spp_begin, spp_end, seed, flags, 0)
+
+    # the tile loop of render() (src/render.cpp:59-82): sums of samples [spp_begin, spp_end) per pixel
+    def render_sums(self, integrator="mis", max_depth=5, spp_begin=0, spp_end=1, seed=0, sumsq=True, flags=0):
+        s = np.empty((self.height, self.width, 3), np.float64)
+        s2 = np.empty_like(s) if sumsq else None
+        st = TakeStats()
+        o = self._opts(integrator, max_depth, spp_begin, spp_end, seed, flags)
+        _check(self.lib.take_gpu_render(self.h, C.byref(o), s.ctypes.data, s2.ctypes.data if sumsq else None, C.byref(st)))
+        return s, s2, st.as_dict()
+
+    def render_sums_device(self, d_sum_ptr: int, d_sumsq_ptr: int, integrator="mis", max_depth=5, spp_begin=0, spp_end=1,
+                           seed=0, flags=0):
+        """Accumulate into caller-owned DEVICE buffers (e.g. torch tensors' data_ptr()) -- no host copies."""
+        st = TakeStats()
+        o = self._opts(integrator, max_depth, spp_begin, spp_end, seed, flags)
+        _check(self.lib.take_gpu_render_device(self.h, C.byref(o), d_sum_ptr, d_sumsq_ptr or None, C.byref(st)))
+        return st.as_dict()
+
+    def radiance_samples(self, px, py, s, integrator="mis", max_depth=5, seed=0):
+        px = np.ascontiguousarray(px, np.int32); py = np.ascontiguousarray(py, np.int32); s = np.ascontiguousarray(s, np.int64)
+        out = np.empty((len(px), 3), np.float64)
+        o = self._opts(integrator, max_depth, 0, 0, seed)
+        _check(self.lib.take_gpu_radiance_samples(self.h, C.byref(o), len(px), px.ctypes.data, py.ctypes.data,
+                                                  s.ctypes.data, out.ctypes.data))
+        return out
+
+
+def render(params, device: int = 0, integrator: str = "mis", seed: int = 0) -> np.ndarray:
+    """Mirror of `Image3 render(const std::vector<std::string>& params)` (src/render.h:5, src/render.cpp:9-87):
+    params[0] is the scene (a TAKESCN1 file written by the scene flattener), `-max_depth N` as in render.cpp:14-23
+    (default 50).  Returns the H x W x 3 float64 image, row 0 = top (what render.cpp:78 stores)."""
+    if len(params) < 1:
+        return np.zeros((0, 0, 3))
+    max_depth, filename = 50, None
+    i = 0
+    while i < len(params):
+        if params[i] == "-max_depth":
+            i += 1
+            max_depth = int(params[i])
+        elif filename is None:
+            filename = params[i]
+        i += 1
+    flat = FlatScene.load(filename)
+    scene = GpuScene(flat, device)
+    try:
+        s, _, _ = scene.render_sums(integrator, max_depth, 0, flat.spp, seed, sumsq=False)
+    finally:
+        scene.close()
+    return s / float(flat.spp)

@@ -1,0 +1,306 @@
+// Hit reconstruction, textures, BSDFs and light sampling on the device, in FP64 with the reference's operation
+// order (see device_common.cuh for the arithmetic contract).  Each function cites the reference lines it replaces.
+#pragma once
+#include "device_common.cuh"
+
+namespace take {
+
+struct Isect {  // src/intersection.h:4-12
+    D3 pos, gn, sn;
+    D2 uv;
+    int32_t material, light;
+};
+
+__device__ __forceinline__ D3 ld3(const double *p) { return mk3(p[0], p[1], p[2]); }
+
+__device__ __forceinline__ D2 sphere_uv(D3 p) {  // src/shape.cpp:3-11
+    double theta = acos(-p.y);
+    double phi = atan2(-p.z, p.x) + TAKE_PI;
+    D2 r; r.x = phi / (2 * TAKE_PI); r.y = -theta / TAKE_PI;
+    return r;
+}
+
+// src/shape.cpp:30-41 (sphere) and :80-108 (triangle)
+__device__ __forceinline__ void fill_isect(const DevScene &sc, D3 o, D3 d, int prim, double t, double u, double v, Isect &out) {
+    out.pos = add(o, mul(d, t));
+    out.material = sc.prim_material[prim];
+    out.light = sc.prim_light[prim];
+    const uint8_t flags = sc.prim_flags[prim];
+    const int32_t *id = sc.indices + 3 * (int64_t)prim;
+    if (flags & TAKE_PRIM_SPHERE) {
+        const double *s = sc.spheres + 4 * (int64_t)id[0];
+        D3 gn = normalize(sub(out.pos, mk3(s[0], s[1], s[2])));
+        out.gn = dot(d, gn) < 0 ? gn : neg(gn);
+        out.sn = out.gn;
+        out.uv = sphere_uv(out.gn);
+        return;
+    }
+    const int64_t i0 = id[0], i1 = id[1], i2 = id[2];
+    D3 v0 = ld3(sc.positions + 3 * i0);
+    D3 e1 = sub(ld3(sc.positions + 3 * i1), v0), e2 = sub(ld3(sc.positions + 3 * i2), v0);
+    D3 gn = normalize(cross(e1, e2));
+    out.gn = dot(d, gn) < 0 ? gn : neg(gn);
+    const double w = 1 - u - v;
+    if (!(flags & TAKE_PRIM_HAS_UVS)) {
+        out.uv.x = u; out.uv.y = v;
+    } else {
+        const double *a = sc.uvs + 2 * i0, *b = sc.uvs + 2 * i1, *c = sc.uvs + 2 * i2;
+        out.uv.x = w * a[0] + u * b[0] + v * c[0];
+        out.uv.y = w * a[1] + u * b[1] + v * c[1];
+    }
+    if (!(flags & TAKE_PRIM_HAS_NORMALS)) {
+        out.sn = out.gn;
+    } else {
+        D3 n0 = ld3(sc.normals + 3 * i0), n1 = ld3(sc.normals + 3 * i1), n2 = ld3(sc.normals + 3 * i2);
+        out.sn = normalize(add(add(mul(n0, w), mul(n1, u)), mul(n2, v)));
+    }
+}
+
+// src/texture.cpp:3-26, including the wrap-column quirk (weights use x2 = 0 there) taken literally.
+__device__ __forceinline__ D3 eval_texture(const DevScene &sc, const TakeMaterialDesc &m, D2 uv) {
+    if (m.tex_id < 0) return mk3(m.color[0], m.color[1], m.color[2]);
+    const DevTexture img = sc.textures[m.tex_id];
+    double x = img.w * modulo1(m.uscale * uv.x + m.uoffset);
+    double y = img.h * modulo1(m.vscale * uv.y + m.voffset);
+    int x1 = (int)floor(x);
+    int x2 = (x1 + 1) == img.w ? 0 : (x1 + 1);
+    int y1 = (int)floor(y);
+    int y2 = (y1 + 1) == img.h ? 0 : (y1 + 1);
+    auto px = [&](int xx, int yy) {
+        xx = min(max(xx, 0), img.w - 1);  // the reference indexes unchecked; only a rounding corner case can reach w
+        yy = min(max(yy, 0), img.h - 1);
+        return ld3(img.rgb + 3 * ((int64_t)yy * img.w + xx));
+    };
+    D3 q11 = px(x1, y1), q12 = px(x1, y2), q21 = px(x2, y1), q22 = px(x2, y2);
+    if (x1 == x2) x2 += 1;
+    if (y1 == y2) y2 += 1;
+    D3 acc = add(add(add(mul(mul(q11, x2 - x), y2 - y), mul(mul(q21, x - x1), y2 - y)), mul(mul(q12, x2 - x), y - y1)),
+                 mul(mul(q22, x - x1), y - y1));
+    return divs(acc, (double)((x2 - x1) * (y2 - y1)));
+}
+
+// ---- src/material.h:121-140 -------------------------------------------------------------------
+__device__ __forceinline__ D3 sample_hemisphere_cos(Rng &rng) {
+    double u1 = rng.next();
+    double u2 = rng.next();
+    double phi = TAKE_TWOPI * u2;
+    double sqrt_u1 = sqrt(clampd(u1, 0, 1));
+    return mk3(cos(phi) * sqrt_u1, sin(phi) * sqrt_u1, sqrt(clampd(1 - u1, 0, 1)));
+}
+__device__ __forceinline__ double blinn_G_hat(D3 omega, D3 n, double alpha) {
+    double odn = dot(omega, n);
+    double a = sqrt(0.5 * alpha + 1) / sqrt(1 / (odn * odn) - 1);
+    double a2 = a * a;
+    return a < 1.6 ? (3.535 * a + 2.181 * a2) / (1 + 2.276 * a + 2.577 * a2) : 1;
+}
+__device__ __forceinline__ D3 shading_n(D3 dir_in, const Isect &v) { return dot(dir_in, v.sn) < 0 ? neg(v.sn) : v.sn; }
+__device__ __forceinline__ D3 reflect(D3 dir_in, D3 n) { return add(neg(dir_in), mul(n, 2 * dot(dir_in, n))); }
+
+__device__ __forceinline__ bool is_lambert_like(int t) {
+    return t == TAKE_MAT_DIFFUSE || t >= TAKE_MAT_DISNEY_DIFFUSE;
+}
+__device__ __forceinline__ bool is_specular(int t) { return t == TAKE_MAT_PLASTIC || t == TAKE_MAT_MIRROR; }
+
+// phong.inl:9-19 / blinn_phong.inl:9-19 / blinn_phong_microfacet.inl:9-19: power-cosine lobe in a local frame
+__device__ __forceinline__ D3 sample_power_cos_lobe(double exponent, Rng &rng) {
+    double u1 = rng.next();
+    double u2 = rng.next();
+    double ra1 = 1 / (exponent + 1);
+    double phi = TAKE_TWOPI * u2;
+    double sqrt_u1 = sqrt(clampd(1 - pow(u1, 2 * ra1), 0, 1));
+    return normalize(mk3(cos(phi) * sqrt_u1, sin(phi) * sqrt_u1, clampd(pow(u1, ra1), 0, 1)));
+}
+
+// sample_bsdf (src/material.cpp:76-82 + materials/*.inl); false == std::nullopt
+__device__ inline bool sample_bsdf(const TakeMaterialDesc &m, D3 dir_in, const Isect &v, Rng &rng, D3 &dir_out, double &pdf) {
+    if (dot(v.gn, dir_in) < 0) return false;
+    D3 n = shading_n(dir_in, v);
+    const int t = m.type;
+    if (is_lambert_like(t)) {  // diffuse.inl:1-14, disney_*.inl:1-14
+        dir_out = to_world(n, sample_hemisphere_cos(rng));
+        pdf = dot(v.gn, dir_out) < 0 ? 0.0 : fmax(dot(n, dir_out), 0.0) / TAKE_PI;
+        return true;
+    }
+    if (t == TAKE_MAT_MIRROR) {  // mirror.inl:1-10
+        dir_out = reflect(dir_in, n);
+        pdf = 1;
+        return true;
+    }
+    if (t == TAKE_MAT_PLASTIC) {  // plastic.inl:1-27
+        D3 rd = reflect(dir_in, n);
+        double eta = m.p[0];
+        double F0 = pow((eta - 1) / (eta + 1), 2.0);
+        double F = F0 + (1 - F0) * pow(1 - dot(n, rd), 5.0);
+        double u = rng.next();
+        if (u <= F) {
+            dir_out = rd;
+            pdf = 1;
+        } else {
+            dir_out = to_world(n, sample_hemisphere_cos(rng));
+            pdf = dot(v.gn, dir_out) < 0 ? 0.0 : fmax(dot(n, dir_out), 0.0) / TAKE_PI;
+        }
+        return true;
+    }
+    const double ex = m.p[0];
+    if (t == TAKE_MAT_PHONG) {  // phong.inl:1-28
+        D3 local = sample_power_cos_lobe(ex, rng);
+        D3 rd = normalize(reflect(dir_in, n));
+        dir_out = normalize(to_world(rd, local));
+        pdf = dot(v.gn, dir_out) < 0 ? 0.0 : fmax(0.0, (ex + 1) / TAKE_TWOPI * pow(dot(rd, dir_out), ex));
+        return true;
+    }
+    // blinn_phong.inl:1-29 / blinn_phong_microfacet.inl:1-29
+    D3 local_h = sample_power_cos_lobe(ex, rng);
+    D3 h = normalize(to_world(n, local_h));
+    dir_out = normalize(add(neg(dir_in), mul(h, 2 * dot(dir_in, h))));
+    if (dot(v.gn, dir_out) <= 0 || dot(h, n) <= 0 || dot(dir_out, h) <= 0) {
+        pdf = 0;
+    } else if (t == TAKE_MAT_BLINN_PHONG) {
+        pdf = (ex + 1) * 0.25 * TAKE_INVTWOPI * pow(dot(n, h), ex) / dot(dir_out, h);
+    } else {
+        pdf = (ex + 1) * 0.25 * TAKE_INVTWOPI * pow(clampd(dot(n, h), 0, 1), ex) / dot(dir_out, h);
+    }
+    return true;
+}
+
+// get_bsdf_pdf (src/material.cpp:84-90 + materials/*.inl)
+__device__ inline double bsdf_pdf(const TakeMaterialDesc &m, D3 dir_in, D3 dir_out, const Isect &v) {
+    const int t = m.type;
+    if (t == TAKE_MAT_MIRROR) return 0;  // mirror.inl:12-14
+    if (dot(v.gn, dir_out) < 0) return 0;
+    D3 n = shading_n(dir_in, v);
+    if (is_lambert_like(t)) return fmax(dot(n, dir_out), 0.0) / TAKE_PI;  // diffuse.inl:16-21
+    if (t == TAKE_MAT_PLASTIC) {  // plastic.inl:29-38
+        double eta = m.p[0];
+        double F0 = pow((eta - 1) / (eta + 1), 2.0);
+        double F = F0 + (1 - F0) * pow(1 - dot(n, dir_out), 5.0);
+        return (1 - F) * fmax(dot(n, dir_out), 0.0) / TAKE_PI;
+    }
+    const double ex = m.p[0];
+    if (t == TAKE_MAT_PHONG) {  // phong.inl:30-40
+        D3 rd = normalize(reflect(dir_in, n));
+        return fmax(0.0, (ex + 1) / TAKE_TWOPI * pow(dot(rd, dir_out), ex));
+    }
+    D3 h = normalize(add(dir_out, dir_in));  // blinn_phong.inl:31-41, blinn_phong_microfacet.inl:31-41
+    if (dot(v.gn, dir_out) <= 0 || dot(h, n) <= 0 || dot(dir_out, h) <= 0) return 0;
+    if (t == TAKE_MAT_BLINN_PHONG) return (ex + 1) * 0.25 * TAKE_INVTWOPI * pow(dot(n, h), ex) / dot(dir_out, h);
+    return (ex + 1) * 0.25 * TAKE_INVTWOPI * pow(clampd(dot(n, h), 0, 1), ex) / dot(dir_out, h);
+}
+
+// eval (src/material.cpp:92-98 + materials/*.inl): BSDF * cos.  rec_pdf is SampleRecord::pdf, which Plastic::eval
+// uses to tell its two lobes apart (plastic.inl:44).
+__device__ inline D3 bsdf_eval(const DevScene &sc, const TakeMaterialDesc &m, D3 dir_in, D3 dir_out, double rec_pdf,
+                               const Isect &v) {
+    const D3 zero = mk3(0, 0, 0);
+    if (dot(v.gn, dir_in) < 0 || dot(v.gn, dir_out) < 0) return zero;
+    D3 n = shading_n(dir_in, v);
+    const int t = m.type;
+    if (t == TAKE_MAT_DISNEY_CLEARCOAT) return zero;  // disney_clearcoat.inl:22-27
+    if (t == TAKE_MAT_DIFFUSE || t == TAKE_MAT_DISNEY_METAL || t == TAKE_MAT_DISNEY_GLASS || t == TAKE_MAT_DISNEY_SHEEN ||
+        t == TAKE_MAT_DISNEY_BSDF) {  // diffuse.inl:23-29 and the Lambertian stubs
+        D3 Kd = eval_texture(sc, m, v.uv);
+        return divs(mul(Kd, fmax(dot(n, dir_out), 0.0)), TAKE_PI);
+    }
+    if (t == TAKE_MAT_MIRROR) {  // mirror.inl:16-23
+        D3 F0 = eval_texture(sc, m, v.uv);
+        return add(F0, mul(rsub(1, F0), pow(1 - dot(n, dir_out), 5.0)));
+    }
+    if (t == TAKE_MAT_PLASTIC) {  // plastic.inl:40-52
+        if (rec_pdf == 1.0) return mk3(1, 1, 1);
+        D3 Kd = eval_texture(sc, m, v.uv);
+        return divs(mul(Kd, fmax(dot(n, dir_out), 0.0)), TAKE_PI);
+    }
+    const double ex = m.p[0];
+    if (t == TAKE_MAT_PHONG) {  // phong.inl:42-54
+        D3 rd = normalize(reflect(dir_in, n));
+        D3 Ks = eval_texture(sc, m, v.uv);
+        if (dot(n, dir_out) <= 0) return zero;
+        return mul(divs(mul(Ks, ex + 1), TAKE_TWOPI), pow(fmax(dot(dir_out, rd), 0.0), ex));
+    }
+    if (t == TAKE_MAT_BLINN_PHONG) {  // blinn_phong.inl:43-56
+        if (dot(n, dir_out) <= 0) return zero;
+        D3 h = normalize(add(dir_out, dir_in));
+        D3 Ks = eval_texture(sc, m, v.uv);
+        D3 Fh = add(Ks, mul(rsub(1, Ks), pow(1 - dot(h, dir_out), 5.0)));
+        double s = (ex + 2) * 0.25 * TAKE_INVPI / (2 - pow(2.0, -ex / 2));
+        return mul(mul(Fh, s), pow(fmax(0.0, dot(n, h)), ex));
+    }
+    if (t == TAKE_MAT_BLINN_MICROFACET) {  // blinn_phong_microfacet.inl:43-60
+        D3 h = normalize(add(dir_out, dir_in));
+        if (dot(n, dir_out) <= 0 || dot(dir_out, h) <= 0 || dot(dir_in, h) <= 0) return zero;
+        D3 Ks = eval_texture(sc, m, v.uv);
+        D3 Fh = add(Ks, mul(rsub(1, Ks), pow(1 - dot(h, dir_out), 5.0)));
+        double Dh = (ex + 2) * TAKE_INVTWOPI * pow(clampd(dot(n, h), 0, 1), ex);
+        double G = blinn_G_hat(dir_out, n, ex) * blinn_G_hat(dir_in, n, ex);
+        return divs(mul(mul(mul(Fh, Dh), G), 0.25), dot(n, dir_in));
+    }
+    // TAKE_MAT_DISNEY_DIFFUSE: disney_diffuse.inl:22-47
+    D3 h = normalize(add(dir_in, dir_out));
+    double hdout = dot(h, dir_out), ndout = dot(n, dir_out), ndin = dot(n, dir_in);
+    D3 Kd = eval_texture(sc, m, v.uv);
+    double rough = m.p[0], subsurface = m.p[1];
+    double p_in = pow(1 - dot(n, dir_in), 5.0), p_out = pow(1 - dot(n, dir_out), 5.0);
+    double FD90 = 0.5 + 2 * rough * hdout * hdout;
+    D3 f_base = mul(mul(mul(mul(Kd, TAKE_INVPI), 1 + (FD90 - 1) * p_in), 1 + (FD90 - 1) * p_out), ndout);
+    double FSS90 = rough * hdout * hdout;
+    double inner = (1 + (FSS90 - 1) * p_in) * (1 + (FSS90 - 1) * p_out) * (1 / (fabs(ndin) + fabs(ndout)) - 0.5) + 0.5;
+    D3 f_ss = mul(mul(mul(mul(Kd, 1.25), TAKE_INVPI), inner), ndout);
+    return add(mul(f_base, 1 - subsurface), mul(f_ss, subsurface));
+}
+
+// ---- lights: src/light.cpp:5-7,32-56, src/shape.cpp:125-184 ------------------------------------------
+__device__ __forceinline__ double prim_area(const DevScene &sc, int prim) {  // get_area_op, shape.cpp:171-184
+    const int32_t *id = sc.indices + 3 * (int64_t)prim;
+    if (sc.prim_flags[prim] & TAKE_PRIM_SPHERE) {
+        double r = sc.spheres[4 * (int64_t)id[0] + 3];
+        return 4 * TAKE_PI * r * r;
+    }
+    D3 v0 = ld3(sc.positions + 3 * (int64_t)id[0]);
+    return length(cross(sub(ld3(sc.positions + 3 * (int64_t)id[1]), v0), sub(ld3(sc.positions + 3 * (int64_t)id[2]), v0))) / 2;
+}
+
+__device__ inline void sample_on_prim(const DevScene &sc, int prim, D3 ref_pos, Rng &rng, D3 &pos, D3 &nrm) {
+    const int32_t *id = sc.indices + 3 * (int64_t)prim;
+    if (sc.prim_flags[prim] & TAKE_PRIM_SPHERE) {  // shape.cpp:125-144
+        const double *s = sc.spheres + 4 * (int64_t)id[0];
+        D3 c = mk3(s[0], s[1], s[2]);
+        double u1 = rng.next();
+        double u2 = rng.next();
+        double r = s[3];
+        double d = length(sub(c, ref_pos));
+        double z = 1 + u1 * (r / d - 1);
+        double z2 = z * z;
+        double sin_theta = sqrt(clampd(1 - z2, 0, 1));
+        D3 local_p = normalize(mk3(cos(2 * TAKE_PI * u2) * sin_theta, sin(2 * TAKE_PI * u2) * sin_theta, z));
+        nrm = normalize(to_world(normalize(sub(ref_pos, c)), local_p));
+        pos = add(c, mul(nrm, r));
+        return;
+    }
+    const int64_t i0 = id[0], i1 = id[1], i2 = id[2];  // shape.cpp:146-169
+    D3 v0 = ld3(sc.positions + 3 * i0), v1 = ld3(sc.positions + 3 * i1), v2 = ld3(sc.positions + 3 * i2);
+    double u1 = rng.next();
+    double u2 = rng.next();
+    double b1 = 1 - sqrt(u1);
+    double b2 = sqrt(u1) * u2;
+    double b0 = 1 - b1 - b2;
+    pos = add(add(mul(v0, b0), mul(v1, b1)), mul(v2, b2));
+    D3 n = normalize(cross(sub(v1, v0), sub(v2, v0)));
+    D3 sn = add(add(mul(ld3(sc.normals + 3 * i0), b0), mul(ld3(sc.normals + 3 * i1), b1)), mul(ld3(sc.normals + 3 * i2), b2));
+    nrm = dot(sn, n) > 0 ? n : neg(n);
+}
+
+__device__ __forceinline__ double light_pdf_area(const DevScene &sc, int light_id, D3 light_pos, D3 ref_pos) {  // light.cpp:32-48
+    const TakeLightDesc &l = sc.lights[light_id];
+    if (l.kind != TAKE_LIGHT_AREA) return 0;
+    const int prim = l.prim_id;
+    if (sc.prim_flags[prim] & TAKE_PRIM_SPHERE) {
+        double r = sc.spheres[4 * (int64_t)sc.indices[3 * (int64_t)prim] + 3];
+        double d = length(sub(light_pos, ref_pos));
+        return 1 / (TAKE_TWOPI * r * r * (1 - r / d));
+    }
+    return 1 / prim_area(sc, prim);
+}
+
+__device__ __forceinline__ D3 light_intensity(const TakeLightDesc &l) { return mk3(l.intensity[0], l.intensity[1], l.intensity[2]); }
+
+}  // namespace take

@@ -1,0 +1,636 @@
+// C-ABI of the B200 rendering core (include/take_gpu.h): host orchestration of the CUDA kernels.
+// There is no CPU fallback anywhere in this file: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/take_gpu.h"
+#include "bvh_build.h"
+#include "wavefront.cuh"
+
+using namespace take;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string &msg) {
+    g_error = msg;
+    return code;
+}
+
+#define CU(expr)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t e_ = (expr);                                                                             \
+        if (e_ != cudaSuccess)                                                                               \
+            return fail(e_ == cudaErrorMemoryAllocation ? TAKE_E_NOMEM : TAKE_E_CUDA,                        \
+                        std::string(#expr) + ": " + cudaGetErrorString(e_));                                 \
+    } while (0)
+
+int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+struct DeviceBuffer {
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~DeviceBuffer() { if (p) cudaFree(p); }
+    cudaError_t ensure(size_t n) {
+        if (n <= bytes) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+    template <typename T> T *as() { return (T *)p; }
+};
+
+}  // namespace
+
+struct TakeScene {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    DevScene dev{};
+    int width = 0, height = 0;
+    // scene storage
+    DeviceBuffer nodes, tris, ref_nodes, positions, normals, uvs, indices, prim_material, prim_light, dfs_rank, prim_flags,
+        prim_mtype, spheres, materials, lights, textures;
+    std::vector<DeviceBuffer *> tex_data;
+    // wave storage
+    DeviceBuffer ray, hit, path, pend, shadow, q0, q1, q_sorted, q_shadow, pass, totals, scratch_a, scratch_b, scratch_c,
+        fetch;
+    int64_t wave_capacity = 0;
+    int blocks_extend = 0, blocks_shadow = 0, blocks_isect = 0, blocks_occl = 0;
+    // diagnostics
+    double build_ms_ref = 0, build_ms_fast = 0;
+    int fast_depth = 0;
+    double sah_cost = 0;
+    int64_t num_fast_nodes = 0;
+    ~TakeScene() {
+        for (auto *b : tex_data) delete b;
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+template <typename T>
+int upload(DeviceBuffer &buf, const T *src, size_t count, cudaStream_t s) {
+    size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+    CU(buf.ensure(bytes));
+    if (count) CU(cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    return TAKE_OK;
+}
+
+double now_ms() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+int validate(const TakeSceneDesc *d) {
+    if (!d) return fail(TAKE_E_INVALID, "null scene description");
+    if (d->camera.width <= 0 || d->camera.height <= 0) return fail(TAKE_E_INVALID, "camera resolution must be positive");
+    if (d->num_prims < 0 || d->num_vertices < 0 || d->num_spheres < 0) return fail(TAKE_E_INVALID, "negative count");
+    if (d->num_prims >= (1 << 28)) return fail(TAKE_E_INVALID, "too many primitives (limit 2^28)");
+    if (d->num_prims > 0 && (!d->indices || !d->prim_material || !d->prim_light || !d->prim_flags))
+        return fail(TAKE_E_INVALID, "primitive arrays missing");
+    if (d->num_vertices > 0 && (!d->positions || !d->normals || !d->uvs)) return fail(TAKE_E_INVALID, "vertex arrays missing");
+    for (int64_t i = 0; i < d->num_prims; ++i) {
+        const int32_t *id = d->indices + 3 * i;
+        if (d->prim_flags[i] & TAKE_PRIM_SPHERE) {
+            if (id[0] < 0 || id[0] >= d->num_spheres) return fail(TAKE_E_INVALID, "sphere index out of range");
+        } else {
+            for (int k = 0; k < 3; ++k)
+                if (id[k] < 0 || id[k] >= d->num_vertices) return fail(TAKE_E_INVALID, "vertex index out of range");
+        }
+        if (d->prim_material[i] < 0 || d->prim_material[i] >= d->num_materials)
+            return fail(TAKE_E_INVALID, "material id out of range");  // the reference would index out of bounds
+        if (d->prim_light[i] < -1 || d->prim_light[i] >= d->num_lights) return fail(TAKE_E_INVALID, "light id out of range");
+    }
+    for (int i = 0; i < d->num_materials; ++i) {
+        const TakeMaterialDesc &m = d->materials[i];
+        if (m.type < 0 || m.type > TAKE_MAT_DISNEY_BSDF) return fail(TAKE_E_INVALID, "unknown material type");
+        if (m.tex_id >= d->num_textures) return fail(TAKE_E_INVALID, "texture id out of range");
+    }
+    for (int i = 0; i < d->num_lights; ++i) {
+        const TakeLightDesc &l = d->lights[i];
+        if (l.kind == TAKE_LIGHT_AREA && (l.prim_id < 0 || l.prim_id >= d->num_prims))
+            return fail(TAKE_E_INVALID, "area light primitive out of range");
+    }
+    return TAKE_OK;
+}
+
+int ensure_wave(TakeScene *s, int64_t capacity) {
+    if (capacity <= s->wave_capacity) return TAKE_OK;
+    CU(s->ray.ensure(capacity * sizeof(RayRec)));
+    CU(s->hit.ensure(capacity * sizeof(HitRec)));
+    CU(s->path.ensure(capacity * sizeof(PathRec)));
+    CU(s->pend.ensure(capacity * sizeof(PendRec)));
+    CU(s->shadow.ensure(capacity * sizeof(ShadowRec)));
+    CU(s->q0.ensure(capacity * 4));
+    CU(s->q1.ensure(capacity * 4));
+    CU(s->q_sorted.ensure(capacity * 4));
+    CU(s->q_shadow.ensure(capacity * 4));
+    CU(s->pass.ensure(sizeof(PassCounters) * TAKE_MAX_PASSES));
+    CU(s->totals.ensure(sizeof(Totals)));
+    s->wave_capacity = capacity;
+    return TAKE_OK;
+}
+
+struct StageTimer {
+    bool on = false;
+    cudaStream_t stream;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> stage;
+    double ms[6] = {0, 0, 0, 0, 0, 0};
+    void begin(int st) {
+        if (!on) return;
+        cudaEvent_t a;
+        cudaEventCreate(&a);
+        cudaEventRecord(a, stream);
+        ev.push_back(a);
+        stage.push_back(st);
+    }
+    void end() {
+        if (!on) return;
+        cudaEvent_t b;
+        cudaEventCreate(&b);
+        cudaEventRecord(b, stream);
+        ev.push_back(b);
+    }
+    void collect() {
+        if (!on) return;
+        cudaStreamSynchronize(stream);
+        for (size_t i = 0; i < stage.size(); ++i) {
+            float t = 0;
+            cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]);
+            ms[stage[i]] += t;
+        }
+        for (auto e : ev) cudaEventDestroy(e);
+        ev.clear();
+        stage.clear();
+    }
+};
+enum { ST_GENERATE = 0, ST_EXTEND, ST_SHADE, ST_SHADOW, ST_SORT, ST_OTHER };
+
+int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, double *d_sumsq, double *d_list_out,
+                StageTimer &tm, bool count, int64_t &launches) {
+    cudaStream_t st = s->stream;
+    const int n_passes = o->max_depth + 2;
+    CU(cudaMemsetAsync(w.pass, 0, sizeof(PassCounters) * (size_t)(n_passes + 1), st));
+    tm.begin(ST_GENERATE);
+    k_generate<<<(w.n_slots + 255) / 256, 256, 0, st>>>(s->dev, w);
+    tm.end();
+    launches++;
+    const int shade_blocks = std::max(1, std::min((w.n_slots + 127) / 128, s->sm_count * 64));
+    const int scatter_blocks = std::max(1, std::min((w.n_slots + 255) / 256, s->sm_count * 16));
+    for (int b = 0; b < n_passes; ++b) {
+        tm.begin(ST_EXTEND);
+        if (count) k_extend<true><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
+        else k_extend<false><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
+        tm.end();
+        if (w.sort_enabled) {
+            tm.begin(ST_SORT);
+            k_scatter<<<scatter_blocks, 256, 0, st>>>(w, b);
+            tm.end();
+            launches++;
+        }
+        tm.begin(ST_SHADE);
+        k_shade<<<shade_blocks, 128, 0, st>>>(s->dev, w, b);
+        tm.end();
+        launches += 2;
+        if (o->integrator == TAKE_INTEGRATOR_MIS && b <= o->max_depth) {
+            tm.begin(ST_SHADOW);
+            if (count) k_shadow<true><<<s->blocks_shadow, 128, 0, st>>>(s->dev, w, b);
+            else k_shadow<false><<<s->blocks_shadow, 128, 0, st>>>(s->dev, w, b);
+            tm.end();
+            launches++;
+        }
+    }
+    tm.begin(ST_OTHER);
+    if (d_list_out) k_gather_radiance<<<(w.n_slots + 255) / 256, 256, 0, st>>>(w, d_list_out, n_passes);
+    else k_accumulate<<<(w.chunk_pixels + 255) / 256, 256, 0, st>>>(w, d_sum, d_sumsq, n_passes);
+    tm.end();
+    launches++;
+    CU(cudaGetLastError());
+    return TAKE_OK;
+}
+
+void fill_wave_ptrs(TakeScene *s, Wave &w, const TakeRenderOpts *o) {
+    memset(&w, 0, sizeof(w));
+    w.ray = s->ray.as<RayRec>();
+    w.hit = s->hit.as<HitRec>();
+    w.path = s->path.as<PathRec>();
+    w.pend = s->pend.as<PendRec>();
+    w.shadow = s->shadow.as<ShadowRec>();
+    w.q_extend[0] = s->q0.as<int32_t>();
+    w.q_extend[1] = s->q1.as<int32_t>();
+    w.q_sorted = s->q_sorted.as<int32_t>();
+    w.q_shadow = s->q_shadow.as<int32_t>();
+    w.pass = s->pass.as<PassCounters>();
+    w.totals = s->totals.as<Totals>();
+    w.integrator = o->integrator;
+    w.max_depth = o->max_depth;
+    w.sort_enabled = (o->flags & TAKE_RENDER_NO_SORT) ? 0 : 1;
+    w.seed = o->seed;
+}
+
+int check_opts(const TakeScene *s, const TakeRenderOpts *o) {
+    if (!s || !o) return fail(TAKE_E_INVALID, "null argument");
+    if (o->integrator < TAKE_INTEGRATOR_MIS || o->integrator > TAKE_INTEGRATOR_ONE_SAMPLE_MIS)
+        return fail(TAKE_E_INVALID, "unknown integrator");
+    if (o->max_depth < -1 || o->max_depth + 3 > TAKE_MAX_PASSES)
+        return fail(TAKE_E_INVALID, "max_depth out of range (-1 .. " + std::to_string(TAKE_MAX_PASSES - 3) + ")");
+    if (o->spp_end < o->spp_begin) return fail(TAKE_E_INVALID, "spp_end < spp_begin");
+    return TAKE_OK;
+}
+
+void read_totals(TakeScene *s, TakeStats *stats, const StageTimer &tm, double ms_total, int64_t launches) {
+    if (!stats) return;
+    Totals t;
+    cudaMemcpy(&t, s->totals.p, sizeof(t), cudaMemcpyDeviceToHost);
+    memset(stats, 0, sizeof(*stats));
+    stats->samples = (int64_t)t.samples;
+    stats->extend_rays = (int64_t)t.extend_rays;
+    stats->shadow_rays = (int64_t)t.shadow_rays;
+    stats->shaded = (int64_t)t.shaded;
+    stats->box_tests = (int64_t)t.box_tests;
+    stats->tri_tests = (int64_t)t.tri_tests;
+    stats->kernel_launches = launches;
+    stats->ms_total = ms_total;
+    stats->ms_generate = tm.ms[ST_GENERATE];
+    stats->ms_extend = tm.ms[ST_EXTEND];
+    stats->ms_shade = tm.ms[ST_SHADE];
+    stats->ms_shadow = tm.ms[ST_SHADOW];
+    stats->ms_sort = tm.ms[ST_SORT];
+    stats->ms_other = tm.ms[ST_OTHER];
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *take_gpu_last_error(void) { return g_error.c_str(); }
+const char *take_gpu_version(void) { return "take_b200 0.1 (sm_100a)"; }
+
+int take_gpu_device_count(int *count) {
+    if (!count) return fail(TAKE_E_INVALID, "null argument");
+    *count = 0;
+    CU(cudaGetDeviceCount(count));
+    return TAKE_OK;
+}
+
+int take_gpu_scene_create(int device, const TakeSceneDesc *d, TakeScene **out) {
+    if (!out) return fail(TAKE_E_INVALID, "null argument");
+    *out = nullptr;
+    if (int rc = validate(d)) return rc;
+    CU(cudaSetDevice(device));
+    TakeScene *s = new TakeScene;
+    struct Guard { TakeScene *&p; bool ok = false; ~Guard() { if (!ok) { delete p; p = nullptr; } } } guard{s};
+    s->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    s->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    cudaStream_t st = s->stream;
+    const int threads = std::max(1u, std::thread::hardware_concurrency());
+    const int64_t n = d->num_prims;
+
+    // primitive boxes exactly as build_bvh (src/scene.cpp:4-23)
+    std::vector<Aabb> boxes((size_t)n);
+    double abs_max = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        Aabb &b = boxes[i];
+        const int32_t *id = d->indices + 3 * i;
+        if (d->prim_flags[i] & TAKE_PRIM_SPHERE) {
+            const double *sp = d->spheres + 4 * (int64_t)id[0];
+            for (int a = 0; a < 3; ++a) { b.lo[a] = sp[a] - sp[3]; b.hi[a] = sp[a] + sp[3]; }
+        } else {
+            const double *p0 = d->positions + 3 * (int64_t)id[0], *p1 = d->positions + 3 * (int64_t)id[1],
+                         *p2 = d->positions + 3 * (int64_t)id[2];
+            for (int a = 0; a < 3; ++a) {
+                b.lo[a] = std::min(std::min(p0[a], p1[a]), p2[a]);
+                b.hi[a] = std::max(std::max(p0[a], p1[a]), p2[a]);
+            }
+        }
+        for (int a = 0; a < 3; ++a) abs_max = std::max(abs_max, std::max(fabs(b.lo[a]), fabs(b.hi[a])));
+    }
+
+    RefTree ref;
+    FastTree fast;
+    double t0 = now_ms();
+    build_reference_tree(boxes.data(), n, threads, ref);
+    double t1 = now_ms();
+    const int max_leaf = std::min(8, std::max(1, env_int("TAKE_BVH_MAX_LEAF", 4)));
+    build_fast_tree(boxes.data(), n, max_leaf, 0.0f, threads, fast);
+    double t2 = now_ms();
+    s->build_ms_ref = t1 - t0;
+    s->build_ms_fast = t2 - t1;
+    s->fast_depth = fast.depth;
+    s->sah_cost = fast.sah_cost;
+    s->num_fast_nodes = (int64_t)fast.nodes.size();
+    if (fast.depth > TAKE_STACK_SMEM + TAKE_STACK_LOCAL)
+        return fail(TAKE_E_INVALID, "acceleration tree too deep (" + std::to_string(fast.depth) + ")");
+
+    // leaf-ordered FP64 primitive records: v0 | idbits | e1 | aux | e2 | kind
+    std::vector<double> tris((size_t)n * 12);
+    for (int64_t slot = 0; slot < n; ++slot) {
+        const int32_t prim = fast.leaf_prims[slot];
+        double *T = tris.data() + 12 * slot;
+        const int32_t *id = d->indices + 3 * (int64_t)prim;
+        long long bits = ((long long)ref.dfs_rank[prim] << 32) | (long long)(uint32_t)prim;
+        memcpy(&T[3], &bits, 8);
+        if (d->prim_flags[prim] & TAKE_PRIM_SPHERE) {
+            const double *sp = d->spheres + 4 * (int64_t)id[0];
+            T[0] = sp[0]; T[1] = sp[1]; T[2] = sp[2];
+            T[4] = T[5] = T[6] = 0; T[7] = sp[3];
+            T[8] = T[9] = T[10] = 0; T[11] = 1.0;
+        } else {
+            const double *p0 = d->positions + 3 * (int64_t)id[0], *p1 = d->positions + 3 * (int64_t)id[1],
+                         *p2 = d->positions + 3 * (int64_t)id[2];
+            for (int a = 0; a < 3; ++a) {
+                T[a] = p0[a];
+                T[4 + a] = p1[a] - p0[a];  // e1 = v1 - v0, e2 = v2 - v0 (src/shape.cpp:53-54), computed once
+                T[8 + a] = p2[a] - p0[a];
+            }
+            T[7] = 0; T[11] = 0.0;
+        }
+    }
+    std::vector<uint8_t> mtype((size_t)n);
+    for (int64_t i = 0; i < n; ++i) mtype[i] = (uint8_t)d->materials[d->prim_material[i]].type;
+
+    int rc;
+    if ((rc = upload(s->nodes, fast.nodes.data(), fast.nodes.size(), st))) return rc;
+    if ((rc = upload(s->tris, tris.data(), tris.size(), st))) return rc;
+    if ((rc = upload(s->ref_nodes, ref.nodes.data(), ref.nodes.size(), st))) return rc;
+    if ((rc = upload(s->positions, d->positions, (size_t)d->num_vertices * 3, st))) return rc;
+    if ((rc = upload(s->normals, d->normals, (size_t)d->num_vertices * 3, st))) return rc;
+    if ((rc = upload(s->uvs, d->uvs, (size_t)d->num_vertices * 2, st))) return rc;
+    if ((rc = upload(s->indices, d->indices, (size_t)n * 3, st))) return rc;
+    if ((rc = upload(s->prim_material, d->prim_material, (size_t)n, st))) return rc;
+    if ((rc = upload(s->prim_light, d->prim_light, (size_t)n, st))) return rc;
+    if ((rc = upload(s->dfs_rank, ref.dfs_rank.data(), ref.dfs_rank.size(), st))) return rc;
+    if ((rc = upload(s->prim_flags, d->prim_flags, (size_t)n, st))) return rc;
+    if ((rc = upload(s->prim_mtype, mtype.data(), mtype.size(), st))) return rc;
+    if ((rc = upload(s->spheres, d->spheres, (size_t)d->num_spheres * 4, st))) return rc;
+    if ((rc = upload(s->materials, d->materials, (size_t)d->num_materials, st))) return rc;
+    if ((rc = upload(s->lights, d->lights, (size_t)d->num_lights, st))) return rc;
+    std::vector<DevTexture> tex((size_t)d->num_textures);
+    for (int i = 0; i < d->num_textures; ++i) {
+        const TakeTextureDesc &t = d->textures[i];
+        if (t.width <= 0 || t.height <= 0 || !t.rgb) return fail(TAKE_E_INVALID, "bad texture");
+        DeviceBuffer *b = new DeviceBuffer;
+        s->tex_data.push_back(b);
+        if ((rc = upload(*b, t.rgb, (size_t)t.width * t.height * 3, st))) return rc;
+        tex[i].w = t.width; tex[i].h = t.height; tex[i].rgb = b->as<double>();
+    }
+    if ((rc = upload(s->textures, tex.data(), tex.size(), st))) return rc;
+    CU(cudaStreamSynchronize(st));
+
+    DevScene &v = s->dev;
+    v.nodes = s->nodes.as<float4>();
+    v.tris = s->tris.as<double2>();
+    v.ref_nodes = s->ref_nodes.as<RefNode>();
+    v.ref_root = ref.root;
+    v.fast_depth = fast.depth;
+    v.positions = s->positions.as<double>(); v.normals = s->normals.as<double>(); v.uvs = s->uvs.as<double>();
+    v.indices = s->indices.as<int32_t>(); v.prim_material = s->prim_material.as<int32_t>();
+    v.prim_light = s->prim_light.as<int32_t>(); v.dfs_rank = s->dfs_rank.as<int32_t>();
+    v.prim_flags = s->prim_flags.as<uint8_t>(); v.prim_mtype = s->prim_mtype.as<uint8_t>();
+    v.spheres = s->spheres.as<double>();
+    v.materials = s->materials.as<TakeMaterialDesc>();
+    v.lights = s->lights.as<TakeLightDesc>();
+    v.textures = s->textures.as<DevTexture>();
+    v.num_lights = d->num_lights; v.num_materials = d->num_materials;
+    v.num_prims = n;
+    // camera basis: src/render.cpp:37-44, same operations on the host's libm
+    const TakeCamera &c = d->camera;
+    s->width = v.width = c.width; s->height = v.height = c.height;
+    {
+        auto sub3 = [](const double *a, const double *b, double *o) { for (int i = 0; i < 3; ++i) o[i] = a[i] - b[i]; };
+        auto norm3 = [](double *a) {
+            double l = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+            if (l <= 0) { a[0] = a[1] = a[2] = 0; return; }
+            double inv = 1.0 / l;
+            for (int i = 0; i < 3; ++i) a[i] *= inv;
+        };
+        auto cross3 = [](const double *a, const double *b, double *o) {
+            o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+        };
+        double theta = c.vfov / 180 * TAKE_PI;
+        double h = tan(theta / 2);
+        v.viewport_h = 2 * h;
+        v.viewport_w = v.viewport_h / c.height * c.width;
+        double w[3], u[3], vv[3];
+        sub3(c.lookfrom, c.lookat, w); norm3(w);
+        cross3(c.up, w, u); norm3(u);
+        cross3(w, u, vv);
+        v.lookfrom = {c.lookfrom[0], c.lookfrom[1], c.lookfrom[2]};
+        v.cam_u = {u[0], u[1], u[2]}; v.cam_v = {vv[0], vv[1], vv[2]}; v.cam_w = {w[0], w[1], w[2]};
+    }
+    v.background = {d->background[0], d->background[1], d->background[2]};
+    v.abs_max = (float)abs_max;
+
+    // persistent-kernel launch widths: every SM filled to the occupancy the kernel allows
+    auto blocks_for = [&](const void *fn) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+        return per_sm * s->sm_count;
+    };
+    s->blocks_extend = blocks_for((const void *)k_extend<false>);
+    s->blocks_shadow = blocks_for((const void *)k_shadow<false>);
+    s->blocks_isect = blocks_for((const void *)k_intersect_fast<false>);
+    s->blocks_occl = blocks_for((const void *)k_intersect_fast<true>);
+    CU(s->fetch.ensure(256));
+    guard.ok = true;
+    *out = s;
+    return TAKE_OK;
+}
+
+int take_gpu_scene_destroy(TakeScene *s) {
+    if (!s) return TAKE_OK;
+    cudaSetDevice(s->device);
+    delete s;
+    return TAKE_OK;
+}
+
+void *take_gpu_scene_stream(TakeScene *s) { return s ? (void *)s->stream : nullptr; }
+
+// diagnostics: out[0..5] = reference-tree build ms, fast-tree build ms, fast-tree depth, SAH cost, #fast nodes, #SMs
+int take_gpu_scene_info(TakeScene *s, double *out) {
+    if (!s || !out) return fail(TAKE_E_INVALID, "null argument");
+    out[0] = s->build_ms_ref; out[1] = s->build_ms_fast; out[2] = s->fast_depth; out[3] = s->sah_cost;
+    out[4] = (double)s->num_fast_nodes; out[5] = s->sm_count;
+    return TAKE_OK;
+}
+
+int take_gpu_intersect_device(TakeScene *s, const TakeRay *d_rays, int64_t n, TakeHit *d_hits, int flags) {
+    if (!s || (n > 0 && (!d_rays || !d_hits))) return fail(TAKE_E_INVALID, "null argument");
+    if (n < 0 || n > 0xfffffff0LL) return fail(TAKE_E_INVALID, "ray count out of range");
+    if (n == 0) return TAKE_OK;
+    CU(cudaSetDevice(s->device));
+    if (flags == TAKE_ISECT_EXACT) {
+        k_intersect_exact<<<(unsigned)((n + 127) / 128), 128, 0, s->stream>>>(s->dev, d_rays, n, d_hits);
+    } else if (flags == TAKE_ISECT_FAST) {
+        CU(cudaMemsetAsync(s->fetch.p, 0, 4, s->stream));
+        k_intersect_fast<false><<<s->blocks_isect, 128, 0, s->stream>>>(s->dev, d_rays, n, d_hits, nullptr, s->fetch.as<uint32_t>());
+    } else {
+        return fail(TAKE_E_INVALID, "unknown intersect flags");
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s->stream));
+    return TAKE_OK;
+}
+
+int take_gpu_intersect(TakeScene *s, const TakeRay *rays, int64_t n, TakeHit *hits, int flags) {
+    if (!s || (n > 0 && (!rays || !hits))) return fail(TAKE_E_INVALID, "null argument");
+    if (n < 0) return fail(TAKE_E_INVALID, "negative ray count");
+    CU(cudaSetDevice(s->device));
+    const int64_t chunk = 1 << 24;
+    for (int64_t off = 0; off < n; off += chunk) {
+        const int64_t m = std::min(chunk, n - off);
+        CU(s->scratch_a.ensure(m * sizeof(TakeRay)));
+        CU(s->scratch_b.ensure(m * sizeof(TakeHit)));
+        CU(cudaMemcpyAsync(s->scratch_a.p, rays + off, m * sizeof(TakeRay), cudaMemcpyHostToDevice, s->stream));
+        if (int rc = take_gpu_intersect_device(s, s->scratch_a.as<TakeRay>(), m, s->scratch_b.as<TakeHit>(), flags)) return rc;
+        CU(cudaMemcpyAsync(hits + off, s->scratch_b.p, m * sizeof(TakeHit), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    return TAKE_OK;
+}
+
+int take_gpu_occluded(TakeScene *s, const TakeRay *rays, int64_t n, uint8_t *occluded) {
+    if (!s || (n > 0 && (!rays || !occluded))) return fail(TAKE_E_INVALID, "null argument");
+    if (n < 0) return fail(TAKE_E_INVALID, "negative ray count");
+    CU(cudaSetDevice(s->device));
+    const int64_t chunk = 1 << 24;
+    for (int64_t off = 0; off < n; off += chunk) {
+        const int64_t m = std::min(chunk, n - off);
+        CU(s->scratch_a.ensure(m * sizeof(TakeRay)));
+        CU(s->scratch_b.ensure(m));
+        CU(cudaMemcpyAsync(s->scratch_a.p, rays + off, m * sizeof(TakeRay), cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemsetAsync(s->fetch.p, 0, 4, s->stream));
+        k_intersect_fast<true><<<s->blocks_occl, 128, 0, s->stream>>>(s->dev, s->scratch_a.as<TakeRay>(), m, nullptr,
+                                                                      s->scratch_b.as<uint8_t>(), s->fetch.as<uint32_t>());
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(occluded + off, s->scratch_b.p, m, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    return TAKE_OK;
+}
+
+int take_gpu_render_device(TakeScene *s, const TakeRenderOpts *o, double *d_sum, double *d_sumsq, TakeStats *stats) {
+    if (int rc = check_opts(s, o)) return rc;
+    if (!d_sum) return fail(TAKE_E_INVALID, "null output buffer");
+    CU(cudaSetDevice(s->device));
+    const int64_t npix = (int64_t)s->width * s->height;
+    const int64_t spp = o->spp_end - o->spp_begin;
+    const int64_t cap_env = std::max<int64_t>(1024, (int64_t)env_int("TAKE_WAVE_SLOTS", 1 << 22));
+    const int64_t capacity = std::min<int64_t>(cap_env, std::max<int64_t>(npix * std::max<int64_t>(spp, 1), 1024));
+    if (int rc = ensure_wave(s, capacity)) return rc;
+    CU(cudaMemsetAsync(s->totals.p, 0, sizeof(Totals), s->stream));
+    StageTimer tm;
+    tm.on = stats && env_int("TAKE_STAGE_TIMES", 0);
+    tm.stream = s->stream;
+    const bool count = env_int("TAKE_COUNT_TESTS", 0) != 0;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, s->stream));
+    int64_t launches = 0;
+    Wave w;
+    fill_wave_ptrs(s, w, o);
+    const int64_t chunk_pixels = std::min(npix, capacity);
+    for (int64_t base = 0; base < npix; base += chunk_pixels) {
+        const int64_t cp = std::min(chunk_pixels, npix - base);
+        const int64_t per_wave = std::max<int64_t>(1, capacity / cp);
+        for (int64_t s0 = o->spp_begin; s0 < o->spp_end; s0 += per_wave) {
+            const int64_t ns = std::min(per_wave, o->spp_end - s0);
+            w.chunk_pixels = (int32_t)cp;
+            w.chunk_base = (int32_t)base;
+            w.sample0 = s0;
+            w.samples_in_wave = (int32_t)ns;
+            w.n_slots = (int32_t)(cp * ns);
+            if (int rc = launch_wave(s, w, o, d_sum, d_sumsq, nullptr, tm, count, launches)) return rc;
+            tm.collect();
+        }
+    }
+    CU(cudaEventRecord(e1, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    read_totals(s, stats, tm, ms, launches);
+    return TAKE_OK;
+}
+
+int take_gpu_render(TakeScene *s, const TakeRenderOpts *o, double *sum_rgb, double *sumsq_rgb, TakeStats *stats) {
+    if (int rc = check_opts(s, o)) return rc;
+    if (!sum_rgb) return fail(TAKE_E_INVALID, "null output buffer");
+    CU(cudaSetDevice(s->device));
+    const size_t bytes = (size_t)s->width * s->height * 3 * sizeof(double);
+    CU(s->scratch_a.ensure(bytes));
+    CU(cudaMemsetAsync(s->scratch_a.p, 0, bytes, s->stream));
+    if (sumsq_rgb) {
+        CU(s->scratch_b.ensure(bytes));
+        CU(cudaMemsetAsync(s->scratch_b.p, 0, bytes, s->stream));
+    }
+    if (int rc = take_gpu_render_device(s, o, s->scratch_a.as<double>(), sumsq_rgb ? s->scratch_b.as<double>() : nullptr, stats))
+        return rc;
+    CU(cudaMemcpyAsync(sum_rgb, s->scratch_a.p, bytes, cudaMemcpyDeviceToHost, s->stream));
+    if (sumsq_rgb) CU(cudaMemcpyAsync(sumsq_rgb, s->scratch_b.p, bytes, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return TAKE_OK;
+}
+
+int take_gpu_radiance_samples(TakeScene *s, const TakeRenderOpts *o, int64_t n, const int32_t *px, const int32_t *py,
+                              const int64_t *smp, double *rgb) {
+    if (int rc = check_opts(s, o)) return rc;
+    if (n < 0 || (n > 0 && (!px || !py || !smp || !rgb))) return fail(TAKE_E_INVALID, "bad sample list");
+    if (n == 0) return TAKE_OK;
+    CU(cudaSetDevice(s->device));
+    const int64_t cap = 1 << 20;
+    if (int rc = ensure_wave(s, std::min(n, cap))) return rc;
+    std::vector<int32_t> pixel((size_t)std::min(n, cap));
+    StageTimer tm;
+    tm.stream = s->stream;
+    int64_t launches = 0;
+    CU(cudaMemsetAsync(s->totals.p, 0, sizeof(Totals), s->stream));
+    for (int64_t off = 0; off < n; off += cap) {
+        const int64_t m = std::min(cap, n - off);
+        for (int64_t i = 0; i < m; ++i) {
+            if (px[off + i] < 0 || px[off + i] >= s->width || py[off + i] < 0 || py[off + i] >= s->height)
+                return fail(TAKE_E_INVALID, "pixel out of range");
+            pixel[i] = py[off + i] * s->width + px[off + i];
+        }
+        CU(s->scratch_a.ensure(m * 4));
+        CU(s->scratch_b.ensure(m * 8));
+        CU(s->scratch_c.ensure(m * 24));
+        CU(cudaMemcpyAsync(s->scratch_a.p, pixel.data(), m * 4, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(s->scratch_b.p, smp + off, m * 8, cudaMemcpyHostToDevice, s->stream));
+        Wave w;
+        fill_wave_ptrs(s, w, o);
+        w.chunk_pixels = (int32_t)m;
+        w.n_slots = (int32_t)m;
+        w.samples_in_wave = 1;
+        w.list_pixel = s->scratch_a.as<int32_t>();
+        w.list_sample = s->scratch_b.as<int64_t>();
+        if (int rc = launch_wave(s, w, o, nullptr, nullptr, s->scratch_c.as<double>(), tm, false, launches)) return rc;
+        CU(cudaMemcpyAsync(rgb + 3 * off, s->scratch_c.p, m * 24, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    return TAKE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,242 @@
+// Ray-scene intersection on the device.
+//
+//  trace_exact  -- the reference's traversal verbatim: its own tree topology, FP64 slab test with divisions and
+//                  fmin/fmax (src/bbox.h:18-32), left-then-right DFS with tmax shrinking after each accepted hit
+//                  and later hits replacing earlier ones (src/bvh.cpp:86-109), unrolled into an explicit stack.
+//                  Bit-identical (id and t) to the reference on every ray, including exact ties.
+//  trace_fast   -- production path: SAH BVH2 with 64-byte nodes (both children's boxes, four float4 fetches),
+//                  conservative FP32 slab tests, near-child-first ordering, per-thread stack in shared memory
+//                  (conflict-free column layout) spilling to local memory, and the SAME FP64 leaf test.  Any
+//                  traversal that never culls a primitive the FP64 leaf test would accept returns the same closest
+//                  hit; equal-t candidates are resolved by the reference's DFS rank.
+#pragma once
+#include "device_common.cuh"
+
+namespace take {
+
+#define TAKE_STACK_SMEM 24   // entries per thread kept in shared memory
+#define TAKE_STACK_LOCAL 72  // overflow entries in local memory (tree depth limit = 96, checked on the host)
+
+// ---- leaf tests: src/shape.cpp:44-78 (triangle) and :13-29 (sphere), accept/reject part ---------------
+__device__ __forceinline__ bool hit_triangle(D3 v0, D3 e1, D3 e2, D3 o, D3 d, double tmin, double tmax, double &t,
+                                             double &bu, double &bv) {
+    D3 h = cross(d, e2);
+    double a = dot(e1, h);
+    if (a > -TAKE_EPS && a < TAKE_EPS) return false;
+    double f = 1.0 / a;
+    D3 s = sub(o, v0);
+    double u = f * dot(s, h);
+    if (u < 0.0 || u > 1.0) return false;
+    D3 q = cross(s, e1);
+    double v = f * dot(d, q);
+    if (v < 0.0 || u + v > 1.0) return false;
+    double tt = f * dot(e2, q);
+    if (tt < tmin || tmax < tt) return false;
+    t = tt; bu = u; bv = v;
+    return true;
+}
+
+__device__ __forceinline__ bool hit_sphere(D3 c, double radius, D3 o, D3 d, double tmin, double tmax, double &t) {
+    D3 oc = sub(o, c);
+    double a = dot(d, d);
+    double half_b = dot(oc, d);
+    double cc = dot(oc, oc) - radius * radius;
+    double disc = half_b * half_b - a * cc;
+    if (disc < 0) return false;
+    double sqrtd = sqrt(disc);
+    double root = (-half_b - sqrtd) / a;
+    if (root < tmin || tmax < root) {
+        root = (-half_b + sqrtd) / a;
+        if (root < tmin || tmax < root) return false;
+    }
+    t = root;
+    return true;
+}
+
+// Leaf test by primitive id, from the reference-layout arrays (used by the exact path).
+__device__ __forceinline__ bool hit_prim(const DevScene &sc, int prim, D3 o, D3 d, double tmin, double tmax, double &t,
+                                         double &bu, double &bv) {
+    bu = bv = 0;
+    if (sc.prim_flags[prim] & TAKE_PRIM_SPHERE) {
+        const double *s = sc.spheres + 4 * (int64_t)sc.indices[3 * (int64_t)prim];
+        return hit_sphere(mk3(s[0], s[1], s[2]), s[3], o, d, tmin, tmax, t);
+    }
+    const int32_t *id = sc.indices + 3 * (int64_t)prim;
+    const double *p0 = sc.positions + 3 * (int64_t)id[0], *p1 = sc.positions + 3 * (int64_t)id[1],
+                 *p2 = sc.positions + 3 * (int64_t)id[2];
+    D3 v0 = mk3(p0[0], p0[1], p0[2]);
+    D3 e1 = sub(mk3(p1[0], p1[1], p1[2]), v0), e2 = sub(mk3(p2[0], p2[1], p2[2]), v0);
+    return hit_triangle(v0, e1, e2, o, d, tmin, tmax, t, bu, bv);
+}
+
+// ---- exact mode ---------------------------------------------------------------------------------------
+__device__ __forceinline__ bool slab_exact(const RefNode &b, D3 o, D3 d, double tmin, double tmax) {  // bbox.h:18-32
+    double ta = (b.lo[0] - o.x) / d.x, tb = (b.hi[0] - o.x) / d.x;
+    double t_min = fmax(fmin(ta, tb), tmin), t_max = fmin(fmax(ta, tb), tmax);
+    if (t_max < t_min) return false;
+    ta = (b.lo[1] - o.y) / d.y; tb = (b.hi[1] - o.y) / d.y;
+    t_min = fmax(fmin(ta, tb), t_min); t_max = fmin(fmax(ta, tb), t_max);
+    if (t_max < t_min) return false;
+    ta = (b.lo[2] - o.z) / d.z; tb = (b.hi[2] - o.z) / d.z;
+    t_min = fmax(fmin(ta, tb), t_min); t_max = fmin(fmax(ta, tb), t_max);
+    return !(t_max < t_min);
+}
+
+// The recursion of bvh.cpp:86-109 is equivalent to: visit nodes in left-to-right DFS order; test a node's box when
+// it is reached (with the tmax current at that moment); at a leaf, accept a hit with tmin <= t <= tmax, which then
+// becomes both the result and the new tmax.  The root's own box is never tested.
+__device__ inline void trace_exact(const DevScene &sc, D3 o, D3 d, double tmin, double tmax, HitOut &out) {
+    out.prim = -1; out.rank = -1; out.t = 0; out.u = 0; out.v = 0;
+    if (sc.ref_root < 0) return;
+    int32_t stack[128];
+    int sp = 0;
+    int32_t node = sc.ref_root;
+    bool first = true;
+    for (;;) {
+        const RefNode &n = sc.ref_nodes[node];
+        if (first || slab_exact(n, o, d, tmin, tmax)) {
+            first = false;
+            if (n.prim != -1) {
+                double t, bu, bv;
+                if (hit_prim(sc, n.prim, o, d, tmin, tmax, t, bu, bv)) {
+                    out.prim = n.prim; out.t = t; out.u = bu; out.v = bv;
+                    tmax = t;
+                }
+            } else {
+                stack[sp++] = n.right;
+                node = n.left;
+                continue;
+            }
+        }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+}
+
+// ---- fast mode ------------------------------------------------------------------------------------------
+struct TravStack {
+    int32_t *s_node;  // shared-memory column base (this thread), element stride = blockDim.x
+    float *s_tn;
+    int stride;
+    int32_t l_node[TAKE_STACK_LOCAL];
+    float l_tn[TAKE_STACK_LOCAL];
+    int sp;
+    __device__ __forceinline__ void push(int32_t node, float tn) {
+        if (sp < TAKE_STACK_SMEM) { s_node[sp * stride] = node; s_tn[sp * stride] = tn; }
+        else { l_node[sp - TAKE_STACK_SMEM] = node; l_tn[sp - TAKE_STACK_SMEM] = tn; }
+        ++sp;
+    }
+    __device__ __forceinline__ void pop(int32_t &node, float &tn) {
+        --sp;
+        if (sp < TAKE_STACK_SMEM) { node = s_node[sp * stride]; tn = s_tn[sp * stride]; }
+        else { node = l_node[sp - TAKE_STACK_SMEM]; tn = l_tn[sp - TAKE_STACK_SMEM]; }
+    }
+};
+
+#define TAKE_SLACK 1.00000191f  // 1 + 2^-19: relative slack on the exit distance (error analysis in DESIGN.md)
+
+struct TravCounters {
+    unsigned long long box, tri;
+};
+
+template <bool ANY_HIT, bool COUNT>
+__device__ __forceinline__ void trace_fast(const DevScene &sc, D3 o, D3 d, double tmin, double tmax, TravStack &st,
+                                           HitOut &out, TravCounters *cnt) {
+    out.prim = -1; out.rank = -1; out.t = 0; out.u = 0; out.v = 0;
+    if (sc.num_prims <= 0) return;
+    // FP32 image of the ray.  Every box plane is tested as  t = plane * idir - (o -+ delta) * idir  with one FMA;
+    // delta (absolute) covers the rounding of the origin, of the product (o*idir) and of the FMA itself.
+    const float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
+    const float idx = 1.0f / (float)d.x, idy = 1.0f / (float)d.y, idz = 1.0f / (float)d.z;
+    const float delta = 1.9073486e-6f * fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fmaxf(fabsf(oz), sc.abs_max));  // 2^-19
+    const float olx = -(ox + delta) * idx, ohx = -(ox - delta) * idx;
+    const float oly = -(oy + delta) * idy, ohy = -(oy - delta) * idy;
+    const float olz = -(oz + delta) * idz, ohz = -(oz - delta) * idz;
+    const float tmin_f = __double2float_rd(tmin);
+    float tbest_f = __double2float_ru(tmax);
+    double best_t = tmax;
+
+    st.sp = 0;
+    int32_t node = 0;  // root
+    for (;;) {
+        while (node >= 0) {
+            const float4 q0 = __ldg(sc.nodes + 4 * (int64_t)node);
+            const float4 q1 = __ldg(sc.nodes + 4 * (int64_t)node + 1);
+            const float4 q2 = __ldg(sc.nodes + 4 * (int64_t)node + 2);
+            const float4 q3 = __ldg(sc.nodes + 4 * (int64_t)node + 3);
+            if (COUNT) cnt->box += 2;
+            float a, b;
+            a = fmaf(q0.x, idx, olx); b = fmaf(q0.y, idx, ohx);
+            float tn0 = fminf(a, b), tf0 = fmaxf(a, b);
+            a = fmaf(q0.z, idy, oly); b = fmaf(q0.w, idy, ohy);
+            tn0 = fmaxf(tn0, fminf(a, b)); tf0 = fminf(tf0, fmaxf(a, b));
+            a = fmaf(q2.x, idz, olz); b = fmaf(q2.y, idz, ohz);
+            tn0 = fmaxf(tn0, fminf(a, b)); tf0 = fminf(tf0, fmaxf(a, b));
+            tn0 = fmaxf(tn0, tmin_f); tf0 = fminf(tf0, tbest_f);
+            a = fmaf(q1.x, idx, olx); b = fmaf(q1.y, idx, ohx);
+            float tn1 = fminf(a, b), tf1 = fmaxf(a, b);
+            a = fmaf(q1.z, idy, oly); b = fmaf(q1.w, idy, ohy);
+            tn1 = fmaxf(tn1, fminf(a, b)); tf1 = fminf(tf1, fmaxf(a, b));
+            a = fmaf(q2.z, idz, olz); b = fmaf(q2.w, idz, ohz);
+            tn1 = fmaxf(tn1, fminf(a, b)); tf1 = fminf(tf1, fmaxf(a, b));
+            tn1 = fmaxf(tn1, tmin_f); tf1 = fminf(tf1, tbest_f);
+            const bool h0 = tn0 <= tf0 * TAKE_SLACK, h1 = tn1 <= tf1 * TAKE_SLACK;
+            const int32_t c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
+            if (h0 && h1) {
+                if (tn1 < tn0) { st.push(c0, tn0); node = c1; }
+                else { st.push(c1, tn1); node = c0; }
+            } else if (h0) {
+                node = c0;
+            } else if (h1) {
+                node = c1;
+            } else {
+                // pop, skipping entries that the current best hit has made unreachable
+                for (;;) {
+                    if (st.sp == 0) return;
+                    float tn;
+                    st.pop(node, tn);
+                    if (tn <= tbest_f * TAKE_SLACK) break;
+                }
+            }
+        }
+        // leaf: ~node = (first slot << 3) | (count - 1)
+        {
+            const int32_t code = ~node;
+            const int64_t first = code >> 3;
+            const int count = (code & 7) + 1;
+            for (int k = 0; k < count; ++k) {
+                const double2 *T = sc.tris + 6 * (first + k);
+                const double2 a0 = __ldg(T), a1 = __ldg(T + 1), a2 = __ldg(T + 2), a3 = __ldg(T + 3), a4 = __ldg(T + 4),
+                              a5 = __ldg(T + 5);
+                if (COUNT) cnt->tri += 1;
+                double t, bu = 0, bv = 0;
+                bool ok;
+                if (a5.y == 0.0) {
+                    ok = hit_triangle(mk3(a0.x, a0.y, a1.x), mk3(a2.x, a2.y, a3.x), mk3(a4.x, a4.y, a5.x), o, d, tmin, best_t,
+                                      t, bu, bv);
+                } else {
+                    ok = hit_sphere(mk3(a0.x, a0.y, a1.x), a3.y, o, d, tmin, best_t, t);
+                }
+                if (ok) {
+                    const long long bits = __double_as_longlong(a1.y);
+                    const int32_t prim = (int32_t)(bits & 0xffffffffLL), rank = (int32_t)(bits >> 32);
+                    // min t; exact ties go to the primitive the reference's DFS reaches last (bvh.cpp:94-108)
+                    if (t < best_t || out.prim < 0 || rank > out.rank) {
+                        out.prim = prim; out.rank = rank; out.t = t; out.u = bu; out.v = bv;
+                        best_t = t;
+                        tbest_f = __double2float_ru(t);
+                        if (ANY_HIT) return;
+                    }
+                }
+            }
+        }
+        for (;;) {
+            if (st.sp == 0) return;
+            float tn;
+            st.pop(node, tn);
+            if (tn <= tbest_f * TAKE_SLACK) break;
+        }
+    }
+}
+
+}  // namespace take

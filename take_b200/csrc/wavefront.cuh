@@ -1,0 +1,622 @@
+// Wavefront path tracing: generate -> [extend -> sort-by-material -> shade -> shadow-connect] x bounces -> accumulate.
+// Replaces the per-pixel loop of src/render.cpp:59-82 and the integrators of src/integrator/path_tracing.h.
+//
+// A "wave" is a batch of path samples, one per slot.  Per-slot state lives in 32-byte-multiple records (one or two
+// full sectors per gathered access); queues are arrays of slot indices filled through warp-aggregated atomics.
+// All queue lengths stay on the device: each pass `b` owns its own counters (no resets, no host round trips), and the
+// traversal kernels are persistent -- warps pull batches of 32 queue entries until the queue is dry -- so a fixed
+// launch configuration serves every pass.
+#pragma once
+#include "shading.cuh"
+#include "traverse.cuh"
+
+namespace take {
+
+struct RayRec {  // 64 B : the extend ray of the slot (tmin is always c_EPSILON)
+    double ox, oy, oz, dx, dy, dz, tmax;
+    int32_t aux0, aux1;
+};
+struct HitRec {  // 32 B
+    int32_t prim;
+    uint32_t keyrank;  // sort key (4 bits) | rank inside the key's bin (28 bits)
+    double t, u, v;
+};
+struct PathRec {  // 64 B
+    double thr[3], rad[3];
+    uint32_t k;      // random_real draws consumed so far
+    int32_t depth;   // index of the next integrator loop iteration
+    int32_t flags;   // PEND_* describing the extend ray in flight
+    int32_t pad;
+};
+struct PendRec {  // 32 B : BSDF sample waiting for its extend ray (FG and pdf of src/integrator/path_tracing.h:70-73)
+    double fg[3], bpdf;
+};
+struct ShadowRec {  // 64 B : NEE connection waiting for its shadow ray (origin = RayRec.o)
+    double dx, dy, dz, tmax, cx, cy, cz, pad;
+};
+static_assert(sizeof(RayRec) == 64 && sizeof(HitRec) == 32 && sizeof(PathRec) == 64 && sizeof(PendRec) == 32 &&
+                  sizeof(ShadowRec) == 64, "record sizes");
+
+enum { PEND_PRIMARY = 0, PEND_BSDF = 1, PEND_LIGHT = 2, PEND_SPECULAR = 4 };
+
+#define TAKE_NBINS 16      // sort bins: 0 = miss, 1 + material type
+#define TAKE_MAX_PASSES 80
+
+struct PassCounters {  // one per pass, zeroed once per wave
+    uint32_t n_extend;          // entries in this pass's extend queue
+    uint32_t n_shadow;          // entries in this pass's shadow queue
+    uint32_t fetch_extend;      // persistent-kernel work cursors
+    uint32_t fetch_shadow;
+    uint32_t bins[TAKE_NBINS];  // histogram of sort keys
+    uint32_t pad[12];
+};
+static_assert(sizeof(PassCounters) == 128, "PassCounters");
+
+struct Totals {  // running totals over a render call
+    unsigned long long samples, extend_rays, shadow_rays, shaded, box_tests, tri_tests, miss_after_light_sample;
+    unsigned long long pad;
+};
+
+struct Wave {
+    RayRec *ray;
+    HitRec *hit;
+    PathRec *path;
+    PendRec *pend;
+    ShadowRec *shadow;
+    int32_t *q_extend[2];
+    int32_t *q_sorted;
+    int32_t *q_shadow;
+    PassCounters *pass;  // [TAKE_MAX_PASSES]
+    Totals *totals;
+    // slot -> (pixel, sample): slot = s_local * chunk_pixels + pixel_local, unless an explicit list is given
+    int32_t chunk_pixels, chunk_base;
+    int64_t sample0;
+    int32_t n_slots, samples_in_wave;
+    const int32_t *list_pixel;  // optional explicit (pixel, sample) list (take_gpu_radiance_samples)
+    const int64_t *list_sample;
+    int32_t integrator, max_depth, sort_enabled, pad0;
+    uint64_t seed;
+};
+
+__device__ __forceinline__ void slot_identity(const Wave &w, int slot, uint32_t &pixel, uint64_t &sample) {
+    if (w.list_pixel) {
+        pixel = (uint32_t)w.list_pixel[slot];
+        sample = (uint64_t)w.list_sample[slot];
+    } else {
+        pixel = (uint32_t)(w.chunk_base + slot % w.chunk_pixels);
+        sample = (uint64_t)(w.sample0 + slot / w.chunk_pixels);
+    }
+}
+
+// Append to a device queue with one atomic per warp: lanes that want to push are ranked with ballot/popc,
+// the first of them reserves the range, shfl broadcasts the base.
+__device__ __forceinline__ void queue_push(bool want, int32_t *queue, uint32_t *counter, int32_t value) {
+    const unsigned active = __activemask();
+    const unsigned mask = __ballot_sync(active, want);
+    if (mask == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(active, base, leader);
+    if (want) queue[base + __popc(mask & ((1u << lane) - 1u))] = value;
+}
+
+// ---- generate: src/render.cpp:65-75 -------------------------------------------------------------------
+__global__ void k_generate(DevScene sc, Wave w) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot == 0) w.pass[0].n_extend = (uint32_t)w.n_slots;
+    if (slot >= w.n_slots) return;
+    uint32_t pixel;
+    uint64_t sample;
+    slot_identity(w, slot, pixel, sample);
+    const int col = (int)(pixel % (uint32_t)sc.width), row = (int)(pixel / (uint32_t)sc.width);
+    const int x = col, y = sc.height - 1 - row;  // the reference's y-up loop variable; image row = H - y - 1
+    Rng rng = {w.seed, sample, pixel, 0};
+    const double jx = rng.next();
+    const double jy = rng.next();
+    D3 dir = sub(add(mul(mul(sc.cam_u, (x + jx) / sc.width - 0.5), sc.viewport_w),
+                     mul(mul(sc.cam_v, (y + jy) / sc.height - 0.5), sc.viewport_h)),
+                 sc.cam_w);
+    dir = normalize(dir);
+    RayRec r;
+    r.ox = sc.lookfrom.x; r.oy = sc.lookfrom.y; r.oz = sc.lookfrom.z;
+    r.dx = dir.x; r.dy = dir.y; r.dz = dir.z;
+    r.tmax = INFINITY;
+    r.aux0 = r.aux1 = 0;
+    w.ray[slot] = r;
+    PathRec p;
+    p.thr[0] = p.thr[1] = p.thr[2] = 1.0;
+    p.rad[0] = p.rad[1] = p.rad[2] = 0.0;
+    p.k = rng.k;
+    p.depth = 0;
+    p.flags = PEND_PRIMARY;
+    p.pad = 0;
+    w.path[slot] = p;
+    w.q_extend[0][slot] = slot;
+}
+
+// ---- extend: closest hit for every queued ray + histogram of the shading sort key ------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_extend(DevScene sc, Wave w, int pass) {
+    __shared__ int32_t s_node[TAKE_STACK_SMEM * 128];
+    __shared__ float s_tn[TAKE_STACK_SMEM * 128];
+    TravStack st;
+    st.s_node = s_node + threadIdx.x;
+    st.s_tn = s_tn + threadIdx.x;
+    st.stride = 128;
+    PassCounters &pc = w.pass[pass];
+    const uint32_t n = pc.n_extend;
+    const int32_t *queue = w.q_extend[pass & 1];
+    const int lane = threadIdx.x & 31;
+    TravCounters cnt = {0, 0};
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&pc.fetch_extend, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        const bool valid = i < n;
+        int slot = -1;
+        uint32_t key = 0;
+        HitOut h;
+        if (valid) {
+            slot = queue[i];
+            const RayRec r = w.ray[slot];
+            trace_fast<false, COUNT>(sc, mk3(r.ox, r.oy, r.oz), mk3(r.dx, r.dy, r.dz), TAKE_EPS, r.tmax, st, h, &cnt);
+            key = h.prim < 0 ? 0u : 1u + (uint32_t)sc.prim_mtype[h.prim];
+        }
+        // warp-aggregated histogram: lanes with the same key elect a leader that bumps the bin once
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const unsigned peers = __match_any_sync(vmask, key);
+            const int leader = __ffs(peers) - 1;
+            uint32_t rbase = 0;
+            if (lane == leader) rbase = atomicAdd(&pc.bins[key], (uint32_t)__popc(peers));
+            rbase = __shfl_sync(peers, rbase, leader);
+            const uint32_t rank = rbase + __popc(peers & ((1u << lane) - 1u));
+            HitRec hr;
+            hr.prim = h.prim;
+            hr.keyrank = (key << 28) | rank;
+            hr.t = h.t; hr.u = h.u; hr.v = h.v;
+            w.hit[slot] = hr;
+        }
+    }
+    if (COUNT) {
+        atomicAdd(&w.totals->box_tests, cnt.box);
+        atomicAdd(&w.totals->tri_tests, cnt.tri);
+    }
+}
+
+// ---- sort: scatter slots into material-contiguous order ---------------------------------------------------
+__global__ void k_scatter(Wave w, int pass) {
+    __shared__ uint32_t offs[TAKE_NBINS];
+    const PassCounters &pc = w.pass[pass];
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int b = 0; b < TAKE_NBINS; ++b) { offs[b] = acc; acc += pc.bins[b]; }
+    }
+    __syncthreads();
+    const uint32_t n = pc.n_extend;
+    const int32_t *queue = w.q_extend[pass & 1];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int slot = queue[i];
+        const uint32_t kr = w.hit[slot].keyrank;
+        w.q_sorted[offs[kr >> 28] + (kr & 0x0fffffffu)] = slot;
+    }
+}
+
+// ---- shade -----------------------------------------------------------------------------------------------
+struct ShadeCtx {
+    const DevScene &sc;
+    const Wave &w;
+    int slot, pass;
+    D3 thr, rad;
+    Rng rng;
+    bool emit_extend, emit_shadow;
+    D3 org;        // origin of the rays leaving this vertex (v.pos)
+    D3 ext_dir;    // extend ray
+    D3 sh_dir, sh_contrib;
+    double sh_tmax;
+    D3 pend_fg;
+    double pend_pdf;
+    int pend_flags;
+    int depth;
+    int shaded;    // integrator loop iterations entered (statistics)
+};
+
+// NEE light-sample geometry shared by the integrators: path_tracing.h:31-43 / :189-200.
+// Returns false when the reference `break`s (light_pdf <= 0).
+__device__ __forceinline__ bool nee_sample(const DevScene &sc, const TakeLightDesc &l, int light_id, const Isect &v, Rng &rng,
+                                           D3 &light_dir, double &dist, double &lpdf) {
+    D3 lp, ln;
+    sample_on_prim(sc, l.prim_id, v.pos, rng, lp, ln);
+    dist = length(sub(lp, v.pos));
+    light_dir = normalize(sub(lp, v.pos));
+    lpdf = light_pdf_area(sc, light_id, lp, v.pos) * (dist * dist) / (fmax(dot(neg(ln), light_dir), 0.0) * sc.num_lights);
+    return !(lpdf <= 0);
+}
+
+// light pdf of a BSDF-sampled hit on an emitter: path_tracing.h:88-96 / :255-263
+__device__ __forceinline__ bool hit_light_pdf(const DevScene &sc, const Isect &nv, D3 prev_pos, double &lpdf) {
+    double d = length(sub(nv.pos, prev_pos));
+    D3 light_dir = normalize(sub(nv.pos, prev_pos));
+    lpdf = light_pdf_area(sc, nv.light, nv.pos, prev_pos) * (d * d) / (fmax(dot(neg(nv.gn), light_dir), 0.0) * sc.num_lights);
+    return !(lpdf <= 0);
+}
+
+// Multi-sample MIS: src/integrator/path_tracing.h:5-111.  One call = "finish iteration depth-1 with the hit that
+// just arrived, then run iteration depth up to the point where it needs rays".
+__device__ inline void shade_mis(ShadeCtx &c, const RayRec &ray, const HitRec &hit, const PathRec &path) {
+    const DevScene &sc = c.sc;
+    const D3 o = mk3(ray.ox, ray.oy, ray.oz), d = mk3(ray.dx, ray.dy, ray.dz);
+    Isect v;
+    if (path.flags == PEND_PRIMARY) {
+        if (hit.prim < 0) { c.rad = sc.background; return; }  // :8
+        fill_isect(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
+        if (v.light != -1 && sc.lights[v.light].kind == TAKE_LIGHT_AREA)  // :14-18
+            c.rad = add(c.rad, mulv(c.thr, light_intensity(sc.lights[v.light])));
+    } else {
+        const PendRec pend = c.w.pend[c.slot];
+        const D3 FG = mk3(pend.fg[0], pend.fg[1], pend.fg[2]);
+        const double bpdf = pend.bpdf;
+        const bool spec = (path.flags & PEND_SPECULAR) != 0;
+        if (hit.prim < 0) {  // :82-87
+            c.thr = mulv(c.thr, divs(FG, bpdf));
+            c.rad = add(c.rad, mulv(c.thr, sc.background));
+            return;
+        }
+        fill_isect(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
+        if (v.light != -1) {  // :88-101
+            double lpdf;
+            if (!hit_light_pdf(sc, v, o, lpdf)) return;
+            const TakeLightDesc &l = sc.lights[v.light];
+            if (l.kind == TAKE_LIGHT_AREA) {
+                D3 C2 = mul(mulv(FG, light_intensity(l)), spec ? (1 / bpdf) : (bpdf / (lpdf * lpdf + bpdf * bpdf)));
+                c.rad = add(c.rad, mulv(c.thr, C2));
+            }
+        }
+        c.thr = mulv(c.thr, divs(FG, bpdf));  // :107
+    }
+    if (c.depth > c.w.max_depth) return;  // loop bound :20
+    c.shaded += 1;
+    const D3 dir_in = neg(d);
+    const TakeMaterialDesc &m = sc.materials[v.material];
+    const bool spec = is_specular(m.type);
+    c.org = v.pos;
+    if (sc.num_lights > 0 && !spec) {  // :30-59
+        const int light_id = (int)floor(c.rng.next() * sc.num_lights);
+        const TakeLightDesc &l = sc.lights[light_id];
+        if (l.kind == TAKE_LIGHT_AREA) {
+            D3 light_dir;
+            double dist, lpdf;
+            if (!nee_sample(sc, l, light_id, v, c.rng, light_dir, dist, lpdf)) return;
+            const double bpdf = bsdf_pdf(m, dir_in, light_dir, v);
+            if (bpdf > 0 && !isinf(lpdf)) {
+                D3 FG = bsdf_eval(sc, m, dir_in, light_dir, 0.0, v);
+                D3 C1 = divs(mul(mulv(FG, light_intensity(l)), lpdf), lpdf * lpdf + bpdf * bpdf);
+                c.emit_shadow = true;
+                c.sh_dir = light_dir;
+                c.sh_tmax = (1 - TAKE_EPS) * dist;
+                c.sh_contrib = mulv(c.thr, C1);
+            }
+        }
+    }
+    D3 rec_dir;
+    double rec_pdf;
+    if (!sample_bsdf(m, dir_in, v, c.rng, rec_dir, rec_pdf)) return;  // :65-69
+    c.pend_fg = bsdf_eval(sc, m, dir_in, rec_dir, rec_pdf, v);
+    c.ext_dir = normalize(rec_dir);
+    c.pend_pdf = rec_pdf;
+    if (rec_pdf <= 0) return;  // :75-78
+    c.pend_flags = PEND_BSDF | (spec ? PEND_SPECULAR : 0);
+    c.emit_extend = true;
+    c.depth += 1;
+}
+
+// No MIS: src/integrator/path_tracing.h:114-157
+__device__ inline void shade_raw(ShadeCtx &c, const RayRec &ray, const HitRec &hit, const PathRec &path) {
+    const DevScene &sc = c.sc;
+    const D3 o = mk3(ray.ox, ray.oy, ray.oz), d = mk3(ray.dx, ray.dy, ray.dz);
+    if (hit.prim < 0) {
+        if (path.flags == PEND_PRIMARY) c.rad = sc.background;         // :117
+        else c.rad = add(c.rad, mulv(c.thr, sc.background));            // :148-152 (throughput already updated, :145)
+        return;
+    }
+    Isect v;
+    fill_isect(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
+    if (c.depth > c.w.max_depth) return;
+    if (v.light != -1) {  // :123-129
+        if (sc.lights[v.light].kind == TAKE_LIGHT_AREA) c.rad = add(c.rad, mulv(c.thr, light_intensity(sc.lights[v.light])));
+        return;
+    }
+    c.shaded += 1;
+    const D3 dir_in = neg(d);
+    const TakeMaterialDesc &m = sc.materials[v.material];
+    D3 rec_dir;
+    double pdf;
+    if (!sample_bsdf(m, dir_in, v, c.rng, rec_dir, pdf)) return;
+    D3 FG = bsdf_eval(sc, m, dir_in, rec_dir, pdf, v);
+    c.ext_dir = normalize(rec_dir);
+    if (pdf <= 0) return;
+    c.thr = mulv(c.thr, divs(FG, pdf));
+    c.org = v.pos;
+    c.pend_fg = FG;
+    c.pend_pdf = pdf;
+    c.pend_flags = PEND_BSDF;
+    c.emit_extend = true;
+    c.depth += 1;
+}
+
+// One-sample MIS: src/integrator/path_tracing.h:161-271
+__device__ inline void shade_one_sample(ShadeCtx &c, const RayRec &ray, const HitRec &hit, const PathRec &path) {
+    const DevScene &sc = c.sc;
+    const D3 o = mk3(ray.ox, ray.oy, ray.oz), d = mk3(ray.dx, ray.dy, ray.dz);
+    const int nl = sc.num_lights;
+    Isect v;
+    if (path.flags == PEND_PRIMARY) {
+        if (hit.prim < 0) { c.rad = sc.background; return; }
+        fill_isect(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
+    } else if (path.flags & PEND_LIGHT) {
+        if (hit.prim < 0) {
+            // the reference dereferences an empty optional here (:220, undefined behaviour): terminate and count
+            atomicAdd(&c.w.totals->miss_after_light_sample, 1ULL);
+            return;
+        }
+        fill_isect(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
+    } else {
+        const PendRec pend = c.w.pend[c.slot];
+        const D3 FG = mk3(pend.fg[0], pend.fg[1], pend.fg[2]);
+        const bool spec = (path.flags & PEND_SPECULAR) != 0;
+        double pdf = (nl == 0 || spec) ? pend.bpdf : 0.5 * pend.bpdf;  // :245
+        if (hit.prim < 0) {  // :247-252
+            c.thr = mulv(c.thr, divs(FG, pdf));
+            c.rad = add(c.rad, mulv(c.thr, sc.background));
+            return;
+        }
+        fill_isect(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
+        if (!spec && v.light != -1) {  // :253-265
+            double lpdf;
+            if (!hit_light_pdf(sc, v, o, lpdf)) return;
+            pdf += 0.5 * lpdf;
+        }
+        c.thr = mulv(c.thr, divs(FG, pdf));
+    }
+    const D3 dir_in = neg(d);
+    for (; c.depth <= c.w.max_depth; c.depth += 1) {
+        if (v.light != -1 && sc.lights[v.light].kind == TAKE_LIGHT_AREA) {  // :170-177
+            c.rad = add(c.rad, mulv(c.thr, light_intensity(sc.lights[v.light])));
+            return;
+        }
+        c.shaded += 1;
+        const TakeMaterialDesc &m = sc.materials[v.material];
+        const bool spec = is_specular(m.type);
+        c.org = v.pos;
+        if (nl > 0 && !spec && c.rng.next() <= 0.5) {  // :187
+            const int light_id = (int)floor(c.rng.next() * nl);
+            const TakeLightDesc &l = sc.lights[light_id];
+            if (l.kind != TAKE_LIGHT_AREA) continue;  // a point light: the iteration does nothing (:190)
+            D3 light_dir;
+            double dist, lpdf;
+            if (!nee_sample(sc, l, light_id, v, c.rng, light_dir, dist, lpdf)) return;
+            const double bpdf = bsdf_pdf(m, dir_in, light_dir, v);
+            if (bpdf <= 0) return;
+            D3 FG = bsdf_eval(sc, m, dir_in, light_dir, 0.0, v);
+            c.thr = mulv(c.thr, divs(FG, 0.5 * lpdf + 0.5 * bpdf));  // :225
+            c.ext_dir = light_dir;
+            c.pend_fg = FG;
+            c.pend_pdf = bpdf;
+            c.pend_flags = PEND_LIGHT;
+            c.emit_extend = true;
+            c.depth += 1;
+            return;
+        }
+        D3 rec_dir;
+        double rec_pdf;
+        if (!sample_bsdf(m, dir_in, v, c.rng, rec_dir, rec_pdf)) return;
+        c.pend_fg = bsdf_eval(sc, m, dir_in, rec_dir, rec_pdf, v);
+        c.ext_dir = normalize(rec_dir);
+        c.pend_pdf = rec_pdf;
+        if (rec_pdf <= 0) return;
+        c.pend_flags = PEND_BSDF | (spec ? PEND_SPECULAR : 0);
+        c.emit_extend = true;
+        c.depth += 1;
+        return;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_shade(DevScene sc, Wave w, int pass) {
+    PassCounters &pc = w.pass[pass];
+    const uint32_t n = pc.n_extend;
+    const int32_t *queue = w.sort_enabled ? w.q_sorted : w.q_extend[pass & 1];
+    int32_t *q_next = w.q_extend[(pass + 1) & 1];
+    // grid-stride with whole warps, so that the queue pushes below always see converged warps
+    const uint32_t n_round = (n + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        const bool valid = i < n;
+        bool emit_extend = false, emit_shadow = false;
+        int slot = -1, shaded = 0;
+        if (valid) {
+            slot = queue[i];
+            const RayRec ray = w.ray[slot];
+            const HitRec hit = w.hit[slot];
+            const PathRec path = w.path[slot];
+            uint32_t pixel;
+            uint64_t sample;
+            slot_identity(w, slot, pixel, sample);
+            ShadeCtx c = {sc, w, slot, pass};
+            c.thr = mk3(path.thr[0], path.thr[1], path.thr[2]);
+            c.rad = mk3(path.rad[0], path.rad[1], path.rad[2]);
+            c.rng.seed = w.seed; c.rng.sample = sample; c.rng.pixel = pixel; c.rng.k = path.k;
+            c.emit_extend = c.emit_shadow = false;
+            c.depth = path.depth;
+            c.pend_flags = 0;
+            c.shaded = 0;
+            c.org = mk3(ray.ox, ray.oy, ray.oz);
+            if (w.integrator == TAKE_INTEGRATOR_MIS) shade_mis(c, ray, hit, path);
+            else if (w.integrator == TAKE_INTEGRATOR_RAW) shade_raw(c, ray, hit, path);
+            else shade_one_sample(c, ray, hit, path);
+            emit_extend = c.emit_extend;
+            emit_shadow = c.emit_shadow;
+            shaded = c.shaded;
+            PathRec p;
+            p.thr[0] = c.thr.x; p.thr[1] = c.thr.y; p.thr[2] = c.thr.z;
+            p.rad[0] = c.rad.x; p.rad[1] = c.rad.y; p.rad[2] = c.rad.z;
+            p.k = c.rng.k;
+            p.depth = c.depth;
+            p.flags = c.pend_flags;
+            p.pad = 0;
+            w.path[slot] = p;
+            if (emit_extend || emit_shadow) {
+                RayRec r;
+                r.ox = c.org.x; r.oy = c.org.y; r.oz = c.org.z;
+                r.dx = c.ext_dir.x; r.dy = c.ext_dir.y; r.dz = c.ext_dir.z;
+                r.tmax = INFINITY;
+                r.aux0 = r.aux1 = 0;
+                w.ray[slot] = r;
+            }
+            if (emit_extend) {
+                PendRec pe;
+                pe.fg[0] = c.pend_fg.x; pe.fg[1] = c.pend_fg.y; pe.fg[2] = c.pend_fg.z;
+                pe.bpdf = c.pend_pdf;
+                w.pend[slot] = pe;
+            }
+            if (emit_shadow) {
+                ShadowRec s;
+                s.dx = c.sh_dir.x; s.dy = c.sh_dir.y; s.dz = c.sh_dir.z;
+                s.tmax = c.sh_tmax;
+                s.cx = c.sh_contrib.x; s.cy = c.sh_contrib.y; s.cz = c.sh_contrib.z;
+                s.pad = 0;
+                w.shadow[slot] = s;
+            }
+        }
+        queue_push(emit_extend, q_next, &w.pass[pass + 1].n_extend, slot);
+        queue_push(emit_shadow, w.q_shadow, &pc.n_shadow, slot);
+        shaded = __reduce_add_sync(0xffffffffu, shaded);
+        if ((threadIdx.x & 31) == 0 && shaded) atomicAdd(&w.totals->shaded, (unsigned long long)shaded);
+    }
+}
+
+// ---- shadow-connect: any-hit query; unoccluded connections add throughput * C1 (path_tracing.h:53-60) ----------
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_shadow(DevScene sc, Wave w, int pass) {
+    __shared__ int32_t s_node[TAKE_STACK_SMEM * 128];
+    __shared__ float s_tn[TAKE_STACK_SMEM * 128];
+    TravStack st;
+    st.s_node = s_node + threadIdx.x;
+    st.s_tn = s_tn + threadIdx.x;
+    st.stride = 128;
+    PassCounters &pc = w.pass[pass];
+    const uint32_t n = pc.n_shadow;
+    const int lane = threadIdx.x & 31;
+    TravCounters cnt = {0, 0};
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&pc.fetch_shadow, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        if (i < n) {
+            const int slot = w.q_shadow[i];
+            const RayRec r = w.ray[slot];
+            const ShadowRec s = w.shadow[slot];
+            HitOut h;
+            trace_fast<true, COUNT>(sc, mk3(r.ox, r.oy, r.oz), mk3(s.dx, s.dy, s.dz), TAKE_EPS, s.tmax, st, h, &cnt);
+            if (h.prim < 0) {
+                PathRec *p = w.path + slot;
+                p->rad[0] += s.cx; p->rad[1] += s.cy; p->rad[2] += s.cz;
+            }
+        }
+    }
+    if (COUNT) {
+        atomicAdd(&w.totals->box_tests, cnt.box);
+        atomicAdd(&w.totals->tri_tests, cnt.tri);
+    }
+}
+
+// ---- accumulate: per pixel, add the wave's samples in ascending sample order (src/render.cpp:67-78) ------------
+__global__ void k_accumulate(Wave w, double *sum, double *sumsq, int n_passes) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0) {
+        unsigned long long ext = 0, sh = 0;
+        for (int b = 0; b < n_passes; ++b) { ext += w.pass[b].n_extend; sh += w.pass[b].n_shadow; }
+        atomicAdd(&w.totals->extend_rays, ext);
+        atomicAdd(&w.totals->shadow_rays, sh);
+        atomicAdd(&w.totals->samples, (unsigned long long)w.n_slots);
+    }
+    if (p >= w.chunk_pixels) return;
+    const size_t o = 3 * (size_t)(w.chunk_base + p);
+    double a0 = sum[o], a1 = sum[o + 1], a2 = sum[o + 2];
+    double b0 = 0, b1 = 0, b2 = 0;
+    if (sumsq) { b0 = sumsq[o]; b1 = sumsq[o + 1]; b2 = sumsq[o + 2]; }
+    for (int s = 0; s < w.samples_in_wave; ++s) {
+        const PathRec *pr = w.path + ((size_t)s * w.chunk_pixels + p);
+        const double r0 = pr->rad[0], r1 = pr->rad[1], r2 = pr->rad[2];
+        a0 += r0; a1 += r1; a2 += r2;
+        b0 += r0 * r0; b1 += r1 * r1; b2 += r2 * r2;
+    }
+    sum[o] = a0; sum[o + 1] = a1; sum[o + 2] = a2;
+    if (sumsq) { sumsq[o] = b0; sumsq[o + 1] = b1; sumsq[o + 2] = b2; }
+}
+
+// explicit-list mode: radiance of each slot
+__global__ void k_gather_radiance(Wave w, double *out, int n_passes) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s == 0) {
+        unsigned long long ext = 0, sh = 0;
+        for (int b = 0; b < n_passes; ++b) { ext += w.pass[b].n_extend; sh += w.pass[b].n_shadow; }
+        atomicAdd(&w.totals->extend_rays, ext);
+        atomicAdd(&w.totals->shadow_rays, sh);
+        atomicAdd(&w.totals->samples, (unsigned long long)w.n_slots);
+    }
+    if (s >= w.n_slots) return;
+    out[3 * (size_t)s] = w.path[s].rad[0];
+    out[3 * (size_t)s + 1] = w.path[s].rad[1];
+    out[3 * (size_t)s + 2] = w.path[s].rad[2];
+}
+
+// ---- direct intersection entry points (take_gpu_intersect / take_gpu_occluded) -------------------------------
+template <bool ANY_HIT>
+__global__ void __launch_bounds__(128) k_intersect_fast(DevScene sc, const TakeRay *rays, int64_t n, TakeHit *hits, uint8_t *occ,
+                                                        uint32_t *fetch) {
+    __shared__ int32_t s_node[TAKE_STACK_SMEM * 128];
+    __shared__ float s_tn[TAKE_STACK_SMEM * 128];
+    TravStack st;
+    st.s_node = s_node + threadIdx.x;
+    st.s_tn = s_tn + threadIdx.x;
+    st.stride = 128;
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(fetch, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if ((int64_t)base >= n) break;
+        const int64_t i = (int64_t)base + lane;
+        if (i < n) {
+            const TakeRay r = rays[i];
+            HitOut h;
+            trace_fast<ANY_HIT, false>(sc, mk3(r.origin[0], r.origin[1], r.origin[2]), mk3(r.dir[0], r.dir[1], r.dir[2]), r.tmin,
+                                       r.tmax, st, h, nullptr);
+            if (ANY_HIT) {
+                occ[i] = h.prim >= 0 ? 1 : 0;
+            } else {
+                TakeHit o;
+                o.prim_id = h.prim; o.pad = 0; o.t = h.t; o.u = h.u; o.v = h.v;
+                hits[i] = o;
+            }
+        }
+    }
+}
+
+__global__ void k_intersect_exact(DevScene sc, const TakeRay *rays, int64_t n, TakeHit *hits) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const TakeRay r = rays[i];
+    HitOut h;
+    trace_exact(sc, mk3(r.origin[0], r.origin[1], r.origin[2]), mk3(r.dir[0], r.dir[1], r.dir[2]), r.tmin, r.tmax, h);
+    TakeHit o;
+    o.prim_id = h.prim; o.pad = 0; o.t = h.t; o.u = h.u; o.v = h.v;
+    hits[i] = o;
+}
+
+}  // namespace take
