@@ -195,6 +195,16 @@ void *take_gpu_scene_stream(TakeScene *scene);
  * number of fast-tree nodes, SM count of the device. */
 int take_gpu_scene_info(TakeScene *scene, double *out);
 
+/* Host-only diagnostics: build exactly the acceleration structures take_gpu_scene_create would upload, without
+ * touching CUDA, and copy them out for inspection (tests/test_bvh_host.py).  Layouts are documented in
+ * take_b200/csrc/bvh_build.h. */
+typedef struct TakeHostBuild TakeHostBuild;
+int take_gpu_host_build(const TakeSceneDesc *desc, TakeHostBuild **out);
+int take_gpu_host_build_info(TakeHostBuild *h, double *out8);
+int take_gpu_host_build_copy(TakeHostBuild *h, void *ref_nodes, int32_t *dfs_rank, void *fast_nodes, int32_t *leaf_prims,
+                             double *leaf_records);
+int take_gpu_host_build_free(TakeHostBuild *h);
+
 const char *take_gpu_last_error(void);
 const char *take_gpu_version(void);
 

@@ -204,3 +204,39 @@ def render(params, device: int = 0, integrator: str = "mis", seed: int = 0) -> n
     finally:
         scene.close()
     return s / float(flat.spp)
+
+
+# ---- host-only diagnostics -------------------------------------------------------------------------------
+REF_NODE_DTYPE = np.dtype([("lo", "<f8", 3), ("hi", "<f8", 3), ("left", "<i4"), ("right", "<i4"), ("prim", "<i4"), ("pad", "<i4")])
+FAST_NODE_DTYPE = np.dtype([("c0lox", "<f4"), ("c0hix", "<f4"), ("c0loy", "<f4"), ("c0hiy", "<f4"),
+                            ("c1lox", "<f4"), ("c1hix", "<f4"), ("c1loy", "<f4"), ("c1hiy", "<f4"),
+                            ("c0loz", "<f4"), ("c0hiz", "<f4"), ("c1loz", "<f4"), ("c1hiz", "<f4"),
+                            ("child0", "<i4"), ("child1", "<i4"), ("count0", "<i4"), ("count1", "<i4")])
+assert REF_NODE_DTYPE.itemsize == 64 and FAST_NODE_DTYPE.itemsize == 64
+
+
+def host_build(flat: FlatScene) -> dict:
+    """The acceleration structures take_gpu_scene_create would upload, built on the host only (no CUDA needed)."""
+    L = load_library()
+    L.take_gpu_host_build.argtypes = [C.POINTER(TakeSceneDesc), C.POINTER(C.c_void_p)]
+    L.take_gpu_host_build_info.argtypes = [C.c_void_p, C.c_void_p]
+    L.take_gpu_host_build_copy.argtypes = [C.c_void_p] * 6
+    L.take_gpu_host_build_free.argtypes = [C.c_void_p]
+    desc = flat.to_desc()
+    h = C.c_void_p()
+    _check(L.take_gpu_host_build(C.byref(desc), C.byref(h)))
+    try:
+        info = (C.c_double * 8)()
+        _check(L.take_gpu_host_build_info(h, info))
+        n_ref, root, n_fast, n_prims, depth = (int(info[i]) for i in range(5))
+        ref = np.zeros(n_ref, REF_NODE_DTYPE)
+        rank = np.zeros(n_prims, np.int32)
+        fast = np.zeros(n_fast, FAST_NODE_DTYPE)
+        leaf = np.zeros(n_prims, np.int32)
+        recs = np.zeros((n_prims, 12), np.float64)
+        _check(L.take_gpu_host_build_copy(h, ref.ctypes.data, rank.ctypes.data, fast.ctypes.data, leaf.ctypes.data,
+                                          recs.ctypes.data))
+    finally:
+        L.take_gpu_host_build_free(h)
+    return dict(ref_nodes=ref, ref_root=root, dfs_rank=rank, fast_nodes=fast, leaf_prims=leaf, leaf_records=recs,
+                depth=depth, abs_max=float(info[5]), ms_ref=float(info[6]), ms_fast=float(info[7]))

@@ -130,6 +130,77 @@ int validate(const TakeSceneDesc *d) {
     return TAKE_OK;
 }
 
+struct HostBuild {
+    RefTree ref;
+    FastTree fast;
+    std::vector<double> tris;  // 12 doubles per leaf slot
+    double abs_max = 0, ms_ref = 0, ms_fast = 0;
+};
+
+// Everything scene_create does before touching CUDA: primitive boxes, both trees, leaf-ordered primitive records.
+int host_build(const TakeSceneDesc *d, int threads, HostBuild &hb) {
+    const int64_t n = d->num_prims;
+    // primitive boxes exactly as build_bvh (src/scene.cpp:4-23)
+    std::vector<Aabb> boxes((size_t)n);
+    double abs_max = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        Aabb &b = boxes[i];
+        const int32_t *id = d->indices + 3 * i;
+        if (d->prim_flags[i] & TAKE_PRIM_SPHERE) {
+            const double *sp = d->spheres + 4 * (int64_t)id[0];
+            for (int a = 0; a < 3; ++a) { b.lo[a] = sp[a] - sp[3]; b.hi[a] = sp[a] + sp[3]; }
+        } else {
+            const double *p0 = d->positions + 3 * (int64_t)id[0], *p1 = d->positions + 3 * (int64_t)id[1],
+                         *p2 = d->positions + 3 * (int64_t)id[2];
+            for (int a = 0; a < 3; ++a) {
+                b.lo[a] = std::min(std::min(p0[a], p1[a]), p2[a]);
+                b.hi[a] = std::max(std::max(p0[a], p1[a]), p2[a]);
+            }
+        }
+        for (int a = 0; a < 3; ++a) abs_max = std::max(abs_max, std::max(fabs(b.lo[a]), fabs(b.hi[a])));
+    }
+    hb.abs_max = abs_max;
+    RefTree &ref = hb.ref;
+    FastTree &fast = hb.fast;
+    double t0 = now_ms();
+    build_reference_tree(boxes.data(), n, threads, ref);
+    double t1 = now_ms();
+    const int max_leaf = std::min(8, std::max(1, env_int("TAKE_BVH_MAX_LEAF", 4)));
+    build_fast_tree(boxes.data(), n, max_leaf, 0.0f, threads, fast);
+    double t2 = now_ms();
+    hb.ms_ref = t1 - t0;
+    hb.ms_fast = t2 - t1;
+    if (fast.depth > TAKE_STACK_SMEM + TAKE_STACK_LOCAL)
+        return fail(TAKE_E_INVALID, "acceleration tree too deep (" + std::to_string(fast.depth) + ")");
+
+    // leaf-ordered FP64 primitive records: v0 | idbits | e1 | aux | e2 | kind
+    std::vector<double> &tris = hb.tris;
+    tris.assign((size_t)n * 12, 0.0);
+    for (int64_t slot = 0; slot < n; ++slot) {
+        const int32_t prim = fast.leaf_prims[slot];
+        double *T = tris.data() + 12 * slot;
+        const int32_t *id = d->indices + 3 * (int64_t)prim;
+        long long bits = ((long long)ref.dfs_rank[prim] << 32) | (long long)(uint32_t)prim;
+        memcpy(&T[3], &bits, 8);
+        if (d->prim_flags[prim] & TAKE_PRIM_SPHERE) {
+            const double *sp = d->spheres + 4 * (int64_t)id[0];
+            T[0] = sp[0]; T[1] = sp[1]; T[2] = sp[2];
+            T[4] = T[5] = T[6] = 0; T[7] = sp[3];
+            T[8] = T[9] = T[10] = 0; T[11] = 1.0;
+        } else {
+            const double *p0 = d->positions + 3 * (int64_t)id[0], *p1 = d->positions + 3 * (int64_t)id[1],
+                         *p2 = d->positions + 3 * (int64_t)id[2];
+            for (int a = 0; a < 3; ++a) {
+                T[a] = p0[a];
+                T[4 + a] = p1[a] - p0[a];  // e1 = v1 - v0, e2 = v2 - v0 (src/shape.cpp:53-54), computed once
+                T[8 + a] = p2[a] - p0[a];
+            }
+            T[7] = 0; T[11] = 0.0;
+        }
+    }
+    return TAKE_OK;
+}
+
 int ensure_wave(TakeScene *s, int64_t capacity) {
     if (capacity <= s->wave_capacity) return TAKE_OK;
     CU(s->ray.ensure(capacity * sizeof(RayRec)));
@@ -305,67 +376,17 @@ int take_gpu_scene_create(int device, const TakeSceneDesc *d, TakeScene **out) {
     cudaStream_t st = s->stream;
     const int threads = std::max(1u, std::thread::hardware_concurrency());
     const int64_t n = d->num_prims;
-
-    // primitive boxes exactly as build_bvh (src/scene.cpp:4-23)
-    std::vector<Aabb> boxes((size_t)n);
-    double abs_max = 0;
-    for (int64_t i = 0; i < n; ++i) {
-        Aabb &b = boxes[i];
-        const int32_t *id = d->indices + 3 * i;
-        if (d->prim_flags[i] & TAKE_PRIM_SPHERE) {
-            const double *sp = d->spheres + 4 * (int64_t)id[0];
-            for (int a = 0; a < 3; ++a) { b.lo[a] = sp[a] - sp[3]; b.hi[a] = sp[a] + sp[3]; }
-        } else {
-            const double *p0 = d->positions + 3 * (int64_t)id[0], *p1 = d->positions + 3 * (int64_t)id[1],
-                         *p2 = d->positions + 3 * (int64_t)id[2];
-            for (int a = 0; a < 3; ++a) {
-                b.lo[a] = std::min(std::min(p0[a], p1[a]), p2[a]);
-                b.hi[a] = std::max(std::max(p0[a], p1[a]), p2[a]);
-            }
-        }
-        for (int a = 0; a < 3; ++a) abs_max = std::max(abs_max, std::max(fabs(b.lo[a]), fabs(b.hi[a])));
-    }
-
-    RefTree ref;
-    FastTree fast;
-    double t0 = now_ms();
-    build_reference_tree(boxes.data(), n, threads, ref);
-    double t1 = now_ms();
-    const int max_leaf = std::min(8, std::max(1, env_int("TAKE_BVH_MAX_LEAF", 4)));
-    build_fast_tree(boxes.data(), n, max_leaf, 0.0f, threads, fast);
-    double t2 = now_ms();
-    s->build_ms_ref = t1 - t0;
-    s->build_ms_fast = t2 - t1;
+    HostBuild hb;
+    if (int rc = host_build(d, threads, hb)) return rc;
+    RefTree &ref = hb.ref;
+    FastTree &fast = hb.fast;
+    std::vector<double> &tris = hb.tris;
+    const double abs_max = hb.abs_max;
+    s->build_ms_ref = hb.ms_ref;
+    s->build_ms_fast = hb.ms_fast;
     s->fast_depth = fast.depth;
     s->sah_cost = fast.sah_cost;
     s->num_fast_nodes = (int64_t)fast.nodes.size();
-    if (fast.depth > TAKE_STACK_SMEM + TAKE_STACK_LOCAL)
-        return fail(TAKE_E_INVALID, "acceleration tree too deep (" + std::to_string(fast.depth) + ")");
-
-    // leaf-ordered FP64 primitive records: v0 | idbits | e1 | aux | e2 | kind
-    std::vector<double> tris((size_t)n * 12);
-    for (int64_t slot = 0; slot < n; ++slot) {
-        const int32_t prim = fast.leaf_prims[slot];
-        double *T = tris.data() + 12 * slot;
-        const int32_t *id = d->indices + 3 * (int64_t)prim;
-        long long bits = ((long long)ref.dfs_rank[prim] << 32) | (long long)(uint32_t)prim;
-        memcpy(&T[3], &bits, 8);
-        if (d->prim_flags[prim] & TAKE_PRIM_SPHERE) {
-            const double *sp = d->spheres + 4 * (int64_t)id[0];
-            T[0] = sp[0]; T[1] = sp[1]; T[2] = sp[2];
-            T[4] = T[5] = T[6] = 0; T[7] = sp[3];
-            T[8] = T[9] = T[10] = 0; T[11] = 1.0;
-        } else {
-            const double *p0 = d->positions + 3 * (int64_t)id[0], *p1 = d->positions + 3 * (int64_t)id[1],
-                         *p2 = d->positions + 3 * (int64_t)id[2];
-            for (int a = 0; a < 3; ++a) {
-                T[a] = p0[a];
-                T[4 + a] = p1[a] - p0[a];  // e1 = v1 - v0, e2 = v2 - v0 (src/shape.cpp:53-54), computed once
-                T[8 + a] = p2[a] - p0[a];
-            }
-            T[7] = 0; T[11] = 0.0;
-        }
-    }
     std::vector<uint8_t> mtype((size_t)n);
     for (int64_t i = 0; i < n; ++i) mtype[i] = (uint8_t)d->materials[d->prim_material[i]].type;
 
@@ -471,6 +492,46 @@ int take_gpu_scene_info(TakeScene *s, double *out) {
     if (!s || !out) return fail(TAKE_E_INVALID, "null argument");
     out[0] = s->build_ms_ref; out[1] = s->build_ms_fast; out[2] = s->fast_depth; out[3] = s->sah_cost;
     out[4] = (double)s->num_fast_nodes; out[5] = s->sm_count;
+    return TAKE_OK;
+}
+
+// ---- host-only diagnostics: the acceleration structures scene_create would upload, without touching CUDA ----
+struct TakeHostBuild {
+    HostBuild hb;
+};
+
+int take_gpu_host_build(const TakeSceneDesc *d, TakeHostBuild **out) {
+    if (!out) return fail(TAKE_E_INVALID, "null argument");
+    *out = nullptr;
+    if (int rc = validate(d)) return rc;
+    TakeHostBuild *h = new TakeHostBuild;
+    if (int rc = host_build(d, std::max(1u, std::thread::hardware_concurrency()), h->hb)) { delete h; return rc; }
+    *out = h;
+    return TAKE_OK;
+}
+// out[0..7] = #reference nodes, reference root, #fast nodes, #prims, fast depth, abs_max, build ms (ref), build ms (fast)
+int take_gpu_host_build_info(TakeHostBuild *h, double *out) {
+    if (!h || !out) return fail(TAKE_E_INVALID, "null argument");
+    out[0] = (double)h->hb.ref.nodes.size(); out[1] = h->hb.ref.root; out[2] = (double)h->hb.fast.nodes.size();
+    out[3] = (double)h->hb.fast.leaf_prims.size(); out[4] = h->hb.fast.depth; out[5] = h->hb.abs_max;
+    out[6] = h->hb.ms_ref; out[7] = h->hb.ms_fast;
+    return TAKE_OK;
+}
+// any pointer may be NULL.  ref_nodes: 64 B each (6 doubles box, 4 int32 left,right,prim,pad); fast_nodes: 64 B each
+// (12 floats, 4 int32); leaf_records: 12 doubles per slot.
+int take_gpu_host_build_copy(TakeHostBuild *h, void *ref_nodes, int32_t *dfs_rank, void *fast_nodes, int32_t *leaf_prims,
+                             double *leaf_records) {
+    if (!h) return fail(TAKE_E_INVALID, "null argument");
+    const HostBuild &b = h->hb;
+    if (ref_nodes) memcpy(ref_nodes, b.ref.nodes.data(), b.ref.nodes.size() * sizeof(RefNode));
+    if (dfs_rank) memcpy(dfs_rank, b.ref.dfs_rank.data(), b.ref.dfs_rank.size() * 4);
+    if (fast_nodes) memcpy(fast_nodes, b.fast.nodes.data(), b.fast.nodes.size() * sizeof(FastNode));
+    if (leaf_prims) memcpy(leaf_prims, b.fast.leaf_prims.data(), b.fast.leaf_prims.size() * 4);
+    if (leaf_records) memcpy(leaf_records, b.tris.data(), b.tris.size() * 8);
+    return TAKE_OK;
+}
+int take_gpu_host_build_free(TakeHostBuild *h) {
+    delete h;
     return TAKE_OK;
 }
 
