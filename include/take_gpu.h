@@ -142,7 +142,9 @@ typedef struct TakeRenderOpts {
 
 enum {
     TAKE_RENDER_DEFAULT = 0,
-    TAKE_RENDER_NO_SORT = 1 /* disable the per-bounce material sort (A/B measurements) */
+    TAKE_RENDER_NO_SORT = 1,     /* disable the per-bounce material sort (A/B measurements)                    */
+    TAKE_RENDER_STAGE_TIMES = 2, /* bracket every kernel with CUDA events and fill TakeStats::ms_<stage>       */
+    TAKE_RENDER_COUNT_TESTS = 4  /* run the instrumented traversal kernels and fill box_tests / tri_tests      */
 };
 
 typedef struct TakeStats {
@@ -150,11 +152,13 @@ typedef struct TakeStats {
     int64_t extend_rays;    /* closest-hit rays traced (primary + bounce)         */
     int64_t shadow_rays;    /* any-hit rays traced                                */
     int64_t shaded;         /* path vertices shaded                               */
-    int64_t box_tests;      /* filled only by the instrumented (TAKE_STATS) build */
-    int64_t tri_tests;
+    int64_t box_tests;      /* extend kernel: ray-box tests   (only with TAKE_RENDER_COUNT_TESTS) */
+    int64_t tri_tests;      /* extend kernel: leaf tests      (only with TAKE_RENDER_COUNT_TESTS) */
     int64_t kernel_launches;
     double ms_total;        /* device time of the whole call (CUDA events)        */
-    double ms_generate, ms_extend, ms_shade, ms_shadow, ms_sort, ms_other;
+    double ms_generate, ms_extend, ms_shade, ms_shadow, ms_sort, ms_other; /* only with TAKE_RENDER_STAGE_TIMES */
+    int64_t shadow_box_tests, shadow_tri_tests; /* shadow kernel (only with TAKE_RENDER_COUNT_TESTS) */
+    int64_t miss_after_light_sample; /* one-sample MIS: light-aimed rays that missed everything (reference: UB) */
 } TakeStats;
 
 typedef struct TakeScene TakeScene; /* opaque */

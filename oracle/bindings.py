@@ -91,11 +91,12 @@ class RefScene:
         self.lib.ref_occluded(self.h, _ptr(rays, np.float64), len(rays), _ptr(occ, np.uint8), threads)
         return occ
 
-    def render(self, integrator="mis", max_depth=5, spp_begin=0, spp_end=1, seed=0, threads=8, sumsq=True):
+    def render(self, integrator="mis", max_depth=5, spp_begin=0, spp_end=1, seed=0, threads=8, sumsq=True,
+               row_begin=0, row_step=1):
         s = np.zeros((self.height, self.width, 3), np.float64)
         s2 = np.zeros_like(s) if sumsq else None
         rc = self.lib.ref_render(self.h, INTEGRATORS[integrator], max_depth, spp_begin, spp_end, seed, threads,
-                                 _ptr(s, np.float64), _ptr(s2, np.float64))
+                                 _ptr(s, np.float64), _ptr(s2, np.float64), row_begin, row_step)
         if rc != 0:
             raise RuntimeError(self.lib.ref_last_error().decode())
         return s, s2
@@ -123,7 +124,7 @@ class RefLib:
         L.ref_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.ref_occluded.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
         L.ref_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_uint64, C.c_int,
-                                 C.c_void_p, C.c_void_p]
+                                 C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.ref_radiance_samples.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.ref_rng_selfcheck.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_int]
@@ -195,12 +196,12 @@ class OracleScene:
         return occ
 
     def render(self, integrator="mis", max_depth=5, spp_begin=0, spp_end=1, seed=0, threads=8, sumsq=True,
-               stats=False):
+               stats=False, row_begin=0, row_step=1):
         s = np.zeros((self.height, self.width, 3), np.float64)
         s2 = np.zeros_like(s) if sumsq else None
         st = np.zeros(6, np.int64)
         rc = self.lib.oracle_render(self.h, INTEGRATORS[integrator], max_depth, spp_begin, spp_end, seed, threads,
-                                    _ptr(s, np.float64), _ptr(s2, np.float64), _ptr(st, np.int64))
+                                    _ptr(s, np.float64), _ptr(s2, np.float64), _ptr(st, np.int64), row_begin, row_step)
         assert rc == 0
         return (s, s2, st) if stats else (s, s2)
 
@@ -237,7 +238,7 @@ class OracleLib:
         L.oracle_dfs_rank.argtypes = [vp, vp]
         L.oracle_intersect.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, i32]
         L.oracle_occluded.argtypes = [vp, vp, i64, vp, i32]
-        L.oracle_render.argtypes = [vp, i32, i32, i64, i64, u64, i32, vp, vp, vp]
+        L.oracle_render.argtypes = [vp, i32, i32, i64, i64, u64, i32, vp, vp, vp, i32, i32]
         L.oracle_radiance_samples.argtypes = [vp, i32, i32, u64, i64, vp, vp, vp, vp, i32]
         L.oracle_primary_rays.argtypes = [vp, u64, i64, vp, vp, vp, i32, vp]
         L.oracle_stream_real.restype = C.c_double

@@ -406,8 +406,10 @@ void ref_occluded(void *h, const double *rays, int64_t n, uint8_t *occ, int nthr
 // `integrator` (0 = path_tracing, 1 = path_tracing_raw, 2 = path_tracing_one_sample_MIS).
 // sum / sumsq: W*H*3 doubles in image layout (row 0 = top, as src/render.cpp:78 writes), accumulated
 // in ascending sample order starting from 0.  sumsq may be NULL.
+// Only image rows r (from the top) with r % row_step == row_begin are rendered (row_step = 1: all rows), which
+// gives bench.py a bounded, unbiased subsample of a frame.
 int ref_render(void *h, int integrator, int max_depth, int64_t spp_begin, int64_t spp_end, uint64_t seed,
-               int nthreads, double *sum, double *sumsq) {
+               int nthreads, double *sum, double *sumsq, int row_begin, int row_step) {
     Scene &sc = ((RefScene *)h)->scene;
     Integrator f = pick_integrator(integrator);
     if (!f) { g_error = "unknown integrator"; return -1; }
@@ -417,6 +419,7 @@ int ref_render(void *h, int integrator, int max_depth, int64_t spp_begin, int64_
     int nwords = stream_words_needed(max_depth);
     try {
         run_threads(nthreads, cam.height, [&](int64_t y) {
+            if (row_step > 1 && (cam.height - y - 1) % row_step != row_begin) return;
             for (int x = 0; x < cam.width; ++x) {
                 Vector3 acc{0, 0, 0}, acc2{0, 0, 0};
                 for (int64_t s = spp_begin; s < spp_end; ++s) {

@@ -922,8 +922,9 @@ void oracle_dfs_rank(void *h, int32_t *rank) {
 }
 
 // stats (optional): int64[6] = extend rays, shadow rays, shaded vertices, box tests, leaf tests, misses after a light sample
+// Only image rows r (from the top) with r % row_step == row_begin are rendered (row_step = 1: all rows).
 int oracle_render(void *h, int integrator, int max_depth, int64_t spp_begin, int64_t spp_end, uint64_t seed, int nthreads,
-                  double *sum, double *sumsq, int64_t *stats) {
+                  double *sum, double *sumsq, int64_t *stats, int row_begin, int row_step) {
     const Scene &sc = *(Scene *)h;
     Integrator f = pick(integrator);
     if (!f) return -1;
@@ -932,6 +933,7 @@ int oracle_render(void *h, int integrator, int max_depth, int64_t spp_begin, int
     std::vector<Counters> per_row(H);
     run_threads(nthreads, H, [&](int64_t y) {
         Counters cn;
+        if (row_step > 1 && (H - y - 1) % row_step != row_begin) return;
         for (int x = 0; x < W; ++x) {
             V3 acc = {0, 0, 0}, acc2 = {0, 0, 0};
             for (int64_t s = spp_begin; s < spp_end; ++s) {

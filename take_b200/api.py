@@ -23,7 +23,7 @@ LIB_PATH = os.path.join(_HERE, "libtake_gpu.so")
 
 INTEGRATORS = {"mis": 0, "raw": 1, "one_sample_mis": 2}
 ISECT_FAST, ISECT_EXACT = 0, 1
-RENDER_NO_SORT = 1
+RENDER_NO_SORT, RENDER_STAGE_TIMES, RENDER_COUNT_TESTS = 1, 2, 4
 
 EXPORTS = [
     "take_gpu_device_count", "take_gpu_scene_create", "take_gpu_scene_destroy", "take_gpu_intersect",
@@ -46,7 +46,8 @@ class TakeStats(C.Structure):
     _fields_ = [("samples", C.c_int64), ("extend_rays", C.c_int64), ("shadow_rays", C.c_int64), ("shaded", C.c_int64),
                 ("box_tests", C.c_int64), ("tri_tests", C.c_int64), ("kernel_launches", C.c_int64),
                 ("ms_total", C.c_double), ("ms_generate", C.c_double), ("ms_extend", C.c_double),
-                ("ms_shade", C.c_double), ("ms_shadow", C.c_double), ("ms_sort", C.c_double), ("ms_other", C.c_double)]
+                ("ms_shade", C.c_double), ("ms_shadow", C.c_double), ("ms_sort", C.c_double), ("ms_other", C.c_double),
+                ("shadow_box_tests", C.c_int64), ("shadow_tri_tests", C.c_int64), ("miss_after_light_sample", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

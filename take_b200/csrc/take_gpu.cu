@@ -337,6 +337,9 @@ void read_totals(TakeScene *s, TakeStats *stats, const StageTimer &tm, double ms
     stats->shaded = (int64_t)t.shaded;
     stats->box_tests = (int64_t)t.box_tests;
     stats->tri_tests = (int64_t)t.tri_tests;
+    stats->shadow_box_tests = (int64_t)t.shadow_box_tests;
+    stats->shadow_tri_tests = (int64_t)t.shadow_tri_tests;
+    stats->miss_after_light_sample = (int64_t)t.miss_after_light_sample;
     stats->kernel_launches = launches;
     stats->ms_total = ms_total;
     stats->ms_generate = tm.ms[ST_GENERATE];
@@ -601,9 +604,9 @@ int take_gpu_render_device(TakeScene *s, const TakeRenderOpts *o, double *d_sum,
     if (int rc = ensure_wave(s, capacity)) return rc;
     CU(cudaMemsetAsync(s->totals.p, 0, sizeof(Totals), s->stream));
     StageTimer tm;
-    tm.on = stats && env_int("TAKE_STAGE_TIMES", 0);
+    tm.on = stats && ((o->flags & TAKE_RENDER_STAGE_TIMES) || env_int("TAKE_STAGE_TIMES", 0));
     tm.stream = s->stream;
-    const bool count = env_int("TAKE_COUNT_TESTS", 0) != 0;
+    const bool count = (o->flags & TAKE_RENDER_COUNT_TESTS) || env_int("TAKE_COUNT_TESTS", 0) != 0;
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
@@ -623,7 +626,6 @@ int take_gpu_render_device(TakeScene *s, const TakeRenderOpts *o, double *d_sum,
             w.samples_in_wave = (int32_t)ns;
             w.n_slots = (int32_t)(cp * ns);
             if (int rc = launch_wave(s, w, o, d_sum, d_sumsq, nullptr, tm, count, launches)) return rc;
-            tm.collect();
         }
     }
     CU(cudaEventRecord(e1, s->stream));
@@ -632,6 +634,7 @@ int take_gpu_render_device(TakeScene *s, const TakeRenderOpts *o, double *d_sum,
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    tm.collect();
     read_totals(s, stats, tm, ms, launches);
     return TAKE_OK;
 }

@@ -54,7 +54,7 @@ static_assert(sizeof(PassCounters) == 128, "PassCounters");
 
 struct Totals {  // running totals over a render call
     unsigned long long samples, extend_rays, shadow_rays, shaded, box_tests, tri_tests, miss_after_light_sample;
-    unsigned long long pad;
+    unsigned long long shadow_box_tests, shadow_tri_tests, pad[7];
 };
 
 struct Wave {
@@ -529,8 +529,8 @@ __global__ void __launch_bounds__(128) k_shadow(DevScene sc, Wave w, int pass) {
         }
     }
     if (COUNT) {
-        atomicAdd(&w.totals->box_tests, cnt.box);
-        atomicAdd(&w.totals->tri_tests, cnt.tri);
+        atomicAdd(&w.totals->shadow_box_tests, cnt.box);
+        atomicAdd(&w.totals->shadow_tri_tests, cnt.tri);
     }
 }
 

@@ -61,7 +61,7 @@ class SceneBuilder:
         self.background = f32(background)
         self.materials = []   # (type, color|None, tex|None, params dict)
         self.textures = []    # (name, rgbe uint8 [h,w,4])
-        self.meshes = []      # dicts
+        self.meshes = []      # shapes in the order the reference would parse them: mesh dicts and sphere dicts
 
     # -- materials ----------------------------------------------------------------------------
     def material(self, mtype, color=(0.5, 0.5, 0.5), texture=None, uvscale=(1, 1), uvoffset=(0, 0), **params) -> int:
@@ -88,6 +88,12 @@ class SceneBuilder:
             normals=np.asarray(normals, dtype=np.float32).reshape(-1, 3),
             uvs=None if uvs is None else np.asarray(uvs, dtype=np.float32).reshape(-1, 2),
             material=int(material), radiance=None if radiance is None else f32(radiance)))
+        return len(self.meshes) - 1
+
+    def sphere(self, center, radius, material=0, radiance=None):
+        """<shape type="sphere"> (src/parse/parse_scene.cpp:785-808)."""
+        self.meshes.append(dict(sphere=True, center=f32(center), radius=float(f32(radius)), material=int(material),
+                                radiance=None if radiance is None else f32(radiance)))
         return len(self.meshes) - 1
 
     def quad(self, p0, p1, p2, p3, material=0, radiance=None, normal=None):
@@ -120,10 +126,22 @@ class SceneBuilder:
 
     # -- outputs ------------------------------------------------------------------------------
     def flat(self) -> FlatScene:
-        pos, nrm, uv, idx, pmat, plight, pflags, lights = [], [], [], [], [], [], [], []
+        pos, nrm, uv, idx, pmat, plight, pflags, lights, spheres = [], [], [], [], [], [], [], [], []
         base = 0
         n_prims = 0
         for m in self.meshes:
+            if m.get("sphere"):
+                idx.append(np.array([[len(spheres), 0, 0]], np.int32))
+                spheres.append([*m["center"], m["radius"]])
+                pmat.append(np.array([m["material"]], np.int32))
+                pflags.append(np.array([sio.PRIM_SPHERE], np.uint8))
+                if m["radiance"] is not None:
+                    plight.append(np.array([len(lights)], np.int32))
+                    lights.append((sio.LIGHT_AREA, n_prims, tuple(m["radiance"]), (0.0, 0.0, 0.0)))
+                else:
+                    plight.append(np.array([-1], np.int32))
+                n_prims += 1
+                continue
             nv, nf = len(m["positions"]), len(m["indices"])
             pos.append(m["positions"].astype(np.float64))
             nrm.append(ref_normalize(m["normals"].astype(np.float64)))
@@ -169,7 +187,7 @@ class SceneBuilder:
             self.width, self.height, self.lookfrom, self.lookat, self.up, self.vfov, self.background,
             cat(pos, (0, 3), np.float64), cat(nrm, (0, 3), np.float64), cat(uv, (0, 2), np.float64),
             cat(idx, (0, 3), np.int32), cat(pmat, (0,), np.int32), cat(plight, (0,), np.int32),
-            cat(pflags, (0,), np.uint8), np.zeros((0, 4)), mats,
+            cat(pflags, (0,), np.uint8), np.array(spheres, np.float64).reshape(-1, 4), mats,
             np.array(lights, dtype=sio.LIGHT_DTYPE) if lights else np.zeros(0, sio.LIGHT_DTYPE), textures,
             self.spp)._canon()
 
@@ -201,6 +219,14 @@ class SceneBuilder:
                 x.append(f'  <float name="{k}" value="{_fmt(v)}"/>')
             x.append('</bsdf>')
         for i, m in enumerate(self.meshes):
+            if m.get("sphere"):
+                c = m["center"]
+                x.append(f'<shape type="sphere"><point name="center" x="{_fmt(c[0])}" y="{_fmt(c[1])}" z="{_fmt(c[2])}"/>'
+                         f'<float name="radius" value="{_fmt(m["radius"])}"/><ref id="m{m["material"]}"/>')
+                if m["radiance"] is not None:
+                    x.append(f'  <emitter type="area"><rgb name="radiance" value="{_vec(m["radiance"])}"/></emitter>')
+                x.append('</shape>')
+                continue
             write_ply(os.path.join(directory, f"mesh{i}.ply"), m["positions"], m["indices"], m["normals"], m["uvs"])
             x.append(f'<shape type="ply"><string name="filename" value="mesh{i}.ply"/><ref id="m{m["material"]}"/>')
             if m["radiance"] is not None:
@@ -357,5 +383,68 @@ def multi_light(width=1920, height=1080, spp=1024, n_side=20, seed=3) -> SceneBu
     return b
 
 
+def _room(b, floor, ceiling, back, left, right):
+    b.quad((-1, 0, 1), (1, 0, 1), (1, 0, -1), (-1, 0, -1), floor)
+    b.quad((-1, 2, -1), (1, 2, -1), (1, 2, 1), (-1, 2, 1), ceiling)
+    b.quad((-1, 0, -1), (1, 0, -1), (1, 2, -1), (-1, 2, -1), back)
+    b.quad((-1, 0, 1), (-1, 0, -1), (-1, 2, -1), (-1, 2, 1), left)
+    b.quad((1, 0, -1), (1, 0, 1), (1, 2, 1), (1, 2, -1), right)
+
+
+def procedural_rgbe(w, h, kind="checker", seed=0) -> np.ndarray:
+    """Small procedural textures straight in RGBE bytes (exactly representable texels)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    out = np.zeros((h, w, 4), np.uint8)
+    if kind == "checker":
+        c = ((xx // max(1, w // 8) + yy // max(1, h // 8)) % 2).astype(bool)
+        out[..., 0] = np.where(c, 230, 40)
+        out[..., 1] = np.where(c, 200, 60)
+        out[..., 2] = np.where(c, 90, 150)
+    else:
+        out[..., :3] = rng.integers(30, 250, size=(h, w, 3))
+    out[..., 3] = 128  # mantissa * 2^-8  ->  values in (0, 1)
+    out[:, 0, 0] |= 1  # never (2, 2, <128) at a row start: keeps stb_image on its flat-decoding path
+    return out
+
+
+def textured_room(width=256, height=256, spp=16) -> SceneBuilder:
+    """Image textures on several BSDFs with non-trivial uv scale / offset (exercises the wrap-around column and
+    row of src/texture.cpp:13-24) -- the pinned part of config 3 (the environment map itself has no reference)."""
+    b = SceneBuilder(width, height, (0, 1, 3.8), (0, 1, 0), (0, 1, 0), 39.3, spp, (0.2, 0.25, 0.3))
+    t0 = b.texture_rgbe(procedural_rgbe(16, 16, "checker"))
+    t1 = b.texture_rgbe(procedural_rgbe(13, 7, "noise", seed=5))
+    floor = b.material(sio.MAT_DIFFUSE, texture=t0, uvscale=(3.7, 2.3), uvoffset=(0.31, 0.05))
+    back = b.material(sio.MAT_BLINN_MICROFACET, texture=t1, uvscale=(1.0, 1.0), uvoffset=(0.0, 0.0), exponent=40)
+    left = b.material(sio.MAT_PHONG, texture=t1, uvscale=(-2.5, 4.0), uvoffset=(0.5, 0.5), exponent=12)
+    right = b.material(sio.MAT_DISNEY_DIFFUSE, texture=t0, uvscale=(5.0, 5.0), uvoffset=(0.0, 0.0), roughness=0.4, subsurface=0.3)
+    white = b.material(sio.MAT_DIFFUSE, (0.73, 0.73, 0.73))
+    black = b.material(sio.MAT_DIFFUSE, (0, 0, 0))
+    plastic = b.material(sio.MAT_PLASTIC, texture=t0, uvscale=(2.0, 2.0), uvoffset=(0.0, 0.0), eta=1.5)
+    _room(b, floor, white, back, left, right)
+    b.quad((-0.25, 1.98, -0.25), (0.25, 1.98, -0.25), (0.25, 1.98, 0.25), (-0.25, 1.98, 0.25), black, radiance=(17, 12, 4))
+    b.box((-0.35, 0.6, -0.3), (0.3, 0.6, 0.3), 18, plastic)
+    b.box((0.35, 0.3, 0.35), (0.3, 0.3, 0.3), -17, floor)
+    return b
+
+
+def sphere_room(width=256, height=256, spp=16) -> SceneBuilder:
+    """Spheres (src/shape.cpp:13-42), including a spherical emitter (cone sampling, shape.cpp:125-144)."""
+    b = SceneBuilder(width, height, (0, 1, 3.8), (0, 1, 0), (0, 1, 0), 39.3, spp, (0.1, 0.1, 0.1))
+    white = b.material(sio.MAT_DIFFUSE, (0.73, 0.73, 0.73))
+    red = b.material(sio.MAT_DIFFUSE, (0.65, 0.05, 0.05))
+    green = b.material(sio.MAT_DIFFUSE, (0.12, 0.45, 0.15))
+    black = b.material(sio.MAT_DIFFUSE, (0, 0, 0))
+    mirror = b.material(sio.MAT_MIRROR, (0.9, 0.9, 0.9))
+    glossy = b.material(sio.MAT_BLINN_PHONG, (0.3, 0.5, 0.8), exponent=25)
+    _room(b, white, white, white, red, green)
+    b.sphere((0.0, 1.6, 0.0), 0.2, black, radiance=(20, 18, 15))
+    b.sphere((-0.45, 0.4, -0.2), 0.4, mirror)
+    b.sphere((0.45, 0.3, 0.3), 0.3, glossy)
+    b.quad((-0.2, 1.99, -0.7), (0.2, 1.99, -0.7), (0.2, 1.99, -0.4), (-0.2, 1.99, -0.4), black, radiance=(6, 8, 10))
+    return b
+
+
 def build(name: str, **kw) -> SceneBuilder:
-    return {"cornell": cornell_box, "heightfield": heightfield, "multi_light": multi_light}[name](**kw)
+    return {"cornell": cornell_box, "heightfield": heightfield, "multi_light": multi_light,
+            "textured": textured_room, "spheres": sphere_room}[name](**kw)

@@ -1,0 +1,175 @@
+"""Host-side checks that need no GPU: the C-ABI library loads, exports every symbol include/take_gpu.h declares, refuses
+to run without a device (no silent CPU path), and builds the acceleration structures the kernels rely on."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from take_b200 import api, scenes, sceneio
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "take_gpu.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(take_gpu_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(gpu_lib):
+    names = declared_functions()
+    assert len(names) >= 15
+    missing = [n for n in names if not hasattr(gpu_lib, n)]
+    assert missing == []
+    assert set(api.EXPORTS) <= set(names)
+    assert b"sm_100a" in gpu_lib.take_gpu_version()
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(sceneio.TakeCamera) == 8 + 10 * 8
+    assert sceneio.MAT_DTYPE.itemsize == 80 and sceneio.LIGHT_DTYPE.itemsize == 56
+    assert C.sizeof(api.TakeRenderOpts) == 40
+    assert C.sizeof(api.TakeStats) == 7 * 8 + 7 * 8 + 3 * 8
+    assert api.RAY_DTYPE.itemsize == 64 and api.HIT_DTYPE.itemsize == 32
+
+
+def _cuda_available():
+    try:
+        return api.device_count() > 0
+    except api.TakeGpuError:
+        return False
+
+
+def test_no_silent_cpu_fallback(gpu_lib):
+    """Without a CUDA device every compute entry point must fail loudly."""
+    if _cuda_available():
+        pytest.skip("a CUDA device is present")
+    flat = scenes.cornell_box(8, 8, 1).flat()
+    with pytest.raises(api.TakeGpuError):
+        api.GpuScene(flat)
+    with pytest.raises(api.TakeGpuError):
+        api.device_count()
+
+
+def test_invalid_scene_is_rejected(gpu_lib):
+    flat = scenes.cornell_box(8, 8, 1).flat()
+    flat.indices[3, 1] = 10 ** 6
+    with pytest.raises(api.TakeGpuError, match="vertex index"):
+        api.host_build(flat)
+    flat = scenes.cornell_box(8, 8, 1).flat()
+    flat.prim_material[0] = 99
+    with pytest.raises(api.TakeGpuError, match="material"):
+        api.host_build(flat)
+
+
+def test_reference_order_tree_matches_oracle(oracle_lib, small_scene):
+    name, _, flat = small_scene
+    hb = api.host_build(flat)
+    sc = oracle_lib.load(flat)
+    box, links, root = sc.bvh()
+    r = hb["ref_nodes"]
+    assert hb["ref_root"] == root
+    assert np.array_equal(np.concatenate([r["lo"], r["hi"]], axis=1), box)
+    assert np.array_equal(np.stack([r["left"], r["right"], r["prim"]], axis=1), links)
+    assert np.array_equal(hb["dfs_rank"], sc.dfs_rank())
+
+
+def _walk_fast_tree(hb):
+    """Returns per-node (first_slot, end_slot) of inner nodes and checks structural invariants."""
+    nodes, n_prims = hb["fast_nodes"], len(hb["leaf_prims"])
+    covered = np.zeros(n_prims, np.int32)
+    visited = np.zeros(len(nodes), bool)
+    stack = [0]
+    while stack:
+        i = stack.pop()
+        assert not visited[i]
+        visited[i] = True
+        for k in (0, 1):
+            c, cnt = int(nodes[i][f"child{k}"]), int(nodes[i][f"count{k}"])
+            lo = [nodes[i][f"c{k}lo{a}"] for a in "xyz"]
+            hi = [nodes[i][f"c{k}hi{a}"] for a in "xyz"]
+            if c >= 0:
+                assert cnt == 0
+                stack.append(c)
+            elif lo[0] <= hi[0]:           # a real leaf (empty children have inverted boxes)
+                code = ~c
+                first, count = code >> 3, (code & 7) + 1
+                assert count == cnt and 1 <= count <= 8
+                covered[first:first + count] += 1
+    assert visited.all()
+    assert (covered == 1).all()            # every leaf slot belongs to exactly one leaf
+    assert sorted(hb["leaf_prims"].tolist()) == list(range(n_prims))
+
+
+def test_fast_tree_structure(small_scene):
+    _, _, flat = small_scene
+    hb = api.host_build(flat)
+    _walk_fast_tree(hb)
+    # leaf records: slot 3 carries (rank << 32 | prim), e1 / e2 are exact differences of the FP64 vertices
+    recs, prims = hb["leaf_records"], hb["leaf_prims"]
+    bits = recs[:, 3].copy().view(np.int64)
+    assert np.array_equal((bits & 0xffffffff).astype(np.int32), prims)
+    assert np.array_equal((bits >> 32).astype(np.int32), hb["dfs_rank"][prims])
+    tri = (flat.prim_flags[prims] & sceneio.PRIM_SPHERE) == 0
+    idx = flat.indices[prims[tri]]
+    v0, v1, v2 = (flat.positions[idx[:, k]] for k in range(3))
+    assert np.array_equal(recs[tri, 0:3], v0)
+    assert np.array_equal(recs[tri, 4:7], v1 - v0)
+    assert np.array_equal(recs[tri, 8:11], v2 - v0)
+
+
+def test_fast_boxes_contain_their_primitives(small_scene):
+    """Every child box (FP32, rounded outward) must contain the FP64 bounds of all primitives below it."""
+    _, _, flat = small_scene
+    hb = api.host_build(flat)
+    nodes, prims = hb["fast_nodes"], hb["leaf_prims"]
+    sph = (flat.prim_flags & sceneio.PRIM_SPHERE) != 0
+    lo = np.empty((flat.num_prims, 3)); hi = np.empty((flat.num_prims, 3))
+    tri_idx = flat.indices[~sph]
+    P = flat.positions[tri_idx]            # [n,3,3]
+    lo[~sph], hi[~sph] = P.min(axis=1), P.max(axis=1)
+    if sph.any():
+        s = flat.spheres[flat.indices[sph, 0]]
+        lo[sph], hi[sph] = s[:, :3] - s[:, 3:4], s[:, :3] + s[:, 3:4]
+
+    def bounds(i):  # FP64 bounds of everything below inner node i, checking on the way down
+        blo, bhi = np.full(3, np.inf), np.full(3, -np.inf)
+        for k in (0, 1):
+            c = int(nodes[i][f"child{k}"])
+            clo = np.array([nodes[i][f"c{k}lo{a}"] for a in "xyz"], np.float64)
+            chi = np.array([nodes[i][f"c{k}hi{a}"] for a in "xyz"], np.float64)
+            if c >= 0:
+                l, h = bounds(c)
+            elif clo[0] <= chi[0]:
+                code = ~c
+                sl = prims[(code >> 3):(code >> 3) + (code & 7) + 1]
+                l, h = lo[sl].min(axis=0), hi[sl].max(axis=0)
+            else:
+                continue
+            assert (clo < l).all() and (chi > h).all()    # strictly outside: outward rounding + one ulp
+            blo, bhi = np.minimum(blo, l), np.maximum(bhi, h)
+        return blo, bhi
+
+    import sys
+    sys.setrecursionlimit(10000)
+    bounds(0)
+
+
+def test_degenerate_scenes_build():
+    empty = scenes.SceneBuilder(8, 8, (0, 0, 5), (0, 0, 0)).flat()
+    hb = api.host_build(empty)
+    assert len(hb["fast_nodes"]) == 1 and len(hb["ref_nodes"]) == 0 and hb["ref_root"] == -1
+    b = scenes.SceneBuilder(8, 8, (0, 0, 5), (0, 0, 0))
+    m = b.material(sceneio.MAT_DIFFUSE, (0.5, 0.5, 0.5))
+    b.mesh([(0, 0, 0), (1, 0, 0), (0, 1, 0)], [[0, 1, 2]], [(0, 0, 1)] * 3, None, m)
+    hb = api.host_build(b.flat())
+    assert len(hb["fast_nodes"]) == 1 and len(hb["ref_nodes"]) == 1
+    _walk_fast_tree(hb)
+    # many identical triangles: centroids coincide, the builder must still terminate with legal leaves
+    b = scenes.SceneBuilder(8, 8, (0, 0, 5), (0, 0, 0))
+    m = b.material(sceneio.MAT_DIFFUSE, (0.5, 0.5, 0.5))
+    for _ in range(37):
+        b.mesh([(0, 0, 0), (1, 0, 0), (0, 1, 0)], [[0, 1, 2]], [(0, 0, 1)] * 3, None, m)
+    _walk_fast_tree(api.host_build(b.flat()))
