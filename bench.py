@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the hot path (BVH ray-scene intersection + Monte-Carlo path integration) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path on the host cores
+
+Workload (BASELINE.json configs[1]): procedural 1 002 530-triangle displaced mesh, Blinn-Phong microfacet BRDF
+(the reference's only microfacet model), one-sample MIS, 1920x1080, max_depth 5.  A "step" renders SPP_PER_STEP
+samples of every pixel (one pass of generate -> extend -> sort -> shade -> accumulate waves); with N GPUs every rank
+renders its own sample-index range of every step (weak scaling, scene replicated), and the partial accumulation
+buffers are combined by ONE NCCL all-reduce inside the timed region.
+Prints one JSON line (see DESIGN.md "Measurement" for every key).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "c2_heightfield_1M_tri_blinn_microfacet_one_sample_mis_1920x1080"
+INTEGRATOR = "one_sample_mis"
+MAX_DEPTH = 5
+SEED = 20261018
+# SURVEY.md 8(d) counting rules (algorithmic bytes / flops)
+B_BOX, B_TRI, B_RAY_EXT, B_RAY_SH, B_VERTEX, B_SAMPLE = 32, 48, 48, 36, 352, 12
+F_BOX, F_TRI = 27, 60
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_scene():
+    from take_b200 import scenes
+    return scenes.heightfield()          # n=708 -> 1 002 528 + 2 triangles, 1920x1080
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU side: the reference's own code (oracle/_ref) when it was compiled, else our CPU restatement
+# ------------------------------------------------------------------------------------------------------------
+class CpuRenderer:
+    def __init__(self, builder, flat):
+        from oracle import bindings as ob
+        self.ob = ob
+        self.cores = os.cpu_count() or 1
+        self.port = ob.OracleLib().load(flat)        # ray counts per sample (bit-identical paths)
+        if ob.have_ref():
+            self.kind = "reference"
+            self.tmp = tempfile.TemporaryDirectory()
+            self.scene = ob.RefLib().load(builder.write(self.tmp.name))
+        else:
+            self.kind = "port"
+            self.scene = self.port
+        self.W, self.H = flat.width, flat.height
+
+    def run(self, sample_index, row_begin, row_step):
+        """Render one sample of every row_step-th image row with all host threads; returns (seconds, samples)."""
+        t0 = time.perf_counter()
+        self.scene.render(INTEGRATOR, MAX_DEPTH, sample_index, sample_index + 1, seed=SEED, threads=self.cores, sumsq=True,
+                          row_begin=row_begin, row_step=row_step)
+        dt = time.perf_counter() - t0
+        rows = len(range(row_begin, self.H, row_step))
+        return dt, rows * self.W
+
+    def rays_per_sample(self, row_step=64):
+        _, _, st = self.port.render(INTEGRATOR, MAX_DEPTH, 0, 1, seed=SEED, threads=self.cores, stats=True, row_begin=0,
+                                    row_step=row_step)
+        n = len(range(0, self.H, row_step)) * self.W
+        return float(st[0] + st[1]) / n
+
+    def pick_row_step(self, target_seconds):
+        dt, n = self.run(0, 0, 64)
+        rate = n / max(dt, 1e-6)
+        want = rate * target_seconds
+        return int(max(1, min(64, round(self.W * self.H / max(want, 1.0))))), rate
+
+
+def cpu_baseline(builder, flat, target_seconds=15.0):
+    cpu = CpuRenderer(builder, flat)
+    rps = cpu.rays_per_sample()
+    row_step, _ = cpu.pick_row_step(target_seconds)
+    dt, n = cpu.run(1, 0, row_step)
+    return {"value": n * rps / dt / 1e6, "unit": "Mrays/s", "samples_per_s": n / dt, "cores": cpu.cores, "kind": cpu.kind,
+            "sample": f"1 spp of every {row_step}-th row of the 1920x1080 frame ({n} path samples, {dt:.1f} s), "
+                      f"{rps:.3f} rays/sample, integrator {INTEGRATOR}, max_depth {MAX_DEPTH}"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    builder = build_scene()
+    flat = builder.flat()
+    cpu = CpuRenderer(builder, flat)
+    rps = cpu.rays_per_sample()
+    # bound every step to a few seconds so that warmup + steps end within minutes
+    row_step, _ = cpu.pick_row_step(max(1.0, min(6.0, 150.0 / max(1, args.steps + args.warmup))))
+    for i in range(args.warmup):
+        cpu.run(i, i % row_step, row_step)
+    t_total, n_total = 0.0, 0
+    for i in range(args.steps):
+        dt, n = cpu.run(args.warmup + i, i % row_step, row_step)
+        t_total += dt
+        n_total += n
+    value = n_total * rps / t_total / 1e6
+    sample = (f"each step: 1 spp of every {row_step}-th row of the 1920x1080 frame ({n_total // max(1, args.steps)} path samples), "
+              f"{rps:.3f} rays/sample")
+    print(json.dumps({
+        "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "samples_per_s": n_total / t_total,
+        "config": {"workload": WORKLOAD, "integrator": INTEGRATOR, "max_depth": MAX_DEPTH, "resolution": [flat.width, flat.height],
+                   "triangles": flat.num_prims},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cpu.cores, "kind": cpu.kind, "sample": sample},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from take_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+
+    builder = build_scene()
+    flat = builder.flat()
+    t0 = time.perf_counter()
+    gs = api.GpuScene(flat, device=local)
+    scene_create_ms = 1e3 * (time.perf_counter() - t0)
+    info = gs.info()
+    H, W = flat.height, flat.width
+    S = args.spp_per_step
+    ext = torch.cuda.ExternalStream(gs.stream, device=dev)
+    d_sum = torch.zeros((H, W, 3), dtype=torch.float64, device=dev)
+    d_sq = torch.zeros_like(d_sum)
+    torch.cuda.synchronize()
+
+    def spp_range(step):
+        lo = (step * world + rank) * S
+        return lo, lo + S
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    totals = {"rays": 0, "samples": 0, "launches": 0, "extend": 0, "shadow": 0}
+
+    def device_step(step, flags=0, acc=None):
+        lo, hi = spp_range(step)
+        st = gs.render_sums_device(d_sum.data_ptr(), d_sq.data_ptr(), INTEGRATOR, MAX_DEPTH, lo, hi, seed=SEED, flags=flags)
+        if acc is not None:
+            acc["rays"] += st["extend_rays"] + st["shadow_rays"]
+            acc["samples"] += st["samples"]
+            acc["launches"] += st["kernel_launches"]
+            acc["extend"] += st["extend_rays"]
+            acc["shadow"] += st["shadow_rays"]
+        return st
+
+    # ---- timed region: K steps + the one reduction, device-timed on the launching stream -----------------------
+    for i in range(args.warmup):
+        device_step(i)
+    d_sum.zero_(); d_sq.zero_()
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for i in range(args.steps):
+        device_step(args.warmup + i, acc=totals)
+    if world > 1:
+        dist.all_reduce(d_sum)       # the path's one exchange step: sum of the partial accumulation buffers (NCCL)
+        dist.all_reduce(d_sq)
+        torch.cuda.synchronize()
+    e1.record(ext)
+    e1.synchronize()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    agg = torch.tensor([totals["rays"], totals["samples"], totals["launches"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg)
+    clock_info = clocks.stop() if clocks else None
+    ms = float(ms.item())
+    rays_all, samples_all, launches_all = (float(v) for v in agg.tolist())
+    mean_check = float((d_sum / (S * args.steps * world)).mean().item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- e2e: the C-ABI call a host application makes (host buffers, D2H of the result inside the timed region) ----
+    h_sum = torch.empty((H, W, 3), dtype=torch.float64, pin_memory=True).numpy()
+    h_sq = torch.empty((H, W, 3), dtype=torch.float64, pin_memory=True).numpy()
+    o_rays, e2e_steps = 0, max(2, min(args.steps, 6))
+    import ctypes as C
+    st = api.TakeStats()
+
+    def host_step(step):
+        lo, hi = spp_range(step)
+        o = api.TakeRenderOpts(api.INTEGRATORS[INTEGRATOR], MAX_DEPTH, lo, hi, SEED, 0, 0)
+        rc = gs.lib.take_gpu_render(gs.h, C.byref(o), h_sum.ctypes.data, h_sq.ctypes.data, C.byref(st))
+        assert rc == 0, gs.lib.take_gpu_last_error()
+        return st.extend_rays + st.shadow_rays
+
+    host_step(0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        o_rays += host_step(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e = {"value": o_rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": C.sizeof(api.TakeRenderOpts),
+           "d2h_bytes_per_step": int(h_sum.nbytes + h_sq.nbytes), "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+           "note": "take_gpu_render(): camera rays are generated on the device (replaces render.cpp:69-75), so the per-step "
+                   "host input is the options struct; the scene is uploaded once by take_gpu_scene_create "
+                   f"({scene_create_ms:.0f} ms incl. host BVH builds)"}
+
+    # ---- roofline of the dominant kernel (k_extend): events inside the library on the launching stream -----------
+    peak, sm_max, peak_src = measured_peaks()
+    rs = {"ms_extend": 0.0, "ms_shade": 0.0, "ms_generate": 0.0, "ms_sort": 0.0, "ms_other": 0.0, "ms_total": 0.0, "launches": 0}
+    r_steps = max(2, min(args.steps, 4))
+    for i in range(r_steps):
+        s_ = device_step(i, flags=api.RENDER_STAGE_TIMES)
+        for k in ("ms_extend", "ms_shade", "ms_generate", "ms_sort", "ms_other", "ms_total"):
+            rs[k] += s_[k]
+    cnt = device_step(0, flags=api.RENDER_COUNT_TESTS)
+    passes = MAX_DEPTH + 2
+    ext_launches_per_step = max(1, cnt["waves"]) * passes
+    alg_bytes = B_BOX * cnt["box_tests"] + B_TRI * cnt["tri_tests"] + B_RAY_EXT * cnt["extend_rays"]
+    alg_flops = F_BOX * cnt["box_tests"] + F_TRI * cnt["tri_tests"]
+    ms_ext_step = rs["ms_extend"] / r_steps
+    achieved = alg_bytes / (ms_ext_step * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "extend_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    sm_mhz = (clock_info or {}).get("sm_mhz") or sm_max
+    fp32_peak = 2 * 128 * info["sm_count"] * sm_mhz * 1e6 / 1e12
+    roofline = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "bytes_per_launch": alg_bytes / ext_launches_per_step, "ms_per_launch": ms_ext_step / ext_launches_per_step,
+                "launches_per_step": ext_launches_per_step,
+                "extend_grays_per_s": cnt["extend_rays"] / (ms_ext_step * 1e-3) / 1e9,
+                "box_tests_per_ray": cnt["box_tests"] / max(1, cnt["extend_rays"]),
+                "tri_tests_per_ray": cnt["tri_tests"] / max(1, cnt["extend_rays"]),
+                "test_rate_tflops": alg_flops / (ms_ext_step * 1e-3) / 1e12, "fp32_peak_tflops": fp32_peak,
+                "test_rate_frac_fp32": alg_flops / (ms_ext_step * 1e-3) / 1e12 / fp32_peak,
+                "stage_share": {k[3:]: rs[k] / max(rs["ms_total"], 1e-9) for k in rs if k.startswith("ms_") and k != "ms_total"}}
+
+    # ---- CPU baseline (reported, not the target) -----------------------------------------------------------------
+    base = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            base = cpu_baseline(builder, flat)
+        except Exception as ex:  # the baseline must never take the GPU number down with it
+            base = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(ex)}
+
+    line = {
+        "metric": "Mrays/s", "value": rays_all / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "samples_per_s": samples_all / (ms * 1e-3),
+        "config": {"workload": WORKLOAD, "integrator": INTEGRATOR, "max_depth": MAX_DEPTH, "resolution": [W, H],
+                   "triangles": flat.num_prims, "spp_per_step_per_gpu": S, "parallelism": f"spp-range x{world}, scene replicated",
+                   "l2": "per-step working set (2M-4M path records, 256 B each, + 130 MB of tree and triangles) exceeds the 126 MB L2",
+                   "bvh": {"nodes": int(info["fast_nodes"]), "depth": int(info["fast_tree_depth"]),
+                           "build_ms": info["build_ms_fast_tree"] + info["build_ms_reference_tree"]}},
+        "e2e": e2e, "gpu_launches": int(launches_all), "clocks": clock_info, "roofline": roofline, "cpu_baseline": base,
+        "rays_per_sample": rays_all / max(1.0, samples_all), "image_mean": mean_check, "scene_create_ms": scene_create_ms,
+    }
+    print(json.dumps(line))
+    gs.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--spp-per-step", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -159,6 +159,7 @@ typedef struct TakeStats {
     double ms_generate, ms_extend, ms_shade, ms_shadow, ms_sort, ms_other; /* only with TAKE_RENDER_STAGE_TIMES */
     int64_t shadow_box_tests, shadow_tri_tests; /* shadow kernel (only with TAKE_RENDER_COUNT_TESTS) */
     int64_t miss_after_light_sample; /* one-sample MIS: light-aimed rays that missed everything (reference: UB) */
+    int64_t waves;                   /* generate..accumulate rounds; every pass of a wave launches one extend kernel */
 } TakeStats;
 
 typedef struct TakeScene TakeScene; /* opaque */

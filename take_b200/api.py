@@ -47,7 +47,8 @@ class TakeStats(C.Structure):
                 ("box_tests", C.c_int64), ("tri_tests", C.c_int64), ("kernel_launches", C.c_int64),
                 ("ms_total", C.c_double), ("ms_generate", C.c_double), ("ms_extend", C.c_double),
                 ("ms_shade", C.c_double), ("ms_shadow", C.c_double), ("ms_sort", C.c_double), ("ms_other", C.c_double),
-                ("shadow_box_tests", C.c_int64), ("shadow_tri_tests", C.c_int64), ("miss_after_light_sample", C.c_int64)]
+                ("shadow_box_tests", C.c_int64), ("shadow_tri_tests", C.c_int64), ("miss_after_light_sample", C.c_int64),
+                ("waves", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -326,7 +326,7 @@ int check_opts(const TakeScene *s, const TakeRenderOpts *o) {
     return TAKE_OK;
 }
 
-void read_totals(TakeScene *s, TakeStats *stats, const StageTimer &tm, double ms_total, int64_t launches) {
+void read_totals(TakeScene *s, TakeStats *stats, const StageTimer &tm, double ms_total, int64_t launches, int64_t waves) {
     if (!stats) return;
     Totals t;
     cudaMemcpy(&t, s->totals.p, sizeof(t), cudaMemcpyDeviceToHost);
@@ -341,6 +341,7 @@ void read_totals(TakeScene *s, TakeStats *stats, const StageTimer &tm, double ms
     stats->shadow_tri_tests = (int64_t)t.shadow_tri_tests;
     stats->miss_after_light_sample = (int64_t)t.miss_after_light_sample;
     stats->kernel_launches = launches;
+    stats->waves = waves;
     stats->ms_total = ms_total;
     stats->ms_generate = tm.ms[ST_GENERATE];
     stats->ms_extend = tm.ms[ST_EXTEND];
@@ -611,7 +612,7 @@ int take_gpu_render_device(TakeScene *s, const TakeRenderOpts *o, double *d_sum,
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
     CU(cudaEventRecord(e0, s->stream));
-    int64_t launches = 0;
+    int64_t launches = 0, waves = 0;
     Wave w;
     fill_wave_ptrs(s, w, o);
     const int64_t chunk_pixels = std::min(npix, capacity);
@@ -626,6 +627,7 @@ int take_gpu_render_device(TakeScene *s, const TakeRenderOpts *o, double *d_sum,
             w.samples_in_wave = (int32_t)ns;
             w.n_slots = (int32_t)(cp * ns);
             if (int rc = launch_wave(s, w, o, d_sum, d_sumsq, nullptr, tm, count, launches)) return rc;
+            waves++;
         }
     }
     CU(cudaEventRecord(e1, s->stream));
@@ -635,7 +637,7 @@ int take_gpu_render_device(TakeScene *s, const TakeRenderOpts *o, double *d_sum,
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     tm.collect();
-    read_totals(s, stats, tm, ms, launches);
+    read_totals(s, stats, tm, ms, launches, waves);
     return TAKE_OK;
 }
 

@@ -31,7 +31,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(sceneio.TakeCamera) == 8 + 10 * 8
     assert sceneio.MAT_DTYPE.itemsize == 80 and sceneio.LIGHT_DTYPE.itemsize == 56
     assert C.sizeof(api.TakeRenderOpts) == 40
-    assert C.sizeof(api.TakeStats) == 7 * 8 + 7 * 8 + 3 * 8
+    assert C.sizeof(api.TakeStats) == 7 * 8 + 7 * 8 + 4 * 8
     assert api.RAY_DTYPE.itemsize == 64 and api.HIT_DTYPE.itemsize == 32
 
 
