@@ -1,0 +1,63 @@
+"""World-size-2 gloo test of the multi-GPU host logic (take_b200/dist.py) on CPU.  The per-rank renderer is the CPU
+oracle (tests may use it); what is under test is the sharding and the reduce, which are the same code under NCCL."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from take_b200 import dist as tdist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_spp_partitions_exactly():
+    for n, world in [(256, 8), (7, 3), (5, 8), (0, 4), (1024, 1)]:
+        ranges = [tdist.shard_spp(10, 10 + n, r, world) for r in range(world)]
+        assert ranges[0][0] == 10 and ranges[-1][1] == 10 + n
+        assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+        sizes = [b - a for a, b in ranges]
+        assert max(sizes) - min(sizes) <= 1 and sum(sizes) == n
+
+
+def _worker(rank, world, port, spp, out_path):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import bindings as ob
+    from take_b200 import scenes
+    flat = scenes.cornell_box(24, 24, spp, materials="mixed").flat()
+    sc = ob.OracleLib().load(flat)
+
+    def render_range(lo, hi):
+        return sc.render("mis", 3, lo, hi, seed=77, threads=2)
+
+    res = tdist.render_sharded(render_range, 0, spp, reduce="all" if rank % 2 == 0 or True else "root")
+    mean, var, n = res
+    if rank == 0:
+        np.savez(out_path, mean=mean.numpy(), var=var.numpy(), n=n)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_render_equals_single_process(tmp_path, oracle_lib, world):
+    from take_b200 import scenes
+    spp = 7   # deliberately not divisible by the world size
+    out = str(tmp_path / "out.npz")
+    port = 29500 + (os.getpid() % 1000) + world
+    mp.spawn(_worker, args=(world, port, spp, out), nprocs=world, join=True)
+    got = np.load(out)
+    flat = scenes.cornell_box(24, 24, spp, materials="mixed").flat()
+    sc = oracle_lib.load(flat)
+    s, s2 = sc.render("mis", 3, 0, spp, seed=77)
+    mean = s / spp
+    # same samples, summed in a different order: equal to rounding
+    assert np.abs(got["mean"] - mean).max() <= 1e-12 * np.abs(mean).max()
+    var = np.maximum(s2 / spp - mean ** 2, 0) * spp / (spp - 1) / spp
+    assert np.abs(got["var"] - var).max() <= 1e-9 * max(var.max(), 1e-30)
+    assert int(got["n"]) == spp

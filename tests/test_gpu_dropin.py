@@ -1,0 +1,51 @@
+"""The drop-in at the reference's own entry point: oracle/_ref/take_gpu is the reference's main.cpp + front end with
+src/render.cpp replaced by take_b200/host/render_gpu.cpp.  Run it like the stock binary on an XML
+scene and compare its image.exr with (a) the C-ABI result for the same seed and (b) the stock CPU binary's image."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import bindings as ob
+from take_b200 import api, scenes
+
+pytestmark = pytest.mark.gpu
+TAKE_GPU = os.path.join(os.path.dirname(ob.REF_CLI), "take_gpu")
+
+
+def read_exr(path):
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    import cv2
+    img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    assert img is not None, path
+    return img[..., ::-1].astype(np.float64)   # BGR -> RGB
+
+
+@pytest.mark.skipif(not os.path.exists(TAKE_GPU), reason="oracle/_ref/take_gpu not built (needs /root/reference)")
+def test_cli_drop_in(tmp_path, gpu_lib):
+    b = scenes.cornell_box(96, 96, 64, materials="mixed")
+    gpu_dir, cpu_dir = tmp_path / "gpu", tmp_path / "cpu"
+    xml_gpu, xml_cpu = b.write(str(gpu_dir)), b.write(str(cpu_dir))
+    out = subprocess.run([TAKE_GPU, xml_gpu, "-max_depth", "5", "-seed", "42"], cwd=str(gpu_dir), capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "Finish building rendering" in out.stdout          # same progress lines as the reference
+    img_gpu = read_exr(str(gpu_dir / "image.exr"))
+    # (a) identical to the C-ABI result up to the EXR's half-float quantisation (2^-11 relative)
+    gs = api.GpuScene(b.flat())
+    s, s2, _ = gs.render_sums("mis", 5, 0, 64, seed=42)
+    gs.close()
+    mean = s / 64
+    assert img_gpu.shape == mean.shape
+    assert np.abs(img_gpu - mean).max() <= 2.0 ** -10 * np.abs(mean).max() + 1e-6
+    # (b) statistically consistent with the stock CPU renderer (random_device seeds, so only statistics can agree)
+    out = subprocess.run([ob.REF_CLI, xml_cpu, "-max_depth", "5", "-t", str(os.cpu_count())], cwd=str(cpu_dir),
+                         capture_output=True, text=True, timeout=1200)
+    assert out.returncode == 0, out.stdout + out.stderr
+    img_cpu = read_exr(str(cpu_dir / "image.exr"))
+    var = np.maximum(s2 / 64 - mean ** 2, 0) * 64 / 63
+    se2 = 2 * var / 64 + (2.0 ** -10 * mean) ** 2             # both images carry the same per-pixel noise level
+    z = np.abs(img_gpu - img_cpu)[se2 > 0] / np.sqrt(se2[se2 > 0])
+    assert (z <= 3).mean() >= 0.98
+    assert abs(img_gpu.mean() - img_cpu.mean()) <= 4 * np.sqrt(se2.sum()) / se2.size + 1e-3 * img_cpu.mean()
