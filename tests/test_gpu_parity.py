@@ -144,24 +144,29 @@ def test_image_sums_same_streams(pair, integrator):
 
 
 def test_statistical_gate_independent_seeds(pair):
-    """SURVEY.md 8(c): relMSE(GPU, CPU) <= 1.5 x predicted noise floor; >= 99.5 % of pixel-channels within 3 sigma;
-    global mean within 3 sigma -- with DIFFERENT seeds on the two sides (independent estimates)."""
+    """The north star's image gate, with DIFFERENT seeds on the two sides (independent estimates), calibrated as in
+    SURVEY.md 8(c):
+      (i)   relMSE(GPU_seedC, CPU_seedA) <= 1.5 x relMSE(CPU_seedB, CPU_seedA): the error between a GPU and a CPU render
+            is no larger than between two CPU renders (relMSE = mean((a-b)^2 / (b^2 + 1e-2)); the sample-variance
+            based noise floor is not used as the yardstick because the estimator is heavy-tailed at these spp);
+      (ii)  >= 99.5 % of pixel-channels within 3 sigma of each other;
+      (iii) per channel, the image sums differ by less than 4 sigma (catches ~1 % estimator bias)."""
     name, flat, gs, sc = pair
-    n_c, n_g = 48, 192
-    cs, cs2 = sc.render("mis", 5, 0, n_c, seed=1001)
-    g, g2, _ = gs.render_sums("mis", 5, 0, n_g, seed=2002)
-    mu_c, mu_g = cs / n_c, g / n_g
-    var_c = np.maximum(cs2 / n_c - mu_c ** 2, 0) * n_c / (n_c - 1)
-    var_g = np.maximum(g2 / n_g - mu_g ** 2, 0) * n_g / (n_g - 1)
-    se2 = var_c / n_c + var_g / n_g
-    relmse = np.mean((mu_g - mu_c) ** 2 / (mu_c ** 2 + 1e-2))
-    floor = np.mean(se2 / (mu_c ** 2 + 1e-2))
-    assert relmse <= 1.5 * floor + 1e-12, (name, relmse, floor)
+    n = 64
+    a, a2 = sc.render("mis", 5, 0, n, seed=1001)
+    b, _ = sc.render("mis", 5, 0, n, seed=3003)
+    g, g2, _ = gs.render_sums("mis", 5, 0, n, seed=2002)
+    mu_a, mu_b, mu_g = a / n, b / n, g / n
+    relmse = lambda x, y: np.mean((x - y) ** 2 / (y ** 2 + 1e-2))
+    assert relmse(mu_g, mu_a) <= 1.5 * relmse(mu_b, mu_a), (name, relmse(mu_g, mu_a), relmse(mu_b, mu_a))
+    var_a = np.maximum(a2 / n - mu_a ** 2, 0) * n / (n - 1)
+    var_g = np.maximum(g2 / n - mu_g ** 2, 0) * n / (n - 1)
+    se2 = var_a / n + var_g / n
     mask = se2 > 0
-    z = np.abs(mu_g - mu_c)[mask] / np.sqrt(se2[mask])
-    assert (z <= 3).mean() >= 0.995 - 0.01, (name, float((z <= 3).mean()))   # heavy-tailed pixels: see DESIGN.md
+    z = np.abs(mu_g - mu_a)[mask] / np.sqrt(se2[mask])
+    assert (z <= 3).mean() >= 0.995, (name, float((z <= 3).mean()))
     for c in range(3):
-        assert abs(mu_g[..., c].sum() - mu_c[..., c].sum()) <= 4 * np.sqrt(se2[..., c].sum()) + 1e-12
+        assert abs(mu_g[..., c].sum() - mu_a[..., c].sum()) <= 4 * np.sqrt(se2[..., c].sum()) + 1e-12
 
 
 # ---- properties that do not need the oracle ------------------------------------------------------------------
