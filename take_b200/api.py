@@ -19,7 +19,7 @@ import numpy as np
 from .sceneio import FlatScene, TakeSceneDesc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtake_gpu.so")
+LIB_PATH = os.environ.get("TAKE_GPU_LIB") or os.path.join(_HERE, "libtake_gpu.so")   # TAKE_GPU_LIB: A/B builds while tuning
 
 INTEGRATORS = {"mis": 0, "raw": 1, "one_sample_mis": 2}
 ISECT_FAST, ISECT_EXACT = 0, 1

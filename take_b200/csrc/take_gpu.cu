@@ -70,6 +70,8 @@ struct TakeScene {
         fetch;
     int64_t wave_capacity = 0;
     int blocks_extend = 0, blocks_shadow = 0, blocks_isect = 0, blocks_occl = 0;
+    int blocks_extend2 = 0, blocks_shadow2 = 0, blocks_isect2 = 0, blocks_occl2 = 0;
+    int traversal = 2;  // 1: one ray per thread to completion; 2: warp-persistent while-while with re-fetch (TAKE_TRAVERSAL)
     // diagnostics
     double build_ms_ref = 0, build_ms_fast = 0;
     int fast_depth = 0;
@@ -267,8 +269,13 @@ int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, d
     const int scatter_blocks = std::max(1, std::min((w.n_slots + 255) / 256, s->sm_count * 16));
     for (int b = 0; b < n_passes; ++b) {
         tm.begin(ST_EXTEND);
-        if (count) k_extend<true><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
-        else k_extend<false><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
+        if (s->traversal == 2) {
+            if (count) k_extend2<true><<<s->blocks_extend2, 128, 0, st>>>(s->dev, w, b);
+            else k_extend2<false><<<s->blocks_extend2, 128, 0, st>>>(s->dev, w, b);
+        } else {
+            if (count) k_extend<true><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
+            else k_extend<false><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
+        }
         tm.end();
         if (w.sort_enabled) {
             tm.begin(ST_SORT);
@@ -282,8 +289,13 @@ int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, d
         launches += 2;
         if (o->integrator == TAKE_INTEGRATOR_MIS && b <= o->max_depth) {
             tm.begin(ST_SHADOW);
-            if (count) k_shadow<true><<<s->blocks_shadow, 128, 0, st>>>(s->dev, w, b);
-            else k_shadow<false><<<s->blocks_shadow, 128, 0, st>>>(s->dev, w, b);
+            if (s->traversal == 2) {
+                if (count) k_shadow2<true><<<s->blocks_shadow2, 128, 0, st>>>(s->dev, w, b);
+                else k_shadow2<false><<<s->blocks_shadow2, 128, 0, st>>>(s->dev, w, b);
+            } else {
+                if (count) k_shadow<true><<<s->blocks_shadow, 128, 0, st>>>(s->dev, w, b);
+                else k_shadow<false><<<s->blocks_shadow, 128, 0, st>>>(s->dev, w, b);
+            }
             tm.end();
             launches++;
         }
@@ -314,6 +326,7 @@ void fill_wave_ptrs(TakeScene *s, Wave &w, const TakeRenderOpts *o) {
     w.max_depth = o->max_depth;
     w.sort_enabled = (o->flags & TAKE_RENDER_NO_SORT) ? 0 : 1;
     w.seed = o->seed;
+    w.tile_w = (s->width % 8 == 0 && s->height % 4 == 0 && !env_int("TAKE_NO_TILES", 0)) ? s->width : 0;
 }
 
 int check_opts(const TakeScene *s, const TakeRenderOpts *o) {
@@ -476,6 +489,11 @@ int take_gpu_scene_create(int device, const TakeSceneDesc *d, TakeScene **out) {
     s->blocks_shadow = blocks_for((const void *)k_shadow<false>);
     s->blocks_isect = blocks_for((const void *)k_intersect_fast<false>);
     s->blocks_occl = blocks_for((const void *)k_intersect_fast<true>);
+    s->blocks_extend2 = blocks_for((const void *)k_extend2<false>);
+    s->blocks_shadow2 = blocks_for((const void *)k_shadow2<false>);
+    s->blocks_isect2 = blocks_for((const void *)k_intersect_fast2<false>);
+    s->blocks_occl2 = blocks_for((const void *)k_intersect_fast2<true>);
+    s->traversal = env_int("TAKE_TRAVERSAL", 2) == 1 ? 1 : 2;
     CU(s->fetch.ensure(256));
     guard.ok = true;
     *out = s;
@@ -548,7 +566,10 @@ int take_gpu_intersect_device(TakeScene *s, const TakeRay *d_rays, int64_t n, Ta
         k_intersect_exact<<<(unsigned)((n + 127) / 128), 128, 0, s->stream>>>(s->dev, d_rays, n, d_hits);
     } else if (flags == TAKE_ISECT_FAST) {
         CU(cudaMemsetAsync(s->fetch.p, 0, 4, s->stream));
-        k_intersect_fast<false><<<s->blocks_isect, 128, 0, s->stream>>>(s->dev, d_rays, n, d_hits, nullptr, s->fetch.as<uint32_t>());
+        if (s->traversal == 2)
+            k_intersect_fast2<false><<<s->blocks_isect2, 128, 0, s->stream>>>(s->dev, d_rays, n, d_hits, nullptr, s->fetch.as<uint32_t>());
+        else
+            k_intersect_fast<false><<<s->blocks_isect, 128, 0, s->stream>>>(s->dev, d_rays, n, d_hits, nullptr, s->fetch.as<uint32_t>());
     } else {
         return fail(TAKE_E_INVALID, "unknown intersect flags");
     }
@@ -585,8 +606,12 @@ int take_gpu_occluded(TakeScene *s, const TakeRay *rays, int64_t n, uint8_t *occ
         CU(s->scratch_b.ensure(m));
         CU(cudaMemcpyAsync(s->scratch_a.p, rays + off, m * sizeof(TakeRay), cudaMemcpyHostToDevice, s->stream));
         CU(cudaMemsetAsync(s->fetch.p, 0, 4, s->stream));
-        k_intersect_fast<true><<<s->blocks_occl, 128, 0, s->stream>>>(s->dev, s->scratch_a.as<TakeRay>(), m, nullptr,
-                                                                      s->scratch_b.as<uint8_t>(), s->fetch.as<uint32_t>());
+        if (s->traversal == 2)
+            k_intersect_fast2<true><<<s->blocks_occl2, 128, 0, s->stream>>>(s->dev, s->scratch_a.as<TakeRay>(), m, nullptr,
+                                                                           s->scratch_b.as<uint8_t>(), s->fetch.as<uint32_t>());
+        else
+            k_intersect_fast<true><<<s->blocks_occl, 128, 0, s->stream>>>(s->dev, s->scratch_a.as<TakeRay>(), m, nullptr,
+                                                                          s->scratch_b.as<uint8_t>(), s->fetch.as<uint32_t>());
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(occluded + off, s->scratch_b.p, m, cudaMemcpyDeviceToHost, s->stream));
         CU(cudaStreamSynchronize(s->stream));
@@ -615,7 +640,7 @@ int take_gpu_render_device(TakeScene *s, const TakeRenderOpts *o, double *d_sum,
     int64_t launches = 0, waves = 0;
     Wave w;
     fill_wave_ptrs(s, w, o);
-    const int64_t chunk_pixels = std::min(npix, capacity);
+    const int64_t chunk_pixels = std::min(npix, capacity & ~int64_t(31));
     for (int64_t base = 0; base < npix; base += chunk_pixels) {
         const int64_t cp = std::min(chunk_pixels, npix - base);
         const int64_t per_wave = std::max<int64_t>(1, capacity / cp);

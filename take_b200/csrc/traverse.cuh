@@ -239,4 +239,184 @@ __device__ __forceinline__ void trace_fast(const DevScene &sc, D3 o, D3 d, doubl
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Warp-persistent traversal ("while-while" with dynamic re-fetch).
+//
+// trace_fast above walks one ray to completion per thread; lanes whose rays end early idle until the slowest ray
+// of the warp is done, and the long FP64 leaf test of one lane stalls the 31 others in the middle of their node
+// loop (measured: 10 of 32 lanes active per issued instruction on primary rays).  This variant keeps a warp
+// resident and splits every round into convergent phases:
+//   1. re-fetch: lanes without a ray are counted with __ballot_sync / __popc; when enough are idle one lane reserves
+//      that many queue entries with a single atomicAdd, __shfl_sync broadcasts the base, and the idle lanes load new
+//      rays (ray compaction by replacement);
+//   2. node phase: every lane descends inner nodes until it holds a leaf (or runs out of nodes);
+//   3. leaf phase: all lanes holding a leaf run the FP64 leaf test together, then pop;
+//   4. retire: lanes whose stack ran dry hand their result to `io` at a convergent point.
+// Results are identical to trace_fast (same boxes, same leaf test, same tie rule) -- only the schedule differs.
+// `IO` supplies  bool load(i, lane state...)  and  void retire(mask, done, ...)  (see the kernels in wavefront.cuh).
+// ---------------------------------------------------------------------------------------------------------
+#define TAKE_NODE_DONE ((int32_t)0x80000000)
+#ifndef TAKE_REFILL_MIN
+#define TAKE_REFILL_MIN 8
+#endif
+
+struct LaneRay {        // FP32 image of the ray for the box tests + the FP64 window for the leaf test
+    float idx, idy, idz, olx, ohx, oly, ohy, olz, ohz, tmin_f, tbest_f;
+    double tmin, best_t;
+    const double *o;    // FP64 origin (3 doubles) and direction (3 doubles) stay in memory and are re-read per leaf
+    const double *d;
+};
+
+__device__ __forceinline__ void lane_ray_setup(LaneRay &r, const DevScene &sc, const double *o, const double *d, double tmin,
+                                               double tmax) {
+    const float ox = (float)o[0], oy = (float)o[1], oz = (float)o[2];
+    r.idx = 1.0f / (float)d[0]; r.idy = 1.0f / (float)d[1]; r.idz = 1.0f / (float)d[2];
+    const float delta = 1.9073486e-6f * fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fmaxf(fabsf(oz), sc.abs_max));
+    r.olx = -(ox + delta) * r.idx; r.ohx = -(ox - delta) * r.idx;
+    r.oly = -(oy + delta) * r.idy; r.ohy = -(oy - delta) * r.idy;
+    r.olz = -(oz + delta) * r.idz; r.ohz = -(oz - delta) * r.idz;
+    r.tmin_f = __double2float_rd(tmin);
+    r.tbest_f = __double2float_ru(tmax);
+    r.tmin = tmin;
+    r.best_t = tmax;
+    r.o = o;
+    r.d = d;
+}
+
+template <bool ANY_HIT, bool COUNT, typename IO>
+__device__ __forceinline__ void trace_warp_persistent(const DevScene &sc, IO &io, uint32_t n, uint32_t *fetch, TravStack &st,
+                                                      TravCounters *cnt) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    bool active = false, exhausted = (n == 0) || sc.num_prims <= 0;
+    int32_t node = TAKE_NODE_DONE;
+    uint32_t item = 0;
+    LaneRay r;
+    HitOut out;
+    out.prim = -1; out.rank = -1; out.t = 0; out.u = 0; out.v = 0;
+    st.sp = 0;
+    if (sc.num_prims <= 0) {  // nothing to hit: every ray misses (still has to be retired)
+        for (uint32_t base = 0;; ) {
+            if (lane == 0) base = atomicAdd(fetch, 32u);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= n) return;
+            const uint32_t i = base + lane;
+            const bool v = i < n;
+            if (v) io.load(i, sc, r);
+            io.retire(__ballot_sync(0xffffffffu, v), v, i, out);
+        }
+    }
+    for (;;) {
+        // ---- 1. re-fetch ----
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (idle != 0u && !exhausted && (idle == 0xffffffffu || __popc(idle) >= TAKE_REFILL_MIN)) {
+            const int want = __popc(idle);
+            uint32_t base = 0;
+            if (lane == __ffs(idle) - 1) base = atomicAdd(fetch, (uint32_t)want);
+            base = __shfl_sync(0xffffffffu, base, __ffs(idle) - 1);
+            if (base + (uint32_t)want >= n) exhausted = true;
+            if (!active) {
+                const uint32_t i = base + (uint32_t)__popc(idle & lt_mask);
+                if (i < n) {
+                    item = i;
+                    io.load(i, sc, r);
+                    active = true;
+                    node = 0;
+                    st.sp = 0;
+                    out.prim = -1; out.rank = -1; out.t = 0; out.u = 0; out.v = 0;
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0u) {
+            if (exhausted) return;
+            continue;
+        }
+        // ---- 2. node phase ----
+        while (active && node >= 0) {
+            const float4 q0 = __ldg(sc.nodes + 4 * (int64_t)node);
+            const float4 q1 = __ldg(sc.nodes + 4 * (int64_t)node + 1);
+            const float4 q2 = __ldg(sc.nodes + 4 * (int64_t)node + 2);
+            const float4 q3 = __ldg(sc.nodes + 4 * (int64_t)node + 3);
+            if (COUNT) cnt->box += 2;
+            float a, b;
+            a = fmaf(q0.x, r.idx, r.olx); b = fmaf(q0.y, r.idx, r.ohx);
+            float tn0 = fminf(a, b), tf0 = fmaxf(a, b);
+            a = fmaf(q0.z, r.idy, r.oly); b = fmaf(q0.w, r.idy, r.ohy);
+            tn0 = fmaxf(tn0, fminf(a, b)); tf0 = fminf(tf0, fmaxf(a, b));
+            a = fmaf(q2.x, r.idz, r.olz); b = fmaf(q2.y, r.idz, r.ohz);
+            tn0 = fmaxf(tn0, fminf(a, b)); tf0 = fminf(tf0, fmaxf(a, b));
+            tn0 = fmaxf(tn0, r.tmin_f); tf0 = fminf(tf0, r.tbest_f);
+            a = fmaf(q1.x, r.idx, r.olx); b = fmaf(q1.y, r.idx, r.ohx);
+            float tn1 = fminf(a, b), tf1 = fmaxf(a, b);
+            a = fmaf(q1.z, r.idy, r.oly); b = fmaf(q1.w, r.idy, r.ohy);
+            tn1 = fmaxf(tn1, fminf(a, b)); tf1 = fminf(tf1, fmaxf(a, b));
+            a = fmaf(q2.z, r.idz, r.olz); b = fmaf(q2.w, r.idz, r.ohz);
+            tn1 = fmaxf(tn1, fminf(a, b)); tf1 = fminf(tf1, fmaxf(a, b));
+            tn1 = fmaxf(tn1, r.tmin_f); tf1 = fminf(tf1, r.tbest_f);
+            const bool h0 = tn0 <= tf0 * TAKE_SLACK, h1 = tn1 <= tf1 * TAKE_SLACK;
+            const int32_t c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
+            if (h0 && h1) {
+                if (tn1 < tn0) { st.push(c0, tn0); node = c1; }
+                else { st.push(c1, tn1); node = c0; }
+            } else if (h0) {
+                node = c0;
+            } else if (h1) {
+                node = c1;
+            } else {
+                node = TAKE_NODE_DONE;
+                while (st.sp > 0) {
+                    int32_t nn; float tn;
+                    st.pop(nn, tn);
+                    if (tn <= r.tbest_f * TAKE_SLACK) { node = nn; break; }
+                }
+            }
+        }
+        // ---- 3. leaf phase ----
+        if (active && node != TAKE_NODE_DONE) {  // node < 0: a leaf
+            const int32_t code = ~node;
+            const int64_t first = code >> 3;
+            const int count = (code & 7) + 1;
+            const D3 o = mk3(r.o[0], r.o[1], r.o[2]), d = mk3(r.d[0], r.d[1], r.d[2]);
+            bool stop = false;
+            for (int k = 0; k < count && !stop; ++k) {
+                const double2 *T = sc.tris + 6 * (first + k);
+                const double2 a0 = __ldg(T), a1 = __ldg(T + 1), a2 = __ldg(T + 2), a3 = __ldg(T + 3), a4 = __ldg(T + 4),
+                              a5 = __ldg(T + 5);
+                if (COUNT) cnt->tri += 1;
+                double t, bu = 0, bv = 0;
+                bool ok;
+                if (a5.y == 0.0)
+                    ok = hit_triangle(mk3(a0.x, a0.y, a1.x), mk3(a2.x, a2.y, a3.x), mk3(a4.x, a4.y, a5.x), o, d, r.tmin, r.best_t, t,
+                                      bu, bv);
+                else
+                    ok = hit_sphere(mk3(a0.x, a0.y, a1.x), a3.y, o, d, r.tmin, r.best_t, t);
+                if (ok) {
+                    const long long bits = __double_as_longlong(a1.y);
+                    const int32_t prim = (int32_t)(bits & 0xffffffffLL), rank = (int32_t)(bits >> 32);
+                    if (t < r.best_t || out.prim < 0 || rank > out.rank) {
+                        out.prim = prim; out.rank = rank; out.t = t; out.u = bu; out.v = bv;
+                        r.best_t = t;
+                        r.tbest_f = __double2float_ru(t);
+                        if (ANY_HIT) stop = true;
+                    }
+                }
+            }
+            node = TAKE_NODE_DONE;
+            if (!(ANY_HIT && stop)) {
+                while (st.sp > 0) {
+                    int32_t nn; float tn;
+                    st.pop(nn, tn);
+                    if (tn <= r.tbest_f * TAKE_SLACK) { node = nn; break; }
+                }
+            }
+        }
+        // ---- 4. retire ----
+        const bool done = active && node == TAKE_NODE_DONE;
+        const unsigned dmask = __ballot_sync(0xffffffffu, done);
+        if (dmask) io.retire(dmask, done, item, out);
+        if (done) active = false;
+    }
+}
+
 }  // namespace take

@@ -74,16 +74,28 @@ struct Wave {
     int32_t n_slots, samples_in_wave;
     const int32_t *list_pixel;  // optional explicit (pixel, sample) list (take_gpu_radiance_samples)
     const int64_t *list_sample;
-    int32_t integrator, max_depth, sort_enabled, pad0;
+    int32_t integrator, max_depth, sort_enabled;
+    int32_t tile_w;  // > 0: image width, pixels are enumerated in 8x4 tiles (one warp = one tile); 0: row-major
     uint64_t seed;
 };
+
+// Pixel enumeration.  Consecutive indices walk 8x4 tiles so that the 32 primary rays of a warp form a compact bundle
+// (one warp = one tile) instead of a 32x1 strip; any bijection is fine for the result because a sample's random
+// stream is keyed by the pixel, not by the slot.
+__device__ __forceinline__ uint32_t pixel_of_index(const Wave &w, uint32_t idx) {
+    if (w.tile_w <= 0) return idx;
+    const uint32_t tiles_x = (uint32_t)w.tile_w >> 3;
+    const uint32_t tile = idx >> 5, in = idx & 31u;
+    const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    return (ty * 4u + (in >> 3)) * (uint32_t)w.tile_w + tx * 8u + (in & 7u);
+}
 
 __device__ __forceinline__ void slot_identity(const Wave &w, int slot, uint32_t &pixel, uint64_t &sample) {
     if (w.list_pixel) {
         pixel = (uint32_t)w.list_pixel[slot];
         sample = (uint64_t)w.list_sample[slot];
     } else {
-        pixel = (uint32_t)(w.chunk_base + slot % w.chunk_pixels);
+        pixel = pixel_of_index(w, (uint32_t)(w.chunk_base + slot % w.chunk_pixels));
         sample = (uint64_t)(w.sample0 + slot / w.chunk_pixels);
     }
 }
@@ -545,7 +557,7 @@ __global__ void k_accumulate(Wave w, double *sum, double *sumsq, int n_passes) {
         atomicAdd(&w.totals->samples, (unsigned long long)w.n_slots);
     }
     if (p >= w.chunk_pixels) return;
-    const size_t o = 3 * (size_t)(w.chunk_base + p);
+    const size_t o = 3 * (size_t)pixel_of_index(w, (uint32_t)(w.chunk_base + p));
     double a0 = sum[o], a1 = sum[o + 1], a2 = sum[o + 2];
     double b0 = 0, b1 = 0, b2 = 0;
     if (sumsq) { b0 = sumsq[o]; b1 = sumsq[o + 1]; b2 = sumsq[o + 2]; }
@@ -606,6 +618,127 @@ __global__ void __launch_bounds__(128) k_intersect_fast(DevScene sc, const TakeR
             }
         }
     }
+}
+
+// ---- warp-persistent variants (trace_warp_persistent): same results, different schedule ------------------------
+#ifndef TAKE_EXTEND_MIN_BLOCKS
+#define TAKE_EXTEND_MIN_BLOCKS 6
+#endif
+
+struct ExtendIO {
+    const Wave &w;
+    PassCounters &pc;
+    const int32_t *queue;
+    int slot;
+    __device__ __forceinline__ void load(uint32_t i, const DevScene &sc, LaneRay &r) {
+        slot = queue[i];
+        const RayRec *rr = w.ray + slot;
+        lane_ray_setup(r, sc, &rr->ox, &rr->dx, TAKE_EPS, rr->tmax);
+    }
+    // called by the whole warp; `mask` = lanes that retire a ray now
+    __device__ __forceinline__ void retire(unsigned mask, bool done, uint32_t, const HitOut &h) {
+        if (!done) return;
+        const int lane = threadIdx.x & 31;
+        const uint32_t key = h.prim < 0 ? 0u : 1u + (uint32_t)w_mtype[h.prim];
+        const unsigned peers = __match_any_sync(mask, key);
+        const int leader = __ffs(peers) - 1;
+        uint32_t rbase = 0;
+        if (lane == leader) rbase = atomicAdd(&pc.bins[key], (uint32_t)__popc(peers));
+        rbase = __shfl_sync(peers, rbase, leader);
+        HitRec hr;
+        hr.prim = h.prim;
+        hr.keyrank = (key << 28) | (rbase + __popc(peers & ((1u << lane) - 1u)));
+        hr.t = h.t; hr.u = h.u; hr.v = h.v;
+        w.hit[slot] = hr;
+    }
+    const uint8_t *w_mtype;
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128, TAKE_EXTEND_MIN_BLOCKS) k_extend2(DevScene sc, Wave w, int pass) {
+    __shared__ int32_t s_node[TAKE_STACK_SMEM * 128];
+    __shared__ float s_tn[TAKE_STACK_SMEM * 128];
+    TravStack st;
+    st.s_node = s_node + threadIdx.x;
+    st.s_tn = s_tn + threadIdx.x;
+    st.stride = 128;
+    PassCounters &pc = w.pass[pass];
+    ExtendIO io = {w, pc, w.q_extend[pass & 1], -1, sc.prim_mtype};
+    TravCounters cnt = {0, 0};
+    trace_warp_persistent<false, COUNT>(sc, io, pc.n_extend, &pc.fetch_extend, st, &cnt);
+    if (COUNT) {
+        atomicAdd(&w.totals->box_tests, cnt.box);
+        atomicAdd(&w.totals->tri_tests, cnt.tri);
+    }
+}
+
+struct ShadowIO {
+    const Wave &w;
+    int slot;
+    __device__ __forceinline__ void load(uint32_t i, const DevScene &sc, LaneRay &r) {
+        slot = w.q_shadow[i];
+        const RayRec *rr = w.ray + slot;
+        const ShadowRec *sr = w.shadow + slot;
+        lane_ray_setup(r, sc, &rr->ox, &sr->dx, TAKE_EPS, sr->tmax);
+    }
+    __device__ __forceinline__ void retire(unsigned, bool done, uint32_t, const HitOut &h) {
+        if (!done || h.prim >= 0) return;
+        const ShadowRec *sr = w.shadow + slot;
+        PathRec *p = w.path + slot;
+        p->rad[0] += sr->cx; p->rad[1] += sr->cy; p->rad[2] += sr->cz;
+    }
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128, TAKE_EXTEND_MIN_BLOCKS) k_shadow2(DevScene sc, Wave w, int pass) {
+    __shared__ int32_t s_node[TAKE_STACK_SMEM * 128];
+    __shared__ float s_tn[TAKE_STACK_SMEM * 128];
+    TravStack st;
+    st.s_node = s_node + threadIdx.x;
+    st.s_tn = s_tn + threadIdx.x;
+    st.stride = 128;
+    PassCounters &pc = w.pass[pass];
+    ShadowIO io = {w, -1};
+    TravCounters cnt = {0, 0};
+    trace_warp_persistent<true, COUNT>(sc, io, pc.n_shadow, &pc.fetch_shadow, st, &cnt);
+    if (COUNT) {
+        atomicAdd(&w.totals->shadow_box_tests, cnt.box);
+        atomicAdd(&w.totals->shadow_tri_tests, cnt.tri);
+    }
+}
+
+template <bool ANY_HIT>
+struct ApiIO {
+    const TakeRay *rays;
+    TakeHit *hits;
+    uint8_t *occ;
+    __device__ __forceinline__ void load(uint32_t i, const DevScene &sc, LaneRay &r) {
+        const TakeRay *ry = rays + i;
+        lane_ray_setup(r, sc, ry->origin, ry->dir, ry->tmin, ry->tmax);
+    }
+    __device__ __forceinline__ void retire(unsigned, bool done, uint32_t i, const HitOut &h) {
+        if (!done) return;
+        if (ANY_HIT) {
+            occ[i] = h.prim >= 0 ? 1 : 0;
+        } else {
+            TakeHit o;
+            o.prim_id = h.prim; o.pad = 0; o.t = h.t; o.u = h.u; o.v = h.v;
+            hits[i] = o;
+        }
+    }
+};
+
+template <bool ANY_HIT>
+__global__ void __launch_bounds__(128, TAKE_EXTEND_MIN_BLOCKS) k_intersect_fast2(DevScene sc, const TakeRay *rays, int64_t n, TakeHit *hits, uint8_t *occ,
+                                                         uint32_t *fetch) {
+    __shared__ int32_t s_node[TAKE_STACK_SMEM * 128];
+    __shared__ float s_tn[TAKE_STACK_SMEM * 128];
+    TravStack st;
+    st.s_node = s_node + threadIdx.x;
+    st.s_tn = s_tn + threadIdx.x;
+    st.stride = 128;
+    ApiIO<ANY_HIT> io = {rays, hits, occ};
+    trace_warp_persistent<ANY_HIT, false>(sc, io, (uint32_t)n, fetch, st, nullptr);
 }
 
 __global__ void k_intersect_exact(DevScene sc, const TakeRay *rays, int64_t n, TakeHit *hits) {

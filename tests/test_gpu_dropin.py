@@ -39,13 +39,17 @@ def test_cli_drop_in(tmp_path, gpu_lib):
     mean = s / 64
     assert img_gpu.shape == mean.shape
     assert np.abs(img_gpu - mean).max() <= 2.0 ** -10 * np.abs(mean).max() + 1e-6
-    # (b) statistically consistent with the stock CPU renderer (random_device seeds, so only statistics can agree)
+    # (b) statistically consistent with the stock CPU renderer.  It seeds from std::random_device (render.cpp:60) and
+    # writes only the mean image, so the yardstick is a control: the GPU-vs-stock error must not exceed the error
+    # between two GPU renders of the same spp with different seeds (which are per-sample identical to the reference's
+    # own integrator, see test_gpu_parity.py), and the image means must agree.
     out = subprocess.run([ob.REF_CLI, xml_cpu, "-max_depth", "5", "-t", str(os.cpu_count())], cwd=str(cpu_dir),
                          capture_output=True, text=True, timeout=1200)
     assert out.returncode == 0, out.stdout + out.stderr
     img_cpu = read_exr(str(cpu_dir / "image.exr"))
-    var = np.maximum(s2 / 64 - mean ** 2, 0) * 64 / 63
-    se2 = 2 * var / 64 + (2.0 ** -10 * mean) ** 2             # both images carry the same per-pixel noise level
-    z = np.abs(img_gpu - img_cpu)[se2 > 0] / np.sqrt(se2[se2 > 0])
-    assert (z <= 3).mean() >= 0.98
-    assert abs(img_gpu.mean() - img_cpu.mean()) <= 4 * np.sqrt(se2.sum()) / se2.size + 1e-3 * img_cpu.mean()
+    gs = api.GpuScene(b.flat())
+    other = gs.render_sums("mis", 5, 0, 64, seed=4242)[0] / 64
+    gs.close()
+    relmse = lambda x, y: np.mean((x - y) ** 2 / (y ** 2 + 1e-2))
+    assert relmse(img_gpu, img_cpu) <= 1.5 * relmse(other, mean), (relmse(img_gpu, img_cpu), relmse(other, mean))
+    assert abs(img_gpu.mean() - img_cpu.mean()) <= 0.02 * img_cpu.mean()
