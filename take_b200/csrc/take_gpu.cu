@@ -71,7 +71,8 @@ struct TakeScene {
     int64_t wave_capacity = 0;
     int blocks_extend = 0, blocks_shadow = 0, blocks_isect = 0, blocks_occl = 0;
     int blocks_extend2 = 0, blocks_shadow2 = 0, blocks_isect2 = 0, blocks_occl2 = 0;
-    int traversal = 2;  // 1: one ray per thread to completion; 2: warp-persistent while-while with re-fetch (TAKE_TRAVERSAL)
+    int traversal = 1;  // 1: one ray per thread to completion (default, measured faster); 2: warp-persistent while-while
+                        // with dynamic re-fetch (TAKE_TRAVERSAL=2)
     // diagnostics
     double build_ms_ref = 0, build_ms_fast = 0;
     int fast_depth = 0;
@@ -261,10 +262,12 @@ int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, d
     cudaStream_t st = s->stream;
     const int n_passes = o->max_depth + 2;
     CU(cudaMemsetAsync(w.pass, 0, sizeof(PassCounters) * (size_t)(n_passes + 1), st));
-    tm.begin(ST_GENERATE);
-    k_generate<<<(w.n_slots + 255) / 256, 256, 0, st>>>(s->dev, w);
-    tm.end();
-    launches++;
+    if (!w.fused_primary) {
+        tm.begin(ST_GENERATE);
+        k_generate<<<(w.n_slots + 255) / 256, 256, 0, st>>>(s->dev, w);
+        tm.end();
+        launches++;
+    }
     const int shade_blocks = std::max(1, std::min((w.n_slots + 127) / 128, s->sm_count * 64));
     const int scatter_blocks = std::max(1, std::min((w.n_slots + 255) / 256, s->sm_count * 16));
     for (int b = 0; b < n_passes; ++b) {
@@ -284,7 +287,9 @@ int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, d
             launches++;
         }
         tm.begin(ST_SHADE);
-        k_shade<<<shade_blocks, 128, 0, st>>>(s->dev, w, b);
+        if (o->integrator == TAKE_INTEGRATOR_MIS) k_shade<TAKE_INTEGRATOR_MIS><<<shade_blocks, 128, 0, st>>>(s->dev, w, b);
+        else if (o->integrator == TAKE_INTEGRATOR_RAW) k_shade<TAKE_INTEGRATOR_RAW><<<shade_blocks, 128, 0, st>>>(s->dev, w, b);
+        else k_shade<TAKE_INTEGRATOR_ONE_SAMPLE_MIS><<<shade_blocks, 128, 0, st>>>(s->dev, w, b);
         tm.end();
         launches += 2;
         if (o->integrator == TAKE_INTEGRATOR_MIS && b <= o->max_depth) {
@@ -326,6 +331,8 @@ void fill_wave_ptrs(TakeScene *s, Wave &w, const TakeRenderOpts *o) {
     w.max_depth = o->max_depth;
     w.sort_enabled = (o->flags & TAKE_RENDER_NO_SORT) ? 0 : 1;
     w.seed = o->seed;
+    // explicit sample lists (take_gpu_radiance_samples) and the v2 traversal keep the separate generate kernel
+    w.fused_primary = (s->traversal == 1 && !env_int("TAKE_NO_FUSE", 0)) ? 1 : 0;
     w.tile_w = (s->width % 8 == 0 && s->height % 4 == 0 && !env_int("TAKE_NO_TILES", 0)) ? s->width : 0;
 }
 
@@ -493,7 +500,7 @@ int take_gpu_scene_create(int device, const TakeSceneDesc *d, TakeScene **out) {
     s->blocks_shadow2 = blocks_for((const void *)k_shadow2<false>);
     s->blocks_isect2 = blocks_for((const void *)k_intersect_fast2<false>);
     s->blocks_occl2 = blocks_for((const void *)k_intersect_fast2<true>);
-    s->traversal = env_int("TAKE_TRAVERSAL", 2) == 1 ? 1 : 2;
+    s->traversal = env_int("TAKE_TRAVERSAL", 1) == 2 ? 2 : 1;
     CU(s->fetch.ensure(256));
     guard.ok = true;
     *out = s;
@@ -625,7 +632,7 @@ int take_gpu_render_device(TakeScene *s, const TakeRenderOpts *o, double *d_sum,
     CU(cudaSetDevice(s->device));
     const int64_t npix = (int64_t)s->width * s->height;
     const int64_t spp = o->spp_end - o->spp_begin;
-    const int64_t cap_env = std::max<int64_t>(1024, (int64_t)env_int("TAKE_WAVE_SLOTS", 1 << 22));
+    const int64_t cap_env = std::max<int64_t>(1024, (int64_t)env_int("TAKE_WAVE_SLOTS", 1 << 24));
     const int64_t capacity = std::min<int64_t>(cap_env, std::max<int64_t>(npix * std::max<int64_t>(spp, 1), 1024));
     if (int rc = ensure_wave(s, capacity)) return rc;
     CU(cudaMemsetAsync(s->totals.p, 0, sizeof(Totals), s->stream));

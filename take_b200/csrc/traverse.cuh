@@ -14,8 +14,11 @@
 
 namespace take {
 
+#ifndef TAKE_STACK_SMEM
 #define TAKE_STACK_SMEM 24   // entries per thread kept in shared memory
-#define TAKE_STACK_LOCAL 72  // overflow entries in local memory (tree depth limit = 96, checked on the host)
+#endif
+#define TAKE_STACK_LOCAL (96 - TAKE_STACK_SMEM)  // overflow entries in local memory (tree depth limit = 96, checked on the host)
+#define TAKE_STACK_SMEM_ALLOC (TAKE_STACK_SMEM > 0 ? TAKE_STACK_SMEM : 1)
 
 // ---- leaf tests: src/shape.cpp:44-78 (triangle) and :13-29 (sphere), accept/reject part ---------------
 __device__ __forceinline__ bool hit_triangle(D3 v0, D3 e1, D3 e2, D3 o, D3 d, double tmin, double tmax, double &t,
@@ -133,6 +136,13 @@ struct TravStack {
     }
 };
 
+// Reciprocal direction for the FMA slab form  t = plane * idir - (o -+ delta) * idir.  An infinite idir (zero direction
+// component) would turn that into inf - inf = NaN for exactly the slabs that contain the origin; clamping |idir| to
+// 1e18 keeps every product finite (|coordinate| * 1e18 << FLT_MAX), gives the correct signs (the delta padding makes
+// "origin inside the slab" robustly negative/positive), and still acts as infinity: the smallest exit distance it can
+// produce, delta * 1e18 >= 1e12 scene extents, is beyond any hit inside the scene bounds.
+__device__ __forceinline__ float safe_rcp(float d) { return fminf(fmaxf(1.0f / d, -1e18f), 1e18f); }
+
 #define TAKE_SLACK 1.00000191f  // 1 + 2^-19: relative slack on the exit distance (error analysis in DESIGN.md)
 
 struct TravCounters {
@@ -147,7 +157,7 @@ __device__ __forceinline__ void trace_fast(const DevScene &sc, D3 o, D3 d, doubl
     // FP32 image of the ray.  Every box plane is tested as  t = plane * idir - (o -+ delta) * idir  with one FMA;
     // delta (absolute) covers the rounding of the origin, of the product (o*idir) and of the FMA itself.
     const float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
-    const float idx = 1.0f / (float)d.x, idy = 1.0f / (float)d.y, idz = 1.0f / (float)d.z;
+    const float idx = safe_rcp((float)d.x), idy = safe_rcp((float)d.y), idz = safe_rcp((float)d.z);
     const float delta = 1.9073486e-6f * fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fmaxf(fabsf(oz), sc.abs_max));  // 2^-19
     const float olx = -(ox + delta) * idx, ohx = -(ox - delta) * idx;
     const float oly = -(oy + delta) * idy, ohy = -(oy - delta) * idy;
@@ -271,7 +281,7 @@ struct LaneRay {        // FP32 image of the ray for the box tests + the FP64 wi
 __device__ __forceinline__ void lane_ray_setup(LaneRay &r, const DevScene &sc, const double *o, const double *d, double tmin,
                                                double tmax) {
     const float ox = (float)o[0], oy = (float)o[1], oz = (float)o[2];
-    r.idx = 1.0f / (float)d[0]; r.idy = 1.0f / (float)d[1]; r.idz = 1.0f / (float)d[2];
+    r.idx = safe_rcp((float)d[0]); r.idy = safe_rcp((float)d[1]); r.idz = safe_rcp((float)d[2]);
     const float delta = 1.9073486e-6f * fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fmaxf(fabsf(oz), sc.abs_max));
     r.olx = -(ox + delta) * r.idx; r.ohx = -(ox - delta) * r.idx;
     r.oly = -(oy + delta) * r.idy; r.ohy = -(oy - delta) * r.idy;

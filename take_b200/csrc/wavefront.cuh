@@ -75,6 +75,7 @@ struct Wave {
     const int32_t *list_pixel;  // optional explicit (pixel, sample) list (take_gpu_radiance_samples)
     const int64_t *list_sample;
     int32_t integrator, max_depth, sort_enabled;
+    int32_t fused_primary;  // 1: no k_generate -- pass 0 of extend and shade compute the camera ray themselves
     int32_t tile_w;  // > 0: image width, pixels are enumerated in 8x4 tiles (one warp = one tile); 0: row-major
     uint64_t seed;
 };
@@ -114,11 +115,12 @@ __device__ __forceinline__ void queue_push(bool want, int32_t *queue, uint32_t *
     if (want) queue[base + __popc(mask & ((1u << lane) - 1u))] = value;
 }
 
-// ---- generate: src/render.cpp:65-75 -------------------------------------------------------------------
-__global__ void k_generate(DevScene sc, Wave w) {
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot == 0) w.pass[0].n_extend = (uint32_t)w.n_slots;
-    if (slot >= w.n_slots) return;
+#ifndef TAKE_V1_MIN_BLOCKS
+#define TAKE_V1_MIN_BLOCKS 1
+#endif
+
+// Camera ray of a slot: src/render.cpp:69-75 (jittered pinhole; first draw -> x, second -> y).  Consumes 2 draws.
+__device__ __forceinline__ void primary_ray(const DevScene &sc, const Wave &w, int slot, D3 &o, D3 &dir) {
     uint32_t pixel;
     uint64_t sample;
     slot_identity(w, slot, pixel, sample);
@@ -127,12 +129,27 @@ __global__ void k_generate(DevScene sc, Wave w) {
     Rng rng = {w.seed, sample, pixel, 0};
     const double jx = rng.next();
     const double jy = rng.next();
-    D3 dir = sub(add(mul(mul(sc.cam_u, (x + jx) / sc.width - 0.5), sc.viewport_w),
-                     mul(mul(sc.cam_v, (y + jy) / sc.height - 0.5), sc.viewport_h)),
-                 sc.cam_w);
+    dir = sub(add(mul(mul(sc.cam_u, (x + jx) / sc.width - 0.5), sc.viewport_w),
+                  mul(mul(sc.cam_v, (y + jy) / sc.height - 0.5), sc.viewport_h)),
+              sc.cam_w);
     dir = normalize(dir);
+    o = sc.lookfrom;
+}
+
+// Length of pass `pass`'s extend queue.  With fused primaries pass 0 has no queue: entry i is slot i.
+__device__ __forceinline__ uint32_t pass_count(const Wave &w, int pass) {
+    return (pass == 0 && w.fused_primary) ? (uint32_t)w.n_slots : w.pass[pass].n_extend;
+}
+
+// ---- generate: src/render.cpp:65-75 (only when the primaries are not fused into pass 0) ----------------------
+__global__ void k_generate(DevScene sc, Wave w) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot == 0) w.pass[0].n_extend = (uint32_t)w.n_slots;
+    if (slot >= w.n_slots) return;
+    D3 org, dir;
+    primary_ray(sc, w, slot, org, dir);
     RayRec r;
-    r.ox = sc.lookfrom.x; r.oy = sc.lookfrom.y; r.oz = sc.lookfrom.z;
+    r.ox = org.x; r.oy = org.y; r.oz = org.z;
     r.dx = dir.x; r.dy = dir.y; r.dz = dir.z;
     r.tmax = INFINITY;
     r.aux0 = r.aux1 = 0;
@@ -140,7 +157,7 @@ __global__ void k_generate(DevScene sc, Wave w) {
     PathRec p;
     p.thr[0] = p.thr[1] = p.thr[2] = 1.0;
     p.rad[0] = p.rad[1] = p.rad[2] = 0.0;
-    p.k = rng.k;
+    p.k = 2;
     p.depth = 0;
     p.flags = PEND_PRIMARY;
     p.pad = 0;
@@ -150,15 +167,16 @@ __global__ void k_generate(DevScene sc, Wave w) {
 
 // ---- extend: closest hit for every queued ray + histogram of the shading sort key ------------------------
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_extend(DevScene sc, Wave w, int pass) {
-    __shared__ int32_t s_node[TAKE_STACK_SMEM * 128];
-    __shared__ float s_tn[TAKE_STACK_SMEM * 128];
+__global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_extend(DevScene sc, Wave w, int pass) {
+    __shared__ int32_t s_node[TAKE_STACK_SMEM_ALLOC * 128];
+    __shared__ float s_tn[TAKE_STACK_SMEM_ALLOC * 128];
     TravStack st;
     st.s_node = s_node + threadIdx.x;
     st.s_tn = s_tn + threadIdx.x;
     st.stride = 128;
     PassCounters &pc = w.pass[pass];
-    const uint32_t n = pc.n_extend;
+    const uint32_t n = pass_count(w, pass);
+    const bool primary = pass == 0 && w.fused_primary;
     const int32_t *queue = w.q_extend[pass & 1];
     const int lane = threadIdx.x & 31;
     TravCounters cnt = {0, 0};
@@ -173,9 +191,17 @@ __global__ void __launch_bounds__(128) k_extend(DevScene sc, Wave w, int pass) {
         uint32_t key = 0;
         HitOut h;
         if (valid) {
-            slot = queue[i];
-            const RayRec r = w.ray[slot];
-            trace_fast<false, COUNT>(sc, mk3(r.ox, r.oy, r.oz), mk3(r.dx, r.dy, r.dz), TAKE_EPS, r.tmax, st, h, &cnt);
+            D3 o, d;
+            double tmax = INFINITY;
+            if (primary) {
+                slot = (int)i;
+                primary_ray(sc, w, slot, o, d);
+            } else {
+                slot = queue[i];
+                const RayRec r = w.ray[slot];
+                o = mk3(r.ox, r.oy, r.oz); d = mk3(r.dx, r.dy, r.dz); tmax = r.tmax;
+            }
+            trace_fast<false, COUNT>(sc, o, d, TAKE_EPS, tmax, st, h, &cnt);
             key = h.prim < 0 ? 0u : 1u + (uint32_t)sc.prim_mtype[h.prim];
         }
         // warp-aggregated histogram: lanes with the same key elect a leader that bumps the bin once
@@ -209,10 +235,11 @@ __global__ void k_scatter(Wave w, int pass) {
         for (int b = 0; b < TAKE_NBINS; ++b) { offs[b] = acc; acc += pc.bins[b]; }
     }
     __syncthreads();
-    const uint32_t n = pc.n_extend;
+    const uint32_t n = pass_count(w, pass);
+    const bool primary = pass == 0 && w.fused_primary;
     const int32_t *queue = w.q_extend[pass & 1];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int slot = queue[i];
+        const int slot = primary ? (int)i : queue[i];
         const uint32_t kr = w.hit[slot].keyrank;
         w.q_sorted[offs[kr >> 28] + (kr & 0x0fffffffu)] = slot;
     }
@@ -437,9 +464,14 @@ __device__ inline void shade_one_sample(ShadeCtx &c, const RayRec &ray, const Hi
     }
 }
 
-__global__ void __launch_bounds__(128) k_shade(DevScene sc, Wave w, int pass) {
+#ifndef TAKE_SHADE_MIN_BLOCKS
+#define TAKE_SHADE_MIN_BLOCKS 1
+#endif
+template <int INTEGRATOR>
+__global__ void __launch_bounds__(128, TAKE_SHADE_MIN_BLOCKS) k_shade(DevScene sc, Wave w, int pass) {
     PassCounters &pc = w.pass[pass];
-    const uint32_t n = pc.n_extend;
+    const uint32_t n = pass_count(w, pass);
+    const bool primary = pass == 0 && w.fused_primary;
     const int32_t *queue = w.sort_enabled ? w.q_sorted : w.q_extend[pass & 1];
     int32_t *q_next = w.q_extend[(pass + 1) & 1];
     // grid-stride with whole warps, so that the queue pushes below always see converged warps
@@ -449,10 +481,22 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, Wave w, int pass) {
         bool emit_extend = false, emit_shadow = false;
         int slot = -1, shaded = 0;
         if (valid) {
-            slot = queue[i];
-            const RayRec ray = w.ray[slot];
+            slot = (primary && !w.sort_enabled) ? (int)i : queue[i];
+            RayRec ray;
+            PathRec path;
             const HitRec hit = w.hit[slot];
-            const PathRec path = w.path[slot];
+            if (primary) {  // nothing was stored for the camera ray: recompute it (2 draws) and start the path
+                D3 o, d;
+                primary_ray(sc, w, slot, o, d);
+                ray.ox = o.x; ray.oy = o.y; ray.oz = o.z; ray.dx = d.x; ray.dy = d.y; ray.dz = d.z;
+                ray.tmax = INFINITY; ray.aux0 = ray.aux1 = 0;
+                path.thr[0] = path.thr[1] = path.thr[2] = 1.0;
+                path.rad[0] = path.rad[1] = path.rad[2] = 0.0;
+                path.k = 2; path.depth = 0; path.flags = PEND_PRIMARY; path.pad = 0;
+            } else {
+                ray = w.ray[slot];
+                path = w.path[slot];
+            }
             uint32_t pixel;
             uint64_t sample;
             slot_identity(w, slot, pixel, sample);
@@ -465,8 +509,8 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, Wave w, int pass) {
             c.pend_flags = 0;
             c.shaded = 0;
             c.org = mk3(ray.ox, ray.oy, ray.oz);
-            if (w.integrator == TAKE_INTEGRATOR_MIS) shade_mis(c, ray, hit, path);
-            else if (w.integrator == TAKE_INTEGRATOR_RAW) shade_raw(c, ray, hit, path);
+            if (INTEGRATOR == TAKE_INTEGRATOR_MIS) shade_mis(c, ray, hit, path);
+            else if (INTEGRATOR == TAKE_INTEGRATOR_RAW) shade_raw(c, ray, hit, path);
             else shade_one_sample(c, ray, hit, path);
             emit_extend = c.emit_extend;
             emit_shadow = c.emit_shadow;
@@ -511,9 +555,9 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, Wave w, int pass) {
 
 // ---- shadow-connect: any-hit query; unoccluded connections add throughput * C1 (path_tracing.h:53-60) ----------
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_shadow(DevScene sc, Wave w, int pass) {
-    __shared__ int32_t s_node[TAKE_STACK_SMEM * 128];
-    __shared__ float s_tn[TAKE_STACK_SMEM * 128];
+__global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_shadow(DevScene sc, Wave w, int pass) {
+    __shared__ int32_t s_node[TAKE_STACK_SMEM_ALLOC * 128];
+    __shared__ float s_tn[TAKE_STACK_SMEM_ALLOC * 128];
     TravStack st;
     st.s_node = s_node + threadIdx.x;
     st.s_tn = s_tn + threadIdx.x;
@@ -551,7 +595,7 @@ __global__ void k_accumulate(Wave w, double *sum, double *sumsq, int n_passes) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p == 0) {
         unsigned long long ext = 0, sh = 0;
-        for (int b = 0; b < n_passes; ++b) { ext += w.pass[b].n_extend; sh += w.pass[b].n_shadow; }
+        for (int b = 0; b < n_passes; ++b) { ext += pass_count(w, b); sh += w.pass[b].n_shadow; }
         atomicAdd(&w.totals->extend_rays, ext);
         atomicAdd(&w.totals->shadow_rays, sh);
         atomicAdd(&w.totals->samples, (unsigned long long)w.n_slots);
@@ -576,7 +620,7 @@ __global__ void k_gather_radiance(Wave w, double *out, int n_passes) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s == 0) {
         unsigned long long ext = 0, sh = 0;
-        for (int b = 0; b < n_passes; ++b) { ext += w.pass[b].n_extend; sh += w.pass[b].n_shadow; }
+        for (int b = 0; b < n_passes; ++b) { ext += pass_count(w, b); sh += w.pass[b].n_shadow; }
         atomicAdd(&w.totals->extend_rays, ext);
         atomicAdd(&w.totals->shadow_rays, sh);
         atomicAdd(&w.totals->samples, (unsigned long long)w.n_slots);
@@ -589,10 +633,10 @@ __global__ void k_gather_radiance(Wave w, double *out, int n_passes) {
 
 // ---- direct intersection entry points (take_gpu_intersect / take_gpu_occluded) -------------------------------
 template <bool ANY_HIT>
-__global__ void __launch_bounds__(128) k_intersect_fast(DevScene sc, const TakeRay *rays, int64_t n, TakeHit *hits, uint8_t *occ,
+__global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_intersect_fast(DevScene sc, const TakeRay *rays, int64_t n, TakeHit *hits, uint8_t *occ,
                                                         uint32_t *fetch) {
-    __shared__ int32_t s_node[TAKE_STACK_SMEM * 128];
-    __shared__ float s_tn[TAKE_STACK_SMEM * 128];
+    __shared__ int32_t s_node[TAKE_STACK_SMEM_ALLOC * 128];
+    __shared__ float s_tn[TAKE_STACK_SMEM_ALLOC * 128];
     TravStack st;
     st.s_node = s_node + threadIdx.x;
     st.s_tn = s_tn + threadIdx.x;
@@ -656,8 +700,8 @@ struct ExtendIO {
 
 template <bool COUNT>
 __global__ void __launch_bounds__(128, TAKE_EXTEND_MIN_BLOCKS) k_extend2(DevScene sc, Wave w, int pass) {
-    __shared__ int32_t s_node[TAKE_STACK_SMEM * 128];
-    __shared__ float s_tn[TAKE_STACK_SMEM * 128];
+    __shared__ int32_t s_node[TAKE_STACK_SMEM_ALLOC * 128];
+    __shared__ float s_tn[TAKE_STACK_SMEM_ALLOC * 128];
     TravStack st;
     st.s_node = s_node + threadIdx.x;
     st.s_tn = s_tn + threadIdx.x;
@@ -691,8 +735,8 @@ struct ShadowIO {
 
 template <bool COUNT>
 __global__ void __launch_bounds__(128, TAKE_EXTEND_MIN_BLOCKS) k_shadow2(DevScene sc, Wave w, int pass) {
-    __shared__ int32_t s_node[TAKE_STACK_SMEM * 128];
-    __shared__ float s_tn[TAKE_STACK_SMEM * 128];
+    __shared__ int32_t s_node[TAKE_STACK_SMEM_ALLOC * 128];
+    __shared__ float s_tn[TAKE_STACK_SMEM_ALLOC * 128];
     TravStack st;
     st.s_node = s_node + threadIdx.x;
     st.s_tn = s_tn + threadIdx.x;
@@ -731,8 +775,8 @@ struct ApiIO {
 template <bool ANY_HIT>
 __global__ void __launch_bounds__(128, TAKE_EXTEND_MIN_BLOCKS) k_intersect_fast2(DevScene sc, const TakeRay *rays, int64_t n, TakeHit *hits, uint8_t *occ,
                                                          uint32_t *fetch) {
-    __shared__ int32_t s_node[TAKE_STACK_SMEM * 128];
-    __shared__ float s_tn[TAKE_STACK_SMEM * 128];
+    __shared__ int32_t s_node[TAKE_STACK_SMEM_ALLOC * 128];
+    __shared__ float s_tn[TAKE_STACK_SMEM_ALLOC * 128];
     TravStack st;
     st.s_node = s_node + threadIdx.x;
     st.s_tn = s_tn + threadIdx.x;
