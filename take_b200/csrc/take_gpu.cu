@@ -66,9 +66,14 @@ struct TakeScene {
         prim_mtype, spheres, materials, lights, textures;
     std::vector<DeviceBuffer *> tex_data;
     // wave storage
-    DeviceBuffer ray, hit, path, pend, shadow, q0, q1, q_sorted, q_shadow, pass, totals, scratch_a, scratch_b, scratch_c,
-        fetch;
+    struct WaveBuffers {
+        DeviceBuffer ray, hit, path, pend, shadow, q0, q1, q_sorted, q_shadow, pass;
+    } wb[2];  // two waves in flight: set i is driven by streams[i]
+    DeviceBuffer totals, scratch_a, scratch_b, scratch_c, fetch;
+    cudaStream_t stream2 = nullptr;       // second wave stream (stream is the first and the API's stream)
+    cudaEvent_t ev_acc[2] = {nullptr, nullptr}, ev_begin = nullptr;
     int64_t wave_capacity = 0;
+    int wave_sets = 0;
     int blocks_extend = 0, blocks_shadow = 0, blocks_isect = 0, blocks_occl = 0;
     int blocks_extend2 = 0, blocks_shadow2 = 0, blocks_isect2 = 0, blocks_occl2 = 0;
     int traversal = 1;  // 1: one ray per thread to completion (default, measured faster); 2: warp-persistent while-while
@@ -80,6 +85,9 @@ struct TakeScene {
     int64_t num_fast_nodes = 0;
     ~TakeScene() {
         for (auto *b : tex_data) delete b;
+        for (auto e : ev_acc) if (e) cudaEventDestroy(e);
+        if (ev_begin) cudaEventDestroy(ev_begin);
+        if (stream2) cudaStreamDestroy(stream2);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -204,20 +212,26 @@ int host_build(const TakeSceneDesc *d, int threads, HostBuild &hb) {
     return TAKE_OK;
 }
 
-int ensure_wave(TakeScene *s, int64_t capacity) {
-    if (capacity <= s->wave_capacity) return TAKE_OK;
-    CU(s->ray.ensure(capacity * sizeof(RayRec)));
-    CU(s->hit.ensure(capacity * sizeof(HitRec)));
-    CU(s->path.ensure(capacity * sizeof(PathRec)));
-    CU(s->pend.ensure(capacity * sizeof(PendRec)));
-    CU(s->shadow.ensure(capacity * sizeof(ShadowRec)));
-    CU(s->q0.ensure(capacity * 4));
-    CU(s->q1.ensure(capacity * 4));
-    CU(s->q_sorted.ensure(capacity * 4));
-    CU(s->q_shadow.ensure(capacity * 4));
-    CU(s->pass.ensure(sizeof(PassCounters) * TAKE_MAX_PASSES));
+int ensure_wave(TakeScene *s, int64_t capacity, int sets) {
+    if (capacity <= s->wave_capacity && sets <= s->wave_sets) return TAKE_OK;
+    capacity = std::max(capacity, s->wave_capacity);
+    sets = std::max(sets, s->wave_sets);
+    for (int i = 0; i < sets; ++i) {
+        TakeScene::WaveBuffers &b = s->wb[i];
+        CU(b.ray.ensure(capacity * sizeof(RayRec)));
+        CU(b.hit.ensure(capacity * sizeof(HitRec)));
+        CU(b.path.ensure(capacity * sizeof(PathRec)));
+        CU(b.pend.ensure(capacity * sizeof(PendRec)));
+        CU(b.shadow.ensure(capacity * sizeof(ShadowRec)));
+        CU(b.q0.ensure(capacity * 4));
+        CU(b.q1.ensure(capacity * 4));
+        CU(b.q_sorted.ensure(capacity * 4));
+        CU(b.q_shadow.ensure(capacity * 4));
+        CU(b.pass.ensure(sizeof(PassCounters) * TAKE_MAX_PASSES));
+    }
     CU(s->totals.ensure(sizeof(Totals)));
     s->wave_capacity = capacity;
+    s->wave_sets = sets;
     return TAKE_OK;
 }
 
@@ -225,10 +239,13 @@ struct StageTimer {
     bool on = false;
     cudaStream_t stream;
     std::vector<cudaEvent_t> ev;
-    std::vector<int> stage;
+    std::vector<int> stage, pass_of;
     double ms[6] = {0, 0, 0, 0, 0, 0};
+    double ms_pass[6][TAKE_MAX_PASSES] = {};
+    int cur_pass = 0;
     void begin(int st) {
         if (!on) return;
+        pass_of.push_back(cur_pass);
         cudaEvent_t a;
         cudaEventCreate(&a);
         cudaEventRecord(a, stream);
@@ -249,17 +266,30 @@ struct StageTimer {
             float t = 0;
             cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]);
             ms[stage[i]] += t;
+            ms_pass[stage[i]][pass_of[i]] += t;
+        }
+        if (env_int("TAKE_PASS_TIMES", 0)) {  // development aid: per-pass stage times on stderr
+            static const char *names[6] = {"generate", "extend", "shade", "shadow", "sort", "other"};
+            for (int st = 1; st <= 3; ++st) {
+                fprintf(stderr, "[take_gpu] %-8s per pass (ms):", names[st]);
+                for (int b = 0; b < 12; ++b) fprintf(stderr, " %.3f", ms_pass[st][b]);
+                fprintf(stderr, "\n");
+            }
         }
         for (auto e : ev) cudaEventDestroy(e);
         ev.clear();
         stage.clear();
+        pass_of.clear();
     }
 };
 enum { ST_GENERATE = 0, ST_EXTEND, ST_SHADE, ST_SHADOW, ST_SORT, ST_OTHER };
 
+// `acc_after`: event the accumulation must wait for (the previous wave's accumulation: keeps the per-pixel summation
+// order and avoids concurrent read-modify-write of the image); `acc_done`: recorded after this wave's accumulation.
 int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, double *d_sumsq, double *d_list_out,
-                StageTimer &tm, bool count, int64_t &launches) {
-    cudaStream_t st = s->stream;
+                StageTimer &tm, bool count, int64_t &launches, cudaStream_t st, cudaEvent_t acc_after = nullptr,
+                cudaEvent_t acc_done = nullptr) {
+    tm.stream = st;
     const int n_passes = o->max_depth + 2;
     CU(cudaMemsetAsync(w.pass, 0, sizeof(PassCounters) * (size_t)(n_passes + 1), st));
     if (!w.fused_primary) {
@@ -271,6 +301,7 @@ int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, d
     const int shade_blocks = std::max(1, std::min((w.n_slots + 127) / 128, s->sm_count * 64));
     const int scatter_blocks = std::max(1, std::min((w.n_slots + 255) / 256, s->sm_count * 16));
     for (int b = 0; b < n_passes; ++b) {
+        tm.cur_pass = b;
         tm.begin(ST_EXTEND);
         if (s->traversal == 2) {
             if (count) k_extend2<true><<<s->blocks_extend2, 128, 0, st>>>(s->dev, w, b);
@@ -305,27 +336,30 @@ int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, d
             launches++;
         }
     }
+    if (acc_after) CU(cudaStreamWaitEvent(st, acc_after, 0));
     tm.begin(ST_OTHER);
     if (d_list_out) k_gather_radiance<<<(w.n_slots + 255) / 256, 256, 0, st>>>(w, d_list_out, n_passes);
     else k_accumulate<<<(w.chunk_pixels + 255) / 256, 256, 0, st>>>(w, d_sum, d_sumsq, n_passes);
     tm.end();
     launches++;
+    if (acc_done) CU(cudaEventRecord(acc_done, st));
     CU(cudaGetLastError());
     return TAKE_OK;
 }
 
-void fill_wave_ptrs(TakeScene *s, Wave &w, const TakeRenderOpts *o) {
+void fill_wave_ptrs(TakeScene *s, Wave &w, const TakeRenderOpts *o, int set = 0) {
     memset(&w, 0, sizeof(w));
-    w.ray = s->ray.as<RayRec>();
-    w.hit = s->hit.as<HitRec>();
-    w.path = s->path.as<PathRec>();
-    w.pend = s->pend.as<PendRec>();
-    w.shadow = s->shadow.as<ShadowRec>();
-    w.q_extend[0] = s->q0.as<int32_t>();
-    w.q_extend[1] = s->q1.as<int32_t>();
-    w.q_sorted = s->q_sorted.as<int32_t>();
-    w.q_shadow = s->q_shadow.as<int32_t>();
-    w.pass = s->pass.as<PassCounters>();
+    TakeScene::WaveBuffers &b = s->wb[set];
+    w.ray = b.ray.as<RayRec>();
+    w.hit = b.hit.as<HitRec>();
+    w.path = b.path.as<PathRec>();
+    w.pend = b.pend.as<PendRec>();
+    w.shadow = b.shadow.as<ShadowRec>();
+    w.q_extend[0] = b.q0.as<int32_t>();
+    w.q_extend[1] = b.q1.as<int32_t>();
+    w.q_sorted = b.q_sorted.as<int32_t>();
+    w.q_shadow = b.q_shadow.as<int32_t>();
+    w.pass = b.pass.as<PassCounters>();
     w.totals = s->totals.as<Totals>();
     w.integrator = o->integrator;
     w.max_depth = o->max_depth;
@@ -634,40 +668,66 @@ int take_gpu_render_device(TakeScene *s, const TakeRenderOpts *o, double *d_sum,
     const int64_t spp = o->spp_end - o->spp_begin;
     const int64_t cap_env = std::max<int64_t>(1024, (int64_t)env_int("TAKE_WAVE_SLOTS", 1 << 24));
     const int64_t capacity = std::min<int64_t>(cap_env, std::max<int64_t>(npix * std::max<int64_t>(spp, 1), 1024));
-    if (int rc = ensure_wave(s, capacity)) return rc;
-    CU(cudaMemsetAsync(s->totals.p, 0, sizeof(Totals), s->stream));
     StageTimer tm;
     tm.on = stats && ((o->flags & TAKE_RENDER_STAGE_TIMES) || env_int("TAKE_STAGE_TIMES", 0));
     tm.stream = s->stream;
     const bool count = (o->flags & TAKE_RENDER_COUNT_TESTS) || env_int("TAKE_COUNT_TESTS", 0) != 0;
+    // Two waves in flight on two streams: the thin late passes of one wave (few, long rays) overlap the fat early passes
+    // of the next, and the latency-bound shade kernels share the SMs with the issue-bound traversal kernels.  Per-kernel
+    // timing (TAKE_RENDER_STAGE_TIMES) needs kernels that run alone, so it serialises on one stream.
+    const int64_t chunk_pixels = std::min(npix, capacity & ~int64_t(31));
+    const int64_t per_wave_full = std::max<int64_t>(1, capacity / chunk_pixels);
+    const int64_t n_waves_est = ((npix + chunk_pixels - 1) / chunk_pixels) * ((std::max<int64_t>(spp, 1) + per_wave_full - 1) / per_wave_full);
+    const int sets = (!tm.on && n_waves_est > 1 && env_int("TAKE_OVERLAP", 1)) ? 2 : 1;
+    if (int rc = ensure_wave(s, capacity, sets)) return rc;
+    if (sets == 2 && !s->stream2) {
+        CU(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&s->ev_acc[0], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s->ev_acc[1], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s->ev_begin, cudaEventDisableTiming));
+    }
+    cudaStream_t streams[2] = {s->stream, sets == 2 ? s->stream2 : s->stream};
+    CU(cudaMemsetAsync(s->totals.p, 0, sizeof(Totals), s->stream));
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
     CU(cudaEventRecord(e0, s->stream));
+    if (sets == 2) {  // the second stream starts after everything already queued on the first (output buffers, totals)
+        CU(cudaEventRecord(s->ev_begin, s->stream));
+        CU(cudaStreamWaitEvent(s->stream2, s->ev_begin, 0));
+    }
     int64_t launches = 0, waves = 0;
-    Wave w;
-    fill_wave_ptrs(s, w, o);
-    const int64_t chunk_pixels = std::min(npix, capacity & ~int64_t(31));
+    Wave w[2];
+    fill_wave_ptrs(s, w[0], o, 0);
+    if (sets == 2) fill_wave_ptrs(s, w[1], o, 1);
+    cudaEvent_t prev_acc = nullptr;
     for (int64_t base = 0; base < npix; base += chunk_pixels) {
         const int64_t cp = std::min(chunk_pixels, npix - base);
         const int64_t per_wave = std::max<int64_t>(1, capacity / cp);
         for (int64_t s0 = o->spp_begin; s0 < o->spp_end; s0 += per_wave) {
             const int64_t ns = std::min(per_wave, o->spp_end - s0);
-            w.chunk_pixels = (int32_t)cp;
-            w.chunk_base = (int32_t)base;
-            w.sample0 = s0;
-            w.samples_in_wave = (int32_t)ns;
-            w.n_slots = (int32_t)(cp * ns);
-            if (int rc = launch_wave(s, w, o, d_sum, d_sumsq, nullptr, tm, count, launches)) return rc;
+            const int k = sets == 2 ? (int)(waves & 1) : 0;
+            Wave &wv = w[k];
+            wv.chunk_pixels = (int32_t)cp;
+            wv.chunk_base = (int32_t)base;
+            wv.sample0 = s0;
+            wv.samples_in_wave = (int32_t)ns;
+            wv.n_slots = (int32_t)(cp * ns);
+            cudaEvent_t done = sets == 2 ? s->ev_acc[k] : nullptr;
+            if (int rc = launch_wave(s, wv, o, d_sum, d_sumsq, nullptr, tm, count, launches, streams[k], prev_acc, done)) return rc;
+            prev_acc = done;
             waves++;
         }
     }
+    // join: accumulations are chained and are the last kernel of their wave, so the last one orders everything
+    if (sets == 2 && prev_acc) CU(cudaStreamWaitEvent(s->stream, prev_acc, 0));
     CU(cudaEventRecord(e1, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    tm.stream = s->stream;
     tm.collect();
     read_totals(s, stats, tm, ms, launches, waves);
     return TAKE_OK;
@@ -699,7 +759,7 @@ int take_gpu_radiance_samples(TakeScene *s, const TakeRenderOpts *o, int64_t n, 
     if (n == 0) return TAKE_OK;
     CU(cudaSetDevice(s->device));
     const int64_t cap = 1 << 20;
-    if (int rc = ensure_wave(s, std::min(n, cap))) return rc;
+    if (int rc = ensure_wave(s, std::min(n, cap), 1)) return rc;
     std::vector<int32_t> pixel((size_t)std::min(n, cap));
     StageTimer tm;
     tm.stream = s->stream;
@@ -724,7 +784,7 @@ int take_gpu_radiance_samples(TakeScene *s, const TakeRenderOpts *o, int64_t n, 
         w.samples_in_wave = 1;
         w.list_pixel = s->scratch_a.as<int32_t>();
         w.list_sample = s->scratch_b.as<int64_t>();
-        if (int rc = launch_wave(s, w, o, nullptr, nullptr, s->scratch_c.as<double>(), tm, false, launches)) return rc;
+        if (int rc = launch_wave(s, w, o, nullptr, nullptr, s->scratch_c.as<double>(), tm, false, launches, s->stream)) return rc;
         CU(cudaMemcpyAsync(rgb + 3 * off, s->scratch_c.p, m * 24, cudaMemcpyDeviceToHost, s->stream));
         CU(cudaStreamSynchronize(s->stream));
     }

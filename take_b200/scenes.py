@@ -445,6 +445,65 @@ def sphere_room(width=256, height=256, spp=16) -> SceneBuilder:
     return b
 
 
+def _icosphere(subdiv):
+    """Unit icosphere: (vertices [n,3], faces [m,3]); 20 * 4^subdiv faces."""
+    phi = (1 + 5 ** 0.5) / 2
+    v = np.array([[-1, phi, 0], [1, phi, 0], [-1, -phi, 0], [1, -phi, 0], [0, -1, phi], [0, 1, phi], [0, -1, -phi], [0, 1, -phi],
+                  [phi, 0, -1], [phi, 0, 1], [-phi, 0, -1], [-phi, 0, 1]], np.float64)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    f = np.array([[0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11], [1, 5, 9], [5, 11, 4], [11, 10, 2], [10, 7, 6],
+                  [7, 1, 8], [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8], [3, 8, 9], [4, 9, 5], [2, 4, 11], [6, 2, 10],
+                  [8, 6, 7], [9, 8, 1]], np.int64)
+    for _ in range(subdiv):
+        e = np.sort(np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]]), axis=1)
+        ue, inv = np.unique(e, axis=0, return_inverse=True)
+        mid = v[ue[:, 0]] + v[ue[:, 1]]
+        mid /= np.linalg.norm(mid, axis=1, keepdims=True)
+        m = len(v) + inv.reshape(3, -1)          # midpoint ids of edges (01), (12), (20) per face
+        v = np.concatenate([v, mid])
+        a, b, c = f[:, 0], f[:, 1], f[:, 2]
+        f = np.concatenate([np.stack([a, m[0], m[2]], 1), np.stack([b, m[1], m[0]], 1), np.stack([c, m[2], m[1]], 1),
+                            np.stack([m[0], m[1], m[2]], 1)])
+    return v, f.astype(np.int32)
+
+
+def instanced_spheres(width=3840, height=2160, spp=4096, copies_side=11, subdiv=6, seed=5, n_lights=64) -> SceneBuilder:
+    """Config 5: copies_side^2 copies (random yaw) of a displaced icosphere (20*4^subdiv faces: subdiv 6 = 81 920, so
+    11x11 copies + the ground = 10.04 M triangles; the reference has no instancing, so the copies are flattened) on a ground grid,
+    extent about +-1000, a mix of diffuse and blinn_microfacet materials, n_lights quad lights."""
+    rng = np.random.default_rng(seed)
+    sv, sf = _icosphere(subdiv)
+    b = SceneBuilder(width, height, (0, 900, 2200), (0, 0, 0), (0, 1, 0), 40.0, spp, (0.02, 0.03, 0.05))
+    mats = [b.material(sio.MAT_DIFFUSE, (0.7, 0.7, 0.7)), b.material(sio.MAT_DIFFUSE, (0.7, 0.3, 0.2)),
+            b.material(sio.MAT_BLINN_MICROFACET, (0.8, 0.7, 0.4), exponent=80),
+            b.material(sio.MAT_BLINN_MICROFACET, (0.5, 0.6, 0.8), exponent=30)]
+    black = b.material(sio.MAT_DIFFUSE, (0, 0, 0))
+    # bumpy unit sphere shared by all copies
+    bump = 1.0 + 0.08 * np.sin(7 * sv[:, 0]) * np.sin(5 * sv[:, 1] + 1.0) * np.sin(6 * sv[:, 2] + 2.0)
+    base = sv * bump[:, None]
+    pitch = 2000.0 / copies_side
+    for j in range(copies_side):
+        for i in range(copies_side):
+            yaw = rng.uniform(0, 2 * np.pi)
+            c, s = np.cos(yaw), np.sin(yaw)
+            R = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+            r = 0.38 * pitch * rng.uniform(0.7, 1.0)
+            centre = np.array([-1000 + (i + 0.5) * pitch, r * 1.05, -1000 + (j + 0.5) * pitch])
+            P = base @ R.T * r + centre
+            N = sv @ R.T
+            b.mesh(P, sf, N, None, mats[(i + j * copies_side) % len(mats)])
+    gp, gt, gn, guv = _grid_mesh(256, 1100.0, lambda X, Z: 4.0 * np.sin(0.01 * X) * np.cos(0.013 * Z))
+    b.mesh(gp, gt, gn, guv, mats[0])
+    side = int(np.ceil(np.sqrt(n_lights)))
+    for k in range(n_lights):
+        lx = -900 + 1800 * ((k % side) + 0.5) / side
+        lz = -900 + 1800 * ((k // side) + 0.5) / side
+        h = 40.0
+        b.quad((lx - h, 700, lz - h), (lx + h, 700, lz - h), (lx + h, 700, lz + h), (lx - h, 700, lz + h), black,
+               radiance=(30, 28, 25))
+    return b
+
+
 def build(name: str, **kw) -> SceneBuilder:
     return {"cornell": cornell_box, "heightfield": heightfield, "multi_light": multi_light,
-            "textured": textured_room, "spheres": sphere_room}[name](**kw)
+            "textured": textured_room, "spheres": sphere_room, "instanced": instanced_spheres}[name](**kw)

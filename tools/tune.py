@@ -35,3 +35,5 @@ for tag, env in variants:
         e["TAKE_GPU_LIB"] = os.path.join(ROOT, "take_b200", env["LIB"])
     r = subprocess.run([sys.executable, __file__], env=e, capture_output=True, text=True)
     print(r.stdout.strip() or ("FAILED " + tag + " " + r.stderr[-400:]))
+    if "[take_gpu]" in r.stderr:
+        print("\n".join(l for l in r.stderr.splitlines() if l.startswith("[take_gpu]")))
