@@ -327,7 +327,7 @@ def run_ours(args):
         "samples_per_s": samples_all / (ms * 1e-3),
         "config": {"workload": WORKLOAD, "integrator": INTEGRATOR, "max_depth": MAX_DEPTH, "resolution": [W, H],
                    "triangles": flat.num_prims, "spp_per_step_per_gpu": S, "parallelism": f"spp-range x{world}, scene replicated",
-                   "l2": "per-step working set (2M-4M path records, 256 B each, + 130 MB of tree and triangles) exceeds the 126 MB L2",
+                   "l2": "inputs larger than L2: each wave streams 16.6 M path records (272 B/slot, 4.5 GB) besides 130 MB of tree + leaf records (L2 is 126 MB); no explicit flush",
                    "bvh": {"nodes": int(info["fast_nodes"]), "depth": int(info["fast_tree_depth"]),
                            "build_ms": info["build_ms_fast_tree"] + info["build_ms_reference_tree"]}},
         "e2e": e2e, "gpu_launches": int(launches_all), "clocks": clock_info, "roofline": roofline, "cpu_baseline": base,

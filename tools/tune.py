@@ -6,11 +6,12 @@ sys.path.insert(0, ROOT)
 def child():
     from take_b200 import api, scenes
     integ = os.environ.get("TUNE_INTEGRATOR", "one_sample_mis")
+    spp = int(os.environ.get("TUNE_SPP", "16"))
     flat = scenes.heightfield().flat()
     gs = api.GpuScene(flat)
     best = None
     for rep in range(4):
-        s, s2, st = gs.render_sums(integ, 5, 0, 8, seed=1, flags=api.RENDER_STAGE_TIMES if rep == 3 else 0)
+        s, s2, st = gs.render_sums(integ, 5, 0, spp, seed=1, flags=api.RENDER_STAGE_TIMES if rep == 3 else 0)
         if rep < 3 and (best is None or st["ms_total"] < best): best = st["ms_total"]
     rays = st["extend_rays"] + st["shadow_rays"]
     print(json.dumps(dict(tag=os.environ.get("TUNE_TAG"), ms_best=round(best, 3), mrays=round(rays / best / 1e3, 1),
