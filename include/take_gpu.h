@@ -208,6 +208,7 @@ int take_gpu_host_build(const TakeSceneDesc *desc, TakeHostBuild **out);
 int take_gpu_host_build_info(TakeHostBuild *h, double *out8);
 int take_gpu_host_build_copy(TakeHostBuild *h, void *ref_nodes, int32_t *dfs_rank, void *fast_nodes, int32_t *leaf_prims,
                              double *leaf_records);
+int64_t take_gpu_host_build_wide(TakeHostBuild *h, void *wide_nodes); /* returns the node count; copies if non-NULL */
 int take_gpu_host_build_free(TakeHostBuild *h);
 
 const char *take_gpu_last_error(void);

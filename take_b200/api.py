@@ -214,7 +214,10 @@ FAST_NODE_DTYPE = np.dtype([("c0lox", "<f4"), ("c0hix", "<f4"), ("c0loy", "<f4")
                             ("c1lox", "<f4"), ("c1hix", "<f4"), ("c1loy", "<f4"), ("c1hiy", "<f4"),
                             ("c0loz", "<f4"), ("c0hiz", "<f4"), ("c1loz", "<f4"), ("c1hiz", "<f4"),
                             ("child0", "<i4"), ("child1", "<i4"), ("count0", "<i4"), ("count1", "<i4")])
-assert REF_NODE_DTYPE.itemsize == 64 and FAST_NODE_DTYPE.itemsize == 64
+WIDE_NODE_DTYPE = np.dtype([("lox", "<f4", 4), ("hix", "<f4", 4), ("loy", "<f4", 4), ("hiy", "<f4", 4), ("loz", "<f4", 4),
+                            ("hiz", "<f4", 4), ("child", "<i4", 4), ("count", "<i4", 4)])
+WIDE_EMPTY = 0x7fffffff
+assert REF_NODE_DTYPE.itemsize == 64 and FAST_NODE_DTYPE.itemsize == 64 and WIDE_NODE_DTYPE.itemsize == 128
 
 
 def host_build(flat: FlatScene) -> dict:
@@ -238,7 +241,11 @@ def host_build(flat: FlatScene) -> dict:
         recs = np.zeros((n_prims, 12), np.float64)
         _check(L.take_gpu_host_build_copy(h, ref.ctypes.data, rank.ctypes.data, fast.ctypes.data, leaf.ctypes.data,
                                           recs.ctypes.data))
+        L.take_gpu_host_build_wide.restype = C.c_int64
+        L.take_gpu_host_build_wide.argtypes = [C.c_void_p, C.c_void_p]
+        wide = np.zeros(int(L.take_gpu_host_build_wide(h, None)), WIDE_NODE_DTYPE)
+        L.take_gpu_host_build_wide(h, wide.ctypes.data)
     finally:
         L.take_gpu_host_build_free(h)
-    return dict(ref_nodes=ref, ref_root=root, dfs_rank=rank, fast_nodes=fast, leaf_prims=leaf, leaf_records=recs,
+    return dict(ref_nodes=ref, ref_root=root, dfs_rank=rank, fast_nodes=fast, wide_nodes=wide, leaf_prims=leaf, leaf_records=recs,
                 depth=depth, abs_max=float(info[5]), ms_ref=float(info[6]), ms_fast=float(info[7]))

@@ -301,6 +301,80 @@ struct Flattener {
     }
 };
 
+// Collapse the binary SAH tree into 4-wide nodes: start from a binary node's two children and keep replacing the inner
+// child with the largest surface area by its own two children until there are four (or only leaves are left).
+struct WideFlattener {
+    const std::vector<TmpNode> &tmp;
+    std::vector<WideNode> &out;
+    float pad;
+    int depth = 0;
+
+    void set_child(WideNode &n, int k, const TmpNode *c, int32_t idx, int32_t cnt) {
+        if (c) {
+            n.lox[k] = round_down(c->box.lo[0], pad); n.hix[k] = round_up(c->box.hi[0], pad);
+            n.loy[k] = round_down(c->box.lo[1], pad); n.hiy[k] = round_up(c->box.hi[1], pad);
+            n.loz[k] = round_down(c->box.lo[2], pad); n.hiz[k] = round_up(c->box.hi[2], pad);
+        } else {
+            n.lox[k] = n.loy[k] = n.loz[k] = INFINITY;
+            n.hix[k] = n.hiy[k] = n.hiz[k] = -INFINITY;
+        }
+        n.child[k] = idx;
+        n.count[k] = cnt;
+    }
+
+    void run(int32_t root) {
+        struct Item { int32_t tmp_id, out_id, depth; };
+        std::vector<Item> stack;
+        out.clear();
+        out.reserve(tmp.size() / 3 + 2);
+        const TmpNode &r = tmp[root];
+        out.emplace_back();
+        if (r.count > 0 || r.left < 0) {  // root is a leaf or the tree is empty
+            memset(&out[0], 0, sizeof(WideNode));
+            for (int k = 0; k < 4; ++k) set_child(out[0], k, nullptr, TAKE_WIDE_EMPTY, 0);
+            if (r.count > 0) set_child(out[0], 0, &r, leaf_code(r.first, r.count), r.count);
+            depth = 1;
+            return;
+        }
+        stack.push_back({root, 0, 1});
+        while (!stack.empty()) {
+            Item it = stack.back();
+            stack.pop_back();
+            depth = std::max(depth, it.depth);
+            int32_t kids[4];
+            int nk = 0;
+            kids[nk++] = tmp[it.tmp_id].left;
+            kids[nk++] = tmp[it.tmp_id].right;
+            while (nk < 4) {
+                int best = -1;
+                double best_area = -1;
+                for (int k = 0; k < nk; ++k) {
+                    const TmpNode &c = tmp[kids[k]];
+                    if (c.count > 0) continue;  // a leaf stays a leaf
+                    double a = half_area(c.box.lo, c.box.hi);
+                    if (a > best_area) { best_area = a; best = k; }
+                }
+                if (best < 0) break;
+                const TmpNode &c = tmp[kids[best]];
+                kids[best] = c.left;
+                kids[nk++] = c.right;
+            }
+            for (int k = 0; k < 4; ++k) {
+                if (k >= nk) { set_child(out[it.out_id], k, nullptr, TAKE_WIDE_EMPTY, 0); continue; }
+                const TmpNode *c = &tmp[kids[k]];
+                if (c->count > 0) {
+                    set_child(out[it.out_id], k, c, leaf_code(c->first, c->count), c->count);
+                } else {
+                    int32_t id = (int32_t)out.size();
+                    out.emplace_back();
+                    set_child(out[it.out_id], k, c, id, 0);
+                    stack.push_back({kids[k], id, it.depth + 1});
+                }
+            }
+        }
+    }
+};
+
 }  // namespace
 
 void build_reference_tree(const Aabb *boxes, int64_t n, int threads, RefTree &out) {
@@ -328,6 +402,9 @@ void build_fast_tree(const Aabb *boxes, int64_t n, int max_leaf, float pad, int 
     Flattener f{b.nodes, out.nodes, pad};
     f.run(root);
     out.depth = f.depth;
+    WideFlattener wf{b.nodes, out.wide, pad};
+    wf.run(root);
+    out.wide_depth = wf.depth;
     // SAH cost of the final tree (diagnostic)
     double cost = 0, root_area = n > 0 ? half_area(b.nodes[root].box.lo, b.nodes[root].box.hi) : 0;
     if (root_area > 0) {

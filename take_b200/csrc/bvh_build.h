@@ -32,6 +32,16 @@ struct alignas(16) FastNode {  // 64 bytes = 4 x float4
 };
 static_assert(sizeof(FastNode) == 64, "FastNode must be 64 bytes");
 
+// 4-wide node, 128 bytes = 8 x float4: per-axis lo / hi planes of the four children (SoA, one float4 each), the four
+// child links, and padding to a full 128-byte line.  Links as in FastNode; an unused child is TAKE_WIDE_EMPTY.
+struct alignas(16) WideNode {
+    float lox[4], hix[4], loy[4], hiy[4], loz[4], hiz[4];
+    int32_t child[4];
+    int32_t count[4];  // leaf primitive counts (diagnostics)
+};
+static_assert(sizeof(WideNode) == 128, "WideNode must be 128 bytes");
+#define TAKE_WIDE_EMPTY 0x7fffffff
+
 struct RefTree {
     std::vector<RefNode> nodes;
     int32_t root = -1;
@@ -40,8 +50,9 @@ struct RefTree {
 
 struct FastTree {
     std::vector<FastNode> nodes;     // node 0 is the root (always an inner node, possibly with an empty child 1)
+    std::vector<WideNode> wide;      // the same tree collapsed to 4-wide nodes (node 0 is the root)
     std::vector<int32_t> leaf_prims; // primitive ids in leaf order; a leaf is a contiguous slot range
-    int depth = 0;
+    int depth = 0, wide_depth = 0;
     double sah_cost = 0;
 };
 

@@ -62,7 +62,7 @@ struct TakeScene {
     DevScene dev{};
     int width = 0, height = 0;
     // scene storage
-    DeviceBuffer nodes, tris, ref_nodes, positions, normals, uvs, indices, prim_material, prim_light, dfs_rank, prim_flags,
+    DeviceBuffer nodes, wide_nodes, tris, ref_nodes, positions, normals, uvs, indices, prim_material, prim_light, dfs_rank, prim_flags,
         prim_mtype, spheres, materials, lights, textures;
     std::vector<DeviceBuffer *> tex_data;
     // wave storage
@@ -76,6 +76,7 @@ struct TakeScene {
     int wave_sets = 0;
     int blocks_extend = 0, blocks_shadow = 0, blocks_isect = 0, blocks_occl = 0;
     int blocks_extend2 = 0, blocks_shadow2 = 0, blocks_isect2 = 0, blocks_occl2 = 0;
+    bool wide = true;   // 4-wide nodes (TAKE_BVH_WIDTH=4, default) or binary nodes (TAKE_BVH_WIDTH=2)
     int traversal = 1;  // 1: one ray per thread to completion (default, measured faster); 2: warp-persistent while-while
                         // with dynamic re-fetch (TAKE_TRAVERSAL=2)
     // diagnostics
@@ -307,8 +308,13 @@ int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, d
             if (count) k_extend2<true><<<s->blocks_extend2, 128, 0, st>>>(s->dev, w, b);
             else k_extend2<false><<<s->blocks_extend2, 128, 0, st>>>(s->dev, w, b);
         } else {
-            if (count) k_extend<true><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
-            else k_extend<false><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
+            if (s->wide) {
+                if (count) k_extend<true, true><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
+                else k_extend<false, true><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
+            } else {
+                if (count) k_extend<true, false><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
+                else k_extend<false, false><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
+            }
         }
         tm.end();
         if (w.sort_enabled) {
@@ -329,8 +335,13 @@ int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, d
                 if (count) k_shadow2<true><<<s->blocks_shadow2, 128, 0, st>>>(s->dev, w, b);
                 else k_shadow2<false><<<s->blocks_shadow2, 128, 0, st>>>(s->dev, w, b);
             } else {
-                if (count) k_shadow<true><<<s->blocks_shadow, 128, 0, st>>>(s->dev, w, b);
-                else k_shadow<false><<<s->blocks_shadow, 128, 0, st>>>(s->dev, w, b);
+                if (s->wide) {
+                    if (count) k_shadow<true, true><<<s->blocks_shadow, 128, 0, st>>>(s->dev, w, b);
+                    else k_shadow<false, true><<<s->blocks_shadow, 128, 0, st>>>(s->dev, w, b);
+                } else {
+                    if (count) k_shadow<true, false><<<s->blocks_shadow, 128, 0, st>>>(s->dev, w, b);
+                    else k_shadow<false, false><<<s->blocks_shadow, 128, 0, st>>>(s->dev, w, b);
+                }
             }
             tm.end();
             launches++;
@@ -450,6 +461,7 @@ int take_gpu_scene_create(int device, const TakeSceneDesc *d, TakeScene **out) {
 
     int rc;
     if ((rc = upload(s->nodes, fast.nodes.data(), fast.nodes.size(), st))) return rc;
+    if ((rc = upload(s->wide_nodes, fast.wide.data(), fast.wide.size(), st))) return rc;
     if ((rc = upload(s->tris, tris.data(), tris.size(), st))) return rc;
     if ((rc = upload(s->ref_nodes, ref.nodes.data(), ref.nodes.size(), st))) return rc;
     if ((rc = upload(s->positions, d->positions, (size_t)d->num_vertices * 3, st))) return rc;
@@ -478,6 +490,7 @@ int take_gpu_scene_create(int device, const TakeSceneDesc *d, TakeScene **out) {
 
     DevScene &v = s->dev;
     v.nodes = s->nodes.as<float4>();
+    v.wide_nodes = s->wide_nodes.as<float4>();
     v.tris = s->tris.as<double2>();
     v.ref_nodes = s->ref_nodes.as<RefNode>();
     v.ref_root = ref.root;
@@ -526,10 +539,18 @@ int take_gpu_scene_create(int device, const TakeSceneDesc *d, TakeScene **out) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
         return per_sm * s->sm_count;
     };
-    s->blocks_extend = blocks_for((const void *)k_extend<false>);
-    s->blocks_shadow = blocks_for((const void *)k_shadow<false>);
-    s->blocks_isect = blocks_for((const void *)k_intersect_fast<false>);
-    s->blocks_occl = blocks_for((const void *)k_intersect_fast<true>);
+    s->wide = env_int("TAKE_BVH_WIDTH", 4) == 4;
+    if (s->wide) {
+        s->blocks_extend = blocks_for((const void *)k_extend<false, true>);
+        s->blocks_shadow = blocks_for((const void *)k_shadow<false, true>);
+        s->blocks_isect = blocks_for((const void *)k_intersect_fast<false, true>);
+        s->blocks_occl = blocks_for((const void *)k_intersect_fast<true, true>);
+    } else {
+        s->blocks_extend = blocks_for((const void *)k_extend<false, false>);
+        s->blocks_shadow = blocks_for((const void *)k_shadow<false, false>);
+        s->blocks_isect = blocks_for((const void *)k_intersect_fast<false, false>);
+        s->blocks_occl = blocks_for((const void *)k_intersect_fast<true, false>);
+    }
     s->blocks_extend2 = blocks_for((const void *)k_extend2<false>);
     s->blocks_shadow2 = blocks_for((const void *)k_shadow2<false>);
     s->blocks_isect2 = blocks_for((const void *)k_intersect_fast2<false>);
@@ -593,6 +614,12 @@ int take_gpu_host_build_copy(TakeHostBuild *h, void *ref_nodes, int32_t *dfs_ran
     if (leaf_records) memcpy(leaf_records, b.tris.data(), b.tris.size() * 8);
     return TAKE_OK;
 }
+// 4-wide nodes (128 B each: 24 floats, 4 int32 links, 4 int32 counts); returns their number, copies if `wide_nodes` != NULL
+int64_t take_gpu_host_build_wide(TakeHostBuild *h, void *wide_nodes) {
+    if (!h) return fail(TAKE_E_INVALID, "null argument");
+    if (wide_nodes) memcpy(wide_nodes, h->hb.fast.wide.data(), h->hb.fast.wide.size() * sizeof(WideNode));
+    return (int64_t)h->hb.fast.wide.size();
+}
 int take_gpu_host_build_free(TakeHostBuild *h) {
     delete h;
     return TAKE_OK;
@@ -610,7 +637,8 @@ int take_gpu_intersect_device(TakeScene *s, const TakeRay *d_rays, int64_t n, Ta
         if (s->traversal == 2)
             k_intersect_fast2<false><<<s->blocks_isect2, 128, 0, s->stream>>>(s->dev, d_rays, n, d_hits, nullptr, s->fetch.as<uint32_t>());
         else
-            k_intersect_fast<false><<<s->blocks_isect, 128, 0, s->stream>>>(s->dev, d_rays, n, d_hits, nullptr, s->fetch.as<uint32_t>());
+            if (s->wide) k_intersect_fast<false, true><<<s->blocks_isect, 128, 0, s->stream>>>(s->dev, d_rays, n, d_hits, nullptr, s->fetch.as<uint32_t>());
+            else k_intersect_fast<false, false><<<s->blocks_isect, 128, 0, s->stream>>>(s->dev, d_rays, n, d_hits, nullptr, s->fetch.as<uint32_t>());
     } else {
         return fail(TAKE_E_INVALID, "unknown intersect flags");
     }
@@ -651,8 +679,12 @@ int take_gpu_occluded(TakeScene *s, const TakeRay *rays, int64_t n, uint8_t *occ
             k_intersect_fast2<true><<<s->blocks_occl2, 128, 0, s->stream>>>(s->dev, s->scratch_a.as<TakeRay>(), m, nullptr,
                                                                            s->scratch_b.as<uint8_t>(), s->fetch.as<uint32_t>());
         else
-            k_intersect_fast<true><<<s->blocks_occl, 128, 0, s->stream>>>(s->dev, s->scratch_a.as<TakeRay>(), m, nullptr,
-                                                                          s->scratch_b.as<uint8_t>(), s->fetch.as<uint32_t>());
+            if (s->wide)
+                k_intersect_fast<true, true><<<s->blocks_occl, 128, 0, s->stream>>>(s->dev, s->scratch_a.as<TakeRay>(), m, nullptr,
+                                                                                    s->scratch_b.as<uint8_t>(), s->fetch.as<uint32_t>());
+            else
+                k_intersect_fast<true, false><<<s->blocks_occl, 128, 0, s->stream>>>(s->dev, s->scratch_a.as<TakeRay>(), m, nullptr,
+                                                                                     s->scratch_b.as<uint8_t>(), s->fetch.as<uint32_t>());
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(occluded + off, s->scratch_b.p, m, cudaMemcpyDeviceToHost, s->stream));
         CU(cudaStreamSynchronize(s->stream));

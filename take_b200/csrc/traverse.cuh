@@ -251,6 +251,121 @@ __device__ __forceinline__ void trace_fast(const DevScene &sc, D3 o, D3 d, doubl
 
 
 // ---------------------------------------------------------------------------------------------------------
+// 4-wide variant of trace_fast: same conservative slab arithmetic, same FP64 leaf test and tie rule, on 128-byte
+// nodes that hold four children (bvh_build.h: WideNode).  Half as many dependent node fetches per ray; the up to
+// four hits of a node are ordered near-to-far with a 5-comparator network on (distance bits | child slot) keys.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cswap(uint32_t &a, uint32_t &b) {
+    const uint32_t lo = min(a, b), hi = max(a, b);
+    a = lo; b = hi;
+}
+
+template <bool ANY_HIT, bool COUNT>
+__device__ __forceinline__ void trace_fast4(const DevScene &sc, D3 o, D3 d, double tmin, double tmax, TravStack &st,
+                                            HitOut &out, TravCounters *cnt) {
+    out.prim = -1; out.rank = -1; out.t = 0; out.u = 0; out.v = 0;
+    if (sc.num_prims <= 0) return;
+    const float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
+    const float idx = safe_rcp((float)d.x), idy = safe_rcp((float)d.y), idz = safe_rcp((float)d.z);
+    const float delta = 1.9073486e-6f * fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fmaxf(fabsf(oz), sc.abs_max));  // 2^-19
+    const float olx = -(ox + delta) * idx, ohx = -(ox - delta) * idx;
+    const float oly = -(oy + delta) * idy, ohy = -(oy - delta) * idy;
+    const float olz = -(oz + delta) * idz, ohz = -(oz - delta) * idz;
+    const float tmin_f = __double2float_rd(tmin);
+    float tbest_f = __double2float_ru(tmax);
+    double best_t = tmax;
+
+    st.sp = 0;
+    int32_t node = 0;  // root
+    for (;;) {
+        while (node >= 0) {
+            const float4 *N = sc.wide_nodes + 8 * (int64_t)node;
+            const float4 lox = __ldg(N), hix = __ldg(N + 1), loy = __ldg(N + 2), hiy = __ldg(N + 3), loz = __ldg(N + 4),
+                         hiz = __ldg(N + 5);
+            const int4 ch = __ldg((const int4 *)(N + 6));
+            if (COUNT) cnt->box += 4;
+            uint32_t key[4];
+#define TAKE_WIDE_CHILD(K, LX, HX, LY, HY, LZ, HZ, C)                                            \
+            {                                                                                      \
+                float a = fmaf(LX, idx, olx), b = fmaf(HX, idx, ohx);                              \
+                float tn = fminf(a, b), tf = fmaxf(a, b);                                          \
+                a = fmaf(LY, idy, oly); b = fmaf(HY, idy, ohy);                                    \
+                tn = fmaxf(tn, fminf(a, b)); tf = fminf(tf, fmaxf(a, b));                          \
+                a = fmaf(LZ, idz, olz); b = fmaf(HZ, idz, ohz);                                    \
+                tn = fmaxf(tn, fminf(a, b)); tf = fminf(tf, fmaxf(a, b));                          \
+                tn = fmaxf(tn, tmin_f); tf = fminf(tf, tbest_f);                                   \
+                const bool h = (tn <= tf * TAKE_SLACK) && (C != TAKE_WIDE_EMPTY);                  \
+                key[K] = h ? ((__float_as_uint(tn) & 0xfffffffcu) | (uint32_t)K) : 0xffffffffu;    \
+            }
+            TAKE_WIDE_CHILD(0, lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x, ch.x)
+            TAKE_WIDE_CHILD(1, lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, ch.y)
+            TAKE_WIDE_CHILD(2, lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, ch.z)
+            TAKE_WIDE_CHILD(3, lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, ch.w)
+#undef TAKE_WIDE_CHILD
+            // sort the four keys ascending: misses (0xffffffff) sink to the end, hits come out near-to-far
+            cswap(key[0], key[1]); cswap(key[2], key[3]); cswap(key[0], key[2]); cswap(key[1], key[3]); cswap(key[1], key[2]);
+#define TAKE_WIDE_PICK(KEY) (((KEY) & 3u) == 0u ? ch.x : ((KEY) & 3u) == 1u ? ch.y : ((KEY) & 3u) == 2u ? ch.z : ch.w)
+            if (key[3] != 0xffffffffu) st.push(TAKE_WIDE_PICK(key[3]), __uint_as_float(key[3] & 0xfffffffcu));
+            if (key[2] != 0xffffffffu) st.push(TAKE_WIDE_PICK(key[2]), __uint_as_float(key[2] & 0xfffffffcu));
+            if (key[1] != 0xffffffffu) st.push(TAKE_WIDE_PICK(key[1]), __uint_as_float(key[1] & 0xfffffffcu));
+            if (key[0] != 0xffffffffu) {
+                node = TAKE_WIDE_PICK(key[0]);
+            } else {
+                for (;;) {
+                    if (st.sp == 0) return;
+                    float tn;
+                    st.pop(node, tn);
+                    if (tn <= tbest_f * TAKE_SLACK) break;
+                }
+            }
+#undef TAKE_WIDE_PICK
+        }
+        {
+            const int32_t code = ~node;
+            const int64_t first = code >> 3;
+            const int count = (code & 7) + 1;
+            for (int k = 0; k < count; ++k) {
+                const double2 *T = sc.tris + 6 * (first + k);
+                const double2 a0 = __ldg(T), a1 = __ldg(T + 1), a2 = __ldg(T + 2), a3 = __ldg(T + 3), a4 = __ldg(T + 4),
+                              a5 = __ldg(T + 5);
+                if (COUNT) cnt->tri += 1;
+                double t, bu = 0, bv = 0;
+                bool ok;
+                if (a5.y == 0.0)
+                    ok = hit_triangle(mk3(a0.x, a0.y, a1.x), mk3(a2.x, a2.y, a3.x), mk3(a4.x, a4.y, a5.x), o, d, tmin, best_t, t,
+                                      bu, bv);
+                else
+                    ok = hit_sphere(mk3(a0.x, a0.y, a1.x), a3.y, o, d, tmin, best_t, t);
+                if (ok) {
+                    const long long bits = __double_as_longlong(a1.y);
+                    const int32_t prim = (int32_t)(bits & 0xffffffffLL), rank = (int32_t)(bits >> 32);
+                    if (t < best_t || out.prim < 0 || rank > out.rank) {
+                        out.prim = prim; out.rank = rank; out.t = t; out.u = bu; out.v = bv;
+                        best_t = t;
+                        tbest_f = __double2float_ru(t);
+                        if (ANY_HIT) return;
+                    }
+                }
+            }
+        }
+        for (;;) {
+            if (st.sp == 0) return;
+            float tn;
+            st.pop(node, tn);
+            if (tn <= tbest_f * TAKE_SLACK) break;
+        }
+    }
+}
+
+// Dispatch on the tree width chosen at scene creation.
+template <bool ANY_HIT, bool COUNT, bool WIDE>
+__device__ __forceinline__ void trace_any(const DevScene &sc, D3 o, D3 d, double tmin, double tmax, TravStack &st, HitOut &out,
+                                          TravCounters *cnt) {
+    if (WIDE) trace_fast4<ANY_HIT, COUNT>(sc, o, d, tmin, tmax, st, out, cnt);
+    else trace_fast<ANY_HIT, COUNT>(sc, o, d, tmin, tmax, st, out, cnt);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Warp-persistent traversal ("while-while" with dynamic re-fetch).
 //
 // trace_fast above walks one ray to completion per thread; lanes whose rays end early idle until the slowest ray

@@ -166,7 +166,7 @@ __global__ void k_generate(DevScene sc, Wave w) {
 }
 
 // ---- extend: closest hit for every queued ray + histogram of the shading sort key ------------------------
-template <bool COUNT>
+template <bool COUNT, bool WIDE>
 __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_extend(DevScene sc, Wave w, int pass) {
     __shared__ int32_t s_node[TAKE_STACK_SMEM_ALLOC * 128];
     __shared__ float s_tn[TAKE_STACK_SMEM_ALLOC * 128];
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_extend(DevScene sc,
                 const RayRec r = w.ray[slot];
                 o = mk3(r.ox, r.oy, r.oz); d = mk3(r.dx, r.dy, r.dz); tmax = r.tmax;
             }
-            trace_fast<false, COUNT>(sc, o, d, TAKE_EPS, tmax, st, h, &cnt);
+            trace_any<false, COUNT, WIDE>(sc, o, d, TAKE_EPS, tmax, st, h, &cnt);
             key = h.prim < 0 ? 0u : 1u + (uint32_t)sc.prim_mtype[h.prim];
         }
         // warp-aggregated histogram: lanes with the same key elect a leader that bumps the bin once
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(128, TAKE_SHADE_MIN_BLOCKS) k_shade(DevScene s
 }
 
 // ---- shadow-connect: any-hit query; unoccluded connections add throughput * C1 (path_tracing.h:53-60) ----------
-template <bool COUNT>
+template <bool COUNT, bool WIDE>
 __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_shadow(DevScene sc, Wave w, int pass) {
     __shared__ int32_t s_node[TAKE_STACK_SMEM_ALLOC * 128];
     __shared__ float s_tn[TAKE_STACK_SMEM_ALLOC * 128];
@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_shadow(DevScene sc,
             const RayRec r = w.ray[slot];
             const ShadowRec s = w.shadow[slot];
             HitOut h;
-            trace_fast<true, COUNT>(sc, mk3(r.ox, r.oy, r.oz), mk3(s.dx, s.dy, s.dz), TAKE_EPS, s.tmax, st, h, &cnt);
+            trace_any<true, COUNT, WIDE>(sc, mk3(r.ox, r.oy, r.oz), mk3(s.dx, s.dy, s.dz), TAKE_EPS, s.tmax, st, h, &cnt);
             if (h.prim < 0) {
                 PathRec *p = w.path + slot;
                 p->rad[0] += s.cx; p->rad[1] += s.cy; p->rad[2] += s.cz;
@@ -632,7 +632,7 @@ __global__ void k_gather_radiance(Wave w, double *out, int n_passes) {
 }
 
 // ---- direct intersection entry points (take_gpu_intersect / take_gpu_occluded) -------------------------------
-template <bool ANY_HIT>
+template <bool ANY_HIT, bool WIDE>
 __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_intersect_fast(DevScene sc, const TakeRay *rays, int64_t n, TakeHit *hits, uint8_t *occ,
                                                         uint32_t *fetch) {
     __shared__ int32_t s_node[TAKE_STACK_SMEM_ALLOC * 128];
@@ -651,8 +651,8 @@ __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_intersect_fast(DevS
         if (i < n) {
             const TakeRay r = rays[i];
             HitOut h;
-            trace_fast<ANY_HIT, false>(sc, mk3(r.origin[0], r.origin[1], r.origin[2]), mk3(r.dir[0], r.dir[1], r.dir[2]), r.tmin,
-                                       r.tmax, st, h, nullptr);
+            trace_any<ANY_HIT, false, WIDE>(sc, mk3(r.origin[0], r.origin[1], r.origin[2]), mk3(r.dir[0], r.dir[1], r.dir[2]),
+                                            r.tmin, r.tmax, st, h, nullptr);
             if (ANY_HIT) {
                 occ[i] = h.prim >= 0 ? 1 : 0;
             } else {

@@ -173,3 +173,50 @@ def test_degenerate_scenes_build():
     for _ in range(37):
         b.mesh([(0, 0, 0), (1, 0, 0), (0, 1, 0)], [[0, 1, 2]], [(0, 0, 1)] * 3, None, m)
     _walk_fast_tree(api.host_build(b.flat()))
+
+
+def test_wide_tree_structure(small_scene):
+    """The 4-wide collapse covers every leaf slot exactly once and every child box contains what is below it."""
+    _, _, flat = small_scene
+    hb = api.host_build(flat)
+    wide, prims = hb["wide_nodes"], hb["leaf_prims"]
+    n_prims = len(prims)
+    sph = (flat.prim_flags & sceneio.PRIM_SPHERE) != 0
+    lo = np.empty((n_prims, 3)); hi = np.empty((n_prims, 3))
+    P = flat.positions[flat.indices[~sph]]
+    lo[~sph], hi[~sph] = P.min(axis=1), P.max(axis=1)
+    if sph.any():
+        s = flat.spheres[flat.indices[sph, 0]]
+        lo[sph], hi[sph] = s[:, :3] - s[:, 3:4], s[:, :3] + s[:, 3:4]
+    covered = np.zeros(n_prims, np.int32)
+    seen = np.zeros(len(wide), bool)
+
+    def bounds(i):
+        assert not seen[i]
+        seen[i] = True
+        blo, bhi = np.full(3, np.inf), np.full(3, -np.inf)
+        for k in range(4):
+            c = int(wide[i]["child"][k])
+            if c == api.WIDE_EMPTY:
+                continue
+            clo = np.array([wide[i][a][k] for a in ("lox", "loy", "loz")], np.float64)
+            chi = np.array([wide[i][a][k] for a in ("hix", "hiy", "hiz")], np.float64)
+            if c >= 0:
+                l, h = bounds(c)
+            else:
+                code = ~c
+                first, count = code >> 3, (code & 7) + 1
+                assert count == int(wide[i]["count"][k])
+                covered[first:first + count] += 1
+                sl = prims[first:first + count]
+                l, h = lo[sl].min(axis=0), hi[sl].max(axis=0)
+            assert (clo < l).all() and (chi > h).all()
+            blo, bhi = np.minimum(blo, l), np.maximum(bhi, h)
+        return blo, bhi
+
+    import sys
+    sys.setrecursionlimit(10000)
+    if n_prims:
+        bounds(0)
+        assert seen.all() and (covered == 1).all()
+        assert len(wide) <= max(1, len(hb["fast_nodes"]))   # collapsing never adds nodes

@@ -1,5 +1,7 @@
 """BASELINE.json-size checks on the GPU (config 2: 1 002 530 primitives, 1920x1080).  The oracle only sees bounded
 subsets here; the rest is covered by size-independent properties."""
+import os
+
 import numpy as np
 import pytest
 
@@ -57,3 +59,89 @@ def test_full_frame_properties(big, oracle_lib):
     err = np.abs(lo[rows] - cs[rows]).max(axis=2) / (np.abs(cs[rows]).max(axis=2) + 1e-12)
     assert (err > 1e-9).mean() <= 1e-3
     sc.close()
+
+
+# ---- config 1: Cornell box 512x512, 64 spp, multi-sample MIS (the reference's own CPU-runnable case) -------------
+def test_config1_cornell_full(gpu_lib, oracle_lib):
+    flat = scenes.cornell_box().flat()
+    assert (flat.width, flat.height, flat.spp, flat.num_prims) == (512, 512, 64, 32)
+    gs = api.GpuScene(flat)
+    s, s2, st = gs.render_sums("mis", 5, 0, 64, seed=2026)
+    assert st["samples"] == 512 * 512 * 64
+    sc = oracle_lib.load(flat)
+    cs, cs2 = sc.render("mis", 5, 0, 64, seed=2026, threads=os.cpu_count(), row_begin=3, row_step=16)
+    rows = np.arange(3, 512, 16)
+    err = np.abs(s[rows] - cs[rows]).max(axis=2) / (np.abs(cs[rows]).max(axis=2) + 1e-12)
+    assert (err > 1e-9).mean() <= 2e-3          # 64 samples per pixel: allow a few diverged paths (see test_gpu_parity)
+    assert abs(s[rows].sum() - cs[rows].sum()) <= 1e-6 * cs[rows].sum()
+    mean = s / 64
+    assert 0.1 < mean.mean() < 1.0 and np.isfinite(mean).all()
+    gs.close()
+    sc.close()
+
+
+# ---- config 4: hundreds of emissive triangles, multi-sample MIS, 1920x1080 -----------------------------------------
+def test_config4_multi_light_full(gpu_lib, oracle_lib):
+    flat = scenes.multi_light().flat()
+    assert len(flat.lights) == 400 and (flat.width, flat.height) == (1920, 1080)
+    gs = api.GpuScene(flat)
+    sc = oracle_lib.load(flat)
+    py, px = np.mgrid[0:1080:3, 0:1920:3]
+    rays = sc.primary_rays(px.ravel(), py.ravel(), seed=5)
+    pe, te, _ = gs.intersect(rays, exact=True)
+    pf, tf, _ = gs.intersect(rays, exact=False)
+    op, ot, _ = sc.intersect(rays)
+    assert np.array_equal(pe, op) and np.array_equal(pf, op) and np.array_equal(te, ot) and np.array_equal(tf, ot)
+    s, s2, st = gs.render_sums("mis", 5, 0, 2, seed=9)
+    assert st["shadow_rays"] > 0.5 * st["samples"]
+    cs, _ = sc.render("mis", 5, 0, 2, seed=9, threads=os.cpu_count(), row_begin=7, row_step=40)
+    rows = np.arange(7, 1080, 40)
+    err = np.abs(s[rows] - cs[rows]).max(axis=2) / (np.abs(cs[rows]).max(axis=2) + 1e-12)
+    assert (err > 1e-9).mean() <= 1e-3
+    gs.close()
+    sc.close()
+
+
+# ---- config 5: 10 M flattened triangles, 3840x2160 ------------------------------------------------------------------
+def test_config5_ten_million_triangles(gpu_lib, oracle_lib):
+    # the generator is checked against the oracle at a reduced size ...
+    small = scenes.instanced_spheres(160, 90, 2, copies_side=3, subdiv=4, n_lights=4).flat()
+    gs, sc = api.GpuScene(small), oracle_lib.load(small)
+    cs, _ = sc.render("mis", 5, 0, 2, seed=4)
+    s, _, _ = gs.render_sums("mis", 5, 0, 2, seed=4)
+    err = np.abs(s - cs).max(axis=2) / (np.abs(cs).max(axis=2) + 1e-12)
+    assert (err > 1e-9).mean() <= 1e-3
+    gs.close()
+    sc.close()
+    # ... and at full size the fast traversal is checked against the exact kernel (the reference's own tree and FP64
+    # slab test on the device), which needs no CPU-side 10 M-primitive build
+    flat = scenes.instanced_spheres().flat()
+    assert flat.num_prims > 10_000_000 and (flat.width, flat.height) == (3840, 2160)
+    gs = api.GpuScene(flat)
+    info = gs.info()
+    H, W = flat.height, flat.width
+    rng = np.random.default_rng(3)
+    n = 2_000_000
+    # camera rays built on the host the way render.cpp:69-75 does (float64), random sub-pixel positions
+    x, y = rng.uniform(0, W, n), rng.uniform(0, H, n)
+    th = np.tan(np.radians(flat.vfov) / 2)
+    w = flat.lookfrom - flat.lookat; w /= np.linalg.norm(w)
+    u = np.cross(flat.up, w); u /= np.linalg.norm(u)
+    v = np.cross(w, u)
+    d = u[None] * ((x / W - 0.5) * 2 * th * W / H)[:, None] + v[None] * ((y / H - 0.5) * 2 * th)[:, None] - w[None]
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = api.make_rays(np.tile(flat.lookfrom, (n, 1)), d)
+    pe, te, uve = gs.intersect(rays, exact=True)
+    pf, tf, uvf = gs.intersect(rays, exact=False)
+    assert np.array_equal(pe, pf) and np.array_equal(te, tf) and np.array_equal(uve, uvf)
+    assert (pe >= 0).mean() > 0.5
+    hit = pe >= 0
+    sec = ob.secondary_rays(rays[hit][:500_000], te[hit][:500_000], pe[hit][:500_000], seed=2)
+    p1, t1, _ = gs.intersect(sec, exact=True)
+    p2, t2, _ = gs.intersect(sec, exact=False)
+    assert np.array_equal(p1, p2) and np.array_equal(t1, t2)
+    a, _, st = gs.render_sums("mis", 5, 0, 1, seed=1, sumsq=False)
+    assert st["samples"] == W * H and np.isfinite(a).all() and a.sum() > 0
+    print("config 5:", flat.num_prims, "prims;", info, "; 1 spp 4K:", st["ms_total"], "ms,",
+          (st["extend_rays"] + st["shadow_rays"]) / st["ms_total"] / 1e3, "Mrays/s")
+    gs.close()

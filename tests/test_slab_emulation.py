@@ -105,6 +105,57 @@ def check_paths(hb, rays, prim, t):
     return int(hit.sum())
 
 
+def check_paths_wide(hb, rays, prim, t):
+    """Same property on the 4-wide collapse: the child whose subtree holds the true hit passes the emulated test."""
+    wide = hb["wide_nodes"]
+    n = len(wide)
+    # leaf-slot range below each child
+    rng_ = np.zeros((n, 4, 2), np.int64)
+    order, stack = [], [0]
+    while stack:
+        i = stack.pop()
+        order.append(i)
+        stack.extend(int(c) for c in wide[i]["child"] if 0 <= c < 0x7fffffff)
+    for i in reversed(order):
+        for k in range(4):
+            c = int(wide[i]["child"][k])
+            if c == 0x7fffffff:
+                rng_[i, k] = (1 << 40, -1)
+            elif c >= 0:
+                sub = rng_[c][rng_[c][:, 1] >= 0]
+                rng_[i, k] = (sub[:, 0].min(), sub[:, 1].max())
+            else:
+                code = ~c
+                rng_[i, k] = (code >> 3, (code >> 3) + (code & 7) + 1)
+    slot_of = np.empty(len(hb["leaf_prims"]), np.int64)
+    slot_of[hb["leaf_prims"]] = np.arange(len(slot_of))
+    hit = prim >= 0
+    rays, slot, t = rays[hit], slot_of[prim[hit]], t[hit]
+    idir, ol, oh = ray_setup(rays, hb["abs_max"])
+    tmin_f = np.nextafter(rays[:, 6].astype(F), F(-np.inf))
+    tbest_f = float_round_up(t)
+    node = np.zeros(len(rays), np.int64)
+    alive = np.ones(len(rays), bool)
+    steps = 0
+    while alive.any():
+        idx = np.nonzero(alive)[0]
+        nd = node[idx]
+        inside = (slot[idx, None] >= rng_[nd, :, 0]) & (slot[idx, None] < rng_[nd, :, 1])
+        assert (inside.sum(axis=1) == 1).all()
+        k = inside.argmax(axis=1)
+        pick = lambda name: wide[name][nd, k]
+        lo = np.stack([pick("lox"), pick("loy"), pick("loz")], axis=1)
+        hi = np.stack([pick("hix"), pick("hiy"), pick("hiz")], axis=1)
+        ok = box_pass(lo, hi, idir[idx], ol[idx], oh[idx], tmin_f[idx], tbest_f[idx])
+        assert ok.all(), f"{(~ok).sum()} wide boxes on the path to the true hit would be culled"
+        child = wide["child"][nd, k]
+        node[idx] = child
+        alive[idx] = child >= 0
+        steps += 1
+        assert steps < 200
+    return int(hit.sum())
+
+
 def axis_parallel_rays(flat, rng, n):
     lo, hi = flat.positions.min(axis=0), flat.positions.max(axis=0)
     ext = hi - lo
@@ -137,12 +188,15 @@ def test_true_hit_is_never_culled(oracle_lib, name):
         rays = all_pixel_rays(sc, jitter=jitter)
         p, t, _ = sc.intersect(rays)
         total += check_paths(hb, rays, p, t)
+        assert check_paths_wide(hb, rays, p, t) == int((p >= 0).sum())
         sec = ob.secondary_rays(rays, t, p, seed=4)
         p2, t2, _ = sc.intersect(sec)
         total += check_paths(hb, sec, p2, t2)
+        check_paths_wide(hb, sec, p2, t2)
     ap = axis_parallel_rays(flat, rng, 20000)
     p, t, _ = sc.intersect(ap)
     n_ap = check_paths(hb, ap, p, t)
+    check_paths_wide(hb, ap, p, t)
     assert n_ap > 100, "axis-parallel set must actually hit something"
     # far-away origins: the per-ray padding scales with |origin|
     far = all_pixel_rays(sc, jitter=True)

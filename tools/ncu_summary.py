@@ -1,0 +1,121 @@
+"""Turn the ncu artefacts of a gpurun call (gpurun_out/*.ncu-rep, launches_bench.csv) into the committed summaries under
+profiles/.  Usage: python tools/ncu_summary.py r01"""
+import collections, csv, io, json, os, re, subprocess, sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "profiles")
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+
+METRICS = [
+    ("gpu__time_duration.sum", "duration"),
+    ("dram__bytes_read.sum", "dram_read"),
+    ("dram__bytes_write.sum", "dram_write"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct_of_peak"),
+    ("lts__t_bytes.sum", "l2_bytes"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2_pct_of_peak"),
+    ("lts__t_sector_hit_rate.pct", "l2_hit_pct"),
+    ("l1tex__t_sector_hit_rate.pct", "l1_hit_pct"),
+    ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1_pct_of_peak"),
+    ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_pct_of_peak"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
+    ("smsp__thread_inst_executed_per_inst_executed.ratio", "active_threads_per_inst"),
+    ("smsp__inst_executed.sum", "warp_insts"),
+    ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved_occupancy_pct"),
+    ("launch__registers_per_thread", "registers"),
+    ("launch__grid_size", "grid"),
+    ("launch__block_size", "block"),
+    ("smsp__warps_eligible.avg.per_cycle_active", "eligible_warps_per_cycle"),
+    ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "fp64_pipe_pct"),
+    ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall_long_scoreboard"),
+]
+
+
+def raw(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    return rows[0], rows[1], rows[2:]
+
+
+def to_bytes(v, unit):
+    v = float(v.replace(",", ""))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+
+
+def to_us(v, unit):
+    v = float(v.replace(",", ""))
+    return v * {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}.get(unit, 1)
+
+
+def summarise(rep, name):
+    hdr, units, data = raw(rep)
+    idx = {h: i for i, h in enumerate(hdr)}
+    rows = []
+    for d in data:
+        r = {"kernel": re.sub(r"\(.*", "", d[idx["Kernel Name"]])}
+        for m, short in METRICS:
+            if m not in idx:
+                continue
+            v, u = d[idx[m]], units[idx[m]]
+            if short == "duration":
+                r["duration_us"] = round(to_us(v, u), 2)
+            elif short in ("dram_read", "dram_write", "l2_bytes"):
+                r[short + "_MB"] = round(to_bytes(v, u) / 1e6, 3)
+            else:
+                r[short] = round(float(v.replace(",", "")), 3)
+        dur = r["duration_us"] * 1e-6
+        r["dram_GBps"] = round((r.get("dram_read_MB", 0) + r.get("dram_write_MB", 0)) * 1e6 / dur / 1e9, 1)
+        if "l2_bytes_MB" in r:
+            r["l2_GBps"] = round(r["l2_bytes_MB"] * 1e6 / dur / 1e9, 1)
+        r["warp_execution_efficiency_pct"] = round(100 * r.get("active_threads_per_inst", 0) / 32, 1)
+        rows.append(r)
+    path = os.path.join(OUT, f"{tag}_{name}.csv")
+    keys = list(rows[0].keys())
+    with open(path, "w", newline="") as f:
+        w = csv.DictWriter(f, fieldnames=keys)
+        w.writeheader()
+        w.writerows(rows)
+    return rows
+
+
+def launch_list(path):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    agg = collections.OrderedDict()
+    total = 0.0
+    for row in csv.DictReader(lines):
+        k = re.sub(r"\(.*", "", row["Kernel Name"])
+        us = to_us(row["Metric Value"], row["Metric Unit"])
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += us
+        total += us
+    out = os.path.join(OUT, f"{tag}_launches_bench_summary.csv")
+    with open(out, "w") as f:
+        f.write("kernel,launches,total_us,share_pct,avg_us\n")
+        for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"\"{k}\",{n},{us:.1f},{100 * us / total:.2f},{us / n:.1f}\n")
+    return agg, total
+
+
+os.makedirs(OUT, exist_ok=True)
+g = os.path.join(ROOT, "gpurun_out")
+res = {}
+for name in ("extend", "shade", "shadow"):
+    rep = os.path.join(g, f"prof_{name}.ncu-rep")
+    if os.path.exists(rep):
+        res[name] = summarise(rep, f"ncu_{name}")
+        for r in res[name]:
+            print(name, {k: r[k] for k in ("duration_us", "dram_GBps", "l2_GBps", "issue_active_pct", "warp_execution_efficiency_pct",
+                                            "achieved_occupancy_pct", "registers", "l1_hit_pct", "l2_hit_pct") if k in r})
+if os.path.exists(os.path.join(g, "launches_bench.csv")):
+    import shutil
+    shutil.copy(os.path.join(g, "launches_bench.csv"), os.path.join(OUT, f"{tag}_launches_bench.csv"))
+    agg, total = launch_list(os.path.join(g, "launches_bench.csv"))
+    for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:8]:
+        print(f"{k:50s} n={n:4d} {us/1e3:9.3f} ms {100*us/total:5.1f}%")
+if "extend" in res:
+    # traffic of the dominant kernel per launch: the largest (primary-ray) launch of the capture
+    r = max(res["extend"], key=lambda x: x["duration_us"])
+    json.dump({"kernel": r["kernel"], "dram_bytes_per_launch": (r["dram_read_MB"] + r["dram_write_MB"]) * 1e6,
+               "launch_duration_us_under_ncu": r["duration_us"],
+               "note": "ncu --set full capture of tools/prof_run.py (2 spp x 1920x1080 wave, pass-0 launch); see " + f"{tag}_ncu_extend.csv"},
+              open(os.path.join(OUT, "extend_traffic.json"), "w"), indent=1)
