@@ -127,14 +127,21 @@ class CpuRenderer:
         return int(max(1, min(64, round(self.W * self.H / max(want, 1.0))))), rate
 
 
-def cpu_baseline(builder, flat, target_seconds=15.0):
+def cpu_baseline(builder, flat, target_seconds=12.0):
+    """Bounded sample: whole 1920x1080 frames of 1 spp each (sample indices 1, 2, ...) until ~target_seconds of CPU work."""
     cpu = CpuRenderer(builder, flat)
     rps = cpu.rays_per_sample()
-    row_step, _ = cpu.pick_row_step(target_seconds)
-    dt, n = cpu.run(1, 0, row_step)
-    return {"value": n * rps / dt / 1e6, "unit": "Mrays/s", "samples_per_s": n / dt, "cores": cpu.cores, "kind": cpu.kind,
-            "sample": f"1 spp of every {row_step}-th row of the 1920x1080 frame ({n} path samples, {dt:.1f} s), "
-                      f"{rps:.3f} rays/sample, integrator {INTEGRATOR}, max_depth {MAX_DEPTH}"}
+    cpu.run(0, 0, 16)                      # warm the caches / thread pool
+    t_total, n_total, k = 0.0, 0, 0
+    while t_total < target_seconds and k < 64:
+        k += 1
+        dt, n = cpu.run(k, 0, 1)
+        t_total += dt
+        n_total += n
+    return {"value": n_total * rps / t_total / 1e6, "unit": "Mrays/s", "samples_per_s": n_total / t_total, "cores": cpu.cores,
+            "kind": cpu.kind,
+            "sample": f"{k} spp of the full 1920x1080 frame ({n_total} path samples, {t_total:.1f} s), {rps:.3f} rays/sample, "
+                      f"integrator {INTEGRATOR}, max_depth {MAX_DEPTH}"}
 
 
 def run_reference_arm(args):

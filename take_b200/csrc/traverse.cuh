@@ -20,6 +20,34 @@ namespace take {
 #define TAKE_STACK_LOCAL (96 - TAKE_STACK_SMEM)  // overflow entries in local memory (tree depth limit = 96, checked on the host)
 #define TAKE_STACK_SMEM_ALLOC (TAKE_STACK_SMEM > 0 ? TAKE_STACK_SMEM : 1)
 
+// 256-bit read-only loads (sm_100: LDG.E.256).  The traversal kernels are bound by L1 wavefront throughput -- every
+// lane of a divergent warp touches its own cache line, one wavefront per line per load instruction -- so moving a
+// 64-byte node in two instructions instead of four halves the wavefronts per node.  Addresses must be 32-byte aligned.
+#ifndef TAKE_LDG256
+#define TAKE_LDG256 1
+#endif
+struct F8 { float4 a, b; };
+struct D4 { double2 a, b; };
+__device__ __forceinline__ F8 ldg_f8(const float4 *p) {
+    F8 r;
+#if TAKE_LDG256
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+#else
+    r.a = __ldg(p); r.b = __ldg(p + 1);
+#endif
+    return r;
+}
+__device__ __forceinline__ D4 ldg_d4(const double2 *p) {
+    D4 r;
+#if TAKE_LDG256
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a.x), "=d"(r.a.y), "=d"(r.b.x), "=d"(r.b.y) : "l"(p));
+#else
+    r.a = __ldg(p); r.b = __ldg(p + 1);
+#endif
+    return r;
+}
+
 // ---- leaf tests: src/shape.cpp:44-78 (triangle) and :13-29 (sphere), accept/reject part ---------------
 __device__ __forceinline__ bool hit_triangle(D3 v0, D3 e1, D3 e2, D3 o, D3 d, double tmin, double tmax, double &t,
                                              double &bu, double &bv) {
@@ -170,10 +198,8 @@ __device__ __forceinline__ void trace_fast(const DevScene &sc, D3 o, D3 d, doubl
     int32_t node = 0;  // root
     for (;;) {
         while (node >= 0) {
-            const float4 q0 = __ldg(sc.nodes + 4 * (int64_t)node);
-            const float4 q1 = __ldg(sc.nodes + 4 * (int64_t)node + 1);
-            const float4 q2 = __ldg(sc.nodes + 4 * (int64_t)node + 2);
-            const float4 q3 = __ldg(sc.nodes + 4 * (int64_t)node + 3);
+            const F8 n01 = ldg_f8(sc.nodes + 4 * (int64_t)node), n23 = ldg_f8(sc.nodes + 4 * (int64_t)node + 2);
+            const float4 q0 = n01.a, q1 = n01.b, q2 = n23.a, q3 = n23.b;
             if (COUNT) cnt->box += 2;
             float a, b;
             a = fmaf(q0.x, idx, olx); b = fmaf(q0.y, idx, ohx);
@@ -216,8 +242,8 @@ __device__ __forceinline__ void trace_fast(const DevScene &sc, D3 o, D3 d, doubl
             const int count = (code & 7) + 1;
             for (int k = 0; k < count; ++k) {
                 const double2 *T = sc.tris + 6 * (first + k);
-                const double2 a0 = __ldg(T), a1 = __ldg(T + 1), a2 = __ldg(T + 2), a3 = __ldg(T + 3), a4 = __ldg(T + 4),
-                              a5 = __ldg(T + 5);
+                const D4 t01 = ldg_d4(T), t23 = ldg_d4(T + 2), t45 = ldg_d4(T + 4);
+                const double2 a0 = t01.a, a1 = t01.b, a2 = t23.a, a3 = t23.b, a4 = t45.a, a5 = t45.b;
                 if (COUNT) cnt->tri += 1;
                 double t, bu = 0, bv = 0;
                 bool ok;
@@ -280,8 +306,8 @@ __device__ __forceinline__ void trace_fast4(const DevScene &sc, D3 o, D3 d, doub
     for (;;) {
         while (node >= 0) {
             const float4 *N = sc.wide_nodes + 8 * (int64_t)node;
-            const float4 lox = __ldg(N), hix = __ldg(N + 1), loy = __ldg(N + 2), hiy = __ldg(N + 3), loz = __ldg(N + 4),
-                         hiz = __ldg(N + 5);
+            const F8 nx = ldg_f8(N), ny = ldg_f8(N + 2), nz = ldg_f8(N + 4);
+            const float4 lox = nx.a, hix = nx.b, loy = ny.a, hiy = ny.b, loz = nz.a, hiz = nz.b;
             const int4 ch = __ldg((const int4 *)(N + 6));
             if (COUNT) cnt->box += 4;
             uint32_t key[4];
@@ -326,8 +352,8 @@ __device__ __forceinline__ void trace_fast4(const DevScene &sc, D3 o, D3 d, doub
             const int count = (code & 7) + 1;
             for (int k = 0; k < count; ++k) {
                 const double2 *T = sc.tris + 6 * (first + k);
-                const double2 a0 = __ldg(T), a1 = __ldg(T + 1), a2 = __ldg(T + 2), a3 = __ldg(T + 3), a4 = __ldg(T + 4),
-                              a5 = __ldg(T + 5);
+                const D4 t01 = ldg_d4(T), t23 = ldg_d4(T + 2), t45 = ldg_d4(T + 4);
+                const double2 a0 = t01.a, a1 = t01.b, a2 = t23.a, a3 = t23.b, a4 = t45.a, a5 = t45.b;
                 if (COUNT) cnt->tri += 1;
                 double t, bu = 0, bv = 0;
                 bool ok;
@@ -506,8 +532,8 @@ __device__ __forceinline__ void trace_warp_persistent(const DevScene &sc, IO &io
             bool stop = false;
             for (int k = 0; k < count && !stop; ++k) {
                 const double2 *T = sc.tris + 6 * (first + k);
-                const double2 a0 = __ldg(T), a1 = __ldg(T + 1), a2 = __ldg(T + 2), a3 = __ldg(T + 3), a4 = __ldg(T + 4),
-                              a5 = __ldg(T + 5);
+                const D4 t01 = ldg_d4(T), t23 = ldg_d4(T + 2), t45 = ldg_d4(T + 4);
+                const double2 a0 = t01.a, a1 = t01.b, a2 = t23.a, a3 = t23.b, a4 = t45.a, a5 = t45.b;
                 if (COUNT) cnt->tri += 1;
                 double t, bu = 0, bv = 0;
                 bool ok;
