@@ -112,6 +112,16 @@ typedef struct TakeSceneDesc {
     const TakeMaterialDesc *materials;
     const TakeTextureDesc *textures;
     const TakeLightDesc *lights;
+    /* EXTENSION (no counterpart in the reference, whose only "environment" is the constant background_color):
+     * a lat-long environment map.  Row 0 is +y (up); a direction d maps to u = (atan2(-d.z, d.x) + pi) / 2pi (the phi of
+     * get_sphere_uv, src/shape.cpp:3-11) and v = acos(d.y) / pi; lookups are piecewise constant.  With env_rgb == NULL
+     * nothing changes.  env_sample == 0: the map only replaces background_color on misses (a constant map then gives
+     * exactly the reference's <background> render).  env_sample == 1: the map additionally takes part in light
+     * sampling as light number num_lights (uniform pick over num_lights + 1), importance sampled through marginal /
+     * conditional CDF tables of luminance x sin(theta), with MIS weights on BSDF-sampled misses. */
+    int32_t env_width, env_height;
+    int32_t env_sample, reserved2;
+    const double *env_rgb; /* env_height * env_width * 3 */
 } TakeSceneDesc;
 
 /* A ray exactly as the reference's `Ray` (src/ray.h:4-9): 8 doubles. */

@@ -215,6 +215,17 @@ class OracleScene:
         assert rc == 0
         return out
 
+    def env_sample(self, u1, u2):
+        out = np.empty(4, np.float64)
+        self.lib.oracle_env_sample(self.h, float(u1), float(u2), _ptr(out, np.float64))
+        return out[:3].copy(), float(out[3])
+
+    def env_eval(self, direction):
+        d = np.ascontiguousarray(direction, np.float64)
+        out = np.empty(4, np.float64)
+        self.lib.oracle_env_eval(self.h, _ptr(d, np.float64), _ptr(out, np.float64))
+        return out[:3].copy(), float(out[3])
+
     def primary_rays(self, px, py, s=None, seed=0, jitter=True):
         px = np.ascontiguousarray(px, np.int32); py = np.ascontiguousarray(py, np.int32)
         s = np.zeros(len(px), np.int64) if s is None else np.ascontiguousarray(s, np.int64)
@@ -244,6 +255,8 @@ class OracleLib:
         L.oracle_stream_real.restype = C.c_double
         L.oracle_stream_real.argtypes = [u64, u32, u64, u32]
         L.oracle_philox.argtypes = [vp, vp, vp]
+        L.oracle_env_sample.argtypes = [vp, C.c_double, C.c_double, vp]
+        L.oracle_env_eval.argtypes = [vp, vp, vp]
 
     def load(self, flat) -> OracleScene:
         return OracleScene(self.lib, flat)

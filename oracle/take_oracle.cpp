@@ -116,6 +116,13 @@ struct Scene {
     std::vector<Tex> tex;
     std::vector<Node> nodes;
     int root = -1;
+    // EXTENSION without a reference counterpart (see include/take_gpu.h): lat-long environment map
+    int env_w = 0, env_h = 0, env_sample = 0;
+    std::vector<double> env_rgb, env_marg, env_cond;  // marginal CDF [h+1], conditional CDFs [h][w+1]
+    double env_total = 0;
+    bool has_env() const { return env_w > 0; }
+    // number of entries of the uniform light pick: the scene's lights plus, when it is sampled, the environment
+    size_t pick_count() const { return lights.size() + ((has_env() && env_sample) ? 1 : 0); }
 };
 
 // ---- src/bvh.cpp:8-45 + src/scene.cpp:4-23 ----------------------------------------------------
@@ -352,6 +359,89 @@ inline V3 eval_texture(const Scene &sc, const TakeMaterialDesc &m, V2 uv) {
     V3 acc = add(add(add(mul(mul(q11, x2 - x), y2 - y), mul(mul(q21, x - x1), y2 - y)), mul(mul(q12, x2 - x), y - y1)),
                  mul(mul(q22, x - x1), y - y1));
     return divs(acc, (double)((x2 - x1) * (y2 - y1)));
+}
+
+// ---- environment map (EXTENSION: our own design, parity unpinned except the constant-map case) ---------------
+// Conventions follow the reference's idioms: phi of get_sphere_uv (src/shape.cpp:3-11), luminance() (src/vector.h:
+// 309-311), CDF inversion by upper_bound + clamp (src/light.cpp:9-17).
+inline double luminance(V3 c) { return c.x * 0.212671 + c.y * 0.715160 + c.z * 0.072169; }
+inline double clamp1(double v) { return v < -1.0 ? -1.0 : (v > 1.0 ? 1.0 : v); }
+
+inline void env_texel(const Scene &sc, V3 d, int &i, int &j, double &theta) {
+    theta = acos(clamp1(d.y));
+    double u = (atan2(-d.z, d.x) + PI) / (2 * PI), v = theta / PI;
+    i = (int)floor(u * sc.env_w);
+    j = (int)floor(v * sc.env_h);
+    i = i < 0 ? 0 : (i >= sc.env_w ? sc.env_w - 1 : i);
+    j = j < 0 ? 0 : (j >= sc.env_h ? sc.env_h - 1 : j);
+}
+inline V3 env_rgb_at(const Scene &sc, int i, int j) {
+    const double *p = &sc.env_rgb[3 * ((size_t)j * sc.env_w + i)];
+    return {p[0], p[1], p[2]};
+}
+inline double env_func(const Scene &sc, int i, int j) {  // sampling weight of a texel: luminance x sin(theta at the row centre)
+    return luminance(env_rgb_at(sc, i, j)) * sin(PI * (j + 0.5) / sc.env_h);
+}
+inline V3 env_radiance(const Scene &sc, V3 d) {
+    int i, j;
+    double theta;
+    env_texel(sc, d, i, j, theta);
+    return env_rgb_at(sc, i, j);
+}
+inline V3 miss_radiance(const Scene &sc, V3 d) { return sc.has_env() ? env_radiance(sc, d) : sc.background; }
+// solid-angle pdf of sampling direction d from the tables
+inline double env_pdf(const Scene &sc, V3 d) {
+    int i, j;
+    double theta;
+    env_texel(sc, d, i, j, theta);
+    double st = sin(theta);
+    if (!(st > 0) || !(sc.env_total > 0)) return 0;
+    return env_func(sc, i, j) / sc.env_total * ((double)sc.env_w * sc.env_h) / (2 * PI * PI * st);
+}
+inline int upper_bound_idx(const double *a, int n, double x) {  // first index with a[idx] > x, in [0, n]
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) / 2;
+        if (x < a[mid]) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+// Two draws -> direction and its solid-angle pdf (0 if the map is black or the direction degenerate).
+inline void env_sample_dir(const Scene &sc, double u1, double u2, V3 &dir, double &pdf) {
+    pdf = 0;
+    dir = {0, 1, 0};
+    if (!(sc.env_total > 0)) return;
+    const int W = sc.env_w, H = sc.env_h;
+    double x = u1 * sc.env_total;
+    int j = upper_bound_idx(sc.env_marg.data(), H + 1, x) - 1;
+    j = j < 0 ? 0 : (j > H - 1 ? H - 1 : j);
+    double row = sc.env_marg[j + 1] - sc.env_marg[j];
+    if (!(row > 0)) return;
+    double dv = (x - sc.env_marg[j]) / row;
+    const double *c = &sc.env_cond[(size_t)j * (W + 1)];
+    double y = u2 * c[W];
+    int i = upper_bound_idx(c, W + 1, y) - 1;
+    i = i < 0 ? 0 : (i > W - 1 ? W - 1 : i);
+    double cell = c[i + 1] - c[i];
+    if (!(cell > 0)) return;
+    double du = (y - c[i]) / cell;
+    double u = (i + du) / W, v = (j + dv) / H;
+    double theta = v * PI, phi = u * (2 * PI) - PI;
+    double st = sin(theta);
+    dir = {st * cos(phi), cos(theta), -(st * sin(phi))};
+    if (!(st > 0)) return;
+    pdf = env_func(sc, i, j) / sc.env_total * ((double)W * H) / (2 * PI * PI * st);
+}
+void build_env_tables(Scene &sc) {
+    const int W = sc.env_w, H = sc.env_h;
+    sc.env_marg.assign(H + 1, 0.0);
+    sc.env_cond.assign((size_t)H * (W + 1), 0.0);
+    for (int j = 0; j < H; ++j) {
+        double *c = &sc.env_cond[(size_t)j * (W + 1)];
+        for (int i = 0; i < W; ++i) c[i + 1] = c[i] + env_func(sc, i, j);
+        sc.env_marg[j + 1] = sc.env_marg[j] + c[W];
+    }
+    sc.env_total = sc.env_marg[H];
 }
 
 // ---- random stream -----------------------------------------------------------------------------
@@ -591,9 +681,10 @@ inline V3 intensity(const TakeLightDesc &l) { return {l.intensity[0], l.intensit
 // ---- src/integrator/path_tracing.h:5-111 ---------------------------------------------------------
 V3 path_tracing(const Scene &sc, Ray r, Rng &rng, int max_depth, Counters &cn) {
     Isect v;
-    if (!scene_intersect(sc, r, v, cn)) return sc.background;
+    if (!scene_intersect(sc, r, v, cn)) return miss_radiance(sc, r.d);
     V3 radiance = {0, 0, 0}, throughput = {1, 1, 1};
-    size_t nl = sc.lights.size();
+    const size_t nl = sc.pick_count();            // == lights.size() unless a sampled environment map is present
+    const bool env_light = nl > sc.lights.size();
     if (v.light != -1 && sc.lights[v.light].kind == TAKE_LIGHT_AREA)
         radiance = add(radiance, mulv(throughput, intensity(sc.lights[v.light])));
     for (int i = 0; i <= max_depth; ++i) {
@@ -604,6 +695,22 @@ V3 path_tracing(const Scene &sc, Ray r, Rng &rng, int max_depth, Counters &cn) {
         V3 C1 = {0, 0, 0};
         if (nl > 0 && !spec) {
             int light_id = (int)floor(rng.next() * nl);
+            if (env_light && light_id == (int)sc.lights.size()) {  // EXTENSION: the environment as a light
+                double u1 = rng.next();
+                double u2 = rng.next();
+                V3 light_dir;
+                double pdf_w;
+                env_sample_dir(sc, u1, u2, light_dir, pdf_w);
+                double lpdf = pdf_w / nl;
+                if (lpdf <= 0) break;
+                double bpdf = bsdf_pdf(m, dir_in, light_dir, v);
+                if (bpdf > 0 && !isinf(lpdf)) {
+                    V3 FG = bsdf_eval(sc, m, dir_in, light_dir, 0.0, v);
+                    Ray sh = {v.pos, light_dir, EPS, INFINITY};
+                    if (!scene_occluded(sc, sh, cn))
+                        C1 = divs(mul(mulv(FG, env_radiance(sc, light_dir)), lpdf), lpdf * lpdf + bpdf * bpdf);
+                }
+            } else {
             const TakeLightDesc &l = sc.lights[light_id];
             if (l.kind == TAKE_LIGHT_AREA) {
                 LightSample lp = sample_on_prim(sc, l.prim_id, v.pos, rng);
@@ -620,6 +727,7 @@ V3 path_tracing(const Scene &sc, Ray r, Rng &rng, int max_depth, Counters &cn) {
                         C1 = divs(mul(mulv(FG, intensity(l)), lpdf), lpdf * lpdf + bpdf * bpdf);
                 }
             }
+            }
         }
         radiance = add(radiance, mulv(throughput, C1));
 
@@ -634,8 +742,14 @@ V3 path_tracing(const Scene &sc, Ray r, Rng &rng, int max_depth, Counters &cn) {
         r = {v.pos, dir_out, EPS, INFINITY};
         Isect nv;
         if (!scene_intersect(sc, r, nv, cn)) {
+            if (env_light) {  // EXTENSION: the miss found the sampled environment -> MIS weight as for an emitter hit (:99)
+                lpdf = env_pdf(sc, dir_out) / nl;
+                V3 Ce = mul(mulv(FG, env_radiance(sc, dir_out)), spec ? (1 / bpdf) : (bpdf / (lpdf * lpdf + bpdf * bpdf)));
+                radiance = add(radiance, mulv(throughput, Ce));
+                break;
+            }
             throughput = mulv(throughput, divs(FG, bpdf));
-            radiance = add(radiance, mulv(throughput, sc.background));
+            radiance = add(radiance, mulv(throughput, miss_radiance(sc, dir_out)));
             break;
         }
         if (nv.light != -1) {
@@ -657,7 +771,7 @@ V3 path_tracing(const Scene &sc, Ray r, Rng &rng, int max_depth, Counters &cn) {
 // ---- src/integrator/path_tracing.h:114-157 -------------------------------------------------------
 V3 path_tracing_raw(const Scene &sc, Ray r, Rng &rng, int max_depth, Counters &cn) {
     Isect v;
-    if (!scene_intersect(sc, r, v, cn)) return sc.background;
+    if (!scene_intersect(sc, r, v, cn)) return miss_radiance(sc, r.d);
     V3 radiance = {0, 0, 0}, throughput = {1, 1, 1};
     for (int i = 0; i <= max_depth; ++i) {
         if (v.light != -1 && sc.lights[v.light].kind == TAKE_LIGHT_AREA) {
@@ -680,7 +794,7 @@ V3 path_tracing_raw(const Scene &sc, Ray r, Rng &rng, int max_depth, Counters &c
         r = {v.pos, dir_out, EPS, INFINITY};
         Isect nv;
         if (!scene_intersect(sc, r, nv, cn)) {
-            radiance = add(radiance, mulv(throughput, sc.background));
+            radiance = add(radiance, mulv(throughput, miss_radiance(sc, dir_out)));
             break;
         }
         v = nv;
@@ -691,9 +805,10 @@ V3 path_tracing_raw(const Scene &sc, Ray r, Rng &rng, int max_depth, Counters &c
 // ---- src/integrator/path_tracing.h:161-271 -------------------------------------------------------
 V3 path_tracing_one_sample_mis(const Scene &sc, Ray r, Rng &rng, int max_depth, Counters &cn) {
     Isect v;
-    if (!scene_intersect(sc, r, v, cn)) return sc.background;
+    if (!scene_intersect(sc, r, v, cn)) return miss_radiance(sc, r.d);
     V3 radiance = {0, 0, 0}, throughput = {1, 1, 1};
-    size_t nl = sc.lights.size();
+    const size_t nl = sc.pick_count();            // == lights.size() unless a sampled environment map is present
+    const bool env_light = nl > sc.lights.size();
     for (int i = 0; i <= max_depth; ++i) {
         if (v.light != -1 && sc.lights[v.light].kind == TAKE_LIGHT_AREA) {
             radiance = add(radiance, mulv(throughput, intensity(sc.lights[v.light])));
@@ -705,6 +820,27 @@ V3 path_tracing_one_sample_mis(const Scene &sc, Ray r, Rng &rng, int max_depth, 
         bool spec = is_specular(m);
         if (nl > 0 && !spec && rng.next() <= 0.5) {
             int light_id = (int)floor(rng.next() * nl);
+            if (env_light && light_id == (int)sc.lights.size()) {  // EXTENSION: the environment as a light
+                double u1 = rng.next();
+                double u2 = rng.next();
+                V3 light_dir;
+                double pdf_w;
+                env_sample_dir(sc, u1, u2, light_dir, pdf_w);
+                double lpdf = pdf_w / nl;
+                if (lpdf <= 0) break;
+                double bpdf = bsdf_pdf(m, dir_in, light_dir, v);
+                if (bpdf <= 0) break;
+                V3 FG = bsdf_eval(sc, m, dir_in, light_dir, 0.0, v);
+                r = {v.pos, light_dir, EPS, INFINITY};
+                Isect nv;
+                throughput = mulv(throughput, divs(FG, 0.5 * lpdf + 0.5 * bpdf));
+                if (!scene_intersect(sc, r, nv, cn)) {  // reached the environment: that is the light we aimed at
+                    radiance = add(radiance, mulv(throughput, env_radiance(sc, light_dir)));
+                    break;
+                }
+                v = nv;  // hit an obstacle: continue from it, as the reference's area-light branch does (:220-225)
+                continue;
+            }
             const TakeLightDesc &l = sc.lights[light_id];
             if (l.kind == TAKE_LIGHT_AREA) {
                 LightSample lp = sample_on_prim(sc, l.prim_id, v.pos, rng);
@@ -741,8 +877,9 @@ V3 path_tracing_one_sample_mis(const Scene &sc, Ray r, Rng &rng, int max_depth, 
             bool hit = scene_intersect(sc, r, nv, cn);
             double pdf = (nl == 0 || spec) ? bpdf : 0.5 * bpdf;
             if (!hit) {
+                if (env_light && !spec) pdf += 0.5 * (env_pdf(sc, dir_out) / nl);  // EXTENSION: mixture pdf, as :255-265 for emitters
                 throughput = mulv(throughput, divs(FG, pdf));
-                radiance = add(radiance, mulv(throughput, sc.background));
+                radiance = add(radiance, mulv(throughput, miss_radiance(sc, dir_out)));
                 break;
             }
             if (!spec && nv.light != -1) {
@@ -843,6 +980,13 @@ void *oracle_scene_create(const TakeSceneDesc *d) {
     for (int i = 0; i < d->num_textures; ++i) {
         const TakeTextureDesc &t = d->textures[i];
         sc->tex.push_back({t.width, t.height, std::vector<double>(t.rgb, t.rgb + (size_t)t.width * t.height * 3)});
+    }
+    if (d->env_rgb && d->env_width > 0 && d->env_height > 0) {
+        sc->env_w = d->env_width;
+        sc->env_h = d->env_height;
+        sc->env_sample = d->env_sample;
+        sc->env_rgb.assign(d->env_rgb, d->env_rgb + (size_t)d->env_width * d->env_height * 3);
+        build_env_tables(*sc);
     }
     build_bvh(*sc);
     return sc;
@@ -989,6 +1133,21 @@ void oracle_primary_rays(void *h, uint64_t seed, int64_t n, const int32_t *px, c
         o[0] = c.lookfrom[0]; o[1] = c.lookfrom[1]; o[2] = c.lookfrom[2];
         o[3] = d.x; o[4] = d.y; o[5] = d.z; o[6] = EPS; o[7] = INFINITY;
     }
+}
+
+// EXTENSION test hooks: environment sampling.  out = {dir3, pdf}; pdf_of = pdf of an arbitrary direction; rad = radiance.
+void oracle_env_sample(void *h, double u1, double u2, double *out) {
+    const Scene &sc = *(Scene *)h;
+    V3 d;
+    double pdf;
+    env_sample_dir(sc, u1, u2, d, pdf);
+    out[0] = d.x; out[1] = d.y; out[2] = d.z; out[3] = pdf;
+}
+void oracle_env_eval(void *h, const double *dir, double *out) {
+    const Scene &sc = *(Scene *)h;
+    V3 d = {dir[0], dir[1], dir[2]};
+    V3 r = env_radiance(sc, d);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = env_pdf(sc, d);
 }
 
 double oracle_stream_real(uint64_t seed, uint32_t pixel, uint64_t sample, uint32_t k) {

@@ -126,6 +126,12 @@ struct DevScene {
     double viewport_w, viewport_h;
     D3 background;
     float abs_max;  // max |coordinate| over the scene, for the per-ray conservative padding
+    // EXTENSION (include/take_gpu.h): lat-long environment map and its sampling tables
+    const double *env_rgb, *env_marg, *env_cond;  // texels [h][w][3]; marginal CDF [h+1]; conditional CDFs [h][w+1]
+    double env_total;
+    int32_t env_w, env_h;
+    int32_t env_light;   // 1: the environment is entry number num_lights of the uniform light pick
+    int32_t pick_count;  // num_lights + env_light: the N of sample_light (src/light.cpp:5-7) and of the 1/N in the light pdfs
 };
 
 struct HitOut {

@@ -79,6 +79,71 @@ __device__ __forceinline__ D3 eval_texture(const DevScene &sc, const TakeMateria
     return divs(acc, (double)((x2 - x1) * (y2 - y1)));
 }
 
+// ---- environment map (EXTENSION, see include/take_gpu.h; mirrors oracle/take_oracle.cpp) ------------------------
+__device__ __forceinline__ double luminance(D3 c) { return c.x * 0.212671 + c.y * 0.715160 + c.z * 0.072169; }  // vector.h:309-311
+__device__ __forceinline__ double clamp1(double v) { return v < -1.0 ? -1.0 : (v > 1.0 ? 1.0 : v); }
+
+__device__ __forceinline__ void env_texel(const DevScene &sc, D3 d, int &i, int &j, double &theta) {
+    theta = acos(clamp1(d.y));
+    double u = (atan2(-d.z, d.x) + TAKE_PI) / (2 * TAKE_PI), v = theta / TAKE_PI;
+    i = (int)floor(u * sc.env_w);
+    j = (int)floor(v * sc.env_h);
+    i = i < 0 ? 0 : (i >= sc.env_w ? sc.env_w - 1 : i);
+    j = j < 0 ? 0 : (j >= sc.env_h ? sc.env_h - 1 : j);
+}
+__device__ __forceinline__ D3 env_rgb_at(const DevScene &sc, int i, int j) { return ld3(sc.env_rgb + 3 * ((int64_t)j * sc.env_w + i)); }
+__device__ __forceinline__ double env_func(const DevScene &sc, int i, int j) {
+    return luminance(env_rgb_at(sc, i, j)) * sin(TAKE_PI * (j + 0.5) / sc.env_h);
+}
+__device__ __forceinline__ D3 env_radiance(const DevScene &sc, D3 d) {
+    int i, j;
+    double theta;
+    env_texel(sc, d, i, j, theta);
+    return env_rgb_at(sc, i, j);
+}
+__device__ __forceinline__ D3 miss_radiance(const DevScene &sc, D3 d) { return sc.env_rgb ? env_radiance(sc, d) : sc.background; }
+__device__ __forceinline__ double env_pdf(const DevScene &sc, D3 d) {
+    int i, j;
+    double theta;
+    env_texel(sc, d, i, j, theta);
+    double st = sin(theta);
+    if (!(st > 0) || !(sc.env_total > 0)) return 0;
+    return env_func(sc, i, j) / sc.env_total * ((double)sc.env_w * sc.env_h) / (2 * TAKE_PI * TAKE_PI * st);
+}
+__device__ __forceinline__ int upper_bound_idx(const double *a, int n, double x) {  // first index with a[idx] > x (light.cpp:14)
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) / 2;
+        if (x < a[mid]) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+__device__ inline void env_sample_dir(const DevScene &sc, double u1, double u2, D3 &dir, double &pdf) {
+    pdf = 0;
+    dir = mk3(0, 1, 0);
+    if (!(sc.env_total > 0)) return;
+    const int W = sc.env_w, H = sc.env_h;
+    double x = u1 * sc.env_total;
+    int j = upper_bound_idx(sc.env_marg, H + 1, x) - 1;
+    j = j < 0 ? 0 : (j > H - 1 ? H - 1 : j);
+    double row = sc.env_marg[j + 1] - sc.env_marg[j];
+    if (!(row > 0)) return;
+    double dv = (x - sc.env_marg[j]) / row;
+    const double *c = sc.env_cond + (int64_t)j * (W + 1);
+    double y = u2 * c[W];
+    int i = upper_bound_idx(c, W + 1, y) - 1;
+    i = i < 0 ? 0 : (i > W - 1 ? W - 1 : i);
+    double cell = c[i + 1] - c[i];
+    if (!(cell > 0)) return;
+    double du = (y - c[i]) / cell;
+    double u = (i + du) / W, v = (j + dv) / H;
+    double theta = v * TAKE_PI, phi = u * (2 * TAKE_PI) - TAKE_PI;
+    double st = sin(theta);
+    dir = mk3(st * cos(phi), cos(theta), -(st * sin(phi)));
+    if (!(st > 0)) return;
+    pdf = env_func(sc, i, j) / sc.env_total * ((double)W * H) / (2 * TAKE_PI * TAKE_PI * st);
+}
+
 // ---- src/material.h:121-140 -------------------------------------------------------------------
 __device__ __forceinline__ D3 sample_hemisphere_cos(Rng &rng) {
     double u1 = rng.next();

@@ -62,6 +62,7 @@ struct TakeScene {
     DevScene dev{};
     int width = 0, height = 0;
     // scene storage
+    DeviceBuffer env_rgb, env_marg, env_cond;
     DeviceBuffer nodes, wide_nodes, tris, ref_nodes, positions, normals, uvs, indices, prim_material, prim_light, dfs_rank, prim_flags,
         prim_mtype, spheres, materials, lights, textures;
     std::vector<DeviceBuffer *> tex_data;
@@ -134,6 +135,7 @@ int validate(const TakeSceneDesc *d) {
         if (m.type < 0 || m.type > TAKE_MAT_DISNEY_BSDF) return fail(TAKE_E_INVALID, "unknown material type");
         if (m.tex_id >= d->num_textures) return fail(TAKE_E_INVALID, "texture id out of range");
     }
+    if (d->env_rgb && (d->env_width <= 0 || d->env_height <= 0)) return fail(TAKE_E_INVALID, "bad environment map size");
     for (int i = 0; i < d->num_lights; ++i) {
         const TakeLightDesc &l = d->lights[i];
         if (l.kind == TAKE_LIGHT_AREA && (l.prim_id < 0 || l.prim_id >= d->num_prims))
@@ -486,6 +488,30 @@ int take_gpu_scene_create(int device, const TakeSceneDesc *d, TakeScene **out) {
         tex[i].w = t.width; tex[i].h = t.height; tex[i].rgb = b->as<double>();
     }
     if ((rc = upload(s->textures, tex.data(), tex.size(), st))) return rc;
+    // EXTENSION: environment map + marginal / conditional CDF tables of luminance x sin(theta at the row centre).
+    // Same loops and operation order as oracle/take_oracle.cpp:build_env_tables, so the tables are bit-identical.
+    std::vector<double> env_marg, env_cond;
+    double env_total = 0;
+    const bool has_env = d->env_rgb && d->env_width > 0 && d->env_height > 0;
+    if (has_env) {
+        const int W = d->env_width, H = d->env_height;
+        env_marg.assign((size_t)H + 1, 0.0);
+        env_cond.assign((size_t)H * (W + 1), 0.0);
+        for (int j = 0; j < H; ++j) {
+            double *c = &env_cond[(size_t)j * (W + 1)];
+            const double sj = sin(TAKE_PI * (j + 0.5) / H);
+            for (int i = 0; i < W; ++i) {
+                const double *p = d->env_rgb + 3 * ((size_t)j * W + i);
+                const double lum = p[0] * 0.212671 + p[1] * 0.715160 + p[2] * 0.072169;
+                c[i + 1] = c[i] + lum * sj;
+            }
+            env_marg[j + 1] = env_marg[j] + c[W];
+        }
+        env_total = env_marg[H];
+        if ((rc = upload(s->env_rgb, d->env_rgb, (size_t)W * H * 3, st))) return rc;
+        if ((rc = upload(s->env_marg, env_marg.data(), env_marg.size(), st))) return rc;
+        if ((rc = upload(s->env_cond, env_cond.data(), env_cond.size(), st))) return rc;
+    }
     CU(cudaStreamSynchronize(st));
 
     DevScene &v = s->dev;
@@ -504,6 +530,14 @@ int take_gpu_scene_create(int device, const TakeSceneDesc *d, TakeScene **out) {
     v.lights = s->lights.as<TakeLightDesc>();
     v.textures = s->textures.as<DevTexture>();
     v.num_lights = d->num_lights; v.num_materials = d->num_materials;
+    v.env_rgb = has_env ? s->env_rgb.as<double>() : nullptr;
+    v.env_marg = has_env ? s->env_marg.as<double>() : nullptr;
+    v.env_cond = has_env ? s->env_cond.as<double>() : nullptr;
+    v.env_total = env_total;
+    v.env_w = has_env ? d->env_width : 0;
+    v.env_h = has_env ? d->env_height : 0;
+    v.env_light = (has_env && d->env_sample) ? 1 : 0;
+    v.pick_count = d->num_lights + v.env_light;
     v.num_prims = n;
     // camera basis: src/render.cpp:37-44, same operations on the host's libm
     const TakeCamera &c = d->camera;

@@ -37,7 +37,7 @@ struct ShadowRec {  // 64 B : NEE connection waiting for its shadow ray (origin 
 static_assert(sizeof(RayRec) == 64 && sizeof(HitRec) == 32 && sizeof(PathRec) == 64 && sizeof(PendRec) == 32 &&
                   sizeof(ShadowRec) == 64, "record sizes");
 
-enum { PEND_PRIMARY = 0, PEND_BSDF = 1, PEND_LIGHT = 2, PEND_SPECULAR = 4 };
+enum { PEND_PRIMARY = 0, PEND_BSDF = 1, PEND_LIGHT = 2, PEND_SPECULAR = 4, PEND_ENV = 8 };
 
 #define TAKE_NBINS 16      // sort bins: 0 = miss, 1 + material type
 #define TAKE_MAX_PASSES 80
@@ -272,7 +272,7 @@ __device__ __forceinline__ bool nee_sample(const DevScene &sc, const TakeLightDe
     sample_on_prim(sc, l.prim_id, v.pos, rng, lp, ln);
     dist = length(sub(lp, v.pos));
     light_dir = normalize(sub(lp, v.pos));
-    lpdf = light_pdf_area(sc, light_id, lp, v.pos) * (dist * dist) / (fmax(dot(neg(ln), light_dir), 0.0) * sc.num_lights);
+    lpdf = light_pdf_area(sc, light_id, lp, v.pos) * (dist * dist) / (fmax(dot(neg(ln), light_dir), 0.0) * sc.pick_count);
     return !(lpdf <= 0);
 }
 
@@ -280,7 +280,7 @@ __device__ __forceinline__ bool nee_sample(const DevScene &sc, const TakeLightDe
 __device__ __forceinline__ bool hit_light_pdf(const DevScene &sc, const Isect &nv, D3 prev_pos, double &lpdf) {
     double d = length(sub(nv.pos, prev_pos));
     D3 light_dir = normalize(sub(nv.pos, prev_pos));
-    lpdf = light_pdf_area(sc, nv.light, nv.pos, prev_pos) * (d * d) / (fmax(dot(neg(nv.gn), light_dir), 0.0) * sc.num_lights);
+    lpdf = light_pdf_area(sc, nv.light, nv.pos, prev_pos) * (d * d) / (fmax(dot(neg(nv.gn), light_dir), 0.0) * sc.pick_count);
     return !(lpdf <= 0);
 }
 
@@ -291,7 +291,7 @@ __device__ inline void shade_mis(ShadeCtx &c, const RayRec &ray, const HitRec &h
     const D3 o = mk3(ray.ox, ray.oy, ray.oz), d = mk3(ray.dx, ray.dy, ray.dz);
     Isect v;
     if (path.flags == PEND_PRIMARY) {
-        if (hit.prim < 0) { c.rad = sc.background; return; }  // :8
+        if (hit.prim < 0) { c.rad = miss_radiance(sc, d); return; }  // :8
         fill_isect(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
         if (v.light != -1 && sc.lights[v.light].kind == TAKE_LIGHT_AREA)  // :14-18
             c.rad = add(c.rad, mulv(c.thr, light_intensity(sc.lights[v.light])));
@@ -301,8 +301,14 @@ __device__ inline void shade_mis(ShadeCtx &c, const RayRec &ray, const HitRec &h
         const double bpdf = pend.bpdf;
         const bool spec = (path.flags & PEND_SPECULAR) != 0;
         if (hit.prim < 0) {  // :82-87
+            if (sc.env_light) {  // EXTENSION: the miss found the sampled environment -> MIS weight as for an emitter hit (:99)
+                const double lpdf = env_pdf(sc, d) / sc.pick_count;
+                D3 Ce = mul(mulv(FG, env_radiance(sc, d)), spec ? (1 / bpdf) : (bpdf / (lpdf * lpdf + bpdf * bpdf)));
+                c.rad = add(c.rad, mulv(c.thr, Ce));
+                return;
+            }
             c.thr = mulv(c.thr, divs(FG, bpdf));
-            c.rad = add(c.rad, mulv(c.thr, sc.background));
+            c.rad = add(c.rad, mulv(c.thr, miss_radiance(sc, d)));
             return;
         }
         fill_isect(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
@@ -323,10 +329,27 @@ __device__ inline void shade_mis(ShadeCtx &c, const RayRec &ray, const HitRec &h
     const TakeMaterialDesc &m = sc.materials[v.material];
     const bool spec = is_specular(m.type);
     c.org = v.pos;
-    if (sc.num_lights > 0 && !spec) {  // :30-59
-        const int light_id = (int)floor(c.rng.next() * sc.num_lights);
-        const TakeLightDesc &l = sc.lights[light_id];
-        if (l.kind == TAKE_LIGHT_AREA) {
+    if (sc.pick_count > 0 && !spec) {  // :30-59
+        const int light_id = (int)floor(c.rng.next() * sc.pick_count);
+        if (sc.env_light && light_id == sc.num_lights) {  // EXTENSION: the environment as a light
+            const double u1 = c.rng.next();
+            const double u2 = c.rng.next();
+            D3 light_dir;
+            double pdf_w;
+            env_sample_dir(sc, u1, u2, light_dir, pdf_w);
+            const double lpdf = pdf_w / sc.pick_count;
+            if (lpdf <= 0) return;
+            const double bpdf = bsdf_pdf(m, dir_in, light_dir, v);
+            if (bpdf > 0 && !isinf(lpdf)) {
+                D3 FG = bsdf_eval(sc, m, dir_in, light_dir, 0.0, v);
+                D3 C1 = divs(mul(mulv(FG, env_radiance(sc, light_dir)), lpdf), lpdf * lpdf + bpdf * bpdf);
+                c.emit_shadow = true;
+                c.sh_dir = light_dir;
+                c.sh_tmax = INFINITY;
+                c.sh_contrib = mulv(c.thr, C1);
+            }
+        } else if (sc.lights[light_id].kind == TAKE_LIGHT_AREA) {
+            const TakeLightDesc &l = sc.lights[light_id];
             D3 light_dir;
             double dist, lpdf;
             if (!nee_sample(sc, l, light_id, v, c.rng, light_dir, dist, lpdf)) return;
@@ -358,8 +381,8 @@ __device__ inline void shade_raw(ShadeCtx &c, const RayRec &ray, const HitRec &h
     const DevScene &sc = c.sc;
     const D3 o = mk3(ray.ox, ray.oy, ray.oz), d = mk3(ray.dx, ray.dy, ray.dz);
     if (hit.prim < 0) {
-        if (path.flags == PEND_PRIMARY) c.rad = sc.background;         // :117
-        else c.rad = add(c.rad, mulv(c.thr, sc.background));            // :148-152 (throughput already updated, :145)
+        if (path.flags == PEND_PRIMARY) c.rad = miss_radiance(sc, d);  // :117
+        else c.rad = add(c.rad, mulv(c.thr, miss_radiance(sc, d)));     // :148-152 (throughput already updated, :145)
         return;
     }
     Isect v;
@@ -391,12 +414,16 @@ __device__ inline void shade_raw(ShadeCtx &c, const RayRec &ray, const HitRec &h
 __device__ inline void shade_one_sample(ShadeCtx &c, const RayRec &ray, const HitRec &hit, const PathRec &path) {
     const DevScene &sc = c.sc;
     const D3 o = mk3(ray.ox, ray.oy, ray.oz), d = mk3(ray.dx, ray.dy, ray.dz);
-    const int nl = sc.num_lights;
+    const int nl = sc.pick_count;
     Isect v;
     if (path.flags == PEND_PRIMARY) {
-        if (hit.prim < 0) { c.rad = sc.background; return; }
+        if (hit.prim < 0) { c.rad = miss_radiance(sc, d); return; }
         fill_isect(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
     } else if (path.flags & PEND_LIGHT) {
+        if (hit.prim < 0 && (path.flags & PEND_ENV)) {  // EXTENSION: reached the environment we aimed at
+            c.rad = add(c.rad, mulv(c.thr, env_radiance(sc, d)));
+            return;
+        }
         if (hit.prim < 0) {
             // the reference dereferences an empty optional here (:220, undefined behaviour): terminate and count
             atomicAdd(&c.w.totals->miss_after_light_sample, 1ULL);
@@ -409,8 +436,9 @@ __device__ inline void shade_one_sample(ShadeCtx &c, const RayRec &ray, const Hi
         const bool spec = (path.flags & PEND_SPECULAR) != 0;
         double pdf = (nl == 0 || spec) ? pend.bpdf : 0.5 * pend.bpdf;  // :245
         if (hit.prim < 0) {  // :247-252
+            if (sc.env_light && !spec) pdf += 0.5 * (env_pdf(sc, d) / nl);  // EXTENSION: mixture pdf, as :255-265 for emitters
             c.thr = mulv(c.thr, divs(FG, pdf));
-            c.rad = add(c.rad, mulv(c.thr, sc.background));
+            c.rad = add(c.rad, mulv(c.thr, miss_radiance(sc, d)));
             return;
         }
         fill_isect(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
@@ -433,6 +461,26 @@ __device__ inline void shade_one_sample(ShadeCtx &c, const RayRec &ray, const Hi
         c.org = v.pos;
         if (nl > 0 && !spec && c.rng.next() <= 0.5) {  // :187
             const int light_id = (int)floor(c.rng.next() * nl);
+            if (sc.env_light && light_id == sc.num_lights) {  // EXTENSION: the environment as a light
+                const double u1 = c.rng.next();
+                const double u2 = c.rng.next();
+                D3 light_dir;
+                double pdf_w;
+                env_sample_dir(sc, u1, u2, light_dir, pdf_w);
+                const double lpdf = pdf_w / nl;
+                if (lpdf <= 0) return;
+                const double bpdf = bsdf_pdf(m, dir_in, light_dir, v);
+                if (bpdf <= 0) return;
+                D3 FG = bsdf_eval(sc, m, dir_in, light_dir, 0.0, v);
+                c.thr = mulv(c.thr, divs(FG, 0.5 * lpdf + 0.5 * bpdf));
+                c.ext_dir = light_dir;
+                c.pend_fg = FG;
+                c.pend_pdf = bpdf;
+                c.pend_flags = PEND_LIGHT | PEND_ENV;
+                c.emit_extend = true;
+                c.depth += 1;
+                return;
+            }
             const TakeLightDesc &l = sc.lights[light_id];
             if (l.kind != TAKE_LIGHT_AREA) continue;  // a point light: the iteration does nothing (:190)
             D3 light_dir;

@@ -20,6 +20,7 @@ camera and background.  It converts to the C-ABI `TakeSceneDesc`
     MatRec   materials[nmat]   {i32 type, i32 tex_id, f64 color[3], f64 uscale,vscale,uoffset,voffset, f64 p[2]}
     LightRec lights[nlight]    {i32 kind, i32 prim_id, f64 intensity[3], f64 position[3]}
     per texture: i64 w, h ; f64 rgb[w*h*3]             (src/image.h:13-39 layout, row 0 first)
+    if hdr[7] & 1: i64 w, h ; f64 rgb[w*h*3]           environment map (extension); hdr[7] & 2 = env_sample
 """
 from __future__ import annotations
 
@@ -60,6 +61,8 @@ class TakeSceneDesc(C.Structure):
         ("num_spheres", C.c_int64), ("spheres", C.c_void_p),
         ("num_materials", C.c_int32), ("num_textures", C.c_int32), ("num_lights", C.c_int32), ("reserved", C.c_int32),
         ("materials", C.c_void_p), ("textures", C.c_void_p), ("lights", C.c_void_p),
+        ("env_width", C.c_int32), ("env_height", C.c_int32), ("env_sample", C.c_int32), ("reserved2", C.c_int32),
+        ("env_rgb", C.c_void_p),
     ]
 
 
@@ -84,6 +87,8 @@ class FlatScene:
     lights: np.ndarray             # LIGHT_DTYPE [nlight]
     textures: list = field(default_factory=list)   # list of f64 [h,w,3]
     spp: int = 16
+    env: object = None             # optional lat-long environment map f64 [h,w,3] (extension, see take_gpu.h)
+    env_sample: bool = False
 
     @property
     def num_prims(self) -> int:
@@ -106,6 +111,8 @@ class FlatScene:
         self.materials = c(self.materials, dtype=MAT_DTYPE)
         self.lights = c(self.lights, dtype=LIGHT_DTYPE)
         self.textures = [c(t, dtype=np.float64) for t in self.textures]
+        if self.env is not None:
+            self.env = c(self.env, dtype=np.float64)
         return self
 
     # ---- C-ABI view -------------------------------------------------------------------------
@@ -136,6 +143,10 @@ class FlatScene:
             self._tex_descs[i].height, self._tex_descs[i].width = t.shape[0], t.shape[1]
             self._tex_descs[i].rgb = t.ctypes.data
         d.textures = C.addressof(self._tex_descs)
+        if self.env is not None:
+            d.env_height, d.env_width = self.env.shape[0], self.env.shape[1]
+            d.env_sample = 1 if self.env_sample else 0
+            d.env_rgb = self.env.ctypes.data
         return d
 
     # ---- TAKESCN1 ---------------------------------------------------------------------------
@@ -145,7 +156,8 @@ class FlatScene:
         with open(path, "wb") as f:
             f.write(b"TAKESCN1")
             np.array([self.positions.shape[0], n_p, len(self.materials), len(self.textures), len(self.lights),
-                      self.spheres.shape[0], self.spp, 0], dtype="<i8").tofile(f)
+                      self.spheres.shape[0], self.spp,
+                      (1 if self.env is not None else 0) | (2 if self.env_sample else 0)], dtype="<i8").tofile(f)
             np.array([self.width, self.height], dtype="<i8").tofile(f)
             np.concatenate([self.lookfrom, self.lookat, self.up, [self.vfov], self.background]).astype("<f8").tofile(f)
             for a in (self.positions, self.normals, self.uvs, self.indices, self.prim_material, self.prim_light):
@@ -161,6 +173,9 @@ class FlatScene:
             for t in self.textures:
                 np.array([t.shape[1], t.shape[0]], dtype="<i8").tofile(f)
                 t.tofile(f)
+            if self.env is not None:
+                np.array([self.env.shape[1], self.env.shape[0]], dtype="<i8").tofile(f)
+                self.env.tofile(f)
 
     @staticmethod
     def load(path) -> "FlatScene":
@@ -175,7 +190,7 @@ class FlatScene:
             off[0] += dt.itemsize * count
             return a
 
-        nv, n_p, nmat, ntex, nlight, nsph, spp, _ = (int(v) for v in take("<i8", 8))
+        nv, n_p, nmat, ntex, nlight, nsph, spp, envflags = (int(v) for v in take("<i8", 8))
         w, h = (int(v) for v in take("<i8", 2))
         cam = take("<f8", 13)
         pos, nrm, uv = take("<f8", 3 * nv), take("<f8", 3 * nv), take("<f8", 2 * nv)
@@ -189,8 +204,12 @@ class FlatScene:
         for _ in range(ntex):
             tw, th = (int(v) for v in take("<i8", 2))
             textures.append(take("<f8", tw * th * 3).reshape(th, tw, 3))
+        env = None
+        if envflags & 1:
+            ew, eh = (int(v) for v in take("<i8", 2))
+            env = take("<f8", ew * eh * 3).reshape(eh, ew, 3)
         return FlatScene(w, h, cam[0:3], cam[3:6], cam[6:9], float(cam[9]), cam[10:13], pos, nrm, uv, idx, pmat,
-                         plight, flags, sph, mats, lights, textures, spp)._canon()
+                         plight, flags, sph, mats, lights, textures, spp, env, bool(envflags & 2))._canon()
 
     def same_as(self, other: "FlatScene") -> list:
         """Names of fields that differ (bit-for-bit on values; -0.0 == 0.0)."""
@@ -207,4 +226,7 @@ class FlatScene:
         if len(self.textures) != len(other.textures) or any(
                 a.shape != b.shape or not np.array_equal(a, b) for a, b in zip(self.textures, other.textures)):
             bad.append("textures")
+        if (self.env is None) != (other.env is None) or (self.env is not None and not np.array_equal(self.env, other.env)) \
+                or self.env_sample != other.env_sample:
+            bad.append("env")
         return bad

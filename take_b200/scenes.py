@@ -62,6 +62,8 @@ class SceneBuilder:
         self.materials = []   # (type, color|None, tex|None, params dict)
         self.textures = []    # (name, rgbe uint8 [h,w,4])
         self.meshes = []      # shapes in the order the reference would parse them: mesh dicts and sphere dicts
+        self.env = None       # optional environment map (extension: the reference has none)
+        self.env_sample = False
 
     # -- materials ----------------------------------------------------------------------------
     def material(self, mtype, color=(0.5, 0.5, 0.5), texture=None, uvscale=(1, 1), uvoffset=(0, 0), **params) -> int:
@@ -77,6 +79,12 @@ class SceneBuilder:
         assert rgbe.ndim == 3 and rgbe.shape[2] == 4
         self.textures.append(rgbe)
         return len(self.textures) - 1
+
+    def environment(self, rgb, sample=True):
+        """Lat-long environment map [h,w,3] (row 0 = up).  EXTENSION: the reference's only environment is the constant
+        <background>; `write()` therefore refuses such a scene unless the map is constant."""
+        self.env = np.ascontiguousarray(rgb, dtype=np.float64)
+        self.env_sample = bool(sample)
 
     # -- geometry -----------------------------------------------------------------------------
     def mesh(self, positions, indices, normals, uvs=None, material=0, radiance=None):
@@ -189,11 +197,13 @@ class SceneBuilder:
             cat(idx, (0, 3), np.int32), cat(pmat, (0,), np.int32), cat(plight, (0,), np.int32),
             cat(pflags, (0,), np.uint8), np.array(spheres, np.float64).reshape(-1, 4), mats,
             np.array(lights, dtype=sio.LIGHT_DTYPE) if lights else np.zeros(0, sio.LIGHT_DTYPE), textures,
-            self.spp)._canon()
+            self.spp, self.env, self.env_sample)._canon()
 
     def write(self, directory) -> str:
         """Write scene.xml + meshes + textures under `directory`; returns the XML path."""
         os.makedirs(directory, exist_ok=True)
+        if self.env is not None:
+            raise ValueError("the reference has no environment emitter: scenes with an environment map cannot be written as XML")
         x = ['<?xml version="1.0" encoding="utf-8"?>', '<scene version="0.5.0">']
         x.append('<sensor type="perspective">')
         x.append(f'  <float name="fov" value="{_fmt(self.vfov)}"/><string name="fovAxis" value="y"/>')
@@ -504,6 +514,56 @@ def instanced_spheres(width=3840, height=2160, spp=4096, copies_side=11, subdiv=
     return b
 
 
+def sky_environment(width=2048, height=1024, seed=11, sun_peak=5e4, sun_sigma_deg=1.5) -> np.ndarray:
+    """Synthetic HDR sky: vertical gradient + ground tint + one Gaussian sun (config 3)."""
+    v = (np.arange(height) + 0.5) / height                     # 0 = zenith, 1 = nadir
+    u = (np.arange(width) + 0.5) / width
+    theta = v[:, None] * np.pi
+    phi = u[None, :] * 2 * np.pi - np.pi
+    d = np.stack([np.sin(theta) * np.cos(phi), np.cos(theta) * np.ones_like(phi), -np.sin(theta) * np.sin(phi)], axis=-1)
+    up = np.clip(d[..., 1], 0, 1)[..., None]
+    sky = (1 - up) * np.array([0.9, 0.95, 1.0]) + up * np.array([0.25, 0.45, 0.9])
+    ground = np.array([0.18, 0.16, 0.14])
+    img = np.where(d[..., 1:2] >= 0, sky, ground)
+    rng = np.random.default_rng(seed)
+    sun = np.array([np.cos(rng.uniform(0, 2 * np.pi)) * 0.6, 0.7, 0.0])
+    sun[2] = np.sqrt(max(0.0, 1 - sun[0] ** 2 - sun[1] ** 2))
+    ang = np.arccos(np.clip(d @ sun, -1, 1))
+    img = img + sun_peak * np.exp(-0.5 * (ang / np.radians(sun_sigma_deg)) ** 2)[..., None] * np.array([1.0, 0.95, 0.85])
+    return img
+
+
+def ibl_scene(width=1024, height=1024, spp=512, n_objects=64, seed=7, env_size=(2048, 1024), sample_env=True) -> SceneBuilder:
+    """Config 3: textured procedural objects (boxes and bumpy icospheres with image textures) on a textured ground, lit by
+    an importance-sampled HDR environment map.  The environment part is an extension without a reference implementation."""
+    rng = np.random.default_rng(seed)
+    b = SceneBuilder(width, height, (0, 14, 34), (0, 2.5, 0), (0, 1, 0), 40.0, spp, (0, 0, 0))
+    checker = b.texture_rgbe(procedural_rgbe(64, 64, "checker"))
+    noise = b.texture_rgbe(procedural_rgbe(64, 64, "noise", seed=3))
+    ground = b.material(sio.MAT_DIFFUSE, texture=checker, uvscale=(12.0, 12.0))
+    mats = [b.material(sio.MAT_DIFFUSE, texture=noise, uvscale=(2.0, 2.0)),
+            b.material(sio.MAT_BLINN_MICROFACET, texture=checker, uvscale=(3.0, 3.0), exponent=60),
+            b.material(sio.MAT_BLINN_MICROFACET, texture=noise, uvscale=(1.0, 1.0), exponent=200),
+            b.material(sio.MAT_DIFFUSE, (0.7, 0.7, 0.7))]
+    gp, gt, gn, guv = _grid_mesh(64, 40.0, lambda X, Z: 0.15 * np.sin(0.4 * X) * np.cos(0.3 * Z))
+    b.mesh(gp, gt, gn, guv, ground)
+    sv, sf = _icosphere(4)                                           # 5120 faces
+    suv = np.stack([np.arctan2(sv[:, 2], sv[:, 0]) / (2 * np.pi) + 0.5, np.arccos(np.clip(sv[:, 1], -1, 1)) / np.pi], axis=1)
+    side = int(np.ceil(np.sqrt(n_objects)))
+    for k in range(n_objects):
+        cx = -28 + 56 * ((k % side) + 0.5) / side + rng.uniform(-1.5, 1.5)
+        cz = -28 + 56 * ((k // side) + 0.5) / side + rng.uniform(-1.5, 1.5)
+        r = rng.uniform(1.0, 2.4)
+        m = mats[k % len(mats)]
+        if k % 3 == 0:
+            b.box((cx, r, cz), (r * 0.8, r, r * 0.8), rng.uniform(0, 90), m, bottom=True)
+        else:
+            bump = 1.0 + 0.1 * np.sin(6 * sv[:, 0] + k) * np.sin(5 * sv[:, 1]) * np.sin(7 * sv[:, 2])
+            b.mesh(sv * bump[:, None] * r + np.array([cx, r * 1.05, cz]), sf, sv, suv, m)
+    b.environment(sky_environment(*env_size), sample=sample_env)
+    return b
+
+
 def build(name: str, **kw) -> SceneBuilder:
     return {"cornell": cornell_box, "heightfield": heightfield, "multi_light": multi_light,
-            "textured": textured_room, "spheres": sphere_room, "instanced": instanced_spheres}[name](**kw)
+            "textured": textured_room, "spheres": sphere_room, "instanced": instanced_spheres, "ibl": ibl_scene}[name](**kw)
