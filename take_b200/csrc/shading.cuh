@@ -118,7 +118,7 @@ __device__ __forceinline__ int upper_bound_idx(const double *a, int n, double x)
     }
     return lo;
 }
-__device__ inline void env_sample_dir(const DevScene &sc, double u1, double u2, D3 &dir, double &pdf) {
+__device__ __forceinline__ void env_sample_dir(const DevScene &sc, double u1, double u2, D3 &dir, double &pdf) {
     pdf = 0;
     dir = mk3(0, 1, 0);
     if (!(sc.env_total > 0)) return;
@@ -177,7 +177,7 @@ __device__ __forceinline__ D3 sample_power_cos_lobe(double exponent, Rng &rng) {
 }
 
 // sample_bsdf (src/material.cpp:76-82 + materials/*.inl); false == std::nullopt
-__device__ inline bool sample_bsdf(const TakeMaterialDesc &m, D3 dir_in, const Isect &v, Rng &rng, D3 &dir_out, double &pdf) {
+__device__ __forceinline__ bool sample_bsdf(const TakeMaterialDesc &m, D3 dir_in, const Isect &v, Rng &rng, D3 &dir_out, double &pdf) {
     if (dot(v.gn, dir_in) < 0) return false;
     D3 n = shading_n(dir_in, v);
     const int t = m.type;
@@ -229,7 +229,7 @@ __device__ inline bool sample_bsdf(const TakeMaterialDesc &m, D3 dir_in, const I
 }
 
 // get_bsdf_pdf (src/material.cpp:84-90 + materials/*.inl)
-__device__ inline double bsdf_pdf(const TakeMaterialDesc &m, D3 dir_in, D3 dir_out, const Isect &v) {
+__device__ __forceinline__ double bsdf_pdf(const TakeMaterialDesc &m, D3 dir_in, D3 dir_out, const Isect &v) {
     const int t = m.type;
     if (t == TAKE_MAT_MIRROR) return 0;  // mirror.inl:12-14
     if (dot(v.gn, dir_out) < 0) return 0;
@@ -254,7 +254,7 @@ __device__ inline double bsdf_pdf(const TakeMaterialDesc &m, D3 dir_in, D3 dir_o
 
 // eval (src/material.cpp:92-98 + materials/*.inl): BSDF * cos.  rec_pdf is SampleRecord::pdf, which Plastic::eval
 // uses to tell its two lobes apart (plastic.inl:44).
-__device__ inline D3 bsdf_eval(const DevScene &sc, const TakeMaterialDesc &m, D3 dir_in, D3 dir_out, double rec_pdf,
+__device__ __forceinline__ D3 bsdf_eval(const DevScene &sc, const TakeMaterialDesc &m, D3 dir_in, D3 dir_out, double rec_pdf,
                                const Isect &v) {
     const D3 zero = mk3(0, 0, 0);
     if (dot(v.gn, dir_in) < 0 || dot(v.gn, dir_out) < 0) return zero;
@@ -324,7 +324,7 @@ __device__ __forceinline__ double prim_area(const DevScene &sc, int prim) {  // 
     return length(cross(sub(ld3(sc.positions + 3 * (int64_t)id[1]), v0), sub(ld3(sc.positions + 3 * (int64_t)id[2]), v0))) / 2;
 }
 
-__device__ inline void sample_on_prim(const DevScene &sc, int prim, D3 ref_pos, Rng &rng, D3 &pos, D3 &nrm) {
+__device__ __forceinline__ void sample_on_prim(const DevScene &sc, int prim, D3 ref_pos, Rng &rng, D3 &pos, D3 &nrm) {
     const int32_t *id = sc.indices + 3 * (int64_t)prim;
     if (sc.prim_flags[prim] & TAKE_PRIM_SPHERE) {  // shape.cpp:125-144
         const double *s = sc.spheres + 4 * (int64_t)id[0];

@@ -326,9 +326,12 @@ int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, d
             launches++;
         }
         tm.begin(ST_SHADE);
-        if (o->integrator == TAKE_INTEGRATOR_MIS) k_shade<TAKE_INTEGRATOR_MIS><<<shade_blocks, 128, 0, st>>>(s->dev, w, b);
-        else if (o->integrator == TAKE_INTEGRATOR_RAW) k_shade<TAKE_INTEGRATOR_RAW><<<shade_blocks, 128, 0, st>>>(s->dev, w, b);
-        else k_shade<TAKE_INTEGRATOR_ONE_SAMPLE_MIS><<<shade_blocks, 128, 0, st>>>(s->dev, w, b);
+        const bool env = s->dev.env_rgb != nullptr;
+#define TAKE_SHADE(I) (env ? k_shade<I, true><<<shade_blocks, 128, 0, st>>>(s->dev, w, b) : k_shade<I, false><<<shade_blocks, 128, 0, st>>>(s->dev, w, b))
+        if (o->integrator == TAKE_INTEGRATOR_MIS) TAKE_SHADE(TAKE_INTEGRATOR_MIS);
+        else if (o->integrator == TAKE_INTEGRATOR_RAW) TAKE_SHADE(TAKE_INTEGRATOR_RAW);
+        else TAKE_SHADE(TAKE_INTEGRATOR_ONE_SAMPLE_MIS);
+#undef TAKE_SHADE
         tm.end();
         launches += 2;
         if (o->integrator == TAKE_INTEGRATOR_MIS && b <= o->max_depth) {

@@ -284,14 +284,20 @@ __device__ __forceinline__ bool hit_light_pdf(const DevScene &sc, const Isect &n
     return !(lpdf <= 0);
 }
 
+// Radiance carried by a ray that leaves the scene.  ENV = false compiles the environment-map extension out of the
+// kernels used for scenes without a map (the reference's case), keeping their register budget.
+template <bool ENV>
+__device__ __forceinline__ D3 miss_rad(const DevScene &sc, D3 d) { return ENV ? env_radiance(sc, d) : sc.background; }
+
 // Multi-sample MIS: src/integrator/path_tracing.h:5-111.  One call = "finish iteration depth-1 with the hit that
 // just arrived, then run iteration depth up to the point where it needs rays".
-__device__ inline void shade_mis(ShadeCtx &c, const RayRec &ray, const HitRec &hit, const PathRec &path) {
+template <bool ENV>
+__device__ __forceinline__ void shade_mis(ShadeCtx &c, const RayRec &ray, const HitRec &hit, const PathRec &path) {
     const DevScene &sc = c.sc;
     const D3 o = mk3(ray.ox, ray.oy, ray.oz), d = mk3(ray.dx, ray.dy, ray.dz);
     Isect v;
     if (path.flags == PEND_PRIMARY) {
-        if (hit.prim < 0) { c.rad = miss_radiance(sc, d); return; }  // :8
+        if (hit.prim < 0) { c.rad = miss_rad<ENV>(sc, d); return; }  // :8
         fill_isect(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
         if (v.light != -1 && sc.lights[v.light].kind == TAKE_LIGHT_AREA)  // :14-18
             c.rad = add(c.rad, mulv(c.thr, light_intensity(sc.lights[v.light])));
@@ -301,14 +307,14 @@ __device__ inline void shade_mis(ShadeCtx &c, const RayRec &ray, const HitRec &h
         const double bpdf = pend.bpdf;
         const bool spec = (path.flags & PEND_SPECULAR) != 0;
         if (hit.prim < 0) {  // :82-87
-            if (sc.env_light) {  // EXTENSION: the miss found the sampled environment -> MIS weight as for an emitter hit (:99)
+            if (ENV && sc.env_light) {  // EXTENSION: the miss found the sampled environment -> MIS weight as for an emitter hit (:99)
                 const double lpdf = env_pdf(sc, d) / sc.pick_count;
                 D3 Ce = mul(mulv(FG, env_radiance(sc, d)), spec ? (1 / bpdf) : (bpdf / (lpdf * lpdf + bpdf * bpdf)));
                 c.rad = add(c.rad, mulv(c.thr, Ce));
                 return;
             }
             c.thr = mulv(c.thr, divs(FG, bpdf));
-            c.rad = add(c.rad, mulv(c.thr, miss_radiance(sc, d)));
+            c.rad = add(c.rad, mulv(c.thr, miss_rad<ENV>(sc, d)));
             return;
         }
         fill_isect(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
@@ -331,7 +337,7 @@ __device__ inline void shade_mis(ShadeCtx &c, const RayRec &ray, const HitRec &h
     c.org = v.pos;
     if (sc.pick_count > 0 && !spec) {  // :30-59
         const int light_id = (int)floor(c.rng.next() * sc.pick_count);
-        if (sc.env_light && light_id == sc.num_lights) {  // EXTENSION: the environment as a light
+        if (ENV && sc.env_light && light_id == sc.num_lights) {  // EXTENSION: the environment as a light
             const double u1 = c.rng.next();
             const double u2 = c.rng.next();
             D3 light_dir;
@@ -377,12 +383,13 @@ __device__ inline void shade_mis(ShadeCtx &c, const RayRec &ray, const HitRec &h
 }
 
 // No MIS: src/integrator/path_tracing.h:114-157
-__device__ inline void shade_raw(ShadeCtx &c, const RayRec &ray, const HitRec &hit, const PathRec &path) {
+template <bool ENV>
+__device__ __forceinline__ void shade_raw(ShadeCtx &c, const RayRec &ray, const HitRec &hit, const PathRec &path) {
     const DevScene &sc = c.sc;
     const D3 o = mk3(ray.ox, ray.oy, ray.oz), d = mk3(ray.dx, ray.dy, ray.dz);
     if (hit.prim < 0) {
-        if (path.flags == PEND_PRIMARY) c.rad = miss_radiance(sc, d);  // :117
-        else c.rad = add(c.rad, mulv(c.thr, miss_radiance(sc, d)));     // :148-152 (throughput already updated, :145)
+        if (path.flags == PEND_PRIMARY) c.rad = miss_rad<ENV>(sc, d);  // :117
+        else c.rad = add(c.rad, mulv(c.thr, miss_rad<ENV>(sc, d)));     // :148-152 (throughput already updated, :145)
         return;
     }
     Isect v;
@@ -411,16 +418,17 @@ __device__ inline void shade_raw(ShadeCtx &c, const RayRec &ray, const HitRec &h
 }
 
 // One-sample MIS: src/integrator/path_tracing.h:161-271
-__device__ inline void shade_one_sample(ShadeCtx &c, const RayRec &ray, const HitRec &hit, const PathRec &path) {
+template <bool ENV>
+__device__ __forceinline__ void shade_one_sample(ShadeCtx &c, const RayRec &ray, const HitRec &hit, const PathRec &path) {
     const DevScene &sc = c.sc;
     const D3 o = mk3(ray.ox, ray.oy, ray.oz), d = mk3(ray.dx, ray.dy, ray.dz);
-    const int nl = sc.pick_count;
+    const int nl = ENV ? sc.pick_count : sc.num_lights;
     Isect v;
     if (path.flags == PEND_PRIMARY) {
-        if (hit.prim < 0) { c.rad = miss_radiance(sc, d); return; }
+        if (hit.prim < 0) { c.rad = miss_rad<ENV>(sc, d); return; }
         fill_isect(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
     } else if (path.flags & PEND_LIGHT) {
-        if (hit.prim < 0 && (path.flags & PEND_ENV)) {  // EXTENSION: reached the environment we aimed at
+        if (ENV && hit.prim < 0 && (path.flags & PEND_ENV)) {  // EXTENSION: reached the environment we aimed at
             c.rad = add(c.rad, mulv(c.thr, env_radiance(sc, d)));
             return;
         }
@@ -436,9 +444,9 @@ __device__ inline void shade_one_sample(ShadeCtx &c, const RayRec &ray, const Hi
         const bool spec = (path.flags & PEND_SPECULAR) != 0;
         double pdf = (nl == 0 || spec) ? pend.bpdf : 0.5 * pend.bpdf;  // :245
         if (hit.prim < 0) {  // :247-252
-            if (sc.env_light && !spec) pdf += 0.5 * (env_pdf(sc, d) / nl);  // EXTENSION: mixture pdf, as :255-265 for emitters
+            if (ENV && sc.env_light && !spec) pdf += 0.5 * (env_pdf(sc, d) / nl);  // EXTENSION: mixture pdf, as :255-265 for emitters
             c.thr = mulv(c.thr, divs(FG, pdf));
-            c.rad = add(c.rad, mulv(c.thr, miss_radiance(sc, d)));
+            c.rad = add(c.rad, mulv(c.thr, miss_rad<ENV>(sc, d)));
             return;
         }
         fill_isect(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
@@ -461,7 +469,7 @@ __device__ inline void shade_one_sample(ShadeCtx &c, const RayRec &ray, const Hi
         c.org = v.pos;
         if (nl > 0 && !spec && c.rng.next() <= 0.5) {  // :187
             const int light_id = (int)floor(c.rng.next() * nl);
-            if (sc.env_light && light_id == sc.num_lights) {  // EXTENSION: the environment as a light
+            if (ENV && sc.env_light && light_id == sc.num_lights) {  // EXTENSION: the environment as a light
                 const double u1 = c.rng.next();
                 const double u2 = c.rng.next();
                 D3 light_dir;
@@ -515,7 +523,7 @@ __device__ inline void shade_one_sample(ShadeCtx &c, const RayRec &ray, const Hi
 #ifndef TAKE_SHADE_MIN_BLOCKS
 #define TAKE_SHADE_MIN_BLOCKS 1
 #endif
-template <int INTEGRATOR>
+template <int INTEGRATOR, bool ENV>
 __global__ void __launch_bounds__(128, TAKE_SHADE_MIN_BLOCKS) k_shade(DevScene sc, Wave w, int pass) {
     PassCounters &pc = w.pass[pass];
     const uint32_t n = pass_count(w, pass);
@@ -557,9 +565,9 @@ __global__ void __launch_bounds__(128, TAKE_SHADE_MIN_BLOCKS) k_shade(DevScene s
             c.pend_flags = 0;
             c.shaded = 0;
             c.org = mk3(ray.ox, ray.oy, ray.oz);
-            if (INTEGRATOR == TAKE_INTEGRATOR_MIS) shade_mis(c, ray, hit, path);
-            else if (INTEGRATOR == TAKE_INTEGRATOR_RAW) shade_raw(c, ray, hit, path);
-            else shade_one_sample(c, ray, hit, path);
+            if (INTEGRATOR == TAKE_INTEGRATOR_MIS) shade_mis<ENV>(c, ray, hit, path);
+            else if (INTEGRATOR == TAKE_INTEGRATOR_RAW) shade_raw<ENV>(c, ray, hit, path);
+            else shade_one_sample<ENV>(c, ray, hit, path);
             emit_extend = c.emit_extend;
             emit_shadow = c.emit_shadow;
             shaded = c.shaded;
