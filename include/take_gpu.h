@@ -199,6 +199,15 @@ int take_gpu_render(TakeScene *scene, const TakeRenderOpts *opts, double *sum_rg
 int take_gpu_render_device(TakeScene *scene, const TakeRenderOpts *opts, double *d_sum_rgb, double *d_sumsq_rgb,
                            TakeStats *stats);
 
+/* Single-process multi-GPU render (what parallel_for over tiles, src/parallel.cpp:183-237, becomes across GPUs): the
+ * host-side acceleration structures are built once, the scene is replicated on devices[0..ndev), device i renders a
+ * contiguous share of the sample-index range [spp_begin, spp_end) of every pixel, and the partial sums are combined on
+ * devices[0] with one NCCL sum-reduce (libnccl.so.2 is loaded on first use).  Because a sample's random stream depends
+ * only on (seed, pixel, sample index) the result equals the single-GPU render up to summation order.  Host outputs as
+ * take_gpu_render. */
+int take_gpu_render_multi(int ndev, const int *devices, const TakeSceneDesc *desc, const TakeRenderOpts *opts, double *sum_rgb,
+                          double *sumsq_rgb, TakeStats *stats);
+
 /* Radiance of `n` individual path samples (pixel x, image row y from the top, sample index s): 3 doubles each. */
 int take_gpu_radiance_samples(TakeScene *scene, const TakeRenderOpts *opts, int64_t n, const int32_t *px,
                               const int32_t *py, const int64_t *s, double *rgb);

@@ -28,7 +28,7 @@ RENDER_NO_SORT, RENDER_STAGE_TIMES, RENDER_COUNT_TESTS = 1, 2, 4
 EXPORTS = [
     "take_gpu_device_count", "take_gpu_scene_create", "take_gpu_scene_destroy", "take_gpu_intersect",
     "take_gpu_occluded", "take_gpu_intersect_device", "take_gpu_render", "take_gpu_render_device",
-    "take_gpu_radiance_samples", "take_gpu_scene_stream", "take_gpu_scene_info", "take_gpu_last_error",
+    "take_gpu_radiance_samples", "take_gpu_render_multi", "take_gpu_scene_stream", "take_gpu_scene_info", "take_gpu_last_error",
     "take_gpu_version",
 ]
 
@@ -182,6 +182,22 @@ class GpuScene:
         _check(self.lib.take_gpu_radiance_samples(self.h, C.byref(o), len(px), px.ctypes.data, py.ctypes.data,
                                                   s.ctypes.data, out.ctypes.data))
         return out
+
+
+def render_multi(flat: FlatScene, devices, integrator="mis", max_depth=5, spp_begin=0, spp_end=1, seed=0, sumsq=True):
+    """take_gpu_render_multi: one process, several GPUs, one NCCL sum-reduce.  Returns (sum, sumsq, stats)."""
+    L = load_library()
+    L.take_gpu_render_multi.argtypes = [C.c_int, C.c_void_p, C.POINTER(TakeSceneDesc), C.POINTER(TakeRenderOpts), C.c_void_p,
+                                        C.c_void_p, C.POINTER(TakeStats)]
+    devs = (C.c_int * len(devices))(*devices)
+    desc = flat.to_desc()
+    s = np.empty((flat.height, flat.width, 3), np.float64)
+    s2 = np.empty_like(s) if sumsq else None
+    st = TakeStats()
+    o = TakeRenderOpts(INTEGRATORS[integrator], max_depth, spp_begin, spp_end, seed, 0, 0)
+    _check(L.take_gpu_render_multi(len(devices), devs, C.byref(desc), C.byref(o), s.ctypes.data,
+                                   s2.ctypes.data if sumsq else None, C.byref(st)))
+    return s, s2, st.as_dict()
 
 
 def render(params, device: int = 0, integrator: str = "mis", seed: int = 0) -> np.ndarray:

@@ -435,10 +435,20 @@ int take_gpu_device_count(int *count) {
     return TAKE_OK;
 }
 
+static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild &hb, TakeScene **out);
+
 int take_gpu_scene_create(int device, const TakeSceneDesc *d, TakeScene **out) {
     if (!out) return fail(TAKE_E_INVALID, "null argument");
     *out = nullptr;
     if (int rc = validate(d)) return rc;
+    HostBuild hb;
+    if (int rc = host_build(d, std::max(1u, std::thread::hardware_concurrency()), hb)) return rc;
+    return scene_create_from(device, d, hb, out);
+}
+
+// Upload an already built scene to `device` (the host-side trees are shared by all replicas of a multi-GPU render).
+static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild &hb, TakeScene **out) {
+    *out = nullptr;
     CU(cudaSetDevice(device));
     TakeScene *s = new TakeScene;
     struct Guard { TakeScene *&p; bool ok = false; ~Guard() { if (!ok) { delete p; p = nullptr; } } } guard{s};
@@ -448,10 +458,7 @@ int take_gpu_scene_create(int device, const TakeSceneDesc *d, TakeScene **out) {
     s->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     cudaStream_t st = s->stream;
-    const int threads = std::max(1u, std::thread::hardware_concurrency());
     const int64_t n = d->num_prims;
-    HostBuild hb;
-    if (int rc = host_build(d, threads, hb)) return rc;
     RefTree &ref = hb.ref;
     FastTree &fast = hb.fast;
     std::vector<double> &tris = hb.tris;
@@ -818,6 +825,115 @@ int take_gpu_render(TakeScene *s, const TakeRenderOpts *o, double *sum_rgb, doub
     CU(cudaMemcpyAsync(sum_rgb, s->scratch_a.p, bytes, cudaMemcpyDeviceToHost, s->stream));
     if (sumsq_rgb) CU(cudaMemcpyAsync(sumsq_rgb, s->scratch_b.p, bytes, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
+    return TAKE_OK;
+}
+
+// ---- single-process multi-GPU render: scene replicated, sample ranges sharded, one NCCL sum-reduce ------------------
+#include <dlfcn.h>
+namespace {
+struct Nccl {
+    typedef void *comm_t;
+    int (*CommInitAll)(comm_t *, int, const int *) = nullptr;
+    int (*CommDestroy)(comm_t) = nullptr;
+    int (*Reduce)(const void *, void *, size_t, int, int, int, comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+    Nccl() {
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return;
+        CommInitAll = (decltype(CommInitAll))dlsym(h, "ncclCommInitAll");
+        CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+        Reduce = (decltype(Reduce))dlsym(h, "ncclReduce");
+        GroupStart = (decltype(GroupStart))dlsym(h, "ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))dlsym(h, "ncclGroupEnd");
+        GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+        ok = CommInitAll && CommDestroy && Reduce && GroupStart && GroupEnd && GetErrorString;
+    }
+};
+const int kNcclFloat64 = 8, kNcclSum = 0;  // ncclDataType_t / ncclRedOp_t values (nccl.h)
+}  // namespace
+
+int take_gpu_render_multi(int ndev, const int *devices, const TakeSceneDesc *d, const TakeRenderOpts *o, double *sum_rgb,
+                          double *sumsq_rgb, TakeStats *stats) {
+    if (ndev < 1 || !devices || !o || !sum_rgb) return fail(TAKE_E_INVALID, "bad arguments");
+    if (int rc = validate(d)) return rc;
+    static Nccl nccl;
+    if (ndev > 1 && !nccl.ok) return fail(TAKE_E_CUDA, "libnccl.so.2 could not be loaded (needed to combine the partial images)");
+    HostBuild hb;
+    if (int rc = host_build(d, std::max(1u, std::thread::hardware_concurrency()), hb)) return rc;
+    const size_t count = (size_t)d->camera.width * d->camera.height * 3, bytes = count * sizeof(double);
+    std::vector<TakeScene *> scenes(ndev, nullptr);
+    std::vector<double *> d_sum(ndev, nullptr), d_sq(ndev, nullptr);
+    std::vector<TakeStats> st(ndev);
+    std::vector<int> rcs(ndev, TAKE_OK);
+    std::vector<std::string> errs(ndev);
+    auto cleanup = [&]() {
+        for (int i = 0; i < ndev; ++i) {
+            cudaSetDevice(devices[i]);
+            if (d_sum[i]) cudaFree(d_sum[i]);
+            if (d_sq[i]) cudaFree(d_sq[i]);
+            if (scenes[i]) take_gpu_scene_destroy(scenes[i]);
+        }
+    };
+    // replicas: one host thread per GPU uploads the scene and renders its contiguous share of [spp_begin, spp_end)
+    const int64_t n = std::max<int64_t>(0, o->spp_end - o->spp_begin), base = n / ndev, rem = n % ndev;
+    std::vector<std::thread> pool;
+    for (int i = 0; i < ndev; ++i) {
+        pool.emplace_back([&, i]() {
+            auto body = [&]() -> int {
+                if (int rc = scene_create_from(devices[i], d, hb, &scenes[i])) return rc;
+                CU(cudaMalloc((void **)&d_sum[i], bytes));
+                CU(cudaMemsetAsync(d_sum[i], 0, bytes, scenes[i]->stream));
+                if (sumsq_rgb) {
+                    CU(cudaMalloc((void **)&d_sq[i], bytes));
+                    CU(cudaMemsetAsync(d_sq[i], 0, bytes, scenes[i]->stream));
+                }
+                TakeRenderOpts mine = *o;
+                mine.spp_begin = o->spp_begin + i * base + std::min<int64_t>(i, rem);
+                mine.spp_end = mine.spp_begin + base + (i < rem ? 1 : 0);
+                return take_gpu_render_device(scenes[i], &mine, d_sum[i], d_sq[i], &st[i]);
+            };
+            rcs[i] = body();
+            if (rcs[i]) errs[i] = g_error;  // g_error is thread-local
+        });
+    }
+    for (auto &t : pool) t.join();
+    for (int i = 0; i < ndev; ++i)
+        if (rcs[i]) { int rc = rcs[i]; std::string e = errs[i]; cleanup(); return fail(rc, e); }
+    // the path's one exchange step: sum-reduce of the W x H x 3 partial buffers onto devices[0] over NVLink
+    if (ndev > 1) {
+        std::vector<Nccl::comm_t> comms(ndev, nullptr);
+        int r = nccl.CommInitAll(comms.data(), ndev, devices);
+        if (r) { cleanup(); return fail(TAKE_E_CUDA, std::string("ncclCommInitAll: ") + nccl.GetErrorString(r)); }
+        for (int pass = 0; pass < (sumsq_rgb ? 2 : 1) && !r; ++pass) {
+            nccl.GroupStart();
+            for (int i = 0; i < ndev && !r; ++i) {
+                double *buf = pass == 0 ? d_sum[i] : d_sq[i];
+                r = nccl.Reduce(buf, buf, count, kNcclFloat64, kNcclSum, 0, comms[i], scenes[i]->stream);
+            }
+            int e = nccl.GroupEnd();
+            if (!r) r = e;
+        }
+        for (int i = 0; i < ndev; ++i) { cudaSetDevice(devices[i]); cudaStreamSynchronize(scenes[i]->stream); }
+        for (auto c : comms) if (c) nccl.CommDestroy(c);
+        if (r) { cleanup(); return fail(TAKE_E_CUDA, std::string("ncclReduce: ") + nccl.GetErrorString(r)); }
+    }
+    cudaSetDevice(devices[0]);
+    cudaError_t ce = cudaMemcpy(sum_rgb, d_sum[0], bytes, cudaMemcpyDeviceToHost);
+    if (ce == cudaSuccess && sumsq_rgb) ce = cudaMemcpy(sumsq_rgb, d_sq[0], bytes, cudaMemcpyDeviceToHost);
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        for (int i = 0; i < ndev; ++i) {
+            stats->samples += st[i].samples; stats->extend_rays += st[i].extend_rays; stats->shadow_rays += st[i].shadow_rays;
+            stats->shaded += st[i].shaded; stats->kernel_launches += st[i].kernel_launches; stats->waves += st[i].waves;
+            stats->ms_total = std::max(stats->ms_total, st[i].ms_total);
+        }
+    }
+    cleanup();
+    if (ce != cudaSuccess) return fail(TAKE_E_CUDA, cudaGetErrorString(ce));
     return TAKE_OK;
 }
 

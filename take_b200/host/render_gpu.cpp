@@ -7,7 +7,7 @@
 // aggregate (src/scene.h:13-33) is flattened into a TakeSceneDesc -- this is the only code that looks inside the
 // std::variant types -- and build_bvh + the tile loop + the integrators run on the GPU.
 //
-// Additive flags (the reference ignores unknown params): -integrator mis|raw|one_sample_mis   -seed N   -device D
+// Additive flags (the reference ignores unknown params): -integrator mis|raw|one_sample_mis   -seed N   -device D   -gpus N
 // It is compiled against the reference's headers; it contains no reference code.
 #include <cstring>
 #include <iostream>
@@ -132,12 +132,13 @@ void flatten(const Scene &sc, Flattened &f) {
 
 Image3 render(const std::vector<std::string> &params) {
     if (params.size() < 1) return Image3(0, 0);
-    int max_depth = 50, device = 0, integrator = TAKE_INTEGRATOR_MIS;  // render.cpp:14,76
+    int max_depth = 50, device = 0, gpus = 1, integrator = TAKE_INTEGRATOR_MIS;  // render.cpp:14,76
     uint64_t seed = 0;
     std::string filename;
     for (int i = 0; i < (int)params.size(); i++) {
         if (params[i] == "-max_depth") max_depth = std::stoi(params[++i]);
         else if (params[i] == "-device") device = std::stoi(params[++i]);
+        else if (params[i] == "-gpus") gpus = std::stoi(params[++i]);
         else if (params[i] == "-seed") seed = std::stoull(params[++i]);
         else if (params[i] == "-integrator") {
             const std::string v = params[++i];
@@ -152,6 +153,24 @@ Image3 render(const std::vector<std::string> &params) {
 
     Flattened flat;
     flatten(scene, flat);
+    const Camera &cam0 = scene.camera;
+    if (gpus > 1) {  // scene replicated on GPUs device .. device+gpus-1, samples sharded, one NCCL reduce
+        std::vector<int> devs(gpus);
+        for (int i = 0; i < gpus; ++i) devs[i] = device + i;
+        std::vector<double> sum((size_t)cam0.width * cam0.height * 3);
+        TakeRenderOpts opts{};
+        opts.integrator = integrator; opts.max_depth = max_depth; opts.spp_begin = 0; opts.spp_end = scene.options.spp; opts.seed = seed;
+        TakeStats stats{};
+        std::cout << "Building BVH and rendering on " << gpus << " GPUs..." << std::endl;
+        tick(timer);
+        if (take_gpu_render_multi(gpus, devs.data(), &flat.desc, &opts, sum.data(), nullptr, &stats) != TAKE_OK)
+            Error(std::string("take_gpu: ") + take_gpu_last_error());
+        Image3 img(cam0.width, cam0.height);
+        const Real inv = Real(1) / Real(scene.options.spp);
+        for (size_t i = 0; i < img.data.size(); ++i) img.data[i] = Vector3{sum[3 * i], sum[3 * i + 1], sum[3 * i + 2]} * inv;
+        std::cout << std::endl << "Finish building rendering. Took " << tick(timer) << " seconds." << std::endl;
+        return img;
+    }
     std::cout << "Building BVH..." << std::endl;
     tick(timer);
     TakeScene *gpu = nullptr;
