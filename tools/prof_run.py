@@ -1,11 +1,12 @@
-"""Short profiling workload: config-2 scene, one wave of 2 spp at 1920x1080 (one-sample MIS), then one wave of the
-multi-sample MIS integrator (adds the shadow kernel).  No torch import, a handful of launches: meant for `ncu`."""
+"""Short profiling workload for `ncu`: config-2 scene, ONE bench-sized wave (8 spp x 1920x1080 = 16.6 M slots) of the
+one-sample-MIS integrator (7 extend + 7 shade launches), then one wave of the multi-sample MIS integrator (adds the
+shadow kernel).  No torch import."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from take_b200 import api, scenes
 flat = scenes.heightfield().flat()
 gs = api.GpuScene(flat)
 for integ in ("one_sample_mis", "mis"):
-    s, s2, st = gs.render_sums(integ, 5, 0, 2, seed=1)
-    print(integ, st["ms_total"], st["extend_rays"], st["shadow_rays"], st["kernel_launches"])
+    s, s2, st = gs.render_sums(integ, 5, 0, 8, seed=1, flags=api.RENDER_COUNT_TESTS if "--count" in sys.argv else 0)
+    print(integ, {k: st[k] for k in ("ms_total", "extend_rays", "shadow_rays", "box_tests", "tri_tests", "kernel_launches", "waves")})
 gs.close()
