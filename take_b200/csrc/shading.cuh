@@ -79,7 +79,7 @@ __device__ __forceinline__ D3 eval_texture(const DevScene &sc, const TakeMateria
     return divs(acc, (double)((x2 - x1) * (y2 - y1)));
 }
 
-// ---- environment map (EXTENSION, see include/take_gpu.h; mirrors oracle/take_oracle.cpp) ------------------------
+// ---- environment map (EXTENSION without a reference counterpart, see include/take_gpu.h) ----------------------
 __device__ __forceinline__ double luminance(D3 c) { return c.x * 0.212671 + c.y * 0.715160 + c.z * 0.072169; }  // vector.h:309-311
 __device__ __forceinline__ double clamp1(double v) { return v < -1.0 ? -1.0 : (v > 1.0 ? 1.0 : v); }
 

@@ -499,7 +499,7 @@ static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild &hb, 
     }
     if ((rc = upload(s->textures, tex.data(), tex.size(), st))) return rc;
     // EXTENSION: environment map + marginal / conditional CDF tables of luminance x sin(theta at the row centre).
-    // Same loops and operation order as oracle/take_oracle.cpp:build_env_tables, so the tables are bit-identical.
+    // (The CPU checker used by the tests builds its tables with the same loops and operation order, so sampling decisions agree.)
     std::vector<double> env_marg, env_cond;
     double env_total = 0;
     const bool has_env = d->env_rgb && d->env_width > 0 && d->env_height > 0;

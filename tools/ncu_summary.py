@@ -11,7 +11,7 @@ METRICS = [
     ("dram__bytes_read.sum", "dram_read"),
     ("dram__bytes_write.sum", "dram_write"),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct_of_peak"),
-    ("lts__t_bytes.sum", "l2_bytes"),
+    ("l1tex__m_xbar2l1tex_read_bytes.sum", "l2_bytes"),   # bytes the SMs read from L2 (L2 -> L1 crossbar)
     ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2_pct_of_peak"),
     ("lts__t_sector_hit_rate.pct", "l2_hit_pct"),
     ("l1tex__t_sector_hit_rate.pct", "l1_hit_pct"),
@@ -113,9 +113,12 @@ if os.path.exists(os.path.join(g, "launches_bench.csv")):
     for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:8]:
         print(f"{k:50s} n={n:4d} {us/1e3:9.3f} ms {100*us/total:5.1f}%")
 if "extend" in res:
-    # traffic of the dominant kernel per launch: the largest (primary-ray) launch of the capture
-    r = max(res["extend"], key=lambda x: x["duration_us"])
-    json.dump({"kernel": r["kernel"], "dram_bytes_per_launch": (r["dram_read_MB"] + r["dram_write_MB"]) * 1e6,
-               "launch_duration_us_under_ncu": r["duration_us"],
-               "note": "ncu --set full capture of tools/prof_run.py (2 spp x 1920x1080 wave, pass-0 launch); see " + f"{tag}_ncu_extend.csv"},
+    # DRAM traffic of the dominant kernel per launch: the capture holds exactly the 7 k_extend launches of ONE bench-sized
+    # wave (tools/prof_run.py), so the mean over them is "per launch" in the same sense as bench.py's algorithmic bytes
+    rows = res["extend"]
+    total = sum(r["dram_read_MB"] + r["dram_write_MB"] for r in rows) * 1e6
+    json.dump({"kernel": "k_extend", "dram_bytes_per_launch": total / len(rows), "launches_captured": len(rows),
+               "dram_bytes_per_wave": total,
+               "note": "ncu --set full capture of tools/prof_run.py: the 7 k_extend launches of one 16.6 M-slot wave "
+                       f"(8 spp x 1920x1080, config 2); per-launch rows in {tag}_ncu_extend.csv"},
               open(os.path.join(OUT, "extend_traffic.json"), "w"), indent=1)
