@@ -43,12 +43,16 @@ for name, make, integ, spp in CONFIGS:
         else:
             cpu, kind = O.load(flat), "port"
         port = cpu if kind == "port" else O.load(flat) if flat.num_prims < 3_000_000 else None
-        step = max(1, int(round(flat.width * flat.height / 400000)))            # ~400 k path samples per measurement
+        step = max(1, int(round(flat.width * flat.height / 1000000)))           # ~1 M path samples per call
         rows = len(range(0, flat.height, step))
-        t0 = time.perf_counter()
-        cpu.render(integ, 5, 0, 1, seed=1, threads=cores, sumsq=False, row_begin=0, row_step=step)
-        dt = time.perf_counter() - t0
-        n = rows * flat.width
+        cpu.render(integ, 5, 0, 1, seed=1, threads=cores, sumsq=False, row_begin=0, row_step=max(step, 8))   # warm-up
+        dt, n, k = 0.0, 0, 0
+        while dt < 5.0 and k < 64:                                                # bounded sample: about 5 s of CPU work
+            t0 = time.perf_counter()
+            cpu.render(integ, 5, k, k + 1, seed=1, threads=cores, sumsq=False, row_begin=k % step, row_step=step)
+            dt += time.perf_counter() - t0
+            n += len(range(k % step, flat.height, step)) * flat.width
+            k += 1
         line.update(cpu_kind=kind, cpu_cores=cores, cpu_msamples_s=round(n / dt / 1e6, 4), cpu_sample=f"{n} samples in {dt:.1f} s",
                     cpu_mrays_s=round(n / dt / 1e6 * line["rays_per_sample"], 3),
                     speedup=round(line["gpu_msamples_s"] / (n / dt / 1e6), 0))
