@@ -189,6 +189,8 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
@@ -231,6 +233,9 @@ def run_ours(args):
     # ---- timed region: K steps + the one reduction, device-timed on the launching stream -----------------------
     for i in range(args.warmup):
         device_step(i)
+    if world > 1:                    # warm the collective too (communicator set-up, buffer registration)
+        dist.all_reduce(d_sum)
+        dist.all_reduce(d_sq)
     d_sum.zero_(); d_sq.zero_()
     barrier()
     clocks = ClockSampler(local) if rank == 0 else None
