@@ -538,70 +538,80 @@ __global__ void __launch_bounds__(128, TAKE_SHADE_MIN_BLOCKS) k_shade(DevScene s
         int slot = -1, shaded = 0;
         if (valid) {
             slot = (primary && !w.sort_enabled) ? (int)i : queue[i];
-            RayRec ray;
-            PathRec path;
             const HitRec hit = w.hit[slot];
-            if (primary) {  // nothing was stored for the camera ray: recompute it (2 draws) and start the path
-                D3 o, d;
-                primary_ray(sc, w, slot, o, d);
-                ray.ox = o.x; ray.oy = o.y; ray.oz = o.z; ray.dx = d.x; ray.dy = d.y; ray.dz = d.z;
-                ray.tmax = INFINITY; ray.aux0 = ray.aux1 = 0;
-                path.thr[0] = path.thr[1] = path.thr[2] = 1.0;
-                path.rad[0] = path.rad[1] = path.rad[2] = 0.0;
-                path.k = 2; path.depth = 0; path.flags = PEND_PRIMARY; path.pad = 0;
+            if (primary && !ENV && hit.prim < 0) {
+                // a camera ray that left the scene: the sample is the background colour (path_tracing.h:8); no need to
+                // recompute the ray (the environment-map build needs its direction and takes the general path)
+                PathRec p;
+                p.thr[0] = p.thr[1] = p.thr[2] = 1.0;
+                p.rad[0] = sc.background.x; p.rad[1] = sc.background.y; p.rad[2] = sc.background.z;
+                p.k = 2; p.depth = 0; p.flags = 0; p.pad = 0;
+                w.path[slot] = p;
             } else {
-                ray = w.ray[slot];
-                path = w.path[slot];
-            }
-            uint32_t pixel;
-            uint64_t sample;
-            slot_identity(w, slot, pixel, sample);
-            ShadeCtx c = {sc, w, slot, pass};
-            c.thr = mk3(path.thr[0], path.thr[1], path.thr[2]);
-            c.rad = mk3(path.rad[0], path.rad[1], path.rad[2]);
-            c.rng.seed = w.seed; c.rng.sample = sample; c.rng.pixel = pixel; c.rng.k = path.k;
-            c.emit_extend = c.emit_shadow = false;
-            c.depth = path.depth;
-            c.pend_flags = 0;
-            c.shaded = 0;
-            c.org = mk3(ray.ox, ray.oy, ray.oz);
-            if (INTEGRATOR == TAKE_INTEGRATOR_MIS) shade_mis<ENV>(c, ray, hit, path);
-            else if (INTEGRATOR == TAKE_INTEGRATOR_RAW) shade_raw<ENV>(c, ray, hit, path);
-            else shade_one_sample<ENV>(c, ray, hit, path);
-            emit_extend = c.emit_extend;
-            emit_shadow = c.emit_shadow;
-            shaded = c.shaded;
-            PathRec p;
-            p.thr[0] = c.thr.x; p.thr[1] = c.thr.y; p.thr[2] = c.thr.z;
-            p.rad[0] = c.rad.x; p.rad[1] = c.rad.y; p.rad[2] = c.rad.z;
-            p.k = c.rng.k;
-            p.depth = c.depth;
-            p.flags = c.pend_flags;
-            p.pad = 0;
-            w.path[slot] = p;
-            if (emit_extend || emit_shadow) {
-                RayRec r;
-                r.ox = c.org.x; r.oy = c.org.y; r.oz = c.org.z;
-                r.dx = c.ext_dir.x; r.dy = c.ext_dir.y; r.dz = c.ext_dir.z;
-                r.tmax = INFINITY;
-                r.aux0 = r.aux1 = 0;
-                w.ray[slot] = r;
-            }
-            if (emit_extend) {
-                PendRec pe;
-                pe.fg[0] = c.pend_fg.x; pe.fg[1] = c.pend_fg.y; pe.fg[2] = c.pend_fg.z;
-                pe.bpdf = c.pend_pdf;
-                w.pend[slot] = pe;
-            }
-            if (emit_shadow) {
-                ShadowRec s;
-                s.dx = c.sh_dir.x; s.dy = c.sh_dir.y; s.dz = c.sh_dir.z;
-                s.tmax = c.sh_tmax;
-                s.cx = c.sh_contrib.x; s.cy = c.sh_contrib.y; s.cz = c.sh_contrib.z;
-                s.pad = 0;
-                w.shadow[slot] = s;
-            }
-        }
+                RayRec ray;
+                PathRec path;
+                if (primary) {  // nothing was stored for the camera ray: recompute it (2 draws) and start the path
+                    D3 o, d;
+                    primary_ray(sc, w, slot, o, d);
+                    ray.ox = o.x; ray.oy = o.y; ray.oz = o.z; ray.dx = d.x; ray.dy = d.y; ray.dz = d.z;
+                    ray.tmax = INFINITY; ray.aux0 = ray.aux1 = 0;
+                    path.thr[0] = path.thr[1] = path.thr[2] = 1.0;
+                    path.rad[0] = path.rad[1] = path.rad[2] = 0.0;
+                    path.k = 2; path.depth = 0; path.flags = PEND_PRIMARY; path.pad = 0;
+                } else {
+                    ray = w.ray[slot];
+                    path = w.path[slot];
+                }
+                uint32_t pixel;
+                uint64_t sample;
+                slot_identity(w, slot, pixel, sample);
+                ShadeCtx c = {sc, w, slot, pass};
+                c.thr = mk3(path.thr[0], path.thr[1], path.thr[2]);
+                c.rad = mk3(path.rad[0], path.rad[1], path.rad[2]);
+                c.rng.seed = w.seed; c.rng.sample = sample; c.rng.pixel = pixel; c.rng.k = path.k;
+                c.emit_extend = c.emit_shadow = false;
+                c.depth = path.depth;
+                c.pend_flags = 0;
+                c.shaded = 0;
+                c.org = mk3(ray.ox, ray.oy, ray.oz);
+                if (INTEGRATOR == TAKE_INTEGRATOR_MIS) shade_mis<ENV>(c, ray, hit, path);
+                else if (INTEGRATOR == TAKE_INTEGRATOR_RAW) shade_raw<ENV>(c, ray, hit, path);
+                else shade_one_sample<ENV>(c, ray, hit, path);
+                emit_extend = c.emit_extend;
+                emit_shadow = c.emit_shadow;
+                shaded = c.shaded;
+                PathRec p;
+                p.thr[0] = c.thr.x; p.thr[1] = c.thr.y; p.thr[2] = c.thr.z;
+                p.rad[0] = c.rad.x; p.rad[1] = c.rad.y; p.rad[2] = c.rad.z;
+                p.k = c.rng.k;
+                p.depth = c.depth;
+                p.flags = c.pend_flags;
+                p.pad = 0;
+                w.path[slot] = p;
+                if (emit_extend || emit_shadow) {
+                    RayRec r;
+                    r.ox = c.org.x; r.oy = c.org.y; r.oz = c.org.z;
+                    r.dx = c.ext_dir.x; r.dy = c.ext_dir.y; r.dz = c.ext_dir.z;
+                    r.tmax = INFINITY;
+                    r.aux0 = r.aux1 = 0;
+                    w.ray[slot] = r;
+                }
+                if (emit_extend) {
+                    PendRec pe;
+                    pe.fg[0] = c.pend_fg.x; pe.fg[1] = c.pend_fg.y; pe.fg[2] = c.pend_fg.z;
+                    pe.bpdf = c.pend_pdf;
+                    w.pend[slot] = pe;
+                }
+                if (emit_shadow) {
+                    ShadowRec s;
+                    s.dx = c.sh_dir.x; s.dy = c.sh_dir.y; s.dz = c.sh_dir.z;
+                    s.tmax = c.sh_tmax;
+                    s.cx = c.sh_contrib.x; s.cy = c.sh_contrib.y; s.cz = c.sh_contrib.z;
+                    s.pad = 0;
+                    w.shadow[slot] = s;
+                }
+                    }
+}
         queue_push(emit_extend, q_next, &w.pass[pass + 1].n_extend, slot);
         queue_push(emit_shadow, w.q_shadow, &pc.n_shadow, slot);
         shaded = __reduce_add_sync(0xffffffffu, shaded);
