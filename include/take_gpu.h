@@ -45,7 +45,11 @@ enum {
     TAKE_MAT_DISNEY_GLASS = 8,     /* (src/materials/disney_metal.inl:1-28 and siblings)  */
     TAKE_MAT_DISNEY_CLEARCOAT = 9, /* cosine sampling, eval == 0 (disney_clearcoat.inl:22-27) */
     TAKE_MAT_DISNEY_SHEEN = 10,
-    TAKE_MAT_DISNEY_BSDF = 11
+    TAKE_MAT_DISNEY_BSDF = 11,
+    /* EXTENSION (no counterpart in the reference, whose only microfacet model is BlinnPhongMicrofacet): GGX /
+     * Trowbridge-Reitz distribution with the separable Smith shadowing term and Schlick Fresnel, written in the
+     * structure of src/materials/blinn_phong_microfacet.inl.  p[0] = roughness alpha.  Parity unpinned. */
+    TAKE_MAT_GGX = 12
 };
 
 enum { TAKE_LIGHT_POINT = 0, TAKE_LIGHT_AREA = 1 }; /* src/light.h:9-19 */

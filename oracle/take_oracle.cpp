@@ -466,13 +466,24 @@ inline double blinn_G_hat(V3 omega, V3 n, double alpha) {
     return a < 1.6 ? (3.535 * a + 2.181 * a2) / (1 + 2.276 * a + 2.577 * a2) : 1;
 }
 
+// EXTENSION (TAKE_MAT_GGX): GGX distribution and Smith G1, no reference counterpart
+inline double ggx_D(double ndh, double alpha) {
+    double a2 = alpha * alpha;
+    double k = ndh * ndh * (a2 - 1) + 1;
+    return a2 / (PI * k * k);
+}
+inline double ggx_G1(double ndw, double alpha) {
+    double a2 = alpha * alpha;
+    return 2 * ndw / (ndw + sqrt(a2 + (1 - a2) * ndw * ndw));
+}
+
 inline V3 shading_n(V3 dir_in, const Isect &v) { return dot(dir_in, v.sn) < 0 ? neg(v.sn) : v.sn; }
 inline V3 reflect(V3 dir_in, V3 n) { return add(neg(dir_in), mul(n, 2 * dot(dir_in, n))); }
 
 inline bool is_lambert_like(int t) {
     return t == TAKE_MAT_DIFFUSE || t == TAKE_MAT_DISNEY_DIFFUSE || t == TAKE_MAT_DISNEY_METAL ||
            t == TAKE_MAT_DISNEY_GLASS || t == TAKE_MAT_DISNEY_CLEARCOAT || t == TAKE_MAT_DISNEY_SHEEN ||
-           t == TAKE_MAT_DISNEY_BSDF;
+           t == TAKE_MAT_DISNEY_BSDF;  // (TAKE_MAT_GGX is not)
 }
 
 // Blinn-Phong half-vector sampling shared by blinn_phong.inl:1-29 and blinn_phong_microfacet.inl:1-29;
@@ -516,6 +527,19 @@ bool sample_bsdf(const TakeMaterialDesc &m, V3 dir_in, const Isect &v, Rng &rng,
         }
         return true;
     }
+    if (t == TAKE_MAT_GGX) {  // EXTENSION: sample h ~ D(h) (n.h), reflect; structure of blinn_phong_microfacet.inl:1-29
+        double alpha = m.p[0];
+        double u1 = rng.next();
+        double u2 = rng.next();
+        double phi = TWOPI * u2;
+        double cos_t = sqrt(clampd((1 - u1) / (1 + (alpha * alpha - 1) * u1), 0, 1));
+        double sin_t = sqrt(clampd(1 - cos_t * cos_t, 0, 1));
+        V3 h = normalize(to_world(n, V3{cos(phi) * sin_t, sin(phi) * sin_t, cos_t}));
+        dir_out = normalize(add(neg(dir_in), mul(h, 2 * dot(dir_in, h))));
+        if (dot(v.gn, dir_out) <= 0 || dot(h, n) <= 0 || dot(dir_out, h) <= 0) pdf = 0;
+        else pdf = ggx_D(clampd(dot(n, h), 0, 1), alpha) * dot(n, h) * 0.25 / dot(dir_out, h);
+        return true;
+    }
     double ex = m.p[0];
     if (t == TAKE_MAT_PHONG) {  // phong.inl:1-28
         V3 local = sample_power_cos_lobe(ex, rng);
@@ -551,6 +575,11 @@ double bsdf_pdf(const TakeMaterialDesc &m, V3 dir_in, V3 dir_out, const Isect &v
         double F = F0 + (1 - F0) * pow(1 - dot(n, dir_out), 5.0);
         return (1 - F) * fmax(dot(n, dir_out), 0.0) / PI;
     }
+    if (t == TAKE_MAT_GGX) {  // EXTENSION
+        V3 h = normalize(add(dir_out, dir_in));
+        if (dot(v.gn, dir_out) <= 0 || dot(h, n) <= 0 || dot(dir_out, h) <= 0) return 0;
+        return ggx_D(clampd(dot(n, h), 0, 1), m.p[0]) * dot(n, h) * 0.25 / dot(dir_out, h);
+    }
     double ex = m.p[0];
     if (t == TAKE_MAT_PHONG) {  // phong.inl:30-40
         V3 rd = normalize(reflect(dir_in, n));
@@ -582,6 +611,15 @@ V3 bsdf_eval(const Scene &sc, const TakeMaterialDesc &m, V3 dir_in, V3 dir_out, 
         if (rec_pdf == 1.0) return {1, 1, 1};
         V3 Kd = eval_texture(sc, m, v.uv);
         return divs(mul(Kd, fmax(dot(n, dir_out), 0.0)), PI);
+    }
+    if (t == TAKE_MAT_GGX) {  // EXTENSION: F D G / (4 n.w_in), the form of blinn_phong_microfacet.inl:43-60
+        V3 h = normalize(add(dir_out, dir_in));
+        if (dot(n, dir_out) <= 0 || dot(dir_out, h) <= 0 || dot(dir_in, h) <= 0) return zero;
+        V3 Ks = eval_texture(sc, m, v.uv);
+        V3 Fh = add(Ks, mul(rsub(1, Ks), pow(1 - dot(h, dir_out), 5.0)));
+        double Dh = ggx_D(clampd(dot(n, h), 0, 1), m.p[0]);
+        double G = ggx_G1(dot(n, dir_out), m.p[0]) * ggx_G1(dot(n, dir_in), m.p[0]);
+        return divs(mul(mul(mul(Fh, Dh), G), 0.25), dot(n, dir_in));
     }
     double ex = m.p[0];
     if (t == TAKE_MAT_PHONG) {  // phong.inl:42-54

@@ -162,7 +162,17 @@ __device__ __forceinline__ D3 shading_n(D3 dir_in, const Isect &v) { return dot(
 __device__ __forceinline__ D3 reflect(D3 dir_in, D3 n) { return add(neg(dir_in), mul(n, 2 * dot(dir_in, n))); }
 
 __device__ __forceinline__ bool is_lambert_like(int t) {
-    return t == TAKE_MAT_DIFFUSE || t >= TAKE_MAT_DISNEY_DIFFUSE;
+    return t == TAKE_MAT_DIFFUSE || (t >= TAKE_MAT_DISNEY_DIFFUSE && t <= TAKE_MAT_DISNEY_BSDF);
+}
+// EXTENSION (TAKE_MAT_GGX): GGX distribution and Smith G1, no reference counterpart
+__device__ __forceinline__ double ggx_D(double ndh, double alpha) {
+    double a2 = alpha * alpha;
+    double k = ndh * ndh * (a2 - 1) + 1;
+    return a2 / (TAKE_PI * k * k);
+}
+__device__ __forceinline__ double ggx_G1(double ndw, double alpha) {
+    double a2 = alpha * alpha;
+    return 2 * ndw / (ndw + sqrt(a2 + (1 - a2) * ndw * ndw));
 }
 __device__ __forceinline__ bool is_specular(int t) { return t == TAKE_MAT_PLASTIC || t == TAKE_MAT_MIRROR; }
 
@@ -206,6 +216,19 @@ __device__ __forceinline__ bool sample_bsdf(const TakeMaterialDesc &m, D3 dir_in
         }
         return true;
     }
+    if (t == TAKE_MAT_GGX) {  // EXTENSION: sample h ~ D(h) (n.h), reflect; structure of blinn_phong_microfacet.inl:1-29
+        const double alpha = m.p[0];
+        double u1 = rng.next();
+        double u2 = rng.next();
+        double phi = TAKE_TWOPI * u2;
+        double cos_t = sqrt(clampd((1 - u1) / (1 + (alpha * alpha - 1) * u1), 0, 1));
+        double sin_t = sqrt(clampd(1 - cos_t * cos_t, 0, 1));
+        D3 h = normalize(to_world(n, mk3(cos(phi) * sin_t, sin(phi) * sin_t, cos_t)));
+        dir_out = normalize(add(neg(dir_in), mul(h, 2 * dot(dir_in, h))));
+        if (dot(v.gn, dir_out) <= 0 || dot(h, n) <= 0 || dot(dir_out, h) <= 0) pdf = 0;
+        else pdf = ggx_D(clampd(dot(n, h), 0, 1), alpha) * dot(n, h) * 0.25 / dot(dir_out, h);
+        return true;
+    }
     const double ex = m.p[0];
     if (t == TAKE_MAT_PHONG) {  // phong.inl:1-28
         D3 local = sample_power_cos_lobe(ex, rng);
@@ -241,6 +264,11 @@ __device__ __forceinline__ double bsdf_pdf(const TakeMaterialDesc &m, D3 dir_in,
         double F = F0 + (1 - F0) * pow(1 - dot(n, dir_out), 5.0);
         return (1 - F) * fmax(dot(n, dir_out), 0.0) / TAKE_PI;
     }
+    if (t == TAKE_MAT_GGX) {  // EXTENSION
+        D3 h = normalize(add(dir_out, dir_in));
+        if (dot(v.gn, dir_out) <= 0 || dot(h, n) <= 0 || dot(dir_out, h) <= 0) return 0;
+        return ggx_D(clampd(dot(n, h), 0, 1), m.p[0]) * dot(n, h) * 0.25 / dot(dir_out, h);
+    }
     const double ex = m.p[0];
     if (t == TAKE_MAT_PHONG) {  // phong.inl:30-40
         D3 rd = normalize(reflect(dir_in, n));
@@ -274,6 +302,15 @@ __device__ __forceinline__ D3 bsdf_eval(const DevScene &sc, const TakeMaterialDe
         if (rec_pdf == 1.0) return mk3(1, 1, 1);
         D3 Kd = eval_texture(sc, m, v.uv);
         return divs(mul(Kd, fmax(dot(n, dir_out), 0.0)), TAKE_PI);
+    }
+    if (t == TAKE_MAT_GGX) {  // EXTENSION: F D G / (4 n.w_in), the form of blinn_phong_microfacet.inl:43-60
+        D3 h = normalize(add(dir_out, dir_in));
+        if (dot(n, dir_out) <= 0 || dot(dir_out, h) <= 0 || dot(dir_in, h) <= 0) return zero;
+        D3 Ks = eval_texture(sc, m, v.uv);
+        D3 Fh = add(Ks, mul(rsub(1, Ks), pow(1 - dot(h, dir_out), 5.0)));
+        double Dh = ggx_D(clampd(dot(n, h), 0, 1), m.p[0]);
+        double G = ggx_G1(dot(n, dir_out), m.p[0]) * ggx_G1(dot(n, dir_in), m.p[0]);
+        return divs(mul(mul(mul(Fh, Dh), G), 0.25), dot(n, dir_in));
     }
     const double ex = m.p[0];
     if (t == TAKE_MAT_PHONG) {  // phong.inl:42-54

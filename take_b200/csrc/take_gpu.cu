@@ -132,7 +132,7 @@ int validate(const TakeSceneDesc *d) {
     }
     for (int i = 0; i < d->num_materials; ++i) {
         const TakeMaterialDesc &m = d->materials[i];
-        if (m.type < 0 || m.type > TAKE_MAT_DISNEY_BSDF) return fail(TAKE_E_INVALID, "unknown material type");
+        if (m.type < 0 || m.type > TAKE_MAT_GGX) return fail(TAKE_E_INVALID, "unknown material type");
         if (m.tex_id >= d->num_textures) return fail(TAKE_E_INVALID, "texture id out of range");
     }
     if (d->env_rgb && (d->env_width <= 0 || d->env_height <= 0)) return fail(TAKE_E_INVALID, "bad environment map size");

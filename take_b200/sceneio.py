@@ -32,6 +32,7 @@ import numpy as np
 # Material::index() order of the reference's std::variant (src/material.h:82-93).
 MAT_DIFFUSE, MAT_MIRROR, MAT_PLASTIC, MAT_PHONG, MAT_BLINN_PHONG, MAT_BLINN_MICROFACET = range(6)
 MAT_DISNEY_DIFFUSE, MAT_DISNEY_METAL, MAT_DISNEY_GLASS, MAT_DISNEY_CLEARCOAT, MAT_DISNEY_SHEEN, MAT_DISNEY_BSDF = range(6, 12)
+MAT_GGX = 12   # EXTENSION: no counterpart in the reference (include/take_gpu.h)
 
 LIGHT_POINT, LIGHT_AREA = 0, 1
 PRIM_HAS_NORMALS, PRIM_HAS_UVS, PRIM_SPHERE = 1, 2, 4

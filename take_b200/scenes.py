@@ -184,6 +184,8 @@ class SceneBuilder:
             elif t == sio.MAT_DISNEY_DIFFUSE:
                 mats[i]["p"][0] = p.get("roughness", 0.5)
                 mats[i]["p"][1] = p.get("subsurface", 0.0)
+            elif t == sio.MAT_GGX:
+                mats[i]["p"][0] = p.get("alpha", 0.14)
         textures = []
         for rgbe in self.textures:
             scale = np.ldexp(np.float32(1.0), rgbe[..., 3].astype(np.int32) - 136).astype(np.float32)
@@ -204,6 +206,8 @@ class SceneBuilder:
         os.makedirs(directory, exist_ok=True)
         if self.env is not None:
             raise ValueError("the reference has no environment emitter: scenes with an environment map cannot be written as XML")
+        if any(m["type"] == sio.MAT_GGX for m in self.materials):
+            raise ValueError("the reference has no GGX BSDF: scenes using the GGX extension cannot be written as XML")
         x = ['<?xml version="1.0" encoding="utf-8"?>', '<scene version="0.5.0">']
         x.append('<sensor type="perspective">')
         x.append(f'  <float name="fov" value="{_fmt(self.vfov)}"/><string name="fovAxis" value="y"/>')
@@ -348,6 +352,8 @@ def heightfield(n=708, width=1920, height=1080, spp=256, seed=1234, mtype=sio.MA
     b = SceneBuilder(width, height, (0, 160, 240), (0, 0, 0), (0, 1, 0), 45.0, spp, (0.05, 0.05, 0.08))
     if mtype == sio.MAT_BLINN_MICROFACET:
         m = b.material(mtype, (0.7, 0.6, 0.4), exponent=100)
+    elif mtype == sio.MAT_GGX:
+        m = b.material(mtype, (0.7, 0.6, 0.4), alpha=0.14)   # the GGX variant of config 2 (extension, unpinned)
     else:
         m = b.material(mtype, (0.7, 0.6, 0.4))
     black = b.material(sio.MAT_DIFFUSE, (0, 0, 0))
