@@ -1,6 +1,7 @@
 #include "bvh_build.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -121,7 +122,9 @@ struct SahBuilder {
     Forker fork;
 
     SahBuilder(const Aabb *b, int32_t *i, int64_t n, int ml, int threads)
-        : boxes(b), ids(i), nodes((size_t)std::max<int64_t>(2 * n, 2)), max_leaf(ml), c_trav(1.0), c_isect(1.2), fork(threads) {}
+        : boxes(b), ids(i), nodes((size_t)std::max<int64_t>(2 * n, 2)), max_leaf(ml), c_trav(1.0), c_isect(1.2), fork(threads) {
+        if (const char *e = getenv("TAKE_SAH_CISECT")) c_isect = atof(e);  // tuning knob: cost of a leaf test relative to a node visit
+    }
 
     int32_t alloc() { return next.fetch_add(1); }
 
@@ -130,48 +133,107 @@ struct SahBuilder {
         n.count = (int32_t)(hi - lo);
     }
 
+    // Run f(tid, a, b) over [lo, hi) split into `parts` contiguous chunks on their own threads (used only for the few huge
+    // ranges at the top of the tree, where the recursion itself offers no parallelism yet).
+    template <typename F>
+    static void chunked(int64_t lo, int64_t hi, int parts, F f) {
+        if (parts <= 1) { f(0, lo, hi); return; }
+        std::vector<std::thread> pool;
+        const int64_t m = hi - lo;
+        for (int t = 1; t < parts; ++t) pool.emplace_back(f, t, lo + m * t / parts, lo + m * (t + 1) / parts);
+        f(0, lo, lo + m / parts);
+        for (auto &t : pool) t.join();
+    }
+    int top_threads = 1;  // threads for the chunked top-level loops
+
+    struct Bins {
+        Aabb box[3][NBINS];
+        int64_t cnt[3][NBINS];
+        void clear() {
+            for (int x = 0; x < 3; ++x)
+                for (int b = 0; b < NBINS; ++b) {
+                    cnt[x][b] = 0;
+                    for (int a = 0; a < 3; ++a) { box[x][b].lo[a] = INFINITY; box[x][b].hi[a] = -INFINITY; }
+                }
+        }
+    };
+
     void build(int32_t node_id, int64_t lo, int64_t hi) {
         TmpNode &node = nodes[node_id];
         int64_t m = hi - lo;
+        const int parts = m >= (1 << 18) ? std::min<int>(top_threads, (int)(m >> 16)) : 1;
         Aabb bb, cb;
         for (int a = 0; a < 3; ++a) { bb.lo[a] = cb.lo[a] = INFINITY; bb.hi[a] = cb.hi[a] = -INFINITY; }
-        for (int64_t i = lo; i < hi; ++i) {
-            const Aabb &b = boxes[ids[i]];
-            for (int a = 0; a < 3; ++a) {
-                bb.lo[a] = std::min(bb.lo[a], b.lo[a]);
-                bb.hi[a] = std::max(bb.hi[a], b.hi[a]);
-                double c = 0.5 * (b.lo[a] + b.hi[a]);
-                cb.lo[a] = std::min(cb.lo[a], c);
-                cb.hi[a] = std::max(cb.hi[a], c);
-            }
+        {
+            std::vector<Aabb> pbb(parts, bb), pcb(parts, cb);
+            chunked(lo, hi, parts, [&](int tid, int64_t a0, int64_t a1) {
+                Aabb tb = pbb[tid], tc = pcb[tid];
+                for (int64_t i = a0; i < a1; ++i) {
+                    const Aabb &b = boxes[ids[i]];
+                    for (int a = 0; a < 3; ++a) {
+                        tb.lo[a] = std::min(tb.lo[a], b.lo[a]);
+                        tb.hi[a] = std::max(tb.hi[a], b.hi[a]);
+                        double c = 0.5 * (b.lo[a] + b.hi[a]);
+                        tc.lo[a] = std::min(tc.lo[a], c);
+                        tc.hi[a] = std::max(tc.hi[a], c);
+                    }
+                }
+                pbb[tid] = tb; pcb[tid] = tc;
+            });
+            for (int t = 0; t < parts; ++t)
+                for (int a = 0; a < 3; ++a) {
+                    bb.lo[a] = std::min(bb.lo[a], pbb[t].lo[a]); bb.hi[a] = std::max(bb.hi[a], pbb[t].hi[a]);
+                    cb.lo[a] = std::min(cb.lo[a], pcb[t].lo[a]); cb.hi[a] = std::max(cb.hi[a], pcb[t].hi[a]);
+                }
         }
         node.box = bb;
         if (m == 1) { make_leaf(node, lo, hi); return; }
 
-        // best binned split over the three axes
+        // bin all three axes in one pass (per-thread bins for the huge ranges, merged afterwards)
+        double scale3[3];
+        bool axis_ok[3];
+        for (int x = 0; x < 3; ++x) {
+            double ext = cb.hi[x] - cb.lo[x];
+            axis_ok[x] = ext > 0;
+            scale3[x] = axis_ok[x] ? NBINS / ext : 0.0;
+        }
+        std::vector<Bins> pbins(parts);
+        chunked(lo, hi, parts, [&](int tid, int64_t a0, int64_t a1) {
+            Bins &B = pbins[tid];
+            B.clear();
+            for (int64_t i = a0; i < a1; ++i) {
+                const Aabb &b = boxes[ids[i]];
+                for (int x = 0; x < 3; ++x) {
+                    if (!axis_ok[x]) continue;
+                    int k = (int)((0.5 * (b.lo[x] + b.hi[x]) - cb.lo[x]) * scale3[x]);
+                    k = std::min(std::max(k, 0), NBINS - 1);
+                    B.cnt[x][k]++;
+                    for (int a = 0; a < 3; ++a) {
+                        B.box[x][k].lo[a] = std::min(B.box[x][k].lo[a], b.lo[a]);
+                        B.box[x][k].hi[a] = std::max(B.box[x][k].hi[a], b.hi[a]);
+                    }
+                }
+            }
+        });
+        Bins &bins = pbins[0];
+        for (int t = 1; t < parts; ++t)
+            for (int x = 0; x < 3; ++x)
+                for (int b = 0; b < NBINS; ++b) {
+                    bins.cnt[x][b] += pbins[t].cnt[x][b];
+                    for (int a = 0; a < 3; ++a) {
+                        bins.box[x][b].lo[a] = std::min(bins.box[x][b].lo[a], pbins[t].box[x][b].lo[a]);
+                        bins.box[x][b].hi[a] = std::max(bins.box[x][b].hi[a], pbins[t].box[x][b].hi[a]);
+                    }
+                }
+
+        // best split over the three axes
         double best_cost = INFINITY;
         int best_axis = -1, best_bin = -1;
         double parent_area = half_area(bb.lo, bb.hi);
         for (int axis = 0; axis < 3; ++axis) {
-            double ext = cb.hi[axis] - cb.lo[axis];
-            if (!(ext > 0)) continue;
-            double scale = NBINS / ext;
-            Aabb bin_box[NBINS];
-            int64_t bin_cnt[NBINS];
-            for (int b = 0; b < NBINS; ++b) {
-                bin_cnt[b] = 0;
-                for (int a = 0; a < 3; ++a) { bin_box[b].lo[a] = INFINITY; bin_box[b].hi[a] = -INFINITY; }
-            }
-            for (int64_t i = lo; i < hi; ++i) {
-                const Aabb &b = boxes[ids[i]];
-                int k = (int)((0.5 * (b.lo[axis] + b.hi[axis]) - cb.lo[axis]) * scale);
-                k = std::min(std::max(k, 0), NBINS - 1);
-                bin_cnt[k]++;
-                for (int a = 0; a < 3; ++a) {
-                    bin_box[k].lo[a] = std::min(bin_box[k].lo[a], b.lo[a]);
-                    bin_box[k].hi[a] = std::max(bin_box[k].hi[a], b.hi[a]);
-                }
-            }
+            if (!axis_ok[axis]) continue;
+            const Aabb *bin_box = bins.box[axis];
+            const int64_t *bin_cnt = bins.cnt[axis];
             double right_area[NBINS];
             int64_t right_cnt[NBINS];
             Aabb acc;
@@ -206,13 +268,36 @@ struct SahBuilder {
             if (m <= max_leaf && leaf_cost <= split_cost) { make_leaf(node, lo, hi); return; }
             double ext = cb.hi[best_axis] - cb.lo[best_axis];
             double scale = NBINS / ext;
-            int32_t *p = std::partition(ids + lo, ids + hi, [&](int32_t id) {
+            auto goes_left = [&](int32_t id) {
                 const Aabb &b = boxes[id];
                 int k = (int)((0.5 * (b.lo[best_axis] + b.hi[best_axis]) - cb.lo[best_axis]) * scale);
                 k = std::min(std::max(k, 0), NBINS - 1);
                 return k <= best_bin;
-            });
-            mid = p - ids;
+            };
+            if (parts > 1) {
+                // chunk-wise counting partition through a scratch copy (which side a primitive lands on is all that
+                // matters; the order inside a side only permutes leaf slots)
+                std::vector<int64_t> nleft(parts + 1, 0);
+                chunked(lo, hi, parts, [&](int tid, int64_t a0, int64_t a1) {
+                    int64_t c = 0;
+                    for (int64_t i = a0; i < a1; ++i) c += goes_left(ids[i]) ? 1 : 0;
+                    nleft[tid + 1] = c;
+                });
+                for (int t = 0; t < parts; ++t) nleft[t + 1] += nleft[t];
+                const int64_t total_left = nleft[parts];
+                std::vector<int32_t> scratch(ids + lo, ids + hi);
+                chunked(lo, hi, parts, [&](int tid, int64_t a0, int64_t a1) {
+                    int64_t l = lo + nleft[tid], r = lo + total_left + (a0 - lo) - nleft[tid];
+                    for (int64_t i = a0; i < a1; ++i) {
+                        const int32_t id = scratch[i - lo];
+                        if (goes_left(id)) ids[l++] = id; else ids[r++] = id;
+                    }
+                });
+                mid = lo + total_left;
+            } else {
+                int32_t *p = std::partition(ids + lo, ids + hi, goes_left);
+                mid = p - ids;
+            }
         }
         if (mid <= lo || mid >= hi) {
             // all centroids coincide (or binning failed): leaf if allowed, otherwise split the range in half
@@ -397,6 +482,7 @@ void build_fast_tree(const Aabb *boxes, int64_t n, int max_leaf, float pad, int 
     out.leaf_prims.assign((size_t)std::max<int64_t>(n, 0), 0);
     for (int64_t i = 0; i < n; ++i) out.leaf_prims[i] = (int32_t)i;
     SahBuilder b(boxes, out.leaf_prims.data(), n, std::max(1, max_leaf), threads);
+    b.top_threads = std::max(1, threads);
     int32_t root = b.alloc();
     if (n > 0) b.build(root, 0, n);
     Flattener f{b.nodes, out.nodes, pad};

@@ -176,14 +176,15 @@ int host_build(const TakeSceneDesc *d, int threads, HostBuild &hb) {
     hb.abs_max = abs_max;
     RefTree &ref = hb.ref;
     FastTree &fast = hb.fast;
-    double t0 = now_ms();
-    build_reference_tree(boxes.data(), n, threads, ref);
-    double t1 = now_ms();
+    // the two trees are independent: build them side by side (the reference-order tree is bound by its serial
+    // top-level std::sort calls, which must stay libstdc++'s to reproduce the reference's tie order)
     const int max_leaf = std::min(8, std::max(1, env_int("TAKE_BVH_MAX_LEAF", 4)));
+    double t0 = now_ms(), t_ref = 0;
+    std::thread ref_thread([&] { build_reference_tree(boxes.data(), n, threads, ref); t_ref = now_ms() - t0; });
     build_fast_tree(boxes.data(), n, max_leaf, 0.0f, threads, fast);
-    double t2 = now_ms();
-    hb.ms_ref = t1 - t0;
-    hb.ms_fast = t2 - t1;
+    hb.ms_fast = now_ms() - t0;
+    ref_thread.join();
+    hb.ms_ref = t_ref;
     if (fast.depth > TAKE_STACK_SMEM + TAKE_STACK_LOCAL)
         return fail(TAKE_E_INVALID, "acceleration tree too deep (" + std::to_string(fast.depth) + ")");
 
