@@ -7,7 +7,7 @@ def child():
     from take_b200 import api, scenes
     integ = os.environ.get("TUNE_INTEGRATOR", "one_sample_mis")
     spp = int(os.environ.get("TUNE_SPP", "16"))
-    flat = scenes.heightfield().flat()
+    flat = scenes.build(os.environ.get("TUNE_SCENE", "heightfield")).flat()
     gs = api.GpuScene(flat)
     best = None
     for rep in range(4):
