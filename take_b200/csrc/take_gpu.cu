@@ -381,6 +381,9 @@ void fill_wave_ptrs(TakeScene *s, Wave &w, const TakeRenderOpts *o, int set = 0)
     w.integrator = o->integrator;
     w.max_depth = o->max_depth;
     w.sort_enabled = (o->flags & TAKE_RENDER_NO_SORT) ? 0 : 1;
+    const int n_pick = s->dev.env_light ? s->dev.pick_count : s->dev.num_lights;
+    w.sort_branch = (w.sort_enabled && o->integrator == TAKE_INTEGRATOR_ONE_SAMPLE_MIS && n_pick > 0 &&
+                     !env_int("TAKE_NO_SORT_BRANCH", 0)) ? 1 : 0;
     w.seed = o->seed;
     // explicit sample lists (take_gpu_radiance_samples) and the v2 traversal keep the separate generate kernel
     w.fused_primary = (s->traversal == 1 && !env_int("TAKE_NO_FUSE", 0)) ? 1 : 0;

@@ -18,6 +18,12 @@ namespace take {
 #define TAKE_STACK_SMEM 24   // entries per thread kept in shared memory
 #endif
 #define TAKE_STACK_LOCAL (96 - TAKE_STACK_SMEM)  // overflow entries in local memory (tree depth limit = 96, checked on the host)
+#ifndef TAKE_PIN_SBASE
+#define TAKE_PIN_SBASE 1
+#endif
+#ifndef TAKE_PUSH_ALWAYS
+#define TAKE_PUSH_ALWAYS 0
+#endif
 #define TAKE_STACK_SMEM_ALLOC (TAKE_STACK_SMEM > 0 ? TAKE_STACK_SMEM : 1)
 
 // 256-bit read-only loads (sm_100: LDG.E.256).  The traversal kernels are bound by L1 wavefront throughput -- every
@@ -145,24 +151,60 @@ __device__ inline void trace_exact(const DevScene &sc, D3 o, D3 d, double tmin, 
 }
 
 // ---- fast mode ------------------------------------------------------------------------------------------
+// Per-thread traversal stack of (node, entry distance) pairs.  The first TAKE_STACK_SMEM levels live in shared memory
+// (column layout entry[level][thread]: one 64-bit access per lane, conflict-free), deeper levels in a local-memory
+// array owned by the kernel.  The struct itself holds only scalars -- the shared-window address of the column, the
+// overflow pointer and the depth -- so that after inlining all of it stays in registers (an earlier version embedded
+// the overflow array, which pinned every field, `sp` included, in local memory: ~25 instructions and three dependent
+// local loads per push).
+#define TAKE_TRACE_BLOCK 128  // threads per block of every traversal kernel
 struct TravStack {
-    int32_t *s_node;  // shared-memory column base (this thread), element stride = blockDim.x
-    float *s_tn;
-    int stride;
-    int32_t l_node[TAKE_STACK_LOCAL];
-    float l_tn[TAKE_STACK_LOCAL];
+    uint32_t sbase;  // shared-window byte address of entry[0][this thread]
+    uint2 *l;        // overflow levels (local memory)
     int sp;
-    __device__ __forceinline__ void push(int32_t node, float tn) {
-        if (sp < TAKE_STACK_SMEM) { s_node[sp * stride] = node; s_tn[sp * stride] = tn; }
-        else { l_node[sp - TAKE_STACK_SMEM] = node; l_tn[sp - TAKE_STACK_SMEM] = tn; }
+    __device__ __forceinline__ void init(uint2 *smem_block, uint2 *local_levels) {
+        sbase = (uint32_t)__cvta_generic_to_shared(smem_block + threadIdx.x);
+        l = local_levels;
+        sp = 0;
+#if TAKE_PIN_SBASE
+        asm volatile("" : "+r"(sbase));  // opaque: keeps the address in a register instead of re-deriving it (S2R) per push
+#endif
+    }
+    // Store at the top without moving it (callers bump `sp` by a predicate: a branch-free conditional push; the slot
+    // above the top may hold garbage, which is never read).
+    __device__ __forceinline__ void put_bits(int32_t node, uint32_t tn_bits) {
+        if (sp < TAKE_STACK_SMEM)
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(sbase + (uint32_t)sp * (TAKE_TRACE_BLOCK * 8u)), "r"(node), "r"(tn_bits) : "memory");
+        else
+            l[sp - TAKE_STACK_SMEM] = make_uint2((uint32_t)node, tn_bits);
+    }
+    __device__ __forceinline__ void push_bits(int32_t node, uint32_t tn_bits) {
+        if (sp < TAKE_STACK_SMEM)
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(sbase + (uint32_t)sp * (TAKE_TRACE_BLOCK * 8u)), "r"(node), "r"(tn_bits) : "memory");
+        else
+            l[sp - TAKE_STACK_SMEM] = make_uint2((uint32_t)node, tn_bits);
         ++sp;
     }
+    __device__ __forceinline__ void push(int32_t node, float tn) { push_bits(node, __float_as_uint(tn)); }
     __device__ __forceinline__ void pop(int32_t &node, float &tn) {
         --sp;
-        if (sp < TAKE_STACK_SMEM) { node = s_node[sp * stride]; tn = s_tn[sp * stride]; }
-        else { node = l_node[sp - TAKE_STACK_SMEM]; tn = l_tn[sp - TAKE_STACK_SMEM]; }
+        uint32_t a, b;
+        if (sp < TAKE_STACK_SMEM) {
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(sbase + (uint32_t)sp * (TAKE_TRACE_BLOCK * 8u)) : "memory");
+        } else {
+            const uint2 e = l[sp - TAKE_STACK_SMEM];
+            a = e.x; b = e.y;
+        }
+        node = (int32_t)a;
+        tn = __uint_as_float(b);
     }
 };
+// Declares the storage of a traversal stack inside a kernel of TAKE_TRACE_BLOCK threads and initialises `st`.
+#define TAKE_DECLARE_STACK(st)                                                  \
+    __shared__ uint2 st##_smem[TAKE_STACK_SMEM_ALLOC * TAKE_TRACE_BLOCK];       \
+    uint2 st##_local[TAKE_STACK_LOCAL + 1];                                      \
+    TravStack st;                                                               \
+    st.init(st##_smem, st##_local)
 
 // Reciprocal direction for the FMA slab form  t = plane * idir - (o -+ delta) * idir.  An infinite idir (zero direction
 // component) would turn that into inf - inf = NaN for exactly the slabs that contain the origin; clamping |idir| to
@@ -172,6 +214,8 @@ struct TravStack {
 __device__ __forceinline__ float safe_rcp(float d) { return fminf(fmaxf(1.0f / d, -1e18f), 1e18f); }
 
 #define TAKE_SLACK 1.00000191f  // 1 + 2^-19: relative slack on the exit distance (error analysis in DESIGN.md)
+
+#define TAKE_NODE_DONE ((int32_t)0x80000000)  // "no node left" (never a valid leaf link: ~0x7fffffff is the empty-child code)
 
 struct TravCounters {
     unsigned long long box, tri;
@@ -330,10 +374,17 @@ __device__ __forceinline__ void trace_fast4(const DevScene &sc, D3 o, D3 d, doub
 #undef TAKE_WIDE_CHILD
             // sort the four keys ascending: misses (0xffffffff) sink to the end, hits come out near-to-far
             cswap(key[0], key[1]); cswap(key[2], key[3]); cswap(key[0], key[2]); cswap(key[1], key[3]); cswap(key[1], key[2]);
-#define TAKE_WIDE_PICK(KEY) (((KEY) & 3u) == 0u ? ch.x : ((KEY) & 3u) == 1u ? ch.y : ((KEY) & 3u) == 2u ? ch.z : ch.w)
-            if (key[3] != 0xffffffffu) st.push(TAKE_WIDE_PICK(key[3]), __uint_as_float(key[3] & 0xfffffffcu));
-            if (key[2] != 0xffffffffu) st.push(TAKE_WIDE_PICK(key[2]), __uint_as_float(key[2] & 0xfffffffcu));
-            if (key[1] != 0xffffffffu) st.push(TAKE_WIDE_PICK(key[1]), __uint_as_float(key[1] & 0xfffffffcu));
+            // child link of the slot in a key's low two bits: three selects, no branches
+#define TAKE_WIDE_PICK(KEY) (((KEY) & 2u) ? (((KEY) & 1u) ? ch.w : ch.z) : (((KEY) & 1u) ? ch.y : ch.x))
+#if TAKE_PUSH_ALWAYS
+            st.put_bits(TAKE_WIDE_PICK(key[3]), key[3] & 0xfffffffcu); st.sp += (key[3] != 0xffffffffu);
+            st.put_bits(TAKE_WIDE_PICK(key[2]), key[2] & 0xfffffffcu); st.sp += (key[2] != 0xffffffffu);
+            st.put_bits(TAKE_WIDE_PICK(key[1]), key[1] & 0xfffffffcu); st.sp += (key[1] != 0xffffffffu);
+#else
+            if (key[3] != 0xffffffffu) st.push_bits(TAKE_WIDE_PICK(key[3]), key[3] & 0xfffffffcu);
+            if (key[2] != 0xffffffffu) st.push_bits(TAKE_WIDE_PICK(key[2]), key[2] & 0xfffffffcu);
+            if (key[1] != 0xffffffffu) st.push_bits(TAKE_WIDE_PICK(key[1]), key[1] & 0xfffffffcu);
+#endif
             if (key[0] != 0xffffffffu) {
                 node = TAKE_WIDE_PICK(key[0]);
             } else {
@@ -383,11 +434,140 @@ __device__ __forceinline__ void trace_fast4(const DevScene &sc, D3 o, D3 d, doub
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Speculative 4-wide traversal (warp-cooperative schedule, same results as trace_fast4).
+//
+// trace_fast4 alternates "descend until MY ray holds a leaf" and "test MY leaf": a lane that reaches its leaf early
+// idles until the slowest lane of the warp gets there, and the long FP64 leaf test then runs for whichever lanes
+// happen to hold one.  Here a lane that reaches a leaf *postpones* it and keeps descending from its stack while any
+// other lane of the warp is still searching (__any_sync); the leaf phase starts only when every lane holds a leaf or
+// has run dry, so the FP64 tests execute with as many lanes as possible.  Speculated visits use the not-yet-shrunk
+// best distance, so they may test a few more boxes than trace_fast4 -- never fewer -- and the closest hit and the
+// tie rule are order-independent, so the result is identical.
+// Must be entered by all lanes of `__activemask()` together (the kernels call it under `if (valid)`).
+// ---------------------------------------------------------------------------------------------------------
+template <bool ANY_HIT, bool COUNT>
+__device__ __forceinline__ void trace_spec4(const DevScene &sc, D3 o, D3 d, double tmin, double tmax, TravStack &st,
+                                            HitOut &out, TravCounters *cnt) {
+    const unsigned wmask = __activemask();
+    out.prim = -1; out.rank = -1; out.t = 0; out.u = 0; out.v = 0;
+    const float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
+    const float idx = safe_rcp((float)d.x), idy = safe_rcp((float)d.y), idz = safe_rcp((float)d.z);
+    const float delta = 1.9073486e-6f * fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fmaxf(fabsf(oz), sc.abs_max));  // 2^-19
+    const float olx = -(ox + delta) * idx, ohx = -(ox - delta) * idx;
+    const float oly = -(oy + delta) * idy, ohy = -(oy - delta) * idy;
+    const float olz = -(oz + delta) * idz, ohz = -(oz - delta) * idz;
+    const float tmin_f = __double2float_rd(tmin);
+    float tbest_f = __double2float_ru(tmax);
+    double best_t = tmax;
+
+    st.sp = 0;
+    int32_t node = sc.num_prims > 0 ? 0 : TAKE_NODE_DONE;
+    int32_t leaf = 0;  // postponed leaf link (< 0), or 0 = none
+#define TAKE_SPEC_POP()                                                      \
+    {                                                                         \
+        node = TAKE_NODE_DONE;                                                \
+        while (st.sp > 0) {                                                   \
+            int32_t nn; float tn;                                             \
+            st.pop(nn, tn);                                                   \
+            if (tn <= tbest_f * TAKE_SLACK) { node = nn; break; }             \
+        }                                                                     \
+    }
+    while (__any_sync(wmask, node != TAKE_NODE_DONE)) {
+        // ---- node phase: runs while some lane has neither a leaf nor an empty stack ----
+        for (;;) {
+            if (node >= 0) {
+                const float4 *N = sc.wide_nodes + 8 * (int64_t)node;
+                const F8 nx = ldg_f8(N), ny = ldg_f8(N + 2), nz = ldg_f8(N + 4);
+                const float4 lox = nx.a, hix = nx.b, loy = ny.a, hiy = ny.b, loz = nz.a, hiz = nz.b;
+                const int4 ch = __ldg((const int4 *)(N + 6));
+                if (COUNT) cnt->box += 4;
+                uint32_t key[4];
+#define TAKE_WIDE_CHILD(K, LX, HX, LY, HY, LZ, HZ, C)                                            \
+                {                                                                                  \
+                    float a = fmaf(LX, idx, olx), b = fmaf(HX, idx, ohx);                          \
+                    float tn = fminf(a, b), tf = fmaxf(a, b);                                      \
+                    a = fmaf(LY, idy, oly); b = fmaf(HY, idy, ohy);                                \
+                    tn = fmaxf(tn, fminf(a, b)); tf = fminf(tf, fmaxf(a, b));                      \
+                    a = fmaf(LZ, idz, olz); b = fmaf(HZ, idz, ohz);                                \
+                    tn = fmaxf(tn, fminf(a, b)); tf = fminf(tf, fmaxf(a, b));                      \
+                    tn = fmaxf(tn, tmin_f); tf = fminf(tf, tbest_f);                               \
+                    const bool h = (tn <= tf * TAKE_SLACK) && (C != TAKE_WIDE_EMPTY);              \
+                    key[K] = h ? ((__float_as_uint(tn) & 0xfffffffcu) | (uint32_t)K) : 0xffffffffu; \
+                }
+                TAKE_WIDE_CHILD(0, lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x, ch.x)
+                TAKE_WIDE_CHILD(1, lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, ch.y)
+                TAKE_WIDE_CHILD(2, lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, ch.z)
+                TAKE_WIDE_CHILD(3, lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, ch.w)
+#undef TAKE_WIDE_CHILD
+                cswap(key[0], key[1]); cswap(key[2], key[3]); cswap(key[0], key[2]); cswap(key[1], key[3]); cswap(key[1], key[2]);
+#define TAKE_WIDE_PICK(KEY) (((KEY) & 2u) ? (((KEY) & 1u) ? ch.w : ch.z) : (((KEY) & 1u) ? ch.y : ch.x))
+                if (key[3] != 0xffffffffu) st.push_bits(TAKE_WIDE_PICK(key[3]), key[3] & 0xfffffffcu);
+                if (key[2] != 0xffffffffu) st.push_bits(TAKE_WIDE_PICK(key[2]), key[2] & 0xfffffffcu);
+                if (key[1] != 0xffffffffu) st.push_bits(TAKE_WIDE_PICK(key[1]), key[1] & 0xfffffffcu);
+                if (key[0] != 0xffffffffu) node = TAKE_WIDE_PICK(key[0]);
+                else TAKE_SPEC_POP()
+#undef TAKE_WIDE_PICK
+            }
+            if (node < 0 && node != TAKE_NODE_DONE && leaf == 0) {  // first leaf: postpone it, keep going
+                leaf = node;
+                TAKE_SPEC_POP()
+            }
+            // a lane is still searching if it holds no leaf yet and has nodes left
+            if (!__any_sync(wmask, leaf == 0 && node != TAKE_NODE_DONE)) break;
+        }
+        // ---- leaf phase: the postponed leaf, then any further leaves that are next on this lane's stack ----
+        while (leaf < 0) {
+            const int32_t code = ~leaf;
+            const int64_t first = code >> 3;
+            const int count = (code & 7) + 1;
+            leaf = 0;
+            for (int k = 0; k < count; ++k) {
+                const double2 *T = sc.tris + 6 * (first + k);
+                const D4 t01 = ldg_d4(T), t23 = ldg_d4(T + 2), t45 = ldg_d4(T + 4);
+                const double2 a0 = t01.a, a1 = t01.b, a2 = t23.a, a3 = t23.b, a4 = t45.a, a5 = t45.b;
+                if (COUNT) cnt->tri += 1;
+                double t, bu = 0, bv = 0;
+                bool ok;
+                if (a5.y == 0.0)
+                    ok = hit_triangle(mk3(a0.x, a0.y, a1.x), mk3(a2.x, a2.y, a3.x), mk3(a4.x, a4.y, a5.x), o, d, tmin, best_t, t,
+                                      bu, bv);
+                else
+                    ok = hit_sphere(mk3(a0.x, a0.y, a1.x), a3.y, o, d, tmin, best_t, t);
+                if (ok) {
+                    const long long bits = __double_as_longlong(a1.y);
+                    const int32_t prim = (int32_t)(bits & 0xffffffffLL), rank = (int32_t)(bits >> 32);
+                    if (t < best_t || out.prim < 0 || rank > out.rank) {
+                        out.prim = prim; out.rank = rank; out.t = t; out.u = bu; out.v = bv;
+                        best_t = t;
+                        tbest_f = __double2float_ru(t);
+                        if (ANY_HIT) { node = TAKE_NODE_DONE; st.sp = 0; k = count; }
+                    }
+                }
+            }
+            if (node < 0 && node != TAKE_NODE_DONE) {
+                leaf = node;
+                TAKE_SPEC_POP()
+            }
+        }
+        // the hit may have shrunk the window below the entry distance of the inner node picked speculatively
+        // (harmless: its boxes are re-tested against the new window when it is visited)
+    }
+#undef TAKE_SPEC_POP
+}
+
+#ifndef TAKE_SPECULATE
+#define TAKE_SPECULATE 0
+#endif
+
 // Dispatch on the tree width chosen at scene creation.
 template <bool ANY_HIT, bool COUNT, bool WIDE>
 __device__ __forceinline__ void trace_any(const DevScene &sc, D3 o, D3 d, double tmin, double tmax, TravStack &st, HitOut &out,
                                           TravCounters *cnt) {
-    if (WIDE) trace_fast4<ANY_HIT, COUNT>(sc, o, d, tmin, tmax, st, out, cnt);
+    if (WIDE) {
+        if (TAKE_SPECULATE) trace_spec4<ANY_HIT, COUNT>(sc, o, d, tmin, tmax, st, out, cnt);
+        else trace_fast4<ANY_HIT, COUNT>(sc, o, d, tmin, tmax, st, out, cnt);
+    }
     else trace_fast<ANY_HIT, COUNT>(sc, o, d, tmin, tmax, st, out, cnt);
 }
 
@@ -407,7 +587,6 @@ __device__ __forceinline__ void trace_any(const DevScene &sc, D3 o, D3 d, double
 // Results are identical to trace_fast (same boxes, same leaf test, same tie rule) -- only the schedule differs.
 // `IO` supplies  bool load(i, lane state...)  and  void retire(mask, done, ...)  (see the kernels in wavefront.cuh).
 // ---------------------------------------------------------------------------------------------------------
-#define TAKE_NODE_DONE ((int32_t)0x80000000)
 #ifndef TAKE_REFILL_MIN
 #define TAKE_REFILL_MIN 8
 #endif

@@ -18,7 +18,7 @@ struct RayRec {  // 64 B : the extend ray of the slot (tmin is always c_EPSILON)
 };
 struct HitRec {  // 32 B
     int32_t prim;
-    uint32_t keyrank;  // sort key (4 bits) | rank inside the key's bin (28 bits)
+    uint32_t keyrank;  // sort key (TAKE_KEY_BITS) | rank inside the key's bin (the remaining low bits)
     double t, u, v;
 };
 struct PathRec {  // 64 B
@@ -39,7 +39,17 @@ static_assert(sizeof(RayRec) == 64 && sizeof(HitRec) == 32 && sizeof(PathRec) ==
 
 enum { PEND_PRIMARY = 0, PEND_BSDF = 1, PEND_LIGHT = 2, PEND_SPECULAR = 4, PEND_ENV = 8 };
 
-#define TAKE_NBINS 16      // sort bins: 0 = miss, 1 + material type
+// Shading sort key: 0 = miss, else (1 + material type) | (branch << 4).  `branch` is the one-sample-MIS integrator's
+// light-or-BSDF coin of the vertex about to be shaded (path_tracing.h:187): the coin is the next draw of the sample's
+// counter-based stream, so the kernel that emits the ray can look at it ahead of time (RayRec.aux0) and the sort makes
+// warps uniform in it as well as in the material -- without it half of every warp idles through the other branch.
+#define TAKE_KEY_BITS 5
+#define TAKE_RANK_BITS (32 - TAKE_KEY_BITS)
+#define TAKE_RANK_MASK ((1u << TAKE_RANK_BITS) - 1u)
+#define TAKE_NBINS (1 << TAKE_KEY_BITS)
+__device__ __forceinline__ uint32_t sort_key(int32_t prim, const uint8_t *prim_mtype, int32_t branch) {
+    return prim < 0 ? 0u : ((1u + (uint32_t)prim_mtype[prim]) | ((uint32_t)branch << 4));
+}
 #define TAKE_MAX_PASSES 80
 
 struct PassCounters {  // one per pass, zeroed once per wave
@@ -48,9 +58,9 @@ struct PassCounters {  // one per pass, zeroed once per wave
     uint32_t fetch_extend;      // persistent-kernel work cursors
     uint32_t fetch_shadow;
     uint32_t bins[TAKE_NBINS];  // histogram of sort keys
-    uint32_t pad[12];
+    uint32_t pad[28];
 };
-static_assert(sizeof(PassCounters) == 128, "PassCounters");
+static_assert(sizeof(PassCounters) == 256 && TAKE_NBINS == 32, "PassCounters");
 
 struct Totals {  // running totals over a render call
     unsigned long long samples, extend_rays, shadow_rays, shaded, box_tests, tri_tests, miss_after_light_sample;
@@ -75,6 +85,7 @@ struct Wave {
     const int32_t *list_pixel;  // optional explicit (pixel, sample) list (take_gpu_radiance_samples)
     const int64_t *list_sample;
     int32_t integrator, max_depth, sort_enabled;
+    int32_t sort_branch;    // 1: the sort key carries the one-sample integrator's light/BSDF coin (RayRec.aux0)
     int32_t fused_primary;  // 1: no k_generate -- pass 0 of extend and shade compute the camera ray themselves
     int32_t tile_w;  // > 0: image width, pixels are enumerated in 8x4 tiles (one warp = one tile); 0: row-major
     uint64_t seed;
@@ -120,13 +131,16 @@ __device__ __forceinline__ void queue_push(bool want, int32_t *queue, uint32_t *
 #endif
 
 // Camera ray of a slot: src/render.cpp:69-75 (jittered pinhole; first draw -> x, second -> y).  Consumes 2 draws.
-__device__ __forceinline__ void primary_ray(const DevScene &sc, const Wave &w, int slot, D3 &o, D3 &dir) {
+// The coin the one-sample integrator will flip first at the vertex this stream reaches next: draw number rng.k.
+__device__ __forceinline__ int32_t peek_branch(Rng rng) { return rng.next() <= 0.5 ? 1 : 0; }
+
+__device__ __forceinline__ void primary_ray(const DevScene &sc, const Wave &w, int slot, D3 &o, D3 &dir, Rng &rng) {
     uint32_t pixel;
     uint64_t sample;
     slot_identity(w, slot, pixel, sample);
     const int col = (int)(pixel % (uint32_t)sc.width), row = (int)(pixel / (uint32_t)sc.width);
     const int x = col, y = sc.height - 1 - row;  // the reference's y-up loop variable; image row = H - y - 1
-    Rng rng = {w.seed, sample, pixel, 0};
+    rng.seed = w.seed; rng.sample = sample; rng.pixel = pixel; rng.k = 0;
     const double jx = rng.next();
     const double jy = rng.next();
     dir = sub(add(mul(mul(sc.cam_u, (x + jx) / sc.width - 0.5), sc.viewport_w),
@@ -134,6 +148,10 @@ __device__ __forceinline__ void primary_ray(const DevScene &sc, const Wave &w, i
               sc.cam_w);
     dir = normalize(dir);
     o = sc.lookfrom;
+}
+__device__ __forceinline__ void primary_ray(const DevScene &sc, const Wave &w, int slot, D3 &o, D3 &dir) {
+    Rng rng;
+    primary_ray(sc, w, slot, o, dir, rng);
 }
 
 // Length of pass `pass`'s extend queue.  With fused primaries pass 0 has no queue: entry i is slot i.
@@ -147,12 +165,14 @@ __global__ void k_generate(DevScene sc, Wave w) {
     if (slot == 0) w.pass[0].n_extend = (uint32_t)w.n_slots;
     if (slot >= w.n_slots) return;
     D3 org, dir;
-    primary_ray(sc, w, slot, org, dir);
+    Rng rng;
+    primary_ray(sc, w, slot, org, dir, rng);
     RayRec r;
     r.ox = org.x; r.oy = org.y; r.oz = org.z;
     r.dx = dir.x; r.dy = dir.y; r.dz = dir.z;
     r.tmax = INFINITY;
-    r.aux0 = r.aux1 = 0;
+    r.aux0 = w.sort_branch ? peek_branch(rng) : 0;
+    r.aux1 = 0;
     w.ray[slot] = r;
     PathRec p;
     p.thr[0] = p.thr[1] = p.thr[2] = 1.0;
@@ -168,12 +188,7 @@ __global__ void k_generate(DevScene sc, Wave w) {
 // ---- extend: closest hit for every queued ray + histogram of the shading sort key ------------------------
 template <bool COUNT, bool WIDE>
 __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_extend(DevScene sc, Wave w, int pass) {
-    __shared__ int32_t s_node[TAKE_STACK_SMEM_ALLOC * 128];
-    __shared__ float s_tn[TAKE_STACK_SMEM_ALLOC * 128];
-    TravStack st;
-    st.s_node = s_node + threadIdx.x;
-    st.s_tn = s_tn + threadIdx.x;
-    st.stride = 128;
+    TAKE_DECLARE_STACK(st);
     PassCounters &pc = w.pass[pass];
     const uint32_t n = pass_count(w, pass);
     const bool primary = pass == 0 && w.fused_primary;
@@ -193,16 +208,20 @@ __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_extend(DevScene sc,
         if (valid) {
             D3 o, d;
             double tmax = INFINITY;
+            int32_t branch = 0;
             if (primary) {
                 slot = (int)i;
-                primary_ray(sc, w, slot, o, d);
+                Rng rng;
+                primary_ray(sc, w, slot, o, d, rng);
+                if (w.sort_branch) branch = peek_branch(rng);
             } else {
                 slot = queue[i];
                 const RayRec r = w.ray[slot];
                 o = mk3(r.ox, r.oy, r.oz); d = mk3(r.dx, r.dy, r.dz); tmax = r.tmax;
+                branch = r.aux0;
             }
             trace_any<false, COUNT, WIDE>(sc, o, d, TAKE_EPS, tmax, st, h, &cnt);
-            key = h.prim < 0 ? 0u : 1u + (uint32_t)sc.prim_mtype[h.prim];
+            key = sort_key(h.prim, sc.prim_mtype, branch);
         }
         // warp-aggregated histogram: lanes with the same key elect a leader that bumps the bin once
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
@@ -215,7 +234,7 @@ __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_extend(DevScene sc,
             const uint32_t rank = rbase + __popc(peers & ((1u << lane) - 1u));
             HitRec hr;
             hr.prim = h.prim;
-            hr.keyrank = (key << 28) | rank;
+            hr.keyrank = (key << TAKE_RANK_BITS) | rank;
             hr.t = h.t; hr.u = h.u; hr.v = h.v;
             w.hit[slot] = hr;
         }
@@ -241,7 +260,7 @@ __global__ void k_scatter(Wave w, int pass) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int slot = primary ? (int)i : queue[i];
         const uint32_t kr = w.hit[slot].keyrank;
-        w.q_sorted[offs[kr >> 28] + (kr & 0x0fffffffu)] = slot;
+        w.q_sorted[offs[kr >> TAKE_RANK_BITS] + (kr & TAKE_RANK_MASK)] = slot;
     }
 }
 
@@ -593,7 +612,9 @@ __global__ void __launch_bounds__(128, TAKE_SHADE_MIN_BLOCKS) k_shade(DevScene s
                     r.ox = c.org.x; r.oy = c.org.y; r.oz = c.org.z;
                     r.dx = c.ext_dir.x; r.dy = c.ext_dir.y; r.dz = c.ext_dir.z;
                     r.tmax = INFINITY;
-                    r.aux0 = r.aux1 = 0;
+                    // the coin of the vertex this ray will reach is the stream's next draw (see TAKE_KEY_BITS)
+                    r.aux0 = (INTEGRATOR == TAKE_INTEGRATOR_ONE_SAMPLE_MIS && w.sort_branch && emit_extend) ? peek_branch(c.rng) : 0;
+                    r.aux1 = 0;
                     w.ray[slot] = r;
                 }
                 if (emit_extend) {
@@ -622,12 +643,7 @@ __global__ void __launch_bounds__(128, TAKE_SHADE_MIN_BLOCKS) k_shade(DevScene s
 // ---- shadow-connect: any-hit query; unoccluded connections add throughput * C1 (path_tracing.h:53-60) ----------
 template <bool COUNT, bool WIDE>
 __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_shadow(DevScene sc, Wave w, int pass) {
-    __shared__ int32_t s_node[TAKE_STACK_SMEM_ALLOC * 128];
-    __shared__ float s_tn[TAKE_STACK_SMEM_ALLOC * 128];
-    TravStack st;
-    st.s_node = s_node + threadIdx.x;
-    st.s_tn = s_tn + threadIdx.x;
-    st.stride = 128;
+    TAKE_DECLARE_STACK(st);
     PassCounters &pc = w.pass[pass];
     const uint32_t n = pc.n_shadow;
     const int lane = threadIdx.x & 31;
@@ -701,12 +717,7 @@ __global__ void k_gather_radiance(Wave w, double *out, int n_passes) {
 template <bool ANY_HIT, bool WIDE>
 __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_intersect_fast(DevScene sc, const TakeRay *rays, int64_t n, TakeHit *hits, uint8_t *occ,
                                                         uint32_t *fetch) {
-    __shared__ int32_t s_node[TAKE_STACK_SMEM_ALLOC * 128];
-    __shared__ float s_tn[TAKE_STACK_SMEM_ALLOC * 128];
-    TravStack st;
-    st.s_node = s_node + threadIdx.x;
-    st.s_tn = s_tn + threadIdx.x;
-    st.stride = 128;
+    TAKE_DECLARE_STACK(st);
     const int lane = threadIdx.x & 31;
     for (;;) {
         uint32_t base = 0;
@@ -743,13 +754,14 @@ struct ExtendIO {
     __device__ __forceinline__ void load(uint32_t i, const DevScene &sc, LaneRay &r) {
         slot = queue[i];
         const RayRec *rr = w.ray + slot;
+        branch = rr->aux0;
         lane_ray_setup(r, sc, &rr->ox, &rr->dx, TAKE_EPS, rr->tmax);
     }
     // called by the whole warp; `mask` = lanes that retire a ray now
     __device__ __forceinline__ void retire(unsigned mask, bool done, uint32_t, const HitOut &h) {
         if (!done) return;
         const int lane = threadIdx.x & 31;
-        const uint32_t key = h.prim < 0 ? 0u : 1u + (uint32_t)w_mtype[h.prim];
+        const uint32_t key = sort_key(h.prim, w_mtype, branch);
         const unsigned peers = __match_any_sync(mask, key);
         const int leader = __ffs(peers) - 1;
         uint32_t rbase = 0;
@@ -757,23 +769,19 @@ struct ExtendIO {
         rbase = __shfl_sync(peers, rbase, leader);
         HitRec hr;
         hr.prim = h.prim;
-        hr.keyrank = (key << 28) | (rbase + __popc(peers & ((1u << lane) - 1u)));
+        hr.keyrank = (key << TAKE_RANK_BITS) | (rbase + __popc(peers & ((1u << lane) - 1u)));
         hr.t = h.t; hr.u = h.u; hr.v = h.v;
         w.hit[slot] = hr;
     }
     const uint8_t *w_mtype;
+    int32_t branch;
 };
 
 template <bool COUNT>
 __global__ void __launch_bounds__(128, TAKE_EXTEND_MIN_BLOCKS) k_extend2(DevScene sc, Wave w, int pass) {
-    __shared__ int32_t s_node[TAKE_STACK_SMEM_ALLOC * 128];
-    __shared__ float s_tn[TAKE_STACK_SMEM_ALLOC * 128];
-    TravStack st;
-    st.s_node = s_node + threadIdx.x;
-    st.s_tn = s_tn + threadIdx.x;
-    st.stride = 128;
+    TAKE_DECLARE_STACK(st);
     PassCounters &pc = w.pass[pass];
-    ExtendIO io = {w, pc, w.q_extend[pass & 1], -1, sc.prim_mtype};
+    ExtendIO io = {w, pc, w.q_extend[pass & 1], -1, sc.prim_mtype, 0};
     TravCounters cnt = {0, 0};
     trace_warp_persistent<false, COUNT>(sc, io, pc.n_extend, &pc.fetch_extend, st, &cnt);
     if (COUNT) {
@@ -801,12 +809,7 @@ struct ShadowIO {
 
 template <bool COUNT>
 __global__ void __launch_bounds__(128, TAKE_EXTEND_MIN_BLOCKS) k_shadow2(DevScene sc, Wave w, int pass) {
-    __shared__ int32_t s_node[TAKE_STACK_SMEM_ALLOC * 128];
-    __shared__ float s_tn[TAKE_STACK_SMEM_ALLOC * 128];
-    TravStack st;
-    st.s_node = s_node + threadIdx.x;
-    st.s_tn = s_tn + threadIdx.x;
-    st.stride = 128;
+    TAKE_DECLARE_STACK(st);
     PassCounters &pc = w.pass[pass];
     ShadowIO io = {w, -1};
     TravCounters cnt = {0, 0};
@@ -841,12 +844,7 @@ struct ApiIO {
 template <bool ANY_HIT>
 __global__ void __launch_bounds__(128, TAKE_EXTEND_MIN_BLOCKS) k_intersect_fast2(DevScene sc, const TakeRay *rays, int64_t n, TakeHit *hits, uint8_t *occ,
                                                          uint32_t *fetch) {
-    __shared__ int32_t s_node[TAKE_STACK_SMEM_ALLOC * 128];
-    __shared__ float s_tn[TAKE_STACK_SMEM_ALLOC * 128];
-    TravStack st;
-    st.s_node = s_node + threadIdx.x;
-    st.s_tn = s_tn + threadIdx.x;
-    st.stride = 128;
+    TAKE_DECLARE_STACK(st);
     ApiIO<ANY_HIT> io = {rays, hits, occ};
     trace_warp_persistent<ANY_HIT, false>(sc, io, (uint32_t)n, fetch, st, nullptr);
 }
