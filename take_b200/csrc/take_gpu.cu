@@ -68,7 +68,7 @@ struct TakeScene {
     std::vector<DeviceBuffer *> tex_data;
     // wave storage
     struct WaveBuffers {
-        DeviceBuffer ray, hit, path, pend, shadow, q0, q1, q_sorted, q_shadow, pass;
+        DeviceBuffer ray, hit, hit_sorted, path, pend, shadow, q0, q1, q_shadow, pass;
     } wb[2];  // two waves in flight: set i is driven by streams[i]
     DeviceBuffer totals, scratch_a, scratch_b, scratch_c, fetch;
     cudaStream_t stream2 = nullptr;       // second wave stream (stream is the first and the API's stream)
@@ -224,12 +224,12 @@ int ensure_wave(TakeScene *s, int64_t capacity, int sets) {
         TakeScene::WaveBuffers &b = s->wb[i];
         CU(b.ray.ensure(capacity * sizeof(RayRec)));
         CU(b.hit.ensure(capacity * sizeof(HitRec)));
+        CU(b.hit_sorted.ensure(capacity * sizeof(HitRec)));
         CU(b.path.ensure(capacity * sizeof(PathRec)));
         CU(b.pend.ensure(capacity * sizeof(PendRec)));
         CU(b.shadow.ensure(capacity * sizeof(ShadowRec)));
         CU(b.q0.ensure(capacity * 4));
         CU(b.q1.ensure(capacity * 4));
-        CU(b.q_sorted.ensure(capacity * 4));
         CU(b.q_shadow.ensure(capacity * 4));
         CU(b.pass.ensure(sizeof(PassCounters) * TAKE_MAX_PASSES));
     }
@@ -369,12 +369,12 @@ void fill_wave_ptrs(TakeScene *s, Wave &w, const TakeRenderOpts *o, int set = 0)
     TakeScene::WaveBuffers &b = s->wb[set];
     w.ray = b.ray.as<RayRec>();
     w.hit = b.hit.as<HitRec>();
+    w.hit_sorted = b.hit_sorted.as<HitRec>();
     w.path = b.path.as<PathRec>();
     w.pend = b.pend.as<PendRec>();
     w.shadow = b.shadow.as<ShadowRec>();
     w.q_extend[0] = b.q0.as<int32_t>();
     w.q_extend[1] = b.q1.as<int32_t>();
-    w.q_sorted = b.q_sorted.as<int32_t>();
     w.q_shadow = b.q_shadow.as<int32_t>();
     w.pass = b.pass.as<PassCounters>();
     w.totals = s->totals.as<Totals>();

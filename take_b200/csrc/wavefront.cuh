@@ -12,26 +12,26 @@
 
 namespace take {
 
-struct RayRec {  // 64 B : the extend ray of the slot (tmin is always c_EPSILON)
+struct __align__(16) RayRec {  // 64 B : the extend ray of the slot (tmin is always c_EPSILON)
     double ox, oy, oz, dx, dy, dz, tmax;
     int32_t aux0, aux1;
 };
-struct HitRec {  // 32 B
+struct __align__(16) HitRec {  // 32 B
     int32_t prim;
     uint32_t keyrank;  // sort key (TAKE_KEY_BITS) | rank inside the key's bin (the remaining low bits)
     double t, u, v;
 };
-struct PathRec {  // 64 B
+struct __align__(16) PathRec {  // 64 B
     double thr[3], rad[3];
     uint32_t k;      // random_real draws consumed so far
     int32_t depth;   // index of the next integrator loop iteration
     int32_t flags;   // PEND_* describing the extend ray in flight
     int32_t pad;
 };
-struct PendRec {  // 32 B : BSDF sample waiting for its extend ray (FG and pdf of src/integrator/path_tracing.h:70-73)
+struct __align__(16) PendRec {  // 32 B : BSDF sample waiting for its extend ray (FG and pdf of src/integrator/path_tracing.h:70-73)
     double fg[3], bpdf;
 };
-struct ShadowRec {  // 64 B : NEE connection waiting for its shadow ray (origin = RayRec.o)
+struct __align__(16) ShadowRec {  // 64 B : NEE connection waiting for its shadow ray (origin = RayRec.o)
     double dx, dy, dz, tmax, cx, cy, cz, pad;
 };
 static_assert(sizeof(RayRec) == 64 && sizeof(HitRec) == 32 && sizeof(PathRec) == 64 && sizeof(PendRec) == 32 &&
@@ -69,12 +69,12 @@ struct Totals {  // running totals over a render call
 
 struct Wave {
     RayRec *ray;
-    HitRec *hit;
+    HitRec *hit;         // by slot (written by extend)
+    HitRec *hit_sorted;  // in material order (copied by the sort, `keyrank` replaced by the slot): shade streams through it
     PathRec *path;
     PendRec *pend;
     ShadowRec *shadow;
     int32_t *q_extend[2];
-    int32_t *q_sorted;
     int32_t *q_shadow;
     PassCounters *pass;  // [TAKE_MAX_PASSES]
     Totals *totals;
@@ -185,6 +185,10 @@ __global__ void k_generate(DevScene sc, Wave w) {
     w.q_extend[0][slot] = slot;
 }
 
+#ifndef TAKE_PREFETCH_CURSOR
+#define TAKE_PREFETCH_CURSOR 1
+#endif
+
 // ---- extend: closest hit for every queued ray + histogram of the shading sort key ------------------------
 template <bool COUNT, bool WIDE>
 __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_extend(DevScene sc, Wave w, int pass) {
@@ -195,11 +199,21 @@ __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_extend(DevScene sc,
     const int32_t *queue = w.q_extend[pass & 1];
     const int lane = threadIdx.x & 31;
     TravCounters cnt = {0, 0};
+    // Work cursor: a warp reserves its NEXT batch of 32 before it starts on the current one, so the round trip of the
+    // atomic hides behind the traversal instead of stalling the warp between batches.
+    uint32_t next = 0;
+#if TAKE_PREFETCH_CURSOR
+    if (lane == 0) next = atomicAdd(&pc.fetch_extend, 32u);
+#endif
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&pc.fetch_extend, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
+#if !TAKE_PREFETCH_CURSOR
+        if (lane == 0) next = atomicAdd(&pc.fetch_extend, 32u);
+#endif
+        const uint32_t base = __shfl_sync(0xffffffffu, next, 0);
         if (base >= n) break;
+#if TAKE_PREFETCH_CURSOR
+        if (lane == 0) next = atomicAdd(&pc.fetch_extend, 32u);
+#endif
         const uint32_t i = base + lane;
         const bool valid = i < n;
         int slot = -1;
@@ -259,8 +273,10 @@ __global__ void k_scatter(Wave w, int pass) {
     const int32_t *queue = w.q_extend[pass & 1];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int slot = primary ? (int)i : queue[i];
-        const uint32_t kr = w.hit[slot].keyrank;
-        w.q_sorted[offs[kr >> TAKE_RANK_BITS] + (kr & TAKE_RANK_MASK)] = slot;
+        HitRec h = w.hit[slot];
+        const uint32_t dst = offs[h.keyrank >> TAKE_RANK_BITS] + (h.keyrank & TAKE_RANK_MASK);
+        h.keyrank = (uint32_t)slot;  // the sorted copy carries the slot in place of the key: shade needs no queue
+        w.hit_sorted[dst] = h;
     }
 }
 
@@ -311,7 +327,7 @@ __device__ __forceinline__ D3 miss_rad(const DevScene &sc, D3 d) { return ENV ? 
 // Multi-sample MIS: src/integrator/path_tracing.h:5-111.  One call = "finish iteration depth-1 with the hit that
 // just arrived, then run iteration depth up to the point where it needs rays".
 template <bool ENV>
-__device__ __forceinline__ void shade_mis(ShadeCtx &c, const RayRec &ray, const HitRec &hit, const PathRec &path) {
+__device__ __forceinline__ void shade_mis(ShadeCtx &c, const RayRec &ray, const HitRec &hit, const PathRec &path, const PendRec &pend) {
     const DevScene &sc = c.sc;
     const D3 o = mk3(ray.ox, ray.oy, ray.oz), d = mk3(ray.dx, ray.dy, ray.dz);
     Isect v;
@@ -321,7 +337,6 @@ __device__ __forceinline__ void shade_mis(ShadeCtx &c, const RayRec &ray, const 
         if (v.light != -1 && sc.lights[v.light].kind == TAKE_LIGHT_AREA)  // :14-18
             c.rad = add(c.rad, mulv(c.thr, light_intensity(sc.lights[v.light])));
     } else {
-        const PendRec pend = c.w.pend[c.slot];
         const D3 FG = mk3(pend.fg[0], pend.fg[1], pend.fg[2]);
         const double bpdf = pend.bpdf;
         const bool spec = (path.flags & PEND_SPECULAR) != 0;
@@ -403,7 +418,7 @@ __device__ __forceinline__ void shade_mis(ShadeCtx &c, const RayRec &ray, const 
 
 // No MIS: src/integrator/path_tracing.h:114-157
 template <bool ENV>
-__device__ __forceinline__ void shade_raw(ShadeCtx &c, const RayRec &ray, const HitRec &hit, const PathRec &path) {
+__device__ __forceinline__ void shade_raw(ShadeCtx &c, const RayRec &ray, const HitRec &hit, const PathRec &path, const PendRec &) {
     const DevScene &sc = c.sc;
     const D3 o = mk3(ray.ox, ray.oy, ray.oz), d = mk3(ray.dx, ray.dy, ray.dz);
     if (hit.prim < 0) {
@@ -438,7 +453,7 @@ __device__ __forceinline__ void shade_raw(ShadeCtx &c, const RayRec &ray, const 
 
 // One-sample MIS: src/integrator/path_tracing.h:161-271
 template <bool ENV>
-__device__ __forceinline__ void shade_one_sample(ShadeCtx &c, const RayRec &ray, const HitRec &hit, const PathRec &path) {
+__device__ __forceinline__ void shade_one_sample(ShadeCtx &c, const RayRec &ray, const HitRec &hit, const PathRec &path, const PendRec &pend) {
     const DevScene &sc = c.sc;
     const D3 o = mk3(ray.ox, ray.oy, ray.oz), d = mk3(ray.dx, ray.dy, ray.dz);
     const int nl = ENV ? sc.pick_count : sc.num_lights;
@@ -458,7 +473,6 @@ __device__ __forceinline__ void shade_one_sample(ShadeCtx &c, const RayRec &ray,
         }
         fill_isect(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
     } else {
-        const PendRec pend = c.w.pend[c.slot];
         const D3 FG = mk3(pend.fg[0], pend.fg[1], pend.fg[2]);
         const bool spec = (path.flags & PEND_SPECULAR) != 0;
         double pdf = (nl == 0 || spec) ? pend.bpdf : 0.5 * pend.bpdf;  // :245
@@ -539,6 +553,9 @@ __device__ __forceinline__ void shade_one_sample(ShadeCtx &c, const RayRec &ray,
     }
 }
 
+#ifndef TAKE_SHADE_EARLY
+#define TAKE_SHADE_EARLY 0   // 0: records fetched when needed, 1: ray+path right after the slot, 2: + the pending BSDF sample
+#endif
 #ifndef TAKE_SHADE_MIN_BLOCKS
 #define TAKE_SHADE_MIN_BLOCKS 1
 #endif
@@ -547,7 +564,7 @@ __global__ void __launch_bounds__(128, TAKE_SHADE_MIN_BLOCKS) k_shade(DevScene s
     PassCounters &pc = w.pass[pass];
     const uint32_t n = pass_count(w, pass);
     const bool primary = pass == 0 && w.fused_primary;
-    const int32_t *queue = w.sort_enabled ? w.q_sorted : w.q_extend[pass & 1];
+    const int32_t *queue = w.q_extend[pass & 1];  // only read when the sort is off
     int32_t *q_next = w.q_extend[(pass + 1) & 1];
     // grid-stride with whole warps, so that the queue pushes below always see converged warps
     const uint32_t n_round = (n + 31u) & ~31u;
@@ -556,8 +573,22 @@ __global__ void __launch_bounds__(128, TAKE_SHADE_MIN_BLOCKS) k_shade(DevScene s
         bool emit_extend = false, emit_shadow = false;
         int slot = -1, shaded = 0;
         if (valid) {
-            slot = (primary && !w.sort_enabled) ? (int)i : queue[i];
-            const HitRec hit = w.hit[slot];
+            const HitRec hit = w.sort_enabled ? w.hit_sorted[i] : w.hit[primary ? (int)i : queue[i]];
+            slot = w.sort_enabled ? (int)hit.keyrank : (primary ? (int)i : queue[i]);
+            // Everything that depends only on the slot is requested before the hit is looked at, so that the gathers
+            // overlap instead of forming a chain (slot -> hit -> ray -> path -> pend): the kernel is latency-bound.
+            RayRec ray;
+            PathRec path;
+            PendRec pend;
+#if TAKE_SHADE_EARLY >= 1
+            if (!primary) {
+                ray = w.ray[slot];
+                path = w.path[slot];
+#if TAKE_SHADE_EARLY >= 2
+                if (INTEGRATOR != TAKE_INTEGRATOR_RAW) pend = w.pend[slot];
+#endif
+            }
+#endif
             if (primary && !ENV && hit.prim < 0) {
                 // a camera ray that left the scene: the sample is the background colour (path_tracing.h:8); no need to
                 // recompute the ray (the environment-map build needs its direction and takes the general path)
@@ -567,8 +598,6 @@ __global__ void __launch_bounds__(128, TAKE_SHADE_MIN_BLOCKS) k_shade(DevScene s
                 p.k = 2; p.depth = 0; p.flags = 0; p.pad = 0;
                 w.path[slot] = p;
             } else {
-                RayRec ray;
-                PathRec path;
                 if (primary) {  // nothing was stored for the camera ray: recompute it (2 draws) and start the path
                     D3 o, d;
                     primary_ray(sc, w, slot, o, d);
@@ -577,10 +606,13 @@ __global__ void __launch_bounds__(128, TAKE_SHADE_MIN_BLOCKS) k_shade(DevScene s
                     path.thr[0] = path.thr[1] = path.thr[2] = 1.0;
                     path.rad[0] = path.rad[1] = path.rad[2] = 0.0;
                     path.k = 2; path.depth = 0; path.flags = PEND_PRIMARY; path.pad = 0;
-                } else {
-                    ray = w.ray[slot];
-                    path = w.path[slot];
                 }
+#if TAKE_SHADE_EARLY < 1
+                else { ray = w.ray[slot]; path = w.path[slot]; }
+#endif
+#if TAKE_SHADE_EARLY < 2
+                if (!primary && INTEGRATOR != TAKE_INTEGRATOR_RAW && (path.flags & PEND_BSDF)) pend = w.pend[slot];
+#endif
                 uint32_t pixel;
                 uint64_t sample;
                 slot_identity(w, slot, pixel, sample);
@@ -593,9 +625,9 @@ __global__ void __launch_bounds__(128, TAKE_SHADE_MIN_BLOCKS) k_shade(DevScene s
                 c.pend_flags = 0;
                 c.shaded = 0;
                 c.org = mk3(ray.ox, ray.oy, ray.oz);
-                if (INTEGRATOR == TAKE_INTEGRATOR_MIS) shade_mis<ENV>(c, ray, hit, path);
-                else if (INTEGRATOR == TAKE_INTEGRATOR_RAW) shade_raw<ENV>(c, ray, hit, path);
-                else shade_one_sample<ENV>(c, ray, hit, path);
+                if (INTEGRATOR == TAKE_INTEGRATOR_MIS) shade_mis<ENV>(c, ray, hit, path, pend);
+                else if (INTEGRATOR == TAKE_INTEGRATOR_RAW) shade_raw<ENV>(c, ray, hit, path, pend);
+                else shade_one_sample<ENV>(c, ray, hit, path, pend);
                 emit_extend = c.emit_extend;
                 emit_shadow = c.emit_shadow;
                 shaded = c.shaded;
@@ -648,11 +680,19 @@ __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_shadow(DevScene sc,
     const uint32_t n = pc.n_shadow;
     const int lane = threadIdx.x & 31;
     TravCounters cnt = {0, 0};
+    uint32_t next = 0;  // next batch reserved ahead of time (see k_extend)
+#if TAKE_PREFETCH_CURSOR
+    if (lane == 0) next = atomicAdd(&pc.fetch_shadow, 32u);
+#endif
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&pc.fetch_shadow, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
+#if !TAKE_PREFETCH_CURSOR
+        if (lane == 0) next = atomicAdd(&pc.fetch_shadow, 32u);
+#endif
+        const uint32_t base = __shfl_sync(0xffffffffu, next, 0);
         if (base >= n) break;
+#if TAKE_PREFETCH_CURSOR
+        if (lane == 0) next = atomicAdd(&pc.fetch_shadow, 32u);
+#endif
         const uint32_t i = base + lane;
         if (i < n) {
             const int slot = w.q_shadow[i];
@@ -719,11 +759,19 @@ __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_intersect_fast(DevS
                                                         uint32_t *fetch) {
     TAKE_DECLARE_STACK(st);
     const int lane = threadIdx.x & 31;
+    uint32_t next = 0;  // next batch reserved ahead of time (see k_extend)
+#if TAKE_PREFETCH_CURSOR
+    if (lane == 0) next = atomicAdd(fetch, 32u);
+#endif
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(fetch, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
+#if !TAKE_PREFETCH_CURSOR
+        if (lane == 0) next = atomicAdd(fetch, 32u);
+#endif
+        const uint32_t base = __shfl_sync(0xffffffffu, next, 0);
         if ((int64_t)base >= n) break;
+#if TAKE_PREFETCH_CURSOR
+        if (lane == 0) next = atomicAdd(fetch, 32u);
+#endif
         const int64_t i = (int64_t)base + lane;
         if (i < n) {
             const TakeRay r = rays[i];
