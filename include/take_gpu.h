@@ -212,6 +212,22 @@ int take_gpu_render_device(TakeScene *scene, const TakeRenderOpts *opts, double 
 int take_gpu_render_multi(int ndev, const int *devices, const TakeSceneDesc *desc, const TakeRenderOpts *opts, double *sum_rgb,
                           double *sumsq_rgb, TakeStats *stats);
 
+/* Output step (replaces the .exr branch of imwrite, src/image.cpp:157-175, and the tinyexr code under it).
+ * Device half: mean = sum * (1/spp) (src/render.cpp:78 via vector.h:194-197), double -> float (image.cpp:159-161),
+ * float -> half with tinyexr's float_to_half_full rounding, channel-planar B,G,R scanlines in 16-line blocks, and the
+ * ZIP pre-filter of CompressZip (byte de-interleave + delta predictor): `packed` (HOST, take_gpu_exr_packed_size
+ * bytes) receives every block exactly as the reference hands it to deflate.  `d_sum_rgb` is a DEVICE buffer in the
+ * layout take_gpu_render_device accumulates into; take_gpu_exr_pack takes the same sums from the HOST. */
+int64_t take_gpu_exr_packed_size(int32_t width, int32_t height);
+int take_gpu_exr_pack_device(TakeScene *scene, const double *d_sum_rgb, int64_t spp, uint8_t *packed);
+int take_gpu_exr_pack(TakeScene *scene, const double *sum_rgb, int64_t spp, uint8_t *packed);
+/* Host half: deflate the blocks on `threads` host threads (0 = all) and write a scanline OpenEXR file with the
+ * reference writer's attributes (HALF B,G,R, ZIP, increasing Y).  Needs no CUDA device. */
+int take_gpu_exr_write_packed(const char *path, int32_t width, int32_t height, const uint8_t *packed, int32_t threads);
+/* render() + imwrite("image.exr") in one call (src/main.cpp:21-24): the FP64 sums never leave the device, the
+ * device->host transfer is 6 bytes per pixel. */
+int take_gpu_render_to_exr(TakeScene *scene, const TakeRenderOpts *opts, const char *path, TakeStats *stats);
+
 /* Radiance of `n` individual path samples (pixel x, image row y from the top, sample index s): 3 doubles each. */
 int take_gpu_radiance_samples(TakeScene *scene, const TakeRenderOpts *opts, int64_t n, const int32_t *px,
                               const int32_t *py, const int64_t *s, double *rgb);

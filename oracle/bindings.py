@@ -128,9 +128,26 @@ class RefLib:
         L.ref_radiance_samples.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.ref_rng_selfcheck.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_int]
+        L.ref_imwrite.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p]
+        L.ref_imread3.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
 
     def load(self, xml_path) -> RefScene:
         return RefScene(self.lib, xml_path)
+
+    def imwrite(self, path, mean_rgb):
+        """The reference's own imwrite (src/image.cpp:135-175) on an (H, W, 3) image of doubles."""
+        a = np.ascontiguousarray(mean_rgb, np.float64)
+        if self.lib.ref_imwrite(os.fsencode(path), a.shape[1], a.shape[0], _ptr(a, np.float64)) != 0:
+            raise RuntimeError("reference imwrite failed: " + self.lib.ref_last_error().decode())
+
+    def imread3(self, path, cap_pixels=1 << 24):
+        """The reference's own imread3 (src/image.cpp:80-133)."""
+        w, h = C.c_int(0), C.c_int(0)
+        out = np.empty(cap_pixels * 3, np.float64)
+        rc = self.lib.ref_imread3(os.fsencode(path), C.byref(w), C.byref(h), _ptr(out, np.float64), out.size)
+        if rc != 0:
+            raise RuntimeError("reference imread3 failed: " + self.lib.ref_last_error().decode())
+        return out[: w.value * h.value * 3].reshape(h.value, w.value, 3).copy()
 
     def rng_selfcheck(self, seed, pixel, sample, n=300) -> int:
         return self.lib.ref_rng_selfcheck(seed, pixel, sample, n)
@@ -257,9 +274,17 @@ class OracleLib:
         L.oracle_philox.argtypes = [vp, vp, vp]
         L.oracle_env_sample.argtypes = [vp, C.c_double, C.c_double, vp]
         L.oracle_env_eval.argtypes = [vp, vp, vp]
+        L.oracle_exr_pack.argtypes = [i32, i32, vp, i64, vp]
 
     def load(self, flat) -> OracleScene:
         return OracleScene(self.lib, flat)
+
+    def exr_pack(self, sum_rgb, spp):
+        """CPU restatement of the output step up to the deflate input (checker for take_gpu_exr_pack*)."""
+        a = np.ascontiguousarray(sum_rgb, np.float64)
+        out = np.empty(a.shape[0] * a.shape[1] * 6, np.uint8)
+        self.lib.oracle_exr_pack(a.shape[1], a.shape[0], _ptr(a, np.float64), spp, _ptr(out, np.uint8))
+        return out
 
     def philox(self, ctr, key):
         ctr = np.ascontiguousarray(ctr, np.uint32); key = np.ascontiguousarray(key, np.uint32)

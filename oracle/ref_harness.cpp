@@ -472,4 +472,32 @@ int ref_rng_selfcheck(uint64_t seed, uint32_t pixel, uint64_t sample, int n) {
     return bad;
 }
 
+// The reference's own output step: Image3 of per-pixel means -> imwrite (src/image.cpp:135-175; ".exr" = half B,G,R ZIP
+// through the vendored tinyexr).  `mean_rgb` is height*width*3 doubles in image layout.
+int ref_imwrite(const char *path, int width, int height, const double *mean_rgb) {
+    try {
+        Image3 img(width, height);
+        for (size_t i = 0; i < img.data.size(); ++i) img.data[i] = Vector3{mean_rgb[3 * i], mean_rgb[3 * i + 1], mean_rgb[3 * i + 2]};
+        imwrite(fs::path(path), img);
+        return 0;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
+// The reference's own reader (src/image.cpp imread3): returns 0 and fills out[height*width*3]; -2 if `cap` is too small.
+int ref_imread3(const char *path, int *width, int *height, double *out, int64_t cap) {
+    try {
+        Image3 img = imread3(fs::path(path));
+        *width = img.width; *height = img.height;
+        if ((int64_t)img.data.size() * 3 > cap) return -2;
+        for (size_t i = 0; i < img.data.size(); ++i) { out[3 * i] = img.data[i].x; out[3 * i + 1] = img.data[i].y; out[3 * i + 2] = img.data[i].z; }
+        return 0;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
 }  // extern "C"

@@ -1193,4 +1193,70 @@ double oracle_stream_real(uint64_t seed, uint32_t pixel, uint64_t sample, uint32
 }
 void oracle_philox(const uint32_t *ctr, const uint32_t *key, uint32_t *out) { take_philox4x32_10(ctr, key, out); }
 
+// ---- output step (TEST CHECKER for take_gpu_exr_pack*): src/render.cpp:78, src/image.cpp:157-161 and, from the
+// reference's vendored tinyexr.h, float_to_half_full (:889-924), the B,G,R planar scanline layout of SaveEXR / EncodeChunk
+// and the pre-filter of CompressZip (:1212-1258).  out = width*height*6 bytes, block after block.
+static uint16_t exr_half(float f32) {
+    uint32_t f;
+    memcpy(&f, &f32, 4);
+    const uint32_t sign = f >> 31, e = (f >> 23) & 0xffu, m = f & 0x7fffffu;
+    uint32_t o = 0;
+    if (e == 0) {
+        o = 0;
+    } else if (e == 255) {
+        o = (31u << 10) | (m ? 0x200u : 0u);
+    } else {
+        const int ne = (int)e - 127 + 15;
+        if (ne >= 31) {
+            o = 31u << 10;
+        } else if (ne <= 0) {
+            if ((14 - ne) <= 24) {
+                const uint32_t mant = m | 0x800000u;
+                o = mant >> (14 - ne);
+                if ((mant >> (13 - ne)) & 1u) o++;
+            }
+        } else {
+            o = ((uint32_t)ne << 10) | (m >> 13);
+            if (m & 0x1000u) o++;
+        }
+    }
+    return (uint16_t)((o & 0x7fffu) | (sign << 15));
+}
+
+void oracle_exr_pack(int width, int height, const double *sum_rgb, int64_t spp, uint8_t *out) {
+    const double inv = 1.0 / (double)spp;
+    const size_t line_bytes = (size_t)width * 6;
+    std::vector<uint8_t> raw, tmp;
+    for (int y0 = 0; y0 < height; y0 += 16) {
+        const int lines = std::min(16, height - y0);
+        const size_t n = lines * line_bytes;
+        raw.assign(n, 0);
+        for (int l = 0; l < lines; ++l)
+            for (int c = 0; c < 3; ++c)  // planes B, G, R
+                for (int x = 0; x < width; ++x) {
+                    const double mean = sum_rgb[3 * ((size_t)(y0 + l) * width + x) + (2 - c)] * inv;
+                    const uint16_t h = exr_half((float)mean);
+                    uint8_t *p = raw.data() + l * line_bytes + (size_t)c * width * 2 + (size_t)x * 2;
+                    p[0] = (uint8_t)(h & 0xff); p[1] = (uint8_t)(h >> 8);
+                }
+        tmp.assign(n, 0);
+        {   // reorder
+            size_t t1 = 0, t2 = (n + 1) / 2, i = 0;
+            for (;;) {
+                if (i < n) tmp[t1++] = raw[i++]; else break;
+                if (i < n) tmp[t2++] = raw[i++]; else break;
+            }
+        }
+        {   // predictor
+            int p = tmp[0];
+            for (size_t i = 1; i < n; ++i) {
+                int d = (int)tmp[i] - p + (128 + 256);
+                p = tmp[i];
+                tmp[i] = (uint8_t)d;
+            }
+        }
+        memcpy(out + (size_t)y0 * line_bytes, tmp.data(), n);
+    }
+}
+
 }  // extern "C"

@@ -29,7 +29,8 @@ EXPORTS = [
     "take_gpu_device_count", "take_gpu_scene_create", "take_gpu_scene_destroy", "take_gpu_intersect",
     "take_gpu_occluded", "take_gpu_intersect_device", "take_gpu_render", "take_gpu_render_device",
     "take_gpu_radiance_samples", "take_gpu_render_multi", "take_gpu_scene_stream", "take_gpu_scene_info", "take_gpu_last_error",
-    "take_gpu_version",
+    "take_gpu_version", "take_gpu_exr_packed_size", "take_gpu_exr_pack_device", "take_gpu_exr_pack", "take_gpu_exr_write_packed",
+    "take_gpu_render_to_exr",
 ]
 
 RAY_DTYPE = np.dtype([("origin", "<f8", 3), ("dir", "<f8", 3), ("tmin", "<f8"), ("tmax", "<f8")])
@@ -84,6 +85,12 @@ def load_library(path: str = LIB_PATH):
     L.take_gpu_scene_stream.restype = vp
     L.take_gpu_scene_stream.argtypes = [vp]
     L.take_gpu_scene_info.argtypes = [vp, vp]
+    L.take_gpu_exr_packed_size.restype = i64
+    L.take_gpu_exr_packed_size.argtypes = [C.c_int32, C.c_int32]
+    L.take_gpu_exr_pack_device.argtypes = [vp, vp, i64, vp]
+    L.take_gpu_exr_pack.argtypes = [vp, vp, i64, vp]
+    L.take_gpu_exr_write_packed.argtypes = [C.c_char_p, C.c_int32, C.c_int32, vp, C.c_int32]
+    L.take_gpu_render_to_exr.argtypes = [vp, C.POINTER(TakeRenderOpts), C.c_char_p, C.POINTER(TakeStats)]
     _lib = L
     return L
 
@@ -175,6 +182,26 @@ class GpuScene:
         _check(self.lib.take_gpu_render_device(self.h, C.byref(o), d_sum_ptr, d_sumsq_ptr or None, C.byref(st)))
         return st.as_dict()
 
+    # the output step (imwrite .exr, src/image.cpp:157-175): device half -> filtered 16-scanline blocks of half B,G,R
+    def exr_pack(self, sum_rgb, spp: int) -> np.ndarray:
+        sum_rgb = np.ascontiguousarray(sum_rgb, np.float64)
+        assert sum_rgb.shape == (self.height, self.width, 3)
+        out = np.empty(self.lib.take_gpu_exr_packed_size(self.width, self.height), np.uint8)
+        _check(self.lib.take_gpu_exr_pack(self.h, sum_rgb.ctypes.data, spp, out.ctypes.data))
+        return out
+
+    def exr_pack_device(self, d_sum_ptr: int, spp: int) -> np.ndarray:
+        out = np.empty(self.lib.take_gpu_exr_packed_size(self.width, self.height), np.uint8)
+        _check(self.lib.take_gpu_exr_pack_device(self.h, d_sum_ptr, spp, out.ctypes.data))
+        return out
+
+    def render_to_exr(self, path, integrator="mis", max_depth=5, spp_begin=0, spp_end=1, seed=0, flags=0) -> dict:
+        """render() + imwrite("image.exr") (src/main.cpp:21-24) without bringing the FP64 sums to the host."""
+        st = TakeStats()
+        o = self._opts(integrator, max_depth, spp_begin, spp_end, seed, flags)
+        _check(self.lib.take_gpu_render_to_exr(self.h, C.byref(o), os.fsencode(path), C.byref(st)))
+        return st.as_dict()
+
     def radiance_samples(self, px, py, s, integrator="mis", max_depth=5, seed=0):
         px = np.ascontiguousarray(px, np.int32); py = np.ascontiguousarray(py, np.int32); s = np.ascontiguousarray(s, np.int64)
         out = np.empty((len(px), 3), np.float64)
@@ -234,6 +261,14 @@ WIDE_NODE_DTYPE = np.dtype([("lox", "<f4", 4), ("hix", "<f4", 4), ("loy", "<f4",
                             ("hiz", "<f4", 4), ("child", "<i4", 4), ("count", "<i4", 4)])
 WIDE_EMPTY = 0x7fffffff
 assert REF_NODE_DTYPE.itemsize == 64 and FAST_NODE_DTYPE.itemsize == 64 and WIDE_NODE_DTYPE.itemsize == 128
+
+
+def write_exr_packed(path, width: int, height: int, packed: np.ndarray, threads: int = 0) -> None:
+    """Host half of the output step: deflate the filtered blocks and write the .exr (no CUDA device needed)."""
+    packed = np.ascontiguousarray(packed, np.uint8)
+    L = load_library()
+    assert packed.size == L.take_gpu_exr_packed_size(width, height)
+    _check(L.take_gpu_exr_write_packed(os.fsencode(path), width, height, packed.ctypes.data, threads))
 
 
 def host_build(flat: FlatScene) -> dict:

@@ -14,6 +14,7 @@
 #include "../../include/take_gpu.h"
 #include "bvh_build.h"
 #include "wavefront.cuh"
+#include "exr_out.cuh"
 
 using namespace take;
 
@@ -66,6 +67,7 @@ struct TakeScene {
     DeviceBuffer nodes, wide_nodes, tris, ref_nodes, positions, normals, uvs, indices, prim_material, prim_light, dfs_rank, prim_flags,
         prim_mtype, spheres, materials, lights, textures;
     std::vector<DeviceBuffer *> tex_data;
+    DeviceBuffer exr_packed;
     // wave storage
     struct WaveBuffers {
         DeviceBuffer ray, hit, hit_sorted, path, pend, shadow, q0, q1, q_shadow, pass;
@@ -430,6 +432,7 @@ void read_totals(TakeScene *s, TakeStats *stats, const StageTimer &tm, double ms
 extern "C" {
 
 const char *take_gpu_last_error(void) { return g_error.c_str(); }
+int take_exr_fail(int code, const std::string &msg) { return fail(code, msg); }  // for exr_write.cpp
 const char *take_gpu_version(void) { return "take_b200 0.1 (sm_100a)"; }
 
 int take_gpu_device_count(int *count) {
@@ -939,6 +942,48 @@ int take_gpu_render_multi(int ndev, const int *devices, const TakeSceneDesc *d, 
     cleanup();
     if (ce != cudaSuccess) return fail(TAKE_E_CUDA, cudaGetErrorString(ce));
     return TAKE_OK;
+}
+
+// ---- output step: mean, double -> float -> half, B/G/R planes, ZIP pre-filter on the device (exr_out.cuh) -----------
+int take_gpu_exr_pack_device(TakeScene *s, const double *d_sum_rgb, int64_t spp, uint8_t *packed) {
+    if (!s || !d_sum_rgb || !packed || spp <= 0) return fail(TAKE_E_INVALID, "take_gpu_exr_pack_device: bad arguments");
+    CU(cudaSetDevice(s->device));
+    const int64_t bytes = take_gpu_exr_packed_size(s->width, s->height);
+    CU(s->exr_packed.ensure((size_t)bytes));
+    ExrGeom g;
+    g.width = s->width; g.height = s->height;
+    g.line_bytes = (int64_t)s->width * 6;
+    g.block_bytes = TAKE_EXR_BLOCK_LINES * g.line_bytes;
+    const double inv = 1.0 / (double)spp;  // vector.h:194-197: color / Real(spp) multiplies by the reciprocal
+    const int blocks = (int)std::min<int64_t>((bytes + 255) / 256, (int64_t)s->sm_count * 16);
+    k_exr_pack<<<blocks, 256, 0, s->stream>>>(g, d_sum_rgb, inv, s->exr_packed.as<uint8_t>());
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(packed, s->exr_packed.p, (size_t)bytes, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return TAKE_OK;
+}
+
+int take_gpu_exr_pack(TakeScene *s, const double *sum_rgb, int64_t spp, uint8_t *packed) {
+    if (!s || !sum_rgb) return fail(TAKE_E_INVALID, "take_gpu_exr_pack: bad arguments");
+    CU(cudaSetDevice(s->device));
+    const size_t bytes = (size_t)s->width * s->height * 3 * sizeof(double);
+    CU(s->scratch_a.ensure(bytes));
+    CU(cudaMemcpyAsync(s->scratch_a.p, sum_rgb, bytes, cudaMemcpyHostToDevice, s->stream));
+    return take_gpu_exr_pack_device(s, s->scratch_a.as<double>(), spp, packed);
+}
+
+int take_gpu_render_to_exr(TakeScene *s, const TakeRenderOpts *o, const char *path, TakeStats *stats) {
+    if (int rc = check_opts(s, o)) return rc;
+    if (!path) return fail(TAKE_E_INVALID, "null path");
+    if (o->spp_end <= o->spp_begin) return fail(TAKE_E_INVALID, "empty sample range");
+    CU(cudaSetDevice(s->device));
+    const size_t bytes = (size_t)s->width * s->height * 3 * sizeof(double);
+    CU(s->scratch_a.ensure(bytes));
+    CU(cudaMemsetAsync(s->scratch_a.p, 0, bytes, s->stream));
+    if (int rc = take_gpu_render_device(s, o, s->scratch_a.as<double>(), nullptr, stats)) return rc;
+    std::vector<uint8_t> packed((size_t)take_gpu_exr_packed_size(s->width, s->height));
+    if (int rc = take_gpu_exr_pack_device(s, s->scratch_a.as<double>(), o->spp_end - o->spp_begin, packed.data())) return rc;
+    return take_gpu_exr_write_packed(path, s->width, s->height, packed.data(), 0);
 }
 
 int take_gpu_radiance_samples(TakeScene *s, const TakeRenderOpts *o, int64_t n, const int32_t *px, const int32_t *py,

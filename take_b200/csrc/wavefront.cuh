@@ -186,7 +186,7 @@ __global__ void k_generate(DevScene sc, Wave w) {
 }
 
 #ifndef TAKE_PREFETCH_CURSOR
-#define TAKE_PREFETCH_CURSOR 1
+#define TAKE_PREFETCH_CURSOR 0   // measured: reserving the next batch early costs 2 % (worse tail balance), kept as an option
 #endif
 
 // ---- extend: closest hit for every queued ray + histogram of the shading sort key ------------------------

@@ -134,12 +134,14 @@ Image3 render(const std::vector<std::string> &params) {
     if (params.size() < 1) return Image3(0, 0);
     int max_depth = 50, device = 0, gpus = 1, integrator = TAKE_INTEGRATOR_MIS;  // render.cpp:14,76
     uint64_t seed = 0;
+    bool gpu_exr = false;  // -gpu_exr: the output step runs on the GPU too (take_gpu_render_to_exr writes ./image.exr)
     std::string filename;
     for (int i = 0; i < (int)params.size(); i++) {
         if (params[i] == "-max_depth") max_depth = std::stoi(params[++i]);
         else if (params[i] == "-device") device = std::stoi(params[++i]);
         else if (params[i] == "-gpus") gpus = std::stoi(params[++i]);
         else if (params[i] == "-seed") seed = std::stoull(params[++i]);
+        else if (params[i] == "-gpu_exr") gpu_exr = true;
         else if (params[i] == "-integrator") {
             const std::string v = params[++i];
             integrator = v == "raw" ? TAKE_INTEGRATOR_RAW : v == "one_sample_mis" ? TAKE_INTEGRATOR_ONE_SAMPLE_MIS : TAKE_INTEGRATOR_MIS;
@@ -189,6 +191,15 @@ Image3 render(const std::vector<std::string> &params) {
     std::cout << "Rendering..." << std::endl;
     tick(timer);
     TakeStats stats{};
+    if (gpu_exr) {
+        // render + `color / spp` + double->float->half + B,G,R planes + ZIP pre-filter on the device, deflate on all host
+        // threads: the FP64 sums never cross PCIe.  main.cpp:23 then calls imwrite on the image returned here, which
+        // returns at once for an empty image (src/image.cpp:136-138), so the stock main() needs no change.
+        if (take_gpu_render_to_exr(gpu, &opts, "image.exr", &stats) != TAKE_OK) Error(std::string("take_gpu: ") + take_gpu_last_error());
+        std::cout << std::endl << "Finish building rendering. Took " << tick(timer) << " seconds." << std::endl;
+        take_gpu_scene_destroy(gpu);
+        return Image3(0, 0);
+    }
     if (take_gpu_render(gpu, &opts, sum.data(), nullptr, &stats) != TAKE_OK) Error(std::string("take_gpu: ") + take_gpu_last_error());
     const Real inv = Real(1) / Real(scene.options.spp);
     for (size_t i = 0; i < img.data.size(); ++i)  // img(x, H-y-1) = color / spp (render.cpp:78); sums are already in image layout

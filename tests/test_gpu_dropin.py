@@ -53,3 +53,24 @@ def test_cli_drop_in(tmp_path, gpu_lib):
     relmse = lambda x, y: np.mean((x - y) ** 2 / (y ** 2 + 1e-2))
     assert relmse(img_gpu, img_cpu) <= 1.5 * relmse(other, mean), (relmse(img_gpu, img_cpu), relmse(other, mean))
     assert abs(img_gpu.mean() - img_cpu.mean()) <= 0.02 * img_cpu.mean()
+
+
+@pytest.mark.skipif(not os.path.exists(TAKE_GPU), reason="oracle/_ref/take_gpu not built (needs /root/reference)")
+def test_cli_gpu_output_step_writes_the_same_pixels(tmp_path, gpu_lib):
+    """-gpu_exr: image.exr written by take_gpu_render_to_exr must hold the same half values as the image.exr the
+    reference's own imwrite (tinyexr) writes from the Image3 the adapter returns without the flag."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from exr_reader import read_exr as read_halves
+    b = scenes.cornell_box(80, 52, 8, materials="mixed")
+    d1, d2 = tmp_path / "host_out", tmp_path / "gpu_out"
+    x1, x2 = b.write(str(d1)), b.write(str(d2))
+    for xml, cwd, extra in ((x1, d1, []), (x2, d2, ["-gpu_exr"])):
+        out = subprocess.run([TAKE_GPU, xml, "-max_depth", "5", "-seed", "7"] + extra, cwd=str(cwd), capture_output=True, text=True,
+                             timeout=600)
+        assert out.returncode == 0, out.stdout + out.stderr
+    a, c = read_halves(str(d1 / "image.exr")), read_halves(str(d2 / "image.exr"))
+    assert [n for n, _ in a["channels"]] == [n for n, _ in c["channels"]] == ["B", "G", "R"]
+    for ch in "BGR":
+        assert np.array_equal(a["planes"][ch], c["planes"][ch])
+    assert c["compression"] == 3
