@@ -392,6 +392,30 @@ void fill_wave_ptrs(TakeScene *s, Wave &w, const TakeRenderOpts *o, int set = 0)
     w.tile_w = (s->width % 8 == 0 && s->height % 4 == 0 && !env_int("TAKE_NO_TILES", 0)) ? s->width : 0;
 }
 
+// Keep the 4-wide tree resident in L2: the wavefront kernels stream gigabytes of per-path records through the cache
+// while every ray keeps returning to the same 36 MB (1 M triangles) of nodes.  The node array is marked "persisting"
+// on the streams that run the traversal kernels (as much of it as the device sets aside), misses are streaming.
+// Measured on B200 (tools/tune.py): k_extend gains 1-2 %, but the set-aside shrinks the L2 left for the shade and sort
+// kernels, which lose more (config 2: +3 % shade; the 10 M-triangle scene: +50 % shade) -- so it is OFF unless
+// TAKE_L2_PERSIST=1.  The evict-first hints on the record traffic of the traversal kernels (ld_stream / st_stream in
+// wavefront.cuh) get most of the benefit without taking cache away from anyone.
+void apply_l2_policy(TakeScene *s, cudaStream_t st) {
+    if (!env_int("TAKE_L2_PERSIST", 0) || !s->wide_nodes.p) return;
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, s->device) != cudaSuccess || p.persistingL2CacheMaxSize <= 0) return;
+    const size_t want = std::min<size_t>(s->wide_nodes.bytes, (size_t)p.persistingL2CacheMaxSize);
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+    cudaStreamAttrValue a;
+    memset(&a, 0, sizeof(a));
+    a.accessPolicyWindow.base_ptr = s->wide_nodes.p;
+    a.accessPolicyWindow.num_bytes = std::min<size_t>(s->wide_nodes.bytes, (size_t)p.accessPolicyMaxWindowSize);
+    a.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)a.accessPolicyWindow.num_bytes);
+    a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &a);
+    cudaGetLastError();
+}
+
 int check_opts(const TakeScene *s, const TakeRenderOpts *o) {
     if (!s || !o) return fail(TAKE_E_INVALID, "null argument");
     if (o->integrator < TAKE_INTEGRATOR_MIS || o->integrator > TAKE_INTEGRATOR_ONE_SAMPLE_MIS)
@@ -608,6 +632,7 @@ static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild &hb, 
     s->blocks_occl2 = blocks_for((const void *)k_intersect_fast2<true>);
     s->traversal = env_int("TAKE_TRAVERSAL", 1) == 2 ? 2 : 1;
     CU(s->fetch.ensure(256));
+    apply_l2_policy(s, s->stream);
     guard.ok = true;
     *out = s;
     return TAKE_OK;
@@ -765,6 +790,7 @@ int take_gpu_render_device(TakeScene *s, const TakeRenderOpts *o, double *d_sum,
     if (int rc = ensure_wave(s, capacity, sets)) return rc;
     if (sets == 2 && !s->stream2) {
         CU(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+        apply_l2_policy(s, s->stream2);
         CU(cudaEventCreateWithFlags(&s->ev_acc[0], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&s->ev_acc[1], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&s->ev_begin, cudaEventDisableTiming));

@@ -37,6 +37,37 @@ struct __align__(16) ShadowRec {  // 64 B : NEE connection waiting for its shado
 static_assert(sizeof(RayRec) == 64 && sizeof(HitRec) == 32 && sizeof(PathRec) == 64 && sizeof(PendRec) == 32 &&
                   sizeof(ShadowRec) == 64, "record sizes");
 
+// Streaming (evict-first) copies of whole records for the traversal kernels: the per-path records are touched once per
+// pass, the tree is re-read by every ray, so the records should not push the tree out of L2.
+#ifndef TAKE_STREAM_HINTS
+#define TAKE_STREAM_HINTS 1
+#endif
+template <typename T>
+__device__ __forceinline__ T ld_stream(const T *p) {
+    static_assert(sizeof(T) % 16 == 0, "records are multiples of 16 bytes");
+#if TAKE_STREAM_HINTS
+    T r;
+    const int4 *s = reinterpret_cast<const int4 *>(p);
+    int4 *d = reinterpret_cast<int4 *>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); ++i) d[i] = __ldcs(s + i);
+    return r;
+#else
+    return *p;
+#endif
+}
+template <typename T>
+__device__ __forceinline__ void st_stream(T *p, const T &v) {
+#if TAKE_STREAM_HINTS
+    const int4 *s = reinterpret_cast<const int4 *>(&v);
+    int4 *d = reinterpret_cast<int4 *>(p);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); ++i) __stcs(d + i, s[i]);
+#else
+    *p = v;
+#endif
+}
+
 enum { PEND_PRIMARY = 0, PEND_BSDF = 1, PEND_LIGHT = 2, PEND_SPECULAR = 4, PEND_ENV = 8 };
 
 // Shading sort key: 0 = miss, else (1 + material type) | (branch << 4).  `branch` is the one-sample-MIS integrator's
@@ -230,7 +261,7 @@ __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_extend(DevScene sc,
                 if (w.sort_branch) branch = peek_branch(rng);
             } else {
                 slot = queue[i];
-                const RayRec r = w.ray[slot];
+                const RayRec r = ld_stream(w.ray + slot);
                 o = mk3(r.ox, r.oy, r.oz); d = mk3(r.dx, r.dy, r.dz); tmax = r.tmax;
                 branch = r.aux0;
             }
@@ -250,7 +281,7 @@ __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_extend(DevScene sc,
             hr.prim = h.prim;
             hr.keyrank = (key << TAKE_RANK_BITS) | rank;
             hr.t = h.t; hr.u = h.u; hr.v = h.v;
-            w.hit[slot] = hr;
+            st_stream(w.hit + slot, hr);
         }
     }
     if (COUNT) {
@@ -696,8 +727,8 @@ __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_shadow(DevScene sc,
         const uint32_t i = base + lane;
         if (i < n) {
             const int slot = w.q_shadow[i];
-            const RayRec r = w.ray[slot];
-            const ShadowRec s = w.shadow[slot];
+            const RayRec r = ld_stream(w.ray + slot);
+            const ShadowRec s = ld_stream(w.shadow + slot);
             HitOut h;
             trace_any<true, COUNT, WIDE>(sc, mk3(r.ox, r.oy, r.oz), mk3(s.dx, s.dy, s.dz), TAKE_EPS, s.tmax, st, h, &cnt);
             if (h.prim < 0) {
