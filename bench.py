@@ -265,31 +265,45 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- e2e: the C-ABI call a host application makes (host buffers, D2H of the result inside the timed region) ----
-    h_sum = torch.empty((H, W, 3), dtype=torch.float64, pin_memory=True).numpy()
-    h_sq = torch.empty((H, W, 3), dtype=torch.float64, pin_memory=True).numpy()
+    # ---- e2e: the C-ABI calls a host application makes (host buffers, D2H of every step's result inside the timed region) ----
+    # take_gpu_render_async + take_gpu_render_wait with two pinned result buffers: the read-back of step k overlaps the
+    # kernels of step k+1; every step's sums are complete on the host when its wait returns, inside the timed region.
+    h_bufs = [(torch.empty((H, W, 3), dtype=torch.float64, pin_memory=True).numpy(),
+               torch.empty((H, W, 3), dtype=torch.float64, pin_memory=True).numpy()) for _ in range(2)]
     o_rays, e2e_steps = 0, max(2, min(args.steps, 6))
     import ctypes as C
-    st = api.TakeStats()
 
-    def host_step(step):
-        lo, hi = spp_range(step)
-        o = api.TakeRenderOpts(api.INTEGRATORS[INTEGRATOR], MAX_DEPTH, lo, hi, SEED, 0, 0)
-        rc = gs.lib.take_gpu_render(gs.h, C.byref(o), h_sum.ctypes.data, h_sq.ctypes.data, C.byref(st))
-        assert rc == 0, gs.lib.take_gpu_last_error()
-        return st.extend_rays + st.shadow_rays
+    def host_steps(n):
+        rays, tickets = 0, []
+        for step in range(n + 1):
+            if step < n:
+                lo, hi = spp_range(step)
+                tickets.append(gs.render_async(h_bufs[step & 1][0], h_bufs[step & 1][1], INTEGRATOR, MAX_DEPTH, lo, hi, seed=SEED))
+            if step >= 1:
+                st_ = gs.render_wait(tickets[step - 1])
+                rays += st_["extend_rays"] + st_["shadow_rays"]
+        return rays
 
-    host_step(0)
+    host_steps(2)                      # both result slots allocated and warm
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        o_rays += host_step(i)
+    o_rays = host_steps(e2e_steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    # the blocking call, for comparison (copy not overlapped)
+    st = api.TakeStats()
+    o = api.TakeRenderOpts(api.INTEGRATORS[INTEGRATOR], MAX_DEPTH, 0, S, SEED, 0, 0)
+    gs.lib.take_gpu_render(gs.h, C.byref(o), h_bufs[0][0].ctypes.data, h_bufs[0][1].ctypes.data, C.byref(st))
+    t1 = time.perf_counter()
+    rc = gs.lib.take_gpu_render(gs.h, C.byref(o), h_bufs[0][0].ctypes.data, h_bufs[0][1].ctypes.data, C.byref(st))
+    assert rc == 0, gs.lib.take_gpu_last_error()
+    blocking_s = time.perf_counter() - t1
     e2e = {"value": o_rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": C.sizeof(api.TakeRenderOpts),
-           "d2h_bytes_per_step": int(h_sum.nbytes + h_sq.nbytes), "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-           "note": "take_gpu_render(): camera rays are generated on the device (replaces render.cpp:69-75), so the per-step "
-                   "host input is the options struct; the scene is uploaded once by take_gpu_scene_create "
+           "d2h_bytes_per_step": int(h_bufs[0][0].nbytes + h_bufs[0][1].nbytes), "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+           "api": "take_gpu_render_async + take_gpu_render_wait, two pinned host buffers",
+           "blocking_call_mrays_per_s": (st.extend_rays + st.shadow_rays) / blocking_s / 1e6,
+           "note": "camera rays are generated on the device (replaces render.cpp:69-75), so the per-step host input is the "
+                   "options struct; the scene is uploaded once by take_gpu_scene_create "
                    f"({scene_create_ms:.0f} ms incl. host BVH builds)"}
 
     # ---- roofline of the dominant kernel (k_extend): events inside the library on the launching stream -----------
@@ -339,7 +353,7 @@ def run_ours(args):
         "samples_per_s": samples_all / (ms * 1e-3),
         "config": {"workload": WORKLOAD, "integrator": INTEGRATOR, "max_depth": MAX_DEPTH, "resolution": [W, H],
                    "triangles": flat.num_prims, "spp_per_step_per_gpu": S, "parallelism": f"spp-range x{world}, scene replicated",
-                   "l2": "inputs larger than L2: each wave streams 16.6 M path records (272 B/slot, 4.5 GB) besides 130 MB of tree + leaf records (L2 is 126 MB); no explicit flush",
+                   "l2": "inputs larger than L2: each wave streams up to 33.5 M path records (300 B/slot, 10 GB) besides 130 MB of tree + leaf records (L2 is 126 MB); no explicit flush",
                    "bvh": {"nodes": int(info["fast_nodes"]), "depth": int(info["fast_tree_depth"]),
                            "build_ms": info["build_ms_fast_tree"] + info["build_ms_reference_tree"]}},
         "e2e": e2e, "gpu_launches": int(launches_all), "clocks": clock_info, "roofline": roofline, "cpu_baseline": base,
@@ -354,10 +368,10 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--spp-per-step", type=int, default=16)
+    ap.add_argument("--spp-per-step", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

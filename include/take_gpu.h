@@ -203,6 +203,16 @@ int take_gpu_render(TakeScene *scene, const TakeRenderOpts *opts, double *sum_rg
 int take_gpu_render_device(TakeScene *scene, const TakeRenderOpts *opts, double *d_sum_rgb, double *d_sumsq_rgb,
                            TakeStats *stats);
 
+/* Asynchronous take_gpu_render: queues the render and the device->host copies of its results and returns a ticket;
+ * take_gpu_render_wait blocks until the host buffers of that ticket are complete and fills `stats`.  Up to TWO tickets
+ * may be in flight per scene, and they complete in order: the copy of call k then overlaps the kernels of call k+1
+ * (a host that consumes per-range results -- progressive display, checkpoints, the bench's per-step read-back -- hides
+ * the PCIe transfer completely).  The host buffers must stay valid until the wait returns and should be page-locked
+ * (cudaHostAlloc / cudaHostRegister); with pageable memory the call still works but the copy is staged synchronously.
+ * TAKE_RENDER_STAGE_TIMES is not available here (it serialises the kernels). */
+int take_gpu_render_async(TakeScene *scene, const TakeRenderOpts *opts, double *sum_rgb, double *sumsq_rgb, int64_t *ticket);
+int take_gpu_render_wait(TakeScene *scene, int64_t ticket, TakeStats *stats);
+
 /* Single-process multi-GPU render (what parallel_for over tiles, src/parallel.cpp:183-237, becomes across GPUs): the
  * host-side acceleration structures are built once, the scene is replicated on devices[0..ndev), device i renders a
  * contiguous share of the sample-index range [spp_begin, spp_end) of every pixel, and the partial sums are combined on

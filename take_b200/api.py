@@ -30,7 +30,7 @@ EXPORTS = [
     "take_gpu_occluded", "take_gpu_intersect_device", "take_gpu_render", "take_gpu_render_device",
     "take_gpu_radiance_samples", "take_gpu_render_multi", "take_gpu_scene_stream", "take_gpu_scene_info", "take_gpu_last_error",
     "take_gpu_version", "take_gpu_exr_packed_size", "take_gpu_exr_pack_device", "take_gpu_exr_pack", "take_gpu_exr_write_packed",
-    "take_gpu_render_to_exr",
+    "take_gpu_render_to_exr", "take_gpu_render_async", "take_gpu_render_wait",
 ]
 
 RAY_DTYPE = np.dtype([("origin", "<f8", 3), ("dir", "<f8", 3), ("tmin", "<f8"), ("tmax", "<f8")])
@@ -85,6 +85,8 @@ def load_library(path: str = LIB_PATH):
     L.take_gpu_scene_stream.restype = vp
     L.take_gpu_scene_stream.argtypes = [vp]
     L.take_gpu_scene_info.argtypes = [vp, vp]
+    L.take_gpu_render_async.argtypes = [vp, C.POINTER(TakeRenderOpts), vp, vp, C.POINTER(i64)]
+    L.take_gpu_render_wait.argtypes = [vp, i64, C.POINTER(TakeStats)]
     L.take_gpu_exr_packed_size.restype = i64
     L.take_gpu_exr_packed_size.argtypes = [C.c_int32, C.c_int32]
     L.take_gpu_exr_pack_device.argtypes = [vp, vp, i64, vp]
@@ -173,6 +175,20 @@ class GpuScene:
         o = self._opts(integrator, max_depth, spp_begin, spp_end, seed, flags)
         _check(self.lib.take_gpu_render(self.h, C.byref(o), s.ctypes.data, s2.ctypes.data if sumsq else None, C.byref(st)))
         return s, s2, st.as_dict()
+
+    def render_async(self, sum_out: np.ndarray, sumsq_out, integrator="mis", max_depth=5, spp_begin=0, spp_end=1, seed=0, flags=0) -> int:
+        """Queue a render into caller-owned (ideally page-locked) host arrays; returns the ticket for render_wait()."""
+        assert sum_out.dtype == np.float64 and sum_out.flags["C_CONTIGUOUS"] and sum_out.size == self.height * self.width * 3
+        t = C.c_int64(-1)
+        o = self._opts(integrator, max_depth, spp_begin, spp_end, seed, flags)
+        _check(self.lib.take_gpu_render_async(self.h, C.byref(o), sum_out.ctypes.data,
+                                              sumsq_out.ctypes.data if sumsq_out is not None else None, C.byref(t)))
+        return t.value
+
+    def render_wait(self, ticket: int) -> dict:
+        st = TakeStats()
+        _check(self.lib.take_gpu_render_wait(self.h, ticket, C.byref(st)))
+        return st.as_dict()
 
     def render_sums_device(self, d_sum_ptr: int, d_sumsq_ptr: int, integrator="mis", max_depth=5, spp_begin=0, spp_end=1,
                            seed=0, flags=0):

@@ -74,11 +74,22 @@ struct TakeScene {
     } wb[2];  // two waves in flight: set i is driven by streams[i]
     DeviceBuffer totals, scratch_a, scratch_b, scratch_c, fetch;
     cudaStream_t stream2 = nullptr;       // second wave stream (stream is the first and the API's stream)
+    // take_gpu_render_async: two result slots, filled by a copy stream behind the render streams
+    struct AsyncSlot {
+        DeviceBuffer sum, sq, totals;
+        cudaEvent_t e0 = nullptr, e1 = nullptr, done = nullptr;
+        int64_t launches = 0, waves = 0, ticket = -1;
+        bool busy = false;
+        take::Totals *h_totals = nullptr;
+    } async_slot[2];
+    cudaStream_t copy_stream = nullptr;
+    int64_t next_ticket = 0;
     cudaEvent_t ev_acc[2] = {nullptr, nullptr}, ev_begin = nullptr;
     int64_t wave_capacity = 0;
     int wave_sets = 0;
     int blocks_extend = 0, blocks_shadow = 0, blocks_isect = 0, blocks_occl = 0;
-    int blocks_extend2 = 0, blocks_shadow2 = 0, blocks_isect2 = 0, blocks_occl2 = 0;
+    int blocks_extend2 = 0, blocks_shadow2 = 0, blocks_isect2 = 0, blocks_occl2 = 0, blocks_extend2w = 0, blocks_shadow2w = 0;
+    int persist_from_pass = 1, persist_shadow = 0;
     bool wide = true;   // 4-wide nodes (TAKE_BVH_WIDTH=4, default) or binary nodes (TAKE_BVH_WIDTH=2)
     int traversal = 1;  // 1: one ray per thread to completion (default, measured faster); 2: warp-persistent while-while
                         // with dynamic re-fetch (TAKE_TRAVERSAL=2)
@@ -91,6 +102,13 @@ struct TakeScene {
         for (auto *b : tex_data) delete b;
         for (auto e : ev_acc) if (e) cudaEventDestroy(e);
         if (ev_begin) cudaEventDestroy(ev_begin);
+        for (auto &a : async_slot) {
+            if (a.e0) cudaEventDestroy(a.e0);
+            if (a.e1) cudaEventDestroy(a.e1);
+            if (a.done) cudaEventDestroy(a.done);
+            if (a.h_totals) cudaFreeHost(a.h_totals);
+        }
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         if (stream2) cudaStreamDestroy(stream2);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -310,8 +328,12 @@ int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, d
         tm.cur_pass = b;
         tm.begin(ST_EXTEND);
         if (s->traversal == 2) {
-            if (count) k_extend2<true><<<s->blocks_extend2, 128, 0, st>>>(s->dev, w, b);
-            else k_extend2<false><<<s->blocks_extend2, 128, 0, st>>>(s->dev, w, b);
+            if (count) k_extend2<true, false><<<s->blocks_extend2, 128, 0, st>>>(s->dev, w, b);
+            else k_extend2<false, false><<<s->blocks_extend2, 128, 0, st>>>(s->dev, w, b);
+        } else if (s->traversal == 3 && s->wide && b >= s->persist_from_pass) {
+            // hybrid: bounce passes (rays of very different lengths) on the warp-persistent kernel with lane refill
+            if (count) k_extend2<true, true><<<s->blocks_extend2w, 128, 0, st>>>(s->dev, w, b);
+            else k_extend2<false, true><<<s->blocks_extend2w, 128, 0, st>>>(s->dev, w, b);
         } else {
             if (s->wide) {
                 if (count) k_extend<true, true><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
@@ -340,8 +362,11 @@ int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, d
         if (o->integrator == TAKE_INTEGRATOR_MIS && b <= o->max_depth) {
             tm.begin(ST_SHADOW);
             if (s->traversal == 2) {
-                if (count) k_shadow2<true><<<s->blocks_shadow2, 128, 0, st>>>(s->dev, w, b);
-                else k_shadow2<false><<<s->blocks_shadow2, 128, 0, st>>>(s->dev, w, b);
+                if (count) k_shadow2<true, false><<<s->blocks_shadow2, 128, 0, st>>>(s->dev, w, b);
+                else k_shadow2<false, false><<<s->blocks_shadow2, 128, 0, st>>>(s->dev, w, b);
+            } else if (s->traversal == 3 && s->wide && s->persist_shadow) {
+                if (count) k_shadow2<true, true><<<s->blocks_shadow2w, 128, 0, st>>>(s->dev, w, b);
+                else k_shadow2<false, true><<<s->blocks_shadow2w, 128, 0, st>>>(s->dev, w, b);
             } else {
                 if (s->wide) {
                     if (count) k_shadow<true, true><<<s->blocks_shadow, 128, 0, st>>>(s->dev, w, b);
@@ -388,7 +413,7 @@ void fill_wave_ptrs(TakeScene *s, Wave &w, const TakeRenderOpts *o, int set = 0)
                      !env_int("TAKE_NO_SORT_BRANCH", 0)) ? 1 : 0;
     w.seed = o->seed;
     // explicit sample lists (take_gpu_radiance_samples) and the v2 traversal keep the separate generate kernel
-    w.fused_primary = (s->traversal == 1 && !env_int("TAKE_NO_FUSE", 0)) ? 1 : 0;
+    w.fused_primary = (s->traversal != 2 && !env_int("TAKE_NO_FUSE", 0)) ? 1 : 0;
     w.tile_w = (s->width % 8 == 0 && s->height % 4 == 0 && !env_int("TAKE_NO_TILES", 0)) ? s->width : 0;
 }
 
@@ -426,10 +451,8 @@ int check_opts(const TakeScene *s, const TakeRenderOpts *o) {
     return TAKE_OK;
 }
 
-void read_totals(TakeScene *s, TakeStats *stats, const StageTimer &tm, double ms_total, int64_t launches, int64_t waves) {
+void fill_stats(const Totals &t, TakeStats *stats, const StageTimer &tm, double ms_total, int64_t launches, int64_t waves) {
     if (!stats) return;
-    Totals t;
-    cudaMemcpy(&t, s->totals.p, sizeof(t), cudaMemcpyDeviceToHost);
     memset(stats, 0, sizeof(*stats));
     stats->samples = (int64_t)t.samples;
     stats->extend_rays = (int64_t)t.extend_rays;
@@ -449,6 +472,13 @@ void read_totals(TakeScene *s, TakeStats *stats, const StageTimer &tm, double ms
     stats->ms_shadow = tm.ms[ST_SHADOW];
     stats->ms_sort = tm.ms[ST_SORT];
     stats->ms_other = tm.ms[ST_OTHER];
+}
+
+void read_totals(TakeScene *s, TakeStats *stats, const StageTimer &tm, double ms_total, int64_t launches, int64_t waves) {
+    if (!stats) return;
+    Totals t;
+    cudaMemcpy(&t, s->totals.p, sizeof(t), cudaMemcpyDeviceToHost);
+    fill_stats(t, stats, tm, ms_total, launches, waves);
 }
 
 }  // namespace
@@ -626,11 +656,19 @@ static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild &hb, 
         s->blocks_isect = blocks_for((const void *)k_intersect_fast<false, false>);
         s->blocks_occl = blocks_for((const void *)k_intersect_fast<true, false>);
     }
-    s->blocks_extend2 = blocks_for((const void *)k_extend2<false>);
-    s->blocks_shadow2 = blocks_for((const void *)k_shadow2<false>);
+    s->blocks_extend2 = blocks_for((const void *)k_extend2<false, false>);
+    s->blocks_shadow2 = blocks_for((const void *)k_shadow2<false, false>);
+    s->blocks_extend2w = blocks_for((const void *)k_extend2<false, true>);
+    s->blocks_shadow2w = blocks_for((const void *)k_shadow2<false, true>);
     s->blocks_isect2 = blocks_for((const void *)k_intersect_fast2<false>);
     s->blocks_occl2 = blocks_for((const void *)k_intersect_fast2<true>);
-    s->traversal = env_int("TAKE_TRAVERSAL", 1) == 2 ? 2 : 1;
+    {   // 1: one ray per thread to completion; 2: warp-persistent with lane refill (binary tree, all passes);
+        // 3: hybrid -- pass 0 as in 1 (fused camera rays), passes >= TAKE_PERSIST_FROM as in 2 on the 4-wide tree
+        const int t = env_int("TAKE_TRAVERSAL", 1);
+        s->traversal = (t == 2 || t == 3) ? t : 1;
+        s->persist_from_pass = std::max(1, env_int("TAKE_PERSIST_FROM", 1));
+        s->persist_shadow = env_int("TAKE_PERSIST_SHADOW", 0);
+    }
     CU(s->fetch.ensure(256));
     apply_l2_policy(s, s->stream);
     guard.ok = true;
@@ -768,16 +806,17 @@ int take_gpu_occluded(TakeScene *s, const TakeRay *rays, int64_t n, uint8_t *occ
     return TAKE_OK;
 }
 
-int take_gpu_render_device(TakeScene *s, const TakeRenderOpts *o, double *d_sum, double *d_sumsq, TakeStats *stats) {
-    if (int rc = check_opts(s, o)) return rc;
-    if (!d_sum) return fail(TAKE_E_INVALID, "null output buffer");
-    CU(cudaSetDevice(s->device));
+}  // extern "C"
+
+namespace {
+// Queue one render call on the scene's streams: everything up to (and including) an event `e1` on s->stream that
+// orders all of its work.  No host synchronisation; `d_totals` receives the counters.
+int render_enqueue(TakeScene *s, const TakeRenderOpts *o, double *d_sum, double *d_sumsq, Totals *d_totals, StageTimer &tm,
+                   cudaEvent_t e0, cudaEvent_t e1, int64_t &launches, int64_t &waves) {
     const int64_t npix = (int64_t)s->width * s->height;
     const int64_t spp = o->spp_end - o->spp_begin;
-    const int64_t cap_env = std::max<int64_t>(1024, (int64_t)env_int("TAKE_WAVE_SLOTS", 1 << 24));
+    const int64_t cap_env = std::max<int64_t>(1024, (int64_t)env_int("TAKE_WAVE_SLOTS", 1 << 25));
     const int64_t capacity = std::min<int64_t>(cap_env, std::max<int64_t>(npix * std::max<int64_t>(spp, 1), 1024));
-    StageTimer tm;
-    tm.on = stats && ((o->flags & TAKE_RENDER_STAGE_TIMES) || env_int("TAKE_STAGE_TIMES", 0));
     tm.stream = s->stream;
     const bool count = (o->flags & TAKE_RENDER_COUNT_TESTS) || env_int("TAKE_COUNT_TESTS", 0) != 0;
     // Two waves in flight on two streams: the thin late passes of one wave (few, long rays) overlap the fat early passes
@@ -796,19 +835,17 @@ int take_gpu_render_device(TakeScene *s, const TakeRenderOpts *o, double *d_sum,
         CU(cudaEventCreateWithFlags(&s->ev_begin, cudaEventDisableTiming));
     }
     cudaStream_t streams[2] = {s->stream, sets == 2 ? s->stream2 : s->stream};
-    CU(cudaMemsetAsync(s->totals.p, 0, sizeof(Totals), s->stream));
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
+    CU(cudaMemsetAsync(d_totals, 0, sizeof(Totals), s->stream));
     CU(cudaEventRecord(e0, s->stream));
     if (sets == 2) {  // the second stream starts after everything already queued on the first (output buffers, totals)
         CU(cudaEventRecord(s->ev_begin, s->stream));
         CU(cudaStreamWaitEvent(s->stream2, s->ev_begin, 0));
     }
-    int64_t launches = 0, waves = 0;
+    launches = 0; waves = 0;
     Wave w[2];
     fill_wave_ptrs(s, w[0], o, 0);
     if (sets == 2) fill_wave_ptrs(s, w[1], o, 1);
+    w[0].totals = w[1].totals = d_totals;
     cudaEvent_t prev_acc = nullptr;
     for (int64_t base = 0; base < npix; base += chunk_pixels) {
         const int64_t cp = std::min(chunk_pixels, npix - base);
@@ -831,14 +868,89 @@ int take_gpu_render_device(TakeScene *s, const TakeRenderOpts *o, double *d_sum,
     // join: accumulations are chained and are the last kernel of their wave, so the last one orders everything
     if (sets == 2 && prev_acc) CU(cudaStreamWaitEvent(s->stream, prev_acc, 0));
     CU(cudaEventRecord(e1, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
+    return TAKE_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int take_gpu_render_device(TakeScene *s, const TakeRenderOpts *o, double *d_sum, double *d_sumsq, TakeStats *stats) {
+    if (int rc = check_opts(s, o)) return rc;
+    if (!d_sum) return fail(TAKE_E_INVALID, "null output buffer");
+    CU(cudaSetDevice(s->device));
+    StageTimer tm;
+    tm.on = stats && ((o->flags & TAKE_RENDER_STAGE_TIMES) || env_int("TAKE_STAGE_TIMES", 0));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    int64_t launches = 0, waves = 0;
+    CU(s->totals.ensure(sizeof(Totals)));
+    int rc = render_enqueue(s, o, d_sum, d_sumsq, s->totals.as<Totals>(), tm, e0, e1, launches, waves);
+    if (rc == TAKE_OK) {
+        cudaError_t e = cudaStreamSynchronize(s->stream);
+        if (e != cudaSuccess) rc = fail(TAKE_E_CUDA, std::string("render: ") + cudaGetErrorString(e));
+    }
     float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
+    if (rc == TAKE_OK) cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    if (rc != TAKE_OK) return rc;
     tm.stream = s->stream;
     tm.collect();
     read_totals(s, stats, tm, ms, launches, waves);
+    return TAKE_OK;
+}
+
+// ---- asynchronous render: up to two calls in flight; the device->host copy of call k overlaps the kernels of call k+1 --
+int take_gpu_render_async(TakeScene *s, const TakeRenderOpts *o, double *sum_rgb, double *sumsq_rgb, int64_t *ticket) {
+    if (int rc = check_opts(s, o)) return rc;
+    if (!sum_rgb || !ticket) return fail(TAKE_E_INVALID, "null argument");
+    if ((o->flags & TAKE_RENDER_STAGE_TIMES) || env_int("TAKE_STAGE_TIMES", 0))
+        return fail(TAKE_E_INVALID, "per-stage timing serialises the kernels: use take_gpu_render for it");
+    CU(cudaSetDevice(s->device));
+    TakeScene::AsyncSlot &a = s->async_slot[s->next_ticket & 1];
+    if (a.busy) return fail(TAKE_E_INVALID, "two renders already in flight: take_gpu_render_wait the older ticket first");
+    const size_t bytes = (size_t)s->width * s->height * 3 * sizeof(double);
+    if (!s->copy_stream) CU(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    if (!a.e0) {
+        CU(cudaEventCreate(&a.e0));
+        CU(cudaEventCreate(&a.e1));
+        CU(cudaEventCreateWithFlags(&a.done, cudaEventDisableTiming));
+        CU(cudaMallocHost((void **)&a.h_totals, sizeof(Totals)));
+        CU(a.totals.ensure(sizeof(Totals)));
+    }
+    CU(a.sum.ensure(bytes));
+    CU(cudaMemsetAsync(a.sum.p, 0, bytes, s->stream));
+    if (sumsq_rgb) {
+        CU(a.sq.ensure(bytes));
+        CU(cudaMemsetAsync(a.sq.p, 0, bytes, s->stream));
+    }
+    StageTimer tm;
+    if (int rc = render_enqueue(s, o, a.sum.as<double>(), sumsq_rgb ? a.sq.as<double>() : nullptr, a.totals.as<Totals>(), tm, a.e0, a.e1,
+                                a.launches, a.waves))
+        return rc;
+    CU(cudaStreamWaitEvent(s->copy_stream, a.e1, 0));
+    CU(cudaMemcpyAsync(sum_rgb, a.sum.p, bytes, cudaMemcpyDeviceToHost, s->copy_stream));
+    if (sumsq_rgb) CU(cudaMemcpyAsync(sumsq_rgb, a.sq.p, bytes, cudaMemcpyDeviceToHost, s->copy_stream));
+    CU(cudaMemcpyAsync(a.h_totals, a.totals.p, sizeof(Totals), cudaMemcpyDeviceToHost, s->copy_stream));
+    CU(cudaEventRecord(a.done, s->copy_stream));
+    a.busy = true;
+    a.ticket = s->next_ticket;
+    *ticket = s->next_ticket++;
+    return TAKE_OK;
+}
+
+int take_gpu_render_wait(TakeScene *s, int64_t ticket, TakeStats *stats) {
+    if (!s) return fail(TAKE_E_INVALID, "null scene");
+    TakeScene::AsyncSlot &a = s->async_slot[ticket & 1];
+    if (!a.busy || a.ticket != ticket) return fail(TAKE_E_INVALID, "unknown or already collected ticket");
+    CU(cudaSetDevice(s->device));
+    a.busy = false;
+    CU(cudaEventSynchronize(a.done));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a.e0, a.e1);
+    StageTimer tm;
+    fill_stats(*a.h_totals, stats, tm, ms, a.launches, a.waves);
     return TAKE_OK;
 }
 

@@ -614,7 +614,49 @@ __device__ __forceinline__ void lane_ray_setup(LaneRay &r, const DevScene &sc, c
     r.d = d;
 }
 
-template <bool ANY_HIT, bool COUNT, typename IO>
+// One 4-wide node visit for the warp-persistent loop: tests the four children (same arithmetic as trace_fast4), pushes
+// the farther hits and returns the nearest one -- or the next live stack entry, or TAKE_NODE_DONE.
+template <bool COUNT>
+__device__ __forceinline__ int32_t visit_wide(const DevScene &sc, int32_t node, const LaneRay &r, TravStack &st, TravCounters *cnt) {
+    const float4 *N = sc.wide_nodes + 8 * (int64_t)node;
+    const F8 nx = ldg_f8(N), ny = ldg_f8(N + 2), nz = ldg_f8(N + 4);
+    const float4 lox = nx.a, hix = nx.b, loy = ny.a, hiy = ny.b, loz = nz.a, hiz = nz.b;
+    const int4 ch = __ldg((const int4 *)(N + 6));
+    if (COUNT) cnt->box += 4;
+    uint32_t key[4];
+#define TAKE_WIDE_CHILD(K, LX, HX, LY, HY, LZ, HZ, C)                                            \
+    {                                                                                              \
+        float a = fmaf(LX, r.idx, r.olx), b = fmaf(HX, r.idx, r.ohx);                              \
+        float tn = fminf(a, b), tf = fmaxf(a, b);                                                  \
+        a = fmaf(LY, r.idy, r.oly); b = fmaf(HY, r.idy, r.ohy);                                    \
+        tn = fmaxf(tn, fminf(a, b)); tf = fminf(tf, fmaxf(a, b));                                  \
+        a = fmaf(LZ, r.idz, r.olz); b = fmaf(HZ, r.idz, r.ohz);                                    \
+        tn = fmaxf(tn, fminf(a, b)); tf = fminf(tf, fmaxf(a, b));                                  \
+        tn = fmaxf(tn, r.tmin_f); tf = fminf(tf, r.tbest_f);                                       \
+        const bool h = (tn <= tf * TAKE_SLACK) && (C != TAKE_WIDE_EMPTY);                          \
+        key[K] = h ? ((__float_as_uint(tn) & 0xfffffffcu) | (uint32_t)K) : 0xffffffffu;            \
+    }
+    TAKE_WIDE_CHILD(0, lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x, ch.x)
+    TAKE_WIDE_CHILD(1, lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, ch.y)
+    TAKE_WIDE_CHILD(2, lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, ch.z)
+    TAKE_WIDE_CHILD(3, lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, ch.w)
+#undef TAKE_WIDE_CHILD
+    cswap(key[0], key[1]); cswap(key[2], key[3]); cswap(key[0], key[2]); cswap(key[1], key[3]); cswap(key[1], key[2]);
+#define TAKE_WIDE_PICK(KEY) (((KEY) & 2u) ? (((KEY) & 1u) ? ch.w : ch.z) : (((KEY) & 1u) ? ch.y : ch.x))
+    if (key[3] != 0xffffffffu) st.push_bits(TAKE_WIDE_PICK(key[3]), key[3] & 0xfffffffcu);
+    if (key[2] != 0xffffffffu) st.push_bits(TAKE_WIDE_PICK(key[2]), key[2] & 0xfffffffcu);
+    if (key[1] != 0xffffffffu) st.push_bits(TAKE_WIDE_PICK(key[1]), key[1] & 0xfffffffcu);
+    if (key[0] != 0xffffffffu) return TAKE_WIDE_PICK(key[0]);
+#undef TAKE_WIDE_PICK
+    while (st.sp > 0) {
+        int32_t nn; float tn;
+        st.pop(nn, tn);
+        if (tn <= r.tbest_f * TAKE_SLACK) return nn;
+    }
+    return TAKE_NODE_DONE;
+}
+
+template <bool ANY_HIT, bool COUNT, bool WIDE, typename IO>
 __device__ __forceinline__ void trace_warp_persistent(const DevScene &sc, IO &io, uint32_t n, uint32_t *fetch, TravStack &st,
                                                       TravCounters *cnt) {
     const int lane = threadIdx.x & 31;
@@ -663,42 +705,46 @@ __device__ __forceinline__ void trace_warp_persistent(const DevScene &sc, IO &io
             continue;
         }
         // ---- 2. node phase ----
+        if (WIDE) {
+            while (active && node >= 0) node = visit_wide<COUNT>(sc, node, r, st, cnt);
+        } else {
         while (active && node >= 0) {
-            const float4 q0 = __ldg(sc.nodes + 4 * (int64_t)node);
-            const float4 q1 = __ldg(sc.nodes + 4 * (int64_t)node + 1);
-            const float4 q2 = __ldg(sc.nodes + 4 * (int64_t)node + 2);
-            const float4 q3 = __ldg(sc.nodes + 4 * (int64_t)node + 3);
-            if (COUNT) cnt->box += 2;
-            float a, b;
-            a = fmaf(q0.x, r.idx, r.olx); b = fmaf(q0.y, r.idx, r.ohx);
-            float tn0 = fminf(a, b), tf0 = fmaxf(a, b);
-            a = fmaf(q0.z, r.idy, r.oly); b = fmaf(q0.w, r.idy, r.ohy);
-            tn0 = fmaxf(tn0, fminf(a, b)); tf0 = fminf(tf0, fmaxf(a, b));
-            a = fmaf(q2.x, r.idz, r.olz); b = fmaf(q2.y, r.idz, r.ohz);
-            tn0 = fmaxf(tn0, fminf(a, b)); tf0 = fminf(tf0, fmaxf(a, b));
-            tn0 = fmaxf(tn0, r.tmin_f); tf0 = fminf(tf0, r.tbest_f);
-            a = fmaf(q1.x, r.idx, r.olx); b = fmaf(q1.y, r.idx, r.ohx);
-            float tn1 = fminf(a, b), tf1 = fmaxf(a, b);
-            a = fmaf(q1.z, r.idy, r.oly); b = fmaf(q1.w, r.idy, r.ohy);
-            tn1 = fmaxf(tn1, fminf(a, b)); tf1 = fminf(tf1, fmaxf(a, b));
-            a = fmaf(q2.z, r.idz, r.olz); b = fmaf(q2.w, r.idz, r.ohz);
-            tn1 = fmaxf(tn1, fminf(a, b)); tf1 = fminf(tf1, fmaxf(a, b));
-            tn1 = fmaxf(tn1, r.tmin_f); tf1 = fminf(tf1, r.tbest_f);
-            const bool h0 = tn0 <= tf0 * TAKE_SLACK, h1 = tn1 <= tf1 * TAKE_SLACK;
-            const int32_t c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
-            if (h0 && h1) {
-                if (tn1 < tn0) { st.push(c0, tn0); node = c1; }
-                else { st.push(c1, tn1); node = c0; }
-            } else if (h0) {
-                node = c0;
-            } else if (h1) {
-                node = c1;
-            } else {
-                node = TAKE_NODE_DONE;
-                while (st.sp > 0) {
-                    int32_t nn; float tn;
-                    st.pop(nn, tn);
-                    if (tn <= r.tbest_f * TAKE_SLACK) { node = nn; break; }
+                const float4 q0 = __ldg(sc.nodes + 4 * (int64_t)node);
+                const float4 q1 = __ldg(sc.nodes + 4 * (int64_t)node + 1);
+                const float4 q2 = __ldg(sc.nodes + 4 * (int64_t)node + 2);
+                const float4 q3 = __ldg(sc.nodes + 4 * (int64_t)node + 3);
+                if (COUNT) cnt->box += 2;
+                float a, b;
+                a = fmaf(q0.x, r.idx, r.olx); b = fmaf(q0.y, r.idx, r.ohx);
+                float tn0 = fminf(a, b), tf0 = fmaxf(a, b);
+                a = fmaf(q0.z, r.idy, r.oly); b = fmaf(q0.w, r.idy, r.ohy);
+                tn0 = fmaxf(tn0, fminf(a, b)); tf0 = fminf(tf0, fmaxf(a, b));
+                a = fmaf(q2.x, r.idz, r.olz); b = fmaf(q2.y, r.idz, r.ohz);
+                tn0 = fmaxf(tn0, fminf(a, b)); tf0 = fminf(tf0, fmaxf(a, b));
+                tn0 = fmaxf(tn0, r.tmin_f); tf0 = fminf(tf0, r.tbest_f);
+                a = fmaf(q1.x, r.idx, r.olx); b = fmaf(q1.y, r.idx, r.ohx);
+                float tn1 = fminf(a, b), tf1 = fmaxf(a, b);
+                a = fmaf(q1.z, r.idy, r.oly); b = fmaf(q1.w, r.idy, r.ohy);
+                tn1 = fmaxf(tn1, fminf(a, b)); tf1 = fminf(tf1, fmaxf(a, b));
+                a = fmaf(q2.z, r.idz, r.olz); b = fmaf(q2.w, r.idz, r.ohz);
+                tn1 = fmaxf(tn1, fminf(a, b)); tf1 = fminf(tf1, fmaxf(a, b));
+                tn1 = fmaxf(tn1, r.tmin_f); tf1 = fminf(tf1, r.tbest_f);
+                const bool h0 = tn0 <= tf0 * TAKE_SLACK, h1 = tn1 <= tf1 * TAKE_SLACK;
+                const int32_t c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
+                if (h0 && h1) {
+                    if (tn1 < tn0) { st.push(c0, tn0); node = c1; }
+                    else { st.push(c1, tn1); node = c0; }
+                } else if (h0) {
+                    node = c0;
+                } else if (h1) {
+                    node = c1;
+                } else {
+                    node = TAKE_NODE_DONE;
+                    while (st.sp > 0) {
+                        int32_t nn; float tn;
+                        st.pop(nn, tn);
+                        if (tn <= r.tbest_f * TAKE_SLACK) { node = nn; break; }
+                    }
                 }
             }
         }

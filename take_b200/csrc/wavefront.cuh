@@ -856,13 +856,13 @@ struct ExtendIO {
     int32_t branch;
 };
 
-template <bool COUNT>
+template <bool COUNT, bool WIDE>
 __global__ void __launch_bounds__(128, TAKE_EXTEND_MIN_BLOCKS) k_extend2(DevScene sc, Wave w, int pass) {
     TAKE_DECLARE_STACK(st);
     PassCounters &pc = w.pass[pass];
     ExtendIO io = {w, pc, w.q_extend[pass & 1], -1, sc.prim_mtype, 0};
     TravCounters cnt = {0, 0};
-    trace_warp_persistent<false, COUNT>(sc, io, pc.n_extend, &pc.fetch_extend, st, &cnt);
+    trace_warp_persistent<false, COUNT, WIDE>(sc, io, pc.n_extend, &pc.fetch_extend, st, &cnt);
     if (COUNT) {
         atomicAdd(&w.totals->box_tests, cnt.box);
         atomicAdd(&w.totals->tri_tests, cnt.tri);
@@ -886,13 +886,13 @@ struct ShadowIO {
     }
 };
 
-template <bool COUNT>
+template <bool COUNT, bool WIDE>
 __global__ void __launch_bounds__(128, TAKE_EXTEND_MIN_BLOCKS) k_shadow2(DevScene sc, Wave w, int pass) {
     TAKE_DECLARE_STACK(st);
     PassCounters &pc = w.pass[pass];
     ShadowIO io = {w, -1};
     TravCounters cnt = {0, 0};
-    trace_warp_persistent<true, COUNT>(sc, io, pc.n_shadow, &pc.fetch_shadow, st, &cnt);
+    trace_warp_persistent<true, COUNT, WIDE>(sc, io, pc.n_shadow, &pc.fetch_shadow, st, &cnt);
     if (COUNT) {
         atomicAdd(&w.totals->shadow_box_tests, cnt.box);
         atomicAdd(&w.totals->shadow_tri_tests, cnt.tri);
@@ -925,7 +925,7 @@ __global__ void __launch_bounds__(128, TAKE_EXTEND_MIN_BLOCKS) k_intersect_fast2
                                                          uint32_t *fetch) {
     TAKE_DECLARE_STACK(st);
     ApiIO<ANY_HIT> io = {rays, hits, occ};
-    trace_warp_persistent<ANY_HIT, false>(sc, io, (uint32_t)n, fetch, st, nullptr);
+    trace_warp_persistent<ANY_HIT, false, false>(sc, io, (uint32_t)n, fetch, st, nullptr);
 }
 
 __global__ void k_intersect_exact(DevScene sc, const TakeRay *rays, int64_t n, TakeHit *hits) {

@@ -186,6 +186,31 @@ def test_render_properties(pair, monkeypatch):
     assert st["kernel_launches"] > 0 and st["extend_rays"] >= flat.width * flat.height * 4
 
 
+def test_async_render_equals_sync(pair):
+    """take_gpu_render_async / _wait: two tickets in flight give the same buffers and counters as the blocking calls,
+    a third is refused until the oldest is collected, tickets cannot be collected twice."""
+    name, flat, gs, sc = pair
+    H, W = flat.height, flat.width
+    want = [gs.render_sums(integ, 5, lo, hi, seed=9) for integ, lo, hi in (("mis", 0, 3), ("one_sample_mis", 3, 5), ("mis", 5, 6))]
+    bufs = [(np.full((H, W, 3), np.nan), np.full((H, W, 3), np.nan)) for _ in range(3)]
+    t0 = gs.render_async(bufs[0][0], bufs[0][1], "mis", 5, 0, 3, seed=9)
+    t1 = gs.render_async(bufs[1][0], None, "one_sample_mis", 5, 3, 5, seed=9)
+    with pytest.raises(api.TakeGpuError):
+        gs.render_async(bufs[2][0], bufs[2][1], "mis", 5, 5, 6, seed=9)          # two already in flight
+    st0 = gs.render_wait(t0)
+    t2 = gs.render_async(bufs[2][0], bufs[2][1], "mis", 5, 5, 6, seed=9)          # slot of t0 is free again
+    st1, st2 = gs.render_wait(t1), gs.render_wait(t2)
+    with pytest.raises(api.TakeGpuError):
+        gs.render_wait(t0)
+    for (s, s2, st), (bs, bs2), got, has_sq in zip(want, bufs, (st0, st1, st2), (True, False, True)):
+        assert np.array_equal(bs, s)
+        if has_sq:
+            assert np.array_equal(bs2, s2)
+        for k in ("samples", "extend_rays", "shadow_rays", "shaded", "kernel_launches", "waves"):
+            assert got[k] == st[k], k
+        assert got["ms_total"] > 0
+
+
 def test_edge_cases(gpu_lib, oracle_lib):
     # empty scene: everything misses, the image is the background
     b = scenes.SceneBuilder(16, 8, (0, 0, 5), (0, 0, 0), background=(0.25, 0.5, 0.75))
