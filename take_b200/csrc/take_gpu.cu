@@ -35,6 +35,10 @@ int fail(int code, const std::string &msg) {
                         std::string(#expr) + ": " + cudaGetErrorString(e_));                                 \
     } while (0)
 
+#ifndef TAKE_WARP_SAMPLES_DEFAULT
+#define TAKE_WARP_SAMPLES_DEFAULT 32
+#endif
+
 int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
     return v && *v ? atoi(v) : dflt;
@@ -822,7 +826,15 @@ int render_enqueue(TakeScene *s, const TakeRenderOpts *o, double *d_sum, double 
     // Two waves in flight on two streams: the thin late passes of one wave (few, long rays) overlap the fat early passes
     // of the next, and the latency-bound shade kernels share the SMs with the issue-bound traversal kernels.  Per-kernel
     // timing (TAKE_RENDER_STAGE_TIMES) needs kernels that run alone, so it serialises on one stream.
-    const int64_t chunk_pixels = std::min(npix, capacity & ~int64_t(31));
+    // Wave shape: a wave covers `chunk_pixels` pixels x `per_wave` sample indices.  The samples of a pixel that sit in
+    // one wave can share warps (TAKE_WARP_SAMPLES, wavefront.cuh: slot_to_local), which makes the camera rays of a warp
+    // nearly identical -- worth more than covering the whole frame per wave -- so when the capacity holds fewer than
+    // that many samples of every pixel the wave covers fewer pixels instead.
+    const int64_t warp_samples = std::max(1, std::min(32, env_int("TAKE_WARP_SAMPLES", TAKE_WARP_SAMPLES_DEFAULT)));
+    int64_t group = 1;  // largest power of two <= min(warp_samples, spp)
+    while (group * 2 <= std::min<int64_t>(warp_samples, std::max<int64_t>(spp, 1))) group *= 2;
+    int64_t chunk_pixels = std::min(npix, capacity & ~int64_t(31));
+    if (capacity / chunk_pixels < group) chunk_pixels = std::max<int64_t>(32, (capacity / group) & ~int64_t(31));
     const int64_t per_wave_full = std::max<int64_t>(1, capacity / chunk_pixels);
     const int64_t n_waves_est = ((npix + chunk_pixels - 1) / chunk_pixels) * ((std::max<int64_t>(spp, 1) + per_wave_full - 1) / per_wave_full);
     const int sets = (!tm.on && n_waves_est > 1 && env_int("TAKE_OVERLAP", 1)) ? 2 : 1;
@@ -849,7 +861,8 @@ int render_enqueue(TakeScene *s, const TakeRenderOpts *o, double *d_sum, double 
     cudaEvent_t prev_acc = nullptr;
     for (int64_t base = 0; base < npix; base += chunk_pixels) {
         const int64_t cp = std::min(chunk_pixels, npix - base);
-        const int64_t per_wave = std::max<int64_t>(1, capacity / cp);
+        int64_t per_wave = std::max<int64_t>(1, capacity / cp);
+        if (per_wave >= group) per_wave -= per_wave % group;  // whole sample groups per wave
         for (int64_t s0 = o->spp_begin; s0 < o->spp_end; s0 += per_wave) {
             const int64_t ns = std::min(per_wave, o->spp_end - s0);
             const int k = sets == 2 ? (int)(waves & 1) : 0;
@@ -858,6 +871,13 @@ int render_enqueue(TakeScene *s, const TakeRenderOpts *o, double *d_sum, double 
             wv.chunk_base = (int32_t)base;
             wv.sample0 = s0;
             wv.samples_in_wave = (int32_t)ns;
+            {   // samples of one pixel that share a warp (wavefront.cuh: slot_to_local): largest power of two <= the
+                // request that divides the wave's sample count while 32 / G_s divides its pixel count
+                int g = 0;
+                while ((2 << g) <= warp_samples && ns % (2 << g) == 0) ++g;
+                while (g > 0 && cp % (32 >> g) != 0) --g;
+                wv.gs_log2 = g;
+            }
             wv.n_slots = (int32_t)(cp * ns);
             cudaEvent_t done = sets == 2 ? s->ev_acc[k] : nullptr;
             if (int rc = launch_wave(s, wv, o, d_sum, d_sumsq, nullptr, tm, count, launches, streams[k], prev_acc, done)) return rc;

@@ -109,8 +109,9 @@ struct Wave {
     int32_t *q_shadow;
     PassCounters *pass;  // [TAKE_MAX_PASSES]
     Totals *totals;
-    // slot -> (pixel, sample): slot = s_local * chunk_pixels + pixel_local, unless an explicit list is given
+    // slot -> (pixel, sample): see slot_of() below, unless an explicit list is given
     int32_t chunk_pixels, chunk_base;
+    int32_t gs_log2;  // log2 of the samples of one pixel that share a warp (0: a warp = 32 pixels of one sample index)
     int64_t sample0;
     int32_t n_slots, samples_in_wave;
     const int32_t *list_pixel;  // optional explicit (pixel, sample) list (take_gpu_radiance_samples)
@@ -133,13 +134,42 @@ __device__ __forceinline__ uint32_t pixel_of_index(const Wave &w, uint32_t idx) 
     return (ty * 4u + (in >> 3)) * (uint32_t)w.tile_w + tx * 8u + (in & 7u);
 }
 
+// Slot layout of a wave.  A warp (32 consecutive slots) holds G_s = 2^gs_log2 samples of each of G_p = 32 / G_s
+// neighbouring pixels: with G_s = 1 it is one sample index of a whole 8x4 tile, with larger G_s the camera rays of a warp
+// differ by sub-pixel jitter only, follow (nearly) the same path through the tree and fetch the same nodes.  Warps are
+// ordered pixel group first, so the sample groups of a pixel group are adjacent.  Any bijection gives the same image
+// (streams are keyed by pixel and sample index); the host falls back to G_s = 1 when the wave's sample count or pixel
+// count is not a multiple of the group sizes.
+__device__ __forceinline__ void slot_to_local(const Wave &w, uint32_t slot, uint32_t &p_local, uint32_t &s_local) {
+    if (w.gs_log2 == 0) {
+        p_local = slot % (uint32_t)w.chunk_pixels;
+        s_local = slot / (uint32_t)w.chunk_pixels;
+        return;
+    }
+    const uint32_t gs = 1u << w.gs_log2, gp_log2 = 5u - (uint32_t)w.gs_log2, gp = 1u << gp_log2;
+    const uint32_t sample_groups = (uint32_t)w.samples_in_wave >> w.gs_log2;
+    const uint32_t wi = slot >> 5, lane = slot & 31u;
+    const uint32_t pg = wi / sample_groups, sg = wi - pg * sample_groups;
+    p_local = (pg << gp_log2) + (lane & (gp - 1u));
+    s_local = sg * gs + (lane >> gp_log2);
+}
+__device__ __forceinline__ size_t slot_of(const Wave &w, uint32_t p_local, uint32_t s_local) {
+    if (w.gs_log2 == 0) return (size_t)s_local * (size_t)w.chunk_pixels + p_local;
+    const uint32_t gp_log2 = 5u - (uint32_t)w.gs_log2, gp = 1u << gp_log2, gs = 1u << w.gs_log2;
+    const uint32_t sample_groups = (uint32_t)w.samples_in_wave >> w.gs_log2;
+    const size_t wi = (size_t)(p_local >> gp_log2) * sample_groups + (s_local >> w.gs_log2);
+    return (wi << 5) + ((s_local & (gs - 1u)) << gp_log2) + (p_local & (gp - 1u));
+}
+
 __device__ __forceinline__ void slot_identity(const Wave &w, int slot, uint32_t &pixel, uint64_t &sample) {
     if (w.list_pixel) {
         pixel = (uint32_t)w.list_pixel[slot];
         sample = (uint64_t)w.list_sample[slot];
     } else {
-        pixel = pixel_of_index(w, (uint32_t)(w.chunk_base + slot % w.chunk_pixels));
-        sample = (uint64_t)(w.sample0 + slot / w.chunk_pixels);
+        uint32_t p_local, s_local;
+        slot_to_local(w, (uint32_t)slot, p_local, s_local);
+        pixel = pixel_of_index(w, (uint32_t)w.chunk_base + p_local);
+        sample = (uint64_t)(w.sample0 + s_local);
     }
 }
 
@@ -759,7 +789,7 @@ __global__ void k_accumulate(Wave w, double *sum, double *sumsq, int n_passes) {
     double b0 = 0, b1 = 0, b2 = 0;
     if (sumsq) { b0 = sumsq[o]; b1 = sumsq[o + 1]; b2 = sumsq[o + 2]; }
     for (int s = 0; s < w.samples_in_wave; ++s) {
-        const PathRec *pr = w.path + ((size_t)s * w.chunk_pixels + p);
+        const PathRec *pr = w.path + slot_of(w, (uint32_t)p, (uint32_t)s);
         const double r0 = pr->rad[0], r1 = pr->rad[1], r2 = pr->rad[2];
         a0 += r0; a1 += r1; a2 += r2;
         b0 += r0 * r0; b1 += r1 * r1; b2 += r2 * r2;
