@@ -246,9 +246,32 @@ __global__ void k_generate(DevScene sc, Wave w) {
     w.q_extend[0][slot] = slot;
 }
 
-#ifndef TAKE_PREFETCH_CURSOR
-#define TAKE_PREFETCH_CURSOR 0   // measured: reserving the next batch early costs 2 % (worse tail balance), kept as an option
+// Work distribution of the persistent traversal kernels: a warp takes `batches` batches of 32 queue entries with ONE
+// atomicAdd on the pass's cursor and works through them.  With one batch per atomic every warp hits the same address
+// once per 32 rays; at 12 G camera rays/s that is a same-address atomic every 2.5 ns and the wait for the returned value
+// shows up as 27 % of the stall samples of pass 0 (ncu, r01c).  Measured (tools/tune.py): 4 batches per atomic make the
+// camera-ray pass 4 % faster, but every other pass SLOWER (-6 % on the first bounce, 2x on the thin late passes): rays of
+// very different lengths need the fine granularity for balance.  So only the camera-ray pass uses TAKE_FETCH_BATCHES.
+// (Reserving the next single batch ahead of time instead was also measured: -2 %.)
+#ifndef TAKE_FETCH_BATCHES
+#define TAKE_FETCH_BATCHES 4
 #endif
+struct WorkCursor {
+    uint32_t cur, end;
+    // warp-uniform: false when the queue is exhausted; `base` = first entry of the next batch of 32
+    __device__ __forceinline__ bool next(uint32_t *cursor, uint32_t n, int lane, uint32_t &base, uint32_t batches = 1) {
+        if (cur >= end) {
+            uint32_t b = 0;
+            if (lane == 0) b = atomicAdd(cursor, 32u * batches);
+            cur = __shfl_sync(0xffffffffu, b, 0);
+            if (cur >= n) return false;
+            end = min(cur + 32u * batches, n);
+        }
+        base = cur;
+        cur += 32u;
+        return true;
+    }
+};
 
 // ---- extend: closest hit for every queued ray + histogram of the shading sort key ------------------------
 template <bool COUNT, bool WIDE>
@@ -260,21 +283,10 @@ __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_extend(DevScene sc,
     const int32_t *queue = w.q_extend[pass & 1];
     const int lane = threadIdx.x & 31;
     TravCounters cnt = {0, 0};
-    // Work cursor: a warp reserves its NEXT batch of 32 before it starts on the current one, so the round trip of the
-    // atomic hides behind the traversal instead of stalling the warp between batches.
-    uint32_t next = 0;
-#if TAKE_PREFETCH_CURSOR
-    if (lane == 0) next = atomicAdd(&pc.fetch_extend, 32u);
-#endif
+    WorkCursor wc = {0, 0};
     for (;;) {
-#if !TAKE_PREFETCH_CURSOR
-        if (lane == 0) next = atomicAdd(&pc.fetch_extend, 32u);
-#endif
-        const uint32_t base = __shfl_sync(0xffffffffu, next, 0);
-        if (base >= n) break;
-#if TAKE_PREFETCH_CURSOR
-        if (lane == 0) next = atomicAdd(&pc.fetch_extend, 32u);
-#endif
+        uint32_t base;
+        if (!wc.next(&pc.fetch_extend, n, lane, base, primary ? TAKE_FETCH_BATCHES : 1)) break;
         const uint32_t i = base + lane;
         const bool valid = i < n;
         int slot = -1;
@@ -614,6 +626,9 @@ __device__ __forceinline__ void shade_one_sample(ShadeCtx &c, const RayRec &ray,
     }
 }
 
+#ifndef TAKE_SHADE_PREFETCH
+#define TAKE_SHADE_PREFETCH 2   // 0: off, 1: next iteration's hit record -> L2, 2: -> L1 (measured: -4 % on one-sample shade)
+#endif
 #ifndef TAKE_SHADE_EARLY
 #define TAKE_SHADE_EARLY 0   // 0: records fetched when needed, 1: ray+path right after the slot, 2: + the pending BSDF sample
 #endif
@@ -633,6 +648,17 @@ __global__ void __launch_bounds__(128, TAKE_SHADE_MIN_BLOCKS) k_shade(DevScene s
         const bool valid = i < n;
         bool emit_extend = false, emit_shadow = false;
         int slot = -1, shaded = 0;
+#if TAKE_SHADE_PREFETCH
+        // the record this thread needs in its next iteration: requested now, so that the ~1 us DRAM round trip at the head
+        // of the dependent chain (hit -> slot -> ray/path -> vertex data) overlaps this iteration's shading
+        if (w.sort_enabled && i + gridDim.x * blockDim.x < n) {
+#if TAKE_SHADE_PREFETCH == 1
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(w.hit_sorted + i + gridDim.x * blockDim.x));
+#else
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(w.hit_sorted + i + gridDim.x * blockDim.x));
+#endif
+        }
+#endif
         if (valid) {
             const HitRec hit = w.sort_enabled ? w.hit_sorted[i] : w.hit[primary ? (int)i : queue[i]];
             slot = w.sort_enabled ? (int)hit.keyrank : (primary ? (int)i : queue[i]);
@@ -741,19 +767,10 @@ __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_shadow(DevScene sc,
     const uint32_t n = pc.n_shadow;
     const int lane = threadIdx.x & 31;
     TravCounters cnt = {0, 0};
-    uint32_t next = 0;  // next batch reserved ahead of time (see k_extend)
-#if TAKE_PREFETCH_CURSOR
-    if (lane == 0) next = atomicAdd(&pc.fetch_shadow, 32u);
-#endif
+    WorkCursor wc = {0, 0};
     for (;;) {
-#if !TAKE_PREFETCH_CURSOR
-        if (lane == 0) next = atomicAdd(&pc.fetch_shadow, 32u);
-#endif
-        const uint32_t base = __shfl_sync(0xffffffffu, next, 0);
-        if (base >= n) break;
-#if TAKE_PREFETCH_CURSOR
-        if (lane == 0) next = atomicAdd(&pc.fetch_shadow, 32u);
-#endif
+        uint32_t base;
+        if (!wc.next(&pc.fetch_shadow, n, lane, base)) break;
         const uint32_t i = base + lane;
         if (i < n) {
             const int slot = w.q_shadow[i];
@@ -820,19 +837,11 @@ __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_intersect_fast(DevS
                                                         uint32_t *fetch) {
     TAKE_DECLARE_STACK(st);
     const int lane = threadIdx.x & 31;
-    uint32_t next = 0;  // next batch reserved ahead of time (see k_extend)
-#if TAKE_PREFETCH_CURSOR
-    if (lane == 0) next = atomicAdd(fetch, 32u);
-#endif
+    WorkCursor wc = {0, 0};
+    const uint32_t n32 = (uint32_t)n;
     for (;;) {
-#if !TAKE_PREFETCH_CURSOR
-        if (lane == 0) next = atomicAdd(fetch, 32u);
-#endif
-        const uint32_t base = __shfl_sync(0xffffffffu, next, 0);
-        if ((int64_t)base >= n) break;
-#if TAKE_PREFETCH_CURSOR
-        if (lane == 0) next = atomicAdd(fetch, 32u);
-#endif
+        uint32_t base;
+        if (!wc.next(fetch, n32, lane, base)) break;
         const int64_t i = (int64_t)base + lane;
         if (i < n) {
             const TakeRay r = rays[i];

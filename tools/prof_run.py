@@ -1,4 +1,4 @@
-"""Short profiling workload for `ncu`: config-2 scene, ONE bench-sized wave (8 spp x 1920x1080 = 16.6 M slots) of the
+"""Short profiling workload for `ncu`: config-2 scene, one bench step (32 spp x 1920x1080: two waves of 1 M pixels x 32 samples, 33.5 M slots each) of the
 one-sample-MIS integrator (7 extend + 7 shade launches), then one wave of the multi-sample MIS integrator (adds the
 shadow kernel).  No torch import."""
 import os, sys
@@ -7,6 +7,6 @@ from take_b200 import api, scenes
 flat = scenes.heightfield().flat()
 gs = api.GpuScene(flat)
 for integ in ("one_sample_mis", "mis"):
-    s, s2, st = gs.render_sums(integ, 5, 0, 8, seed=1, flags=api.RENDER_COUNT_TESTS if "--count" in sys.argv else 0)
+    s, s2, st = gs.render_sums(integ, 5, 0, 32, seed=1, flags=api.RENDER_COUNT_TESTS if "--count" in sys.argv else 0)
     print(integ, {k: st[k] for k in ("ms_total", "extend_rays", "shadow_rays", "box_tests", "tri_tests", "kernel_launches", "waves")})
 gs.close()
