@@ -115,6 +115,9 @@ struct DevScene {
     const int32_t *indices, *prim_material, *prim_light, *dfs_rank;
     const uint8_t *prim_flags, *prim_mtype;
     const double *spheres;
+    // per-primitive shading records (shading.cuh: ShadeRec layout), built on the device by k_build_shade_recs
+    const double *shade_recs;
+    int32_t shade_stride;  // doubles per record: 16 (no primitive carries uvs) or 20
     const TakeMaterialDesc *materials;
     const TakeLightDesc *lights;
     const DevTexture *textures;
@@ -133,6 +136,34 @@ struct DevScene {
     int32_t env_light;   // 1: the environment is entry number num_lights of the uniform light pick
     int32_t pick_count;  // num_lights + env_light: the N of sample_light (src/light.cpp:5-7) and of the 1/N in the light pdfs
 };
+
+// 256-bit read-only loads (sm_100: LDG.E.256).  The traversal kernels are bound by L1 wavefront throughput -- every
+// lane of a divergent warp touches its own cache line, one wavefront per line per load instruction -- so moving a
+// 64-byte node in two instructions instead of four halves the wavefronts per node.  Addresses must be 32-byte aligned.
+#ifndef TAKE_LDG256
+#define TAKE_LDG256 1
+#endif
+struct F8 { float4 a, b; };
+struct D4 { double2 a, b; };
+__device__ __forceinline__ F8 ldg_f8(const float4 *p) {
+    F8 r;
+#if TAKE_LDG256
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+#else
+    r.a = __ldg(p); r.b = __ldg(p + 1);
+#endif
+    return r;
+}
+__device__ __forceinline__ D4 ldg_d4(const double2 *p) {
+    D4 r;
+#if TAKE_LDG256
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a.x), "=d"(r.a.y), "=d"(r.b.x), "=d"(r.b.y) : "l"(p));
+#else
+    r.a = __ldg(p); r.b = __ldg(p + 1);
+#endif
+    return r;
+}
 
 struct HitOut {
     int32_t prim;

@@ -20,8 +20,24 @@ __device__ __forceinline__ D2 sphere_uv(D3 p) {  // src/shape.cpp:3-11
     return r;
 }
 
-// src/shape.cpp:30-41 (sphere) and :80-108 (triangle)
-__device__ __forceinline__ void fill_isect(const DevScene &sc, D3 o, D3 d, int prim, double t, double u, double v, Isect &out) {
+// Per-primitive shading record (ShadeRec): everything fill_isect needs about a primitive in ONE aligned block, so a
+// shaded vertex costs four or five full 32-byte sectors issued together instead of a dependent chain
+// prim -> {material, light, flags, indices} -> {3 positions, 3 normals, 3 uvs} of ~16 partially used sectors.
+// Layout in doubles (stride DevScene::shade_stride = 16, or 20 when some primitive carries uvs):
+//   [0..2]   triangle: normalize(cross(p1 - p0, p2 - p0)), the geometric normal before it is flipped towards the ray
+//            (shape.cpp:84-88; the same operations on the same operands, done once per primitive instead of once per hit)
+//            sphere:   centre, [3] = radius
+//   [3..11]  triangle: the three vertex normals (when TAKE_PRIM_HAS_NORMALS)
+//   [12]     bits: material id | light id << 32        [13] bits: primitive flags
+//   [14..19] triangle: the three vertex uvs (when TAKE_PRIM_HAS_UVS; stride 20 only)
+// The records are derived on the device from the uploaded reference-layout arrays (k_build_shade_recs), with the
+// device's own -fmad=false FP64 arithmetic, so every value is the one fill_isect used to compute per hit.
+#ifndef TAKE_SHADE_RECS
+#define TAKE_SHADE_RECS 1
+#endif
+
+// src/shape.cpp:30-41 (sphere) and :80-108 (triangle), from the reference-layout arrays
+__device__ __forceinline__ void fill_isect_arrays(const DevScene &sc, D3 o, D3 d, int prim, double t, double u, double v, Isect &out) {
     out.pos = add(o, mul(d, t));
     out.material = sc.prim_material[prim];
     out.light = sc.prim_light[prim];
@@ -54,6 +70,78 @@ __device__ __forceinline__ void fill_isect(const DevScene &sc, D3 o, D3 d, int p
         D3 n0 = ld3(sc.normals + 3 * i0), n1 = ld3(sc.normals + 3 * i1), n2 = ld3(sc.normals + 3 * i2);
         out.sn = normalize(add(add(mul(n0, w), mul(n1, u)), mul(n2, v)));
     }
+}
+
+// Writes the record of primitive `prim` (one thread per primitive, launched once by take_gpu_scene_create).
+__global__ void k_build_shade_recs(DevScene sc, double *recs) {
+    const int64_t prim = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (prim >= sc.num_prims) return;
+    double *r = recs + prim * sc.shade_stride;
+    const uint32_t flags = sc.prim_flags[prim];
+    const int32_t *id = sc.indices + 3 * prim;
+    for (int k = 0; k < sc.shade_stride; ++k) r[k] = 0.0;
+    r[12] = __longlong_as_double((long long)(((unsigned long long)(uint32_t)sc.prim_light[prim] << 32) | (uint32_t)sc.prim_material[prim]));
+    r[13] = __longlong_as_double((long long)flags);
+    if (flags & TAKE_PRIM_SPHERE) {
+        const double *s = sc.spheres + 4 * (int64_t)id[0];
+        r[0] = s[0]; r[1] = s[1]; r[2] = s[2]; r[3] = s[3];
+        return;
+    }
+    const int64_t i0 = id[0], i1 = id[1], i2 = id[2];
+    const D3 v0 = ld3(sc.positions + 3 * i0);
+    const D3 e1 = sub(ld3(sc.positions + 3 * i1), v0), e2 = sub(ld3(sc.positions + 3 * i2), v0);
+    const D3 gn = normalize(cross(e1, e2));
+    r[0] = gn.x; r[1] = gn.y; r[2] = gn.z;
+    if (flags & TAKE_PRIM_HAS_NORMALS) {
+        const int64_t iv[3] = {i0, i1, i2};
+        for (int k = 0; k < 3; ++k)
+            for (int c = 0; c < 3; ++c) r[3 + 3 * k + c] = sc.normals[3 * iv[k] + c];
+    }
+    if ((flags & TAKE_PRIM_HAS_UVS) && sc.shade_stride >= 20) {
+        const int64_t iv[3] = {i0, i1, i2};
+        for (int k = 0; k < 3; ++k)
+            for (int c = 0; c < 2; ++c) r[14 + 2 * k + c] = sc.uvs[2 * iv[k] + c];
+    }
+}
+
+// src/shape.cpp:30-41 (sphere) and :80-108 (triangle)
+__device__ __forceinline__ void fill_isect(const DevScene &sc, D3 o, D3 d, int prim, double t, double u, double v, Isect &out) {
+#if !TAKE_SHADE_RECS
+    fill_isect_arrays(sc, o, d, prim, t, u, v, out);
+#else
+    const double2 *R = reinterpret_cast<const double2 *>(sc.shade_recs + (int64_t)prim * sc.shade_stride);
+    const D4 r0 = ldg_d4(R), r1 = ldg_d4(R + 2), r2 = ldg_d4(R + 4), r3 = ldg_d4(R + 6);
+    D4 r4;
+    r4.a.x = r4.a.y = r4.b.x = r4.b.y = 0.0;
+    if (sc.shade_stride >= 20) r4 = ldg_d4(R + 8);
+    out.pos = add(o, mul(d, t));
+    const unsigned long long ml = (unsigned long long)__double_as_longlong(r3.a.x);
+    out.material = (int32_t)(uint32_t)ml;
+    out.light = (int32_t)(uint32_t)(ml >> 32);
+    const uint32_t flags = (uint32_t)__double_as_longlong(r3.a.y);
+    if (flags & TAKE_PRIM_SPHERE) {
+        D3 gn = normalize(sub(out.pos, mk3(r0.a.x, r0.a.y, r0.b.x)));
+        out.gn = dot(d, gn) < 0 ? gn : neg(gn);
+        out.sn = out.gn;
+        out.uv = sphere_uv(out.gn);
+        return;
+    }
+    const D3 gn = mk3(r0.a.x, r0.a.y, r0.b.x);
+    out.gn = dot(d, gn) < 0 ? gn : neg(gn);
+    const double w = 1 - u - v;
+    if (!(flags & TAKE_PRIM_HAS_UVS)) {
+        out.uv.x = u; out.uv.y = v;
+    } else {
+        out.uv.x = w * r3.b.x + u * r4.a.x + v * r4.b.x;
+        out.uv.y = w * r3.b.y + u * r4.a.y + v * r4.b.y;
+    }
+    if (!(flags & TAKE_PRIM_HAS_NORMALS)) {
+        out.sn = out.gn;
+    } else {
+        const D3 n0 = mk3(r0.b.y, r1.a.x, r1.a.y), n1 = mk3(r1.b.x, r1.b.y, r2.a.x), n2 = mk3(r2.a.y, r2.b.x, r2.b.y);
+        out.sn = normalize(add(add(mul(n0, w), mul(n1, u)), mul(n2, v)));
+    }
+#endif
 }
 
 // src/texture.cpp:3-26, including the wrap-column quirk (weights use x2 = 0 there) taken literally.

@@ -69,7 +69,7 @@ struct TakeScene {
     // scene storage
     DeviceBuffer env_rgb, env_marg, env_cond;
     DeviceBuffer nodes, wide_nodes, tris, ref_nodes, positions, normals, uvs, indices, prim_material, prim_light, dfs_rank, prim_flags,
-        prim_mtype, spheres, materials, lights, textures;
+        prim_mtype, spheres, materials, lights, textures, shade_recs;
     std::vector<DeviceBuffer *> tex_data;
     DeviceBuffer exr_packed;
     // wave storage
@@ -419,6 +419,9 @@ void fill_wave_ptrs(TakeScene *s, Wave &w, const TakeRenderOpts *o, int set = 0)
     // explicit sample lists (take_gpu_radiance_samples) and the v2 traversal keep the separate generate kernel
     w.fused_primary = (s->traversal != 2 && !env_int("TAKE_NO_FUSE", 0)) ? 1 : 0;
     w.tile_w = (s->width % 8 == 0 && s->height % 4 == 0 && !env_int("TAKE_NO_TILES", 0)) ? s->width : 0;
+    // camera rays that miss are finished inside k_extend (the environment-map extension needs their direction in the
+    // shade kernel, and the unsorted debugging mode walks every slot, so both keep the general path)
+    w.miss_fast = (w.fused_primary && w.sort_enabled && s->dev.env_rgb == nullptr && !env_int("TAKE_NO_MISS_FAST", 0)) ? 1 : 0;
 }
 
 // Keep the 4-wide tree resident in L2: the wavefront kernels stream gigabytes of per-path records through the cache
@@ -641,6 +644,20 @@ static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild &hb, 
     }
     v.background = {d->background[0], d->background[1], d->background[2]};
     v.abs_max = (float)abs_max;
+
+    // per-primitive shading records, derived on the device from the arrays uploaded above (shading.cuh: ShadeRec)
+    {
+        bool any_uv = false;
+        for (int64_t i = 0; i < n && !any_uv; ++i) any_uv = (d->prim_flags[i] & TAKE_PRIM_HAS_UVS) != 0;
+        v.shade_stride = any_uv ? 20 : 16;
+        CU(s->shade_recs.ensure(std::max<size_t>((size_t)n * v.shade_stride * sizeof(double), 32)));
+        v.shade_recs = s->shade_recs.as<double>();
+        if (n > 0) {
+            k_build_shade_recs<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(v, s->shade_recs.as<double>());
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(st));
+        }
+    }
 
     // persistent-kernel launch widths: every SM filled to the occupancy the kernel allows
     auto blocks_for = [&](const void *fn) {

@@ -26,33 +26,7 @@ namespace take {
 #endif
 #define TAKE_STACK_SMEM_ALLOC (TAKE_STACK_SMEM > 0 ? TAKE_STACK_SMEM : 1)
 
-// 256-bit read-only loads (sm_100: LDG.E.256).  The traversal kernels are bound by L1 wavefront throughput -- every
-// lane of a divergent warp touches its own cache line, one wavefront per line per load instruction -- so moving a
-// 64-byte node in two instructions instead of four halves the wavefronts per node.  Addresses must be 32-byte aligned.
-#ifndef TAKE_LDG256
-#define TAKE_LDG256 1
-#endif
-struct F8 { float4 a, b; };
-struct D4 { double2 a, b; };
-__device__ __forceinline__ F8 ldg_f8(const float4 *p) {
-    F8 r;
-#if TAKE_LDG256
-    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-        : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
-#else
-    r.a = __ldg(p); r.b = __ldg(p + 1);
-#endif
-    return r;
-}
-__device__ __forceinline__ D4 ldg_d4(const double2 *p) {
-    D4 r;
-#if TAKE_LDG256
-    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a.x), "=d"(r.a.y), "=d"(r.b.x), "=d"(r.b.y) : "l"(p));
-#else
-    r.a = __ldg(p); r.b = __ldg(p + 1);
-#endif
-    return r;
-}
+// (256-bit read-only loads ldg_f8 / ldg_d4: device_common.cuh)
 
 // ---- leaf tests: src/shape.cpp:44-78 (triangle) and :13-29 (sphere), accept/reject part ---------------
 __device__ __forceinline__ bool hit_triangle(D3 v0, D3 e1, D3 e2, D3 o, D3 d, double tmin, double tmax, double &t,

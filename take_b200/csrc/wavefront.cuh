@@ -119,6 +119,7 @@ struct Wave {
     int32_t integrator, max_depth, sort_enabled;
     int32_t sort_branch;    // 1: the sort key carries the one-sample integrator's light/BSDF coin (RayRec.aux0)
     int32_t fused_primary;  // 1: no k_generate -- pass 0 of extend and shade compute the camera ray themselves
+    int32_t miss_fast;      // 1: camera rays that leave the scene are finished by k_extend itself (see k_extend)
     int32_t tile_w;  // > 0: image width, pixels are enumerated in 8x4 tiles (one warp = one tile); 0: row-major
     uint64_t seed;
 };
@@ -220,6 +221,13 @@ __device__ __forceinline__ uint32_t pass_count(const Wave &w, int pass) {
     return (pass == 0 && w.fused_primary) ? (uint32_t)w.n_slots : w.pass[pass].n_extend;
 }
 
+// Number of entries the sort and the shade kernel of pass `pass` work on.  With `miss_fast` pass 0 keeps only the camera
+// rays that hit something: k_extend lists their slots in q_extend[0] and counts them in pass[0].n_extend (which the
+// fused camera-ray pass does not otherwise use).
+__device__ __forceinline__ uint32_t shade_count(const Wave &w, int pass) {
+    return (pass == 0 && w.miss_fast) ? w.pass[0].n_extend : pass_count(w, pass);
+}
+
 // ---- generate: src/render.cpp:65-75 (only when the primaries are not fused into pass 0) ----------------------
 __global__ void k_generate(DevScene sc, Wave w) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -280,6 +288,7 @@ __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_extend(DevScene sc,
     PassCounters &pc = w.pass[pass];
     const uint32_t n = pass_count(w, pass);
     const bool primary = pass == 0 && w.fused_primary;
+    const bool miss_fast = pass == 0 && w.miss_fast;
     const int32_t *queue = w.q_extend[pass & 1];
     const int lane = threadIdx.x & 31;
     TravCounters cnt = {0, 0};
@@ -292,15 +301,14 @@ __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_extend(DevScene sc,
         int slot = -1;
         uint32_t key = 0;
         HitOut h;
+        bool rec = false;  // this lane has a hit record for the sort
         if (valid) {
             D3 o, d;
             double tmax = INFINITY;
             int32_t branch = 0;
             if (primary) {
                 slot = (int)i;
-                Rng rng;
-                primary_ray(sc, w, slot, o, d, rng);
-                if (w.sort_branch) branch = peek_branch(rng);
+                primary_ray(sc, w, slot, o, d);
             } else {
                 slot = queue[i];
                 const RayRec r = ld_stream(w.ray + slot);
@@ -308,11 +316,32 @@ __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_extend(DevScene sc,
                 branch = r.aux0;
             }
             trace_any<false, COUNT, WIDE>(sc, o, d, TAKE_EPS, tmax, st, h, &cnt);
-            key = sort_key(h.prim, sc.prim_mtype, branch);
+            if (miss_fast && h.prim < 0) {
+                // A camera ray that left the scene: the sample is the background colour (path_tracing.h:8 and the same
+                // line of the other two integrators).  Finishing it here keeps it out of the sort and the shade pass --
+                // on an open scene most camera rays end this way, and streaming their records through two more kernels
+                // was the larger part of the pass-0 shade time.
+                PathRec p;
+                p.thr[0] = p.thr[1] = p.thr[2] = 1.0;
+                p.rad[0] = sc.background.x; p.rad[1] = sc.background.y; p.rad[2] = sc.background.z;
+                p.k = 2; p.depth = 0; p.flags = 0; p.pad = 0;
+                st_stream(w.path + slot, p);
+            } else {
+                rec = true;
+                if (primary && w.sort_branch) {  // the coin of the first vertex: draw number 2 of the sample's stream
+                    Rng rng;
+                    uint32_t pixel;
+                    uint64_t sample;
+                    slot_identity(w, slot, pixel, sample);
+                    rng.seed = w.seed; rng.sample = sample; rng.pixel = pixel; rng.k = 2;
+                    branch = peek_branch(rng);
+                }
+                key = sort_key(h.prim, sc.prim_mtype, branch);
+            }
         }
         // warp-aggregated histogram: lanes with the same key elect a leader that bumps the bin once
-        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
+        const unsigned vmask = __ballot_sync(0xffffffffu, rec);
+        if (rec) {
             const unsigned peers = __match_any_sync(vmask, key);
             const int leader = __ffs(peers) - 1;
             uint32_t rbase = 0;
@@ -324,6 +353,12 @@ __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_extend(DevScene sc,
             hr.keyrank = (key << TAKE_RANK_BITS) | rank;
             hr.t = h.t; hr.u = h.u; hr.v = h.v;
             st_stream(w.hit + slot, hr);
+        }
+        if (miss_fast && vmask) {  // list the surviving slots for the sort (one atomic per warp)
+            uint32_t qb = 0;
+            if (lane == __ffs(vmask) - 1) qb = atomicAdd(&pc.n_extend, (uint32_t)__popc(vmask));
+            qb = __shfl_sync(0xffffffffu, qb, __ffs(vmask) - 1);
+            if (rec) w.q_extend[0][qb + __popc(vmask & ((1u << lane) - 1u))] = slot;
         }
     }
     if (COUNT) {
@@ -341,8 +376,8 @@ __global__ void k_scatter(Wave w, int pass) {
         for (int b = 0; b < TAKE_NBINS; ++b) { offs[b] = acc; acc += pc.bins[b]; }
     }
     __syncthreads();
-    const uint32_t n = pass_count(w, pass);
-    const bool primary = pass == 0 && w.fused_primary;
+    const uint32_t n = shade_count(w, pass);
+    const bool primary = pass == 0 && w.fused_primary && !w.miss_fast;  // no list of slots: entry i is slot i
     const int32_t *queue = w.q_extend[pass & 1];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int slot = primary ? (int)i : queue[i];
@@ -627,7 +662,10 @@ __device__ __forceinline__ void shade_one_sample(ShadeCtx &c, const RayRec &ray,
 }
 
 #ifndef TAKE_SHADE_PREFETCH
-#define TAKE_SHADE_PREFETCH 2   // 0: off, 1: next iteration's hit record -> L2, 2: -> L1 (measured: -4 % on one-sample shade)
+#define TAKE_SHADE_PREFETCH 2   // 0: off, 1: next iteration's hit record -> L2, 2: -> L1 (measured: -4 % on one-sample shade).
+                                // (A second stage -- reading the next iteration's (prim, slot) early and prefetching the ray /
+                                // path / pending-sample / shading records they point to into L2 -- was measured: shade +4 ... +9 %
+                                // SLOWER on all four scenes; the extra requests compete with the demand loads.)
 #endif
 #ifndef TAKE_SHADE_EARLY
 #define TAKE_SHADE_EARLY 0   // 0: records fetched when needed, 1: ray+path right after the slot, 2: + the pending BSDF sample
@@ -638,7 +676,7 @@ __device__ __forceinline__ void shade_one_sample(ShadeCtx &c, const RayRec &ray,
 template <int INTEGRATOR, bool ENV>
 __global__ void __launch_bounds__(128, TAKE_SHADE_MIN_BLOCKS) k_shade(DevScene sc, Wave w, int pass) {
     PassCounters &pc = w.pass[pass];
-    const uint32_t n = pass_count(w, pass);
+    const uint32_t n = shade_count(w, pass);
     const bool primary = pass == 0 && w.fused_primary;
     const int32_t *queue = w.q_extend[pass & 1];  // only read when the sort is off
     int32_t *q_next = w.q_extend[(pass + 1) & 1];
