@@ -118,6 +118,7 @@ struct DevScene {
     // per-primitive shading records (shading.cuh: ShadeRec layout), built on the device by k_build_shade_recs
     const double *shade_recs;
     int32_t shade_stride;  // doubles per record: 16 (no primitive carries uvs) or 20
+    const double *light_recs;  // per-light records (shading.cuh: LightRec layout), built by k_build_light_recs
     const TakeMaterialDesc *materials;
     const TakeLightDesc *lights;
     const DevTexture *textures;

@@ -105,15 +105,25 @@ __global__ void k_build_shade_recs(DevScene sc, double *recs) {
 }
 
 // src/shape.cpp:30-41 (sphere) and :80-108 (triangle)
+template <bool LD256>
 __device__ __forceinline__ void fill_isect(const DevScene &sc, D3 o, D3 d, int prim, double t, double u, double v, Isect &out) {
 #if !TAKE_SHADE_RECS
     fill_isect_arrays(sc, o, d, prim, t, u, v, out);
 #else
     const double2 *R = reinterpret_cast<const double2 *>(sc.shade_recs + (int64_t)prim * sc.shade_stride);
-    const D4 r0 = ldg_d4(R), r1 = ldg_d4(R + 2), r2 = ldg_d4(R + 4), r3 = ldg_d4(R + 6);
-    D4 r4;
+    // LD256 = false: 128-bit loads, which the compiler is free to schedule next to their uses (measured: the MIS shade kernel
+    // loses its 208 bytes of spills, shade -3 ... -6 % on configs 1, 2, 4).  The environment-map kernels (config 3, textured:
+    // 160-byte records) measured 2 % faster with five 256-bit loads and keep them.
+    D4 r0, r1, r2, r3, r4;
     r4.a.x = r4.a.y = r4.b.x = r4.b.y = 0.0;
-    if (sc.shade_stride >= 20) r4 = ldg_d4(R + 8);
+    if (!LD256) {
+        r0.a = __ldg(R); r0.b = __ldg(R + 1); r1.a = __ldg(R + 2); r1.b = __ldg(R + 3); r2.a = __ldg(R + 4); r2.b = __ldg(R + 5);
+        r3.a = __ldg(R + 6); r3.b = __ldg(R + 7);
+        if (sc.shade_stride >= 20) { r4.a = __ldg(R + 8); r4.b = __ldg(R + 9); }
+    } else {
+        r0 = ldg_d4(R); r1 = ldg_d4(R + 2); r2 = ldg_d4(R + 4); r3 = ldg_d4(R + 6);
+        if (sc.shade_stride >= 20) r4 = ldg_d4(R + 8);
+    }
     out.pos = add(o, mul(d, t));
     const unsigned long long ml = (unsigned long long)__double_as_longlong(r3.a.x);
     out.material = (int32_t)(uint32_t)ml;
@@ -449,7 +459,84 @@ __device__ __forceinline__ double prim_area(const DevScene &sc, int prim) {  // 
     return length(cross(sub(ld3(sc.positions + 3 * (int64_t)id[1]), v0), sub(ld3(sc.positions + 3 * (int64_t)id[2]), v0))) / 2;
 }
 
-__device__ __forceinline__ void sample_on_prim(const DevScene &sc, int prim, D3 ref_pos, Rng &rng, D3 &pos, D3 &nrm) {
+// Per-light record (LightRec, TAKE_LIGHT_REC_STRIDE doubles, 256-byte aligned): what sample_on_light / get_light_pdf need
+// about the emitter's primitive, gathered once on the device (k_build_light_recs) -- one dependent level
+// light id -> record instead of light -> primitive -> {flags, indices} -> {positions, normals}, and the per-light
+// constants (geometric normal, 1 / area) are computed once instead of once per connection, with the very operations
+// the reference performs per call (shape.cpp:146-184), so the values are the same bits.
+//   [0..8]   triangle: v0, v1, v2            sphere: centre [0..2], radius [3]
+//   [9..11]  triangle: normalize(cross(v1 - v0, v2 - v0))
+//   [12..20] triangle: the three vertex normals
+//   [21]     triangle: 1 / get_area  (light.cpp:46-47)
+//   [22]     bits: primitive flags
+#define TAKE_LIGHT_REC_STRIDE 32
+#ifndef TAKE_LIGHT_RECS
+#define TAKE_LIGHT_RECS 1
+#endif
+
+__global__ void k_build_light_recs(DevScene sc, double *recs) {
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= sc.num_lights) return;
+    double *r = recs + (int64_t)li * TAKE_LIGHT_REC_STRIDE;
+    for (int k = 0; k < TAKE_LIGHT_REC_STRIDE; ++k) r[k] = 0.0;
+    const TakeLightDesc &l = sc.lights[li];
+    if (l.kind != TAKE_LIGHT_AREA) return;
+    const int prim = l.prim_id;
+    const uint32_t flags = sc.prim_flags[prim];
+    r[22] = __longlong_as_double((long long)flags);
+    const int32_t *id = sc.indices + 3 * (int64_t)prim;
+    if (flags & TAKE_PRIM_SPHERE) {
+        const double *s = sc.spheres + 4 * (int64_t)id[0];
+        r[0] = s[0]; r[1] = s[1]; r[2] = s[2]; r[3] = s[3];
+        return;
+    }
+    const int64_t iv[3] = {id[0], id[1], id[2]};
+    for (int k = 0; k < 3; ++k)
+        for (int c = 0; c < 3; ++c) {
+            r[3 * k + c] = sc.positions[3 * iv[k] + c];
+            r[12 + 3 * k + c] = sc.normals[3 * iv[k] + c];
+        }
+    const D3 v0 = ld3(r), v1 = ld3(r + 3), v2 = ld3(r + 6);
+    const D3 n = normalize(cross(sub(v1, v0), sub(v2, v0)));
+    r[9] = n.x; r[10] = n.y; r[11] = n.z;
+    r[21] = 1 / prim_area(sc, prim);
+}
+
+// sample_on_light -> sample_on_shape_op (light.cpp:50-56, shape.cpp:125-169)
+__device__ __forceinline__ void sample_on_light(const DevScene &sc, int light_id, int prim, D3 ref_pos, Rng &rng, D3 &pos, D3 &nrm) {
+#if TAKE_LIGHT_RECS
+    // 128-bit loads, consumed in stages (position first, then the normals) so that the record never sits in registers whole
+    const double2 *R = reinterpret_cast<const double2 *>(sc.light_recs + (int64_t)light_id * TAKE_LIGHT_REC_STRIDE);
+    const uint32_t flags = (uint32_t)__double_as_longlong(__ldg(R + 11).x);
+    const double2 q0 = __ldg(R), q1 = __ldg(R + 1);
+    if (flags & TAKE_PRIM_SPHERE) {  // shape.cpp:125-144
+        D3 c = mk3(q0.x, q0.y, q1.x);
+        double u1 = rng.next();
+        double u2 = rng.next();
+        double r = q1.y;
+        double d = length(sub(c, ref_pos));
+        double z = 1 + u1 * (r / d - 1);
+        double z2 = z * z;
+        double sin_theta = sqrt(clampd(1 - z2, 0, 1));
+        D3 local_p = normalize(mk3(cos(2 * TAKE_PI * u2) * sin_theta, sin(2 * TAKE_PI * u2) * sin_theta, z));
+        nrm = normalize(to_world(normalize(sub(ref_pos, c)), local_p));
+        pos = add(c, mul(nrm, r));
+        return;
+    }
+    double u1 = rng.next();  // shape.cpp:146-169
+    double u2 = rng.next();
+    double b1 = 1 - sqrt(u1);
+    double b2 = sqrt(u1) * u2;
+    double b0 = 1 - b1 - b2;
+    const double2 q2 = __ldg(R + 2), q3 = __ldg(R + 3), q4 = __ldg(R + 4);
+    const D3 v0 = mk3(q0.x, q0.y, q1.x), v1 = mk3(q1.y, q2.x, q2.y), v2 = mk3(q3.x, q3.y, q4.x);
+    pos = add(add(mul(v0, b0), mul(v1, b1)), mul(v2, b2));
+    const double2 q5 = __ldg(R + 5), q6 = __ldg(R + 6), q7 = __ldg(R + 7), q8 = __ldg(R + 8), q9 = __ldg(R + 9), q10 = __ldg(R + 10);
+    const D3 n = mk3(q4.y, q5.x, q5.y);
+    const D3 n0 = mk3(q6.x, q6.y, q7.x), n1 = mk3(q7.y, q8.x, q8.y), n2 = mk3(q9.x, q9.y, q10.x);
+    D3 sn = add(add(mul(n0, b0), mul(n1, b1)), mul(n2, b2));
+    nrm = dot(sn, n) > 0 ? n : neg(n);
+#else
     const int32_t *id = sc.indices + 3 * (int64_t)prim;
     if (sc.prim_flags[prim] & TAKE_PRIM_SPHERE) {  // shape.cpp:125-144
         const double *s = sc.spheres + 4 * (int64_t)id[0];
@@ -477,11 +564,21 @@ __device__ __forceinline__ void sample_on_prim(const DevScene &sc, int prim, D3 
     D3 n = normalize(cross(sub(v1, v0), sub(v2, v0)));
     D3 sn = add(add(mul(ld3(sc.normals + 3 * i0), b0), mul(ld3(sc.normals + 3 * i1), b1)), mul(ld3(sc.normals + 3 * i2), b2));
     nrm = dot(sn, n) > 0 ? n : neg(n);
+#endif
 }
 
 __device__ __forceinline__ double light_pdf_area(const DevScene &sc, int light_id, D3 light_pos, D3 ref_pos) {  // light.cpp:32-48
     const TakeLightDesc &l = sc.lights[light_id];
     if (l.kind != TAKE_LIGHT_AREA) return 0;
+#if TAKE_LIGHT_RECS
+    const double *r = sc.light_recs + (int64_t)light_id * TAKE_LIGHT_REC_STRIDE;
+    if ((uint32_t)__double_as_longlong(__ldg(r + 22)) & TAKE_PRIM_SPHERE) {
+        double rad = __ldg(r + 3);
+        double d = length(sub(light_pos, ref_pos));
+        return 1 / (TAKE_TWOPI * rad * rad * (1 - rad / d));
+    }
+    return __ldg(r + 21);
+#else
     const int prim = l.prim_id;
     if (sc.prim_flags[prim] & TAKE_PRIM_SPHERE) {
         double r = sc.spheres[4 * (int64_t)sc.indices[3 * (int64_t)prim] + 3];
@@ -489,6 +586,7 @@ __device__ __forceinline__ double light_pdf_area(const DevScene &sc, int light_i
         return 1 / (TAKE_TWOPI * r * r * (1 - r / d));
     }
     return 1 / prim_area(sc, prim);
+#endif
 }
 
 __device__ __forceinline__ D3 light_intensity(const TakeLightDesc &l) { return mk3(l.intensity[0], l.intensity[1], l.intensity[2]); }

@@ -69,7 +69,7 @@ struct TakeScene {
     // scene storage
     DeviceBuffer env_rgb, env_marg, env_cond;
     DeviceBuffer nodes, wide_nodes, tris, ref_nodes, positions, normals, uvs, indices, prim_material, prim_light, dfs_rank, prim_flags,
-        prim_mtype, spheres, materials, lights, textures, shade_recs;
+        prim_mtype, spheres, materials, lights, textures, shade_recs, light_recs;
     std::vector<DeviceBuffer *> tex_data;
     DeviceBuffer exr_packed;
     // wave storage
@@ -655,8 +655,15 @@ static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild &hb, 
         if (n > 0) {
             k_build_shade_recs<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(v, s->shade_recs.as<double>());
             CU(cudaGetLastError());
-            CU(cudaStreamSynchronize(st));
         }
+        // per-light records (shading.cuh: LightRec)
+        CU(s->light_recs.ensure(std::max<size_t>((size_t)d->num_lights * TAKE_LIGHT_REC_STRIDE * sizeof(double), 256)));
+        v.light_recs = s->light_recs.as<double>();
+        if (d->num_lights > 0) {
+            k_build_light_recs<<<(unsigned)((d->num_lights + 127) / 128), 128, 0, st>>>(v, s->light_recs.as<double>());
+            CU(cudaGetLastError());
+        }
+        CU(cudaStreamSynchronize(st));
     }
 
     // persistent-kernel launch widths: every SM filled to the occupancy the kernel allows

@@ -412,7 +412,7 @@ struct ShadeCtx {
 __device__ __forceinline__ bool nee_sample(const DevScene &sc, const TakeLightDesc &l, int light_id, const Isect &v, Rng &rng,
                                            D3 &light_dir, double &dist, double &lpdf) {
     D3 lp, ln;
-    sample_on_prim(sc, l.prim_id, v.pos, rng, lp, ln);
+    sample_on_light(sc, light_id, l.prim_id, v.pos, rng, lp, ln);
     dist = length(sub(lp, v.pos));
     light_dir = normalize(sub(lp, v.pos));
     lpdf = light_pdf_area(sc, light_id, lp, v.pos) * (dist * dist) / (fmax(dot(neg(ln), light_dir), 0.0) * sc.pick_count);
@@ -441,7 +441,7 @@ __device__ __forceinline__ void shade_mis(ShadeCtx &c, const RayRec &ray, const 
     Isect v;
     if (path.flags == PEND_PRIMARY) {
         if (hit.prim < 0) { c.rad = miss_rad<ENV>(sc, d); return; }  // :8
-        fill_isect(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
+        fill_isect<ENV>(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
         if (v.light != -1 && sc.lights[v.light].kind == TAKE_LIGHT_AREA)  // :14-18
             c.rad = add(c.rad, mulv(c.thr, light_intensity(sc.lights[v.light])));
     } else {
@@ -459,7 +459,7 @@ __device__ __forceinline__ void shade_mis(ShadeCtx &c, const RayRec &ray, const 
             c.rad = add(c.rad, mulv(c.thr, miss_rad<ENV>(sc, d)));
             return;
         }
-        fill_isect(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
+        fill_isect<ENV>(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
         if (v.light != -1) {  // :88-101
             double lpdf;
             if (!hit_light_pdf(sc, v, o, lpdf)) return;
@@ -535,7 +535,7 @@ __device__ __forceinline__ void shade_raw(ShadeCtx &c, const RayRec &ray, const 
         return;
     }
     Isect v;
-    fill_isect(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
+    fill_isect<ENV>(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
     if (c.depth > c.w.max_depth) return;
     if (v.light != -1) {  // :123-129
         if (sc.lights[v.light].kind == TAKE_LIGHT_AREA) c.rad = add(c.rad, mulv(c.thr, light_intensity(sc.lights[v.light])));
@@ -568,7 +568,7 @@ __device__ __forceinline__ void shade_one_sample(ShadeCtx &c, const RayRec &ray,
     Isect v;
     if (path.flags == PEND_PRIMARY) {
         if (hit.prim < 0) { c.rad = miss_rad<ENV>(sc, d); return; }
-        fill_isect(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
+        fill_isect<ENV>(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
     } else if (path.flags & PEND_LIGHT) {
         if (ENV && hit.prim < 0 && (path.flags & PEND_ENV)) {  // EXTENSION: reached the environment we aimed at
             c.rad = add(c.rad, mulv(c.thr, env_radiance(sc, d)));
@@ -579,7 +579,7 @@ __device__ __forceinline__ void shade_one_sample(ShadeCtx &c, const RayRec &ray,
             atomicAdd(&c.w.totals->miss_after_light_sample, 1ULL);
             return;
         }
-        fill_isect(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
+        fill_isect<ENV>(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
     } else {
         const D3 FG = mk3(pend.fg[0], pend.fg[1], pend.fg[2]);
         const bool spec = (path.flags & PEND_SPECULAR) != 0;
@@ -590,7 +590,7 @@ __device__ __forceinline__ void shade_one_sample(ShadeCtx &c, const RayRec &ray,
             c.rad = add(c.rad, mulv(c.thr, miss_rad<ENV>(sc, d)));
             return;
         }
-        fill_isect(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
+        fill_isect<ENV>(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
         if (!spec && v.light != -1) {  // :253-265
             double lpdf;
             if (!hit_light_pdf(sc, v, o, lpdf)) return;

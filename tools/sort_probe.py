@@ -47,3 +47,13 @@ for grid in (16, 64):
 r = np.arange(len(rays))
 sec = rays
 run(r, "primary rays, pixel order")
+# ---- does grouping rays of similar LENGTH help?  (stable sorts: pixel order survives inside a class) ----
+sec = np.empty((len(o), 8)); sec[:, 0:3] = o; sec[:, 3:6] = d; sec[:, 6] = 1e-7; sec[:, 7] = np.inf
+p2, t2, _ = gs.intersect(sec)
+tt = np.where(p2 >= 0, t2, 1e30)
+for bins in (4, 16):
+    cls = np.minimum((sec[:, 4] * bins).astype(np.int64), bins - 1)       # elevation of the direction (a predictor known at shade time)
+    run(np.argsort(cls, kind="stable"), f"elevation classes x{bins}, pixel order inside")
+q = np.quantile(tt[tt < 1e30], np.linspace(0, 1, 9)[1:-1]) if (tt < 1e30).any() else []
+cls = np.searchsorted(q, tt)                                              # the hit distance itself (an oracle predictor: upper bound on the gain)
+run(np.argsort(cls, kind="stable"), "hit-distance octiles (oracle), pixel order inside")
