@@ -21,10 +21,11 @@ struct __align__(16) HitRec {  // 32 B
     uint32_t keyrank;  // sort key (TAKE_KEY_BITS) | rank inside the key's bin (the remaining low bits)
     double t, u, v;
 };
-struct __align__(16) PathRec {  // 64 B
-    double thr[3], rad[3];
+struct __align__(16) PathRec {  // 64 B = two sectors: the radiance sector is all that k_shadow, k_accumulate and a finished path touch
+    double rad[3];
     uint32_t k;      // random_real draws consumed so far
     int32_t depth;   // index of the next integrator loop iteration
+    double thr[3];
     int32_t flags;   // PEND_* describing the extend ray in flight
     int32_t pad;
 };
@@ -321,11 +322,11 @@ __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_extend(DevScene sc,
                 // line of the other two integrators).  Finishing it here keeps it out of the sort and the shade pass --
                 // on an open scene most camera rays end this way, and streaming their records through two more kernels
                 // was the larger part of the pass-0 shade time.
-                PathRec p;
-                p.thr[0] = p.thr[1] = p.thr[2] = 1.0;
-                p.rad[0] = sc.background.x; p.rad[1] = sc.background.y; p.rad[2] = sc.background.z;
-                p.k = 2; p.depth = 0; p.flags = 0; p.pad = 0;
-                st_stream(w.path + slot, p);
+                // (only the radiance sector of the record: nothing reads the rest of a finished path)
+                int4 *ps = reinterpret_cast<int4 *>(w.path + slot);
+                __stcs(ps, make_int4(__double2loint(sc.background.x), __double2hiint(sc.background.x), __double2loint(sc.background.y),
+                                     __double2hiint(sc.background.y)));
+                __stcs(ps + 1, make_int4(__double2loint(sc.background.z), __double2hiint(sc.background.z), 2, 0));
             } else {
                 rec = true;
                 if (primary && w.sort_branch) {  // the coin of the first vertex: draw number 2 of the sample's stream
