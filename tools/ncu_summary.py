@@ -119,6 +119,6 @@ if "extend" in res:
     total = sum(r["dram_read_MB"] + r["dram_write_MB"] for r in rows) * 1e6
     json.dump({"kernel": "k_extend", "dram_bytes_per_launch": total / len(rows), "launches_captured": len(rows),
                "dram_bytes_per_wave": total,
-               "note": "ncu --set full capture of tools/prof_run.py: the 7 k_extend launches of one 16.6 M-slot wave "
-                       f"(8 spp x 1920x1080, config 2); per-launch rows in {tag}_ncu_extend.csv"},
+               "note": "ncu --set full capture of tools/prof_run.py: the 7 k_extend launches of one 33.2 M-slot wave "
+                       f"(16 spp x 1920x1080, config 2); per-launch rows in {tag}_ncu_extend.csv"},
               open(os.path.join(OUT, "extend_traffic.json"), "w"), indent=1)

@@ -24,7 +24,7 @@ L = ["# profiles/ — round 1\n",
      "| file | what |\n|---|---|",
      "| `r01_bench_n1.json`, `r01_bench_reference_n1.json` | the `bench.py` line (ours) and the reference arm, same box, same run |",
      "| `r01_launches_bench.csv`, `r01_launches_bench_summary.csv` | `ncu --metrics gpu__time_duration.sum` launch list of `bench.py --steps 2 --warmup 3 --no-cpu-baseline` (first 300 launches) and its per-kernel totals |",
-     "| `r01_ncu_extend.csv`, `r01_ncu_shade.csv`, `r01_ncu_shadow.csv` | key metrics of `ncu --set full` captures of `tools/prof_run.py` (one bench-sized wave: 8 spp, 16.6 M slots) |",
+     "| `r01_ncu_extend.csv`, `r01_ncu_shade.csv`, `r01_ncu_shadow.csv` | key metrics of `ncu --set full` captures of `tools/prof_run.py` (one bench-sized wave: 16 spp x 1920x1080 = 33.2 M slots) |",
      "| `extend_traffic.json` | DRAM bytes per `k_extend` launch (mean over the 7 launches of that wave) — `roofline.traffic` in bench.py |",
      "| `r01_prof_run_counts.txt` | box / leaf test counts of the same wave (instrumented kernels) |",
      "| `r01_report_scenes.jsonl` | throughput of all five BASELINE configs next to the CPU renderer (tools/report_scenes.py) |",
@@ -37,7 +37,7 @@ for r in list(csv.DictReader(open(P("r01_launches_bench_summary.csv"))))[:4]:
     key = [v for k, v in m.items() if k in r["kernel"]][0]
     L.append(f"| `{r['kernel'].strip()}` | {r['launches']} | {float(r['share_pct']):.1f} % | {100 * ss[key]:.1f} % |")
 L += ["\nThe dominant kernel is `k_extend` (4-wide BVH traversal + FP64 leaf tests) in both views.\n",
-      "## `k_extend<false, true>` — the 7 launches of one wave (pass 0 = 16.6 M camera rays, then the bounce passes)\n", HDR]
+      "## `k_extend<false, true>` — the 7 launches of one wave (pass 0 = 33.2 M camera rays, then the bounce passes)\n", HDR]
 L += [row(r, str(i)) for i, r in enumerate(ext)]
 L += ["\n## `k_shade<one_sample_mis, no env>` — passes 0..2\n", HDR] + [row(r, str(i)) for i, r in enumerate(sh)]
 L += ["\n## `k_shadow<false, true>` (multi-sample MIS wave) — passes 0..1\n", HDR] + [row(r, str(i)) for i, r in enumerate(sw)]
@@ -45,7 +45,7 @@ r = b["roofline"]
 L.append(f"""
 ## Reading
 
-* `k_extend` is **not HBM-bound**: {ext[0]['dram_GBps']} GB/s of DRAM traffic on camera rays (7 % of the measured 6 553 GB/s copy
+* `k_extend` is **not HBM-bound**: {ext[0]['dram_GBps']} GB/s of DRAM traffic on camera rays ({100 * float(ext[0]['dram_GBps']) / 6553:.0f} % of the measured 6 553 GB/s copy
   bandwidth) and {ext[0].get('l2_GBps')} GB/s from L2; measured DRAM traffic per launch ({tr['dram_bytes_per_launch'] / 1e6:.0f} MB) is
   {r['bytes_per_launch'] / tr['dram_bytes_per_launch']:.1f}x *below* the algorithmic bytes ({r['bytes_per_launch'] / 1e6:.0f} MB per launch by the SURVEY.md 8(d)
   counting rule) because the 130 MB of tree and leaf records live in L1/L2.  `roofline.achieved` = algorithmic bytes /
@@ -56,6 +56,7 @@ L.append(f"""
 * Ray-box / ray-triangle test rate against FP32 peak: {r['box_tests_per_ray']:.1f} box + {r['tri_tests_per_ray']:.2f} leaf tests per ray at
   {r['extend_grays_per_s']:.2f} Grays/s = {r['test_rate_tflops']:.2f} TFLOP/s by the 27 / 60 flop counting rule = {100 * r['test_rate_frac_fp32']:.1f} % of the
   {r['fp32_peak_tflops']:.1f} TFLOP/s FP32 peak (the leaf tests actually run in FP64).
-* `k_shade` moves 1.4-2.3 TB/s through DRAM (21-36 % of peak) at 25 % occupancy (128 registers of FP64 state).
+* `k_shade` moves {min(float(x['dram_GBps']) for x in sh) / 1e3:.1f}-{max(float(x['dram_GBps']) for x in sh) / 1e3:.1f} TB/s through DRAM ({100 * min(float(x['dram_GBps']) for x in sh) / 6553:.0f}-{100 * max(float(x['dram_GBps']) for x in sh) / 6553:.0f} % of peak) at 25 % occupancy (128 registers of FP64 state);
+  its top stalls are `long_scoreboard` (gathered records) and instruction-cache misses -- latency-bound, not bandwidth-bound.
 """)
 open(P("README.md"), "w").write("\n".join(L))

@@ -12,8 +12,8 @@ sec = f"""
 
 | quantity | value |
 |---|---|
-| `value` — whole pipeline, buffers resident in HBM | **{b['value']:.0f} Mrays/s**, {b['samples_per_s']/1e6:.0f} M path samples/s, {b['ms_per_step']:.2f} ms per 16-spp step |
-| `e2e` — `take_gpu_render()` with pinned host buffers (99.5 MB device→host per step) | {b['e2e']['value']:.0f} Mrays/s |
+| `value` — whole pipeline, buffers resident in HBM | **{b['value']:.0f} Mrays/s**, {b['samples_per_s']/1e6:.0f} M path samples/s, {b['ms_per_step']:.2f} ms per {b['config']['spp_per_step_per_gpu']}-spp step |
+| `e2e` — `take_gpu_render_async` / `_wait` with pinned host buffers (99.5 MB device→host per step, overlapped with the next step) | {b['e2e']['value']:.0f} Mrays/s (blocking `take_gpu_render`: {b['e2e']['blocking_call_mrays_per_s']:.0f}) |
 | `k_extend` alone | **{r['extend_grays_per_s']:.2f} Grays/s** (north-star target: ≥ 1 Grays/s on this scene) |
 | `roofline` — algorithmic bytes / launch time vs. measured HBM {r['peak']:.0f} GB/s | {r['achieved']:.0f} GB/s = {r['frac']:.2f}; measured DRAM traffic per launch {r['traffic']/1e6:.0f} MB vs {r['bytes_per_launch']/1e6:.0f} MB algorithmic (caches absorb the rest) |
 | box / leaf tests per ray (4-wide tree) | {r['box_tests_per_ray']:.1f} / {r['tri_tests_per_ray']:.2f} (reference tree and order: 224 / 6.7) |
@@ -37,7 +37,7 @@ scale = [json.load(open(P(f"r01_scale_n{n}.json"))) for n in (1, 2, 4, 8) if os.
 if scale:
     base = scale[0]["value"]
     sec += ("\nMulti-GPU (weak scaling, one process per GPU, one NCCL all-reduce inside the timed region; `profiles/r01_scale_n*.json`):\n\n"
-            "| GPUs | Mrays/s | M path samples/s | ms per step (16 spp per GPU) | efficiency vs N=1 |\n|---|---|---|---|---|\n")
+            "| GPUs | Mrays/s | M path samples/s | ms per step ({scale[0]['config']['spp_per_step_per_gpu']} spp per GPU) | efficiency vs N=1 |\n|---|---|---|---|---|\n")
     for x in scale:
         sec += f"| {x['n_gpus']} | {x['value']:.0f} | {x['samples_per_s']/1e6:.0f} | {x['ms_per_step']:.2f} | {100*x['value']/(base*x['n_gpus']):.1f} % |\n"
     sec += ("\n(8×B200 box of the same pool; every rank renders its own sample range of every step, the two 49.8 MB buffers are\n"
