@@ -25,9 +25,6 @@ namespace take {
 #define TAKE_PUSH_ALWAYS 0
 #endif
 #define TAKE_STACK_SMEM_ALLOC (TAKE_STACK_SMEM > 0 ? TAKE_STACK_SMEM : 1)
-#ifndef TAKE_NEARFAR
-#define TAKE_NEARFAR 0
-#endif
 
 // (256-bit read-only loads ldg_f8 / ldg_d4: device_common.cuh)
 
@@ -321,42 +318,12 @@ __device__ __forceinline__ void trace_fast4(const DevScene &sc, D3 o, D3 d, doub
     const float tmin_f = __double2float_rd(tmin);
     float tbest_f = __double2float_ru(tmax);
     double best_t = tmax;
-#if TAKE_NEARFAR
-    // The sign of the direction says which plane of a slab is entered first, so the near and far planes of the four
-    // children are fetched from swapped addresses instead of being sorted with min/max per child and axis (24 FMNMX per
-    // node less).  Near distances use the offset that rounds them down, far distances the one that rounds them up (the
-    // same two offsets as below, swapped with the planes), so the test stays conservative.
-    const int sx = idx < 0.0f ? 1 : 0, sy = idy < 0.0f ? 1 : 0, sz = idz < 0.0f ? 1 : 0;
-    const float onx = sx ? ohx : olx, ofx = sx ? olx : ohx;
-    const float ony = sy ? ohy : oly, ofy = sy ? oly : ohy;
-    const float onz = sz ? ohz : olz, ofz = sz ? olz : ohz;
-#endif
 
     st.sp = 0;
     int32_t node = 0;  // root
     for (;;) {
         while (node >= 0) {
             const float4 *N = sc.wide_nodes + 8 * (int64_t)node;
-#if TAKE_NEARFAR
-            const float4 nrx = __ldg(N + sx), frx = __ldg(N + (sx ^ 1));
-            const float4 nry = __ldg(N + 2 + sy), fry = __ldg(N + 2 + (sy ^ 1));
-            const float4 nrz = __ldg(N + 4 + sz), frz = __ldg(N + 4 + (sz ^ 1));
-            const int4 ch = __ldg((const int4 *)(N + 6));
-            if (COUNT) cnt->box += 4;
-            uint32_t key[4];
-#define TAKE_WIDE_CHILD(K, NX, FX, NY, FY, NZ, FZ, C)                                            \
-            {                                                                                      \
-                float tn = fmaxf(fmaxf(fmaf(NX, idx, onx), fmaf(NY, idy, ony)), fmaxf(fmaf(NZ, idz, onz), tmin_f)); \
-                float tf = fminf(fminf(fmaf(FX, idx, ofx), fmaf(FY, idy, ofy)), fminf(fmaf(FZ, idz, ofz), tbest_f)); \
-                const bool h = (tn <= tf * TAKE_SLACK) && (C != TAKE_WIDE_EMPTY);                  \
-                key[K] = h ? ((__float_as_uint(tn) & 0xfffffffcu) | (uint32_t)K) : 0xffffffffu;    \
-            }
-            TAKE_WIDE_CHILD(0, nrx.x, frx.x, nry.x, fry.x, nrz.x, frz.x, ch.x)
-            TAKE_WIDE_CHILD(1, nrx.y, frx.y, nry.y, fry.y, nrz.y, frz.y, ch.y)
-            TAKE_WIDE_CHILD(2, nrx.z, frx.z, nry.z, fry.z, nrz.z, frz.z, ch.z)
-            TAKE_WIDE_CHILD(3, nrx.w, frx.w, nry.w, fry.w, nrz.w, frz.w, ch.w)
-#undef TAKE_WIDE_CHILD
-#else
             const F8 nx = ldg_f8(N), ny = ldg_f8(N + 2), nz = ldg_f8(N + 4);
             const float4 lox = nx.a, hix = nx.b, loy = ny.a, hiy = ny.b, loz = nz.a, hiz = nz.b;
             const int4 ch = __ldg((const int4 *)(N + 6));
@@ -379,7 +346,6 @@ __device__ __forceinline__ void trace_fast4(const DevScene &sc, D3 o, D3 d, doub
             TAKE_WIDE_CHILD(2, lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, ch.z)
             TAKE_WIDE_CHILD(3, lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, ch.w)
 #undef TAKE_WIDE_CHILD
-#endif
             // sort the four keys ascending: misses (0xffffffff) sink to the end, hits come out near-to-far
             cswap(key[0], key[1]); cswap(key[2], key[3]); cswap(key[0], key[2]); cswap(key[1], key[3]); cswap(key[1], key[2]);
             // child link of the slot in a key's low two bits: three selects, no branches
