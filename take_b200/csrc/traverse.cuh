@@ -25,6 +25,9 @@ namespace take {
 #define TAKE_PUSH_ALWAYS 0
 #endif
 #define TAKE_STACK_SMEM_ALLOC (TAKE_STACK_SMEM > 0 ? TAKE_STACK_SMEM : 1)
+#ifndef TAKE_ANYHIT_UNSORTED
+#define TAKE_ANYHIT_UNSORTED 1
+#endif
 
 // (256-bit read-only loads ldg_f8 / ldg_d4: device_common.cuh)
 
@@ -346,8 +349,12 @@ __device__ __forceinline__ void trace_fast4(const DevScene &sc, D3 o, D3 d, doub
             TAKE_WIDE_CHILD(2, lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, ch.z)
             TAKE_WIDE_CHILD(3, lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, ch.w)
 #undef TAKE_WIDE_CHILD
-            // sort the four keys ascending: misses (0xffffffff) sink to the end, hits come out near-to-far
-            cswap(key[0], key[1]); cswap(key[2], key[3]); cswap(key[0], key[2]); cswap(key[1], key[3]); cswap(key[1], key[2]);
+            // sort the four keys ascending: misses (0xffffffff) sink to the end, hits come out near-to-far.  An any-hit
+            // query has no use for the order (TAKE_ANYHIT_UNSORTED): its window never shrinks, so every child the ray
+            // overlaps is visited unless an occluder ends the search, whichever comes first.
+            if (!(ANY_HIT && TAKE_ANYHIT_UNSORTED)) {
+                cswap(key[0], key[1]); cswap(key[2], key[3]); cswap(key[0], key[2]); cswap(key[1], key[3]); cswap(key[1], key[2]);
+            }
             // child link of the slot in a key's low two bits: three selects, no branches
 #define TAKE_WIDE_PICK(KEY) (((KEY) & 2u) ? (((KEY) & 1u) ? ch.w : ch.z) : (((KEY) & 1u) ? ch.y : ch.x))
 #if TAKE_PUSH_ALWAYS
@@ -366,7 +373,7 @@ __device__ __forceinline__ void trace_fast4(const DevScene &sc, D3 o, D3 d, doub
                     if (st.sp == 0) return;
                     float tn;
                     st.pop(node, tn);
-                    if (tn <= tbest_f * TAKE_SLACK) break;
+                    if ((ANY_HIT && TAKE_ANYHIT_UNSORTED) || tn <= tbest_f * TAKE_SLACK) break;
                 }
             }
 #undef TAKE_WIDE_PICK
@@ -403,7 +410,7 @@ __device__ __forceinline__ void trace_fast4(const DevScene &sc, D3 o, D3 d, doub
             if (st.sp == 0) return;
             float tn;
             st.pop(node, tn);
-            if (tn <= tbest_f * TAKE_SLACK) break;
+            if ((ANY_HIT && TAKE_ANYHIT_UNSORTED) || tn <= tbest_f * TAKE_SLACK) break;
         }
     }
 }
