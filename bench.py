@@ -164,7 +164,7 @@ def run_reference_arm(args):
     value = n_total * rps / t_total / 1e6
     sample = (f"each step: 1 spp of every {row_step}-th row of the 1920x1080 frame ({n_total // max(1, args.steps)} path samples), "
               f"{rps:.3f} rays/sample")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -173,7 +173,7 @@ def run_reference_arm(args):
                    "triangles": flat.num_prims},
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cpu.cores, "kind": cpu.kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -260,11 +260,6 @@ def run_ours(args):
     rays_all, samples_all, launches_all = (float(v) for v in agg.tolist())
     mean_check = float((d_sum / (S * args.steps * world)).mean().item())
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
     # ---- e2e: the C-ABI calls a host application makes (host buffers, D2H of every step's result inside the timed region) ----
     # take_gpu_render_async + take_gpu_render_wait with two pinned result buffers: the read-back of step k overlaps the
     # kernels of step k+1; every step's sums are complete on the host when its wait returns, inside the timed region.
@@ -285,11 +280,21 @@ def run_ours(args):
         return rays
 
     host_steps(2)                      # both result slots allocated and warm
-    torch.cuda.synchronize()
+    barrier()                          # every rank runs its own host loop, all at the same time
     t0 = time.perf_counter()
     o_rays = host_steps(e2e_steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    if world > 1:                      # whole job: rays of all ranks / the slowest rank's time
+        t_max = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        r_sum = torch.tensor([float(o_rays)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+        dist.all_reduce(r_sum)
+        e2e_s, o_rays = float(t_max.item()), float(r_sum.item())
+    if rank != 0:
+        gs.close()
+        dist.destroy_process_group()
+        return
     # the blocking call, for comparison (copy not overlapped)
     st = api.TakeStats()
     o = api.TakeRenderOpts(api.INTEGRATORS[INTEGRATOR], MAX_DEPTH, 0, S, SEED, 0, 0)
@@ -300,7 +305,7 @@ def run_ours(args):
     blocking_s = time.perf_counter() - t1
     e2e = {"value": o_rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": C.sizeof(api.TakeRenderOpts),
            "d2h_bytes_per_step": int(h_bufs[0][0].nbytes + h_bufs[0][1].nbytes), "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-           "api": "take_gpu_render_async + take_gpu_render_wait, two pinned host buffers",
+           "api": "take_gpu_render_async + take_gpu_render_wait, two pinned host buffers per rank; whole job = rays of all ranks / slowest rank",
            "blocking_call_mrays_per_s": (st.extend_rays + st.shadow_rays) / blocking_s / 1e6,
            "note": "camera rays are generated on the device (replaces render.cpp:69-75), so the per-step host input is the "
                    "options struct; the scene is uploaded once by take_gpu_scene_create "
@@ -359,13 +364,36 @@ def run_ours(args):
         "e2e": e2e, "gpu_launches": int(launches_all), "clocks": clock_info, "roofline": roofline, "cpu_baseline": base,
         "rays_per_sample": rays_all / max(1.0, samples_all), "image_mean": mean_check, "scene_create_ms": scene_create_ms,
     }
-    print(json.dumps(line))
+    emit(line)
     gs.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries underneath print there on their own (NCCL's version banner comes
+    from C code, past sys.stdout), so file descriptor 1 is pointed at stderr for the whole run and the line is written to
+    the saved descriptor at the end."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
