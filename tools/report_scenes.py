@@ -17,6 +17,9 @@ only = [a for a in sys.argv[1:] if not a.startswith("-")]
 cores = os.cpu_count()
 O = ob.OracleLib()
 R = ob.RefLib() if ob.have_ref() else None
+_warm = api.GpuScene(scenes.cornell_box(width=32, height=32).flat())   # CUDA context + module load happen here, not in the first timing
+_warm.render_sums("mis", 2, 0, 1, seed=1, sumsq=False)
+_warm.close()
 for name, make, integ, spp in CONFIGS:
     if only and not any(o in name for o in only):
         continue

@@ -37,11 +37,13 @@ scale = [json.load(open(P(f"r01_scale_n{n}.json"))) for n in (1, 2, 4, 8) if os.
 if scale:
     base = scale[0]["value"]
     sec += ("\nMulti-GPU (weak scaling, one process per GPU, one NCCL all-reduce inside the timed region; `profiles/r01_scale_n*.json`):\n\n"
-            "| GPUs | Mrays/s | M path samples/s | ms per step ({scale[0]['config']['spp_per_step_per_gpu']} spp per GPU) | efficiency vs N=1 |\n|---|---|---|---|---|\n")
+            f"| GPUs | Mrays/s | e2e Mrays/s | M path samples/s | ms per step ({scale[0]['config']['spp_per_step_per_gpu']} spp per GPU) | efficiency vs N=1 |\n|---|---|---|---|---|---|\n")
     for x in scale:
-        sec += f"| {x['n_gpus']} | {x['value']:.0f} | {x['samples_per_s']/1e6:.0f} | {x['ms_per_step']:.2f} | {100*x['value']/(base*x['n_gpus']):.1f} % |\n"
+        sec += f"| {x['n_gpus']} | {x['value']:.0f} | {x['e2e']['value']:.0f} | {x['samples_per_s']/1e6:.0f} | {x['ms_per_step']:.2f} | {100*x['value']/(base*x['n_gpus']):.1f} % |\n"
     sec += ("\n(8×B200 box of the same pool; every rank renders its own sample range of every step, the two 49.8 MB buffers are\n"
-            "all-reduced once at the end; `take_gpu_render_multi` was checked against the single-GPU image on the same box.)\n")
+            "all-reduced once at the end; `e2e` = every rank's host loop at once, each reading 99.5 MB per step back into its own\n"
+            "pinned buffers -- the rays of all ranks over the slowest rank's time; `take_gpu_render_multi` was checked against the\n"
+            "single-GPU image on a 2-GPU box.)\n")
 sec += ("\n`compute-sanitizer` is closed on this pool (gpurun refuses it), so memory safety rests on the parity suite, the\n"
         "host-side validation of every index array in `take_gpu_scene_create`, and `tools/sanitize_run.py` (every kernel on\n"
         "tiny waves and chunked images) running clean.\n")
