@@ -3,6 +3,8 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <stdio.h>
+#include <time.h>
 
 #include <algorithm>
 #include <atomic>
@@ -111,18 +113,52 @@ inline double half_area(const double *lo, const double *hi) {
     return dx * dy + dy * dz + dz * dx;
 }
 
+// One primitive as the builder moves it around: its box and id side by side (64 bytes), so that every pass over a range
+// streams memory instead of gathering 48-byte boxes through an index array.
+struct alignas(64) PrimRef {
+    Aabb box;
+    int64_t id;
+    int64_t pad;
+};
+static_assert(sizeof(PrimRef) == 64, "PrimRef");
+
+struct Bounds {  // box of a primitive set and box of its centroids
+    Aabb bb, cb;
+    void clear() {
+        for (int a = 0; a < 3; ++a) { bb.lo[a] = cb.lo[a] = INFINITY; bb.hi[a] = cb.hi[a] = -INFINITY; }
+    }
+    void add(const Aabb &b) {
+        for (int a = 0; a < 3; ++a) {
+            bb.lo[a] = std::min(bb.lo[a], b.lo[a]);
+            bb.hi[a] = std::max(bb.hi[a], b.hi[a]);
+            const double c = 0.5 * (b.lo[a] + b.hi[a]);
+            cb.lo[a] = std::min(cb.lo[a], c);
+            cb.hi[a] = std::max(cb.hi[a], c);
+        }
+    }
+    void merge(const Bounds &o) {
+        for (int a = 0; a < 3; ++a) {
+            bb.lo[a] = std::min(bb.lo[a], o.bb.lo[a]); bb.hi[a] = std::max(bb.hi[a], o.bb.hi[a]);
+            cb.lo[a] = std::min(cb.lo[a], o.cb.lo[a]); cb.hi[a] = std::max(cb.hi[a], o.cb.hi[a]);
+        }
+    }
+};
+
+// Two streaming passes per node: (1) bin the three axes, (2) partition the records in place while accumulating the
+// bounds of the two sides -- so a child starts with its boxes known and never re-reads its range for them.
 struct SahBuilder {
     static const int NBINS = 32;
-    const Aabb *boxes;
-    int32_t *ids;
+    static const int SMALL = 16;  // ranges up to this size take the sparse sweep
+    PrimRef *refs;
+    PrimRef *scratch;  // same length as refs: source of the chunk-parallel partitions near the root
     std::vector<TmpNode> nodes;
     std::atomic<int32_t> next{0};
     int max_leaf;
     double c_trav, c_isect;
     Forker fork;
 
-    SahBuilder(const Aabb *b, int32_t *i, int64_t n, int ml, int threads)
-        : boxes(b), ids(i), nodes((size_t)std::max<int64_t>(2 * n, 2)), max_leaf(ml), c_trav(1.0), c_isect(1.2), fork(threads) {
+    SahBuilder(PrimRef *r, PrimRef *sc, int64_t n, int ml, int threads)
+        : refs(r), scratch(sc), nodes((size_t)std::max<int64_t>(2 * n, 2)), max_leaf(ml), c_trav(1.0), c_isect(1.2), fork(threads) {
         if (const char *e = getenv("TAKE_SAH_CISECT")) c_isect = atof(e);  // tuning knob: cost of a leaf test relative to a node visit
     }
 
@@ -158,38 +194,29 @@ struct SahBuilder {
         }
     };
 
-    void build(int32_t node_id, int64_t lo, int64_t hi) {
+    // bounds of the whole input (the only range whose bounds no parent hands down)
+    Bounds range_bounds(int64_t lo, int64_t hi) {
+        const int parts = (hi - lo) >= (1 << 18) ? std::min<int>(top_threads, (int)((hi - lo) >> 16)) : 1;
+        std::vector<Bounds> pb((size_t)parts);
+        chunked(lo, hi, parts, [&](int tid, int64_t a0, int64_t a1) {
+            Bounds t;
+            t.clear();
+            for (int64_t i = a0; i < a1; ++i) t.add(refs[i].box);
+            pb[tid] = t;
+        });
+        for (int t = 1; t < parts; ++t) pb[0].merge(pb[t]);
+        return pb[0];
+    }
+
+    void build(int32_t node_id, int64_t lo, int64_t hi, const Bounds &bounds) {
         TmpNode &node = nodes[node_id];
-        int64_t m = hi - lo;
+        const int64_t m = hi - lo;
         const int parts = m >= (1 << 18) ? std::min<int>(top_threads, (int)(m >> 16)) : 1;
-        Aabb bb, cb;
-        for (int a = 0; a < 3; ++a) { bb.lo[a] = cb.lo[a] = INFINITY; bb.hi[a] = cb.hi[a] = -INFINITY; }
-        {
-            std::vector<Aabb> pbb(parts, bb), pcb(parts, cb);
-            chunked(lo, hi, parts, [&](int tid, int64_t a0, int64_t a1) {
-                Aabb tb = pbb[tid], tc = pcb[tid];
-                for (int64_t i = a0; i < a1; ++i) {
-                    const Aabb &b = boxes[ids[i]];
-                    for (int a = 0; a < 3; ++a) {
-                        tb.lo[a] = std::min(tb.lo[a], b.lo[a]);
-                        tb.hi[a] = std::max(tb.hi[a], b.hi[a]);
-                        double c = 0.5 * (b.lo[a] + b.hi[a]);
-                        tc.lo[a] = std::min(tc.lo[a], c);
-                        tc.hi[a] = std::max(tc.hi[a], c);
-                    }
-                }
-                pbb[tid] = tb; pcb[tid] = tc;
-            });
-            for (int t = 0; t < parts; ++t)
-                for (int a = 0; a < 3; ++a) {
-                    bb.lo[a] = std::min(bb.lo[a], pbb[t].lo[a]); bb.hi[a] = std::max(bb.hi[a], pbb[t].hi[a]);
-                    cb.lo[a] = std::min(cb.lo[a], pcb[t].lo[a]); cb.hi[a] = std::max(cb.hi[a], pcb[t].hi[a]);
-                }
-        }
+        const Aabb &bb = bounds.bb, &cb = bounds.cb;
         node.box = bb;
         if (m == 1) { make_leaf(node, lo, hi); return; }
 
-        // bin all three axes in one pass (per-thread bins for the huge ranges, merged afterwards)
+        // pass 1: bin all three axes and pick the cheapest split
         double scale3[3];
         bool axis_ok[3];
         for (int x = 0; x < 3; ++x) {
@@ -197,12 +224,50 @@ struct SahBuilder {
             axis_ok[x] = ext > 0;
             scale3[x] = axis_ok[x] ? NBINS / ext : 0.0;
         }
-        std::vector<Bins> pbins(parts);
+        double best_cost = INFINITY;
+        int best_axis = -1, best_bin = -1;
+        const double parent_area = half_area(bb.lo, bb.hi);
+        if (m <= SMALL) {
+            // Most NODES are tiny, and for them clearing, filling and sweeping 3 x 32 dense bins is the whole cost of the
+            // build.  The sweep only changes where a bin is occupied, so a handful of primitives are ordered by bin index
+            // and swept directly: same candidate splits, same boxes, same costs, same choice as the dense sweep below.
+            for (int axis = 0; axis < 3; ++axis) {
+                if (!axis_ok[axis]) continue;
+                int key[SMALL], ord[SMALL];
+                for (int i = 0; i < (int)m; ++i) {
+                    const Aabb &b = refs[lo + i].box;
+                    int k = (int)((0.5 * (b.lo[axis] + b.hi[axis]) - cb.lo[axis]) * scale3[axis]);
+                    key[i] = std::min(std::max(k, 0), NBINS - 1);
+                    int j = i;
+                    while (j > 0 && key[ord[j - 1]] > key[i]) { ord[j] = ord[j - 1]; --j; }
+                    ord[j] = i;
+                }
+                // suffix: box area and count of everything in bins >= key[ord[i]] (valid at the first entry of a bin group)
+                double right_area[SMALL + 1];
+                Aabb acc;
+                for (int a = 0; a < 3; ++a) { acc.lo[a] = INFINITY; acc.hi[a] = -INFINITY; }
+                for (int i = (int)m - 1; i >= 0; --i) {
+                    const Aabb &b = refs[lo + ord[i]].box;
+                    for (int a = 0; a < 3; ++a) { acc.lo[a] = std::min(acc.lo[a], b.lo[a]); acc.hi[a] = std::max(acc.hi[a], b.hi[a]); }
+                    right_area[i] = half_area(acc.lo, acc.hi);
+                }
+                for (int a = 0; a < 3; ++a) { acc.lo[a] = INFINITY; acc.hi[a] = -INFINITY; }
+                for (int i = 0; i < (int)m - 1; ++i) {
+                    const Aabb &b = refs[lo + ord[i]].box;
+                    for (int a = 0; a < 3; ++a) { acc.lo[a] = std::min(acc.lo[a], b.lo[a]); acc.hi[a] = std::max(acc.hi[a], b.hi[a]); }
+                    if (key[ord[i + 1]] == key[ord[i]]) continue;  // inside a bin group: not a split position
+                    const int64_t cl = i + 1, cr = m - cl;
+                    double cost = half_area(acc.lo, acc.hi) * cl + right_area[i + 1] * cr;
+                    if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = key[ord[i]]; }
+                }
+            }
+        } else {
+        std::vector<Bins> pbins((size_t)parts);
         chunked(lo, hi, parts, [&](int tid, int64_t a0, int64_t a1) {
             Bins &B = pbins[tid];
             B.clear();
             for (int64_t i = a0; i < a1; ++i) {
-                const Aabb &b = boxes[ids[i]];
+                const Aabb &b = refs[i].box;
                 for (int x = 0; x < 3; ++x) {
                     if (!axis_ok[x]) continue;
                     int k = (int)((0.5 * (b.lo[x] + b.hi[x]) - cb.lo[x]) * scale3[x]);
@@ -227,9 +292,6 @@ struct SahBuilder {
                 }
 
         // best split over the three axes
-        double best_cost = INFINITY;
-        int best_axis = -1, best_bin = -1;
-        double parent_area = half_area(bb.lo, bb.hi);
         for (int axis = 0; axis < 3; ++axis) {
             if (!axis_ok[axis]) continue;
             const Aabb *bin_box = bins.box[axis];
@@ -261,78 +323,127 @@ struct SahBuilder {
                 if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
             }
         }
+        }
+        // pass 2: partition in place, accumulating the bounds of both sides
         int64_t mid = -1;
+        Bounds bl, br;
+        bl.clear(); br.clear();
         if (best_axis >= 0) {
             double split_cost = c_trav + c_isect * best_cost / (parent_area > 0 ? parent_area : 1.0);
             double leaf_cost = c_isect * (double)m;
             if (m <= max_leaf && leaf_cost <= split_cost) { make_leaf(node, lo, hi); return; }
             double ext = cb.hi[best_axis] - cb.lo[best_axis];
             double scale = NBINS / ext;
-            auto goes_left = [&](int32_t id) {
-                const Aabb &b = boxes[id];
+            auto goes_left = [&](const Aabb &b) {
                 int k = (int)((0.5 * (b.lo[best_axis] + b.hi[best_axis]) - cb.lo[best_axis]) * scale);
                 k = std::min(std::max(k, 0), NBINS - 1);
                 return k <= best_bin;
             };
             if (parts > 1) {
-                // chunk-wise counting partition through a scratch copy (which side a primitive lands on is all that
+                // chunk-wise counting partition through the scratch copy (which side a primitive lands on is all that
                 // matters; the order inside a side only permutes leaf slots)
-                std::vector<int64_t> nleft(parts + 1, 0);
+                std::vector<int64_t> nleft((size_t)parts + 1, 0);
+                std::vector<Bounds> pl((size_t)parts), pr((size_t)parts);
                 chunked(lo, hi, parts, [&](int tid, int64_t a0, int64_t a1) {
                     int64_t c = 0;
-                    for (int64_t i = a0; i < a1; ++i) c += goes_left(ids[i]) ? 1 : 0;
+                    for (int64_t i = a0; i < a1; ++i) {
+                        c += goes_left(refs[i].box) ? 1 : 0;
+                        scratch[i] = refs[i];
+                    }
                     nleft[tid + 1] = c;
                 });
                 for (int t = 0; t < parts; ++t) nleft[t + 1] += nleft[t];
                 const int64_t total_left = nleft[parts];
-                std::vector<int32_t> scratch(ids + lo, ids + hi);
                 chunked(lo, hi, parts, [&](int tid, int64_t a0, int64_t a1) {
                     int64_t l = lo + nleft[tid], r = lo + total_left + (a0 - lo) - nleft[tid];
+                    Bounds tl, tr;
+                    tl.clear(); tr.clear();
                     for (int64_t i = a0; i < a1; ++i) {
-                        const int32_t id = scratch[i - lo];
-                        if (goes_left(id)) ids[l++] = id; else ids[r++] = id;
+                        const PrimRef &p = scratch[i];
+                        if (goes_left(p.box)) { refs[l++] = p; tl.add(p.box); }
+                        else { refs[r++] = p; tr.add(p.box); }
                     }
+                    pl[tid] = tl; pr[tid] = tr;
                 });
+                for (int t = 0; t < parts; ++t) { bl.merge(pl[t]); br.merge(pr[t]); }
                 mid = lo + total_left;
             } else {
-                int32_t *p = std::partition(ids + lo, ids + hi, goes_left);
-                mid = p - ids;
+                // Hoare partition from both ends; every record is inspected exactly once
+                int64_t i = lo, j = hi - 1;
+                for (;;) {
+                    while (i <= j && goes_left(refs[i].box)) { bl.add(refs[i].box); ++i; }
+                    while (i <= j && !goes_left(refs[j].box)) { br.add(refs[j].box); --j; }
+                    if (i >= j) break;
+                    std::swap(refs[i], refs[j]);
+                    bl.add(refs[i].box); br.add(refs[j].box);
+                    ++i; --j;
+                }
+                mid = i;
             }
         }
         if (mid <= lo || mid >= hi) {
             // all centroids coincide (or binning failed): leaf if allowed, otherwise split the range in half
             if (m <= max_leaf) { make_leaf(node, lo, hi); return; }
             mid = lo + m / 2;
+            bl.clear(); br.clear();
+            for (int64_t i = lo; i < mid; ++i) bl.add(refs[i].box);
+            for (int64_t i = mid; i < hi; ++i) br.add(refs[i].box);
         }
         int32_t l = alloc(), r = alloc();
         nodes[node_id].left = l;
         nodes[node_id].right = r;
-        fork.both(m > 32768, [&] { build(l, lo, mid); }, [&] { build(r, mid, hi); });
+        fork.both(m > 32768, [&, bl] { build(l, lo, mid, bl); }, [&, br] { build(r, mid, hi, br); });
     }
 };
 
 // Conservative FP32 image of an FP64 bound: round outward, move out by `pad`, and one more ulp to absorb the
 // rounding of that subtraction / addition.
+// nextafterf(f, +-INFINITY) on the bit pattern (the libm call was a third of the flatten time: ~36 calls per 4-wide node)
+inline float step_up(float f) {
+    if (!(f < INFINITY)) return f;  // +inf, NaN
+    if (f == 0.0f) return 1.401298464324817e-45f;
+    uint32_t b;
+    memcpy(&b, &f, 4);
+    b = f > 0.0f ? b + 1u : b - 1u;
+    memcpy(&f, &b, 4);
+    return f;
+}
+inline float step_down(float f) { return -step_up(-f); }
 inline float round_down(double v, float pad) {
     float f = (float)v;
-    if ((double)f > v) f = nextafterf(f, -INFINITY);
-    return nextafterf(f - pad, -INFINITY);
+    if ((double)f > v) f = step_down(f);
+    return step_down(f - pad);
 }
 inline float round_up(double v, float pad) {
     float f = (float)v;
-    if ((double)f < v) f = nextafterf(f, INFINITY);
-    return nextafterf(f + pad, INFINITY);
+    if ((double)f < v) f = step_up(f);
+    return step_up(f + pad);
 }
 
 inline int32_t leaf_code(int64_t first, int32_t count) { return ~(int32_t)((first << 3) | (int64_t)(count - 1)); }
 
-struct Flattener {
-    const std::vector<TmpNode> &tmp;
-    std::vector<FastNode> &out;
-    float pad;
-    int depth = 0;
+// Flattening = numbering the inner nodes in pre-order and writing their children's conservative FP32 boxes.  It walks
+// the temporary tree in an order unrelated to its memory order, so it is bound by cache misses; for big trees the top
+// `split_depth` levels are flattened serially, every subtree hanging below them is flattened into its own buffer on its
+// own thread, and the buffers are appended with their links shifted.  The node order is then "top part, subtree,
+// subtree, ..." (each subtree still contiguous and in pre-order); any order is a valid tree.
+struct FlatTask {
+    int32_t tmp_id;   // subtree root in the temporary tree
+    int32_t out_id;   // parent node in the output ...
+    int32_t slot;     // ... and the child slot that will point to the subtree
+};
+struct FlatItem { int32_t tmp_id, out_id, depth; };
 
-    void set_child(FastNode &n, int which, const TmpNode *c, int32_t idx, int32_t cnt) {
+struct BinaryPolicy {
+    typedef FastNode Node;
+    const std::vector<TmpNode> &tmp;
+    float pad;
+    static void set_link(FastNode &n, int k, int32_t idx) { (k == 0 ? n.child0 : n.child1) = idx; }
+    static void shift_links(FastNode &n, int32_t base) {
+        if (n.child0 >= 0) n.child0 += base;
+        if (n.child1 >= 0) n.child1 += base;
+    }
+    void set_child(FastNode &n, int which, const TmpNode *c, int32_t idx, int32_t cnt) const {
         float lo[3], hi[3];
         for (int a = 0; a < 3; ++a) {
             if (c) { lo[a] = round_down(c->box.lo[a], pad); hi[a] = round_up(c->box.hi[a], pad); }
@@ -346,55 +457,34 @@ struct Flattener {
             n.child1 = idx; n.count1 = cnt;
         }
     }
-
-    // iterative pre-order flatten (explicit stack: no recursion depth limits on degenerate trees)
-    void run(int32_t root) {
-        struct Item { int32_t tmp_id, out_id, depth; };
-        std::vector<Item> stack;
-        out.clear();
-        out.reserve(tmp.size() / 2 + 2);
-        const TmpNode &r = tmp[root];
-        out.emplace_back();
-        if (r.count > 0 || r.left < 0) {  // root is a leaf (or the tree is empty): wrap it
-            memset(&out[0], 0, sizeof(FastNode));
-            if (r.count > 0) set_child(out[0], 0, &r, leaf_code(r.first, r.count), r.count);
-            else set_child(out[0], 0, nullptr, ~0, 0);
-            set_child(out[0], 1, nullptr, ~0, 0);
-            depth = 1;
-            return;
-        }
-        stack.push_back({root, 0, 1});
-        while (!stack.empty()) {
-            Item it = stack.back();
-            stack.pop_back();
-            depth = std::max(depth, it.depth);
-            const TmpNode &t = tmp[it.tmp_id];
-            const TmpNode *kids[2] = {&tmp[t.left], &tmp[t.right]};
-            int32_t kid_ids[2] = {t.left, t.right};
-            for (int k = 0; k < 2; ++k) {
-                const TmpNode *c = kids[k];
-                if (c->count > 0) {
-                    set_child(out[it.out_id], k, c, leaf_code(c->first, c->count), c->count);
-                } else {
-                    int32_t id = (int32_t)out.size();
-                    out.emplace_back();
-                    set_child(out[it.out_id], k, c, id, 0);
-                    stack.push_back({kid_ids[k], id, it.depth + 1});
-                }
-            }
-        }
+    // children of the output node that stands for temporary node `t`
+    int kids(const TmpNode &t, int32_t *out_kids) const {
+        out_kids[0] = t.left; out_kids[1] = t.right;
+        return 2;
+    }
+    static const int WIDTH = 2;
+    static const int32_t EMPTY_LINK = ~0;
+    // the tree is a single leaf (or empty): wrap it in a root node
+    void wrap_root(FastNode &n, const TmpNode &r) const {
+        memset(&n, 0, sizeof(FastNode));
+        if (r.count > 0) set_child(n, 0, &r, leaf_code(r.first, r.count), r.count);
+        else set_child(n, 0, nullptr, ~0, 0);
+        set_child(n, 1, nullptr, ~0, 0);
     }
 };
 
 // Collapse the binary SAH tree into 4-wide nodes: start from a binary node's two children and keep replacing the inner
 // child with the largest surface area by its own two children until there are four (or only leaves are left).
-struct WideFlattener {
+struct WidePolicy {
+    typedef WideNode Node;
     const std::vector<TmpNode> &tmp;
-    std::vector<WideNode> &out;
     float pad;
-    int depth = 0;
-
-    void set_child(WideNode &n, int k, const TmpNode *c, int32_t idx, int32_t cnt) {
+    static void set_link(WideNode &n, int k, int32_t idx) { n.child[k] = idx; }
+    static void shift_links(WideNode &n, int32_t base) {
+        for (int k = 0; k < 4; ++k)
+            if (n.child[k] >= 0 && n.child[k] != TAKE_WIDE_EMPTY) n.child[k] += base;
+    }
+    void set_child(WideNode &n, int k, const TmpNode *c, int32_t idx, int32_t cnt) const {
         if (c) {
             n.lox[k] = round_down(c->box.lo[0], pad); n.hix[k] = round_up(c->box.hi[0], pad);
             n.loy[k] = round_down(c->box.lo[1], pad); n.hiy[k] = round_up(c->box.hi[1], pad);
@@ -406,57 +496,136 @@ struct WideFlattener {
         n.child[k] = idx;
         n.count[k] = cnt;
     }
-
-    void run(int32_t root) {
-        struct Item { int32_t tmp_id, out_id, depth; };
-        std::vector<Item> stack;
-        out.clear();
-        out.reserve(tmp.size() / 3 + 2);
-        const TmpNode &r = tmp[root];
-        out.emplace_back();
-        if (r.count > 0 || r.left < 0) {  // root is a leaf or the tree is empty
-            memset(&out[0], 0, sizeof(WideNode));
-            for (int k = 0; k < 4; ++k) set_child(out[0], k, nullptr, TAKE_WIDE_EMPTY, 0);
-            if (r.count > 0) set_child(out[0], 0, &r, leaf_code(r.first, r.count), r.count);
-            depth = 1;
-            return;
-        }
-        stack.push_back({root, 0, 1});
-        while (!stack.empty()) {
-            Item it = stack.back();
-            stack.pop_back();
-            depth = std::max(depth, it.depth);
-            int32_t kids[4];
-            int nk = 0;
-            kids[nk++] = tmp[it.tmp_id].left;
-            kids[nk++] = tmp[it.tmp_id].right;
-            while (nk < 4) {
-                int best = -1;
-                double best_area = -1;
-                for (int k = 0; k < nk; ++k) {
-                    const TmpNode &c = tmp[kids[k]];
-                    if (c.count > 0) continue;  // a leaf stays a leaf
-                    double a = half_area(c.box.lo, c.box.hi);
-                    if (a > best_area) { best_area = a; best = k; }
-                }
-                if (best < 0) break;
-                const TmpNode &c = tmp[kids[best]];
-                kids[best] = c.left;
-                kids[nk++] = c.right;
+    int kids(const TmpNode &t, int32_t *out_kids) const {
+        int nk = 0;
+        out_kids[nk++] = t.left;
+        out_kids[nk++] = t.right;
+        while (nk < 4) {
+            int best = -1;
+            double best_area = -1;
+            for (int k = 0; k < nk; ++k) {
+                const TmpNode &c = tmp[out_kids[k]];
+                if (c.count > 0) continue;  // a leaf stays a leaf
+                double a = half_area(c.box.lo, c.box.hi);
+                if (a > best_area) { best_area = a; best = k; }
             }
-            for (int k = 0; k < 4; ++k) {
-                if (k >= nk) { set_child(out[it.out_id], k, nullptr, TAKE_WIDE_EMPTY, 0); continue; }
-                const TmpNode *c = &tmp[kids[k]];
+            if (best < 0) break;
+            const TmpNode &c = tmp[out_kids[best]];
+            out_kids[best] = c.left;
+            out_kids[nk++] = c.right;
+        }
+        return nk;
+    }
+    static const int WIDTH = 4;
+    static const int32_t EMPTY_LINK = TAKE_WIDE_EMPTY;
+    void wrap_root(WideNode &n, const TmpNode &r) const {
+        memset(&n, 0, sizeof(WideNode));
+        for (int k = 0; k < 4; ++k) set_child(n, k, nullptr, TAKE_WIDE_EMPTY, 0);
+        if (r.count > 0) set_child(n, 0, &r, leaf_code(r.first, r.count), r.count);
+    }
+};
+
+template <typename P>
+struct FlattenerT {
+    typedef typename P::Node Node;
+    P pol;
+    std::vector<Node> &out;
+    int depth = 0;
+
+    // Pre-order flatten of the subtree under temporary node `root` into `dst` (explicit stack: no recursion depth limits
+    // on degenerate trees); dst[0] must already exist and stands for `root`.  Inner children found at depth
+    // `defer_depth` are not expanded but listed in `tasks` (when given).  Returns the deepest level reached.
+    int flatten(std::vector<Node> &dst, int32_t root, int depth0, int defer_depth, std::vector<FlatTask> *tasks) const {
+        std::vector<FlatItem> stack;
+        stack.push_back({root, 0, depth0});
+        int deepest = depth0;
+        while (!stack.empty()) {
+            FlatItem it = stack.back();
+            stack.pop_back();
+            deepest = std::max(deepest, it.depth);
+            int32_t kids[4];
+            const int nk = pol.kids(pol.tmp[it.tmp_id], kids);
+            for (int k = 0; k < P::WIDTH; ++k) {
+                if (k >= nk) { pol.set_child(dst[it.out_id], k, nullptr, P::EMPTY_LINK, 0); continue; }
+                const TmpNode *c = &pol.tmp[kids[k]];
                 if (c->count > 0) {
-                    set_child(out[it.out_id], k, c, leaf_code(c->first, c->count), c->count);
+                    pol.set_child(dst[it.out_id], k, c, leaf_code(c->first, c->count), c->count);
+                } else if (tasks && it.depth >= defer_depth) {
+                    pol.set_child(dst[it.out_id], k, c, 0, 0);  // link patched when the subtree has its place
+                    tasks->push_back({kids[k], it.out_id, k});
                 } else {
-                    int32_t id = (int32_t)out.size();
-                    out.emplace_back();
-                    set_child(out[it.out_id], k, c, id, 0);
+                    int32_t id = (int32_t)dst.size();
+                    dst.emplace_back();
+                    pol.set_child(dst[it.out_id], k, c, id, 0);
                     stack.push_back({kids[k], id, it.depth + 1});
                 }
             }
         }
+        return deepest;
+    }
+
+    void run(int32_t root, int threads) {
+        out.clear();
+        const TmpNode &r = pol.tmp[root];
+        out.emplace_back();
+        if (r.count > 0 || r.left < 0) {  // root is a leaf (or the tree is empty): wrap it
+            pol.wrap_root(out[0], r);
+            depth = 1;
+            return;
+        }
+        const size_t n_tmp = pol.tmp.size();
+        if (threads <= 1 || n_tmp < (size_t)(1 << 18)) {
+            out.reserve(n_tmp / P::WIDTH + 2);
+            depth = flatten(out, root, 1, 0, nullptr);
+            return;
+        }
+        // top of the tree serially, down to a level with enough subtrees to balance the threads
+        const int split_depth = P::WIDTH == 2 ? 9 : 5;
+        std::vector<FlatTask> tasks;
+        depth = flatten(out, root, 1, split_depth, &tasks);
+        const size_t nt = tasks.size();
+        std::vector<std::vector<Node>> parts(nt);
+        std::vector<int> deep(nt, 0);
+        std::atomic<size_t> next{0};
+        auto worker = [&] {
+            for (;;) {
+                const size_t t = next.fetch_add(1);
+                if (t >= nt) return;
+                parts[t].emplace_back();
+                deep[t] = flatten(parts[t], tasks[t].tmp_id, split_depth + 1, 0, nullptr);
+            }
+        };
+        {
+            std::vector<std::thread> pool;
+            for (int t = 1; t < threads; ++t) pool.emplace_back(worker);
+            worker();
+            for (auto &t : pool) t.join();
+        }
+        std::vector<size_t> base(nt + 1, out.size());
+        for (size_t t = 0; t < nt; ++t) base[t + 1] = base[t] + parts[t].size();
+        out.resize(base[nt]);
+        next = 0;
+        auto copier = [&] {
+            for (;;) {
+                const size_t t = next.fetch_add(1);
+                if (t >= nt) return;
+                Node *dst = out.data() + base[t];
+                for (size_t i = 0; i < parts[t].size(); ++i) {
+                    Node n = parts[t][i];
+                    P::shift_links(n, (int32_t)base[t]);
+                    dst[i] = n;
+                }
+                P::set_link(out[tasks[t].out_id], tasks[t].slot, (int32_t)base[t]);
+                std::vector<Node>().swap(parts[t]);
+            }
+        };
+        {
+            std::vector<std::thread> pool;
+            for (int t = 1; t < threads; ++t) pool.emplace_back(copier);
+            copier();
+            for (auto &t : pool) t.join();
+        }
+        for (size_t t = 0; t < nt; ++t) depth = std::max(depth, deep[t]);
     }
 };
 
@@ -480,17 +649,46 @@ void build_reference_tree(const Aabb *boxes, int64_t n, int threads, RefTree &ou
 void build_fast_tree(const Aabb *boxes, int64_t n, int max_leaf, float pad, int threads, FastTree &out) {
     out.nodes.clear();
     out.leaf_prims.assign((size_t)std::max<int64_t>(n, 0), 0);
-    for (int64_t i = 0; i < n; ++i) out.leaf_prims[i] = (int32_t)i;
-    SahBuilder b(boxes, out.leaf_prims.data(), n, std::max(1, max_leaf), threads);
+    const int64_t nn = std::max<int64_t>(n, 0);
+    // records moved by the partitions + the scratch copy of the chunk-parallel ones (64-byte aligned)
+    PrimRef *refs = nn ? (PrimRef *)aligned_alloc(64, (size_t)nn * sizeof(PrimRef)) : nullptr;
+    PrimRef *scratch = nn ? (PrimRef *)aligned_alloc(64, (size_t)nn * sizeof(PrimRef)) : nullptr;
+    const int fill_parts = nn >= (1 << 16) ? std::max(1, threads) : 1;
+    SahBuilder::chunked(0, nn, fill_parts, [&](int, int64_t a0, int64_t a1) {
+        for (int64_t i = a0; i < a1; ++i) { refs[i].box = boxes[i]; refs[i].id = i; refs[i].pad = 0; }
+    });
+    SahBuilder b(refs, scratch, n, std::max(1, max_leaf), threads);
     b.top_threads = std::max(1, threads);
     int32_t root = b.alloc();
-    if (n > 0) b.build(root, 0, n);
-    Flattener f{b.nodes, out.nodes, pad};
-    f.run(root);
+    const bool times = getenv("TAKE_BUILD_TIMES") != nullptr;
+    auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    double t0 = now();
+    if (n > 0) {
+        const Bounds all = b.range_bounds(0, n);
+        b.build(root, 0, n, all);
+    }
+    SahBuilder::chunked(0, nn, fill_parts, [&](int, int64_t a0, int64_t a1) {
+        for (int64_t i = a0; i < a1; ++i) out.leaf_prims[i] = (int32_t)refs[i].id;
+    });
+    free(refs);
+    free(scratch);
+    double t1 = now();
+    // the binary and the 4-wide image of the tree are independent: flatten them side by side
+    FlattenerT<BinaryPolicy> f{BinaryPolicy{b.nodes, pad}, out.nodes};
+    FlattenerT<WidePolicy> wf{WidePolicy{b.nodes, pad}, out.wide};
+    if (threads > 1 && nn >= (1 << 16)) {
+        const int tw_threads = std::max(1, threads / 2);
+        std::thread tw([&] { wf.run(root, tw_threads); });
+        f.run(root, std::max(1, threads - tw_threads));
+        tw.join();
+    } else {
+        f.run(root, 1);
+        wf.run(root, 1);
+    }
     out.depth = f.depth;
-    WideFlattener wf{b.nodes, out.wide, pad};
-    wf.run(root);
     out.wide_depth = wf.depth;
+    double t2 = now();
+    if (times) fprintf(stderr, "[take_gpu] fast tree: sah build %.0f ms, flatten (binary | 4-wide) %.0f ms\n", t1 - t0, t2 - t1);
     // SAH cost of the final tree (diagnostic)
     double cost = 0, root_area = n > 0 ? half_area(b.nodes[root].box.lo, b.nodes[root].box.hi) : 0;
     if (root_area > 0) {

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <string>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -168,6 +169,17 @@ int validate(const TakeSceneDesc *d) {
     return TAKE_OK;
 }
 
+// f(a, b) over [0, n) in contiguous chunks on `threads` host threads (the per-primitive loops of host_build)
+template <typename F>
+void parallel_chunks(int64_t n, int threads, F f) {
+    const int parts = n >= (1 << 16) ? std::max(1, threads) : 1;
+    if (parts <= 1) { f((int64_t)0, n); return; }
+    std::vector<std::thread> pool;
+    for (int t = 1; t < parts; ++t) pool.emplace_back(f, n * t / parts, n * (t + 1) / parts);
+    f((int64_t)0, n / parts);
+    for (auto &t : pool) t.join();
+}
+
 struct HostBuild {
     RefTree ref;
     FastTree fast;
@@ -181,22 +193,28 @@ int host_build(const TakeSceneDesc *d, int threads, HostBuild &hb) {
     // primitive boxes exactly as build_bvh (src/scene.cpp:4-23)
     std::vector<Aabb> boxes((size_t)n);
     double abs_max = 0;
-    for (int64_t i = 0; i < n; ++i) {
-        Aabb &b = boxes[i];
-        const int32_t *id = d->indices + 3 * i;
-        if (d->prim_flags[i] & TAKE_PRIM_SPHERE) {
-            const double *sp = d->spheres + 4 * (int64_t)id[0];
-            for (int a = 0; a < 3; ++a) { b.lo[a] = sp[a] - sp[3]; b.hi[a] = sp[a] + sp[3]; }
-        } else {
-            const double *p0 = d->positions + 3 * (int64_t)id[0], *p1 = d->positions + 3 * (int64_t)id[1],
-                         *p2 = d->positions + 3 * (int64_t)id[2];
-            for (int a = 0; a < 3; ++a) {
-                b.lo[a] = std::min(std::min(p0[a], p1[a]), p2[a]);
-                b.hi[a] = std::max(std::max(p0[a], p1[a]), p2[a]);
+    std::mutex abs_mu;
+    parallel_chunks(n, threads, [&](int64_t a0, int64_t a1) {
+        double amax = 0;
+        for (int64_t i = a0; i < a1; ++i) {
+            Aabb &b = boxes[i];
+            const int32_t *id = d->indices + 3 * i;
+            if (d->prim_flags[i] & TAKE_PRIM_SPHERE) {
+                const double *sp = d->spheres + 4 * (int64_t)id[0];
+                for (int a = 0; a < 3; ++a) { b.lo[a] = sp[a] - sp[3]; b.hi[a] = sp[a] + sp[3]; }
+            } else {
+                const double *p0 = d->positions + 3 * (int64_t)id[0], *p1 = d->positions + 3 * (int64_t)id[1],
+                             *p2 = d->positions + 3 * (int64_t)id[2];
+                for (int a = 0; a < 3; ++a) {
+                    b.lo[a] = std::min(std::min(p0[a], p1[a]), p2[a]);
+                    b.hi[a] = std::max(std::max(p0[a], p1[a]), p2[a]);
+                }
             }
+            for (int a = 0; a < 3; ++a) amax = std::max(amax, std::max(fabs(b.lo[a]), fabs(b.hi[a])));
         }
-        for (int a = 0; a < 3; ++a) abs_max = std::max(abs_max, std::max(fabs(b.lo[a]), fabs(b.hi[a])));
-    }
+        std::lock_guard<std::mutex> g(abs_mu);
+        abs_max = std::max(abs_max, amax);
+    });
     hb.abs_max = abs_max;
     RefTree &ref = hb.ref;
     FastTree &fast = hb.fast;
@@ -214,29 +232,31 @@ int host_build(const TakeSceneDesc *d, int threads, HostBuild &hb) {
 
     // leaf-ordered FP64 primitive records: v0 | idbits | e1 | aux | e2 | kind
     std::vector<double> &tris = hb.tris;
-    tris.assign((size_t)n * 12, 0.0);
-    for (int64_t slot = 0; slot < n; ++slot) {
-        const int32_t prim = fast.leaf_prims[slot];
-        double *T = tris.data() + 12 * slot;
-        const int32_t *id = d->indices + 3 * (int64_t)prim;
-        long long bits = ((long long)ref.dfs_rank[prim] << 32) | (long long)(uint32_t)prim;
-        memcpy(&T[3], &bits, 8);
-        if (d->prim_flags[prim] & TAKE_PRIM_SPHERE) {
-            const double *sp = d->spheres + 4 * (int64_t)id[0];
-            T[0] = sp[0]; T[1] = sp[1]; T[2] = sp[2];
-            T[4] = T[5] = T[6] = 0; T[7] = sp[3];
-            T[8] = T[9] = T[10] = 0; T[11] = 1.0;
-        } else {
-            const double *p0 = d->positions + 3 * (int64_t)id[0], *p1 = d->positions + 3 * (int64_t)id[1],
-                         *p2 = d->positions + 3 * (int64_t)id[2];
-            for (int a = 0; a < 3; ++a) {
-                T[a] = p0[a];
-                T[4 + a] = p1[a] - p0[a];  // e1 = v1 - v0, e2 = v2 - v0 (src/shape.cpp:53-54), computed once
-                T[8 + a] = p2[a] - p0[a];
+    tris.resize((size_t)n * 12);
+    parallel_chunks(n, threads, [&](int64_t a0, int64_t a1) {
+        for (int64_t slot = a0; slot < a1; ++slot) {
+            const int32_t prim = fast.leaf_prims[slot];
+            double *T = tris.data() + 12 * slot;
+            const int32_t *id = d->indices + 3 * (int64_t)prim;
+            long long bits = ((long long)ref.dfs_rank[prim] << 32) | (long long)(uint32_t)prim;
+            memcpy(&T[3], &bits, 8);
+            if (d->prim_flags[prim] & TAKE_PRIM_SPHERE) {
+                const double *sp = d->spheres + 4 * (int64_t)id[0];
+                T[0] = sp[0]; T[1] = sp[1]; T[2] = sp[2];
+                T[4] = T[5] = T[6] = 0; T[7] = sp[3];
+                T[8] = T[9] = T[10] = 0; T[11] = 1.0;
+            } else {
+                const double *p0 = d->positions + 3 * (int64_t)id[0], *p1 = d->positions + 3 * (int64_t)id[1],
+                             *p2 = d->positions + 3 * (int64_t)id[2];
+                for (int a = 0; a < 3; ++a) {
+                    T[a] = p0[a];
+                    T[4 + a] = p1[a] - p0[a];  // e1 = v1 - v0, e2 = v2 - v0 (src/shape.cpp:53-54), computed once
+                    T[8 + a] = p2[a] - p0[a];
+                }
+                T[7] = 0; T[11] = 0.0;
             }
-            T[7] = 0; T[11] = 0.0;
         }
-    }
+    });
     return TAKE_OK;
 }
 

@@ -220,3 +220,46 @@ def test_wide_tree_structure(small_scene):
         bounds(0)
         assert seen.all() and (covered == 1).all()
         assert len(wide) <= max(1, len(hb["fast_nodes"]))   # collapsing never adds nodes
+
+
+def test_large_tree_takes_the_parallel_paths():
+    """180 k primitives: the chunk-parallel top-level partitions and the per-subtree parallel flatten of both tree images
+    (bvh_build.cpp) only start at this size.  Every node is reached exactly once, every leaf slot is covered exactly once,
+    children come after their parents, and every child box contains the FP64 bounds of what is below it."""
+    flat = scenes.heightfield(n=300, width=64, height=32).flat()
+    hb = api.host_build(flat)
+    prims = hb["leaf_prims"]
+    n = flat.num_prims
+    assert n > (1 << 17) and sorted(prims.tolist()) == list(range(n))
+    P = flat.positions[flat.indices]
+    plo, phi = P.min(axis=1)[prims], P.max(axis=1)[prims]           # bounds by leaf slot
+
+    def check(n_nodes, children_of):
+        lo = np.full((n_nodes, 3), np.inf); hi = np.full((n_nodes, 3), -np.inf)
+        refs = np.zeros(n_nodes, np.int32)
+        covered = np.zeros(n, np.int32)
+        for i in range(n_nodes - 1, -1, -1):                         # children have larger indices than their parent
+            for c, clo, chi in children_of(i):
+                if c >= 0:
+                    assert c > i
+                    refs[c] += 1
+                    l, h = lo[c], hi[c]
+                else:
+                    code = ~c
+                    first, count = code >> 3, (code & 7) + 1
+                    covered[first:first + count] += 1
+                    l, h = plo[first:first + count].min(axis=0), phi[first:first + count].max(axis=0)
+                assert (clo < l).all() and (chi > h).all()
+                lo[i] = np.minimum(lo[i], l); hi[i] = np.maximum(hi[i], h)
+        assert (refs[1:] == 1).all() and refs[0] == 0 and (covered == 1).all()
+
+    wide = hb["wide_nodes"]
+    wl = np.stack([wide["lox"], wide["loy"], wide["loz"]], axis=2).astype(np.float64)   # [node, child, axis]
+    wh = np.stack([wide["hix"], wide["hiy"], wide["hiz"]], axis=2).astype(np.float64)
+    wc = wide["child"]
+    check(len(wide), lambda i: [(int(wc[i, k]), wl[i, k], wh[i, k]) for k in range(4) if wc[i, k] != api.WIDE_EMPTY])
+    fast = hb["fast_nodes"]
+    fl = [np.stack([fast[f"c{k}lo{a}"] for a in "xyz"], axis=1).astype(np.float64) for k in (0, 1)]
+    fh = [np.stack([fast[f"c{k}hi{a}"] for a in "xyz"], axis=1).astype(np.float64) for k in (0, 1)]
+    fc = [fast["child0"], fast["child1"]]
+    check(len(fast), lambda i: [(int(fc[k][i]), fl[k][i], fh[k][i]) for k in (0, 1) if fl[k][i][0] <= fh[k][i][0]])
