@@ -574,7 +574,7 @@ struct FlattenerT {
             return;
         }
         const size_t n_tmp = pol.tmp.size();
-        if (threads <= 1 || n_tmp < (size_t)(1 << 18)) {
+        if (threads <= 1 || n_tmp < (size_t)(1 << 18) || getenv("TAKE_SERIAL_FLATTEN")) {  // (the knob is for A/B runs)
             out.reserve(n_tmp / P::WIDTH + 2);
             depth = flatten(out, root, 1, 0, nullptr);
             return;
