@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_extend(DevScene sc,
             }
             trace_any<false, COUNT, WIDE>(sc, o, d, TAKE_EPS, tmax, st, h, &cnt);
             if (miss_fast && h.prim < 0) {
-                // A camera ray that left the scene: the sample is the background colour (path_tracing.h:8 and the same
+                // A camera ray that left the scene: the sample is the background colour (path_tracing.h:8, :117, :164 -- the same
                 // line of the other two integrators).  Finishing it here keeps it out of the sort and the shade pass --
                 // on an open scene most camera rays end this way, and streaming their records through two more kernels
                 // was the larger part of the pass-0 shade time.
