@@ -43,15 +43,18 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """nvidia-smi clocks / throttle reasons during the timed region.  nvidia-smi needs a few hundred milliseconds to start and
+    the timed region of the default run is ~140 ms, so the sampler is started EARLY (before the scene is built), every row is
+    stamped on arrival, and only rows that arrived while the GPU was under the bench load (begin() .. stop()) are used; if none
+    did, stop() keeps the same load running until two have (at most 2 s)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.t0 = [], None, None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -59,15 +62,24 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def _under_load(self):
+        return [r for t, r in list(self.rows) if self.t0 is not None and t >= self.t0 + 0.02]
+
+    def stop(self, keep_busy=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        deadline = time.perf_counter() + 2.0
+        while keep_busy is not None and len(self._under_load()) < 2 and time.perf_counter() < deadline:
+            keep_busy()                       # same kernels as the timed region, untimed
+        rows = self._under_load()
         self.proc.terminate()
         sm, smax, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -195,6 +207,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
 
+    clocks = ClockSampler(local) if rank == 0 else None   # started early: see the class comment
     builder = build_scene()
     flat = builder.flat()
     t0 = time.perf_counter()
@@ -238,7 +251,8 @@ def run_ours(args):
         dist.all_reduce(d_sq)
     d_sum.zero_(); d_sq.zero_()
     barrier()
-    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(ext)
     for i in range(args.steps):
@@ -255,10 +269,11 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(agg)
-    clock_info = clocks.stop() if clocks else None
     ms = float(ms.item())
     rays_all, samples_all, launches_all = (float(v) for v in agg.tolist())
     mean_check = float((d_sum / (S * args.steps * world)).mean().item())
+    # (ranks other than 0 wait in the e2e barrier below while rank 0 tops up its clock samples, if it has to)
+    clock_info = clocks.stop(keep_busy=lambda: (device_step(0), torch.cuda.synchronize())) if clocks else None
 
     # ---- e2e: the C-ABI calls a host application makes (host buffers, D2H of every step's result inside the timed region) ----
     # take_gpu_render_async + take_gpu_render_wait with two pinned result buffers: the read-back of step k overlaps the
