@@ -7,6 +7,7 @@
 #include <time.h>
 
 #include <algorithm>
+#include <new>
 #include <atomic>
 #include <thread>
 
@@ -107,6 +108,20 @@ struct TmpNode {
     int32_t count = 0;              // leaf
 };
 
+// Node pool of the SAH builder: raw storage, a node is initialised when it is handed out (value-initialising 2n nodes up
+// front was a serial gigabyte of page faults at 10 M primitives; now the building threads touch their own nodes).
+struct TmpNodePool {
+    TmpNode *p = nullptr;
+    size_t n = 0;
+    explicit TmpNodePool(size_t count) : p((TmpNode *)malloc(count * sizeof(TmpNode))), n(count) {}
+    ~TmpNodePool() { free(p); }
+    TmpNodePool(const TmpNodePool &) = delete;
+    TmpNodePool &operator=(const TmpNodePool &) = delete;
+    TmpNode &operator[](size_t i) { return p[i]; }
+    const TmpNode &operator[](size_t i) const { return p[i]; }
+    size_t size() const { return n; }
+};
+
 inline double half_area(const double *lo, const double *hi) {
     double dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
     if (dx < 0 || dy < 0 || dz < 0) return 0;
@@ -151,7 +166,7 @@ struct SahBuilder {
     static const int SMALL = 16;  // ranges up to this size take the sparse sweep
     PrimRef *refs;
     PrimRef *scratch;  // same length as refs: source of the chunk-parallel partitions near the root
-    std::vector<TmpNode> nodes;
+    TmpNodePool nodes;
     std::atomic<int32_t> next{0};
     int max_leaf;
     double c_trav, c_isect;
@@ -162,7 +177,11 @@ struct SahBuilder {
         if (const char *e = getenv("TAKE_SAH_CISECT")) c_isect = atof(e);  // tuning knob: cost of a leaf test relative to a node visit
     }
 
-    int32_t alloc() { return next.fetch_add(1); }
+    int32_t alloc() {
+        const int32_t i = next.fetch_add(1);
+        new (&nodes[i]) TmpNode();
+        return i;
+    }
 
     void make_leaf(TmpNode &n, int64_t lo, int64_t hi) {
         n.first = lo;
@@ -436,7 +455,7 @@ struct FlatItem { int32_t tmp_id, out_id, depth; };
 
 struct BinaryPolicy {
     typedef FastNode Node;
-    const std::vector<TmpNode> &tmp;
+    const TmpNodePool &tmp;
     float pad;
     static void set_link(FastNode &n, int k, int32_t idx) { (k == 0 ? n.child0 : n.child1) = idx; }
     static void shift_links(FastNode &n, int32_t base) {
@@ -477,7 +496,7 @@ struct BinaryPolicy {
 // child with the largest surface area by its own two children until there are four (or only leaves are left).
 struct WidePolicy {
     typedef WideNode Node;
-    const std::vector<TmpNode> &tmp;
+    const TmpNodePool &tmp;
     float pad;
     static void set_link(WideNode &n, int k, int32_t idx) { n.child[k] = idx; }
     static void shift_links(WideNode &n, int32_t base) {
@@ -650,6 +669,8 @@ void build_fast_tree(const Aabb *boxes, int64_t n, int max_leaf, float pad, int 
     out.nodes.clear();
     out.leaf_prims.assign((size_t)std::max<int64_t>(n, 0), 0);
     const int64_t nn = std::max<int64_t>(n, 0);
+    timespec tsr; clock_gettime(CLOCK_MONOTONIC, &tsr);
+    const double tr0 = tsr.tv_sec * 1e3 + tsr.tv_nsec * 1e-6;
     // records moved by the partitions + the scratch copy of the chunk-parallel ones (64-byte aligned)
     PrimRef *refs = nn ? (PrimRef *)aligned_alloc(64, (size_t)nn * sizeof(PrimRef)) : nullptr;
     PrimRef *scratch = nn ? (PrimRef *)aligned_alloc(64, (size_t)nn * sizeof(PrimRef)) : nullptr;
@@ -688,16 +709,34 @@ void build_fast_tree(const Aabb *boxes, int64_t n, int max_leaf, float pad, int 
     out.depth = f.depth;
     out.wide_depth = wf.depth;
     double t2 = now();
-    if (times) fprintf(stderr, "[take_gpu] fast tree: sah build %.0f ms, flatten (binary | 4-wide) %.0f ms\n", t1 - t0, t2 - t1);
-    // SAH cost of the final tree (diagnostic)
+    if (times) fprintf(stderr, "[take_gpu] fast tree: records %.0f ms, sah build %.0f ms, flatten (binary | 4-wide) %.0f ms\n", t0 - tr0, t1 - t0, t2 - t1);
+    // SAH cost of the final tree (diagnostic): partial sums over a fixed number of chunks, added in chunk order, so the
+    // value does not depend on the thread count
     double cost = 0, root_area = n > 0 ? half_area(b.nodes[root].box.lo, b.nodes[root].box.hi) : 0;
     if (root_area > 0) {
-        int32_t used = b.next.load();
-        for (int32_t i = 0; i < used; ++i) {
-            const TmpNode &t = b.nodes[i];
-            double a = half_area(t.box.lo, t.box.hi) / root_area;
-            cost += t.count > 0 ? a * b.c_isect * t.count : a * b.c_trav;
-        }
+        const int64_t used = b.next.load();
+        const int CH = 64;
+        double part[CH];
+        std::atomic<int> next_chunk{0};
+        auto work = [&] {
+            for (;;) {
+                const int c = next_chunk.fetch_add(1);
+                if (c >= CH) return;
+                double acc = 0;
+                for (int64_t i = used * c / CH; i < used * (c + 1) / CH; ++i) {
+                    const TmpNode &t = b.nodes[i];
+                    double a = half_area(t.box.lo, t.box.hi) / root_area;
+                    acc += t.count > 0 ? a * b.c_isect * t.count : a * b.c_trav;
+                }
+                part[c] = acc;
+            }
+        };
+        std::vector<std::thread> pool;
+        const int workers = used >= (1 << 18) ? std::max(1, threads) : 1;
+        for (int t = 1; t < workers; ++t) pool.emplace_back(work);
+        work();
+        for (auto &t : pool) t.join();
+        for (int c = 0; c < CH; ++c) cost += part[c];
     }
     out.sah_cost = cost;
 }
