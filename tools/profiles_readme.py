@@ -50,9 +50,10 @@ L.append(f"""
   {r['bytes_per_launch'] / tr['dram_bytes_per_launch']:.1f}x *below* the algorithmic bytes ({r['bytes_per_launch'] / 1e6:.0f} MB per launch by the SURVEY.md 8(d)
   counting rule) because the 130 MB of tree and leaf records live in L1/L2.  `roofline.achieved` = algorithmic bytes /
   time = {r['achieved']:.0f} GB/s = {r['frac']:.2f} of the HBM peak.
-* It is latency- and divergence-bound: the top stall is `long_scoreboard` (dependent node fetches), {float(ext[0]['issue_active_pct']):.0f} % of the
-  issue slots are used at {float(ext[0]['achieved_occupancy_pct']):.0f} % occupancy, and only {ext[0]['warp_execution_efficiency_pct']} % (camera rays) / {ext[1]['warp_execution_efficiency_pct']} % (first bounce) of the
-  lanes are active per issued instruction.
+* Camera rays (pass 0) are close to issue-bound: {float(ext[0]['issue_active_pct']):.0f} % of the issue slots used at {float(ext[0]['achieved_occupancy_pct']):.0f} % occupancy with
+  {ext[0]['warp_execution_efficiency_pct']} % of the lanes active.  Bounce rays (pass 1+) are divergence- and latency-bound: {ext[1]['warp_execution_efficiency_pct']} % of the lanes
+  active per issued instruction (ray lengths vary widely), L1 hit rate {float(ext[1]['l1_hit_pct']):.0f} %, top stall `long_scoreboard`
+  (dependent node fetches).
 * Ray-box / ray-triangle test rate against FP32 peak: {r['box_tests_per_ray']:.1f} box + {r['tri_tests_per_ray']:.2f} leaf tests per ray at
   {r['extend_grays_per_s']:.2f} Grays/s = {r['test_rate_tflops']:.2f} TFLOP/s by the 27 / 60 flop counting rule = {100 * r['test_rate_frac_fp32']:.1f} % of the
   {r['fp32_peak_tflops']:.1f} TFLOP/s FP32 peak (the leaf tests actually run in FP64).
