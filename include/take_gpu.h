@@ -260,6 +260,16 @@ int take_gpu_host_build_copy(TakeHostBuild *h, void *ref_nodes, int32_t *dfs_ran
 int64_t take_gpu_host_build_wide(TakeHostBuild *h, void *wide_nodes); /* returns the node count; copies if non-NULL */
 int take_gpu_host_build_free(TakeHostBuild *h);
 
+/* Build once, create many: with one process per GPU (torchrun, MPI) every rank would otherwise run the host builders
+ * on the same cores at the same time.  One rank builds (take_gpu_host_build) and saves; the others load the file --
+ * /dev/shm is the natural place on one node -- and all create their scene from the prebuilt structures.  A build
+ * carries a hash of the primitive data it was made from; take_gpu_scene_create_prebuilt refuses a build that does not
+ * belong to `desc` (TAKE_E_INVALID).  The handle stays the caller's (free it with take_gpu_host_build_free).  The file
+ * is a private cache format tied to this library version, not an exchange format. */
+int take_gpu_host_build_save(TakeHostBuild *h, const char *path);
+int take_gpu_host_build_load(const char *path, TakeHostBuild **out);
+int take_gpu_scene_create_prebuilt(int device, const TakeSceneDesc *desc, TakeHostBuild *h, TakeScene **out);
+
 const char *take_gpu_last_error(void);
 const char *take_gpu_version(void);
 

@@ -117,14 +117,54 @@ def make_rays(origin, direction, tmin=1e-7, tmax=np.inf) -> np.ndarray:
     return rays
 
 
+class HostBuild:
+    """Handle on the host-built acceleration structures of a scene (take_gpu_host_build): build once, save, load in the
+    other ranks of a one-process-per-GPU job, create every rank's GpuScene from it (`GpuScene(flat, prebuilt=...)`)."""
+
+    def __init__(self, flat: FlatScene = None, path: str = None):
+        self.lib = L = load_library()
+        L.take_gpu_host_build.argtypes = [C.POINTER(TakeSceneDesc), C.POINTER(C.c_void_p)]
+        L.take_gpu_host_build_free.argtypes = [C.c_void_p]
+        L.take_gpu_host_build_save.argtypes = [C.c_void_p, C.c_char_p]
+        L.take_gpu_host_build_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.take_gpu_scene_create_prebuilt.argtypes = [C.c_int, C.POINTER(TakeSceneDesc), C.c_void_p, C.POINTER(C.c_void_p)]
+        self.h = C.c_void_p()
+        if path is not None:
+            _check(L.take_gpu_host_build_load(os.fsencode(path), C.byref(self.h)))
+        else:
+            desc = flat.to_desc()
+            _check(L.take_gpu_host_build(C.byref(desc), C.byref(self.h)))
+
+    def save(self, path: str):
+        _check(self.lib.take_gpu_host_build_save(self.h, os.fsencode(path)))
+
+    def arrays(self) -> dict:
+        """Copies of the structures for inspection (layouts: take_b200/csrc/bvh_build.h)."""
+        return _host_build_arrays(self.lib, self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.take_gpu_host_build_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class GpuScene:
-    def __init__(self, flat: FlatScene, device: int = 0):
+    def __init__(self, flat: FlatScene, device: int = 0, prebuilt: "HostBuild" = None):
         self.lib = load_library()
         self.flat = flat
         self.width, self.height = flat.width, flat.height
         self._desc = flat.to_desc()
         h = C.c_void_p()
-        _check(self.lib.take_gpu_scene_create(device, C.byref(self._desc), C.byref(h)))
+        if prebuilt is not None:
+            _check(self.lib.take_gpu_scene_create_prebuilt(device, C.byref(self._desc), prebuilt.h, C.byref(h)))
+        else:
+            _check(self.lib.take_gpu_scene_create(device, C.byref(self._desc), C.byref(h)))
         self.h = h
         self.device = device
 
@@ -287,32 +327,31 @@ def write_exr_packed(path, width: int, height: int, packed: np.ndarray, threads:
     _check(L.take_gpu_exr_write_packed(os.fsencode(path), width, height, packed.ctypes.data, threads))
 
 
-def host_build(flat: FlatScene) -> dict:
-    """The acceleration structures take_gpu_scene_create would upload, built on the host only (no CUDA needed)."""
-    L = load_library()
-    L.take_gpu_host_build.argtypes = [C.POINTER(TakeSceneDesc), C.POINTER(C.c_void_p)]
+def _host_build_arrays(L, h) -> dict:
     L.take_gpu_host_build_info.argtypes = [C.c_void_p, C.c_void_p]
     L.take_gpu_host_build_copy.argtypes = [C.c_void_p] * 6
-    L.take_gpu_host_build_free.argtypes = [C.c_void_p]
-    desc = flat.to_desc()
-    h = C.c_void_p()
-    _check(L.take_gpu_host_build(C.byref(desc), C.byref(h)))
-    try:
-        info = (C.c_double * 8)()
-        _check(L.take_gpu_host_build_info(h, info))
-        n_ref, root, n_fast, n_prims, depth = (int(info[i]) for i in range(5))
-        ref = np.zeros(n_ref, REF_NODE_DTYPE)
-        rank = np.zeros(n_prims, np.int32)
-        fast = np.zeros(n_fast, FAST_NODE_DTYPE)
-        leaf = np.zeros(n_prims, np.int32)
-        recs = np.zeros((n_prims, 12), np.float64)
-        _check(L.take_gpu_host_build_copy(h, ref.ctypes.data, rank.ctypes.data, fast.ctypes.data, leaf.ctypes.data,
-                                          recs.ctypes.data))
-        L.take_gpu_host_build_wide.restype = C.c_int64
-        L.take_gpu_host_build_wide.argtypes = [C.c_void_p, C.c_void_p]
-        wide = np.zeros(int(L.take_gpu_host_build_wide(h, None)), WIDE_NODE_DTYPE)
-        L.take_gpu_host_build_wide(h, wide.ctypes.data)
-    finally:
-        L.take_gpu_host_build_free(h)
+    info = (C.c_double * 8)()
+    _check(L.take_gpu_host_build_info(h, info))
+    n_ref, root, n_fast, n_prims, depth = (int(info[i]) for i in range(5))
+    ref = np.zeros(n_ref, REF_NODE_DTYPE)
+    rank = np.zeros(n_prims, np.int32)
+    fast = np.zeros(n_fast, FAST_NODE_DTYPE)
+    leaf = np.zeros(n_prims, np.int32)
+    recs = np.zeros((n_prims, 12), np.float64)
+    _check(L.take_gpu_host_build_copy(h, ref.ctypes.data, rank.ctypes.data, fast.ctypes.data, leaf.ctypes.data,
+                                      recs.ctypes.data))
+    L.take_gpu_host_build_wide.restype = C.c_int64
+    L.take_gpu_host_build_wide.argtypes = [C.c_void_p, C.c_void_p]
+    wide = np.zeros(int(L.take_gpu_host_build_wide(h, None)), WIDE_NODE_DTYPE)
+    L.take_gpu_host_build_wide(h, wide.ctypes.data)
     return dict(ref_nodes=ref, ref_root=root, dfs_rank=rank, fast_nodes=fast, wide_nodes=wide, leaf_prims=leaf, leaf_records=recs,
                 depth=depth, abs_max=float(info[5]), ms_ref=float(info[6]), ms_fast=float(info[7]))
+
+
+def host_build(flat: FlatScene) -> dict:
+    """The acceleration structures take_gpu_scene_create would upload, built on the host only (no CUDA needed)."""
+    hb = HostBuild(flat)
+    try:
+        return hb.arrays()
+    finally:
+        hb.close()

@@ -171,8 +171,8 @@ int validate(const TakeSceneDesc *d) {
 
 // f(a, b) over [0, n) in contiguous chunks on `threads` host threads (the per-primitive loops of host_build)
 template <typename F>
-void parallel_chunks(int64_t n, int threads, F f) {
-    const int parts = n >= (1 << 16) ? std::max(1, threads) : 1;
+void parallel_chunks(int64_t n, int threads, F f, int64_t min_parallel = 1 << 16) {
+    const int parts = n >= min_parallel ? (int)std::min<int64_t>(std::max(1, threads), n) : 1;
     if (parts <= 1) { f((int64_t)0, n); return; }
     std::vector<std::thread> pool;
     for (int t = 1; t < parts; ++t) pool.emplace_back(f, n * t / parts, n * (t + 1) / parts);
@@ -185,7 +185,38 @@ struct HostBuild {
     FastTree fast;
     std::vector<double> tris;  // 12 doubles per leaf slot
     double abs_max = 0, ms_ref = 0, ms_fast = 0;
+    uint64_t geom_hash = 0;    // of the primitive data the structures were built from (geometry_hash)
+    int64_t num_prims = 0;
 };
+
+// FNV-1a over the arrays the builders read: which primitives, where.  Chunks are hashed on all threads and the chunk
+// hashes are hashed in order, so the value does not depend on the thread count.
+uint64_t fnv1a(const void *data, size_t bytes, uint64_t h = 1469598103934665603ULL) {
+    const unsigned char *p = (const unsigned char *)data;
+    for (size_t i = 0; i < bytes; ++i) { h ^= p[i]; h *= 1099511628211ULL; }
+    return h;
+}
+uint64_t hash_array(const void *data, size_t bytes, int threads) {
+    const size_t CH = 1 << 22;
+    const size_t nch = (bytes + CH - 1) / CH;
+    std::vector<uint64_t> part(nch);
+    parallel_chunks((int64_t)nch, threads, [&](int64_t a0, int64_t a1) {
+        for (int64_t c = a0; c < a1; ++c)
+            part[c] = fnv1a((const char *)data + (size_t)c * CH, std::min(CH, bytes - (size_t)c * CH));
+    }, 8);
+    return fnv1a(part.data(), part.size() * sizeof(uint64_t));
+}
+uint64_t geometry_hash(const TakeSceneDesc *d, int threads) {
+    uint64_t h[5] = {0, 0, 0, 0, 0};
+    if (d->num_prims > 0) {
+        h[0] = hash_array(d->indices, (size_t)d->num_prims * 3 * sizeof(int32_t), threads);
+        h[1] = hash_array(d->prim_flags, (size_t)d->num_prims, threads);
+    }
+    if (d->num_vertices > 0) h[2] = hash_array(d->positions, (size_t)d->num_vertices * 3 * sizeof(double), threads);
+    if (d->num_spheres > 0) h[3] = hash_array(d->spheres, (size_t)d->num_spheres * 4 * sizeof(double), threads);
+    h[4] = (uint64_t)d->num_prims;
+    return fnv1a(h, sizeof(h));
+}
 
 // Everything scene_create does before touching CUDA: primitive boxes, both trees, leaf-ordered primitive records.
 int host_build(const TakeSceneDesc *d, int threads, HostBuild &hb) {
@@ -216,6 +247,8 @@ int host_build(const TakeSceneDesc *d, int threads, HostBuild &hb) {
         abs_max = std::max(abs_max, amax);
     });
     hb.abs_max = abs_max;
+    hb.num_prims = n;
+    hb.geom_hash = geometry_hash(d, threads);
     RefTree &ref = hb.ref;
     FastTree &fast = hb.fast;
     // the two trees are independent: build them side by side (the reference-order tree is bound by its serial
@@ -785,6 +818,86 @@ int64_t take_gpu_host_build_wide(TakeHostBuild *h, void *wide_nodes) {
 int take_gpu_host_build_free(TakeHostBuild *h) {
     delete h;
     return TAKE_OK;
+}
+
+}  // extern "C"
+
+// ---- build once, create many (one process per GPU: a single rank runs the host builders) ---------------------------
+namespace {
+struct HbHeader {
+    char magic[8];           // "TAKEHB02"
+    uint64_t geom_hash;
+    int64_t num_prims, n_ref, n_rank, n_fast, n_wide, n_leaf, n_tris;
+    int32_t ref_root, depth, wide_depth, pad;
+    double sah_cost, abs_max, ms_ref, ms_fast;
+};
+template <typename T>
+bool put(FILE *f, const std::vector<T> &v) { return v.empty() || fwrite(v.data(), sizeof(T), v.size(), f) == v.size(); }
+template <typename T>
+bool get(FILE *f, std::vector<T> &v, int64_t n) {
+    if (n < 0) return false;
+    v.resize((size_t)n);
+    return n == 0 || fread(v.data(), sizeof(T), (size_t)n, f) == (size_t)n;
+}
+}  // namespace
+
+extern "C" {
+
+int take_gpu_host_build_save(TakeHostBuild *h, const char *path) {
+    if (!h || !path) return fail(TAKE_E_INVALID, "null argument");
+    const HostBuild &b = h->hb;
+    HbHeader hd;
+    memset(&hd, 0, sizeof(hd));
+    memcpy(hd.magic, "TAKEHB02", 8);
+    hd.geom_hash = b.geom_hash; hd.num_prims = b.num_prims;
+    hd.n_ref = (int64_t)b.ref.nodes.size(); hd.n_rank = (int64_t)b.ref.dfs_rank.size(); hd.n_fast = (int64_t)b.fast.nodes.size();
+    hd.n_wide = (int64_t)b.fast.wide.size(); hd.n_leaf = (int64_t)b.fast.leaf_prims.size(); hd.n_tris = (int64_t)b.tris.size();
+    hd.ref_root = b.ref.root; hd.depth = b.fast.depth; hd.wide_depth = b.fast.wide_depth;
+    hd.sah_cost = b.fast.sah_cost; hd.abs_max = b.abs_max; hd.ms_ref = b.ms_ref; hd.ms_fast = b.ms_fast;
+    const std::string tmp = std::string(path) + ".part";  // readers never see a half-written file
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return fail(TAKE_E_INVALID, std::string("cannot write ") + tmp);
+    bool ok = fwrite(&hd, sizeof(hd), 1, f) == 1 && put(f, b.ref.nodes) && put(f, b.ref.dfs_rank) && put(f, b.fast.nodes) &&
+              put(f, b.fast.wide) && put(f, b.fast.leaf_prims) && put(f, b.tris);
+    ok = (fclose(f) == 0) && ok;
+    if (!ok || rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); return fail(TAKE_E_INVALID, std::string("write failed: ") + path); }
+    return TAKE_OK;
+}
+
+int take_gpu_host_build_load(const char *path, TakeHostBuild **out) {
+    if (!path || !out) return fail(TAKE_E_INVALID, "null argument");
+    *out = nullptr;
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(TAKE_E_INVALID, std::string("cannot read ") + path);
+    HbHeader hd;
+    TakeHostBuild *h = new TakeHostBuild;
+    HostBuild &b = h->hb;
+    bool ok = fread(&hd, sizeof(hd), 1, f) == 1 && memcmp(hd.magic, "TAKEHB02", 8) == 0;
+    // sizes are fixed by the primitive count: anything else is not a file this library wrote
+    ok = ok && hd.num_prims >= 0 && hd.num_prims < (1 << 28) && hd.n_leaf == hd.num_prims && hd.n_rank == hd.num_prims &&
+         hd.n_tris == 12 * hd.num_prims && hd.n_ref == (hd.num_prims > 0 ? 2 * hd.num_prims - 1 : 0) && hd.n_fast >= 1 &&
+         hd.n_fast <= std::max<int64_t>(hd.num_prims, 1) && hd.n_wide >= 1 && hd.n_wide <= hd.n_fast;
+    ok = ok && get(f, b.ref.nodes, hd.n_ref) && get(f, b.ref.dfs_rank, hd.n_rank) && get(f, b.fast.nodes, hd.n_fast) &&
+         get(f, b.fast.wide, hd.n_wide) && get(f, b.fast.leaf_prims, hd.n_leaf) && get(f, b.tris, hd.n_tris);
+    ok = ok && fgetc(f) == EOF;
+    fclose(f);
+    if (!ok) { delete h; return fail(TAKE_E_INVALID, std::string("not a host-build file of this library: ") + path); }
+    b.geom_hash = hd.geom_hash; b.num_prims = hd.num_prims; b.ref.root = hd.ref_root; b.fast.depth = hd.depth;
+    b.fast.wide_depth = hd.wide_depth; b.fast.sah_cost = hd.sah_cost; b.abs_max = hd.abs_max; b.ms_ref = hd.ms_ref; b.ms_fast = hd.ms_fast;
+    *out = h;
+    return TAKE_OK;
+}
+
+int take_gpu_scene_create_prebuilt(int device, const TakeSceneDesc *d, TakeHostBuild *h, TakeScene **out) {
+    if (!out || !h) return fail(TAKE_E_INVALID, "null argument");
+    *out = nullptr;
+    if (int rc = validate(d)) return rc;
+    const HostBuild &b = h->hb;
+    if (b.num_prims != d->num_prims || (int64_t)b.fast.leaf_prims.size() != d->num_prims ||
+        b.geom_hash != geometry_hash(d, (int)std::max(1u, std::thread::hardware_concurrency())))
+        return fail(TAKE_E_INVALID, "the prebuilt acceleration structures do not belong to this scene");
+    if (b.fast.depth > TAKE_STACK_SMEM + TAKE_STACK_LOCAL) return fail(TAKE_E_INVALID, "acceleration tree too deep");
+    return scene_create_from(device, d, h->hb, out);
 }
 
 int take_gpu_intersect_device(TakeScene *s, const TakeRay *d_rays, int64_t n, TakeHit *d_hits, int flags) {

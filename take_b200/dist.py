@@ -60,3 +60,32 @@ def finalize(s, s2, n: int):
     else:
         var = mean * 0
     return mean, var, n
+
+
+def shared_host_build(flat, path: str = None):
+    """One host build per NODE instead of one per rank: local rank 0 builds the acceleration structures and saves them
+    (default: /dev/shm), the node's other ranks wait at a barrier and load the file.  Returns an `api.HostBuild` to pass
+    as `GpuScene(flat, device=local_rank, prebuilt=...)`.  Without an initialised process group it just builds."""
+    import os
+    import torch.distributed as dist
+    from . import api
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return api.HostBuild(flat)
+    local = int(os.environ.get("LOCAL_RANK", dist.get_rank()))
+    if path is None:
+        base = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+        path = os.path.join(base, f"take_hostbuild_{os.environ.get('MASTER_PORT', '0')}_{flat.num_prims}.bin")
+    hb = None
+    if local == 0:
+        hb = api.HostBuild(flat)
+        hb.save(path)
+    dist.barrier()
+    if local != 0:
+        hb = api.HostBuild(path=path)
+    dist.barrier()
+    if local == 0:
+        try:
+            os.remove(path)
+        except OSError:
+            pass
+    return hb

@@ -263,3 +263,44 @@ def test_large_tree_takes_the_parallel_paths():
     fh = [np.stack([fast[f"c{k}hi{a}"] for a in "xyz"], axis=1).astype(np.float64) for k in (0, 1)]
     fc = [fast["child0"], fast["child1"]]
     check(len(fast), lambda i: [(int(fc[k][i]), fl[k][i], fh[k][i]) for k in (0, 1) if fl[k][i][0] <= fh[k][i][0]])
+
+
+def test_host_build_save_load_roundtrip(tmp_path, small_scene):
+    """Build once, create many: a saved build loads back bit for bit, a truncated or foreign file is refused, and a build is
+    refused for a scene it was not made from (take_gpu_scene_create_prebuilt checks the geometry hash BEFORE touching CUDA)."""
+    import ctypes as C
+    name, _, flat = small_scene
+    hb = api.HostBuild(flat)
+    path = str(tmp_path / "build.bin")
+    hb.save(path)
+    assert not os.path.exists(path + ".part")
+    a, b = hb.arrays(), api.HostBuild(path=path).arrays()
+    for k in ("ref_nodes", "dfs_rank", "fast_nodes", "wide_nodes", "leaf_prims", "leaf_records"):
+        assert np.array_equal(a[k], b[k]), k
+    assert (a["ref_root"], a["depth"], a["abs_max"]) == (b["ref_root"], b["depth"], b["abs_max"])
+    raw = open(path, "rb").read()
+    for bad in (raw[:len(raw) // 2], b"TAKEHB01" + raw[8:], raw + b"x", b""):
+        p2 = str(tmp_path / "bad.bin")
+        open(p2, "wb").write(bad)
+        with pytest.raises(api.TakeGpuError):
+            api.HostBuild(path=p2)
+    with pytest.raises(api.TakeGpuError):
+        api.HostBuild(path=str(tmp_path / "missing.bin"))
+    # a build of a different scene: refused with TAKE_E_INVALID (-1), whether or not a GPU is present
+    other = next(o for o in (scenes.cornell_box(16, 16, 1).flat(), scenes.multi_light(16, 16, 1, n_side=3).flat())
+                 if o.num_prims != flat.num_prims)
+    lib = api.load_library()
+    desc = other.to_desc()
+    h = C.c_void_p()
+    rc = lib.take_gpu_scene_create_prebuilt(0, C.byref(desc), hb.h, C.byref(h))
+    assert rc == -1 and b"do not belong" in lib.take_gpu_last_error()
+    # same counts, one vertex moved: the hash notices
+    import copy
+    moved = copy.copy(flat)
+    moved.positions = flat.positions.copy()
+    moved.positions[flat.indices[0, 0] if not (flat.prim_flags[0] & sceneio.PRIM_SPHERE) else 0] += 0.5
+    desc2 = moved.to_desc()
+    if flat.positions.size:
+        rc = lib.take_gpu_scene_create_prebuilt(0, C.byref(desc2), hb.h, C.byref(h))
+        assert rc == -1 and b"do not belong" in lib.take_gpu_last_error()
+    hb.close()

@@ -61,3 +61,33 @@ def test_sharded_render_equals_single_process(tmp_path, oracle_lib, world):
     var = np.maximum(s2 / spp - mean ** 2, 0) * spp / (spp - 1) / spp
     assert np.abs(got["var"] - var).max() <= 1e-9 * max(var.max(), 1e-30)
     assert int(got["n"]) == spp
+
+
+def _build_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["LOCAL_RANK"] = str(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from take_b200 import scenes
+    flat = scenes.multi_light(16, 16, 1, n_side=6).flat()
+    hb = tdist.shared_host_build(flat, path=os.path.join(out_dir, "shared.bin"))
+    a = hb.arrays()
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **{k: a[k] for k in ("ref_nodes", "dfs_rank", "wide_nodes", "leaf_prims", "leaf_records")},
+             ms_fast=a["ms_fast"])
+    hb.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shared_host_build_builds_once_per_node(tmp_path):
+    """take_b200.dist.shared_host_build: local rank 0 builds and saves, the other ranks load -- every rank ends up with the
+    same structures (the loaded ones carry rank 0's build times: they were not rebuilt) and the file is removed."""
+    world = 2
+    port = 29500 + (os.getpid() % 1000) + 17
+    mp.spawn(_build_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    for k in ("ref_nodes", "dfs_rank", "wide_nodes", "leaf_prims", "leaf_records"):
+        assert np.array_equal(r0[k], r1[k]), k
+    assert float(r0["ms_fast"]) == float(r1["ms_fast"])
+    assert not os.path.exists(tmp_path / "shared.bin")

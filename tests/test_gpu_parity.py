@@ -194,6 +194,30 @@ def test_render_properties(pair, monkeypatch):
     assert st["kernel_launches"] > 0 and st["extend_rays"] >= flat.width * flat.height * 4
 
 
+def test_prebuilt_scene_equals_built_in_place(pair, tmp_path):
+    """Build once, create many (take_gpu_host_build_save / _load / take_gpu_scene_create_prebuilt): a scene created from a
+    build that went through a file answers exactly like the scene that ran the builders itself."""
+    name, flat, gs, sc = pair
+    hb = api.HostBuild(flat)
+    path = str(tmp_path / "build.bin")
+    hb.save(path)
+    hb.close()
+    loaded = api.HostBuild(path=path)
+    gs2 = api.GpuScene(flat, prebuilt=loaded)
+    loaded.close()                                 # the scene keeps nothing of the handle
+    try:
+        rays = all_pixel_rays(sc, seed=21)
+        for exact in (False, True):
+            a, b = gs.intersect(rays, exact=exact), gs2.intersect(rays, exact=exact)
+            assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        for integ in ("mis", "one_sample_mis"):
+            s1, q1, st1 = gs.render_sums(integ, 5, 0, 3, seed=13)
+            s2, q2, st2 = gs2.render_sums(integ, 5, 0, 3, seed=13)
+            assert np.array_equal(s1, s2) and np.array_equal(q1, q2) and st1["extend_rays"] == st2["extend_rays"]
+    finally:
+        gs2.close()
+
+
 def test_async_render_equals_sync(pair):
     """take_gpu_render_async / _wait: two tickets in flight give the same buffers and counters as the blocking calls,
     a third is refused until the oldest is collected, tickets cannot be collected twice."""
