@@ -270,6 +270,11 @@ int take_gpu_host_build_save(TakeHostBuild *h, const char *path);
 int take_gpu_host_build_load(const char *path, TakeHostBuild **out);
 int take_gpu_scene_create_prebuilt(int device, const TakeSceneDesc *desc, TakeHostBuild *h, TakeScene **out);
 
+/* Self-test: the multi-threaded twin of std::sort used by the reference-order builder must return std::sort's exact
+ * permutation, ties included.  Returns the number of differing positions (0 = identical).  pattern: 0 random, 1 ascending,
+ * 2 descending, 3 all equal, 4 organ pipe; distinct: number of different key values (0 = all different). */
+int64_t take_gpu_selftest_sort(int64_t n, int64_t distinct, int32_t pattern, int32_t threads, uint64_t seed);
+
 const char *take_gpu_last_error(void);
 const char *take_gpu_version(void);
 

@@ -44,11 +44,55 @@ struct KeyId {
     int32_t id;
 };
 
+// std::sort, run on several threads, with the IDENTICAL result -- ties included.
+// The reference's tree depends on the order libstdc++'s introsort leaves equal keys in, so no other sorting algorithm may
+// stand in for it.  But introsort's recursion is a tree of independent sub-ranges: after a partition step the right part is
+// sorted by a recursive call and the left part by the next loop iteration (bits/stl_algo.h: __introsort_loop), with the same
+// remaining depth budget.  Running the two on different threads changes nothing about what either does.  The steps
+// themselves are libstdc++'s own (__unguarded_partition_pivot, __partial_sort for the heapsort fallback,
+// __final_insertion_sort), called in std::sort's order, so the sequence of comparisons and moves inside every sub-range
+// is the one std::sort performs.  Without libstdc++ this is plain std::sort.
+template <typename It, typename Cmp>
+void introsort_loop_forked(It first, It last, long depth_limit, Cmp comp, Forker &fork) {
+#if defined(__GLIBCXX__)
+    while (last - first > 16) {  // _S_threshold
+        if (depth_limit == 0) {
+            std::__partial_sort(first, last, last, comp);
+            return;
+        }
+        --depth_limit;
+        It cut = std::__unguarded_partition_pivot(first, last, comp);
+        if (last - first > (1 << 15)) {
+            const long d = depth_limit;
+            fork.both(true, [&, d] { introsort_loop_forked(cut, last, d, comp, fork); },
+                      [&, d] { introsort_loop_forked(first, cut, d, comp, fork); });
+            return;
+        }
+        introsort_loop_forked(cut, last, depth_limit, comp, fork);
+        last = cut;
+    }
+#endif
+}
+template <typename It, typename Less>
+void exact_std_sort(It first, It last, Less less, int threads) {
+#if defined(__GLIBCXX__)
+    if (threads > 1 && last - first > (1 << 16)) {
+        auto comp = __gnu_cxx::__ops::__iter_comp_iter(less);
+        Forker fork(threads);
+        introsort_loop_forked(first, last, (long)std::__lg(last - first) * 2, comp, fork);
+        std::__final_insertion_sort(first, last, comp);
+        return;
+    }
+#endif
+    std::sort(first, last, less);
+}
+
 struct RefBuilder {
     const Aabb *boxes;
     RefNode *nodes;
     int32_t *ids;
     Forker fork;
+    int top_threads = 1;
 
     int32_t build(int64_t lo, int64_t hi, int64_t base) {
         int64_t m = hi - lo;
@@ -81,7 +125,9 @@ struct RefBuilder {
             // The tie order among equal centroids is whatever libstdc++'s introsort yields for this sequence of
             // comparison outcomes; the reference sorts whole BBoxWithID values with the same comparator, so the
             // permutation is identical.
-            std::sort(tmp.begin(), tmp.end(), [](const KeyId &a, const KeyId &b) { return a.key < b.key; });
+            // (near the root, where this recursion offers no parallelism yet, the sort itself forks: exact_std_sort)
+            exact_std_sort(tmp.begin(), tmp.end(), [](const KeyId &a, const KeyId &b) { return a.key < b.key; },
+                           m >= (1 << 18) ? top_threads : 1);
             for (int64_t i = lo; i < hi; ++i) ids[i] = tmp[i - lo].id;
         }
         int64_t ml = m / 2, mr = m - ml;
@@ -650,6 +696,33 @@ struct FlattenerT {
 
 }  // namespace
 
+// Self-test of exact_std_sort (tests/test_capi_host.py): sorts `n` (key, id) pairs drawn from `distinct` different keys
+// (0: all keys different) in the given arrangement with std::sort and with the forked version, returns the number of
+// positions where the two results differ (must be 0).  pattern: 0 random, 1 ascending, 2 descending, 3 all equal,
+// 4 organ pipe.
+int64_t sort_selftest(int64_t n, int64_t distinct, int pattern, int threads, uint64_t seed) {
+    std::vector<KeyId> a((size_t)n);
+    uint64_t x = seed * 2862933555777941757ULL + 3037000493ULL;
+    for (int64_t i = 0; i < n; ++i) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        double k;
+        if (pattern == 1) k = (double)i;
+        else if (pattern == 2) k = (double)(n - i);
+        else if (pattern == 3) k = 1.0;
+        else if (pattern == 4) k = (double)(i < n / 2 ? i : n - i);
+        else k = (double)(x >> 11);
+        if (distinct > 0) k = fmod(k, (double)distinct);
+        a[i] = {k, (int32_t)i};
+    }
+    std::vector<KeyId> b(a);
+    auto less = [](const KeyId &p, const KeyId &q) { return p.key < q.key; };
+    std::sort(a.begin(), a.end(), less);
+    exact_std_sort(b.begin(), b.end(), less, threads);
+    int64_t bad = 0;
+    for (int64_t i = 0; i < n; ++i) bad += (a[i].id != b[i].id || a[i].key != b[i].key) ? 1 : 0;
+    return bad;
+}
+
 void build_reference_tree(const Aabb *boxes, int64_t n, int threads, RefTree &out) {
     out.nodes.clear();
     out.dfs_rank.clear();
@@ -659,6 +732,7 @@ void build_reference_tree(const Aabb *boxes, int64_t n, int threads, RefTree &ou
     std::vector<int32_t> ids((size_t)n);
     for (int64_t i = 0; i < n; ++i) ids[i] = (int32_t)i;
     RefBuilder b{boxes, out.nodes.data(), ids.data(), Forker(threads)};
+    b.top_threads = std::max(1, threads);
     out.root = b.build(0, n, 0);
     // After the recursion ids[] lists the primitives in left-to-right leaf order.
     out.dfs_rank.resize((size_t)n);

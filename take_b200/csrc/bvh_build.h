@@ -57,6 +57,8 @@ struct FastTree {
 };
 
 void build_reference_tree(const Aabb *boxes, int64_t n, int threads, RefTree &out);
+// std::sort vs. its forked twin on synthetic keys: number of differing positions (0 = identical)
+int64_t sort_selftest(int64_t n, int64_t distinct, int pattern, int threads, uint64_t seed);
 // pad: absolute outward padding applied to every FP32 box after outward rounding.
 // max_leaf <= 8 (the leaf code keeps count-1 in 3 bits); n < 2^28.
 void build_fast_tree(const Aabb *boxes, int64_t n, int max_leaf, float pad, int threads, FastTree &out);

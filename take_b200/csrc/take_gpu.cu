@@ -843,6 +843,10 @@ bool get(FILE *f, std::vector<T> &v, int64_t n) {
 
 extern "C" {
 
+int64_t take_gpu_selftest_sort(int64_t n, int64_t distinct, int32_t pattern, int32_t threads, uint64_t seed) {
+    return sort_selftest(n, distinct, pattern, threads, seed);
+}
+
 int take_gpu_host_build_save(TakeHostBuild *h, const char *path) {
     if (!h || !path) return fail(TAKE_E_INVALID, "null argument");
     const HostBuild &b = h->hb;

@@ -304,3 +304,15 @@ def test_host_build_save_load_roundtrip(tmp_path, small_scene):
         rc = lib.take_gpu_scene_create_prebuilt(0, C.byref(desc2), hb.h, C.byref(h))
         assert rc == -1 and b"do not belong" in lib.take_gpu_last_error()
     hb.close()
+
+
+@pytest.mark.parametrize("pattern,distinct", [(0, 0), (0, 1000), (0, 7), (1, 0), (2, 0), (3, 0), (4, 0), (4, 50), (1, 16)])
+def test_forked_sort_is_std_sort(pattern, distinct):
+    """The reference-order tree depends on the order libstdc++'s std::sort leaves EQUAL keys in (src/bvh.cpp:25-31), so the
+    multi-threaded sort used near the root must return std::sort's exact permutation -- on random keys, heavy ties,
+    presorted / reversed / constant / organ-pipe inputs."""
+    lib = api.load_library()
+    lib.take_gpu_selftest_sort.restype = C.c_int64
+    lib.take_gpu_selftest_sort.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_uint64]
+    for n in (70_000, 300_001):
+        assert lib.take_gpu_selftest_sort(n, distinct, pattern, 4, 12345 + n) == 0
