@@ -44,6 +44,18 @@ struct KeyId {
     int32_t id;
 };
 
+// f(tid, a, b) over [lo, hi) split into `parts` contiguous chunks on their own threads (the huge ranges at the top of a
+// tree, where the recursion itself offers no parallelism yet)
+template <typename F>
+void run_chunks(int64_t lo, int64_t hi, int parts, F f) {
+    if (parts <= 1) { f(0, lo, hi); return; }
+    std::vector<std::thread> pool;
+    const int64_t m = hi - lo;
+    for (int t = 1; t < parts; ++t) pool.emplace_back(f, t, lo + m * t / parts, lo + m * (t + 1) / parts);
+    f(0, lo, lo + m / parts);
+    for (auto &t : pool) t.join();
+}
+
 // std::sort, run on several threads, with the IDENTICAL result -- ties included.
 // The reference's tree depends on the order libstdc++'s introsort leaves equal keys in, so no other sorting algorithm may
 // stand in for it.  But introsort's recursion is a tree of independent sub-ranges: after a partition step the right part is
@@ -105,30 +117,48 @@ struct RefBuilder {
             n.pad = 0;
             return (int32_t)base;
         }
+        // near the root the per-primitive passes run in chunks on all threads (the recursion has not fanned out yet)
+        const int parts = m >= (1 << 18) ? std::min<int>(top_threads, (int)(m >> 16)) : 1;
         RefNode big;
         for (int a = 0; a < 3; ++a) { big.lo[a] = INFINITY; big.hi[a] = -INFINITY; }
-        for (int64_t i = lo; i < hi; ++i) {  // merge(), src/bbox.h:45-55
-            const Aabb &b = boxes[ids[i]];
-            for (int a = 0; a < 3; ++a) {
-                big.lo[a] = std::min(big.lo[a], b.lo[a]);
-                big.hi[a] = std::max(big.hi[a], b.hi[a]);
-            }
+        {   // merge(), src/bbox.h:45-55 (min / max are exact: the order of the union does not matter)
+            std::vector<RefNode> part((size_t)parts, big);
+            run_chunks(lo, hi, parts, [&](int tid, int64_t a0, int64_t a1) {
+                RefNode t = part[tid];
+                for (int64_t i = a0; i < a1; ++i) {
+                    const Aabb &b = boxes[ids[i]];
+                    for (int a = 0; a < 3; ++a) {
+                        t.lo[a] = std::min(t.lo[a], b.lo[a]);
+                        t.hi[a] = std::max(t.hi[a], b.hi[a]);
+                    }
+                }
+                part[tid] = t;
+            });
+            for (int t = 0; t < parts; ++t)
+                for (int a = 0; a < 3; ++a) {
+                    big.lo[a] = std::min(big.lo[a], part[t].lo[a]);
+                    big.hi[a] = std::max(big.hi[a], part[t].hi[a]);
+                }
         }
         double ex = big.hi[0] - big.lo[0], ey = big.hi[1] - big.lo[1], ez = big.hi[2] - big.lo[2];
         int axis = (ex > ey && ex > ez) ? 0 : (ey > ex && ey > ez) ? 1 : 2;  // largest_axis(), bbox.h:34-43
         {
             std::vector<KeyId> tmp((size_t)m);
-            for (int64_t i = lo; i < hi; ++i) {
-                const Aabb &b = boxes[ids[i]];
-                tmp[i - lo] = {(b.hi[axis] + b.lo[axis]) * 0.5, ids[i]};  // centre = (p_max + p_min) * (1/2)
-            }
+            run_chunks(lo, hi, parts, [&](int, int64_t a0, int64_t a1) {
+                for (int64_t i = a0; i < a1; ++i) {
+                    const Aabb &b = boxes[ids[i]];
+                    tmp[i - lo] = {(b.hi[axis] + b.lo[axis]) * 0.5, ids[i]};  // centre = (p_max + p_min) * (1/2)
+                }
+            });
             // The tie order among equal centroids is whatever libstdc++'s introsort yields for this sequence of
             // comparison outcomes; the reference sorts whole BBoxWithID values with the same comparator, so the
             // permutation is identical.
             // (near the root, where this recursion offers no parallelism yet, the sort itself forks: exact_std_sort)
             exact_std_sort(tmp.begin(), tmp.end(), [](const KeyId &a, const KeyId &b) { return a.key < b.key; },
                            m >= (1 << 18) ? top_threads : 1);
-            for (int64_t i = lo; i < hi; ++i) ids[i] = tmp[i - lo].id;
+            run_chunks(lo, hi, parts, [&](int, int64_t a0, int64_t a1) {
+                for (int64_t i = a0; i < a1; ++i) ids[i] = tmp[i - lo].id;
+            });
         }
         int64_t ml = m / 2, mr = m - ml;
         int64_t mid = lo + ml;
@@ -237,14 +267,7 @@ struct SahBuilder {
     // Run f(tid, a, b) over [lo, hi) split into `parts` contiguous chunks on their own threads (used only for the few huge
     // ranges at the top of the tree, where the recursion itself offers no parallelism yet).
     template <typename F>
-    static void chunked(int64_t lo, int64_t hi, int parts, F f) {
-        if (parts <= 1) { f(0, lo, hi); return; }
-        std::vector<std::thread> pool;
-        const int64_t m = hi - lo;
-        for (int t = 1; t < parts; ++t) pool.emplace_back(f, t, lo + m * t / parts, lo + m * (t + 1) / parts);
-        f(0, lo, lo + m / parts);
-        for (auto &t : pool) t.join();
-    }
+    static void chunked(int64_t lo, int64_t hi, int parts, F f) { run_chunks(lo, hi, parts, f); }
     int top_threads = 1;  // threads for the chunked top-level loops
 
     struct Bins {
