@@ -27,6 +27,7 @@ L = ["# profiles/ — round 1\n",
      "| `r01_ncu_extend.csv`, `r01_ncu_shade.csv`, `r01_ncu_shadow.csv` | key metrics of `ncu --set full` captures of `tools/prof_run.py` (one bench-sized wave: 16 spp x 1920x1080 = 33.2 M slots) |",
      "| `extend_traffic.json` | DRAM bytes per `k_extend` launch (mean over the 7 launches of that wave) — `roofline.traffic` in bench.py |",
      "| `r01_prof_run_counts.txt` | box / leaf test counts of the same wave (instrumented kernels) |",
+     "| `r01_ncu_shade_mis_config4.csv`, `r01_ncu_traversal_config5.csv` | `tools/ncu_stalls.py` summaries (key metrics + stall-reason shares per launch) of two more `ncu --set full` captures taken earlier in the round (before the light records and the unsorted any-hit traversal): the multi-sample shade kernel on the config-4 scene (`prof_run.py --scene=multi_light --integrator=mis --spp=16`, passes 0-2) and `k_extend` / `k_shadow` on the 10 M-triangle scene (`--scene=instanced --spp=4`, passes 0-1) -- the numbers DESIGN.md sections 5.2 / 5.3 quote for those scenes |",
      "| `r01_report_scenes.jsonl` | throughput of all five BASELINE configs next to the CPU renderer (tools/report_scenes.py) |",
      "| `r01_scale_*.json` | `bench.py` at N = 1, 2, 4, 8 GPUs where a box was available |\n",
      "## Share of a step (launch list vs. bench.py's own CUDA-event stage times)\n",
