@@ -21,10 +21,11 @@ struct Forker {
     template <typename A, typename B>
     void both(bool big, A left, B right) {
         if (big && budget.fetch_sub(1) > 0) {
-            std::thread t(left);
+            // the slot goes back the moment the forked side is done -- not when both are -- so that the side still
+            // running can fork again at its next big node (SAH splits are far from balanced)
+            std::thread t([&] { left(); budget.fetch_add(1); });
             right();
             t.join();
-            budget.fetch_add(1);
         } else {
             if (big) budget.fetch_add(1);
             left();
