@@ -825,12 +825,23 @@ int take_gpu_host_build_free(TakeHostBuild *h) {
 // ---- build once, create many (one process per GPU: a single rank runs the host builders) ---------------------------
 namespace {
 struct HbHeader {
-    char magic[8];           // "TAKEHB02"
+    char magic[8];           // "TAKEHB03"
     uint64_t geom_hash;
     int64_t num_prims, n_ref, n_rank, n_fast, n_wide, n_leaf, n_tris;
     int32_t ref_root, depth, wide_depth, pad;
     double sah_cost, abs_max, ms_ref, ms_fast;
+    uint64_t payload_hash;   // of the arrays that follow (the links in them are trusted by the device code)
 };
+uint64_t payload_hash(const HostBuild &b) {
+    const int threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    uint64_t h[6] = {hash_array(b.ref.nodes.data(), b.ref.nodes.size() * sizeof(RefNode), threads),
+                     hash_array(b.ref.dfs_rank.data(), b.ref.dfs_rank.size() * 4, threads),
+                     hash_array(b.fast.nodes.data(), b.fast.nodes.size() * sizeof(FastNode), threads),
+                     hash_array(b.fast.wide.data(), b.fast.wide.size() * sizeof(WideNode), threads),
+                     hash_array(b.fast.leaf_prims.data(), b.fast.leaf_prims.size() * 4, threads),
+                     hash_array(b.tris.data(), b.tris.size() * 8, threads)};
+    return fnv1a(h, sizeof(h));
+}
 template <typename T>
 bool put(FILE *f, const std::vector<T> &v) { return v.empty() || fwrite(v.data(), sizeof(T), v.size(), f) == v.size(); }
 template <typename T>
@@ -852,7 +863,8 @@ int take_gpu_host_build_save(TakeHostBuild *h, const char *path) {
     const HostBuild &b = h->hb;
     HbHeader hd;
     memset(&hd, 0, sizeof(hd));
-    memcpy(hd.magic, "TAKEHB02", 8);
+    memcpy(hd.magic, "TAKEHB03", 8);
+    hd.payload_hash = payload_hash(b);
     hd.geom_hash = b.geom_hash; hd.num_prims = b.num_prims;
     hd.n_ref = (int64_t)b.ref.nodes.size(); hd.n_rank = (int64_t)b.ref.dfs_rank.size(); hd.n_fast = (int64_t)b.fast.nodes.size();
     hd.n_wide = (int64_t)b.fast.wide.size(); hd.n_leaf = (int64_t)b.fast.leaf_prims.size(); hd.n_tris = (int64_t)b.tris.size();
@@ -876,7 +888,7 @@ int take_gpu_host_build_load(const char *path, TakeHostBuild **out) {
     HbHeader hd;
     TakeHostBuild *h = new TakeHostBuild;
     HostBuild &b = h->hb;
-    bool ok = fread(&hd, sizeof(hd), 1, f) == 1 && memcmp(hd.magic, "TAKEHB02", 8) == 0;
+    bool ok = fread(&hd, sizeof(hd), 1, f) == 1 && memcmp(hd.magic, "TAKEHB03", 8) == 0;
     // sizes are fixed by the primitive count: anything else is not a file this library wrote
     ok = ok && hd.num_prims >= 0 && hd.num_prims < (1 << 28) && hd.n_leaf == hd.num_prims && hd.n_rank == hd.num_prims &&
          hd.n_tris == 12 * hd.num_prims && hd.n_ref == (hd.num_prims > 0 ? 2 * hd.num_prims - 1 : 0) && hd.n_fast >= 1 &&
@@ -885,6 +897,7 @@ int take_gpu_host_build_load(const char *path, TakeHostBuild **out) {
          get(f, b.fast.wide, hd.n_wide) && get(f, b.fast.leaf_prims, hd.n_leaf) && get(f, b.tris, hd.n_tris);
     ok = ok && fgetc(f) == EOF;
     fclose(f);
+    ok = ok && payload_hash(b) == hd.payload_hash;
     if (!ok) { delete h; return fail(TAKE_E_INVALID, std::string("not a host-build file of this library: ") + path); }
     b.geom_hash = hd.geom_hash; b.num_prims = hd.num_prims; b.ref.root = hd.ref_root; b.fast.depth = hd.depth;
     b.fast.wide_depth = hd.wide_depth; b.fast.sah_cost = hd.sah_cost; b.abs_max = hd.abs_max; b.ms_ref = hd.ms_ref; b.ms_fast = hd.ms_fast;

@@ -279,7 +279,9 @@ def test_host_build_save_load_roundtrip(tmp_path, small_scene):
         assert np.array_equal(a[k], b[k]), k
     assert (a["ref_root"], a["depth"], a["abs_max"]) == (b["ref_root"], b["depth"], b["abs_max"])
     raw = open(path, "rb").read()
-    for bad in (raw[:len(raw) // 2], b"TAKEHB01" + raw[8:], raw + b"x", b""):
+    flipped = bytearray(raw)
+    flipped[len(raw) // 2] ^= 0x40                                   # one bit inside an array: the payload hash notices
+    for bad in (raw[:len(raw) // 2], b"TAKEHB01" + raw[8:], raw + b"x", b"", bytes(flipped)):
         p2 = str(tmp_path / "bad.bin")
         open(p2, "wb").write(bad)
         with pytest.raises(api.TakeGpuError):
