@@ -38,6 +38,21 @@ if [ $rc -eq 0 ] && [ "${SKIP_NCU:-0}" != "1" ]; then
     echo "ncu shadow exit $?"
   fi
 fi
+if [ "${EXTRA_NCU:-0}" = "1" ]; then
+  # the two captures behind profiles/r01_ncu_shade_mis_config4.csv and r01_ncu_traversal_config5.csv (tools/ncu_stalls.py)
+  A4="--scene=multi_light --integrator=mis --spp=16"
+  A5="--scene=instanced --integrator=mis --spp=4"
+  if timeout 300 python tools/prof_run.py $A4 > $O/prof_run_c4.log 2>&1; then
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_shade -c 3 -f -o $O/prof_shade_mis \
+        python tools/prof_run.py $A4 > $O/ncu_shade_mis.log 2>&1
+    echo "ncu shade (config 4) exit $?"
+  fi
+  if timeout 300 python tools/prof_run.py $A5 > $O/prof_run_c5.log 2>&1; then
+    timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:k_extend|k_shadow' -c 4 -f -o $O/prof_inst \
+        python tools/prof_run.py $A5 > $O/ncu_inst.log 2>&1
+    echo "ncu traversal (config 5) exit $?"
+  fi
+fi
 if [ "${REPORT_SCENES:-0}" = "1" ]; then
   timeout 900 python tools/report_scenes.py > $O/report_scenes.jsonl 2> $O/report_scenes.err
   echo "report_scenes exit $?"
