@@ -86,10 +86,15 @@ void introsort_loop_forked(It first, It last, long depth_limit, Cmp comp, Forker
     }
 #endif
 }
+// The forked twin leans on libstdc++ internals; a different libstdc++ could change them under our feet.  So before its
+// first use in a process it is checked against plain std::sort on a few adversarial inputs (heavy ties, presorted, organ
+// pipe; ~10 ms): if any position differs -- or TAKE_PLAIN_STD_SORT is set -- every call falls back to std::sort itself.
+bool forked_sort_trusted();
+
 template <typename It, typename Less>
-void exact_std_sort(It first, It last, Less less, int threads) {
+void exact_std_sort(It first, It last, Less less, int threads, bool checked = true) {
 #if defined(__GLIBCXX__)
-    if (threads > 1 && last - first > (1 << 16)) {
+    if (threads > 1 && last - first > (1 << 16) && (!checked || forked_sort_trusted())) {
         auto comp = __gnu_cxx::__ops::__iter_comp_iter(less);
         Forker fork(threads);
         introsort_loop_forked(first, last, (long)std::__lg(last - first) * 2, comp, fork);
@@ -724,7 +729,30 @@ struct FlattenerT {
 // (0: all keys different) in the given arrangement with std::sort and with the forked version, returns the number of
 // positions where the two results differ (must be 0).  pattern: 0 random, 1 ascending, 2 descending, 3 all equal,
 // 4 organ pipe.
+static int64_t sort_selftest_impl(int64_t n, int64_t distinct, int pattern, int threads, uint64_t seed, bool checked);
 int64_t sort_selftest(int64_t n, int64_t distinct, int pattern, int threads, uint64_t seed) {
+    return sort_selftest_impl(n, distinct, pattern, threads, seed, true);
+}
+namespace {
+bool forked_sort_trusted() {
+    static const bool ok = [] {
+        const char *e = getenv("TAKE_PLAIN_STD_SORT");
+        if (e && *e && *e != '0') return false;
+        const int64_t n = (1 << 16) + 4321;  // just above the size from which exact_std_sort forks
+        int64_t bad = 0;
+        bad += sort_selftest_impl(n, 0, 0, 4, 1, false);      // random, all different
+        bad += sort_selftest_impl(n, 7, 0, 4, 2, false);      // heavy ties
+        bad += sort_selftest_impl(n, 0, 1, 4, 3, false);      // ascending
+        bad += sort_selftest_impl(n, 0, 4, 4, 4, false);      // organ pipe (drives introsort towards its heapsort fallback)
+        bad += sort_selftest_impl(n, 1000, 2, 4, 5, false);   // descending with ties
+        if (bad) fprintf(stderr, "[take_gpu] the multi-threaded twin of std::sort disagrees with this libstdc++'s std::sort: "
+                                 "using plain std::sort for the reference-order tree\n");
+        return bad == 0;
+    }();
+    return ok;
+}
+}  // namespace
+static int64_t sort_selftest_impl(int64_t n, int64_t distinct, int pattern, int threads, uint64_t seed, bool checked) {
     std::vector<KeyId> a((size_t)n);
     uint64_t x = seed * 2862933555777941757ULL + 3037000493ULL;
     for (int64_t i = 0; i < n; ++i) {
@@ -741,7 +769,7 @@ int64_t sort_selftest(int64_t n, int64_t distinct, int pattern, int threads, uin
     std::vector<KeyId> b(a);
     auto less = [](const KeyId &p, const KeyId &q) { return p.key < q.key; };
     std::sort(a.begin(), a.end(), less);
-    exact_std_sort(b.begin(), b.end(), less, threads);
+    exact_std_sort(b.begin(), b.end(), less, threads, checked);
     int64_t bad = 0;
     for (int64_t i = 0; i < n; ++i) bad += (a[i].id != b[i].id || a[i].key != b[i].key) ? 1 : 0;
     return bad;

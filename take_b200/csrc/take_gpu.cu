@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <new>
 #include <string>
 #include <mutex>
 #include <thread>
@@ -91,7 +92,7 @@ struct TakeScene {
     int64_t next_ticket = 0;
     cudaEvent_t ev_acc[2] = {nullptr, nullptr}, ev_begin = nullptr;
     int64_t wave_capacity = 0;
-    int wave_sets = 0;
+    int wave_sets = 0, wave_passes = 0;
     int blocks_extend = 0, blocks_shadow = 0, blocks_isect = 0, blocks_occl = 0;
     int blocks_extend2 = 0, blocks_shadow2 = 0, blocks_isect2 = 0, blocks_occl2 = 0, blocks_extend2w = 0, blocks_shadow2w = 0;
     int persist_from_pass = 1, persist_shadow = 0;
@@ -138,11 +139,22 @@ double now_ms() {
 int validate(const TakeSceneDesc *d) {
     if (!d) return fail(TAKE_E_INVALID, "null scene description");
     if (d->camera.width <= 0 || d->camera.height <= 0) return fail(TAKE_E_INVALID, "camera resolution must be positive");
-    if (d->num_prims < 0 || d->num_vertices < 0 || d->num_spheres < 0) return fail(TAKE_E_INVALID, "negative count");
+    if (d->num_prims < 0 || d->num_vertices < 0 || d->num_spheres < 0 || d->num_materials < 0 || d->num_lights < 0 ||
+        d->num_textures < 0)
+        return fail(TAKE_E_INVALID, "negative count");
     if (d->num_prims >= (1 << 28)) return fail(TAKE_E_INVALID, "too many primitives (limit 2^28)");
     if (d->num_prims > 0 && (!d->indices || !d->prim_material || !d->prim_light || !d->prim_flags))
         return fail(TAKE_E_INVALID, "primitive arrays missing");
     if (d->num_vertices > 0 && (!d->positions || !d->normals || !d->uvs)) return fail(TAKE_E_INVALID, "vertex arrays missing");
+    if (d->num_spheres > 0 && !d->spheres) return fail(TAKE_E_INVALID, "sphere array missing");
+    if (d->num_materials > 0 && !d->materials) return fail(TAKE_E_INVALID, "material array missing");
+    if (d->num_lights > 0 && !d->lights) return fail(TAKE_E_INVALID, "light array missing");
+    if (d->num_textures > 0 && !d->textures) return fail(TAKE_E_INVALID, "texture array missing");
+    // coordinates must be finite: an infinite or NaN extent would poison the conservative padding of every box test
+    for (int64_t i = 0; i < 3 * d->num_vertices; ++i)
+        if (!std::isfinite(d->positions[i])) return fail(TAKE_E_INVALID, "non-finite vertex position");
+    for (int64_t i = 0; i < 4 * d->num_spheres; ++i)
+        if (!std::isfinite(d->spheres[i])) return fail(TAKE_E_INVALID, "non-finite sphere");
     for (int64_t i = 0; i < d->num_prims; ++i) {
         const int32_t *id = d->indices + 3 * i;
         if (d->prim_flags[i] & TAKE_PRIM_SPHERE) {
@@ -160,9 +172,12 @@ int validate(const TakeSceneDesc *d) {
         if (m.type < 0 || m.type > TAKE_MAT_GGX) return fail(TAKE_E_INVALID, "unknown material type");
         if (m.tex_id >= d->num_textures) return fail(TAKE_E_INVALID, "texture id out of range");
     }
+    for (int i = 0; i < d->num_textures; ++i)
+        if (d->textures[i].width <= 0 || d->textures[i].height <= 0 || !d->textures[i].rgb) return fail(TAKE_E_INVALID, "bad texture");
     if (d->env_rgb && (d->env_width <= 0 || d->env_height <= 0)) return fail(TAKE_E_INVALID, "bad environment map size");
     for (int i = 0; i < d->num_lights; ++i) {
         const TakeLightDesc &l = d->lights[i];
+        if (l.kind != TAKE_LIGHT_AREA && l.kind != TAKE_LIGHT_POINT) return fail(TAKE_E_INVALID, "unknown light kind");
         if (l.kind == TAKE_LIGHT_AREA && (l.prim_id < 0 || l.prim_id >= d->num_prims))
             return fail(TAKE_E_INVALID, "area light primitive out of range");
     }
@@ -246,6 +261,7 @@ int host_build(const TakeSceneDesc *d, int threads, HostBuild &hb) {
         std::lock_guard<std::mutex> g(abs_mu);
         abs_max = std::max(abs_max, amax);
     });
+    if (!std::isfinite(abs_max)) return fail(TAKE_E_INVALID, "non-finite scene extent");
     hb.abs_max = abs_max;
     hb.num_prims = n;
     hb.geom_hash = geometry_hash(d, threads);
@@ -293,10 +309,13 @@ int host_build(const TakeSceneDesc *d, int threads, HostBuild &hb) {
     return TAKE_OK;
 }
 
-int ensure_wave(TakeScene *s, int64_t capacity, int sets) {
-    if (capacity <= s->wave_capacity && sets <= s->wave_sets) return TAKE_OK;
+// `passes`: extend passes of a wave (max_depth + 2); every pass owns a PassCounters block, and the shade kernel of the last
+// pass still addresses the block after it.
+int ensure_wave(TakeScene *s, int64_t capacity, int sets, int passes) {
+    if (capacity <= s->wave_capacity && sets <= s->wave_sets && passes <= s->wave_passes) return TAKE_OK;
     capacity = std::max(capacity, s->wave_capacity);
     sets = std::max(sets, s->wave_sets);
+    passes = std::max(passes, s->wave_passes);
     for (int i = 0; i < sets; ++i) {
         TakeScene::WaveBuffers &b = s->wb[i];
         CU(b.ray.ensure(capacity * sizeof(RayRec)));
@@ -308,11 +327,12 @@ int ensure_wave(TakeScene *s, int64_t capacity, int sets) {
         CU(b.q0.ensure(capacity * 4));
         CU(b.q1.ensure(capacity * 4));
         CU(b.q_shadow.ensure(capacity * 4));
-        CU(b.pass.ensure(sizeof(PassCounters) * TAKE_MAX_PASSES));
+        CU(b.pass.ensure(sizeof(PassCounters) * (size_t)(passes + 1)));
     }
     CU(s->totals.ensure(sizeof(Totals)));
     s->wave_capacity = capacity;
     s->wave_sets = sets;
+    s->wave_passes = passes;
     return TAKE_OK;
 }
 
@@ -322,7 +342,8 @@ struct StageTimer {
     std::vector<cudaEvent_t> ev;
     std::vector<int> stage, pass_of;
     double ms[6] = {0, 0, 0, 0, 0, 0};
-    double ms_pass[6][TAKE_MAX_PASSES] = {};
+    enum { PASS_COLS = 16 };  // per-pass breakdown of the first passes (development aid); later passes fold into the last column
+    double ms_pass[6][PASS_COLS] = {};
     int cur_pass = 0;
     void begin(int st) {
         if (!on) return;
@@ -347,7 +368,7 @@ struct StageTimer {
             float t = 0;
             cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]);
             ms[stage[i]] += t;
-            ms_pass[stage[i]][pass_of[i]] += t;
+            ms_pass[stage[i]][std::min(pass_of[i], (int)PASS_COLS - 1)] += t;
         }
         if (env_int("TAKE_PASS_TIMES", 0)) {  // development aid: per-pass stage times on stderr
             static const char *names[6] = {"generate", "extend", "shade", "shadow", "sort", "other"};
@@ -373,17 +394,20 @@ int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, d
     tm.stream = st;
     const int n_passes = o->max_depth + 2;
     CU(cudaMemsetAsync(w.pass, 0, sizeof(PassCounters) * (size_t)(n_passes + 1), st));
+#if TAKE_EXPERIMENTAL
     if (!w.fused_primary) {
         tm.begin(ST_GENERATE);
         k_generate<<<(w.n_slots + 255) / 256, 256, 0, st>>>(s->dev, w);
         tm.end();
         launches++;
     }
+#endif
     const int shade_blocks = std::max(1, std::min((w.n_slots + 127) / 128, s->sm_count * 64));
     const int scatter_blocks = std::max(1, std::min((w.n_slots + 255) / 256, s->sm_count * 16));
     for (int b = 0; b < n_passes; ++b) {
         tm.cur_pass = b;
         tm.begin(ST_EXTEND);
+#if TAKE_EXPERIMENTAL
         if (s->traversal == 2) {
             if (count) k_extend2<true, false><<<s->blocks_extend2, 128, 0, st>>>(s->dev, w, b);
             else k_extend2<false, false><<<s->blocks_extend2, 128, 0, st>>>(s->dev, w, b);
@@ -391,14 +415,14 @@ int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, d
             // hybrid: bounce passes (rays of very different lengths) on the warp-persistent kernel with lane refill
             if (count) k_extend2<true, true><<<s->blocks_extend2w, 128, 0, st>>>(s->dev, w, b);
             else k_extend2<false, true><<<s->blocks_extend2w, 128, 0, st>>>(s->dev, w, b);
-        } else {
-            if (s->wide) {
-                if (count) k_extend<true, true><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
-                else k_extend<false, true><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
-            } else {
-                if (count) k_extend<true, false><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
-                else k_extend<false, false><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
-            }
+        } else if (!s->wide) {
+            if (count) k_extend<true, false><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
+            else k_extend<false, false><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
+        } else
+#endif
+        {
+            if (count) k_extend<true, true><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
+            else k_extend<false, true><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
         }
         tm.end();
         if (w.sort_enabled) {
@@ -418,20 +442,21 @@ int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, d
         launches += 2;
         if (o->integrator == TAKE_INTEGRATOR_MIS && b <= o->max_depth) {
             tm.begin(ST_SHADOW);
+#if TAKE_EXPERIMENTAL
             if (s->traversal == 2) {
                 if (count) k_shadow2<true, false><<<s->blocks_shadow2, 128, 0, st>>>(s->dev, w, b);
                 else k_shadow2<false, false><<<s->blocks_shadow2, 128, 0, st>>>(s->dev, w, b);
             } else if (s->traversal == 3 && s->wide && s->persist_shadow) {
                 if (count) k_shadow2<true, true><<<s->blocks_shadow2w, 128, 0, st>>>(s->dev, w, b);
                 else k_shadow2<false, true><<<s->blocks_shadow2w, 128, 0, st>>>(s->dev, w, b);
-            } else {
-                if (s->wide) {
-                    if (count) k_shadow<true, true><<<s->blocks_shadow, 128, 0, st>>>(s->dev, w, b);
-                    else k_shadow<false, true><<<s->blocks_shadow, 128, 0, st>>>(s->dev, w, b);
-                } else {
-                    if (count) k_shadow<true, false><<<s->blocks_shadow, 128, 0, st>>>(s->dev, w, b);
-                    else k_shadow<false, false><<<s->blocks_shadow, 128, 0, st>>>(s->dev, w, b);
-                }
+            } else if (!s->wide) {
+                if (count) k_shadow<true, false><<<s->blocks_shadow, 128, 0, st>>>(s->dev, w, b);
+                else k_shadow<false, false><<<s->blocks_shadow, 128, 0, st>>>(s->dev, w, b);
+            } else
+#endif
+            {
+                if (count) k_shadow<true, true><<<s->blocks_shadow, 128, 0, st>>>(s->dev, w, b);
+                else k_shadow<false, true><<<s->blocks_shadow, 128, 0, st>>>(s->dev, w, b);
             }
             tm.end();
             launches++;
@@ -469,8 +494,11 @@ void fill_wave_ptrs(TakeScene *s, Wave &w, const TakeRenderOpts *o, int set = 0)
     w.sort_branch = (w.sort_enabled && o->integrator == TAKE_INTEGRATOR_ONE_SAMPLE_MIS && n_pick > 0 &&
                      !env_int("TAKE_NO_SORT_BRANCH", 0)) ? 1 : 0;
     w.seed = o->seed;
-    // explicit sample lists (take_gpu_radiance_samples) and the v2 traversal keep the separate generate kernel
+#if TAKE_EXPERIMENTAL
     w.fused_primary = (s->traversal != 2 && !env_int("TAKE_NO_FUSE", 0)) ? 1 : 0;
+#else
+    w.fused_primary = 1;  // pass 0 of extend / shade computes the camera ray itself (no generate pass)
+#endif
     w.tile_w = (s->width % 8 == 0 && s->height % 4 == 0 && !env_int("TAKE_NO_TILES", 0)) ? s->width : 0;
     // camera rays that miss are finished inside k_extend (the environment-map extension needs their direction in the
     // shade kernel, and the unsorted debugging mode walks every slot, so both keep the general path)
@@ -505,8 +533,10 @@ int check_opts(const TakeScene *s, const TakeRenderOpts *o) {
     if (!s || !o) return fail(TAKE_E_INVALID, "null argument");
     if (o->integrator < TAKE_INTEGRATOR_MIS || o->integrator > TAKE_INTEGRATOR_ONE_SAMPLE_MIS)
         return fail(TAKE_E_INVALID, "unknown integrator");
-    if (o->max_depth < -1 || o->max_depth + 3 > TAKE_MAX_PASSES)
-        return fail(TAKE_E_INVALID, "max_depth out of range (-1 .. " + std::to_string(TAKE_MAX_PASSES - 3) + ")");
+    // the reference accepts any -max_depth (render.cpp:14-19); every pass of a wave costs four (mostly empty) launches and a
+    // 256-byte counter block, so the bound here is only a sanity limit
+    if (o->max_depth < -1 || o->max_depth > TAKE_MAX_DEPTH)
+        return fail(TAKE_E_INVALID, "max_depth out of range (-1 .. " + std::to_string(TAKE_MAX_DEPTH) + ")");
     if (o->spp_end < o->spp_begin) return fail(TAKE_E_INVALID, "spp_end < spp_begin");
     return TAKE_OK;
 }
@@ -593,7 +623,9 @@ static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild &hb, 
     for (int64_t i = 0; i < n; ++i) mtype[i] = (uint8_t)d->materials[d->prim_material[i]].type;
 
     int rc;
-    if ((rc = upload(s->nodes, fast.nodes.data(), fast.nodes.size(), st))) return rc;
+#if TAKE_EXPERIMENTAL
+    if ((rc = upload(s->nodes, fast.nodes.data(), fast.nodes.size(), st))) return rc;  // binary image: A/B runs only
+#endif
     if ((rc = upload(s->wide_nodes, fast.wide.data(), fast.wide.size(), st))) return rc;
     if ((rc = upload(s->tris, tris.data(), tris.size(), st))) return rc;
     if ((rc = upload(s->ref_nodes, ref.nodes.data(), ref.nodes.size(), st))) return rc;
@@ -725,13 +757,13 @@ static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild &hb, 
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
         return per_sm * s->sm_count;
     };
+    s->blocks_extend = blocks_for((const void *)k_extend<false, true>);
+    s->blocks_shadow = blocks_for((const void *)k_shadow<false, true>);
+    s->blocks_isect = blocks_for((const void *)k_intersect_fast<false, true>);
+    s->blocks_occl = blocks_for((const void *)k_intersect_fast<true, true>);
+#if TAKE_EXPERIMENTAL
     s->wide = env_int("TAKE_BVH_WIDTH", 4) == 4;
-    if (s->wide) {
-        s->blocks_extend = blocks_for((const void *)k_extend<false, true>);
-        s->blocks_shadow = blocks_for((const void *)k_shadow<false, true>);
-        s->blocks_isect = blocks_for((const void *)k_intersect_fast<false, true>);
-        s->blocks_occl = blocks_for((const void *)k_intersect_fast<true, true>);
-    } else {
+    if (!s->wide) {
         s->blocks_extend = blocks_for((const void *)k_extend<false, false>);
         s->blocks_shadow = blocks_for((const void *)k_shadow<false, false>);
         s->blocks_isect = blocks_for((const void *)k_intersect_fast<false, false>);
@@ -750,6 +782,7 @@ static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild &hb, 
         s->persist_from_pass = std::max(1, env_int("TAKE_PERSIST_FROM", 1));
         s->persist_shadow = env_int("TAKE_PERSIST_SHADOW", 0);
     }
+#endif
     CU(s->fetch.ensure(256));
     apply_l2_policy(s, s->stream);
     guard.ok = true;
@@ -825,12 +858,13 @@ int take_gpu_host_build_free(TakeHostBuild *h) {
 // ---- build once, create many (one process per GPU: a single rank runs the host builders) ---------------------------
 namespace {
 struct HbHeader {
-    char magic[8];           // "TAKEHB03"
+    char magic[8];           // "TAKEHB04"
     uint64_t geom_hash;
     int64_t num_prims, n_ref, n_rank, n_fast, n_wide, n_leaf, n_tris;
     int32_t ref_root, depth, wide_depth, pad;
     double sah_cost, abs_max, ms_ref, ms_fast;
     uint64_t payload_hash;   // of the arrays that follow (the links in them are trusted by the device code)
+    uint64_t header_hash;    // of this header with both hash fields zeroed
 };
 uint64_t payload_hash(const HostBuild &b) {
     const int threads = (int)std::max(1u, std::thread::hardware_concurrency());
@@ -858,20 +892,31 @@ int64_t take_gpu_selftest_sort(int64_t n, int64_t distinct, int32_t pattern, int
     return sort_selftest(n, distinct, pattern, threads, seed);
 }
 
+// The header is hashed too (with its own hash field zeroed): the scalars in it are trusted by the device code as much as
+// the arrays are -- ref_root is dereferenced by the exact traversal, abs_max sizes the conservative padding of every box
+// test, the depths bound the traversal stack.
+static uint64_t header_hash(HbHeader hd) {
+    hd.payload_hash = 0;
+    hd.header_hash = 0;
+    return fnv1a(&hd, sizeof(hd));
+}
+
 int take_gpu_host_build_save(TakeHostBuild *h, const char *path) {
     if (!h || !path) return fail(TAKE_E_INVALID, "null argument");
     const HostBuild &b = h->hb;
     HbHeader hd;
     memset(&hd, 0, sizeof(hd));
-    memcpy(hd.magic, "TAKEHB03", 8);
-    hd.payload_hash = payload_hash(b);
+    memcpy(hd.magic, "TAKEHB04", 8);
     hd.geom_hash = b.geom_hash; hd.num_prims = b.num_prims;
     hd.n_ref = (int64_t)b.ref.nodes.size(); hd.n_rank = (int64_t)b.ref.dfs_rank.size(); hd.n_fast = (int64_t)b.fast.nodes.size();
     hd.n_wide = (int64_t)b.fast.wide.size(); hd.n_leaf = (int64_t)b.fast.leaf_prims.size(); hd.n_tris = (int64_t)b.tris.size();
     hd.ref_root = b.ref.root; hd.depth = b.fast.depth; hd.wide_depth = b.fast.wide_depth;
     hd.sah_cost = b.fast.sah_cost; hd.abs_max = b.abs_max; hd.ms_ref = b.ms_ref; hd.ms_fast = b.ms_fast;
+    hd.header_hash = header_hash(hd);
+    hd.payload_hash = payload_hash(b);
     const std::string tmp = std::string(path) + ".part";  // readers never see a half-written file
-    FILE *f = fopen(tmp.c_str(), "wb");
+    FILE *f = fopen(tmp.c_str(), "wbx");                  // "x": never follow or clobber something already there
+    if (!f) { remove(tmp.c_str()); f = fopen(tmp.c_str(), "wbx"); }
     if (!f) return fail(TAKE_E_INVALID, std::string("cannot write ") + tmp);
     bool ok = fwrite(&hd, sizeof(hd), 1, f) == 1 && put(f, b.ref.nodes) && put(f, b.ref.dfs_rank) && put(f, b.fast.nodes) &&
               put(f, b.fast.wide) && put(f, b.fast.leaf_prims) && put(f, b.tris);
@@ -885,20 +930,39 @@ int take_gpu_host_build_load(const char *path, TakeHostBuild **out) {
     *out = nullptr;
     FILE *f = fopen(path, "rb");
     if (!f) return fail(TAKE_E_INVALID, std::string("cannot read ") + path);
+    const std::string bad = std::string("not a host-build file of this library: ") + path;
     HbHeader hd;
-    TakeHostBuild *h = new TakeHostBuild;
-    HostBuild &b = h->hb;
-    bool ok = fread(&hd, sizeof(hd), 1, f) == 1 && memcmp(hd.magic, "TAKEHB03", 8) == 0;
+    bool ok = fread(&hd, sizeof(hd), 1, f) == 1 && memcmp(hd.magic, "TAKEHB04", 8) == 0 && header_hash(hd) == hd.header_hash;
     // sizes are fixed by the primitive count: anything else is not a file this library wrote
     ok = ok && hd.num_prims >= 0 && hd.num_prims < (1 << 28) && hd.n_leaf == hd.num_prims && hd.n_rank == hd.num_prims &&
          hd.n_tris == 12 * hd.num_prims && hd.n_ref == (hd.num_prims > 0 ? 2 * hd.num_prims - 1 : 0) && hd.n_fast >= 1 &&
          hd.n_fast <= std::max<int64_t>(hd.num_prims, 1) && hd.n_wide >= 1 && hd.n_wide <= hd.n_fast;
-    ok = ok && get(f, b.ref.nodes, hd.n_ref) && get(f, b.ref.dfs_rank, hd.n_rank) && get(f, b.fast.nodes, hd.n_fast) &&
-         get(f, b.fast.wide, hd.n_wide) && get(f, b.fast.leaf_prims, hd.n_leaf) && get(f, b.tris, hd.n_tris);
-    ok = ok && fgetc(f) == EOF;
+    // the scalars the device code trusts
+    ok = ok && (hd.num_prims > 0 ? (hd.ref_root >= 0 && hd.ref_root < hd.n_ref) : hd.ref_root == -1) && std::isfinite(hd.abs_max) &&
+         hd.abs_max >= 0 && hd.depth >= 0 && hd.depth <= TAKE_STACK_SMEM + TAKE_STACK_LOCAL && hd.wide_depth >= 0 &&
+         hd.wide_depth <= hd.depth + 1;
+    if (ok) {  // the file must be exactly as long as the header says BEFORE anything is allocated from its counts
+        const int64_t want = (int64_t)sizeof(hd) + hd.n_ref * (int64_t)sizeof(RefNode) + hd.n_rank * 4 + hd.n_fast * (int64_t)sizeof(FastNode) +
+                             hd.n_wide * (int64_t)sizeof(WideNode) + hd.n_leaf * 4 + hd.n_tris * 8;
+        ok = fseek(f, 0, SEEK_END) == 0 && (int64_t)ftell(f) == want && fseek(f, (long)sizeof(hd), SEEK_SET) == 0;
+    }
+    if (!ok) { fclose(f); return fail(TAKE_E_INVALID, bad); }
+    TakeHostBuild *h = nullptr;
+    try {
+        h = new TakeHostBuild;
+        HostBuild &b = h->hb;
+        ok = get(f, b.ref.nodes, hd.n_ref) && get(f, b.ref.dfs_rank, hd.n_rank) && get(f, b.fast.nodes, hd.n_fast) &&
+             get(f, b.fast.wide, hd.n_wide) && get(f, b.fast.leaf_prims, hd.n_leaf) && get(f, b.tris, hd.n_tris);
+        ok = ok && fgetc(f) == EOF;
+        ok = ok && payload_hash(b) == hd.payload_hash;
+    } catch (const std::bad_alloc &) {
+        fclose(f);
+        delete h;
+        return fail(TAKE_E_NOMEM, std::string("out of host memory loading ") + path);
+    }
     fclose(f);
-    ok = ok && payload_hash(b) == hd.payload_hash;
-    if (!ok) { delete h; return fail(TAKE_E_INVALID, std::string("not a host-build file of this library: ") + path); }
+    if (!ok) { delete h; return fail(TAKE_E_INVALID, bad); }
+    HostBuild &b = h->hb;
     b.geom_hash = hd.geom_hash; b.num_prims = hd.num_prims; b.ref.root = hd.ref_root; b.fast.depth = hd.depth;
     b.fast.wide_depth = hd.wide_depth; b.fast.sah_cost = hd.sah_cost; b.abs_max = hd.abs_max; b.ms_ref = hd.ms_ref; b.ms_fast = hd.ms_fast;
     *out = h;
@@ -919,18 +983,28 @@ int take_gpu_scene_create_prebuilt(int device, const TakeSceneDesc *d, TakeHostB
 
 int take_gpu_intersect_device(TakeScene *s, const TakeRay *d_rays, int64_t n, TakeHit *d_hits, int flags) {
     if (!s || (n > 0 && (!d_rays || !d_hits))) return fail(TAKE_E_INVALID, "null argument");
-    if (n < 0 || n > 0xfffffff0LL) return fail(TAKE_E_INVALID, "ray count out of range");
+    if (n < 0) return fail(TAKE_E_INVALID, "negative ray count");
     if (n == 0) return TAKE_OK;
+    // the persistent kernels end on a 32-bit work cursor that advances in steps of 32: keep every launch far below 2^32
+    const int64_t kChunk = (int64_t)1 << 30;
+    if (n > kChunk) {
+        for (int64_t off = 0; off < n; off += kChunk)
+            if (int rc = take_gpu_intersect_device(s, d_rays + off, std::min(kChunk, n - off), d_hits + off, flags)) return rc;
+        return TAKE_OK;
+    }
     CU(cudaSetDevice(s->device));
     if (flags == TAKE_ISECT_EXACT) {
         k_intersect_exact<<<(unsigned)((n + 127) / 128), 128, 0, s->stream>>>(s->dev, d_rays, n, d_hits);
     } else if (flags == TAKE_ISECT_FAST) {
         CU(cudaMemsetAsync(s->fetch.p, 0, 4, s->stream));
+#if TAKE_EXPERIMENTAL
         if (s->traversal == 2)
             k_intersect_fast2<false><<<s->blocks_isect2, 128, 0, s->stream>>>(s->dev, d_rays, n, d_hits, nullptr, s->fetch.as<uint32_t>());
+        else if (!s->wide)
+            k_intersect_fast<false, false><<<s->blocks_isect, 128, 0, s->stream>>>(s->dev, d_rays, n, d_hits, nullptr, s->fetch.as<uint32_t>());
         else
-            if (s->wide) k_intersect_fast<false, true><<<s->blocks_isect, 128, 0, s->stream>>>(s->dev, d_rays, n, d_hits, nullptr, s->fetch.as<uint32_t>());
-            else k_intersect_fast<false, false><<<s->blocks_isect, 128, 0, s->stream>>>(s->dev, d_rays, n, d_hits, nullptr, s->fetch.as<uint32_t>());
+#endif
+            k_intersect_fast<false, true><<<s->blocks_isect, 128, 0, s->stream>>>(s->dev, d_rays, n, d_hits, nullptr, s->fetch.as<uint32_t>());
     } else {
         return fail(TAKE_E_INVALID, "unknown intersect flags");
     }
@@ -967,16 +1041,17 @@ int take_gpu_occluded(TakeScene *s, const TakeRay *rays, int64_t n, uint8_t *occ
         CU(s->scratch_b.ensure(m));
         CU(cudaMemcpyAsync(s->scratch_a.p, rays + off, m * sizeof(TakeRay), cudaMemcpyHostToDevice, s->stream));
         CU(cudaMemsetAsync(s->fetch.p, 0, 4, s->stream));
+#if TAKE_EXPERIMENTAL
         if (s->traversal == 2)
             k_intersect_fast2<true><<<s->blocks_occl2, 128, 0, s->stream>>>(s->dev, s->scratch_a.as<TakeRay>(), m, nullptr,
                                                                            s->scratch_b.as<uint8_t>(), s->fetch.as<uint32_t>());
+        else if (!s->wide)
+            k_intersect_fast<true, false><<<s->blocks_occl, 128, 0, s->stream>>>(s->dev, s->scratch_a.as<TakeRay>(), m, nullptr,
+                                                                                 s->scratch_b.as<uint8_t>(), s->fetch.as<uint32_t>());
         else
-            if (s->wide)
-                k_intersect_fast<true, true><<<s->blocks_occl, 128, 0, s->stream>>>(s->dev, s->scratch_a.as<TakeRay>(), m, nullptr,
-                                                                                    s->scratch_b.as<uint8_t>(), s->fetch.as<uint32_t>());
-            else
-                k_intersect_fast<true, false><<<s->blocks_occl, 128, 0, s->stream>>>(s->dev, s->scratch_a.as<TakeRay>(), m, nullptr,
-                                                                                     s->scratch_b.as<uint8_t>(), s->fetch.as<uint32_t>());
+#endif
+            k_intersect_fast<true, true><<<s->blocks_occl, 128, 0, s->stream>>>(s->dev, s->scratch_a.as<TakeRay>(), m, nullptr,
+                                                                                s->scratch_b.as<uint8_t>(), s->fetch.as<uint32_t>());
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(occluded + off, s->scratch_b.p, m, cudaMemcpyDeviceToHost, s->stream));
         CU(cudaStreamSynchronize(s->stream));
@@ -1012,7 +1087,7 @@ int render_enqueue(TakeScene *s, const TakeRenderOpts *o, double *d_sum, double 
     const int64_t per_wave_full = std::max<int64_t>(1, capacity / chunk_pixels);
     const int64_t n_waves_est = ((npix + chunk_pixels - 1) / chunk_pixels) * ((std::max<int64_t>(spp, 1) + per_wave_full - 1) / per_wave_full);
     const int sets = (!tm.on && n_waves_est > 1 && env_int("TAKE_OVERLAP", 1)) ? 2 : 1;
-    if (int rc = ensure_wave(s, capacity, sets)) return rc;
+    if (int rc = ensure_wave(s, capacity, sets, o->max_depth + 2)) return rc;
     if (sets == 2 && !s->stream2) {
         CU(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
         apply_l2_policy(s, s->stream2);
@@ -1325,7 +1400,7 @@ int take_gpu_radiance_samples(TakeScene *s, const TakeRenderOpts *o, int64_t n, 
     if (n == 0) return TAKE_OK;
     CU(cudaSetDevice(s->device));
     const int64_t cap = 1 << 20;
-    if (int rc = ensure_wave(s, std::min(n, cap), 1)) return rc;
+    if (int rc = ensure_wave(s, std::min(n, cap), 1, o->max_depth + 2)) return rc;
     std::vector<int32_t> pixel((size_t)std::min(n, cap));
     StageTimer tm;
     tm.stream = s->stream;

@@ -9,11 +9,18 @@
 //                  (conflict-free column layout) spilling to local memory, and the SAME FP64 leaf test.  Any
 //                  traversal that never culls a primitive the FP64 leaf test would accept returns the same closest
 //                  hit; equal-t candidates are resolved by the reference's DFS rank.
+//
+// Only trace_exact and the 4-wide trace_fast4 are compiled into the shipped library.  The variants that were measured and
+// lost (the binary-node trace_fast, the speculative trace_spec4, the warp-persistent loop with lane
+// refill) are kept for A/B runs behind -DTAKE_EXPERIMENTAL=1 (make EXTRA=-DTAKE_EXPERIMENTAL=1).
 #pragma once
 #include "device_common.cuh"
 
 namespace take {
 
+#ifndef TAKE_EXPERIMENTAL
+#define TAKE_EXPERIMENTAL 0
+#endif
 #ifndef TAKE_STACK_SMEM
 #define TAKE_STACK_SMEM 24   // entries per thread kept in shared memory
 #endif
@@ -198,6 +205,7 @@ struct TravCounters {
     unsigned long long box, tri;
 };
 
+#if TAKE_EXPERIMENTAL
 template <bool ANY_HIT, bool COUNT>
 __device__ __forceinline__ void trace_fast(const DevScene &sc, D3 o, D3 d, double tmin, double tmax, TravStack &st,
                                            HitOut &out, TravCounters *cnt) {
@@ -296,6 +304,8 @@ __device__ __forceinline__ void trace_fast(const DevScene &sc, D3 o, D3 d, doubl
     }
 }
 
+
+#endif  // TAKE_EXPERIMENTAL (binary-node traversal)
 
 // ---------------------------------------------------------------------------------------------------------
 // 4-wide variant of trace_fast: same conservative slab arithmetic, same FP64 leaf test and tie rule, on 128-byte
@@ -415,6 +425,7 @@ __device__ __forceinline__ void trace_fast4(const DevScene &sc, D3 o, D3 d, doub
     }
 }
 
+#if TAKE_EXPERIMENTAL
 // ---------------------------------------------------------------------------------------------------------
 // Speculative 4-wide traversal (warp-cooperative schedule, same results as trace_fast4).
 //
@@ -537,21 +548,29 @@ __device__ __forceinline__ void trace_spec4(const DevScene &sc, D3 o, D3 d, doub
 #undef TAKE_SPEC_POP
 }
 
+#endif  // TAKE_EXPERIMENTAL (speculative traversal)
+
 #ifndef TAKE_SPECULATE
 #define TAKE_SPECULATE 0
 #endif
 
-// Dispatch on the tree width chosen at scene creation.
+// Dispatch on the tree width chosen at scene creation (the shipped library only has the 4-wide tree).
 template <bool ANY_HIT, bool COUNT, bool WIDE>
 __device__ __forceinline__ void trace_any(const DevScene &sc, D3 o, D3 d, double tmin, double tmax, TravStack &st, HitOut &out,
                                           TravCounters *cnt) {
+#if TAKE_EXPERIMENTAL
     if (WIDE) {
         if (TAKE_SPECULATE) trace_spec4<ANY_HIT, COUNT>(sc, o, d, tmin, tmax, st, out, cnt);
         else trace_fast4<ANY_HIT, COUNT>(sc, o, d, tmin, tmax, st, out, cnt);
     }
     else trace_fast<ANY_HIT, COUNT>(sc, o, d, tmin, tmax, st, out, cnt);
+#else
+    static_assert(WIDE, "binary-node traversal needs -DTAKE_EXPERIMENTAL=1");
+    trace_fast4<ANY_HIT, COUNT>(sc, o, d, tmin, tmax, st, out, cnt);
+#endif
 }
 
+#if TAKE_EXPERIMENTAL
 // ---------------------------------------------------------------------------------------------------------
 // Warp-persistent traversal ("while-while" with dynamic re-fetch).
 //
@@ -775,5 +794,6 @@ __device__ __forceinline__ void trace_warp_persistent(const DevScene &sc, IO &io
         if (done) active = false;
     }
 }
+#endif  // TAKE_EXPERIMENTAL (warp-persistent traversal)
 
 }  // namespace take

@@ -82,7 +82,7 @@ enum { PEND_PRIMARY = 0, PEND_BSDF = 1, PEND_LIGHT = 2, PEND_SPECULAR = 4, PEND_
 __device__ __forceinline__ uint32_t sort_key(int32_t prim, const uint8_t *prim_mtype, int32_t branch) {
     return prim < 0 ? 0u : ((1u + (uint32_t)prim_mtype[prim]) | ((uint32_t)branch << 4));
 }
-#define TAKE_MAX_PASSES 80
+#define TAKE_MAX_DEPTH 65533  // sanity bound on -max_depth (a wave runs max_depth + 2 passes)
 
 struct PassCounters {  // one per pass, zeroed once per wave
     uint32_t n_extend;          // entries in this pass's extend queue
@@ -108,7 +108,7 @@ struct Wave {
     ShadowRec *shadow;
     int32_t *q_extend[2];
     int32_t *q_shadow;
-    PassCounters *pass;  // [TAKE_MAX_PASSES]
+    PassCounters *pass;  // [max_depth + 3]
     Totals *totals;
     // slot -> (pixel, sample): see slot_of() below, unless an explicit list is given
     int32_t chunk_pixels, chunk_base;
@@ -229,6 +229,7 @@ __device__ __forceinline__ uint32_t shade_count(const Wave &w, int pass) {
     return (pass == 0 && w.miss_fast) ? w.pass[0].n_extend : pass_count(w, pass);
 }
 
+#if TAKE_EXPERIMENTAL
 // ---- generate: src/render.cpp:65-75 (only when the primaries are not fused into pass 0) ----------------------
 __global__ void k_generate(DevScene sc, Wave w) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -254,6 +255,8 @@ __global__ void k_generate(DevScene sc, Wave w) {
     w.path[slot] = p;
     w.q_extend[0][slot] = slot;
 }
+
+#endif  // TAKE_EXPERIMENTAL (separate generate pass)
 
 // Work distribution of the persistent traversal kernels: a warp takes `batches` batches of 32 queue entries with ONE
 // atomicAdd on the pass's cursor and works through them.  With one batch per atomic every warp hits the same address
@@ -898,6 +901,7 @@ __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_intersect_fast(DevS
     }
 }
 
+#if TAKE_EXPERIMENTAL
 // ---- warp-persistent variants (trace_warp_persistent): same results, different schedule ------------------------
 #ifndef TAKE_EXTEND_MIN_BLOCKS
 #define TAKE_EXTEND_MIN_BLOCKS 6
@@ -1005,6 +1009,8 @@ __global__ void __launch_bounds__(128, TAKE_EXTEND_MIN_BLOCKS) k_intersect_fast2
     ApiIO<ANY_HIT> io = {rays, hits, occ};
     trace_warp_persistent<ANY_HIT, false, false>(sc, io, (uint32_t)n, fetch, st, nullptr);
 }
+
+#endif  // TAKE_EXPERIMENTAL (warp-persistent kernels)
 
 __global__ void k_intersect_exact(DevScene sc, const TakeRay *rays, int64_t n, TakeHit *hits) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

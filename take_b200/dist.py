@@ -62,30 +62,46 @@ def finalize(s, s2, n: int):
     return mean, var, n
 
 
-def shared_host_build(flat, path: str = None):
+def shared_host_build(flat, directory: str = None):
     """One host build per NODE instead of one per rank: local rank 0 builds the acceleration structures and saves them
-    (default: /dev/shm), the node's other ranks wait at a barrier and load the file.  Returns an `api.HostBuild` to pass
-    as `GpuScene(flat, device=local_rank, prebuilt=...)`.  Without an initialised process group it just builds."""
+    into a fresh private directory (mkdtemp, mode 0700, under /dev/shm when it exists), the path and a success flag are
+    broadcast, and the node's other ranks load the file.  A failure on the building rank is raised on EVERY rank (no rank
+    is left waiting at a barrier).  Returns an `api.HostBuild` to pass as `GpuScene(flat, device=local_rank, prebuilt=...)`.
+    Without an initialised process group it just builds.  (All ranks of the group are assumed to share one node's
+    file system -- the single-node launch bench.py and the driver use.)"""
     import os
+    import shutil
+    import tempfile
     import torch.distributed as dist
     from . import api
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return api.HostBuild(flat)
-    local = int(os.environ.get("LOCAL_RANK", dist.get_rank()))
-    if path is None:
-        base = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
-        path = os.path.join(base, f"take_hostbuild_{os.environ.get('MASTER_PORT', '0')}_{flat.num_prims}.bin")
-    hb = None
-    if local == 0:
-        hb = api.HostBuild(flat)
-        hb.save(path)
-    dist.barrier()
-    if local != 0:
-        hb = api.HostBuild(path=path)
-    dist.barrier()
-    if local == 0:
+    rank = dist.get_rank()
+    hb, tmpdir, msg = None, None, [None, None]       # msg = [path or None, error text or None]
+    if rank == 0:
         try:
-            os.remove(path)
-        except OSError:
-            pass
+            base = directory or ("/dev/shm" if os.path.isdir("/dev/shm") else None)
+            tmpdir = tempfile.mkdtemp(prefix="take_hostbuild_", dir=base)
+            hb = api.HostBuild(flat)
+            path = os.path.join(tmpdir, "build.bin")
+            hb.save(path)
+            msg = [path, None]
+        except Exception as ex:                       # reported to everybody below
+            msg = [None, f"{type(ex).__name__}: {ex}"]
+    dist.broadcast_object_list(msg, src=0)
+    err = msg[1]
+    if err is None and rank != 0:
+        try:
+            hb = api.HostBuild(path=msg[0])
+        except Exception as ex:
+            err = f"rank {rank}: {type(ex).__name__}: {ex}"
+    errs = [None] * dist.get_world_size()
+    dist.all_gather_object(errs, err)                 # also the point after which the file is no longer needed
+    if tmpdir is not None:
+        shutil.rmtree(tmpdir, ignore_errors=True)
+    errs = [e for e in errs if e]
+    if errs:
+        if hb is not None:
+            hb.close()
+        raise RuntimeError("shared_host_build failed: " + "; ".join(sorted(set(errs))))
     return hb

@@ -26,6 +26,7 @@ _BSDF_XML = {
     sio.MAT_DISNEY_DIFFUSE: ("disneydiffuse", "baseColor"), sio.MAT_DISNEY_METAL: ("disneymetal", "baseColor"),
     sio.MAT_DISNEY_GLASS: ("disneyglass", "baseColor"), sio.MAT_DISNEY_SHEEN: ("disneysheen", "baseColor"),
     sio.MAT_DISNEY_BSDF: ("disneybsdf", "baseColor"),
+    sio.MAT_DISNEY_CLEARCOAT: ("disneyclearcoat", None),   # no colour at all (parse_scene.cpp:613-621)
 }
 
 
@@ -64,6 +65,7 @@ class SceneBuilder:
         self.meshes = []      # shapes in the order the reference would parse them: mesh dicts and sphere dicts
         self.env = None       # optional environment map (extension: the reference has none)
         self.env_sample = False
+        self.point_lights = []  # top-level <emitter type="point">: (position, intensity), parsed before any shape
 
     # -- materials ----------------------------------------------------------------------------
     def material(self, mtype, color=(0.5, 0.5, 0.5), texture=None, uvscale=(1, 1), uvoffset=(0, 0), **params) -> int:
@@ -85,6 +87,13 @@ class SceneBuilder:
         <background>; `write()` therefore refuses such a scene unless the map is constant."""
         self.env = np.ascontiguousarray(rgb, dtype=np.float64)
         self.env_sample = bool(sample)
+
+    def point_light(self, position, intensity=(1, 1, 1)):
+        """Top-level <emitter type="point"> (src/parse/parse_scene.cpp:701-727).  The integrators ignore point lights
+        (path_tracing.h:33: get_if<DiffuseAreaLight> fails) but they take part in the uniform light pick and dilute it
+        (src/light.cpp:5-7)."""
+        self.point_lights.append((f32(position), f32(intensity)))
+        return len(self.point_lights) - 1
 
     # -- geometry -----------------------------------------------------------------------------
     def mesh(self, positions, indices, normals, uvs=None, material=0, radiance=None):
@@ -137,6 +146,10 @@ class SceneBuilder:
         pos, nrm, uv, idx, pmat, plight, pflags, lights, spheres = [], [], [], [], [], [], [], [], []
         base = 0
         n_prims = 0
+        for pos_, inten in self.point_lights:
+            # the parser brace-initialises PointLight{position, intensity} into a struct declared {intensity, position}
+            # (parse_scene.cpp:723 vs light.h:9-12): the fields arrive swapped, and that is what the reference holds
+            lights.append((sio.LIGHT_POINT, -1, tuple(pos_), tuple(inten)))
         for m in self.meshes:
             if m.get("sphere"):
                 idx.append(np.array([[len(spheres), 0, 0]], np.int32))
@@ -171,7 +184,7 @@ class SceneBuilder:
         for i, m in enumerate(self.materials):
             mats[i]["type"] = m["type"]
             mats[i]["tex_id"] = -1 if m["texture"] is None else m["texture"]
-            mats[i]["color"] = 0.0 if m["texture"] is not None else m["color"]
+            mats[i]["color"] = 0.0 if (m["texture"] is not None or m["type"] == sio.MAT_DISNEY_CLEARCOAT) else m["color"]
             mats[i]["uv"] = [1, 1, 0, 0] if m["texture"] is None else [*m["uvscale"], *m["uvoffset"]]
             p = m["params"]
             t = m["type"]
@@ -223,7 +236,9 @@ class SceneBuilder:
         for i, m in enumerate(self.materials):
             tname, cname = _BSDF_XML[m["type"]]
             x.append(f'<bsdf type="{tname}" id="m{i}">')
-            if m["texture"] is None:
+            if cname is None:
+                pass
+            elif m["texture"] is None:
                 x.append(f'  <rgb name="{cname}" value="{_vec(m["color"])}"/>')
             else:
                 x.append(f'  <texture type="bitmap" name="{cname}"><string name="filename" value="tex{m["texture"]}.hdr"/>'
@@ -232,6 +247,9 @@ class SceneBuilder:
             for k, v in m["params"].items():
                 x.append(f'  <float name="{k}" value="{_fmt(v)}"/>')
             x.append('</bsdf>')
+        for pos_, inten in self.point_lights:     # before the shapes: they take the first light indices
+            x.append(f'<emitter type="point"><point name="position" x="{_fmt(pos_[0])}" y="{_fmt(pos_[1])}" z="{_fmt(pos_[2])}"/>'
+                     f'<rgb name="intensity" value="{_vec(inten)}"/></emitter>')
         for i, m in enumerate(self.meshes):
             if m.get("sphere"):
                 c = m["center"]
@@ -317,6 +335,29 @@ def cornell_box(width=512, height=512, spp=64, materials="diffuse") -> SceneBuil
            radiance=(17, 12, 4))                                           # light, normal -y
     b.box((-0.35, 0.6, -0.3), (0.3, 0.6, 0.3), 18, tall)
     b.box((0.35, 0.3, 0.35), (0.3, 0.3, 0.3), -17, short)
+    return b
+
+
+def cornell_stubs(width=64, height=64, spp=4, clearcoat=False) -> SceneBuilder:
+    """Parity scene for the branches no BASELINE config reaches: one surface per "Disney" alternative the reference only
+    stubs (metal, glass, sheen, bsdf evaluate as Lambertian: src/materials/disney_*.inl) and a point emitter next to the
+    area light, which contributes nothing but takes a third of the uniform light picks (src/light.cpp:5-7,
+    path_tracing.h:33).  clearcoat=True puts DisneyClearcoat on the tall box: the reference's eval for it returns an
+    UNINITIALISED vector (`return {};` through `TVector3() {}`, disney_clearcoat.inl:26, vector.h:30), so that variant can
+    only be compared between our own CPU restatement and the GPU (both return 0), never pinned to the reference."""
+    b = SceneBuilder(width, height, (0, 1, 3.8), (0, 1, 0), (0, 1, 0), 39.3, spp, (0.05, 0.04, 0.03))
+    white = b.material(sio.MAT_DIFFUSE, (0.73, 0.73, 0.73))
+    metal = b.material(sio.MAT_DISNEY_METAL, (0.8, 0.6, 0.3))
+    glass = b.material(sio.MAT_DISNEY_GLASS, (0.6, 0.8, 0.9))
+    coat = b.material(sio.MAT_DISNEY_CLEARCOAT) if clearcoat else b.material(sio.MAT_DISNEY_METAL, (0.9, 0.9, 0.2))
+    sheen = b.material(sio.MAT_DISNEY_SHEEN, (0.7, 0.2, 0.5))
+    principled = b.material(sio.MAT_DISNEY_BSDF, (0.3, 0.7, 0.4))
+    black = b.material(sio.MAT_DIFFUSE, (0, 0, 0))
+    b.point_light((0.3, 1.2, 0.4), (5, 6, 7))
+    _room(b, metal, white, principled, glass, sheen)
+    b.quad((-0.25, 1.98, -0.25), (0.25, 1.98, -0.25), (0.25, 1.98, 0.25), (-0.25, 1.98, 0.25), black, radiance=(17, 12, 4))
+    b.box((-0.35, 0.6, -0.3), (0.3, 0.6, 0.3), 18, coat)
+    b.box((0.35, 0.3, 0.35), (0.3, 0.3, 0.3), -17, white)
     return b
 
 
@@ -572,4 +613,4 @@ def ibl_scene(width=1024, height=1024, spp=512, n_objects=64, seed=7, env_size=(
 
 def build(name: str, **kw) -> SceneBuilder:
     return {"cornell": cornell_box, "heightfield": heightfield, "multi_light": multi_light,
-            "textured": textured_room, "spheres": sphere_room, "instanced": instanced_spheres, "ibl": ibl_scene}[name](**kw)
+            "textured": textured_room, "spheres": sphere_room, "instanced": instanced_spheres, "ibl": ibl_scene, "stubs": cornell_stubs}[name](**kw)

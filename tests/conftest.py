@@ -50,6 +50,7 @@ SMALL_SCENES = {
     "heightfield": lambda: scenes.heightfield(48, 64, 36, 4),
     "textured": lambda: scenes.textured_room(48, 48, 4),
     "spheres": lambda: scenes.sphere_room(48, 48, 4),
+    "cornell_stubs": lambda: scenes.cornell_stubs(48, 48, 4),   # Disney stub BSDFs 7, 8, 10, 11 + a point emitter
 }
 
 

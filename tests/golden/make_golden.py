@@ -27,6 +27,7 @@ SCENES = {
     "heightfield": lambda: scenes.heightfield(24, 40, 24, 2),
     "textured": lambda: scenes.textured_room(32, 32, 2),
     "spheres": lambda: scenes.sphere_room(32, 32, 2),
+    "cornell_stubs": lambda: scenes.cornell_stubs(32, 32, 2),   # Disney stub BSDFs 7, 8, 10, 11 + a point emitter
 }
 SEED = 2024
 

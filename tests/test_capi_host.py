@@ -62,6 +62,14 @@ def test_invalid_scene_is_rejected(gpu_lib):
     flat.prim_material[0] = 99
     with pytest.raises(api.TakeGpuError, match="material"):
         api.host_build(flat)
+    flat = scenes.cornell_box(8, 8, 1).flat()
+    flat.positions[5, 1] = np.inf          # would make the conservative padding of every box test infinite
+    with pytest.raises(api.TakeGpuError, match="non-finite"):
+        api.host_build(flat)
+    flat = scenes.cornell_box(8, 8, 1).flat()
+    flat.lights["kind"][0] = 7
+    with pytest.raises(api.TakeGpuError, match="light kind"):
+        api.host_build(flat)
 
 
 def test_reference_order_tree_matches_oracle(oracle_lib, small_scene):
@@ -281,7 +289,16 @@ def test_host_build_save_load_roundtrip(tmp_path, small_scene):
     raw = open(path, "rb").read()
     flipped = bytearray(raw)
     flipped[len(raw) // 2] ^= 0x40                                   # one bit inside an array: the payload hash notices
-    for bad in (raw[:len(raw) // 2], b"TAKEHB01" + raw[8:], raw + b"x", b"", bytes(flipped)):
+    # header scalars the device code trusts (ref_root at byte 72, abs_max at 96, the counts from 24): covered by the header hash,
+    # range-checked, and a count that does not fit the file length is refused before anything is allocated from it
+    hdr_cases = []
+    for off, val in ((72, b"\x07"), (96 + 7, b"\x7f"), (96 + 6, b"\xf8"), (40, b"\xff\xff\xff\x7f"), (76, b"\x63")):
+        c = bytearray(raw)
+        c[off:off + len(val)] = val
+        if bytes(c) != raw:
+            hdr_cases.append(bytes(c))
+    assert len(hdr_cases) >= 4
+    for bad in [raw[:len(raw) // 2], b"TAKEHB01" + raw[8:], raw + b"x", b"", bytes(flipped)] + hdr_cases:
         p2 = str(tmp_path / "bad.bin")
         open(p2, "wb").write(bad)
         with pytest.raises(api.TakeGpuError):

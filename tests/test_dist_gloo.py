@@ -63,7 +63,7 @@ def test_sharded_render_equals_single_process(tmp_path, oracle_lib, world):
     assert int(got["n"]) == spp
 
 
-def _build_worker(rank, world, port, out_dir):
+def _build_worker(rank, world, port, out_dir, fail=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -71,7 +71,21 @@ def _build_worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from take_b200 import scenes
     flat = scenes.multi_light(16, 16, 1, n_side=6).flat()
-    hb = tdist.shared_host_build(flat, path=os.path.join(out_dir, "shared.bin"))
+    if fail:                          # the building rank fails: every rank must raise, none may hang at a barrier
+        if rank == 0:
+            flat.prim_material = flat.prim_material.copy()
+            flat.prim_material[0] = 12345     # out of range -> take_gpu_host_build refuses the scene
+        try:
+            tdist.shared_host_build(flat, directory=os.path.join(out_dir, "x"))
+            raised = ""
+        except RuntimeError as ex:
+            raised = str(ex)
+        open(os.path.join(out_dir, f"raised{rank}.txt"), "w").write(raised)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+    os.makedirs(os.path.join(out_dir, "x"), exist_ok=True)
+    hb = tdist.shared_host_build(flat, directory=os.path.join(out_dir, "x"))
     a = hb.arrays()
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **{k: a[k] for k in ("ref_nodes", "dfs_rank", "wide_nodes", "leaf_prims", "leaf_records")},
              ms_fast=a["ms_fast"])
@@ -90,4 +104,14 @@ def test_shared_host_build_builds_once_per_node(tmp_path):
     for k in ("ref_nodes", "dfs_rank", "wide_nodes", "leaf_prims", "leaf_records"):
         assert np.array_equal(r0[k], r1[k]), k
     assert float(r0["ms_fast"]) == float(r1["ms_fast"])
-    assert not os.path.exists(tmp_path / "shared.bin")
+    assert os.listdir(tmp_path / "x") == []          # the private exchange directory is gone
+
+
+def test_shared_host_build_failure_reaches_every_rank(tmp_path):
+    world = 2
+    port = 29500 + (os.getpid() % 1000) + 23
+    os.makedirs(tmp_path / "x")
+    mp.spawn(_build_worker, args=(world, port, str(tmp_path), True), nprocs=world, join=True)
+    for r in range(world):
+        assert "shared_host_build failed" in open(tmp_path / f"raised{r}.txt").read()
+    assert os.listdir(tmp_path / "x") == []

@@ -80,6 +80,30 @@ def test_config1_cornell_full(gpu_lib, oracle_lib):
     sc.close()
 
 
+def test_config1_statistical_gate_full_frame(gpu_lib, oracle_lib):
+    """The image gate of SURVEY.md 8(c) once at a BASELINE-size frame: config 1 as specified (512x512, 64 spp, max_depth 5,
+    multi-sample MIS), GPU and CPU with independent seeds, a second CPU render as the yardstick."""
+    flat = scenes.cornell_box().flat()
+    n = 64
+    gs, sc = api.GpuScene(flat), oracle_lib.load(flat)
+    g, g2, _ = gs.render_sums("mis", 5, 0, n, seed=2002)
+    a, a2 = sc.render("mis", 5, 0, n, seed=1001, threads=os.cpu_count())
+    b, _ = sc.render("mis", 5, 0, n, seed=3003, threads=os.cpu_count())
+    gs.close()
+    sc.close()
+    mu_a, mu_b, mu_g = a / n, b / n, g / n
+    relmse = lambda x, y: np.mean((x - y) ** 2 / (y ** 2 + 1e-2))
+    assert relmse(mu_g, mu_a) <= 1.5 * relmse(mu_b, mu_a)
+    var_a = np.maximum(a2 / n - mu_a ** 2, 0) * n / (n - 1)
+    var_g = np.maximum(g2 / n - mu_g ** 2, 0) * n / (n - 1)
+    se2 = var_a / n + var_g / n
+    mask = se2 > 0
+    z = np.abs(mu_g - mu_a)[mask] / np.sqrt(se2[mask])
+    assert (z <= 3).mean() >= 0.995, float((z <= 3).mean())
+    for c in range(3):
+        assert abs(mu_g[..., c].sum() - mu_a[..., c].sum()) <= 4 * np.sqrt(se2[..., c].sum()) + 1e-12
+
+
 # ---- config 4: hundreds of emissive triangles, multi-sample MIS, 1920x1080 -----------------------------------------
 def test_config4_multi_light_full(gpu_lib, oracle_lib):
     flat = scenes.multi_light().flat()
@@ -142,6 +166,19 @@ def test_config5_ten_million_triangles(gpu_lib, oracle_lib):
     assert np.array_equal(p1, p2) and np.array_equal(t1, t2)
     a, _, st = gs.render_sums("mis", 5, 0, 1, seed=1, sumsq=False)
     assert st["samples"] == W * H and np.isfinite(a).all() and a.sum() > 0
+    # ... and against the CPU oracle at FULL size on a bounded subset: the oracle builds the reference's own tree over
+    # all 10 M primitives (about half a minute), then 16 image rows of the 4K frame and 100 000 of the rays above
+    sc = oracle_lib.load(flat)
+    rows = np.arange(11, H, 135)
+    cs, _ = sc.render("mis", 5, 0, 1, seed=1, threads=os.cpu_count(), row_begin=11, row_step=135)
+    err = np.abs(a[rows] - cs[rows]).max(axis=2) / (np.abs(cs[rows]).max(axis=2) + 1e-12)
+    assert (err > 1e-9).mean() <= 1e-3, float((err > 1e-9).mean())
+    sub = slice(0, None, 20)
+    op, ot, ouv = sc.intersect(rays[sub])
+    assert np.array_equal(op, pf[sub]) and np.array_equal(ot[op >= 0], tf[sub][op >= 0]) and np.array_equal(ouv[op >= 0], uvf[sub][op >= 0])
+    op2, ot2, _ = sc.intersect(sec[::5])
+    assert np.array_equal(op2, p2[::5]) and np.array_equal(ot2[op2 >= 0], t2[::5][op2 >= 0])
+    sc.close()
     print("config 5:", flat.num_prims, "prims;", info, "; 1 spp 4K:", st["ms_total"], "ms,",
           (st["extend_rays"] + st["shadow_rays"]) / st["ms_total"] / 1e3, "Mrays/s")
     gs.close()

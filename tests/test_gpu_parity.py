@@ -143,19 +143,23 @@ def test_image_sums_same_streams(pair, integrator):
         assert st["samples"] == flat.width * flat.height * (hi - lo)
 
 
-def test_statistical_gate_independent_seeds(pair):
+@pytest.mark.parametrize("integrator", ["mis", "raw", "one_sample_mis"])
+def test_statistical_gate_independent_seeds(pair, integrator):
     """The north star's image gate, with DIFFERENT seeds on the two sides (independent estimates), calibrated as in
-    SURVEY.md 8(c):
+    SURVEY.md 8(c), for each of the three integrators (parity is per integrator: they truncate paths differently,
+    SURVEY.md Appendix A item 11):
       (i)   relMSE(GPU_seedC, CPU_seedA) <= 1.5 x relMSE(CPU_seedB, CPU_seedA): the error between a GPU and a CPU render
             is no larger than between two CPU renders (relMSE = mean((a-b)^2 / (b^2 + 1e-2)); the sample-variance
             based noise floor is not used as the yardstick because the estimator is heavy-tailed at these spp);
-      (ii)  >= 99.5 % of pixel-channels within 3 sigma of each other;
+      (ii)  >= 99.5 % of pixel-channels within 3 sigma of each other (99 % for the no-MIS integrator, whose per-pixel
+            estimates are far from Gaussian at 64 spp: SURVEY.md Appendix C measured 97.5 % even between integrators
+            that agree in the mean);
       (iii) per channel, the image sums differ by less than 4 sigma (catches ~1 % estimator bias)."""
     name, flat, gs, sc = pair
     n = 64
-    a, a2 = sc.render("mis", 5, 0, n, seed=1001)
-    b, _ = sc.render("mis", 5, 0, n, seed=3003)
-    g, g2, _ = gs.render_sums("mis", 5, 0, n, seed=2002)
+    a, a2 = sc.render(integrator, 5, 0, n, seed=1001)
+    b, _ = sc.render(integrator, 5, 0, n, seed=3003)
+    g, g2, _ = gs.render_sums(integrator, 5, 0, n, seed=2002)
     mu_a, mu_b, mu_g = a / n, b / n, g / n
     relmse = lambda x, y: np.mean((x - y) ** 2 / (y ** 2 + 1e-2))
     assert relmse(mu_g, mu_a) <= 1.5 * relmse(mu_b, mu_a), (name, relmse(mu_g, mu_a), relmse(mu_b, mu_a))
@@ -164,9 +168,30 @@ def test_statistical_gate_independent_seeds(pair):
     se2 = var_a / n + var_g / n
     mask = se2 > 0
     z = np.abs(mu_g - mu_a)[mask] / np.sqrt(se2[mask])
-    assert (z <= 3).mean() >= 0.995, (name, float((z <= 3).mean()))
+    assert (z <= 3).mean() >= (0.99 if integrator == "raw" else 0.995), (name, float((z <= 3).mean()))
     for c in range(3):
         assert abs(mu_g[..., c].sum() - mu_a[..., c].sum()) <= 4 * np.sqrt(se2[..., c].sum()) + 1e-12
+
+
+def test_clearcoat_against_the_restatement(gpu_lib, oracle_lib):
+    """DisneyClearcoat (material type 9): cosine-lobe sampling and pdf like the other stubs, but the reference's eval
+    returns an uninitialised vector (disney_clearcoat.inl:26 `return {};` through `TVector3() {}`, vector.h:30), so there
+    is nothing to pin: both our CPU restatement and the GPU return 0 (known deviation 2).  The scene
+    is the pinned `cornell_stubs` with the clearcoat on the tall box."""
+    flat = scenes.cornell_stubs(48, 48, 4, clearcoat=True).flat()
+    assert (flat.materials["type"] == sceneio.MAT_DISNEY_CLEARCOAT).any() and (flat.lights["kind"] == sceneio.LIGHT_POINT).any()
+    gs, sc = api.GpuScene(flat), oracle_lib.load(flat)
+    try:
+        for integ in api.INTEGRATORS:
+            cs, cs2, cst = sc.render(integ, 5, 0, 4, seed=23, stats=True)
+            s, s2, st = gs.render_sums(integ, 5, 0, 4, seed=23)
+            bad = np.abs(s - cs).max(axis=2) > REL * (np.abs(cs).max(axis=2) + 1e-12)
+            assert bad.mean() <= 2e-3, integ
+            if not bad.any():
+                assert st["extend_rays"] == cst[0] and st["shadow_rays"] == cst[1] and st["shaded"] == cst[2]
+    finally:
+        gs.close()
+        sc.close()
 
 
 # ---- properties that do not need the oracle ------------------------------------------------------------------
@@ -278,12 +303,26 @@ def test_bad_arguments(gpu_lib):
     flat = scenes.cornell_box(8, 8, 1).flat()
     gs = api.GpuScene(flat)
     with pytest.raises(api.TakeGpuError):
-        gs.render_sums("mis", 200, 0, 1)            # max_depth beyond the pass table
+        gs.render_sums("mis", 70000, 0, 1)          # max_depth beyond the sanity bound
     with pytest.raises(api.TakeGpuError):
         gs.render_sums("mis", 5, 3, 1)              # spp_end < spp_begin
     with pytest.raises(api.TakeGpuError):
         gs.radiance_samples([99], [0], [0])         # pixel outside the film
     gs.close()
+
+
+def test_deep_paths_like_the_reference_default(gpu_lib, oracle_lib):
+    """The reference's default -max_depth is 50 and it accepts any value (render.cpp:14-19); the pass counters are sized
+    from the request (a fixed table used to refuse anything above 77)."""
+    flat = scenes.cornell_box(24, 24, 2, materials="mixed").flat()
+    gs, sc = api.GpuScene(flat), oracle_lib.load(flat)
+    for integ, depth in (("mis", 50), ("one_sample_mis", 120), ("raw", 300)):
+        cs, _ = sc.render(integ, depth, 0, 2, seed=3)
+        s, _, st = gs.render_sums(integ, depth, 0, 2, seed=3)
+        bad = np.abs(s - cs).max(axis=2) > REL * (np.abs(cs).max(axis=2) + 1e-12)
+        assert bad.mean() <= 2e-3, (integ, depth)
+    gs.close()
+    sc.close()
 
 
 def test_render_entry_point(tmp_path, gpu_lib, oracle_lib):
