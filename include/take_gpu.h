@@ -221,6 +221,16 @@ int take_gpu_render_wait(TakeScene *scene, int64_t ticket, TakeStats *stats);
  * take_gpu_render. */
 int take_gpu_render_multi(int ndev, const int *devices, const TakeSceneDesc *desc, const TakeRenderOpts *opts, double *sum_rgb,
                           double *sumsq_rgb, TakeStats *stats);
+/* The same as a persistent handle, for hosts that render more than once (progressive refinement, spp ranges, animation
+ * of the camera-independent parts): take_gpu_multi_create builds the host-side structures ONCE, uploads one replica per
+ * device (one host thread per device) and creates ONE communicator over all of them; every take_gpu_multi_render then
+ * only enqueues each device's share of the sample range (no host synchronisation in between), issues one grouped
+ * ncclReduce onto devices[0] and one device->host copy from there.  stats->ms_total is the slowest device's time from
+ * its first kernel to the end of its part in the reduce.  Not thread-safe; one handle per set of devices. */
+typedef struct TakeMulti TakeMulti; /* opaque */
+int take_gpu_multi_create(int ndev, const int *devices, const TakeSceneDesc *desc, TakeMulti **out);
+int take_gpu_multi_render(TakeMulti *multi, const TakeRenderOpts *opts, double *sum_rgb, double *sumsq_rgb, TakeStats *stats);
+int take_gpu_multi_destroy(TakeMulti *multi);
 
 /* Output step (replaces the .exr branch of imwrite, src/image.cpp:157-175, and the tinyexr code under it).
  * Device half: mean = sum * (1/spp) (src/render.cpp:78 via vector.h:194-197), double -> float (image.cpp:159-161),

@@ -31,6 +31,7 @@ EXPORTS = [
     "take_gpu_radiance_samples", "take_gpu_render_multi", "take_gpu_scene_stream", "take_gpu_scene_info", "take_gpu_last_error",
     "take_gpu_version", "take_gpu_exr_packed_size", "take_gpu_exr_pack_device", "take_gpu_exr_pack", "take_gpu_exr_write_packed",
     "take_gpu_render_to_exr", "take_gpu_render_async", "take_gpu_render_wait",
+    "take_gpu_multi_create", "take_gpu_multi_render", "take_gpu_multi_destroy",
 ]
 
 RAY_DTYPE = np.dtype([("origin", "<f8", 3), ("dir", "<f8", 3), ("tmin", "<f8"), ("tmax", "<f8")])
@@ -57,6 +58,20 @@ class TakeStats(C.Structure):
 
 class TakeGpuError(RuntimeError):
     pass
+
+
+def kernel_source_hash() -> str:
+    """Short hash of the sources libtake_gpu.so is built from: profile summaries under profiles/ carry it, so a number read
+    from a capture can be tied to the kernels it was captured from (bench.py quotes ncu figures only when it matches)."""
+    import glob
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(_HERE, "csrc")
+    for p in sorted(glob.glob(os.path.join(d, "*.cu")) + glob.glob(os.path.join(d, "*.cuh")) + glob.glob(os.path.join(d, "*.h")) +
+                    glob.glob(os.path.join(d, "*.cpp")) + [os.path.join(d, "Makefile")]):
+        h.update(os.path.basename(p).encode())
+        h.update(open(p, "rb").read())
+    return h.hexdigest()[:12]
 
 
 _lib = None
@@ -93,6 +108,9 @@ def load_library(path: str = LIB_PATH):
     L.take_gpu_exr_pack.argtypes = [vp, vp, i64, vp]
     L.take_gpu_exr_write_packed.argtypes = [C.c_char_p, C.c_int32, C.c_int32, vp, C.c_int32]
     L.take_gpu_render_to_exr.argtypes = [vp, C.POINTER(TakeRenderOpts), C.c_char_p, C.POINTER(TakeStats)]
+    L.take_gpu_multi_create.argtypes = [i32, vp, C.POINTER(TakeSceneDesc), C.POINTER(vp)]
+    L.take_gpu_multi_render.argtypes = [vp, C.POINTER(TakeRenderOpts), vp, vp, C.POINTER(TakeStats)]
+    L.take_gpu_multi_destroy.argtypes = [vp]
     _lib = L
     return L
 
@@ -265,6 +283,41 @@ class GpuScene:
         _check(self.lib.take_gpu_radiance_samples(self.h, C.byref(o), len(px), px.ctypes.data, py.ctypes.data,
                                                   s.ctypes.data, out.ctypes.data))
         return out
+
+
+class MultiGpuScene:
+    """Persistent single-process multi-GPU handle (take_gpu_multi_create / _render / _destroy): the host-side trees are
+    built once, one replica per device, one NCCL communicator; each `render_sums` call shards the sample range over the
+    devices and returns the reduced sums from devices[0]."""
+
+    def __init__(self, flat: FlatScene, devices):
+        self.lib = L = load_library()
+        self.flat = flat
+        self.devices = list(devices)
+        devs = (C.c_int * len(self.devices))(*self.devices)
+        self._desc = flat.to_desc()
+        self.h = C.c_void_p()
+        _check(L.take_gpu_multi_create(len(self.devices), devs, C.byref(self._desc), C.byref(self.h)))
+
+    def render_sums(self, integrator="mis", max_depth=5, spp_begin=0, spp_end=1, seed=0, sumsq=True, out=None):
+        H, W = self.flat.height, self.flat.width
+        s, s2 = out if out is not None else (np.empty((H, W, 3)), np.empty((H, W, 3)) if sumsq else None)
+        o = TakeRenderOpts(INTEGRATORS[integrator], max_depth, spp_begin, spp_end, seed, 0, 0)
+        st = TakeStats()
+        _check(self.lib.take_gpu_multi_render(self.h, C.byref(o), s.ctypes.data, s2.ctypes.data if s2 is not None else None,
+                                              C.byref(st)))
+        return s, s2, st.as_dict()
+
+    def close(self):
+        if self.h:
+            self.lib.take_gpu_multi_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def render_multi(flat: FlatScene, devices, integrator="mis", max_depth=5, spp_begin=0, spp_end=1, seed=0, sumsq=True):

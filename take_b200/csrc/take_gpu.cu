@@ -1,6 +1,7 @@
 // C-ABI of the B200 rendering core (include/take_gpu.h): host orchestration of the CUDA kernels.
 // There is no CPU fallback anywhere in this file: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -1243,7 +1244,8 @@ int take_gpu_render(TakeScene *s, const TakeRenderOpts *o, double *sum_rgb, doub
 }
 
 // ---- single-process multi-GPU render: scene replicated, sample ranges sharded, one NCCL sum-reduce ------------------
-#include <dlfcn.h>
+}  // extern "C"
+
 namespace {
 struct Nccl {
     typedef void *comm_t;
@@ -1268,47 +1270,79 @@ struct Nccl {
     }
 };
 const int kNcclFloat64 = 8, kNcclSum = 0;  // ncclDataType_t / ncclRedOp_t values (nccl.h)
+Nccl &g_nccl() {
+    static Nccl n;  // libnccl.so.2 is loaded on first use
+    return n;
+}
 }  // namespace
 
-int take_gpu_render_multi(int ndev, const int *devices, const TakeSceneDesc *d, const TakeRenderOpts *o, double *sum_rgb,
-                          double *sumsq_rgb, TakeStats *stats) {
-    if (ndev < 1 || !devices || !o || !sum_rgb) return fail(TAKE_E_INVALID, "bad arguments");
+// Persistent multi-GPU handle: everything that does not depend on the render call is done once -- host-side trees built
+// once, one replica per device uploaded from its own host thread, ONE communicator over all devices, per-device partial
+// accumulation buffers -- so that a render call is only: enqueue every device's share (no host synchronisation in
+// between), one grouped ncclReduce onto devices[0], one device->host copy there.
+struct TakeMulti {
+    int ndev = 0;
+    std::vector<int> devices;
+    std::vector<TakeScene *> scenes;
+    std::vector<double *> d_sum, d_sq;
+    std::vector<cudaEvent_t> e0, e1, e_end;
+    std::vector<Nccl::comm_t> comms;
+    size_t count = 0;
+};
+
+extern "C" {
+
+int take_gpu_multi_destroy(TakeMulti *m) {
+    if (!m) return TAKE_OK;
+    for (int i = 0; i < m->ndev; ++i) {
+        cudaSetDevice(m->devices[i]);
+        if (i < (int)m->comms.size() && m->comms[i]) g_nccl().CommDestroy(m->comms[i]);
+        if (i < (int)m->d_sum.size() && m->d_sum[i]) cudaFree(m->d_sum[i]);
+        if (i < (int)m->d_sq.size() && m->d_sq[i]) cudaFree(m->d_sq[i]);
+        if (i < (int)m->e0.size() && m->e0[i]) cudaEventDestroy(m->e0[i]);
+        if (i < (int)m->e1.size() && m->e1[i]) cudaEventDestroy(m->e1[i]);
+        if (i < (int)m->e_end.size() && m->e_end[i]) cudaEventDestroy(m->e_end[i]);
+        if (i < (int)m->scenes.size() && m->scenes[i]) take_gpu_scene_destroy(m->scenes[i]);
+    }
+    delete m;
+    return TAKE_OK;
+}
+
+int take_gpu_multi_create(int ndev, const int *devices, const TakeSceneDesc *d, TakeMulti **out) {
+    if (!out) return fail(TAKE_E_INVALID, "null argument");
+    *out = nullptr;
+    if (ndev < 1 || ndev > 64 || !devices) return fail(TAKE_E_INVALID, "bad device list");
+    for (int i = 0; i < ndev; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) return fail(TAKE_E_INVALID, "a device is listed twice");
     if (int rc = validate(d)) return rc;
-    static Nccl nccl;
-    if (ndev > 1 && !nccl.ok) return fail(TAKE_E_CUDA, "libnccl.so.2 could not be loaded (needed to combine the partial images)");
+    if (ndev > 1 && !g_nccl().ok) return fail(TAKE_E_CUDA, "libnccl.so.2 could not be loaded (needed to combine the partial images)");
     HostBuild hb;
     if (int rc = host_build(d, std::max(1u, std::thread::hardware_concurrency()), hb)) return rc;
-    const size_t count = (size_t)d->camera.width * d->camera.height * 3, bytes = count * sizeof(double);
-    std::vector<TakeScene *> scenes(ndev, nullptr);
-    std::vector<double *> d_sum(ndev, nullptr), d_sq(ndev, nullptr);
-    std::vector<TakeStats> st(ndev);
+    TakeMulti *m = new TakeMulti;
+    m->ndev = ndev;
+    m->devices.assign(devices, devices + ndev);
+    m->scenes.assign(ndev, nullptr);
+    m->d_sum.assign(ndev, nullptr);
+    m->d_sq.assign(ndev, nullptr);
+    m->e0.assign(ndev, nullptr);
+    m->e1.assign(ndev, nullptr);
+    m->e_end.assign(ndev, nullptr);
+    m->count = (size_t)d->camera.width * d->camera.height * 3;
+    const size_t bytes = m->count * sizeof(double);
     std::vector<int> rcs(ndev, TAKE_OK);
     std::vector<std::string> errs(ndev);
-    auto cleanup = [&]() {
-        for (int i = 0; i < ndev; ++i) {
-            cudaSetDevice(devices[i]);
-            if (d_sum[i]) cudaFree(d_sum[i]);
-            if (d_sq[i]) cudaFree(d_sq[i]);
-            if (scenes[i]) take_gpu_scene_destroy(scenes[i]);
-        }
-    };
-    // replicas: one host thread per GPU uploads the scene and renders its contiguous share of [spp_begin, spp_end)
-    const int64_t n = std::max<int64_t>(0, o->spp_end - o->spp_begin), base = n / ndev, rem = n % ndev;
     std::vector<std::thread> pool;
     for (int i = 0; i < ndev; ++i) {
         pool.emplace_back([&, i]() {
             auto body = [&]() -> int {
-                if (int rc = scene_create_from(devices[i], d, hb, &scenes[i])) return rc;
-                CU(cudaMalloc((void **)&d_sum[i], bytes));
-                CU(cudaMemsetAsync(d_sum[i], 0, bytes, scenes[i]->stream));
-                if (sumsq_rgb) {
-                    CU(cudaMalloc((void **)&d_sq[i], bytes));
-                    CU(cudaMemsetAsync(d_sq[i], 0, bytes, scenes[i]->stream));
-                }
-                TakeRenderOpts mine = *o;
-                mine.spp_begin = o->spp_begin + i * base + std::min<int64_t>(i, rem);
-                mine.spp_end = mine.spp_begin + base + (i < rem ? 1 : 0);
-                return take_gpu_render_device(scenes[i], &mine, d_sum[i], d_sq[i], &st[i]);
+                if (int rc = scene_create_from(devices[i], d, hb, &m->scenes[i])) return rc;
+                CU(cudaMalloc((void **)&m->d_sum[i], bytes));
+                CU(cudaMalloc((void **)&m->d_sq[i], bytes));
+                CU(cudaEventCreate(&m->e0[i]));
+                CU(cudaEventCreate(&m->e1[i]));
+                CU(cudaEventCreate(&m->e_end[i]));
+                return TAKE_OK;
             };
             rcs[i] = body();
             if (rcs[i]) errs[i] = g_error;  // g_error is thread-local
@@ -1316,39 +1350,94 @@ int take_gpu_render_multi(int ndev, const int *devices, const TakeSceneDesc *d, 
     }
     for (auto &t : pool) t.join();
     for (int i = 0; i < ndev; ++i)
-        if (rcs[i]) { int rc = rcs[i]; std::string e = errs[i]; cleanup(); return fail(rc, e); }
-    // the path's one exchange step: sum-reduce of the W x H x 3 partial buffers onto devices[0] over NVLink
+        if (rcs[i]) { int rc = rcs[i]; std::string e = errs[i]; take_gpu_multi_destroy(m); return fail(rc, e); }
     if (ndev > 1) {
-        std::vector<Nccl::comm_t> comms(ndev, nullptr);
-        int r = nccl.CommInitAll(comms.data(), ndev, devices);
-        if (r) { cleanup(); return fail(TAKE_E_CUDA, std::string("ncclCommInitAll: ") + nccl.GetErrorString(r)); }
+        m->comms.assign(ndev, nullptr);
+        int r = g_nccl().CommInitAll(m->comms.data(), ndev, devices);
+        if (r) {
+            std::string e = std::string("ncclCommInitAll: ") + g_nccl().GetErrorString(r);
+            take_gpu_multi_destroy(m);
+            return fail(TAKE_E_CUDA, e);
+        }
+    }
+    *out = m;
+    return TAKE_OK;
+}
+
+// Device i renders a contiguous share of [spp_begin, spp_end) of every pixel; the partial sums are combined on
+// devices[0] with one grouped ncclReduce (the path's one exchange step) and copied to the host from there.
+int take_gpu_multi_render(TakeMulti *m, const TakeRenderOpts *o, double *sum_rgb, double *sumsq_rgb, TakeStats *stats) {
+    if (!m || !o || !sum_rgb) return fail(TAKE_E_INVALID, "null argument");
+    if (int rc = check_opts(m->scenes[0], o)) return rc;
+    const int ndev = m->ndev;
+    const size_t bytes = m->count * sizeof(double);
+    const int64_t n = std::max<int64_t>(0, o->spp_end - o->spp_begin), base = n / ndev, rem = n % ndev;
+    std::vector<int64_t> launches(ndev, 0), waves(ndev, 0);
+    for (int i = 0; i < ndev; ++i) {   // enqueue only: nothing here waits for a device
+        TakeScene *s = m->scenes[i];
+        CU(cudaSetDevice(m->devices[i]));
+        CU(cudaMemsetAsync(m->d_sum[i], 0, bytes, s->stream));
+        if (sumsq_rgb) CU(cudaMemsetAsync(m->d_sq[i], 0, bytes, s->stream));
+        TakeRenderOpts mine = *o;
+        mine.spp_begin = o->spp_begin + i * base + std::min<int64_t>(i, rem);
+        mine.spp_end = mine.spp_begin + base + (i < rem ? 1 : 0);
+        mine.flags &= ~TAKE_RENDER_STAGE_TIMES;
+        StageTimer tm;
+        CU(s->totals.ensure(sizeof(Totals)));
+        if (int rc = render_enqueue(s, &mine, m->d_sum[i], sumsq_rgb ? m->d_sq[i] : nullptr, s->totals.as<Totals>(), tm, m->e0[i],
+                                    m->e1[i], launches[i], waves[i]))
+            return rc;
+    }
+    if (ndev > 1) {
+        int r = 0;
         for (int pass = 0; pass < (sumsq_rgb ? 2 : 1) && !r; ++pass) {
-            nccl.GroupStart();
+            g_nccl().GroupStart();
             for (int i = 0; i < ndev && !r; ++i) {
-                double *buf = pass == 0 ? d_sum[i] : d_sq[i];
-                r = nccl.Reduce(buf, buf, count, kNcclFloat64, kNcclSum, 0, comms[i], scenes[i]->stream);
+                double *buf = pass == 0 ? m->d_sum[i] : m->d_sq[i];
+                r = g_nccl().Reduce(buf, buf, m->count, kNcclFloat64, kNcclSum, 0, m->comms[i], m->scenes[i]->stream);
             }
-            int e = nccl.GroupEnd();
+            const int e = g_nccl().GroupEnd();
             if (!r) r = e;
         }
-        for (int i = 0; i < ndev; ++i) { cudaSetDevice(devices[i]); cudaStreamSynchronize(scenes[i]->stream); }
-        for (auto c : comms) if (c) nccl.CommDestroy(c);
-        if (r) { cleanup(); return fail(TAKE_E_CUDA, std::string("ncclReduce: ") + nccl.GetErrorString(r)); }
+        if (r) return fail(TAKE_E_CUDA, std::string("ncclReduce: ") + g_nccl().GetErrorString(r));
     }
-    cudaSetDevice(devices[0]);
-    cudaError_t ce = cudaMemcpy(sum_rgb, d_sum[0], bytes, cudaMemcpyDeviceToHost);
-    if (ce == cudaSuccess && sumsq_rgb) ce = cudaMemcpy(sumsq_rgb, d_sq[0], bytes, cudaMemcpyDeviceToHost);
-    if (stats) {
-        memset(stats, 0, sizeof(*stats));
-        for (int i = 0; i < ndev; ++i) {
-            stats->samples += st[i].samples; stats->extend_rays += st[i].extend_rays; stats->shadow_rays += st[i].shadow_rays;
-            stats->shaded += st[i].shaded; stats->kernel_launches += st[i].kernel_launches; stats->waves += st[i].waves;
-            stats->ms_total = std::max(stats->ms_total, st[i].ms_total);
+    for (int i = 0; i < ndev; ++i) {
+        CU(cudaSetDevice(m->devices[i]));
+        CU(cudaEventRecord(m->e_end[i], m->scenes[i]->stream));
+    }
+    CU(cudaSetDevice(m->devices[0]));
+    CU(cudaMemcpyAsync(sum_rgb, m->d_sum[0], bytes, cudaMemcpyDeviceToHost, m->scenes[0]->stream));
+    if (sumsq_rgb) CU(cudaMemcpyAsync(sumsq_rgb, m->d_sq[0], bytes, cudaMemcpyDeviceToHost, m->scenes[0]->stream));
+    if (stats) memset(stats, 0, sizeof(*stats));
+    for (int i = 0; i < ndev; ++i) {
+        CU(cudaSetDevice(m->devices[i]));
+        CU(cudaStreamSynchronize(m->scenes[i]->stream));
+        if (stats) {
+            TakeStats st;
+            StageTimer tm;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, m->e0[i], m->e_end[i]);   // this device's share AND its part in the reduce
+            read_totals(m->scenes[i], &st, tm, ms, launches[i], waves[i]);
+            stats->samples += st.samples; stats->extend_rays += st.extend_rays; stats->shadow_rays += st.shadow_rays;
+            stats->shaded += st.shaded; stats->kernel_launches += st.kernel_launches; stats->waves += st.waves;
+            stats->miss_after_light_sample += st.miss_after_light_sample;
+            stats->ms_total = std::max(stats->ms_total, st.ms_total);
         }
     }
-    cleanup();
-    if (ce != cudaSuccess) return fail(TAKE_E_CUDA, cudaGetErrorString(ce));
     return TAKE_OK;
+}
+
+// One-shot form: create, render once, destroy.
+int take_gpu_render_multi(int ndev, const int *devices, const TakeSceneDesc *d, const TakeRenderOpts *o, double *sum_rgb,
+                          double *sumsq_rgb, TakeStats *stats) {
+    if (ndev < 1 || !devices || !o || !sum_rgb) return fail(TAKE_E_INVALID, "bad arguments");
+    TakeMulti *m = nullptr;
+    if (int rc = take_gpu_multi_create(ndev, devices, d, &m)) return rc;
+    const int rc = take_gpu_multi_render(m, o, sum_rgb, sumsq_rgb, stats);
+    const std::string e = g_error;
+    take_gpu_multi_destroy(m);
+    if (rc) g_error = e;
+    return rc;
 }
 
 // ---- output step: mean, double -> float -> half, B/G/R planes, ZIP pre-filter on the device (exr_out.cuh) -----------

@@ -105,3 +105,156 @@ def shared_host_build(flat, directory: str = None):
             hb.close()
         raise RuntimeError("shared_host_build failed: " + "; ".join(sorted(set(errs))))
     return hb
+
+
+class ShardedJob:
+    """One submitted sample range: `wait()` blocks until this rank's part of it (render, reduce, read-back) is complete
+    and returns (stats, sum, sumsq): the host arrays on rank 0 when a read-back was asked for, else the device tensors
+    (reduced on rank 0, partial elsewhere).  Both are VIEWS of one of the renderer's two buffer sets: valid until the
+    submit after next reuses that set (copy what must live longer)."""
+
+    def __init__(self, stats, d_sum, d_sq, h_sum, h_sq, done):
+        self.stats, self.d_sum, self.d_sq, self.h_sum, self.h_sq, self.done = stats, d_sum, d_sq, h_sum, h_sq, done
+        self.collected = False
+
+    def wait(self):
+        self.done.synchronize()
+        self.collected = True
+        return self.stats, (self.h_sum if self.h_sum is not None else self.d_sum), (self.h_sq if self.h_sq is not None else self.d_sq)
+
+
+class _HostEngine:
+    """Stand-ins for the CUDA pieces when ShardedRenderer runs on CPU tensors (the gloo tests): streams are the host's
+    program order, events are already complete."""
+
+    class _Ctx:
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    class _Event:
+        def record(self, *_):
+            pass
+
+        def synchronize(self):
+            pass
+
+        def elapsed_time(self, other):
+            return 0.0
+
+    def stream(self, _):
+        return self._Ctx()
+
+    def event(self):
+        return self._Event()
+
+
+class ShardedRenderer:
+    """The one-process-per-GPU render path (torchrun / the driver's launch): what `parallel_for` over image tiles
+    (src/parallel.cpp:183-237) becomes across GPUs.
+
+    * scene replicated: the host-side trees are built ONCE per node (`shared_host_build`) and every rank creates its
+      `GpuScene` from that build;
+    * `submit(lo, hi)`: this rank renders its share (`shard_spp`) of the sample-index range [lo, hi) of every pixel into
+      one of two device buffer sets, then -- on a side stream, so that it overlaps the NEXT submit's kernels -- the
+      partial sums are combined on rank 0 with one NCCL sum-reduce per buffer (the path's only exchange step) and, when
+      `to_host` is set, rank 0 copies the reduced image into pinned host memory (ONE device->host copy per job; the
+      other ranks copy nothing);
+    * two jobs may be in flight; results depend only on (seed, pixel, sample index), so the reduced image equals the
+      single-GPU image up to summation order.
+    Works without a process group (world = 1: no reduce).
+
+    `render_fn(sum, sumsq_or_None, integrator, max_depth, lo, hi, seed, flags) -> stats dict` replaces the GPU scene in the
+    CPU tests (gloo backend, CPU tensors): the sharding, double buffering and reduce are the code under test there."""
+
+    def __init__(self, flat, device=None, sumsq: bool = True, render_fn=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.flat, self.sumsq = flat, sumsq
+        H, W = flat.height, flat.width
+        self.render_fn = render_fn
+        if render_fn is None:
+            from . import api
+            self.device = torch.device(f"cuda:{device}")
+            hb = shared_host_build(flat)
+            try:
+                self.gs = api.GpuScene(flat, device=device, prebuilt=hb)
+            finally:
+                hb.close()
+            self.ext = torch.cuda.ExternalStream(self.gs.stream, device=self.device)   # the library's render stream
+            self.side = torch.cuda.Stream(device=self.device)                          # reduce + read-back
+            self._stream = lambda st: torch.cuda.stream(st)
+            self._event = lambda: torch.cuda.Event(enable_timing=True)
+        else:
+            self.device = torch.device("cpu")
+            self.gs = None
+            eng = _HostEngine()
+            self.ext = self.side = None
+            self._stream, self._event = eng.stream, eng.event
+        self.d_sum = [torch.zeros((H, W, 3), dtype=torch.float64, device=self.device) for _ in range(2)]
+        self.d_sq = [torch.zeros((H, W, 3), dtype=torch.float64, device=self.device) for _ in range(2)] if sumsq else [None, None]
+        self.h_sum = self.h_sq = None
+        self.jobs = [None, None]
+        self.n = 0
+
+    def _host_buffers(self):
+        if self.h_sum is None:
+            t = self.torch
+            H, W = self.flat.height, self.flat.width
+            pin = self.device.type == "cuda"
+            self.h_sum = [t.empty((H, W, 3), dtype=t.float64, pin_memory=pin) for _ in range(2)]
+            self.h_sq = [t.empty((H, W, 3), dtype=t.float64, pin_memory=pin) for _ in range(2)] if self.sumsq else [None, None]
+
+    def submit(self, integrator, max_depth, spp_begin, spp_end, seed=0, to_host=False, flags=0, shard=True, local=False) -> ShardedJob:
+        """shard=False: this rank renders the whole range itself; local=True: no reduce (a single-rank job inside a
+        multi-rank process group -- e.g. rank 0 checking a reduced image against its own render).  Every rank of the group
+        must make the same sequence of non-local submits (the reduce is a collective)."""
+        k = self.n & 1
+        self.n += 1
+        if self.jobs[k] is not None and not self.jobs[k].collected:
+            self.jobs[k].wait()                       # its buffers are about to be reused
+        lo, hi = shard_spp(spp_begin, spp_end, self.rank, self.world) if shard else (spp_begin, spp_end)
+        with self._stream(self.ext):                  # stream-ordered before the kernels that accumulate into them
+            self.d_sum[k].zero_()
+            if self.sumsq:
+                self.d_sq[k].zero_()
+        # (returns when this rank's kernels are done: the reduce below is enqueued behind complete data)
+        if self.render_fn is None:
+            st = self.gs.render_sums_device(self.d_sum[k].data_ptr(), self.d_sq[k].data_ptr() if self.sumsq else 0, integrator,
+                                            max_depth, lo, hi, seed=seed, flags=flags)
+        else:
+            st = self.render_fn(self.d_sum[k], self.d_sq[k], integrator, max_depth, lo, hi, seed, flags)
+        h_sum = h_sq = None
+        with self._stream(self.side):
+            if self.world > 1 and not local:
+                self.dist.reduce(self.d_sum[k], dst=0)      # NCCL sum-reduce onto rank 0 (NVLink / NVSwitch)
+                if self.sumsq:
+                    self.dist.reduce(self.d_sq[k], dst=0)
+            if to_host and self.rank == 0:
+                self._host_buffers()
+                h_sum = self.h_sum[k]
+                h_sum.copy_(self.d_sum[k], non_blocking=True)
+                if self.sumsq:
+                    h_sq = self.h_sq[k]
+                    h_sq.copy_(self.d_sq[k], non_blocking=True)
+            done = self._event()
+            done.record(self.side)
+        job = ShardedJob(st, self.d_sum[k], self.d_sq[k], None if h_sum is None else h_sum.numpy(),
+                         None if h_sq is None else h_sq.numpy(), done)
+        self.jobs[k] = job
+        return job
+
+    def drain(self):
+        for j in self.jobs:
+            if j is not None and not j.collected:
+                j.wait()
+
+    def close(self):
+        self.drain()
+        if self.gs is not None:
+            self.gs.close()

@@ -115,3 +115,56 @@ def test_shared_host_build_failure_reaches_every_rank(tmp_path):
     for r in range(world):
         assert "shared_host_build failed" in open(tmp_path / f"raised{r}.txt").read()
     assert os.listdir(tmp_path / "x") == []
+
+
+def _sharded_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import bindings as ob
+    from take_b200 import scenes
+    flat = scenes.cornell_box(20, 16, 4, materials="mixed").flat()
+    sc = ob.OracleLib().load(flat)
+    calls = []
+
+    def render_fn(d_sum, d_sq, integrator, max_depth, lo, hi, seed, flags):
+        calls.append((lo, hi))
+        s, s2, st = sc.render(integrator, max_depth, lo, hi, seed=seed, threads=2, stats=True)
+        d_sum += torch.from_numpy(s)
+        if d_sq is not None:
+            d_sq += torch.from_numpy(s2)
+        return {"extend_rays": int(st[0]), "shadow_rays": int(st[1]), "samples": (hi - lo) * flat.width * flat.height}
+
+    sr = tdist.ShardedRenderer(flat, sumsq=True, render_fn=render_fn)
+    # three pipelined jobs (two buffer sets: the third reuses the first), the last one not divisible by the world size
+    ranges = [(0, 4), (4, 8), (8, 8 + world + 1)]
+    jobs = [sr.submit("mis", 3, lo, hi, seed=5, to_host=True) for lo, hi in ranges[:2]]
+    res = [tuple(np.array(a) if isinstance(a, np.ndarray) else a for a in jobs[0].wait())]   # views of a buffer set that job 2 reuses
+    jobs.append(sr.submit("mis", 3, *ranges[2], seed=5, to_host=True))
+    res += [jobs[1].wait(), jobs[2].wait()]
+    # a local job inside the group: no collective, whole range on this rank
+    st, loc, _ = sr.submit("mis", 3, 0, 2, seed=5, to_host=(rank == 0), shard=False, local=True).wait()
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "sharded.npz"), s0=res[0][1], q0=res[0][2], s2=res[2][1], q2=res[2][2], loc=np.asarray(loc))
+    assert calls[:3] == [tdist.shard_spp(lo, hi, rank, world) for lo, hi in ranges] and calls[3] == (0, 2)
+    sr.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_renderer_jobs_equal_single_process(tmp_path, oracle_lib, world):
+    """take_b200.dist.ShardedRenderer (the path bench.py --gpus N drives), gloo backend, CPU renderer injected: every job's
+    reduced image on rank 0 equals the single-process render of the same sample range; buffer sets are reused safely."""
+    from take_b200 import scenes
+    port = 29500 + (os.getpid() % 1000) + 40 + world
+    mp.spawn(_sharded_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    got = np.load(tmp_path / "sharded.npz")
+    sc = oracle_lib.load(scenes.cornell_box(20, 16, 4, materials="mixed").flat())
+    for tag, (lo, hi) in (("0", (0, 4)), ("2", (8, 8 + world + 1))):
+        s, s2 = sc.render("mis", 3, lo, hi, seed=5)
+        assert np.abs(got["s" + tag] - s).max() <= 1e-12 * np.abs(s).max()
+        assert np.abs(got["q" + tag] - s2).max() <= 1e-12 * np.abs(s2).max()
+    s, _ = sc.render("mis", 3, 0, 2, seed=5)
+    assert np.abs(got["loc"] - s).max() <= 1e-12 * np.abs(s).max()

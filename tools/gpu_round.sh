@@ -27,19 +27,21 @@ if [ $rc -eq 0 ] && [ "${SKIP_NCU:-0}" != "1" ]; then
   echo "ncu launches exit $?"
   timeout 300 python tools/prof_run.py --count > $O/prof_run_counts.txt 2>&1
   if timeout 300 python tools/prof_run.py > $O/prof_run.log 2>&1; then
-    timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_extend -c 7 -f -o $O/prof_extend \
-        python tools/prof_run.py > $O/ncu_extend.log 2>&1
+    # one bench step = two waves x 7 passes: ALL 14 launches of each kernel (wave 0 is the sky half of the frame, wave 1 the
+    # heavy half -- capturing only the first seven, as round 1 did, misses 62 % of the extend time)
+    timeout 1500 ncu --set full --clock-control none --import-source on -k regex:k_extend -c 14 -f -o $O/prof_extend \
+        python tools/prof_run.py --integrator=one_sample_mis > $O/ncu_extend.log 2>&1
     echo "ncu extend exit $?"
-    timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_shade -c 3 -f -o $O/prof_shade \
-        python tools/prof_run.py > $O/ncu_shade.log 2>&1
+    timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_shade -c 14 -f -o $O/prof_shade \
+        python tools/prof_run.py --integrator=one_sample_mis > $O/ncu_shade.log 2>&1
     echo "ncu shade exit $?"
-    timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_shadow -c 2 -f -o $O/prof_shadow \
-        python tools/prof_run.py > $O/ncu_shadow.log 2>&1
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_shadow -c 4 -f -o $O/prof_shadow \
+        python tools/prof_run.py --integrator=mis --spp=16 > $O/ncu_shadow.log 2>&1
     echo "ncu shadow exit $?"
   fi
 fi
 if [ "${EXTRA_NCU:-0}" = "1" ]; then
-  # the two captures behind profiles/r01_ncu_shade_mis_config4.csv and r01_ncu_traversal_config5.csv (tools/ncu_stalls.py)
+  # the two captures behind profiles/rNN_ncu_shade_mis_config4.csv and rNN_ncu_traversal_config5.csv (tools/ncu_stalls.py)
   A4="--scene=multi_light --integrator=mis --spp=16"
   A5="--scene=instanced --integrator=mis --spp=4"
   if timeout 300 python tools/prof_run.py $A4 > $O/prof_run_c4.log 2>&1; then

@@ -112,13 +112,38 @@ if os.path.exists(os.path.join(g, "launches_bench.csv")):
     agg, total = launch_list(os.path.join(g, "launches_bench.csv"))
     for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:8]:
         print(f"{k:50s} n={n:4d} {us/1e3:9.3f} ms {100*us/total:5.1f}%")
-if "extend" in res:
-    # DRAM traffic of the dominant kernel per launch: the capture holds exactly the 7 k_extend launches of ONE bench-sized
-    # wave (tools/prof_run.py), so the mean over them is "per launch" in the same sense as bench.py's algorithmic bytes
-    rows = res["extend"]
-    total = sum(r["dram_read_MB"] + r["dram_write_MB"] for r in rows) * 1e6
-    json.dump({"kernel": "k_extend", "dram_bytes_per_launch": total / len(rows), "launches_captured": len(rows),
-               "dram_bytes_per_wave": total,
-               "note": "ncu --set full capture of tools/prof_run.py: the 7 k_extend launches of one 33.2 M-slot wave "
-                       f"(16 spp x 1920x1080, config 2); per-launch rows in {tag}_ncu_extend.csv"},
-              open(os.path.join(OUT, "extend_traffic.json"), "w"), indent=1)
+# Per-kernel figures bench.py quotes under roofline.ncu / roofline.traffic, stamped with the hash of the kernel sources they
+# were captured from (bench.py refuses them for any other sources).  The captures hold every launch of ONE bench step of
+# config 2 (tools/prof_run.py: 32 spp x 1920x1080 = two waves of 33.2 M slots, 7 passes each), so "per launch" means the
+# same as in bench.py's algorithmic bytes per launch.
+sys.path.insert(0, ROOT)
+from take_b200 import api  # noqa: E402
+
+kernels = {}
+for name in ("extend", "shade", "shadow"):
+    rows = res.get(name)
+    if not rows:
+        continue
+    dur = sum(r["duration_us"] for r in rows) * 1e-6
+    insts = sum(r.get("warp_insts", 0) for r in rows)
+    kernels["k_" + name] = {
+        "launches_captured": len(rows),
+        "duration_ms_total_under_ncu": round(dur * 1e3, 3),
+        "dram_bytes_per_launch": sum(r["dram_read_MB"] + r["dram_write_MB"] for r in rows) * 1e6 / len(rows),
+        "dram_gbps": round(sum(r["dram_read_MB"] + r["dram_write_MB"] for r in rows) * 1e6 / dur / 1e9, 1),
+        "l2_to_sm_gbps": round(sum(r.get("l2_bytes_MB", 0) for r in rows) * 1e6 / dur / 1e9, 1),
+        "issue_active_pct": round(sum(r.get("issue_active_pct", 0) * r["duration_us"] for r in rows) / (dur * 1e6), 1),
+        "lanes_per_instruction": round(sum(r.get("active_threads_per_inst", 0) * r.get("warp_insts", 0) for r in rows) / max(insts, 1), 2),
+        "achieved_occupancy_pct": round(sum(r.get("achieved_occupancy_pct", 0) * r["duration_us"] for r in rows) / (dur * 1e6), 1),
+        "l1_hit_pct": round(sum(r.get("l1_hit_pct", 0) * r["duration_us"] for r in rows) / (dur * 1e6), 1),
+        "l2_hit_pct": round(sum(r.get("l2_hit_pct", 0) * r["duration_us"] for r in rows) / (dur * 1e6), 1),
+        "registers": rows[0].get("registers"),
+        "rows": f"{tag}_ncu_{name}.csv",
+    }
+if kernels:
+    head = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+    json.dump({"tag": tag, "source_hash": api.kernel_source_hash(), "git_head_when_summarised": head,
+               "workload": "tools/prof_run.py: config 2, one bench step (32 spp x 1920x1080, two waves), one_sample_mis then mis",
+               "note": "ncu --set full --clock-control none; times under ncu are serialised and cold-cache: use shares, not absolutes",
+               "kernels": kernels}, open(os.path.join(OUT, "ncu_metrics.json"), "w"), indent=1)
+    print(json.dumps(kernels, indent=1))
