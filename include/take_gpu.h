@@ -181,8 +181,12 @@ typedef struct TakeScene TakeScene; /* opaque */
 /* Number of usable CUDA devices. */
 int take_gpu_device_count(int *count);
 
-/* Build the acceleration structures on the host (replaces build_bvh / construct_bvh,
- * src/scene.cpp:4-23, src/bvh.cpp:8-45) and upload the scene to `device` once. */
+/* Build the acceleration structures (replaces build_bvh / construct_bvh, src/scene.cpp:4-23, src/bvh.cpp:8-45) and upload
+ * the scene to `device` once.  The traversal tree is built ON THE DEVICE (PLOC over Morton-sorted primitives, collapsed to
+ * 4-wide nodes: take_b200/csrc/bvh_device.cuh); the reference's own tree -- needed for its equal-t tie order and for
+ * TAKE_ISECT_EXACT -- is built by a background host thread from a private copy of the primitive boxes, so this call returns
+ * without waiting for it and the first call that traces rays joins it.  The caller's arrays are not read after the call
+ * returns.  TAKE_DEVICE_BUILD=0 (environment) selects the host's binned-SAH builder instead. */
 int take_gpu_scene_create(int device, const TakeSceneDesc *desc, TakeScene **out);
 int take_gpu_scene_destroy(TakeScene *scene);
 
@@ -259,7 +263,18 @@ void *take_gpu_scene_stream(TakeScene *scene);
  * number of fast-tree nodes, SM count of the device. */
 int take_gpu_scene_info(TakeScene *scene, double *out);
 
-/* Host-only diagnostics: build exactly the acceleration structures take_gpu_scene_create would upload, without
+/* out[0..7] = milliseconds of take_gpu_scene_create: validation, scene upload, primitive boxes for the reference-order tree
+ * (host), fast-tree build on the device (0 for host-built scenes), shading / light records, the whole call; then 1 if the
+ * fast tree was built on the device, 1 if the reference-order tree is still being built in the background (it is joined by
+ * the first call that traces rays: take_gpu_scene_create itself does not wait for it). */
+int take_gpu_scene_create_timings(TakeScene *scene, double *out8);
+/* Copies the fast tree out of the device for inspection: 128-byte 4-wide nodes (take_b200/csrc/bvh_build.h: WideNode) and
+ * the primitive id of every leaf slot (device-built scenes only; pass NULL otherwise).  Returns the number of wide nodes
+ * (either pointer may be NULL). */
+int64_t take_gpu_scene_debug_tree(TakeScene *scene, void *wide_nodes, int32_t *leaf_prims);
+
+/* Host-only diagnostics: build the acceleration structures of the HOST builders (the ones take_gpu_scene_create_prebuilt
+ * and TAKE_DEVICE_BUILD=0 upload; by default take_gpu_scene_create builds its fast tree on the device), without
  * touching CUDA, and copy them out for inspection (tests/test_bvh_host.py).  Layouts are documented in
  * take_b200/csrc/bvh_build.h. */
 typedef struct TakeHostBuild TakeHostBuild;
@@ -279,6 +294,41 @@ int take_gpu_host_build_free(TakeHostBuild *h);
 int take_gpu_host_build_save(TakeHostBuild *h, const char *path);
 int take_gpu_host_build_load(const char *path, TakeHostBuild **out);
 int take_gpu_scene_create_prebuilt(int device, const TakeSceneDesc *desc, TakeHostBuild *h, TakeScene **out);
+
+/* Scene-description builder: big meshes straight into the flat arrays of TakeSceneDesc, on all host threads.
+ * Replaces, for the shapes routed through it, parse_ply (src/parse/parse_ply.cpp:16-120: tinyply buffers copied element by
+ * element), compute_normals (src/compute_normals.cpp:12-47) and the per-face expansion into one std::variant<Sphere,
+ * Triangle> plus one light per emissive face (src/parse/parse_scene.cpp:934-945).  Shapes must be added in the order the
+ * scene file lists them: primitive ids, light ids and vertex offsets are assigned in call order, exactly as the reference's
+ * parser assigns them, and every value is computed with the reference's FP64 operations in its order -- the arrays are
+ * bit-identical to flattening the reference parser's Scene (tests/test_mesh_load.py).  Host-only: needs no CUDA device.
+ * Matrices are 16 doubles, row-major (Matrix4x4::data, src/matrix.h); NULL = identity.  `inv_to_world` is the reference's
+ * own inverse(to_world) (parse_ply.cpp:72), passed in so that the host's matrix code stays the single source of it.
+ * `radiance` = the shape's <emitter type="area"> radiance (3 doubles) or NULL.  Only triangle faces are accepted (the
+ * reference reads any face list as if it had 3 entries, parse_ply.cpp:83-120; a quad there is silently garbage). */
+typedef struct TakeDescBuilder TakeDescBuilder; /* opaque */
+int take_gpu_builder_create(TakeDescBuilder **out);
+int take_gpu_builder_destroy(TakeDescBuilder *b);
+/* <shape type="ply">: ascii, binary_little_endian or binary_big_endian; x,y,z (float / double), optional nx,ny,nz and u,v,
+ * `list <any int> <any int> vertex_indices`.  face_normals: parse_scene.cpp:826-834 (drop the normals; else compute
+ * angle-weighted vertex normals when the file has none). */
+int take_gpu_builder_add_ply(TakeDescBuilder *b, const char *path, const double *to_world, const double *inv_to_world,
+                             int32_t material_id, int32_t face_normals, const double *radiance);
+/* An already parsed TriangleMesh in world space (rectangle / obj / serialized shapes parsed by the reference's own code):
+ * positions 3*nv, normals 3*nv or NULL, uvs 2*nv or NULL, indices 3*nf mesh-local. */
+int take_gpu_builder_add_mesh(TakeDescBuilder *b, int64_t num_vertices, const double *positions, const double *normals,
+                              const double *uvs, int64_t num_faces, const int32_t *indices, int32_t material_id,
+                              int32_t compute_missing_normals, const double *radiance);
+int take_gpu_builder_add_sphere(TakeDescBuilder *b, const double *center, double radius, int32_t material_id, const double *radiance);
+int take_gpu_builder_add_point_light(TakeDescBuilder *b, const double *intensity, const double *position);
+/* Fills the geometry and light fields of `desc` (counts + pointers into the builder: valid until the next add / destroy);
+ * camera, background, materials, textures and environment fields stay the caller's. */
+int take_gpu_builder_finish(TakeDescBuilder *b, TakeSceneDesc *desc);
+/* out[0..3] = file read, conversion, vertex normals, append: milliseconds of the last take_gpu_builder_add_ply */
+int take_gpu_builder_timings(TakeDescBuilder *b, double *out4);
+/* Writes `desc` as a TAKESCN1 file (take_b200/sceneio.py: the flat arrays, little endian); `spp` = Scene::options.spp.
+ * Host-only. */
+int take_gpu_scene_desc_save(const TakeSceneDesc *desc, int64_t spp, const char *path);
 
 /* Self-test: the multi-threaded twin of std::sort used by the reference-order builder must return std::sort's exact
  * permutation, ties included.  Returns the number of differing positions (0 = identical).  pattern: 0 random, 1 ascending,

@@ -32,6 +32,9 @@ EXPORTS = [
     "take_gpu_version", "take_gpu_exr_packed_size", "take_gpu_exr_pack_device", "take_gpu_exr_pack", "take_gpu_exr_write_packed",
     "take_gpu_render_to_exr", "take_gpu_render_async", "take_gpu_render_wait",
     "take_gpu_multi_create", "take_gpu_multi_render", "take_gpu_multi_destroy",
+    "take_gpu_builder_create", "take_gpu_builder_destroy", "take_gpu_builder_add_ply", "take_gpu_builder_add_mesh",
+    "take_gpu_builder_add_sphere", "take_gpu_builder_add_point_light", "take_gpu_builder_finish", "take_gpu_builder_timings",
+    "take_gpu_scene_desc_save", "take_gpu_scene_create_timings", "take_gpu_scene_debug_tree",
 ]
 
 RAY_DTYPE = np.dtype([("origin", "<f8", 3), ("dir", "<f8", 3), ("tmin", "<f8"), ("tmax", "<f8")])
@@ -100,6 +103,9 @@ def load_library(path: str = LIB_PATH):
     L.take_gpu_scene_stream.restype = vp
     L.take_gpu_scene_stream.argtypes = [vp]
     L.take_gpu_scene_info.argtypes = [vp, vp]
+    L.take_gpu_scene_create_timings.argtypes = [vp, vp]
+    L.take_gpu_scene_debug_tree.restype = i64
+    L.take_gpu_scene_debug_tree.argtypes = [vp, vp, vp]
     L.take_gpu_render_async.argtypes = [vp, C.POINTER(TakeRenderOpts), vp, vp, C.POINTER(i64)]
     L.take_gpu_render_wait.argtypes = [vp, i64, C.POINTER(TakeStats)]
     L.take_gpu_exr_packed_size.restype = i64
@@ -108,6 +114,15 @@ def load_library(path: str = LIB_PATH):
     L.take_gpu_exr_pack.argtypes = [vp, vp, i64, vp]
     L.take_gpu_exr_write_packed.argtypes = [C.c_char_p, C.c_int32, C.c_int32, vp, C.c_int32]
     L.take_gpu_render_to_exr.argtypes = [vp, C.POINTER(TakeRenderOpts), C.c_char_p, C.POINTER(TakeStats)]
+    L.take_gpu_builder_create.argtypes = [C.POINTER(vp)]
+    L.take_gpu_builder_destroy.argtypes = [vp]
+    L.take_gpu_builder_add_ply.argtypes = [vp, C.c_char_p, vp, vp, C.c_int32, C.c_int32, vp]
+    L.take_gpu_builder_add_mesh.argtypes = [vp, i64, vp, vp, vp, i64, vp, C.c_int32, C.c_int32, vp]
+    L.take_gpu_builder_add_sphere.argtypes = [vp, vp, C.c_double, C.c_int32, vp]
+    L.take_gpu_builder_add_point_light.argtypes = [vp, vp, vp]
+    L.take_gpu_builder_finish.argtypes = [vp, C.POINTER(TakeSceneDesc)]
+    L.take_gpu_builder_timings.argtypes = [vp, vp]
+    L.take_gpu_scene_desc_save.argtypes = [C.POINTER(TakeSceneDesc), i64, C.c_char_p]
     L.take_gpu_multi_create.argtypes = [i32, vp, C.POINTER(TakeSceneDesc), C.POINTER(vp)]
     L.take_gpu_multi_render.argtypes = [vp, C.POINTER(TakeRenderOpts), vp, vp, C.POINTER(TakeStats)]
     L.take_gpu_multi_destroy.argtypes = [vp]
@@ -203,6 +218,25 @@ class GpuScene:
         keys = ["build_ms_reference_tree", "build_ms_fast_tree", "fast_tree_depth", "sah_cost", "fast_nodes", "sm_count"]
         return dict(zip(keys, out))
 
+    def create_timings(self) -> dict:
+        """Milliseconds of take_gpu_scene_create by phase (does not wait for the background reference-order tree)."""
+        out = (C.c_double * 8)()
+        _check(self.lib.take_gpu_scene_create_timings(self.h, out))
+        keys = ["validate_ms", "upload_ms", "host_boxes_ms", "device_build_ms", "records_ms", "total_ms", "device_built", "reference_tree_pending"]
+        return dict(zip(keys, out))
+
+    def debug_tree(self, leaf_prims=True):
+        """(wide nodes as a structured array, primitive id per leaf slot or None): the fast tree as it sits on the device."""
+        nw = self.lib.take_gpu_scene_debug_tree(self.h, None, None)
+        if nw < 0:
+            _check(int(nw))
+        wide = np.zeros(nw, WIDE_NODE_DTYPE)
+        lp = np.zeros(self.flat.num_prims, np.int32) if leaf_prims else None
+        rc = self.lib.take_gpu_scene_debug_tree(self.h, wide.ctypes.data, lp.ctypes.data if (lp is not None and lp.size) else None)
+        if rc < 0:
+            _check(int(rc))
+        return wide, lp
+
     @property
     def stream(self) -> int:
         return int(self.lib.take_gpu_scene_stream(self.h) or 0)
@@ -283,6 +317,88 @@ class GpuScene:
         _check(self.lib.take_gpu_radiance_samples(self.h, C.byref(o), len(px), px.ctypes.data, py.ctypes.data,
                                                   s.ctypes.data, out.ctypes.data))
         return out
+
+
+class DescBuilder:
+    """take_gpu_builder_*: big meshes straight into the flat arrays of a TakeSceneDesc on all host threads (replaces
+    parse_ply + compute_normals + the per-face Shape / light expansion of the reference's parser for the shapes routed
+    through it).  Shapes must be added in scene-file order.  `arrays()` copies the geometry / light arrays out."""
+
+    def __init__(self):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        _check(self.lib.take_gpu_builder_create(C.byref(self.h)))
+
+    @staticmethod
+    def _vec(a, n):
+        if a is None:
+            return None, None
+        a = np.ascontiguousarray(a, np.float64).reshape(-1)
+        assert a.size == n
+        return a, a.ctypes.data
+
+    def add_ply(self, path, material_id, to_world=None, inv_to_world=None, face_normals=False, radiance=None):
+        m, mp = self._vec(to_world, 16)
+        mi, mip = self._vec(inv_to_world, 16)
+        r, rp = self._vec(radiance, 3)
+        _check(self.lib.take_gpu_builder_add_ply(self.h, os.fsencode(path), mp, mip, material_id, int(face_normals), rp))
+
+    def add_mesh(self, positions, indices, material_id, normals=None, uvs=None, compute_missing_normals=True, radiance=None):
+        pos = np.ascontiguousarray(positions, np.float64).reshape(-1, 3)
+        idx = np.ascontiguousarray(indices, np.int32).reshape(-1, 3)
+        n, npn = self._vec(normals, pos.size)
+        u, upn = self._vec(uvs, 2 * len(pos))
+        r, rp = self._vec(radiance, 3)
+        _check(self.lib.take_gpu_builder_add_mesh(self.h, len(pos), pos.ctypes.data, npn, upn, len(idx), idx.ctypes.data, material_id,
+                                                  int(compute_missing_normals), rp))
+
+    def add_sphere(self, center, radius, material_id, radiance=None):
+        c, cp = self._vec(center, 3)
+        r, rp = self._vec(radiance, 3)
+        _check(self.lib.take_gpu_builder_add_sphere(self.h, cp, float(radius), material_id, rp))
+
+    def add_point_light(self, intensity, position):
+        i, ip = self._vec(intensity, 3)
+        p, pp = self._vec(position, 3)
+        _check(self.lib.take_gpu_builder_add_point_light(self.h, ip, pp))
+
+    def timings(self) -> dict:
+        out = (C.c_double * 4)()
+        _check(self.lib.take_gpu_builder_timings(self.h, out))
+        return dict(zip(("ms_read", "ms_convert", "ms_normals", "ms_append"), out))
+
+    def desc(self) -> TakeSceneDesc:
+        """Geometry and light fields filled (pointers into the builder: keep it alive); the rest zero."""
+        d = TakeSceneDesc()
+        _check(self.lib.take_gpu_builder_finish(self.h, C.byref(d)))
+        return d
+
+    def arrays(self) -> dict:
+        from .sceneio import LIGHT_DTYPE
+        d = self.desc()
+
+        def arr(ptr, n, dt):
+            if n == 0:
+                return np.zeros(0, dt)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n * np.dtype(dt).itemsize,)).view(dt).copy()
+
+        nv, npr = d.num_vertices, d.num_prims
+        return dict(positions=arr(d.positions, 3 * nv, np.float64).reshape(-1, 3), normals=arr(d.normals, 3 * nv, np.float64).reshape(-1, 3),
+                    uvs=arr(d.uvs, 2 * nv, np.float64).reshape(-1, 2), indices=arr(d.indices, 3 * npr, np.int32).reshape(-1, 3),
+                    prim_material=arr(d.prim_material, npr, np.int32), prim_light=arr(d.prim_light, npr, np.int32),
+                    prim_flags=arr(d.prim_flags, npr, np.uint8), spheres=arr(d.spheres, 4 * d.num_spheres, np.float64).reshape(-1, 4),
+                    lights=arr(d.lights, d.num_lights, LIGHT_DTYPE))
+
+    def close(self):
+        if self.h:
+            self.lib.take_gpu_builder_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class MultiGpuScene:

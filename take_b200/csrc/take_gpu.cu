@@ -18,6 +18,7 @@
 #include "bvh_build.h"
 #include "wavefront.cuh"
 #include "exr_out.cuh"
+#include "bvh_device.cuh"
 
 using namespace take;
 
@@ -45,6 +46,13 @@ int fail(int code, const std::string &msg) {
 int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
     return v && *v ? atoi(v) : dflt;
+}
+
+// Host threads the builders may use: all cores, unless TAKE_HOST_THREADS says otherwise (one process per GPU: every rank of a
+// node would otherwise start a full set of threads on the same cores).
+int host_threads() {
+    const int e = env_int("TAKE_HOST_THREADS", 0);
+    return e > 0 ? e : (int)std::max(1u, std::thread::hardware_concurrency());
 }
 
 struct DeviceBuffer {
@@ -100,12 +108,23 @@ struct TakeScene {
     bool wide = true;   // 4-wide nodes (TAKE_BVH_WIDTH=4, default) or binary nodes (TAKE_BVH_WIDTH=2)
     int traversal = 1;  // 1: one ray per thread to completion (default, measured faster); 2: warp-persistent while-while
                         // with dynamic re-fetch (TAKE_TRAVERSAL=2)
+    // Device-built scenes: the reference-order tree (tie-break ranks, exact mode) is built by a host thread while the device
+    // builds the fast tree and while the caller goes on; finish_reference_tree() joins it before the first query.
+    std::thread ref_thread;
+    bool ref_pending = false;
+    RefTree ref_host;
+    std::vector<Aabb> ref_boxes;
+    double ref_t0 = 0;
+    DeviceBuffer leaf_prims;
+    bool device_built = false;
+    double create_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // validate, upload, prim boxes (host), device build, records, total, -, -
     // diagnostics
     double build_ms_ref = 0, build_ms_fast = 0;
     int fast_depth = 0;
     double sah_cost = 0;
     int64_t num_fast_nodes = 0;
     ~TakeScene() {
+        if (ref_thread.joinable()) ref_thread.join();
         for (auto *b : tex_data) delete b;
         for (auto e : ev_acc) if (e) cudaEventDestroy(e);
         if (ev_begin) cudaEventDestroy(ev_begin);
@@ -587,19 +606,188 @@ int take_gpu_device_count(int *count) {
     return TAKE_OK;
 }
 
-static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild &hb, TakeScene **out);
+static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild *hb, TakeScene **out);
 
+// The fast tree is built on the device (bvh_device.cuh) unless TAKE_DEVICE_BUILD=0 asks for the host's binned-SAH builder
+// (the A/B baseline for tree quality; also what the prebuilt / saved-build paths use).
 int take_gpu_scene_create(int device, const TakeSceneDesc *d, TakeScene **out) {
     if (!out) return fail(TAKE_E_INVALID, "null argument");
     *out = nullptr;
+    const double t0 = now_ms();
     if (int rc = validate(d)) return rc;
-    HostBuild hb;
-    if (int rc = host_build(d, std::max(1u, std::thread::hardware_concurrency()), hb)) return rc;
-    return scene_create_from(device, d, hb, out);
+    const double t_validate = now_ms() - t0;
+    int rc;
+    if (env_int("TAKE_DEVICE_BUILD", 1) && !TAKE_EXPERIMENTAL) {
+        rc = scene_create_from(device, d, nullptr, out);
+    } else {
+        HostBuild hb;
+        if ((rc = host_build(d, host_threads(), hb))) return rc;
+        rc = scene_create_from(device, d, &hb, out);
+    }
+    if (rc == TAKE_OK) { (*out)->create_ms[0] = t_validate; (*out)->create_ms[5] = now_ms() - t0; }
+    return rc;
 }
 
-// Upload an already built scene to `device` (the host-side trees are shared by all replicas of a multi-GPU render).
-static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild &hb, TakeScene **out) {
+// Join the background build of the reference-order tree (device-built scenes), upload it and write the tie-break ranks into
+// the leaf records.  Every entry point that traces rays calls this first; it is a no-op afterwards.
+static int finish_reference_tree(TakeScene *s) {
+    if (!s->ref_pending) return TAKE_OK;
+    s->ref_pending = false;
+    if (s->ref_thread.joinable()) s->ref_thread.join();
+    CU(cudaSetDevice(s->device));
+    RefTree &ref = s->ref_host;
+    if (int rc = upload(s->ref_nodes, ref.nodes.data(), ref.nodes.size(), s->stream)) return rc;
+    if (int rc = upload(s->dfs_rank, ref.dfs_rank.data(), ref.dfs_rank.size(), s->stream)) return rc;
+    s->dev.ref_nodes = s->ref_nodes.as<RefNode>();
+    s->dev.ref_root = ref.root;
+    s->dev.dfs_rank = s->dfs_rank.as<int32_t>();
+    const int64_t n = s->dev.num_prims;
+    if (n > 0) {
+        devbuild::k_patch_ranks<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(n, s->dfs_rank.as<int32_t>(), s->tris.as<double>());
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(s->stream));   // the host copies are released below
+    std::vector<RefNode>().swap(ref.nodes);
+    std::vector<int32_t>().swap(ref.dfs_rank);
+    return TAKE_OK;
+}
+
+// Fast tree on the device: see bvh_device.cuh.  Needs the scene arrays (positions, indices, flags, spheres) resident and
+// s->dev pointing at them.  Fills s->wide_nodes, s->leaf_prims, s->tris (leaf records without ranks).
+static int device_build_fast_tree(TakeScene *s, int max_leaf, double &abs_max) {
+    using namespace devbuild;
+    cudaStream_t st = s->stream;
+    const int64_t n = s->dev.num_prims;
+    abs_max = 0;
+    CU(s->leaf_prims.ensure(std::max<size_t>((size_t)n * 4, 16)));
+    CU(s->tris.ensure(std::max<size_t>((size_t)n * 96, 32)));
+    DeviceBuffer wide_tmp, nodes, plo, phi, glob, keys, vals, cl_a, cl_b, nnb, flags, scan, items_a, items_b, kids, icount, iscan, cubtmp, tail;
+    CU(wide_tmp.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(WideNode)));
+    if (n == 0) {
+        k_wide_wrap_root<<<1, 32, 0, st>>>(nullptr, 0, 0, wide_tmp.as<WideNode>(), s->leaf_prims.as<int32_t>());
+        CU(cudaGetLastError());
+        CU(s->wide_nodes.ensure(sizeof(WideNode)));
+        CU(cudaMemcpyAsync(s->wide_nodes.p, wide_tmp.p, sizeof(WideNode), cudaMemcpyDeviceToDevice, st));
+        CU(cudaStreamSynchronize(st));
+        s->fast_depth = 1; s->num_fast_nodes = 1; s->sah_cost = 0;
+        return TAKE_OK;
+    }
+    const unsigned gb = (unsigned)((n + TAKE_DB_BLOCK - 1) / TAKE_DB_BLOCK);
+    CU(plo.ensure((size_t)n * 16)); CU(phi.ensure((size_t)n * 16));
+    CU(glob.ensure(sizeof(Globals)));
+    {
+        Globals g;
+        memset(&g, 0, sizeof(g));
+        for (int a = 0; a < 3; ++a) { g.cmin[a] = 0xffffffffu; g.cmax[a] = 0u; }
+        CU(cudaMemcpyAsync(glob.p, &g, sizeof(g), cudaMemcpyHostToDevice, st));
+    }
+    k_prim_boxes<<<gb, TAKE_DB_BLOCK, 0, st>>>(s->dev, n, plo.as<float4>(), phi.as<float4>(), glob.as<Globals>());
+    CU(cudaGetLastError());
+    // Morton order
+    CU(keys.ensure((size_t)n * 16)); CU(vals.ensure((size_t)n * 8));   // double buffers: [0, n) and [n, 2n)
+    k_morton<<<gb, TAKE_DB_BLOCK, 0, st>>>(n, plo.as<float4>(), phi.as<float4>(), glob.as<Globals>(), keys.as<uint64_t>(), vals.as<uint32_t>());
+    CU(cudaGetLastError());
+    cub::DoubleBuffer<uint64_t> dk(keys.as<uint64_t>(), keys.as<uint64_t>() + n);
+    cub::DoubleBuffer<uint32_t> dv(vals.as<uint32_t>(), vals.as<uint32_t>() + n);
+    size_t tmp_sort = 0, tmp_scan64 = 0, tmp_scan32 = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, dk, dv, (int)n, 0, 63, st));
+    CU(flags.ensure((size_t)n * 8)); CU(scan.ensure((size_t)n * 8));
+    CU(icount.ensure((size_t)n * 4)); CU(iscan.ensure((size_t)n * 4));
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan64, flags.as<uint64_t>(), scan.as<uint64_t>(), (int)n, st));
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan32, icount.as<uint32_t>(), iscan.as<uint32_t>(), (int)n, st));
+    size_t tmp_bytes = std::max(std::max(tmp_sort, tmp_scan64), std::max(tmp_scan32, (size_t)256));
+    CU(cubtmp.ensure(tmp_bytes));
+    CU(cub::DeviceRadixSort::SortPairs(cubtmp.p, tmp_bytes, dk, dv, (int)n, 0, 63, st));
+    // PLOC
+    CU(nodes.ensure((size_t)(2 * n) * sizeof(BNode)));
+    CU(cl_a.ensure((size_t)n * 4)); CU(cl_b.ensure((size_t)n * 4)); CU(nnb.ensure((size_t)n * 4));
+    const float c_trav = 1.0f, c_isect = 1.2f;   // SahBuilder's constants (bvh_build.cpp)
+    k_init_leaves<<<gb, TAKE_DB_BLOCK, 0, st>>>(n, dv.Current(), plo.as<float4>(), phi.as<float4>(), nodes.as<BNode>(), cl_a.as<int32_t>(), c_isect);
+    CU(cudaGetLastError());
+    int32_t *cin = cl_a.as<int32_t>(), *cout = cl_b.as<int32_t>();
+    int32_t m = (int32_t)n, next_node = (int32_t)n;
+    uint64_t *h_tail = nullptr;
+    CU(cudaMallocHost((void **)&h_tail, 4 * sizeof(uint64_t)));
+    struct HostFree { void *p; ~HostFree() { cudaFreeHost(p); } } host_free{h_tail};
+    int rounds = 0;
+    bool pair_fallback = false;
+    while (m > 1) {
+        const unsigned g = (unsigned)((m + TAKE_DB_BLOCK - 1) / TAKE_DB_BLOCK);
+        if (!pair_fallback) k_ploc_nn<TAKE_PLOC_RADIUS><<<g, TAKE_DB_BLOCK, 0, st>>>(m, cin, nodes.as<BNode>(), nnb.as<int32_t>());
+        else k_ploc_pairs<<<g, TAKE_DB_BLOCK, 0, st>>>(m, nnb.as<int32_t>());
+        k_ploc_flags<<<g, TAKE_DB_BLOCK, 0, st>>>(m, nnb.as<int32_t>(), flags.as<uint64_t>());
+        CU(cub::DeviceScan::ExclusiveSum(cubtmp.p, tmp_bytes, flags.as<uint64_t>(), scan.as<uint64_t>(), m, st));
+        CU(cudaMemcpyAsync(h_tail, scan.as<uint64_t>() + (m - 1), 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h_tail + 1, flags.as<uint64_t>() + (m - 1), 8, cudaMemcpyDeviceToHost, st));
+        k_ploc_merge<<<g, TAKE_DB_BLOCK, 0, st>>>(m, nnb.as<int32_t>(), flags.as<uint64_t>(), scan.as<uint64_t>(), cin, cout, nodes.as<BNode>(),
+                                                 next_node, max_leaf, c_trav, c_isect);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(st));
+        const uint64_t tot = h_tail[0] + h_tail[1];
+        const int32_t survivors = (int32_t)(tot & 0xffffffffull), created = (int32_t)(tot >> 32);
+        if (survivors + created != m || created < 0) return fail(TAKE_E_CUDA, "device BVH build: inconsistent PLOC round");
+        // a round without a merge can only come from non-finite areas (coordinates near FLT_MAX): pair neighbours up instead
+        if (created == 0 && pair_fallback) return fail(TAKE_E_CUDA, "device BVH build: no progress");
+        pair_fallback = created == 0;
+        m = survivors;
+        next_node += created;
+        std::swap(cin, cout);
+        ++rounds;
+    }
+    const int32_t root = n > 1 ? next_node - 1 : 0;
+    if (n > 1 && next_node != (int32_t)(2 * n - 1)) return fail(TAKE_E_CUDA, "device BVH build: node count mismatch");
+    // wide collapse, breadth first
+    BNode h_root;
+    CU(cudaMemcpyAsync(&h_root, nodes.as<BNode>() + root, sizeof(BNode), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    s->sah_cost = h_root.hi.w;
+    int32_t n_wide = 1, depth = 1;
+    if (h_root.leaf) {
+        k_wide_wrap_root<<<1, 32, 0, st>>>(nodes.as<BNode>(), root, n, wide_tmp.as<WideNode>(), s->leaf_prims.as<int32_t>());
+        CU(cudaGetLastError());
+    } else {
+        CU(items_a.ensure((size_t)n * sizeof(WorkItem))); CU(items_b.ensure((size_t)n * sizeof(WorkItem)));
+        CU(kids.ensure((size_t)n * sizeof(Kids)));
+        WorkItem first_item = {root, 0, 0, 0};
+        CU(cudaMemcpyAsync(items_a.p, &first_item, sizeof(first_item), cudaMemcpyHostToDevice, st));
+        WorkItem *ia = items_a.as<WorkItem>(), *ib = items_b.as<WorkItem>();
+        int32_t n_items = 1;
+        uint32_t *h32 = reinterpret_cast<uint32_t *>(h_tail);
+        while (n_items > 0) {
+            const unsigned g = (unsigned)((n_items + TAKE_DB_BLOCK - 1) / TAKE_DB_BLOCK);
+            k_wide_kids<<<g, TAKE_DB_BLOCK, 0, st>>>(n_items, ia, nodes.as<BNode>(), kids.as<Kids>(), icount.as<uint32_t>());
+            CU(cub::DeviceScan::ExclusiveSum(cubtmp.p, tmp_bytes, icount.as<uint32_t>(), iscan.as<uint32_t>(), n_items, st));
+            CU(cudaMemcpyAsync(h32, iscan.as<uint32_t>() + (n_items - 1), 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(h32 + 1, icount.as<uint32_t>() + (n_items - 1), 4, cudaMemcpyDeviceToHost, st));
+            k_wide_emit<<<g, TAKE_DB_BLOCK, 0, st>>>(n_items, ia, kids.as<Kids>(), iscan.as<uint32_t>(), nodes.as<BNode>(), wide_tmp.as<WideNode>(),
+                                                    n_wide, ib, s->leaf_prims.as<int32_t>());
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(st));
+            const int32_t inner = (int32_t)(h32[0] + h32[1]);
+            if (inner < 0 || (int64_t)n_wide + inner > n) return fail(TAKE_E_CUDA, "device BVH build: wide node count out of range");
+            n_wide += inner;
+            n_items = inner;
+            std::swap(ia, ib);
+            if (inner > 0) ++depth;
+        }
+    }
+    CU(s->wide_nodes.ensure((size_t)n_wide * sizeof(WideNode)));
+    CU(cudaMemcpyAsync(s->wide_nodes.p, wide_tmp.p, (size_t)n_wide * sizeof(WideNode), cudaMemcpyDeviceToDevice, st));
+    k_leaf_records<<<gb, TAKE_DB_BLOCK, 0, st>>>(s->dev, n, s->leaf_prims.as<int32_t>(), s->tris.as<double>());
+    CU(cudaGetLastError());
+    Globals hg;
+    CU(cudaMemcpyAsync(&hg, glob.p, sizeof(hg), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memcpy(&abs_max, &hg.abs_max_bits, 8);
+    s->fast_depth = depth;
+    s->num_fast_nodes = n_wide;
+    return TAKE_OK;
+}
+
+// Upload a scene to `device`.  hb != nullptr: acceleration structures built on the host (shared by all replicas of a
+// multi-GPU render, or loaded from a file); hb == nullptr: the fast tree is built on the device and the reference-order
+// tree on a background host thread.
+static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild *hb, TakeScene **out) {
     *out = nullptr;
     CU(cudaSetDevice(device));
     TakeScene *s = new TakeScene;
@@ -611,32 +799,75 @@ static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild &hb, 
     CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     cudaStream_t st = s->stream;
     const int64_t n = d->num_prims;
-    RefTree &ref = hb.ref;
-    FastTree &fast = hb.fast;
-    std::vector<double> &tris = hb.tris;
-    const double abs_max = hb.abs_max;
-    s->build_ms_ref = hb.ms_ref;
-    s->build_ms_fast = hb.ms_fast;
-    s->fast_depth = fast.depth;
-    s->sah_cost = fast.sah_cost;
-    s->num_fast_nodes = (int64_t)fast.nodes.size();
+    const int threads = host_threads();
+    double abs_max = hb ? hb->abs_max : 0.0;
+    double t_mark = now_ms();
     std::vector<uint8_t> mtype((size_t)n);
-    for (int64_t i = 0; i < n; ++i) mtype[i] = (uint8_t)d->materials[d->prim_material[i]].type;
+    std::atomic<int> any_uv_flag(0);
+    parallel_chunks(n, threads, [&](int64_t a0, int64_t a1) {
+        bool uv = false;
+        for (int64_t i = a0; i < a1; ++i) {
+            mtype[i] = (uint8_t)d->materials[d->prim_material[i]].type;
+            uv = uv || (d->prim_flags[i] & TAKE_PRIM_HAS_UVS);
+        }
+        if (uv) any_uv_flag.store(1);
+    });
 
     int rc;
+    if (hb) {
+        s->build_ms_ref = hb->ms_ref;
+        s->build_ms_fast = hb->ms_fast;
+        s->fast_depth = hb->fast.depth;
+        s->sah_cost = hb->fast.sah_cost;
+        s->num_fast_nodes = (int64_t)hb->fast.nodes.size();
 #if TAKE_EXPERIMENTAL
-    if ((rc = upload(s->nodes, fast.nodes.data(), fast.nodes.size(), st))) return rc;  // binary image: A/B runs only
+        if ((rc = upload(s->nodes, hb->fast.nodes.data(), hb->fast.nodes.size(), st))) return rc;  // binary image: A/B runs only
 #endif
-    if ((rc = upload(s->wide_nodes, fast.wide.data(), fast.wide.size(), st))) return rc;
-    if ((rc = upload(s->tris, tris.data(), tris.size(), st))) return rc;
-    if ((rc = upload(s->ref_nodes, ref.nodes.data(), ref.nodes.size(), st))) return rc;
+        if ((rc = upload(s->wide_nodes, hb->fast.wide.data(), hb->fast.wide.size(), st))) return rc;
+        if ((rc = upload(s->tris, hb->tris.data(), hb->tris.size(), st))) return rc;
+        if ((rc = upload(s->ref_nodes, hb->ref.nodes.data(), hb->ref.nodes.size(), st))) return rc;
+        if ((rc = upload(s->dfs_rank, hb->ref.dfs_rank.data(), hb->ref.dfs_rank.size(), st))) return rc;
+    } else {
+        // primitive boxes exactly as build_bvh (src/scene.cpp:4-23) for the reference-order tree, which a host thread builds
+        // from ITS OWN copy while everything else goes on (the caller's arrays are not touched after this call returns)
+        s->ref_boxes.resize((size_t)n);
+        parallel_chunks(n, threads, [&](int64_t a0, int64_t a1) {
+            for (int64_t i = a0; i < a1; ++i) {
+                Aabb &b = s->ref_boxes[i];
+                const int32_t *id = d->indices + 3 * i;
+                if (d->prim_flags[i] & TAKE_PRIM_SPHERE) {
+                    const double *sp = d->spheres + 4 * (int64_t)id[0];
+                    for (int a = 0; a < 3; ++a) { b.lo[a] = sp[a] - sp[3]; b.hi[a] = sp[a] + sp[3]; }
+                } else {
+                    const double *p0 = d->positions + 3 * (int64_t)id[0], *p1 = d->positions + 3 * (int64_t)id[1],
+                                 *p2 = d->positions + 3 * (int64_t)id[2];
+                    for (int a = 0; a < 3; ++a) {
+                        b.lo[a] = std::min(std::min(p0[a], p1[a]), p2[a]);
+                        b.hi[a] = std::max(std::max(p0[a], p1[a]), p2[a]);
+                    }
+                }
+            }
+        });
+        s->create_ms[2] = now_ms() - t_mark;
+        s->ref_t0 = now_ms();
+        s->ref_pending = true;
+        // (leaves a core or two to the caller: the device build and the first waves need the launching thread)
+        const int ref_threads = std::max(1, threads - 1);
+        s->ref_thread = std::thread([s, n, ref_threads] {
+            build_reference_tree(s->ref_boxes.data(), n, ref_threads, s->ref_host);
+            std::vector<Aabb>().swap(s->ref_boxes);
+            s->build_ms_ref = now_ms() - s->ref_t0;
+        });
+        CU(s->ref_nodes.ensure(64));
+        CU(s->dfs_rank.ensure(16));
+    }
+    t_mark = now_ms();
     if ((rc = upload(s->positions, d->positions, (size_t)d->num_vertices * 3, st))) return rc;
     if ((rc = upload(s->normals, d->normals, (size_t)d->num_vertices * 3, st))) return rc;
     if ((rc = upload(s->uvs, d->uvs, (size_t)d->num_vertices * 2, st))) return rc;
     if ((rc = upload(s->indices, d->indices, (size_t)n * 3, st))) return rc;
     if ((rc = upload(s->prim_material, d->prim_material, (size_t)n, st))) return rc;
     if ((rc = upload(s->prim_light, d->prim_light, (size_t)n, st))) return rc;
-    if ((rc = upload(s->dfs_rank, ref.dfs_rank.data(), ref.dfs_rank.size(), st))) return rc;
     if ((rc = upload(s->prim_flags, d->prim_flags, (size_t)n, st))) return rc;
     if ((rc = upload(s->prim_mtype, mtype.data(), mtype.size(), st))) return rc;
     if ((rc = upload(s->spheres, d->spheres, (size_t)d->num_spheres * 4, st))) return rc;
@@ -683,8 +914,8 @@ static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild &hb, 
     v.wide_nodes = s->wide_nodes.as<float4>();
     v.tris = s->tris.as<double2>();
     v.ref_nodes = s->ref_nodes.as<RefNode>();
-    v.ref_root = ref.root;
-    v.fast_depth = fast.depth;
+    v.ref_root = hb ? hb->ref.root : -1;
+    s->create_ms[1] = now_ms() - t_mark;
     v.positions = s->positions.as<double>(); v.normals = s->normals.as<double>(); v.uvs = s->uvs.as<double>();
     v.indices = s->indices.as<int32_t>(); v.prim_material = s->prim_material.as<int32_t>();
     v.prim_light = s->prim_light.as<int32_t>(); v.dfs_rank = s->dfs_rank.as<int32_t>();
@@ -729,12 +960,25 @@ static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild &hb, 
         v.cam_u = {u[0], u[1], u[2]}; v.cam_v = {vv[0], vv[1], vv[2]}; v.cam_w = {w[0], w[1], w[2]};
     }
     v.background = {d->background[0], d->background[1], d->background[2]};
+    if (!hb) {
+        t_mark = now_ms();
+        const int max_leaf = std::min(8, std::max(1, env_int("TAKE_BVH_MAX_LEAF", 4)));
+        if ((rc = device_build_fast_tree(s, max_leaf, abs_max))) return rc;
+        if (3 * s->fast_depth + 1 > TAKE_STACK_SMEM + TAKE_STACK_LOCAL)
+            return fail(TAKE_E_INVALID, "acceleration tree too deep (" + std::to_string(s->fast_depth) + " wide levels)");
+        if (!std::isfinite(abs_max)) return fail(TAKE_E_INVALID, "non-finite scene extent");
+        v.wide_nodes = s->wide_nodes.as<float4>();
+        v.tris = s->tris.as<double2>();
+        s->device_built = true;
+        s->build_ms_fast = s->create_ms[3] = now_ms() - t_mark;
+    }
+    v.fast_depth = s->fast_depth;
     v.abs_max = (float)abs_max;
 
     // per-primitive shading records, derived on the device from the arrays uploaded above (shading.cuh: ShadeRec)
+    t_mark = now_ms();
     {
-        bool any_uv = false;
-        for (int64_t i = 0; i < n && !any_uv; ++i) any_uv = (d->prim_flags[i] & TAKE_PRIM_HAS_UVS) != 0;
+        const bool any_uv = any_uv_flag.load() != 0;
         v.shade_stride = any_uv ? 20 : 16;
         CU(s->shade_recs.ensure(std::max<size_t>((size_t)n * v.shade_stride * sizeof(double), 32)));
         v.shade_recs = s->shade_recs.as<double>();
@@ -751,6 +995,7 @@ static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild &hb, 
         }
         CU(cudaStreamSynchronize(st));
     }
+    s->create_ms[4] = now_ms() - t_mark;
 
     // persistent-kernel launch widths: every SM filled to the occupancy the kernel allows
     auto blocks_for = [&](const void *fn) {
@@ -803,9 +1048,37 @@ void *take_gpu_scene_stream(TakeScene *s) { return s ? (void *)s->stream : nullp
 // diagnostics: out[0..5] = reference-tree build ms, fast-tree build ms, fast-tree depth, SAH cost, #fast nodes, #SMs
 int take_gpu_scene_info(TakeScene *s, double *out) {
     if (!s || !out) return fail(TAKE_E_INVALID, "null argument");
+    if (int rc = finish_reference_tree(s)) return rc;   // (its build time is one of the figures)
     out[0] = s->build_ms_ref; out[1] = s->build_ms_fast; out[2] = s->fast_depth; out[3] = s->sah_cost;
     out[4] = (double)s->num_fast_nodes; out[5] = s->sm_count;
     return TAKE_OK;
+}
+
+// out[0..7] = ms of take_gpu_scene_create: validate, scene upload, primitive boxes for the reference-order tree (host), fast
+// tree (device build; 0 for host-built scenes), shading / light records, whole call, 1 if the fast tree was built on the
+// device, 1 if the reference-order tree is still being built in the background
+int take_gpu_scene_create_timings(TakeScene *s, double *out) {
+    if (!s || !out) return fail(TAKE_E_INVALID, "null argument");
+    for (int i = 0; i < 6; ++i) out[i] = s->create_ms[i];
+    out[6] = s->device_built ? 1 : 0;
+    out[7] = s->ref_pending ? 1 : 0;
+    return TAKE_OK;
+}
+
+// Copies the fast tree out of the device (128-byte WideNodes, and the primitive id of every leaf slot) for inspection;
+// returns the number of wide nodes.  leaf_prims is only kept for device-built scenes (NULL otherwise is fine).
+int64_t take_gpu_scene_debug_tree(TakeScene *s, void *wide_nodes, int32_t *leaf_prims) {
+    if (!s) return fail(TAKE_E_INVALID, "null argument");
+    if (cudaSetDevice(s->device) != cudaSuccess) return fail(TAKE_E_CUDA, "cudaSetDevice");
+    const int64_t nw = s->device_built ? s->num_fast_nodes : (int64_t)(s->wide_nodes.bytes / sizeof(WideNode));
+    if (wide_nodes && cudaMemcpy(wide_nodes, s->wide_nodes.p, (size_t)nw * sizeof(WideNode), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return fail(TAKE_E_CUDA, "copying the tree failed");
+    if (leaf_prims) {
+        if (!s->device_built) return fail(TAKE_E_INVALID, "leaf slots are only kept for device-built scenes");
+        if (cudaMemcpy(leaf_prims, s->leaf_prims.p, (size_t)s->dev.num_prims * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return fail(TAKE_E_CUDA, "copying the leaf slots failed");
+    }
+    return nw;
 }
 
 // ---- host-only diagnostics: the acceleration structures scene_create would upload, without touching CUDA ----
@@ -818,7 +1091,7 @@ int take_gpu_host_build(const TakeSceneDesc *d, TakeHostBuild **out) {
     *out = nullptr;
     if (int rc = validate(d)) return rc;
     TakeHostBuild *h = new TakeHostBuild;
-    if (int rc = host_build(d, std::max(1u, std::thread::hardware_concurrency()), h->hb)) { delete h; return rc; }
+    if (int rc = host_build(d, host_threads(), h->hb)) { delete h; return rc; }
     *out = h;
     return TAKE_OK;
 }
@@ -979,13 +1252,14 @@ int take_gpu_scene_create_prebuilt(int device, const TakeSceneDesc *d, TakeHostB
         b.geom_hash != geometry_hash(d, (int)std::max(1u, std::thread::hardware_concurrency())))
         return fail(TAKE_E_INVALID, "the prebuilt acceleration structures do not belong to this scene");
     if (b.fast.depth > TAKE_STACK_SMEM + TAKE_STACK_LOCAL) return fail(TAKE_E_INVALID, "acceleration tree too deep");
-    return scene_create_from(device, d, h->hb, out);
+    return scene_create_from(device, d, &h->hb, out);
 }
 
 int take_gpu_intersect_device(TakeScene *s, const TakeRay *d_rays, int64_t n, TakeHit *d_hits, int flags) {
     if (!s || (n > 0 && (!d_rays || !d_hits))) return fail(TAKE_E_INVALID, "null argument");
     if (n < 0) return fail(TAKE_E_INVALID, "negative ray count");
     if (n == 0) return TAKE_OK;
+    if (int rc = finish_reference_tree(s)) return rc;
     // the persistent kernels end on a 32-bit work cursor that advances in steps of 32: keep every launch far below 2^32
     const int64_t kChunk = (int64_t)1 << 30;
     if (n > kChunk) {
@@ -1035,6 +1309,7 @@ int take_gpu_occluded(TakeScene *s, const TakeRay *rays, int64_t n, uint8_t *occ
     if (!s || (n > 0 && (!rays || !occluded))) return fail(TAKE_E_INVALID, "null argument");
     if (n < 0) return fail(TAKE_E_INVALID, "negative ray count");
     CU(cudaSetDevice(s->device));
+    if (int rc = finish_reference_tree(s)) return rc;
     const int64_t chunk = 1 << 24;
     for (int64_t off = 0; off < n; off += chunk) {
         const int64_t m = std::min(chunk, n - off);
@@ -1067,6 +1342,7 @@ namespace {
 // orders all of its work.  No host synchronisation; `d_totals` receives the counters.
 int render_enqueue(TakeScene *s, const TakeRenderOpts *o, double *d_sum, double *d_sumsq, Totals *d_totals, StageTimer &tm,
                    cudaEvent_t e0, cudaEvent_t e1, int64_t &launches, int64_t &waves) {
+    if (int rc = finish_reference_tree(s)) return rc;   // tie-break ranks must be in the leaf records before the first ray
     const int64_t npix = (int64_t)s->width * s->height;
     const int64_t spp = o->spp_end - o->spp_begin;
     const int64_t cap_env = std::max<int64_t>(1024, (int64_t)env_int("TAKE_WAVE_SLOTS", 1 << 25));
@@ -1318,7 +1594,7 @@ int take_gpu_multi_create(int ndev, const int *devices, const TakeSceneDesc *d, 
     if (int rc = validate(d)) return rc;
     if (ndev > 1 && !g_nccl().ok) return fail(TAKE_E_CUDA, "libnccl.so.2 could not be loaded (needed to combine the partial images)");
     HostBuild hb;
-    if (int rc = host_build(d, std::max(1u, std::thread::hardware_concurrency()), hb)) return rc;
+    if (int rc = host_build(d, host_threads(), hb)) return rc;
     TakeMulti *m = new TakeMulti;
     m->ndev = ndev;
     m->devices.assign(devices, devices + ndev);
@@ -1336,7 +1612,7 @@ int take_gpu_multi_create(int ndev, const int *devices, const TakeSceneDesc *d, 
     for (int i = 0; i < ndev; ++i) {
         pool.emplace_back([&, i]() {
             auto body = [&]() -> int {
-                if (int rc = scene_create_from(devices[i], d, hb, &m->scenes[i])) return rc;
+                if (int rc = scene_create_from(devices[i], d, &hb, &m->scenes[i])) return rc;
                 CU(cudaMalloc((void **)&m->d_sum[i], bytes));
                 CU(cudaMalloc((void **)&m->d_sq[i], bytes));
                 CU(cudaEventCreate(&m->e0[i]));
@@ -1488,6 +1764,7 @@ int take_gpu_radiance_samples(TakeScene *s, const TakeRenderOpts *o, int64_t n, 
     if (n < 0 || (n > 0 && (!px || !py || !smp || !rgb))) return fail(TAKE_E_INVALID, "bad sample list");
     if (n == 0) return TAKE_OK;
     CU(cudaSetDevice(s->device));
+    if (int rc = finish_reference_tree(s)) return rc;
     const int64_t cap = 1 << 20;
     if (int rc = ensure_wave(s, std::min(n, cap), 1, o->max_depth + 2)) return rc;
     std::vector<int32_t> pixel((size_t)std::min(n, cap));

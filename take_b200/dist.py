@@ -169,7 +169,7 @@ class ShardedRenderer:
     `render_fn(sum, sumsq_or_None, integrator, max_depth, lo, hi, seed, flags) -> stats dict` replaces the GPU scene in the
     CPU tests (gloo backend, CPU tensors): the sharding, double buffering and reduce are the code under test there."""
 
-    def __init__(self, flat, device=None, sumsq: bool = True, render_fn=None):
+    def __init__(self, flat, device=None, sumsq: bool = True, render_fn=None, share_host_build: bool = False):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -180,12 +180,22 @@ class ShardedRenderer:
         self.render_fn = render_fn
         if render_fn is None:
             from . import api
+            import os
             self.device = torch.device(f"cuda:{device}")
-            hb = shared_host_build(flat)
-            try:
-                self.gs = api.GpuScene(flat, device=device, prebuilt=hb)
-            finally:
-                hb.close()
+            if share_host_build:
+                # host-built trees, built once per node and loaded by the other ranks (take_gpu_host_build_save / _load)
+                hb = shared_host_build(flat)
+                try:
+                    self.gs = api.GpuScene(flat, device=device, prebuilt=hb)
+                finally:
+                    hb.close()
+            else:
+                # default: every rank builds its fast tree on ITS device (milliseconds) and the reference-order tree on a
+                # background host thread pool sized to its share of the node's cores
+                local_world = int(os.environ.get("LOCAL_WORLD_SIZE", self.world))
+                if self.world > 1 and "TAKE_HOST_THREADS" not in os.environ:
+                    os.environ["TAKE_HOST_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, local_world)))
+                self.gs = api.GpuScene(flat, device=device)
             self.ext = torch.cuda.ExternalStream(self.gs.stream, device=self.device)   # the library's render stream
             self.side = torch.cuda.Stream(device=self.device)                          # reduce + read-back
             self._stream = lambda st: torch.cuda.stream(st)

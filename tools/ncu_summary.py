@@ -1,5 +1,6 @@
-"""Turn the ncu artefacts of a gpurun call (gpurun_out/*.ncu-rep, launches_bench.csv) into the committed summaries under
-profiles/.  Usage: python tools/ncu_summary.py r01"""
+"""Turn the ncu artefacts of a gpurun call (gpurun_out/prof_*_raw.csv = `ncu --page raw --csv` of each capture, written on
+the GPU box by tools/gpu_round.sh; launches_bench.csv) into the committed summaries under profiles/.
+Usage: python tools/ncu_summary.py r02"""
 import collections, csv, io, json, os, re, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -30,10 +31,16 @@ METRICS = [
 ]
 
 
-def raw(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(out)))
+def raw(path):
+    if path.endswith(".ncu-rep"):
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
+        out = open(path).read()
+    rows = [r for r in csv.reader(io.StringIO(out)) if r and not r[0].startswith("==")]
     return rows[0], rows[1], rows[2:]
+
+
+STALL = "smsp__pcsamp_warps_issue_stalled_"
 
 
 def to_bytes(v, unit):
@@ -67,6 +74,11 @@ def summarise(rep, name):
         if "l2_bytes_MB" in r:
             r["l2_GBps"] = round(r["l2_bytes_MB"] * 1e6 / dur / 1e9, 1)
         r["warp_execution_efficiency_pct"] = round(100 * r.get("active_threads_per_inst", 0) / 32, 1)
+        # stall reasons: share of the warp-state samples (top five)
+        stall = {h[len(STALL):]: float(d[idx[h]].replace(",", "")) for h in hdr if h.startswith(STALL) and "not_issued" not in h and d[idx[h]]}
+        tot = sum(stall.values()) or 1.0
+        for rank, (k, v) in enumerate(sorted(stall.items(), key=lambda kv: -kv[1])[:5]):
+            r[f"stall{rank + 1}"] = f"{k} {100 * v / tot:.0f}%"
         rows.append(r)
     path = os.path.join(OUT, f"{tag}_{name}.csv")
     keys = list(rows[0].keys())
@@ -99,8 +111,10 @@ def launch_list(path):
 os.makedirs(OUT, exist_ok=True)
 g = os.path.join(ROOT, "gpurun_out")
 res = {}
-for name in ("extend", "shade", "shadow"):
-    rep = os.path.join(g, f"prof_{name}.ncu-rep")
+for name in ("extend", "shade", "shadow", "shade_mis_config4", "traversal_config5"):
+    rep = os.path.join(g, f"prof_{name}_raw.csv")
+    if not os.path.exists(rep):
+        rep = os.path.join(g, f"prof_{name}.ncu-rep")
     if os.path.exists(rep):
         res[name] = summarise(rep, f"ncu_{name}")
         for r in res[name]:
