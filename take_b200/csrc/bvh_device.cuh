@@ -3,23 +3,22 @@
 // only for the tie-break ranks and the exact mode -- keeps being built on the host, in the background, see take_gpu.cu.)
 //
 // Any tree whose boxes conservatively contain their primitives gives the same closest hit (traverse.cuh), so the builder
-// is free to choose topology for speed.  It is PLOC (parallel locally-ordered clustering, Meister & Bittner 2018), a
-// bottom-up agglomerative build whose trees are close to full-sweep SAH quality:
-//   1. k_prim_boxes      conservative FP32 box per primitive (FP64 bounds rounded outward + one ulp, like the host's
-//                        round_down / round_up), centroid bounds and max |coordinate| by warp-reduced atomics
-//   2. k_morton          63-bit Morton code of each centroid; cub radix sort of (code, primitive)
-//   3. PLOC rounds       every cluster looks at its R neighbours on either side in Morton order and picks the one whose
-//                        union has the smallest surface area (total order on (area, lower index, higher index), so the
-//                        globally best pair is always mutual and every round merges at least one pair); mutual pairs
-//                        merge into a new node; the survivors are compacted in order.  Node ids and positions come from
-//                        prefix sums, not atomics: the tree's memory layout is the same on every run.
-//                        While merging, each node gets its SAH cost with the host builder's constants (node visit 1,
-//                        leaf test 1.2) and subtrees of up to `max_leaf` primitives that are cheaper as a leaf are marked.
-//   4. wide collapse     breadth-first from the root: a binary node's two children are opened (largest surface area first)
-//                        until there are four -- the same rule as the host's WidePolicy -- leaf slots are numbered in
-//                        depth-first order on the way, 128-byte WideNodes are written level by level.
-//   5. k_leaf_records    the 96-byte FP64 leaf records in leaf order (rank field filled in later by k_patch_ranks).
-// All of it is a few milliseconds for a million primitives; the kernels are simple streaming / gather passes.
+// is free to choose topology; what it must keep is traversal speed.  It is therefore the SAME algorithm as the host builder
+// (32-bin SAH over centroids on all three axes, node visit 1, leaf test 1.2, leaves of up to max_leaf primitives when
+// cheaper) run level by level on the device.  (A first version clustered bottom-up -- PLOC over Morton-sorted primitives --
+// and built in 23 ms, but its trees cost 29 % more box tests per ray on config 2: measured, dropped.)
+//   1. k_prim_boxes   conservative FP32 box per primitive (FP64 bounds rounded outward + one ulp, like the host's round_down /
+//                     round_up), scene bounds, centroid bounds and max |coordinate| by warp-reduced atomics
+//   2. SAH levels     one thread block per node with more than SMALL primitives: bin its range (shared-memory bins), three
+//                     threads sweep the three axes, the block partitions the range stably into the other buffer with block
+//                     scans while accumulating both children's box and centroid bounds -- two passes over the range, as on
+//                     the host.  Nodes of up to SMALL primitives are finished by ONE thread each (the host's sparse sweep,
+//                     in-place partition) in a final array.  Positions come from prefix sums and min / max / integer
+//                     atomics, so the tree and the leaf order are the same on every run.
+//   3. wide collapse  breadth-first from the root: a binary node's two children are opened (largest surface area first)
+//                     until there are four -- the same rule as the host's WidePolicy -- 128-byte WideNodes are written
+//                     level by level.  A node's leaf slots are its range of the final primitive order.
+//   4. k_leaf_records the 96-byte FP64 leaf records in leaf order (rank field filled in later by k_patch_ranks).
 #pragma once
 #include <cub/cub.cuh>
 
@@ -28,16 +27,15 @@
 namespace take {
 namespace devbuild {
 
-#ifndef TAKE_PLOC_RADIUS
-#define TAKE_PLOC_RADIUS 16
-#endif
 #define TAKE_DB_BLOCK 256
+#define TAKE_SAH_BINS 32
+#define TAKE_SAH_SMALL 16   // ranges up to this size are finished by one thread (SahBuilder::SMALL on the host)
 
-struct BNode {          // binary node of the PLOC tree (leaves: nodes [0, n) in Morton order; inner nodes follow)
-    float4 lo, hi;      // conservative FP32 box; lo.w = surface half-area, hi.w = SAH cost of the subtree
-    int32_t left, right;  // children (inner) or -1, primitive id (single-primitive leaf)
+struct BNode {          // binary node of the SAH tree
+    float4 lo, hi;      // conservative FP32 box; lo.w = surface half-area
+    int32_t left, right;  // children, or -1 while the node is a leaf
     int32_t count;      // primitives below
-    int32_t leaf;       // 1: the whole subtree is one leaf of `count` primitives
+    int32_t leaf;       // 1: a leaf of `count` primitives (its slots are its range of the final primitive order)
 };
 static_assert(sizeof(BNode) == 48, "BNode");
 
@@ -51,24 +49,32 @@ __device__ __forceinline__ float next_up(float f) { return -next_down(-f); }
 // the host's round_down(v, 0) / round_up(v, 0) (bvh_build.cpp): outward rounding, then one more ulp
 __device__ __forceinline__ float box_lo(double v) { return next_down(__double2float_rd(v)); }
 __device__ __forceinline__ float box_hi(double v) { return next_up(__double2float_ru(v)); }
-__device__ __forceinline__ float half_area(float4 lo, float4 hi) {
-    const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+__device__ __forceinline__ float half_area3(const float *lo, const float *hi) {
+    const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    if (dx < 0.0f || dy < 0.0f || dz < 0.0f) return 0.0f;   // empty box
     return dx * dy + dy * dz + dz * dx;
 }
-// monotone float <-> uint maps for atomicMin / atomicMax on floats
+__device__ __forceinline__ float half_area(float4 lo, float4 hi) {
+    const float l[3] = {lo.x, lo.y, lo.z}, h[3] = {hi.x, hi.y, hi.z};
+    return half_area3(l, h);
+}
+// monotone float <-> uint maps for min / max on floats through integer atomics and redux
 __device__ __forceinline__ uint32_t f2ord(float f) { const uint32_t b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
 __device__ __forceinline__ float ord2f(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+#define TAKE_ORD_PLUS_INF 0xff800000u    // f2ord(+inf)
+#define TAKE_ORD_MINUS_INF 0x007fffffu   // f2ord(-inf)
 
-struct Globals {        // zero / identity initialised by the host before k_prim_boxes
-    uint32_t cmin[3], cmax[3];          // centroid bounds (ordered-uint encoding)
+struct Globals {        // identity-initialised by the host before k_prim_boxes
+    uint32_t bmin[3], bmax[3];          // scene bounds (ordered-uint encoding)
+    uint32_t cmin[3], cmax[3];          // centroid bounds
     unsigned long long abs_max_bits;    // max |coordinate| over the FP64 primitive bounds (bits of a non-negative double)
-    uint32_t pad;
+    int32_t node_count, big_count, small_count, pad;   // allocation counters of the SAH levels
 };
 
 // ---- 1. primitive boxes -------------------------------------------------------------------------------------------
 __global__ void k_prim_boxes(DevScene sc, int64_t n, float4 *plo, float4 *phi, Globals *g) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    float c[3] = {INFINITY, INFINITY, INFINITY};
+    float c[3] = {INFINITY, INFINITY, INFINITY}, bl[3] = {INFINITY, INFINITY, INFINITY}, bh[3] = {-INFINITY, -INFINITY, -INFINITY};
     double amax = 0.0;
     const bool valid = i < n;
     if (valid) {
@@ -81,146 +87,329 @@ __global__ void k_prim_boxes(DevScene sc, int64_t n, float4 *plo, float4 *phi, G
             const double *p0 = sc.positions + 3 * (int64_t)id[0], *p1 = sc.positions + 3 * (int64_t)id[1], *p2 = sc.positions + 3 * (int64_t)id[2];
             for (int a = 0; a < 3; ++a) { lo[a] = fmin(fmin(p0[a], p1[a]), p2[a]); hi[a] = fmax(fmax(p0[a], p1[a]), p2[a]); }
         }
-        const float4 l = make_float4(box_lo(lo[0]), box_lo(lo[1]), box_lo(lo[2]), 0.0f);
+        const float4 l = make_float4(box_lo(lo[0]), box_lo(lo[1]), box_lo(lo[2]), __int_as_float((int32_t)i));   // .w: the primitive id
         const float4 h = make_float4(box_hi(hi[0]), box_hi(hi[1]), box_hi(hi[2]), 0.0f);
         plo[i] = l; phi[i] = h;
         c[0] = 0.5f * (l.x + h.x); c[1] = 0.5f * (l.y + h.y); c[2] = 0.5f * (l.z + h.z);
+        bl[0] = l.x; bl[1] = l.y; bl[2] = l.z; bh[0] = h.x; bh[1] = h.y; bh[2] = h.z;
         for (int a = 0; a < 3; ++a) amax = fmax(amax, fmax(fabs(lo[a]), fabs(hi[a])));
     }
-    // warp reduce, one atomic per warp and quantity
+    // warp reduce (redux on the ordered-uint images), one atomic per warp and quantity
+    const bool lane0 = (threadIdx.x & 31) == 0;
     for (int a = 0; a < 3; ++a) {
-        float mn = valid ? c[a] : INFINITY, mx = valid ? c[a] : -INFINITY;
-        for (int o = 16; o > 0; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
-        if ((threadIdx.x & 31) == 0 && mn <= mx) { atomicMin(&g->cmin[a], f2ord(mn)); atomicMax(&g->cmax[a], f2ord(mx)); }
+        const uint32_t cmn = __reduce_min_sync(0xffffffffu, valid ? f2ord(c[a]) : 0xffffffffu);
+        const uint32_t cmx = __reduce_max_sync(0xffffffffu, valid ? f2ord(c[a]) : 0u);
+        const uint32_t bmn = __reduce_min_sync(0xffffffffu, valid ? f2ord(bl[a]) : 0xffffffffu);
+        const uint32_t bmx = __reduce_max_sync(0xffffffffu, valid ? f2ord(bh[a]) : 0u);
+        if (lane0 && cmn <= cmx) {
+            atomicMin(&g->cmin[a], cmn); atomicMax(&g->cmax[a], cmx);
+            atomicMin(&g->bmin[a], bmn); atomicMax(&g->bmax[a], bmx);
+        }
     }
     for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     if ((threadIdx.x & 31) == 0) atomicMax(&g->abs_max_bits, (unsigned long long)__double_as_longlong(amax));
 }
 
-// ---- 2. Morton codes ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t spread21(uint32_t v) {   // 21 bits -> every third bit of 63
-    uint64_t x = v & 0x1fffffu;
-    x = (x | x << 32) & 0x1f00000000ffffull;
-    x = (x | x << 16) & 0x1f0000ff0000ffull;
-    x = (x | x << 8) & 0x100f00f00f00f00full;
-    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
-    x = (x | x << 2) & 0x1249249249249249ull;
-    return x;
-}
-__global__ void k_morton(int64_t n, const float4 *plo, const float4 *phi, const Globals *g, uint64_t *keys, uint32_t *vals) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 l = plo[i], h = phi[i];
-    const float c[3] = {0.5f * (l.x + h.x), 0.5f * (l.y + h.y), 0.5f * (l.z + h.z)};
-    uint32_t q[3];
-    for (int a = 0; a < 3; ++a) {
-        const float mn = ord2f(g->cmin[a]), mx = ord2f(g->cmax[a]);
-        const float ext = mx - mn;
-        const float t = ext > 0.0f ? (c[a] - mn) / ext : 0.0f;
-        q[a] = (uint32_t)fminf(fmaxf(t * 2097152.0f, 0.0f), 2097151.0f);
-    }
-    keys[i] = (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
-    vals[i] = (uint32_t)i;
-}
+// ---- 2. SAH levels --------------------------------------------------------------------------------------------------
+struct SItem {          // a node whose range still has to be split
+    int32_t node, lo, hi, pad;
+    float bl[3], bh[3], cl[3], ch[3];   // box of the primitives, box of their centroids
+};
+static_assert(sizeof(SItem) == 64, "SItem");
 
-// leaves of the PLOC tree: node i = the i-th primitive in Morton order
-__global__ void k_init_leaves(int64_t n, const uint32_t *sorted_prim, const float4 *plo, const float4 *phi, BNode *nodes, int32_t *cluster,
-                              float c_isect) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t p = sorted_prim[i];
+__device__ __forceinline__ int bin_of(float c, float cb_lo, float scale) {
+    const int k = (int)((c - cb_lo) * scale);
+    return min(max(k, 0), TAKE_SAH_BINS - 1);
+}
+__device__ __forceinline__ float centroid(float l, float h) { return 0.5f * (l + h); }
+
+__device__ __forceinline__ void write_node(BNode *nodes, int32_t id, const float *bl, const float *bh, int32_t count) {
     BNode b;
-    b.lo = plo[p]; b.hi = phi[p];
-    b.lo.w = half_area(b.lo, b.hi);
-    b.hi.w = c_isect;
-    b.left = -1; b.right = (int32_t)p; b.count = 1; b.leaf = 1;
-    nodes[i] = b;
-    cluster[i] = (int32_t)i;
+    b.lo = make_float4(bl[0], bl[1], bl[2], half_area3(bl, bh));
+    b.hi = make_float4(bh[0], bh[1], bh[2], 0.0f);
+    b.left = b.right = -1;
+    b.count = count;
+    b.leaf = count == 1 ? 1 : 0;
+    nodes[id] = b;
 }
 
-// ---- 3. PLOC round ------------------------------------------------------------------------------------------------
-// nearest neighbour of every cluster within +-R positions: smallest surface area of the union, ties by (lower, higher) index
-template <int R>
-__global__ void k_ploc_nn(int32_t m, const int32_t *cluster, const BNode *nodes, int32_t *nn) {
-    __shared__ float4 slo[TAKE_DB_BLOCK + 2 * R], shi[TAKE_DB_BLOCK + 2 * R];
-    const int32_t base = (int32_t)blockIdx.x * TAKE_DB_BLOCK - R;
-    for (int t = threadIdx.x; t < TAKE_DB_BLOCK + 2 * R; t += TAKE_DB_BLOCK) {
-        const int32_t j = base + t;
-        if (j >= 0 && j < m) {
-            const BNode &b = nodes[cluster[j]];
-            slo[t] = b.lo; shi[t] = b.hi;
+// root item from the global bounds
+__global__ void k_sah_root(int32_t n, Globals *g, BNode *nodes, SItem *big, SItem *small) {
+    if (blockIdx.x || threadIdx.x) return;
+    SItem it;
+    it.node = 0; it.lo = 0; it.hi = n; it.pad = 0;
+    for (int a = 0; a < 3; ++a) {
+        it.bl[a] = ord2f(g->bmin[a]); it.bh[a] = ord2f(g->bmax[a]);
+        it.cl[a] = ord2f(g->cmin[a]); it.ch[a] = ord2f(g->cmax[a]);
+    }
+    write_node(nodes, 0, it.bl, it.bh, n);
+    g->node_count = 1;
+    g->big_count = 0; g->small_count = 0;
+    if (n > TAKE_SAH_SMALL) { big[0] = it; g->big_count = 1; }
+    else { small[0] = it; g->small_count = 1; }
+}
+
+// One block per node: bin, sweep, partition (cur -> nxt), emit the children.
+__global__ void __launch_bounds__(TAKE_DB_BLOCK) k_sah_split(const SItem *items, const float4 *cur_lo, const float4 *cur_hi, float4 *nxt_lo,
+                                                             float4 *nxt_hi, BNode *nodes, Globals *g, SItem *next_big, SItem *next_small) {
+    __shared__ uint32_t s_min[3][TAKE_SAH_BINS][3], s_max[3][TAKE_SAH_BINS][3], s_cnt[3][TAKE_SAH_BINS];
+    __shared__ float s_cost[3];
+    __shared__ int s_bin[3], s_nleft[3];
+    __shared__ uint32_t s_child[2][12];   // per side: box min xyz, box max xyz, centroid min xyz, centroid max xyz (ordered uint)
+    __shared__ uint32_t s_wl[TAKE_DB_BLOCK / 32], s_wv[TAKE_DB_BLOCK / 32];
+    __shared__ int s_axis, s_best_bin, s_nl;
+    const SItem it = items[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int32_t lo = it.lo, hi = it.hi, m = hi - lo;
+    float scale3[3];
+    bool axis_ok[3];
+    for (int x = 0; x < 3; ++x) {
+        const float ext = it.ch[x] - it.cl[x];
+        axis_ok[x] = ext > 0.0f;
+        scale3[x] = axis_ok[x] ? (float)TAKE_SAH_BINS / ext : 0.0f;
+    }
+    for (int t = tid; t < 3 * TAKE_SAH_BINS; t += TAKE_DB_BLOCK) {
+        const int x = t / TAKE_SAH_BINS, b = t % TAKE_SAH_BINS;
+        for (int a = 0; a < 3; ++a) { s_min[x][b][a] = 0xffffffffu; s_max[x][b][a] = 0u; }
+        s_cnt[x][b] = 0u;
+    }
+    if (tid < 24) s_child[tid / 12][tid % 12] = ((tid % 12) % 6 < 3) ? 0xffffffffu : 0u;
+    __syncthreads();
+    // pass 1: bin all three axes
+    for (int32_t i = lo + tid; i < hi; i += TAKE_DB_BLOCK) {
+        const float4 l = cur_lo[i], h = cur_hi[i];
+        const float bl[3] = {l.x, l.y, l.z}, bh[3] = {h.x, h.y, h.z};
+        for (int x = 0; x < 3; ++x) {
+            if (!axis_ok[x]) continue;
+            const int k = bin_of(centroid(bl[x], bh[x]), it.cl[x], scale3[x]);
+            atomicAdd(&s_cnt[x][k], 1u);
+            for (int a = 0; a < 3; ++a) { atomicMin(&s_min[x][k][a], f2ord(bl[a])); atomicMax(&s_max[x][k][a], f2ord(bh[a])); }
         }
     }
     __syncthreads();
-    const int32_t i = (int32_t)blockIdx.x * TAKE_DB_BLOCK + threadIdx.x;
-    if (i >= m) return;
-    const float4 lo = slo[threadIdx.x + R], hi = shi[threadIdx.x + R];
-    float best = INFINITY;
-    int32_t best_j = -1;
-    // ascending j with strict '<' picks the lowest j among equal areas for j > i; for j < i the pair key is (area, j, i), and
-    // ascending j again prefers the smaller lower index: the same total order from both ends of a pair
-    for (int d = -R; d <= R; ++d) {
-        const int32_t j = i + d;
-        if (d == 0 || j < 0 || j >= m) continue;
-        const float4 l2 = slo[threadIdx.x + R + d], h2 = shi[threadIdx.x + R + d];
-        const float4 ul = make_float4(fminf(lo.x, l2.x), fminf(lo.y, l2.y), fminf(lo.z, l2.z), 0.0f);
-        const float4 uh = make_float4(fmaxf(hi.x, h2.x), fmaxf(hi.y, h2.y), fmaxf(hi.z, h2.z), 0.0f);
-        const float a = half_area(ul, uh);
-        if (a < best) { best = a; best_j = j; }
+    // sweep: one thread per axis (split between bin b and b+1; the first minimum wins, like the host's ascending loops)
+    if (tid < 3) {
+        const int x = tid;
+        float best = INFINITY;
+        int best_bin = -1, nleft = 0;
+        if (axis_ok[x]) {
+            float right_area[TAKE_SAH_BINS];
+            uint32_t right_cnt[TAKE_SAH_BINS];
+            float al[3] = {INFINITY, INFINITY, INFINITY}, ah[3] = {-INFINITY, -INFINITY, -INFINITY};
+            uint32_t cnt = 0;
+            for (int b = TAKE_SAH_BINS - 1; b > 0; --b) {
+                cnt += s_cnt[x][b];
+                if (s_cnt[x][b]) for (int a = 0; a < 3; ++a) { al[a] = fminf(al[a], ord2f(s_min[x][b][a])); ah[a] = fmaxf(ah[a], ord2f(s_max[x][b][a])); }
+                right_area[b] = half_area3(al, ah);
+                right_cnt[b] = cnt;
+            }
+            for (int a = 0; a < 3; ++a) { al[a] = INFINITY; ah[a] = -INFINITY; }
+            cnt = 0;
+            for (int b = 0; b < TAKE_SAH_BINS - 1; ++b) {
+                cnt += s_cnt[x][b];
+                if (s_cnt[x][b]) for (int a = 0; a < 3; ++a) { al[a] = fminf(al[a], ord2f(s_min[x][b][a])); ah[a] = fmaxf(ah[a], ord2f(s_max[x][b][a])); }
+                if (cnt == 0 || right_cnt[b + 1] == 0) continue;
+                const float cost = half_area3(al, ah) * (float)cnt + right_area[b + 1] * (float)right_cnt[b + 1];
+                if (cost < best) { best = cost; best_bin = b; nleft = (int)cnt; }
+            }
+        }
+        s_cost[x] = best; s_bin[x] = best_bin; s_nleft[x] = nleft;
     }
-    nn[i] = best_j;
-}
-
-// fallback pairing (2k, 2k+1): used for a round in which no union area was finite
-__global__ void k_ploc_pairs(int32_t m, int32_t *nn) {
-    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    const int32_t j = i ^ 1;
-    nn[i] = j < m ? j : -1;
-}
-
-// flags of a round, packed for one prefix sum: low word = the cluster survives (is not the higher half of a merging pair),
-// high word = the cluster is the lower half of a merging pair (a new node is created for it)
-__global__ void k_ploc_flags(int32_t m, const int32_t *nn, uint64_t *flags) {
-    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    const int32_t j = nn[i];
-    const bool mutual = j >= 0 && nn[j] == i;
-    const uint64_t survives = (mutual && j < i) ? 0ull : 1ull;
-    const uint64_t creates = (mutual && i < j) ? 1ull : 0ull;
-    flags[i] = survives | (creates << 32);
-}
-
-__global__ void k_ploc_merge(int32_t m, const int32_t *nn, const uint64_t *flags, const uint64_t *scan, const int32_t *cluster_in,
-                             int32_t *cluster_out, BNode *nodes, int32_t next_node, int max_leaf, float c_trav, float c_isect) {
-    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    const uint64_t f = flags[i], s = scan[i];
-    if (!(f & 1ull)) return;                     // merged away into its partner
-    const int32_t pos = (int32_t)(s & 0xffffffffull);
-    int32_t id = cluster_in[i];
-    if (f >> 32) {                               // lower half of a mutual pair: create the parent
-        const int32_t a = id, b = cluster_in[nn[i]];
-        const BNode na = nodes[a], nb = nodes[b];
-        BNode p;
-        p.lo = make_float4(fminf(na.lo.x, nb.lo.x), fminf(na.lo.y, nb.lo.y), fminf(na.lo.z, nb.lo.z), 0.0f);
-        p.hi = make_float4(fmaxf(na.hi.x, nb.hi.x), fmaxf(na.hi.y, nb.hi.y), fmaxf(na.hi.z, nb.hi.z), 0.0f);
-        const float area = half_area(p.lo, p.hi);
-        p.lo.w = area;
-        p.left = a; p.right = b;
-        p.count = na.count + nb.count;
-        // SAH with the host builder's constants (bvh_build.cpp: c_trav 1, c_isect 1.2)
-        const float inner = c_trav + (area > 0.0f ? (na.lo.w * na.hi.w + nb.lo.w * nb.hi.w) / area : na.hi.w + nb.hi.w);
-        const float as_leaf = c_isect * (float)p.count;
-        p.leaf = (p.count <= max_leaf && as_leaf <= inner) ? 1 : 0;
-        p.hi.w = p.leaf ? as_leaf : inner;
-        id = next_node + (int32_t)(s >> 32);
-        nodes[id] = p;
+    __syncthreads();
+    if (tid == 0) {
+        int axis = -1;
+        float best = INFINITY;
+        for (int x = 0; x < 3; ++x) if (s_bin[x] >= 0 && s_cost[x] < best) { best = s_cost[x]; axis = x; }
+        s_axis = axis;
+        s_best_bin = axis >= 0 ? s_bin[axis] : -1;
+        s_nl = axis >= 0 ? s_nleft[axis] : m / 2;   // all centroids coincide: split the range in half, order kept
     }
-    cluster_out[pos] = id;
+    __syncthreads();
+    const int axis = s_axis, best_bin = s_best_bin;
+    const int32_t nl = s_nl;
+    // pass 2: stable partition into the other buffer, accumulating the bounds of both sides
+    int32_t lrun = 0, rrun = 0;
+    for (int32_t base = lo; base < hi; base += TAKE_DB_BLOCK) {
+        const int32_t i = base + tid;
+        const bool valid = i < hi;
+        float4 l = make_float4(0, 0, 0, 0), h = l;
+        bool left = false;
+        if (valid) {
+            l = cur_lo[i]; h = cur_hi[i];
+            if (axis >= 0) {
+                const float bl = axis == 0 ? l.x : axis == 1 ? l.y : l.z, bh = axis == 0 ? h.x : axis == 1 ? h.y : h.z;
+                left = bin_of(centroid(bl, bh), it.cl[axis], scale3[axis]) <= best_bin;
+            } else {
+                left = (i - lo) < nl;
+            }
+        }
+        const unsigned wmask = __ballot_sync(0xffffffffu, left), vmask = __ballot_sync(0xffffffffu, valid);
+        if (lane == 0) { s_wl[warp] = __popc(wmask); s_wv[warp] = __popc(vmask); }
+        __syncthreads();
+        int32_t lpre = 0, vpre = 0, ltot = 0, vtot = 0;
+        for (int w = 0; w < TAKE_DB_BLOCK / 32; ++w) {
+            if (w < warp) { lpre += s_wl[w]; vpre += s_wv[w]; }
+            ltot += s_wl[w]; vtot += s_wv[w];
+        }
+        const unsigned lt = (1u << lane) - 1u;
+        const int32_t lrank = lpre + __popc(wmask & lt), vrank = vpre + __popc(vmask & lt);
+        if (valid) {
+            const int32_t pos = left ? lo + lrun + lrank : lo + nl + rrun + (vrank - lrank);
+            nxt_lo[pos] = l; nxt_hi[pos] = h;
+        }
+        // children's bounds: warp redux per side and quantity, then one shared atomic per warp
+        const float q[12] = {l.x, l.y, l.z, h.x, h.y, h.z, centroid(l.x, h.x), centroid(l.y, h.y), centroid(l.z, h.z),
+                             centroid(l.x, h.x), centroid(l.y, h.y), centroid(l.z, h.z)};
+        for (int side = 0; side < 2; ++side) {
+            const bool mine = valid && (left == (side == 0));
+            if (!__any_sync(0xffffffffu, mine)) continue;
+            for (int k = 0; k < 12; ++k) {
+                const bool is_min = (k % 6) < 3;
+                const uint32_t v = mine ? f2ord(q[k]) : (is_min ? 0xffffffffu : 0u);
+                const uint32_t r = is_min ? __reduce_min_sync(0xffffffffu, v) : __reduce_max_sync(0xffffffffu, v);
+                if (lane == 0) { if (is_min) atomicMin(&s_child[side][k], r); else atomicMax(&s_child[side][k], r); }
+            }
+        }
+        lrun += ltot; rrun += vtot - ltot;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const int32_t first = atomicAdd(&g->node_count, 2);
+        nodes[it.node].left = first;
+        nodes[it.node].right = first + 1;
+        for (int side = 0; side < 2; ++side) {
+            SItem c;
+            c.node = first + side; c.pad = 0;
+            c.lo = side == 0 ? lo : lo + nl;
+            c.hi = side == 0 ? lo + nl : hi;
+            for (int a = 0; a < 3; ++a) {
+                c.bl[a] = ord2f(s_child[side][a]); c.bh[a] = ord2f(s_child[side][3 + a]);
+                c.cl[a] = ord2f(s_child[side][6 + a]); c.ch[a] = ord2f(s_child[side][9 + a]);
+            }
+            const int32_t cm = c.hi - c.lo;
+            write_node(nodes, c.node, c.bl, c.bh, cm);
+            if (cm > TAKE_SAH_SMALL) next_big[atomicAdd(&g->big_count, 1)] = c;
+            else next_small[atomicAdd(&g->small_count, 1)] = c;
+        }
+    }
 }
 
-// ---- 4. wide collapse (breadth first) -------------------------------------------------------------------------------
+// One thread per node of up to SMALL primitives: copy the range into the final array and finish the subtree there (the
+// host's sparse sweep for small ranges, in-place partition from both ends).
+struct STask { int32_t node, lo, hi; float bl[3], bh[3], cl[3], ch[3]; };
+
+__global__ void k_sah_small(const SItem *items, int32_t n_items, const float4 *cur_lo, const float4 *cur_hi, float4 *fin_lo, float4 *fin_hi,
+                            BNode *nodes, Globals *g, int max_leaf, float c_trav, float c_isect) {
+    const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_items) return;
+    const SItem it = items[t];
+    for (int32_t i = it.lo; i < it.hi; ++i) { fin_lo[i] = cur_lo[i]; fin_hi[i] = cur_hi[i]; }
+    STask stack[TAKE_SAH_SMALL + 2];
+    int sp = 0;
+    {
+        STask r;
+        r.node = it.node; r.lo = it.lo; r.hi = it.hi;
+        for (int a = 0; a < 3; ++a) { r.bl[a] = it.bl[a]; r.bh[a] = it.bh[a]; r.cl[a] = it.cl[a]; r.ch[a] = it.ch[a]; }
+        stack[sp++] = r;
+    }
+    while (sp > 0) {
+        const STask k = stack[--sp];
+        const int32_t lo = k.lo, hi = k.hi, m = hi - lo;
+        if (m <= 1) { nodes[k.node].leaf = 1; continue; }
+        float best_cost = INFINITY;
+        int best_axis = -1, best_bin = -1;
+        float scale3[3];
+        for (int x = 0; x < 3; ++x) {
+            const float ext = k.ch[x] - k.cl[x];
+            scale3[x] = ext > 0.0f ? (float)TAKE_SAH_BINS / ext : 0.0f;
+            if (!(ext > 0.0f)) continue;
+            int key[TAKE_SAH_SMALL], ord[TAKE_SAH_SMALL];
+            for (int i = 0; i < m; ++i) {
+                const float4 l = fin_lo[lo + i], h = fin_hi[lo + i];
+                const float bl = x == 0 ? l.x : x == 1 ? l.y : l.z, bh = x == 0 ? h.x : x == 1 ? h.y : h.z;
+                key[i] = bin_of(centroid(bl, bh), k.cl[x], scale3[x]);
+                int j = i;
+                while (j > 0 && key[ord[j - 1]] > key[i]) { ord[j] = ord[j - 1]; --j; }
+                ord[j] = i;
+            }
+            float right_area[TAKE_SAH_SMALL + 1];
+            float al[3] = {INFINITY, INFINITY, INFINITY}, ah[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (int i = m - 1; i >= 0; --i) {
+                const float4 l = fin_lo[lo + ord[i]], h = fin_hi[lo + ord[i]];
+                al[0] = fminf(al[0], l.x); al[1] = fminf(al[1], l.y); al[2] = fminf(al[2], l.z);
+                ah[0] = fmaxf(ah[0], h.x); ah[1] = fmaxf(ah[1], h.y); ah[2] = fmaxf(ah[2], h.z);
+                right_area[i] = half_area3(al, ah);
+            }
+            for (int a = 0; a < 3; ++a) { al[a] = INFINITY; ah[a] = -INFINITY; }
+            for (int i = 0; i < m - 1; ++i) {
+                const float4 l = fin_lo[lo + ord[i]], h = fin_hi[lo + ord[i]];
+                al[0] = fminf(al[0], l.x); al[1] = fminf(al[1], l.y); al[2] = fminf(al[2], l.z);
+                ah[0] = fmaxf(ah[0], h.x); ah[1] = fmaxf(ah[1], h.y); ah[2] = fmaxf(ah[2], h.z);
+                if (key[ord[i + 1]] == key[ord[i]]) continue;   // inside a bin group: not a split position
+                const float cost = half_area3(al, ah) * (float)(i + 1) + right_area[i + 1] * (float)(m - i - 1);
+                if (cost < best_cost) { best_cost = cost; best_axis = x; best_bin = key[ord[i]]; }
+            }
+        }
+        int32_t mid = -1;
+        float cl_[2][3], ch_[2][3], bl_[2][3], bh_[2][3];
+        for (int s2 = 0; s2 < 2; ++s2) for (int a = 0; a < 3; ++a) { cl_[s2][a] = bl_[s2][a] = INFINITY; ch_[s2][a] = bh_[s2][a] = -INFINITY; }
+        auto grow = [&](int side, float4 l, float4 h) {
+            const float pl[3] = {l.x, l.y, l.z}, ph[3] = {h.x, h.y, h.z};
+            for (int a = 0; a < 3; ++a) {
+                bl_[side][a] = fminf(bl_[side][a], pl[a]); bh_[side][a] = fmaxf(bh_[side][a], ph[a]);
+                const float c = centroid(pl[a], ph[a]);
+                cl_[side][a] = fminf(cl_[side][a], c); ch_[side][a] = fmaxf(ch_[side][a], c);
+            }
+        };
+        if (best_axis >= 0) {
+            const float parent_area = half_area3(k.bl, k.bh);
+            const float split_cost = c_trav + c_isect * best_cost / (parent_area > 0.0f ? parent_area : 1.0f);
+            const float leaf_cost = c_isect * (float)m;
+            if (m <= max_leaf && leaf_cost <= split_cost) { nodes[k.node].leaf = 1; continue; }
+            auto goes_left = [&](int32_t i) {
+                const float4 l = fin_lo[i], h = fin_hi[i];
+                const float bl = best_axis == 0 ? l.x : best_axis == 1 ? l.y : l.z, bh = best_axis == 0 ? h.x : best_axis == 1 ? h.y : h.z;
+                return bin_of(centroid(bl, bh), k.cl[best_axis], scale3[best_axis]) <= best_bin;
+            };
+            int32_t i = lo, j = hi - 1;
+            for (;;) {
+                while (i <= j && goes_left(i)) ++i;
+                while (i <= j && !goes_left(j)) --j;
+                if (i >= j) break;
+                const float4 a0 = fin_lo[i], a1 = fin_hi[i];
+                fin_lo[i] = fin_lo[j]; fin_hi[i] = fin_hi[j];
+                fin_lo[j] = a0; fin_hi[j] = a1;
+                ++i; --j;
+            }
+            mid = i;
+        }
+        if (mid <= lo || mid >= hi) {
+            if (m <= max_leaf) { nodes[k.node].leaf = 1; continue; }
+            mid = lo + m / 2;
+        }
+        for (int32_t i = lo; i < hi; ++i) grow(i < mid ? 0 : 1, fin_lo[i], fin_hi[i]);
+        const int32_t first = atomicAdd(&g->node_count, 2);
+        nodes[k.node].left = first;
+        nodes[k.node].right = first + 1;
+        for (int side = 1; side >= 0; --side) {    // (left child is processed first: popped last-in first-out)
+            STask c;
+            c.node = first + side;
+            c.lo = side == 0 ? lo : mid;
+            c.hi = side == 0 ? mid : hi;
+            for (int a = 0; a < 3; ++a) { c.bl[a] = bl_[side][a]; c.bh[a] = bh_[side][a]; c.cl[a] = cl_[side][a]; c.ch[a] = ch_[side][a]; }
+            write_node(nodes, c.node, c.bl, c.bh, c.hi - c.lo);
+            if (c.hi - c.lo > 1) stack[sp++] = c;
+        }
+    }
+}
+
+// primitive id of every leaf slot (the final order of the SAH partitions)
+__global__ void k_leaf_prims(int64_t n, const float4 *fin_lo, int32_t *leaf_prims) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) leaf_prims[i] = __float_as_int(fin_lo[i].w);
+}
+
+// ---- 3. wide collapse (breadth first) -------------------------------------------------------------------------------
 struct WorkItem {
     int32_t bnode;   // inner binary node this wide node stands for
     int32_t wide;    // index of the wide node to fill
@@ -267,23 +456,9 @@ __global__ void k_wide_kids(int32_t n_items, const WorkItem *items, const BNode 
     inner_count[t] = (uint32_t)ni;
 }
 
-// primitives of a collapsed leaf subtree (<= 8), written in depth-first order
-__device__ inline void emit_leaf_prims(const BNode *nodes, int32_t root, int32_t first, int32_t *leaf_prims) {
-    int32_t stack[16];
-    int sp = 0;
-    stack[sp++] = root;
-    int32_t o = first;
-    while (sp > 0) {
-        const BNode &b = nodes[stack[--sp]];
-        if (b.left < 0) { leaf_prims[o++] = b.right; continue; }
-        stack[sp++] = b.right;
-        stack[sp++] = b.left;
-    }
-}
-
-// pass B: write the wide node, the leaf slots of its leaf children, and the work items of its inner children
+// pass B: write the wide node and the work items of its inner children
 __global__ void k_wide_emit(int32_t n_items, const WorkItem *items, const Kids *kids, const uint32_t *inner_scan, const BNode *nodes,
-                            WideNode *wide, int32_t next_wide, WorkItem *next_items, int32_t *leaf_prims) {
+                            WideNode *wide, int32_t next_wide, WorkItem *next_items) {
     const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_items) return;
     const WorkItem it = items[t];
@@ -303,7 +478,6 @@ __global__ void k_wide_emit(int32_t n_items, const WorkItem *items, const Kids *
         if (is_leaf_node(c)) {
             w.child[q] = ~(int32_t)(((uint32_t)k.first[q] << 3) | (uint32_t)(c.count - 1));
             w.count[q] = c.count;
-            emit_leaf_prims(nodes, k.node[q], k.first[q], leaf_prims);
         } else {
             const int32_t wi = next_wide + slot;
             w.child[q] = wi; w.count[q] = 0;
@@ -317,7 +491,7 @@ __global__ void k_wide_emit(int32_t n_items, const WorkItem *items, const Kids *
 }
 
 // the tree is a single leaf (or empty): a root whose only child is that leaf (bvh_build.cpp: WidePolicy::wrap_root)
-__global__ void k_wide_wrap_root(const BNode *nodes, int32_t root, int64_t n, WideNode *wide, int32_t *leaf_prims) {
+__global__ void k_wide_wrap_root(const BNode *nodes, int32_t root, int64_t n, WideNode *wide) {
     if (blockIdx.x || threadIdx.x) return;
     WideNode w;
     for (int q = 0; q < 4; ++q) {
@@ -331,12 +505,11 @@ __global__ void k_wide_wrap_root(const BNode *nodes, int32_t root, int64_t n, Wi
         w.hix[0] = c.hi.x; w.hiy[0] = c.hi.y; w.hiz[0] = c.hi.z;
         w.child[0] = ~(int32_t)(uint32_t)(c.count - 1);
         w.count[0] = c.count;
-        emit_leaf_prims(nodes, root, 0, leaf_prims);
     }
     wide[0] = w;
 }
 
-// ---- 5. leaf records ----------------------------------------------------------------------------------------------
+// ---- 4. leaf records ----------------------------------------------------------------------------------------------
 // v0 | (rank << 32 | prim) | e1 | radius | e2 | kind -- the layout host_build writes (take_gpu.cu), e1 / e2 with the same FP64
 // subtractions.  The rank (the reference's DFS order, for equal-t ties) is not known yet: k_patch_ranks fills it in.
 __global__ void k_leaf_records(DevScene sc, int64_t n, const int32_t *leaf_prims, double *tris) {

@@ -659,108 +659,108 @@ static int device_build_fast_tree(TakeScene *s, int max_leaf, double &abs_max) {
     cudaStream_t st = s->stream;
     const int64_t n = s->dev.num_prims;
     abs_max = 0;
+    s->sah_cost = 0;
     CU(s->leaf_prims.ensure(std::max<size_t>((size_t)n * 4, 16)));
     CU(s->tris.ensure(std::max<size_t>((size_t)n * 96, 32)));
-    DeviceBuffer wide_tmp, nodes, plo, phi, glob, keys, vals, cl_a, cl_b, nnb, flags, scan, items_a, items_b, kids, icount, iscan, cubtmp, tail;
+    DeviceBuffer wide_tmp, nodes, lo_a, hi_a, lo_b, hi_b, lo_f, hi_f, glob, big_a, big_b, small, items_a, items_b, kids, icount, iscan, cubtmp;
     CU(wide_tmp.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(WideNode)));
     if (n == 0) {
-        k_wide_wrap_root<<<1, 32, 0, st>>>(nullptr, 0, 0, wide_tmp.as<WideNode>(), s->leaf_prims.as<int32_t>());
+        k_wide_wrap_root<<<1, 32, 0, st>>>(nullptr, 0, 0, wide_tmp.as<WideNode>());
         CU(cudaGetLastError());
         CU(s->wide_nodes.ensure(sizeof(WideNode)));
         CU(cudaMemcpyAsync(s->wide_nodes.p, wide_tmp.p, sizeof(WideNode), cudaMemcpyDeviceToDevice, st));
         CU(cudaStreamSynchronize(st));
-        s->fast_depth = 1; s->num_fast_nodes = 1; s->sah_cost = 0;
+        s->fast_depth = 1; s->num_fast_nodes = 1;
         return TAKE_OK;
     }
     const unsigned gb = (unsigned)((n + TAKE_DB_BLOCK - 1) / TAKE_DB_BLOCK);
-    CU(plo.ensure((size_t)n * 16)); CU(phi.ensure((size_t)n * 16));
+    CU(lo_a.ensure((size_t)n * 16)); CU(hi_a.ensure((size_t)n * 16));
+    CU(lo_b.ensure((size_t)n * 16)); CU(hi_b.ensure((size_t)n * 16));
+    CU(lo_f.ensure((size_t)n * 16)); CU(hi_f.ensure((size_t)n * 16));
     CU(glob.ensure(sizeof(Globals)));
     {
         Globals g;
         memset(&g, 0, sizeof(g));
-        for (int a = 0; a < 3; ++a) { g.cmin[a] = 0xffffffffu; g.cmax[a] = 0u; }
+        for (int a = 0; a < 3; ++a) { g.cmin[a] = g.bmin[a] = 0xffffffffu; g.cmax[a] = g.bmax[a] = 0u; }
         CU(cudaMemcpyAsync(glob.p, &g, sizeof(g), cudaMemcpyHostToDevice, st));
     }
-    k_prim_boxes<<<gb, TAKE_DB_BLOCK, 0, st>>>(s->dev, n, plo.as<float4>(), phi.as<float4>(), glob.as<Globals>());
+    Globals *g = glob.as<Globals>();
+    k_prim_boxes<<<gb, TAKE_DB_BLOCK, 0, st>>>(s->dev, n, lo_a.as<float4>(), hi_a.as<float4>(), g);
     CU(cudaGetLastError());
-    // Morton order
-    CU(keys.ensure((size_t)n * 16)); CU(vals.ensure((size_t)n * 8));   // double buffers: [0, n) and [n, 2n)
-    k_morton<<<gb, TAKE_DB_BLOCK, 0, st>>>(n, plo.as<float4>(), phi.as<float4>(), glob.as<Globals>(), keys.as<uint64_t>(), vals.as<uint32_t>());
-    CU(cudaGetLastError());
-    cub::DoubleBuffer<uint64_t> dk(keys.as<uint64_t>(), keys.as<uint64_t>() + n);
-    cub::DoubleBuffer<uint32_t> dv(vals.as<uint32_t>(), vals.as<uint32_t>() + n);
-    size_t tmp_sort = 0, tmp_scan64 = 0, tmp_scan32 = 0;
-    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, dk, dv, (int)n, 0, 63, st));
-    CU(flags.ensure((size_t)n * 8)); CU(scan.ensure((size_t)n * 8));
-    CU(icount.ensure((size_t)n * 4)); CU(iscan.ensure((size_t)n * 4));
-    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan64, flags.as<uint64_t>(), scan.as<uint64_t>(), (int)n, st));
-    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan32, icount.as<uint32_t>(), iscan.as<uint32_t>(), (int)n, st));
-    size_t tmp_bytes = std::max(std::max(tmp_sort, tmp_scan64), std::max(tmp_scan32, (size_t)256));
-    CU(cubtmp.ensure(tmp_bytes));
-    CU(cub::DeviceRadixSort::SortPairs(cubtmp.p, tmp_bytes, dk, dv, (int)n, 0, 63, st));
-    // PLOC
-    CU(nodes.ensure((size_t)(2 * n) * sizeof(BNode)));
-    CU(cl_a.ensure((size_t)n * 4)); CU(cl_b.ensure((size_t)n * 4)); CU(nnb.ensure((size_t)n * 4));
+    // SAH levels
     const float c_trav = 1.0f, c_isect = 1.2f;   // SahBuilder's constants (bvh_build.cpp)
-    k_init_leaves<<<gb, TAKE_DB_BLOCK, 0, st>>>(n, dv.Current(), plo.as<float4>(), phi.as<float4>(), nodes.as<BNode>(), cl_a.as<int32_t>(), c_isect);
+    const size_t cap_big = (size_t)n / TAKE_SAH_SMALL + 4, cap_small = (size_t)n / (TAKE_SAH_SMALL / 2) + 8;
+    CU(nodes.ensure((size_t)(2 * n) * sizeof(BNode)));
+    CU(big_a.ensure(cap_big * sizeof(SItem))); CU(big_b.ensure(cap_big * sizeof(SItem))); CU(small.ensure(cap_small * sizeof(SItem)));
+    int32_t *h_cnt = nullptr;   // pinned: {node_count, big_count, small_count, pad} read back after every level
+    CU(cudaMallocHost((void **)&h_cnt, 8 * sizeof(int32_t)));
+    struct HostFree { void *p; ~HostFree() { cudaFreeHost(p); } } host_free{h_cnt};
+    k_sah_root<<<1, 32, 0, st>>>((int32_t)n, g, nodes.as<BNode>(), big_a.as<SItem>(), small.as<SItem>());
     CU(cudaGetLastError());
-    int32_t *cin = cl_a.as<int32_t>(), *cout = cl_b.as<int32_t>();
-    int32_t m = (int32_t)n, next_node = (int32_t)n;
-    uint64_t *h_tail = nullptr;
-    CU(cudaMallocHost((void **)&h_tail, 4 * sizeof(uint64_t)));
-    struct HostFree { void *p; ~HostFree() { cudaFreeHost(p); } } host_free{h_tail};
-    int rounds = 0;
-    bool pair_fallback = false;
-    while (m > 1) {
-        const unsigned g = (unsigned)((m + TAKE_DB_BLOCK - 1) / TAKE_DB_BLOCK);
-        if (!pair_fallback) k_ploc_nn<TAKE_PLOC_RADIUS><<<g, TAKE_DB_BLOCK, 0, st>>>(m, cin, nodes.as<BNode>(), nnb.as<int32_t>());
-        else k_ploc_pairs<<<g, TAKE_DB_BLOCK, 0, st>>>(m, nnb.as<int32_t>());
-        k_ploc_flags<<<g, TAKE_DB_BLOCK, 0, st>>>(m, nnb.as<int32_t>(), flags.as<uint64_t>());
-        CU(cub::DeviceScan::ExclusiveSum(cubtmp.p, tmp_bytes, flags.as<uint64_t>(), scan.as<uint64_t>(), m, st));
-        CU(cudaMemcpyAsync(h_tail, scan.as<uint64_t>() + (m - 1), 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(h_tail + 1, flags.as<uint64_t>() + (m - 1), 8, cudaMemcpyDeviceToHost, st));
-        k_ploc_merge<<<g, TAKE_DB_BLOCK, 0, st>>>(m, nnb.as<int32_t>(), flags.as<uint64_t>(), scan.as<uint64_t>(), cin, cout, nodes.as<BNode>(),
-                                                 next_node, max_leaf, c_trav, c_isect);
-        CU(cudaGetLastError());
+    float4 *cur_lo = lo_a.as<float4>(), *cur_hi = hi_a.as<float4>(), *nxt_lo = lo_b.as<float4>(), *nxt_hi = hi_b.as<float4>();
+    SItem *bcur = big_a.as<SItem>(), *bnext = big_b.as<SItem>();
+    auto read_counts = [&]() -> int {
+        CU(cudaMemcpyAsync(h_cnt, &g->node_count, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        const uint64_t tot = h_tail[0] + h_tail[1];
-        const int32_t survivors = (int32_t)(tot & 0xffffffffull), created = (int32_t)(tot >> 32);
-        if (survivors + created != m || created < 0) return fail(TAKE_E_CUDA, "device BVH build: inconsistent PLOC round");
-        // a round without a merge can only come from non-finite areas (coordinates near FLT_MAX): pair neighbours up instead
-        if (created == 0 && pair_fallback) return fail(TAKE_E_CUDA, "device BVH build: no progress");
-        pair_fallback = created == 0;
-        m = survivors;
-        next_node += created;
-        std::swap(cin, cout);
-        ++rounds;
+        return TAKE_OK;
+    };
+    if (int rc = read_counts()) return rc;
+    int levels = 0;
+    if (h_cnt[2] > 0) {   // the whole scene is one small node
+        k_sah_small<<<1, 32, 0, st>>>(small.as<SItem>(), h_cnt[2], cur_lo, cur_hi, lo_f.as<float4>(), hi_f.as<float4>(), nodes.as<BNode>(), g,
+                                      max_leaf, c_trav, c_isect);
+        CU(cudaGetLastError());
     }
-    const int32_t root = n > 1 ? next_node - 1 : 0;
-    if (n > 1 && next_node != (int32_t)(2 * n - 1)) return fail(TAKE_E_CUDA, "device BVH build: node count mismatch");
+    int32_t n_big = h_cnt[1];
+    while (n_big > 0) {
+        if ((size_t)n_big > cap_big) return fail(TAKE_E_CUDA, "device BVH build: work queue overflow");
+        CU(cudaMemsetAsync(&g->big_count, 0, 2 * sizeof(int32_t), st));
+        k_sah_split<<<(unsigned)n_big, TAKE_DB_BLOCK, 0, st>>>(bcur, cur_lo, cur_hi, nxt_lo, nxt_hi, nodes.as<BNode>(), g, bnext, small.as<SItem>());
+        CU(cudaGetLastError());
+        if (int rc = read_counts()) return rc;
+        const int32_t n_small = h_cnt[2];
+        if (h_cnt[1] < 0 || n_small < 0 || (size_t)n_small > cap_small || h_cnt[0] > 2 * n) return fail(TAKE_E_CUDA, "device BVH build: inconsistent level");
+        if (n_small > 0) {
+            k_sah_small<<<(unsigned)((n_small + 63) / 64), 64, 0, st>>>(small.as<SItem>(), n_small, nxt_lo, nxt_hi, lo_f.as<float4>(), hi_f.as<float4>(),
+                                                                      nodes.as<BNode>(), g, max_leaf, c_trav, c_isect);
+            CU(cudaGetLastError());
+        }
+        std::swap(cur_lo, nxt_lo); std::swap(cur_hi, nxt_hi); std::swap(bcur, bnext);
+        n_big = h_cnt[1];
+        if (++levels > 4096) return fail(TAKE_E_CUDA, "device BVH build: no progress");
+    }
+    k_leaf_prims<<<gb, TAKE_DB_BLOCK, 0, st>>>(n, lo_f.as<float4>(), s->leaf_prims.as<int32_t>());
+    CU(cudaGetLastError());
     // wide collapse, breadth first
+    const int32_t root = 0;
     BNode h_root;
     CU(cudaMemcpyAsync(&h_root, nodes.as<BNode>() + root, sizeof(BNode), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    s->sah_cost = h_root.hi.w;
     int32_t n_wide = 1, depth = 1;
     if (h_root.leaf) {
-        k_wide_wrap_root<<<1, 32, 0, st>>>(nodes.as<BNode>(), root, n, wide_tmp.as<WideNode>(), s->leaf_prims.as<int32_t>());
+        k_wide_wrap_root<<<1, 32, 0, st>>>(nodes.as<BNode>(), root, n, wide_tmp.as<WideNode>());
         CU(cudaGetLastError());
     } else {
+        size_t tmp_bytes = 0;
+        CU(icount.ensure((size_t)n * 4)); CU(iscan.ensure((size_t)n * 4));
+        CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, icount.as<uint32_t>(), iscan.as<uint32_t>(), (int)n, st));
+        tmp_bytes = std::max<size_t>(tmp_bytes, 256);
+        CU(cubtmp.ensure(tmp_bytes));
         CU(items_a.ensure((size_t)n * sizeof(WorkItem))); CU(items_b.ensure((size_t)n * sizeof(WorkItem)));
         CU(kids.ensure((size_t)n * sizeof(Kids)));
         WorkItem first_item = {root, 0, 0, 0};
         CU(cudaMemcpyAsync(items_a.p, &first_item, sizeof(first_item), cudaMemcpyHostToDevice, st));
         WorkItem *ia = items_a.as<WorkItem>(), *ib = items_b.as<WorkItem>();
         int32_t n_items = 1;
-        uint32_t *h32 = reinterpret_cast<uint32_t *>(h_tail);
+        uint32_t *h32 = reinterpret_cast<uint32_t *>(h_cnt) + 4;
         while (n_items > 0) {
-            const unsigned g = (unsigned)((n_items + TAKE_DB_BLOCK - 1) / TAKE_DB_BLOCK);
-            k_wide_kids<<<g, TAKE_DB_BLOCK, 0, st>>>(n_items, ia, nodes.as<BNode>(), kids.as<Kids>(), icount.as<uint32_t>());
+            const unsigned gi = (unsigned)((n_items + TAKE_DB_BLOCK - 1) / TAKE_DB_BLOCK);
+            k_wide_kids<<<gi, TAKE_DB_BLOCK, 0, st>>>(n_items, ia, nodes.as<BNode>(), kids.as<Kids>(), icount.as<uint32_t>());
             CU(cub::DeviceScan::ExclusiveSum(cubtmp.p, tmp_bytes, icount.as<uint32_t>(), iscan.as<uint32_t>(), n_items, st));
             CU(cudaMemcpyAsync(h32, iscan.as<uint32_t>() + (n_items - 1), 4, cudaMemcpyDeviceToHost, st));
             CU(cudaMemcpyAsync(h32 + 1, icount.as<uint32_t>() + (n_items - 1), 4, cudaMemcpyDeviceToHost, st));
-            k_wide_emit<<<g, TAKE_DB_BLOCK, 0, st>>>(n_items, ia, kids.as<Kids>(), iscan.as<uint32_t>(), nodes.as<BNode>(), wide_tmp.as<WideNode>(),
-                                                    n_wide, ib, s->leaf_prims.as<int32_t>());
+            k_wide_emit<<<gi, TAKE_DB_BLOCK, 0, st>>>(n_items, ia, kids.as<Kids>(), iscan.as<uint32_t>(), nodes.as<BNode>(), wide_tmp.as<WideNode>(),
+                                                     n_wide, ib);
             CU(cudaGetLastError());
             CU(cudaStreamSynchronize(st));
             const int32_t inner = (int32_t)(h32[0] + h32[1]);

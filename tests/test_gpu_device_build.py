@@ -184,7 +184,7 @@ def test_scene_create_does_not_wait_for_the_reference_tree(gpu_lib):
         t = gs.create_timings()
         print("scene_create phases (ms):", {k: round(v, 1) for k, v in t.items()})
         assert t["device_built"] == 1
-        rays = api.make_rays([[0, 160, 240]], [[0, -0.5547, -0.83205]])
+        rays = api.make_rays([[0, 160, 240]], [[0.0137, -0.5547, -0.8262]])   # (not along a mesh edge: those rays slip through, shape.cpp:65,71)
         p, _, _ = gs.intersect(rays, exact=True)          # needs the reference tree
         assert gs.create_timings()["reference_tree_pending"] == 0 and p[0] >= 0
         info = gs.info()
