@@ -175,15 +175,30 @@ __global__ void __launch_bounds__(TAKE_DB_BLOCK) k_sah_split(const SItem *items,
     }
     if (tid < 24) s_child[tid / 12][tid % 12] = ((tid % 12) % 6 < 3) ? 0xffffffffu : 0u;
     __syncthreads();
-    // pass 1: bin all three axes
-    for (int32_t i = lo + tid; i < hi; i += TAKE_DB_BLOCK) {
+    // pass 1: bin all three axes.  Consecutive primitives of a mesh sit next to each other in space, so the lanes of a warp
+    // mostly fall into the same bin: lanes are grouped by bin (__match_any_sync), each group reduces its boxes with redux and
+    // its lowest lane alone touches the shared bins -- without this the same-address shared atomics serialise and the top
+    // levels of a 10 M-primitive scene take seconds.
+    for (int32_t base = lo; base < hi; base += TAKE_DB_BLOCK) {
+        const int32_t i = base + tid;
+        const bool valid = i < hi;
+        const unsigned vm = __ballot_sync(0xffffffffu, valid);
+        if (!valid) continue;
         const float4 l = cur_lo[i], h = cur_hi[i];
         const float bl[3] = {l.x, l.y, l.z}, bh[3] = {h.x, h.y, h.z};
+        uint32_t omin[3], omax[3];
+        for (int a = 0; a < 3; ++a) { omin[a] = f2ord(bl[a]); omax[a] = f2ord(bh[a]); }
         for (int x = 0; x < 3; ++x) {
             if (!axis_ok[x]) continue;
             const int k = bin_of(centroid(bl[x], bh[x]), it.cl[x], scale3[x]);
-            atomicAdd(&s_cnt[x][k], 1u);
-            for (int a = 0; a < 3; ++a) { atomicMin(&s_min[x][k][a], f2ord(bl[a])); atomicMax(&s_max[x][k][a], f2ord(bh[a])); }
+            const unsigned peers = __match_any_sync(vm, k);
+            const bool leader = lane == __ffs(peers) - 1;
+            uint32_t gmin[3], gmax[3];
+            for (int a = 0; a < 3; ++a) { gmin[a] = __reduce_min_sync(peers, omin[a]); gmax[a] = __reduce_max_sync(peers, omax[a]); }
+            if (leader) {
+                atomicAdd(&s_cnt[x][k], (uint32_t)__popc(peers));
+                for (int a = 0; a < 3; ++a) { atomicMin(&s_min[x][k][a], gmin[a]); atomicMax(&s_max[x][k][a], gmax[a]); }
+            }
         }
     }
     __syncthreads();
