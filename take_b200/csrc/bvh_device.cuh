@@ -68,7 +68,7 @@ struct Globals {        // identity-initialised by the host before k_prim_boxes
     uint32_t bmin[3], bmax[3];          // scene bounds (ordered-uint encoding)
     uint32_t cmin[3], cmax[3];          // centroid bounds
     unsigned long long abs_max_bits;    // max |coordinate| over the FP64 primitive bounds (bits of a non-negative double)
-    int32_t node_count, big_count, small_count, pad;   // allocation counters of the SAH levels
+    int32_t node_count, huge_count, med_count, small_count, chunk_count, pad[3];   // allocation counters of the SAH levels
 };
 
 // ---- 1. primitive boxes -------------------------------------------------------------------------------------------
@@ -111,11 +111,24 @@ __global__ void k_prim_boxes(DevScene sc, int64_t n, float4 *plo, float4 *phi, G
 }
 
 // ---- 2. SAH levels --------------------------------------------------------------------------------------------------
+#define TAKE_SAH_CHUNK 4096                    // primitives per block of the chunked path
+#define TAKE_SAH_HUGE (4 * TAKE_SAH_CHUNK)     // nodes above this size are split by several blocks
+
 struct SItem {          // a node whose range still has to be split
     int32_t node, lo, hi, pad;
     float bl[3], bh[3], cl[3], ch[3];   // box of the primitives, box of their centroids
 };
 static_assert(sizeof(SItem) == 64, "SItem");
+struct SChunk { int32_t item, lo, hi, index; };   // one block's share of a huge node (index = chunk number inside the node)
+
+struct SBins {          // shared-memory bins of one node (or one chunk of it)
+    uint32_t mn[3][TAKE_SAH_BINS][3], mx[3][TAKE_SAH_BINS][3], cnt[3][TAKE_SAH_BINS];
+};
+struct HugeState {      // global per huge node of a level
+    SBins bins;
+    uint32_t child[2][12];      // per side: box min, box max, centroid min, centroid max (ordered uint)
+    int32_t axis, best_bin, nl, first_chunk, n_chunks, pad[3];
+};
 
 __device__ __forceinline__ int bin_of(float c, float cb_lo, float scale) {
     const int k = (int)((c - cb_lo) * scale);
@@ -133,54 +146,32 @@ __device__ __forceinline__ void write_node(BNode *nodes, int32_t id, const float
     nodes[id] = b;
 }
 
-// root item from the global bounds
-__global__ void k_sah_root(int32_t n, Globals *g, BNode *nodes, SItem *big, SItem *small) {
-    if (blockIdx.x || threadIdx.x) return;
-    SItem it;
-    it.node = 0; it.lo = 0; it.hi = n; it.pad = 0;
-    for (int a = 0; a < 3; ++a) {
-        it.bl[a] = ord2f(g->bmin[a]); it.bh[a] = ord2f(g->bmax[a]);
-        it.cl[a] = ord2f(g->cmin[a]); it.ch[a] = ord2f(g->cmax[a]);
-    }
-    write_node(nodes, 0, it.bl, it.bh, n);
-    g->node_count = 1;
-    g->big_count = 0; g->small_count = 0;
-    if (n > TAKE_SAH_SMALL) { big[0] = it; g->big_count = 1; }
-    else { small[0] = it; g->small_count = 1; }
-}
-
-// One block per node: bin, sweep, partition (cur -> nxt), emit the children.
-__global__ void __launch_bounds__(TAKE_DB_BLOCK) k_sah_split(const SItem *items, const float4 *cur_lo, const float4 *cur_hi, float4 *nxt_lo,
-                                                             float4 *nxt_hi, BNode *nodes, Globals *g, SItem *next_big, SItem *next_small) {
-    __shared__ uint32_t s_min[3][TAKE_SAH_BINS][3], s_max[3][TAKE_SAH_BINS][3], s_cnt[3][TAKE_SAH_BINS];
-    __shared__ float s_cost[3];
-    __shared__ int s_bin[3], s_nleft[3];
-    __shared__ uint32_t s_child[2][12];   // per side: box min xyz, box max xyz, centroid min xyz, centroid max xyz (ordered uint)
-    __shared__ uint32_t s_wl[TAKE_DB_BLOCK / 32], s_wv[TAKE_DB_BLOCK / 32];
-    __shared__ int s_axis, s_best_bin, s_nl;
-    const SItem it = items[blockIdx.x];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int32_t lo = it.lo, hi = it.hi, m = hi - lo;
-    float scale3[3];
-    bool axis_ok[3];
+__device__ __forceinline__ void item_scales(const SItem &it, float *scale3, bool *axis_ok) {
     for (int x = 0; x < 3; ++x) {
         const float ext = it.ch[x] - it.cl[x];
         axis_ok[x] = ext > 0.0f;
         scale3[x] = axis_ok[x] ? (float)TAKE_SAH_BINS / ext : 0.0f;
     }
-    for (int t = tid; t < 3 * TAKE_SAH_BINS; t += TAKE_DB_BLOCK) {
+}
+
+__device__ __forceinline__ void bins_clear(SBins &B) {
+    for (int t = threadIdx.x; t < 3 * TAKE_SAH_BINS; t += blockDim.x) {
         const int x = t / TAKE_SAH_BINS, b = t % TAKE_SAH_BINS;
-        for (int a = 0; a < 3; ++a) { s_min[x][b][a] = 0xffffffffu; s_max[x][b][a] = 0u; }
-        s_cnt[x][b] = 0u;
+        for (int a = 0; a < 3; ++a) { B.mn[x][b][a] = 0xffffffffu; B.mx[x][b][a] = 0u; }
+        B.cnt[x][b] = 0u;
     }
-    if (tid < 24) s_child[tid / 12][tid % 12] = ((tid % 12) % 6 < 3) ? 0xffffffffu : 0u;
-    __syncthreads();
-    // pass 1: bin all three axes.  Consecutive primitives of a mesh sit next to each other in space, so the lanes of a warp
-    // mostly fall into the same bin: lanes are grouped by bin (__match_any_sync), each group reduces its boxes with redux and
-    // its lowest lane alone touches the shared bins -- without this the same-address shared atomics serialise and the top
-    // levels of a 10 M-primitive scene take seconds.
-    for (int32_t base = lo; base < hi; base += TAKE_DB_BLOCK) {
-        const int32_t i = base + tid;
+}
+
+// Bin [lo, hi) on all three axes into shared bins.  Consecutive primitives of a mesh often sit next to each other in space,
+// so all lanes of a warp frequently fall into ONE bin -- same-address shared atomics would then serialise (measured: seconds
+// at the top levels of a 10 M-primitive scene).  When a whole warp agrees on the bin (__match_all_sync, one instruction) the
+// warp reduces its boxes with redux and one lane updates the bin; otherwise the lanes are spread over bins and update them
+// themselves.
+__device__ __forceinline__ void bin_range(SBins &B, const SItem &it, const float *scale3, const bool *axis_ok, int32_t lo, int32_t hi,
+                                          const float4 *cur_lo, const float4 *cur_hi) {
+    const int lane = threadIdx.x & 31;
+    for (int32_t base = lo; base < hi; base += blockDim.x) {
+        const int32_t i = base + threadIdx.x;
         const bool valid = i < hi;
         const unsigned vm = __ballot_sync(0xffffffffu, valid);
         if (!valid) continue;
@@ -191,47 +182,54 @@ __global__ void __launch_bounds__(TAKE_DB_BLOCK) k_sah_split(const SItem *items,
         for (int x = 0; x < 3; ++x) {
             if (!axis_ok[x]) continue;
             const int k = bin_of(centroid(bl[x], bh[x]), it.cl[x], scale3[x]);
-            const unsigned peers = __match_any_sync(vm, k);
-            const bool leader = lane == __ffs(peers) - 1;
-            uint32_t gmin[3], gmax[3];
-            for (int a = 0; a < 3; ++a) { gmin[a] = __reduce_min_sync(peers, omin[a]); gmax[a] = __reduce_max_sync(peers, omax[a]); }
-            if (leader) {
-                atomicAdd(&s_cnt[x][k], (uint32_t)__popc(peers));
-                for (int a = 0; a < 3; ++a) { atomicMin(&s_min[x][k][a], gmin[a]); atomicMax(&s_max[x][k][a], gmax[a]); }
+            int same = 0;
+            __match_all_sync(vm, k, &same);
+            if (same) {
+                uint32_t gmin[3], gmax[3];
+                for (int a = 0; a < 3; ++a) { gmin[a] = __reduce_min_sync(vm, omin[a]); gmax[a] = __reduce_max_sync(vm, omax[a]); }
+                if (lane == __ffs(vm) - 1) {
+                    atomicAdd(&B.cnt[x][k], (uint32_t)__popc(vm));
+                    for (int a = 0; a < 3; ++a) { atomicMin(&B.mn[x][k][a], gmin[a]); atomicMax(&B.mx[x][k][a], gmax[a]); }
+                }
+            } else {
+                atomicAdd(&B.cnt[x][k], 1u);
+                for (int a = 0; a < 3; ++a) { atomicMin(&B.mn[x][k][a], omin[a]); atomicMax(&B.mx[x][k][a], omax[a]); }
             }
         }
     }
-    __syncthreads();
-    // sweep: one thread per axis (split between bin b and b+1; the first minimum wins, like the host's ascending loops)
-    if (tid < 3) {
-        const int x = tid;
-        float best = INFINITY;
-        int best_bin = -1, nleft = 0;
-        if (axis_ok[x]) {
-            float right_area[TAKE_SAH_BINS];
-            uint32_t right_cnt[TAKE_SAH_BINS];
-            float al[3] = {INFINITY, INFINITY, INFINITY}, ah[3] = {-INFINITY, -INFINITY, -INFINITY};
-            uint32_t cnt = 0;
-            for (int b = TAKE_SAH_BINS - 1; b > 0; --b) {
-                cnt += s_cnt[x][b];
-                if (s_cnt[x][b]) for (int a = 0; a < 3; ++a) { al[a] = fminf(al[a], ord2f(s_min[x][b][a])); ah[a] = fmaxf(ah[a], ord2f(s_max[x][b][a])); }
-                right_area[b] = half_area3(al, ah);
-                right_cnt[b] = cnt;
-            }
-            for (int a = 0; a < 3; ++a) { al[a] = INFINITY; ah[a] = -INFINITY; }
-            cnt = 0;
-            for (int b = 0; b < TAKE_SAH_BINS - 1; ++b) {
-                cnt += s_cnt[x][b];
-                if (s_cnt[x][b]) for (int a = 0; a < 3; ++a) { al[a] = fminf(al[a], ord2f(s_min[x][b][a])); ah[a] = fmaxf(ah[a], ord2f(s_max[x][b][a])); }
-                if (cnt == 0 || right_cnt[b + 1] == 0) continue;
-                const float cost = half_area3(al, ah) * (float)cnt + right_area[b + 1] * (float)right_cnt[b + 1];
-                if (cost < best) { best = cost; best_bin = b; nleft = (int)cnt; }
-            }
-        }
-        s_cost[x] = best; s_bin[x] = best_bin; s_nleft[x] = nleft;
+}
+
+// Sweep of one axis (split between bin b and b+1; the first minimum wins, like the host's ascending loops).
+__device__ inline void sweep_axis(const SBins &B, int x, bool ok, float &best, int &best_bin, int &nleft) {
+    best = INFINITY; best_bin = -1; nleft = 0;
+    if (!ok) return;
+    float right_area[TAKE_SAH_BINS];
+    uint32_t right_cnt[TAKE_SAH_BINS];
+    float al[3] = {INFINITY, INFINITY, INFINITY}, ah[3] = {-INFINITY, -INFINITY, -INFINITY};
+    uint32_t cnt = 0;
+    for (int b = TAKE_SAH_BINS - 1; b > 0; --b) {
+        cnt += B.cnt[x][b];
+        if (B.cnt[x][b]) for (int a = 0; a < 3; ++a) { al[a] = fminf(al[a], ord2f(B.mn[x][b][a])); ah[a] = fmaxf(ah[a], ord2f(B.mx[x][b][a])); }
+        right_area[b] = half_area3(al, ah);
+        right_cnt[b] = cnt;
     }
+    for (int a = 0; a < 3; ++a) { al[a] = INFINITY; ah[a] = -INFINITY; }
+    cnt = 0;
+    for (int b = 0; b < TAKE_SAH_BINS - 1; ++b) {
+        cnt += B.cnt[x][b];
+        if (B.cnt[x][b]) for (int a = 0; a < 3; ++a) { al[a] = fminf(al[a], ord2f(B.mn[x][b][a])); ah[a] = fmaxf(ah[a], ord2f(B.mx[x][b][a])); }
+        if (cnt == 0 || right_cnt[b + 1] == 0) continue;
+        const float cost = half_area3(al, ah) * (float)cnt + right_area[b + 1] * (float)right_cnt[b + 1];
+        if (cost < best) { best = cost; best_bin = b; nleft = (int)cnt; }
+    }
+}
+
+// The three sweeps on threads 0..2 and the choice of the axis on thread 0; results in shared s_axis / s_best_bin / s_nl.
+__device__ __forceinline__ void choose_split(const SBins &B, const bool *axis_ok, int32_t m, float *s_cost, int *s_bin, int *s_nleft,
+                                             int &s_axis, int &s_best_bin, int &s_nl) {
+    if (threadIdx.x < 3) sweep_axis(B, threadIdx.x, axis_ok[threadIdx.x], s_cost[threadIdx.x], s_bin[threadIdx.x], s_nleft[threadIdx.x]);
     __syncthreads();
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
         int axis = -1;
         float best = INFINITY;
         for (int x = 0; x < 3; ++x) if (s_bin[x] >= 0 && s_cost[x] < best) { best = s_cost[x]; axis = x; }
@@ -240,9 +238,15 @@ __global__ void __launch_bounds__(TAKE_DB_BLOCK) k_sah_split(const SItem *items,
         s_nl = axis >= 0 ? s_nleft[axis] : m / 2;   // all centroids coincide: split the range in half, order kept
     }
     __syncthreads();
-    const int axis = s_axis, best_bin = s_best_bin;
-    const int32_t nl = s_nl;
-    // pass 2: stable partition into the other buffer, accumulating the bounds of both sides
+}
+
+// Stable partition of [lo, hi) (a node's range or one chunk of it) into the other buffer.  Lefts go to out_l + rank, rights to
+// out_r + rank; the bounds of both sides are accumulated in s_child with warp redux + one shared atomic per warp and quantity.
+// node_lo / nl: start of the whole node's range and its left count (for the split-in-half fallback of coincident centroids).
+__device__ __forceinline__ void partition_range(const SItem &it, const float *scale3, int axis, int best_bin, int32_t node_lo, int32_t nl,
+                                                int32_t lo, int32_t hi, int32_t out_l, int32_t out_r, const float4 *cur_lo, const float4 *cur_hi,
+                                                float4 *nxt_lo, float4 *nxt_hi, uint32_t (*s_child)[12], uint32_t *s_wl, uint32_t *s_wv) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int32_t lrun = 0, rrun = 0;
     for (int32_t base = lo; base < hi; base += TAKE_DB_BLOCK) {
         const int32_t i = base + tid;
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(TAKE_DB_BLOCK) k_sah_split(const SItem *items,
                 const float bl = axis == 0 ? l.x : axis == 1 ? l.y : l.z, bh = axis == 0 ? h.x : axis == 1 ? h.y : h.z;
                 left = bin_of(centroid(bl, bh), it.cl[axis], scale3[axis]) <= best_bin;
             } else {
-                left = (i - lo) < nl;
+                left = (i - node_lo) < nl;
             }
         }
         const unsigned wmask = __ballot_sync(0xffffffffu, left), vmask = __ballot_sync(0xffffffffu, valid);
@@ -269,10 +273,9 @@ __global__ void __launch_bounds__(TAKE_DB_BLOCK) k_sah_split(const SItem *items,
         const unsigned lt = (1u << lane) - 1u;
         const int32_t lrank = lpre + __popc(wmask & lt), vrank = vpre + __popc(vmask & lt);
         if (valid) {
-            const int32_t pos = left ? lo + lrun + lrank : lo + nl + rrun + (vrank - lrank);
+            const int32_t pos = left ? out_l + lrun + lrank : out_r + rrun + (vrank - lrank);
             nxt_lo[pos] = l; nxt_hi[pos] = h;
         }
-        // children's bounds: warp redux per side and quantity, then one shared atomic per warp
         const float q[12] = {l.x, l.y, l.z, h.x, h.y, h.z, centroid(l.x, h.x), centroid(l.y, h.y), centroid(l.z, h.z),
                              centroid(l.x, h.x), centroid(l.y, h.y), centroid(l.z, h.z)};
         for (int side = 0; side < 2; ++side) {
@@ -288,25 +291,198 @@ __global__ void __launch_bounds__(TAKE_DB_BLOCK) k_sah_split(const SItem *items,
         lrun += ltot; rrun += vtot - ltot;
         __syncthreads();
     }
-    if (tid == 0) {
-        const int32_t first = atomicAdd(&g->node_count, 2);
-        nodes[it.node].left = first;
-        nodes[it.node].right = first + 1;
-        for (int side = 0; side < 2; ++side) {
-            SItem c;
-            c.node = first + side; c.pad = 0;
-            c.lo = side == 0 ? lo : lo + nl;
-            c.hi = side == 0 ? lo + nl : hi;
-            for (int a = 0; a < 3; ++a) {
-                c.bl[a] = ord2f(s_child[side][a]); c.bh[a] = ord2f(s_child[side][3 + a]);
-                c.cl[a] = ord2f(s_child[side][6 + a]); c.ch[a] = ord2f(s_child[side][9 + a]);
+}
+
+// Children of a split node: allocate their ids, write them, queue them by size (huge nodes also reserve their chunks).
+__device__ inline void emit_children(const SItem &it, int32_t nl, const uint32_t (*child)[12], BNode *nodes, Globals *g, SItem *next_huge,
+                                     SItem *next_med, SItem *next_small, SChunk *next_chunks, HugeState *next_state) {
+    const int32_t first = atomicAdd(&g->node_count, 2);
+    nodes[it.node].left = first;
+    nodes[it.node].right = first + 1;
+    for (int side = 0; side < 2; ++side) {
+        SItem c;
+        c.node = first + side; c.pad = 0;
+        c.lo = side == 0 ? it.lo : it.lo + nl;
+        c.hi = side == 0 ? it.lo + nl : it.hi;
+        for (int a = 0; a < 3; ++a) {
+            c.bl[a] = ord2f(child[side][a]); c.bh[a] = ord2f(child[side][3 + a]);
+            c.cl[a] = ord2f(child[side][6 + a]); c.ch[a] = ord2f(child[side][9 + a]);
+        }
+        const int32_t cm = c.hi - c.lo;
+        write_node(nodes, c.node, c.bl, c.bh, cm);
+        if (cm > TAKE_SAH_HUGE) {
+            const int32_t slot = atomicAdd(&g->huge_count, 1);
+            const int32_t nch = (cm + TAKE_SAH_CHUNK - 1) / TAKE_SAH_CHUNK;
+            const int32_t c0 = atomicAdd(&g->chunk_count, nch);
+            next_huge[slot] = c;
+            next_state[slot].first_chunk = c0;
+            next_state[slot].n_chunks = nch;
+            for (int q = 0; q < nch; ++q) {
+                SChunk ch;
+                ch.item = slot; ch.index = q;
+                ch.lo = c.lo + q * TAKE_SAH_CHUNK;
+                ch.hi = min(c.hi, ch.lo + TAKE_SAH_CHUNK);
+                next_chunks[c0 + q] = ch;
             }
-            const int32_t cm = c.hi - c.lo;
-            write_node(nodes, c.node, c.bl, c.bh, cm);
-            if (cm > TAKE_SAH_SMALL) next_big[atomicAdd(&g->big_count, 1)] = c;
-            else next_small[atomicAdd(&g->small_count, 1)] = c;
+        } else if (cm > TAKE_SAH_SMALL) {
+            next_med[atomicAdd(&g->med_count, 1)] = c;
+        } else {
+            next_small[atomicAdd(&g->small_count, 1)] = c;
         }
     }
+}
+
+// root item from the global bounds (reuses emit's queueing rules)
+__global__ void k_sah_root(int32_t n, Globals *g, BNode *nodes, SItem *huge, SItem *med, SItem *small, SChunk *chunks, HugeState *state) {
+    if (blockIdx.x || threadIdx.x) return;
+    SItem it;
+    it.node = 0; it.lo = 0; it.hi = n; it.pad = 0;
+    for (int a = 0; a < 3; ++a) {
+        it.bl[a] = ord2f(g->bmin[a]); it.bh[a] = ord2f(g->bmax[a]);
+        it.cl[a] = ord2f(g->cmin[a]); it.ch[a] = ord2f(g->cmax[a]);
+    }
+    write_node(nodes, 0, it.bl, it.bh, n);
+    g->node_count = 1;
+    g->huge_count = g->med_count = g->small_count = g->chunk_count = 0;
+    if (n > TAKE_SAH_HUGE) {
+        const int32_t nch = (n + TAKE_SAH_CHUNK - 1) / TAKE_SAH_CHUNK;
+        huge[0] = it;
+        state[0].first_chunk = 0; state[0].n_chunks = nch;
+        for (int q = 0; q < nch; ++q) {
+            SChunk ch;
+            ch.item = 0; ch.index = q; ch.lo = q * TAKE_SAH_CHUNK; ch.hi = min(n, ch.lo + TAKE_SAH_CHUNK);
+            chunks[q] = ch;
+        }
+        g->huge_count = 1; g->chunk_count = nch;
+    } else if (n > TAKE_SAH_SMALL) {
+        med[0] = it; g->med_count = 1;
+    } else {
+        small[0] = it; g->small_count = 1;
+    }
+}
+
+// ---- medium nodes: one block per node: bin, sweep, partition (cur -> nxt), emit the children ----
+__global__ void __launch_bounds__(TAKE_DB_BLOCK) k_sah_split(const SItem *items, const float4 *cur_lo, const float4 *cur_hi, float4 *nxt_lo,
+                                                             float4 *nxt_hi, BNode *nodes, Globals *g, SItem *next_huge, SItem *next_med,
+                                                             SItem *next_small, SChunk *next_chunks, HugeState *next_state) {
+    __shared__ SBins B;
+    __shared__ float s_cost[3];
+    __shared__ int s_bin[3], s_nleft[3];
+    __shared__ uint32_t s_child[2][12];
+    __shared__ uint32_t s_wl[TAKE_DB_BLOCK / 32], s_wv[TAKE_DB_BLOCK / 32];
+    __shared__ int s_axis, s_best_bin, s_nl;
+    const SItem it = items[blockIdx.x];
+    const int tid = threadIdx.x;
+    float scale3[3];
+    bool axis_ok[3];
+    item_scales(it, scale3, axis_ok);
+    bins_clear(B);
+    if (tid < 24) s_child[tid / 12][tid % 12] = ((tid % 12) % 6 < 3) ? 0xffffffffu : 0u;
+    __syncthreads();
+    bin_range(B, it, scale3, axis_ok, it.lo, it.hi, cur_lo, cur_hi);
+    __syncthreads();
+    choose_split(B, axis_ok, it.hi - it.lo, s_cost, s_bin, s_nleft, s_axis, s_best_bin, s_nl);
+    const int32_t nl = s_nl;
+    partition_range(it, scale3, s_axis, s_best_bin, it.lo, nl, it.lo, it.hi, it.lo, it.lo + nl, cur_lo, cur_hi, nxt_lo, nxt_hi, s_child, s_wl, s_wv);
+    if (tid == 0) emit_children(it, nl, s_child, nodes, g, next_huge, next_med, next_small, next_chunks, next_state);
+}
+
+// ---- huge nodes: several blocks per node (one per chunk of TAKE_SAH_CHUNK primitives) ----
+__global__ void k_huge_clear(HugeState *state, int32_t n_items) {
+    const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int32_t item = t / (3 * TAKE_SAH_BINS), r = t % (3 * TAKE_SAH_BINS);
+    if (item >= n_items) return;
+    SBins &B = state[item].bins;
+    const int x = r / TAKE_SAH_BINS, b = r % TAKE_SAH_BINS;
+    for (int a = 0; a < 3; ++a) { B.mn[x][b][a] = 0xffffffffu; B.mx[x][b][a] = 0u; }
+    B.cnt[x][b] = 0u;
+    if (r < 24) state[item].child[r / 12][r % 12] = ((r % 12) % 6 < 3) ? 0xffffffffu : 0u;
+}
+
+// pass 1 of a chunk: bin into shared memory, merge into the node's global bins, keep the chunk's own bin counts
+__global__ void __launch_bounds__(TAKE_DB_BLOCK) k_huge_bin(const SItem *items, const SChunk *chunks, const float4 *cur_lo, const float4 *cur_hi,
+                                                            HugeState *state, uint32_t *chunk_cnt) {
+    __shared__ SBins B;
+    const SChunk ch = chunks[blockIdx.x];
+    const SItem it = items[ch.item];
+    float scale3[3];
+    bool axis_ok[3];
+    item_scales(it, scale3, axis_ok);
+    bins_clear(B);
+    __syncthreads();
+    bin_range(B, it, scale3, axis_ok, ch.lo, ch.hi, cur_lo, cur_hi);
+    __syncthreads();
+    SBins &G = state[ch.item].bins;
+    uint32_t *cc = chunk_cnt + (size_t)(state[ch.item].first_chunk + ch.index) * (3 * TAKE_SAH_BINS);
+    for (int t = threadIdx.x; t < 3 * TAKE_SAH_BINS; t += TAKE_DB_BLOCK) {
+        const int x = t / TAKE_SAH_BINS, b = t % TAKE_SAH_BINS;
+        const uint32_t c = B.cnt[x][b];
+        cc[t] = c;
+        if (c) {
+            atomicAdd(&G.cnt[x][b], c);
+            for (int a = 0; a < 3; ++a) { atomicMin(&G.mn[x][b][a], B.mn[x][b][a]); atomicMax(&G.mx[x][b][a], B.mx[x][b][a]); }
+        }
+    }
+}
+
+// one block per huge node: choose the split from the merged bins, turn the chunks' bin counts into output offsets
+// (chunk_off[c] = number of left-going primitives in the chunks before c of the same node)
+__global__ void __launch_bounds__(TAKE_DB_BLOCK) k_huge_choose(const SItem *items, HugeState *state, const uint32_t *chunk_cnt, int32_t *chunk_off) {
+    __shared__ float s_cost[3];
+    __shared__ int s_bin[3], s_nleft[3];
+    __shared__ int s_axis, s_best_bin, s_nl;
+    const SItem it = items[blockIdx.x];
+    HugeState &S = state[blockIdx.x];
+    float scale3[3];
+    bool axis_ok[3];
+    item_scales(it, scale3, axis_ok);
+    choose_split(S.bins, axis_ok, it.hi - it.lo, s_cost, s_bin, s_nleft, s_axis, s_best_bin, s_nl);
+    if (threadIdx.x == 0) {
+        S.axis = s_axis; S.best_bin = s_best_bin; S.nl = s_nl;
+        int32_t acc = 0;
+        for (int c = 0; c < S.n_chunks; ++c) {
+            chunk_off[S.first_chunk + c] = acc;
+            if (s_axis >= 0) {
+                const uint32_t *cc = chunk_cnt + (size_t)(S.first_chunk + c) * (3 * TAKE_SAH_BINS) + s_axis * TAKE_SAH_BINS;
+                for (int b = 0; b <= s_best_bin; ++b) acc += (int32_t)cc[b];
+            } else {   // coincident centroids: the first nl primitives of the range go left
+                const int32_t c_lo = it.lo + c * TAKE_SAH_CHUNK, c_hi = min(it.hi, c_lo + TAKE_SAH_CHUNK);
+                acc += max(0, min(c_hi, it.lo + s_nl) - c_lo);
+            }
+        }
+    }
+}
+
+// pass 2 of a chunk: stable partition into the node's output ranges, merge the children's bounds into the node's state
+__global__ void __launch_bounds__(TAKE_DB_BLOCK) k_huge_partition(const SItem *items, const SChunk *chunks, const float4 *cur_lo, const float4 *cur_hi,
+                                                                  float4 *nxt_lo, float4 *nxt_hi, HugeState *state, const int32_t *chunk_off) {
+    __shared__ uint32_t s_child[2][12];
+    __shared__ uint32_t s_wl[TAKE_DB_BLOCK / 32], s_wv[TAKE_DB_BLOCK / 32];
+    const SChunk ch = chunks[blockIdx.x];
+    const SItem it = items[ch.item];
+    HugeState &S = state[ch.item];
+    const int tid = threadIdx.x;
+    float scale3[3];
+    bool axis_ok[3];
+    item_scales(it, scale3, axis_ok);
+    if (tid < 24) s_child[tid / 12][tid % 12] = ((tid % 12) % 6 < 3) ? 0xffffffffu : 0u;
+    __syncthreads();
+    const int32_t left_before = chunk_off[S.first_chunk + ch.index];
+    const int32_t right_before = (ch.lo - it.lo) - left_before;
+    partition_range(it, scale3, S.axis, S.best_bin, it.lo, S.nl, ch.lo, ch.hi, it.lo + left_before, it.lo + S.nl + right_before, cur_lo, cur_hi,
+                    nxt_lo, nxt_hi, s_child, s_wl, s_wv);
+    if (tid < 24) {
+        const int side = tid / 12, k = tid % 12;
+        if ((k % 6) < 3) atomicMin(&S.child[side][k], s_child[side][k]);
+        else atomicMax(&S.child[side][k], s_child[side][k]);
+    }
+}
+
+__global__ void k_huge_emit(const SItem *items, int32_t n_items, const HugeState *state, BNode *nodes, Globals *g, SItem *next_huge,
+                            SItem *next_med, SItem *next_small, SChunk *next_chunks, HugeState *next_state) {
+    const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_items) return;
+    emit_children(items[t], state[t].nl, state[t].child, nodes, g, next_huge, next_med, next_small, next_chunks, next_state);
 }
 
 // One thread per node of up to SMALL primitives: copy the range into the final array and finish the subtree there (the

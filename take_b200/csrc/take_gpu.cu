@@ -662,7 +662,7 @@ static int device_build_fast_tree(TakeScene *s, int max_leaf, double &abs_max) {
     s->sah_cost = 0;
     CU(s->leaf_prims.ensure(std::max<size_t>((size_t)n * 4, 16)));
     CU(s->tris.ensure(std::max<size_t>((size_t)n * 96, 32)));
-    DeviceBuffer wide_tmp, nodes, lo_a, hi_a, lo_b, hi_b, lo_f, hi_f, glob, big_a, big_b, small, items_a, items_b, kids, icount, iscan, cubtmp;
+    DeviceBuffer wide_tmp, nodes, lo_a, hi_a, lo_b, hi_b, lo_f, hi_f, glob, small, items_a, items_b, kids, icount, iscan, cubtmp;
     CU(wide_tmp.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(WideNode)));
     if (n == 0) {
         k_wide_wrap_root<<<1, 32, 0, st>>>(nullptr, 0, 0, wide_tmp.as<WideNode>());
@@ -687,46 +687,67 @@ static int device_build_fast_tree(TakeScene *s, int max_leaf, double &abs_max) {
     Globals *g = glob.as<Globals>();
     k_prim_boxes<<<gb, TAKE_DB_BLOCK, 0, st>>>(s->dev, n, lo_a.as<float4>(), hi_a.as<float4>(), g);
     CU(cudaGetLastError());
-    // SAH levels
+    // SAH levels: huge nodes by several blocks each (chunks), medium nodes by one block each, small nodes by one thread each
     const float c_trav = 1.0f, c_isect = 1.2f;   // SahBuilder's constants (bvh_build.cpp)
-    const size_t cap_big = (size_t)n / TAKE_SAH_SMALL + 4, cap_small = (size_t)n / (TAKE_SAH_SMALL / 2) + 8;
+    const size_t cap_huge = (size_t)n / TAKE_SAH_HUGE + 4, cap_med = (size_t)n / TAKE_SAH_SMALL + 4, cap_small = (size_t)n / (TAKE_SAH_SMALL / 2) + 8;
+    const size_t cap_chunks = (size_t)n / TAKE_SAH_CHUNK + cap_huge + 4;
+    DeviceBuffer huge_a, huge_b, med_a, med_b, chunks_a, chunks_b, state_a, state_b, chunk_cnt, chunk_off;
     CU(nodes.ensure((size_t)(2 * n) * sizeof(BNode)));
-    CU(big_a.ensure(cap_big * sizeof(SItem))); CU(big_b.ensure(cap_big * sizeof(SItem))); CU(small.ensure(cap_small * sizeof(SItem)));
-    int32_t *h_cnt = nullptr;   // pinned: {node_count, big_count, small_count, pad} read back after every level
-    CU(cudaMallocHost((void **)&h_cnt, 8 * sizeof(int32_t)));
+    CU(huge_a.ensure(cap_huge * sizeof(SItem))); CU(huge_b.ensure(cap_huge * sizeof(SItem)));
+    CU(med_a.ensure(cap_med * sizeof(SItem))); CU(med_b.ensure(cap_med * sizeof(SItem)));
+    CU(small.ensure(cap_small * sizeof(SItem)));
+    CU(chunks_a.ensure(cap_chunks * sizeof(SChunk))); CU(chunks_b.ensure(cap_chunks * sizeof(SChunk)));
+    CU(state_a.ensure(cap_huge * sizeof(HugeState))); CU(state_b.ensure(cap_huge * sizeof(HugeState)));
+    CU(chunk_cnt.ensure(cap_chunks * 3 * TAKE_SAH_BINS * sizeof(uint32_t))); CU(chunk_off.ensure(cap_chunks * sizeof(int32_t)));
+    int32_t *h_cnt = nullptr;   // pinned: {node, huge, medium, small, chunk counts} read back after every level
+    CU(cudaMallocHost((void **)&h_cnt, 16 * sizeof(int32_t)));
     struct HostFree { void *p; ~HostFree() { cudaFreeHost(p); } } host_free{h_cnt};
-    k_sah_root<<<1, 32, 0, st>>>((int32_t)n, g, nodes.as<BNode>(), big_a.as<SItem>(), small.as<SItem>());
+    SItem *hcur = huge_a.as<SItem>(), *hnext = huge_b.as<SItem>(), *mcur = med_a.as<SItem>(), *mnext = med_b.as<SItem>();
+    SChunk *ccur = chunks_a.as<SChunk>(), *cnext = chunks_b.as<SChunk>();
+    HugeState *scur = state_a.as<HugeState>(), *snext = state_b.as<HugeState>();
+    k_sah_root<<<1, 32, 0, st>>>((int32_t)n, g, nodes.as<BNode>(), hcur, mcur, small.as<SItem>(), ccur, scur);
     CU(cudaGetLastError());
     float4 *cur_lo = lo_a.as<float4>(), *cur_hi = hi_a.as<float4>(), *nxt_lo = lo_b.as<float4>(), *nxt_hi = hi_b.as<float4>();
-    SItem *bcur = big_a.as<SItem>(), *bnext = big_b.as<SItem>();
     auto read_counts = [&]() -> int {
-        CU(cudaMemcpyAsync(h_cnt, &g->node_count, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h_cnt, &g->node_count, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
+        if (h_cnt[0] < 1 || h_cnt[0] > 2 * n || h_cnt[1] < 0 || (size_t)h_cnt[1] > cap_huge || h_cnt[2] < 0 || (size_t)h_cnt[2] > cap_med ||
+            h_cnt[3] < 0 || (size_t)h_cnt[3] > cap_small || h_cnt[4] < 0 || (size_t)h_cnt[4] > cap_chunks)
+            return fail(TAKE_E_CUDA, "device BVH build: inconsistent level");
+        return TAKE_OK;
+    };
+    auto run_small = [&](int32_t n_small, const float4 *src_lo, const float4 *src_hi) -> int {
+        if (n_small <= 0) return TAKE_OK;
+        k_sah_small<<<(unsigned)((n_small + 63) / 64), 64, 0, st>>>(small.as<SItem>(), n_small, src_lo, src_hi, lo_f.as<float4>(), hi_f.as<float4>(),
+                                                                  nodes.as<BNode>(), g, max_leaf, c_trav, c_isect);
+        CU(cudaGetLastError());
         return TAKE_OK;
     };
     if (int rc = read_counts()) return rc;
+    if (int rc = run_small(h_cnt[3], cur_lo, cur_hi)) return rc;   // the whole scene is one small node
+    int32_t n_huge = h_cnt[1], n_med = h_cnt[2], n_chunks = h_cnt[4];
     int levels = 0;
-    if (h_cnt[2] > 0) {   // the whole scene is one small node
-        k_sah_small<<<1, 32, 0, st>>>(small.as<SItem>(), h_cnt[2], cur_lo, cur_hi, lo_f.as<float4>(), hi_f.as<float4>(), nodes.as<BNode>(), g,
-                                      max_leaf, c_trav, c_isect);
-        CU(cudaGetLastError());
-    }
-    int32_t n_big = h_cnt[1];
-    while (n_big > 0) {
-        if ((size_t)n_big > cap_big) return fail(TAKE_E_CUDA, "device BVH build: work queue overflow");
-        CU(cudaMemsetAsync(&g->big_count, 0, 2 * sizeof(int32_t), st));
-        k_sah_split<<<(unsigned)n_big, TAKE_DB_BLOCK, 0, st>>>(bcur, cur_lo, cur_hi, nxt_lo, nxt_hi, nodes.as<BNode>(), g, bnext, small.as<SItem>());
-        CU(cudaGetLastError());
-        if (int rc = read_counts()) return rc;
-        const int32_t n_small = h_cnt[2];
-        if (h_cnt[1] < 0 || n_small < 0 || (size_t)n_small > cap_small || h_cnt[0] > 2 * n) return fail(TAKE_E_CUDA, "device BVH build: inconsistent level");
-        if (n_small > 0) {
-            k_sah_small<<<(unsigned)((n_small + 63) / 64), 64, 0, st>>>(small.as<SItem>(), n_small, nxt_lo, nxt_hi, lo_f.as<float4>(), hi_f.as<float4>(),
-                                                                      nodes.as<BNode>(), g, max_leaf, c_trav, c_isect);
+    while (n_huge > 0 || n_med > 0) {
+        CU(cudaMemsetAsync(&g->huge_count, 0, 4 * sizeof(int32_t), st));
+        if (n_huge > 0) {
+            const int per = 3 * TAKE_SAH_BINS;
+            k_huge_clear<<<(unsigned)((n_huge * per + 127) / 128), 128, 0, st>>>(scur, n_huge);
+            k_huge_bin<<<(unsigned)n_chunks, TAKE_DB_BLOCK, 0, st>>>(hcur, ccur, cur_lo, cur_hi, scur, chunk_cnt.as<uint32_t>());
+            k_huge_choose<<<(unsigned)n_huge, TAKE_DB_BLOCK, 0, st>>>(hcur, scur, chunk_cnt.as<uint32_t>(), chunk_off.as<int32_t>());
+            k_huge_partition<<<(unsigned)n_chunks, TAKE_DB_BLOCK, 0, st>>>(hcur, ccur, cur_lo, cur_hi, nxt_lo, nxt_hi, scur, chunk_off.as<int32_t>());
+            k_huge_emit<<<(unsigned)((n_huge + 63) / 64), 64, 0, st>>>(hcur, n_huge, scur, nodes.as<BNode>(), g, hnext, mnext, small.as<SItem>(), cnext, snext);
             CU(cudaGetLastError());
         }
-        std::swap(cur_lo, nxt_lo); std::swap(cur_hi, nxt_hi); std::swap(bcur, bnext);
-        n_big = h_cnt[1];
+        if (n_med > 0) {
+            k_sah_split<<<(unsigned)n_med, TAKE_DB_BLOCK, 0, st>>>(mcur, cur_lo, cur_hi, nxt_lo, nxt_hi, nodes.as<BNode>(), g, hnext, mnext,
+                                                                   small.as<SItem>(), cnext, snext);
+            CU(cudaGetLastError());
+        }
+        if (int rc = read_counts()) return rc;
+        if (int rc = run_small(h_cnt[3], nxt_lo, nxt_hi)) return rc;
+        std::swap(cur_lo, nxt_lo); std::swap(cur_hi, nxt_hi);
+        std::swap(hcur, hnext); std::swap(mcur, mnext); std::swap(ccur, cnext); std::swap(scur, snext);
+        n_huge = h_cnt[1]; n_med = h_cnt[2]; n_chunks = h_cnt[4];
         if (++levels > 4096) return fail(TAKE_E_CUDA, "device BVH build: no progress");
     }
     k_leaf_prims<<<gb, TAKE_DB_BLOCK, 0, st>>>(n, lo_f.as<float4>(), s->leaf_prims.as<int32_t>());
@@ -752,7 +773,7 @@ static int device_build_fast_tree(TakeScene *s, int max_leaf, double &abs_max) {
         CU(cudaMemcpyAsync(items_a.p, &first_item, sizeof(first_item), cudaMemcpyHostToDevice, st));
         WorkItem *ia = items_a.as<WorkItem>(), *ib = items_b.as<WorkItem>();
         int32_t n_items = 1;
-        uint32_t *h32 = reinterpret_cast<uint32_t *>(h_cnt) + 4;
+        uint32_t *h32 = reinterpret_cast<uint32_t *>(h_cnt) + 8;
         while (n_items > 0) {
             const unsigned gi = (unsigned)((n_items + TAKE_DB_BLOCK - 1) / TAKE_DB_BLOCK);
             k_wide_kids<<<gi, TAKE_DB_BLOCK, 0, st>>>(n_items, ia, nodes.as<BNode>(), kids.as<Kids>(), icount.as<uint32_t>());
