@@ -61,7 +61,14 @@ enum { TAKE_PRIM_HAS_NORMALS = 1, TAKE_PRIM_HAS_UVS = 2, TAKE_PRIM_SPHERE = 4 };
 enum {
     TAKE_INTEGRATOR_MIS = 0,           /* path_tracing                :5-111  (what render.cpp:76 calls) */
     TAKE_INTEGRATOR_RAW = 1,           /* path_tracing_raw            :114-157 */
-    TAKE_INTEGRATOR_ONE_SAMPLE_MIS = 2 /* path_tracing_one_sample_MIS :161-271 */
+    TAKE_INTEGRATOR_ONE_SAMPLE_MIS = 2, /* path_tracing_one_sample_MIS :161-271 */
+    /* path_tracing_one_sample_MIS_power :274-380: one-sample MIS with the light picked in proportion to its power
+     * (luminance x area x pi, src/light.cpp:9-30) instead of uniformly -- what a scene with hundreds of unequal emitters
+     * wants (BASELINE config 4).  Dead code in the reference as shipped: nothing fills Scene::lights_power_cdf / _pmf.
+     * The tables are built here from the reference's own light_power() formula in the layout its readers expect (N + 1
+     * running sums from 0 to 1), and the integrator is pinned against the reference's own function driven with tables built
+     * the same way (oracle/ref_harness.cpp).  Not available on scenes with a sampled environment map. */
+    TAKE_INTEGRATOR_ONE_SAMPLE_MIS_POWER = 3
 };
 
 /* take_gpu_intersect flags */

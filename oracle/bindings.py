@@ -19,7 +19,7 @@ REF_SO = os.path.join(HERE, "_ref", "libtake_ref.so")
 REF_CLI = os.path.join(HERE, "_ref", "take_ref")
 ORACLE_SO = os.path.join(HERE, "libtake_oracle.so")
 
-INTEGRATORS = {"mis": 0, "raw": 1, "one_sample_mis": 2}
+INTEGRATORS = {"mis": 0, "raw": 1, "one_sample_mis": 2, "one_sample_mis_power": 3}
 
 
 def build(ref: bool = True):

@@ -35,6 +35,7 @@
 Vector3 path_tracing(const Scene &scene, const Ray &ray, std::mt19937 &rng);
 Vector3 path_tracing_raw(const Scene &scene, const Ray &ray, std::mt19937 &rng);
 Vector3 path_tracing_one_sample_MIS(const Scene &scene, const Ray &ray, std::mt19937 &rng);
+Vector3 path_tracing_one_sample_MIS_power(const Scene &scene, const Ray &ray, std::mt19937 &rng);
 
 namespace {
 
@@ -142,8 +143,29 @@ Integrator pick_integrator(int id) {
         case 0: return path_tracing;
         case 1: return path_tracing_raw;
         case 2: return path_tracing_one_sample_MIS;
+        case 3: return path_tracing_one_sample_MIS_power;
     }
     return nullptr;
+}
+
+// path_tracing_one_sample_MIS_power (path_tracing.h:274-380) picks lights through scene.lights_power_cdf / _pmf, which
+// nothing in the reference ever fills (sample_light_power asserts on the empty table, light.cpp:13): dead code as shipped.
+// The tables are built here, from the reference's own light_power() (light.cpp:25-30), in the only layout its readers accept
+// -- pmf[i] = power_i / total; cdf = the N + 1 running sums from 0 to exactly 1 that sample_light_power's upper_bound +
+// clamp walks (light.cpp:9-17).  Summation in light order, plain doubles: take_b200 and oracle/take_oracle.cpp build the same.
+void build_power_tables(Scene &sc) {
+    const size_t n = sc.lights.size();
+    if (sc.lights_power_cdf.size() == n + 1 || n == 0) return;
+    std::vector<Real> power(n);
+    Real total = 0;
+    for (size_t i = 0; i < n; ++i) { power[i] = light_power(sc, sc.lights[i]); total += power[i]; }
+    sc.lights_power_pmf.assign(n, Real(0));
+    sc.lights_power_cdf.assign(n + 1, Real(0));
+    for (size_t i = 0; i < n; ++i) {
+        sc.lights_power_pmf[i] = power[i] / total;
+        sc.lights_power_cdf[i + 1] = sc.lights_power_cdf[i] + sc.lights_power_pmf[i];
+    }
+    sc.lights_power_cdf[n] = 1;
 }
 
 // One path sample: pixel (x, y) in the reference's y-up loop coordinates (src/render.cpp:65-77).
@@ -413,6 +435,7 @@ int ref_render(void *h, int integrator, int max_depth, int64_t spp_begin, int64_
     Scene &sc = ((RefScene *)h)->scene;
     Integrator f = pick_integrator(integrator);
     if (!f) { g_error = "unknown integrator"; return -1; }
+    if (integrator == 3) build_power_tables(sc);
     sc.options.max_depth = max_depth;
     const Camera &cam = sc.camera;
     CameraBasis b = camera_basis(cam);
@@ -445,6 +468,7 @@ int ref_radiance_samples(void *h, int integrator, int max_depth, uint64_t seed, 
     Scene &sc = ((RefScene *)h)->scene;
     Integrator f = pick_integrator(integrator);
     if (!f) { g_error = "unknown integrator"; return -1; }
+    if (integrator == 3) build_power_tables(sc);
     sc.options.max_depth = max_depth;
     CameraBasis b = camera_basis(sc.camera);
     int nwords = stream_words_needed(max_depth);

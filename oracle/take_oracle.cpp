@@ -121,6 +121,9 @@ struct Scene {
     std::vector<double> env_rgb, env_marg, env_cond;  // marginal CDF [h+1], conditional CDFs [h][w+1]
     double env_total = 0;
     bool has_env() const { return env_w > 0; }
+    // tables of the power-sampling integrator (path_tracing.h:274-380): pmf[i] = light_power(i) / total, cdf = N + 1 running
+    // sums from 0 to exactly 1 -- the layout light.cpp:9-23 reads; nothing in the reference fills them (ref_harness.cpp does)
+    std::vector<double> power_pmf, power_cdf;
     // number of entries of the uniform light pick: the scene's lights plus, when it is sampled, the environment
     size_t pick_count() const { return lights.size() + ((has_env() && env_sample) ? 1 : 0); }
 };
@@ -935,12 +938,91 @@ V3 path_tracing_one_sample_mis(const Scene &sc, Ray r, Rng &rng, int max_depth, 
     return radiance;
 }
 
+// ---- src/integrator/path_tracing.h:274-380: one-sample MIS with lights picked by power ------------------------------
+// Dead code in the reference as shipped (its tables are never filled); pinned through oracle/ref_harness.cpp, which builds
+// the tables the reference's readers expect -- the same way Scene::build_power_tables does here.
+inline int sample_light_power(const Scene &sc, Rng &rng) {  // light.cpp:9-17
+    const double u = rng.next();
+    const int size = (int)sc.power_cdf.size() - 1;
+    const double *ptr = std::upper_bound(sc.power_cdf.data(), sc.power_cdf.data() + size + 1, u);
+    return std::min(std::max((int)(ptr - sc.power_cdf.data() - 1), 0), size - 1);
+}
+
+V3 path_tracing_one_sample_mis_power(const Scene &sc, Ray r, Rng &rng, int max_depth, Counters &cn) {
+    Isect v;
+    if (!scene_intersect(sc, r, v, cn)) return sc.background;                                   // :277
+    V3 radiance = {0, 0, 0}, throughput = {1, 1, 1};
+    for (int i = 0; i <= max_depth; ++i) {
+        if (v.light != -1 && sc.lights[v.light].kind == TAKE_LIGHT_AREA) {                       // :284-291
+            radiance = add(radiance, mulv(throughput, intensity(sc.lights[v.light])));
+            break;
+        }
+        cn.shaded++;
+        V3 dir_in = neg(r.d);
+        const TakeMaterialDesc &m = sc.mats[v.material];
+        bool spec = is_specular(m);
+        if (sc.lights.size() > 0 && !spec && rng.next() <= 0.5) {                                 // :299
+            int light_id = sample_light_power(sc, rng);
+            const TakeLightDesc &l = sc.lights[light_id];
+            if (l.kind == TAKE_LIGHT_AREA) {
+                LightSample lp = sample_on_prim(sc, l.prim_id, v.pos, rng);
+                double d = length(sub(lp.pos, v.pos));
+                V3 light_dir = normalize(sub(lp.pos, v.pos));
+                double lpdf = light_pdf_area(sc, light_id, lp.pos, v.pos) * (d * d) * sc.power_pmf[light_id] /
+                              (fmax(dot(neg(lp.n), light_dir), 0.0));                             // :309
+                if (lpdf <= 0) break;
+                double bpdf = bsdf_pdf(m, dir_in, light_dir, v);
+                if (bpdf <= 0) break;
+                V3 FG = bsdf_eval(sc, m, dir_in, light_dir, 0.0, v);
+                r = {v.pos, light_dir, EPS, INFINITY};
+                Isect nv;
+                if (!scene_intersect(sc, r, nv, cn)) {                                            // :326-330 (checked here, unlike :220)
+                    radiance = add(radiance, mulv(throughput, sc.background));
+                    break;
+                }
+                v = nv;
+                if (v.light == -1) break;                                                         // :332-334
+                throughput = mulv(throughput, divs(FG, 0.5 * lpdf + 0.5 * bpdf));
+            }
+        } else {
+            V3 rec_dir;
+            double rec_pdf;
+            if (!sample_bsdf(m, dir_in, v, rng, rec_dir, rec_pdf)) break;
+            V3 FG = bsdf_eval(sc, m, dir_in, rec_dir, rec_pdf, v);
+            V3 dir_out = normalize(rec_dir);
+            double bpdf = rec_pdf;
+            if (bpdf <= 0) break;
+            r = {v.pos, dir_out, EPS, INFINITY};
+            Isect nv;
+            bool hit = scene_intersect(sc, r, nv, cn);
+            double pdf = (sc.lights.empty() || spec) ? bpdf : 0.5 * bpdf;
+            if (!hit) {
+                throughput = mulv(throughput, divs(FG, pdf));
+                radiance = add(radiance, mulv(throughput, sc.background));
+                break;
+            }
+            if (!spec && nv.light != -1) {                                                        // :363-373
+                double d = length(sub(nv.pos, v.pos));
+                V3 light_dir = normalize(sub(nv.pos, v.pos));
+                double lpdf = light_pdf_area(sc, nv.light, nv.pos, v.pos) * (d * d) * sc.power_pmf[nv.light] /
+                              fmax(dot(neg(nv.gn), light_dir), 0.0);
+                if (lpdf <= 0) break;
+                pdf += 0.5 * lpdf;
+            }
+            throughput = mulv(throughput, divs(FG, pdf));
+            v = nv;
+        }
+    }
+    return radiance;
+}
+
 typedef V3 (*Integrator)(const Scene &, Ray, Rng &, int, Counters &);
 Integrator pick(int id) {
     switch (id) {
         case TAKE_INTEGRATOR_MIS: return path_tracing;
         case TAKE_INTEGRATOR_RAW: return path_tracing_raw;
         case TAKE_INTEGRATOR_ONE_SAMPLE_MIS: return path_tracing_one_sample_mis;
+        case TAKE_INTEGRATOR_ONE_SAMPLE_MIS_POWER: return path_tracing_one_sample_mis_power;
     }
     return nullptr;
 }
@@ -996,6 +1078,28 @@ inline Ray make_ray(const double *r) { return {{r[0], r[1], r[2]}, {r[3], r[4], 
 
 }  // namespace
 
+// light_power (light.cpp:25-30) per light, summed in light order
+void build_power_tables(Scene &sc) {
+    const size_t n = sc.lights.size();
+    if (n == 0) return;
+    std::vector<double> power(n);
+    double total = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const TakeLightDesc &l = sc.lights[i];
+        power[i] = l.kind == TAKE_LIGHT_AREA ? (l.intensity[0] * 0.212671 + l.intensity[1] * 0.715160 + l.intensity[2] * 0.072169) *
+                                                   prim_area(sc, l.prim_id) * PI
+                                             : 0.0;
+        total += power[i];
+    }
+    sc.power_pmf.assign(n, 0.0);
+    sc.power_cdf.assign(n + 1, 0.0);
+    for (size_t i = 0; i < n; ++i) {
+        sc.power_pmf[i] = power[i] / total;
+        sc.power_cdf[i + 1] = sc.power_cdf[i] + sc.power_pmf[i];
+    }
+    sc.power_cdf[n] = 1;
+}
+
 extern "C" {
 
 void *oracle_scene_create(const TakeSceneDesc *d) {
@@ -1027,6 +1131,7 @@ void *oracle_scene_create(const TakeSceneDesc *d) {
         build_env_tables(*sc);
     }
     build_bvh(*sc);
+    build_power_tables(*sc);
     return sc;
 }
 

@@ -21,7 +21,7 @@ from .sceneio import FlatScene, TakeSceneDesc
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TAKE_GPU_LIB") or os.path.join(_HERE, "libtake_gpu.so")   # TAKE_GPU_LIB: A/B builds while tuning
 
-INTEGRATORS = {"mis": 0, "raw": 1, "one_sample_mis": 2}
+INTEGRATORS = {"mis": 0, "raw": 1, "one_sample_mis": 2, "one_sample_mis_power": 3}
 ISECT_FAST, ISECT_EXACT = 0, 1
 RENDER_NO_SORT, RENDER_STAGE_TIMES, RENDER_COUNT_TESTS = 1, 2, 4
 

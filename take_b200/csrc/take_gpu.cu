@@ -80,7 +80,7 @@ struct TakeScene {
     // scene storage
     DeviceBuffer env_rgb, env_marg, env_cond;
     DeviceBuffer nodes, wide_nodes, tris, ref_nodes, positions, normals, uvs, indices, prim_material, prim_light, dfs_rank, prim_flags,
-        prim_mtype, spheres, materials, lights, textures, shade_recs, light_recs;
+        prim_mtype, spheres, materials, lights, textures, shade_recs, light_recs, light_pmf, light_cdf;
     std::vector<DeviceBuffer *> tex_data;
     DeviceBuffer exr_packed;
     // wave storage
@@ -117,6 +117,7 @@ struct TakeScene {
     double ref_t0 = 0;
     DeviceBuffer leaf_prims;
     bool device_built = false;
+    bool power_ok = false;   // the scene has emitters with non-zero total power (the power-sampling integrator needs them)
     double create_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // validate, upload, prim boxes (host), device build, records, total, -, -
     // diagnostics
     double build_ms_ref = 0, build_ms_fast = 0;
@@ -456,7 +457,8 @@ int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, d
 #define TAKE_SHADE(I) (env ? k_shade<I, true><<<shade_blocks, 128, 0, st>>>(s->dev, w, b) : k_shade<I, false><<<shade_blocks, 128, 0, st>>>(s->dev, w, b))
         if (o->integrator == TAKE_INTEGRATOR_MIS) TAKE_SHADE(TAKE_INTEGRATOR_MIS);
         else if (o->integrator == TAKE_INTEGRATOR_RAW) TAKE_SHADE(TAKE_INTEGRATOR_RAW);
-        else TAKE_SHADE(TAKE_INTEGRATOR_ONE_SAMPLE_MIS);
+        else if (o->integrator == TAKE_INTEGRATOR_ONE_SAMPLE_MIS) TAKE_SHADE(TAKE_INTEGRATOR_ONE_SAMPLE_MIS);
+        else TAKE_SHADE(TAKE_INTEGRATOR_ONE_SAMPLE_MIS_POWER);
 #undef TAKE_SHADE
         tm.end();
         launches += 2;
@@ -511,7 +513,7 @@ void fill_wave_ptrs(TakeScene *s, Wave &w, const TakeRenderOpts *o, int set = 0)
     w.max_depth = o->max_depth;
     w.sort_enabled = (o->flags & TAKE_RENDER_NO_SORT) ? 0 : 1;
     const int n_pick = s->dev.env_light ? s->dev.pick_count : s->dev.num_lights;
-    w.sort_branch = (w.sort_enabled && o->integrator == TAKE_INTEGRATOR_ONE_SAMPLE_MIS && n_pick > 0 &&
+    w.sort_branch = (w.sort_enabled && (o->integrator == TAKE_INTEGRATOR_ONE_SAMPLE_MIS || o->integrator == TAKE_INTEGRATOR_ONE_SAMPLE_MIS_POWER) && n_pick > 0 &&
                      !env_int("TAKE_NO_SORT_BRANCH", 0)) ? 1 : 0;
     w.seed = o->seed;
 #if TAKE_EXPERIMENTAL
@@ -551,8 +553,13 @@ void apply_l2_policy(TakeScene *s, cudaStream_t st) {
 
 int check_opts(const TakeScene *s, const TakeRenderOpts *o) {
     if (!s || !o) return fail(TAKE_E_INVALID, "null argument");
-    if (o->integrator < TAKE_INTEGRATOR_MIS || o->integrator > TAKE_INTEGRATOR_ONE_SAMPLE_MIS)
+    if (o->integrator < TAKE_INTEGRATOR_MIS || o->integrator > TAKE_INTEGRATOR_ONE_SAMPLE_MIS_POWER)
         return fail(TAKE_E_INVALID, "unknown integrator");
+    if (o->integrator == TAKE_INTEGRATOR_ONE_SAMPLE_MIS_POWER) {
+        if (s->dev.env_light) return fail(TAKE_E_INVALID, "the power-sampling integrator does not take a sampled environment map");
+        if (s->dev.num_lights > 0 && !s->power_ok)   // (the reference would divide by a zero total power)
+            return fail(TAKE_E_INVALID, "the power-sampling integrator needs emitters with non-zero power");
+    }
     // the reference accepts any -max_depth (render.cpp:14-19); every pass of a wave costs four (mostly empty) launches and a
     // 256-byte counter block, so the bound here is only a sanity limit
     if (o->max_depth < -1 || o->max_depth > TAKE_MAX_DEPTH)
@@ -894,6 +901,37 @@ static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild *hb, 
     if ((rc = upload(s->spheres, d->spheres, (size_t)d->num_spheres * 4, st))) return rc;
     if ((rc = upload(s->materials, d->materials, (size_t)d->num_materials, st))) return rc;
     if ((rc = upload(s->lights, d->lights, (size_t)d->num_lights, st))) return rc;
+    {   // tables of the power-proportional light pick: light_power (src/light.cpp:25-30) = luminance x get_area x pi per light,
+        // summed in light order; pmf = power / total; cdf = the N + 1 running sums from 0 to exactly 1 that sample_light_power
+        // walks (light.cpp:9-17).  The reference never fills these (dead code there); oracle/ref_harness.cpp builds them the
+        // same way for the pin.
+        const size_t nl = (size_t)d->num_lights;
+        std::vector<double> pmf(nl, 0.0), cdf(nl + 1, 0.0), power(nl, 0.0);
+        double total = 0;
+        for (size_t i = 0; i < nl; ++i) {
+            const TakeLightDesc &l = d->lights[i];
+            if (l.kind == TAKE_LIGHT_AREA) {
+                const int32_t *id = d->indices + 3 * (int64_t)l.prim_id;
+                double area;
+                if (d->prim_flags[l.prim_id] & TAKE_PRIM_SPHERE) {   // get_area_op, src/shape.cpp:171-184
+                    const double r = d->spheres[4 * (int64_t)id[0] + 3];
+                    area = 4 * TAKE_PI * r * r;
+                } else {
+                    const double *p0 = d->positions + 3 * (int64_t)id[0], *p1 = d->positions + 3 * (int64_t)id[1], *p2 = d->positions + 3 * (int64_t)id[2];
+                    const double a[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]}, b[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
+                    const double c[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+                    area = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]) / 2;
+                }
+                power[i] = (l.intensity[0] * 0.212671 + l.intensity[1] * 0.715160 + l.intensity[2] * 0.072169) * area * TAKE_PI;
+            }
+            total += power[i];
+        }
+        for (size_t i = 0; i < nl; ++i) { pmf[i] = power[i] / total; cdf[i + 1] = cdf[i] + pmf[i]; }
+        if (nl) cdf[nl] = 1;
+        if ((rc = upload(s->light_pmf, pmf.data(), pmf.size(), st))) return rc;
+        if ((rc = upload(s->light_cdf, cdf.data(), cdf.size(), st))) return rc;
+        s->power_ok = nl > 0 && total > 0 && std::isfinite(total);
+    }
     std::vector<DevTexture> tex((size_t)d->num_textures);
     for (int i = 0; i < d->num_textures; ++i) {
         const TakeTextureDesc &t = d->textures[i];
@@ -946,6 +984,7 @@ static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild *hb, 
     v.lights = s->lights.as<TakeLightDesc>();
     v.textures = s->textures.as<DevTexture>();
     v.num_lights = d->num_lights; v.num_materials = d->num_materials;
+    v.light_pmf = s->light_pmf.as<double>(); v.light_cdf = s->light_cdf.as<double>();
     v.env_rgb = has_env ? s->env_rgb.as<double>() : nullptr;
     v.env_marg = has_env ? s->env_marg.as<double>() : nullptr;
     v.env_cond = has_env ? s->env_cond.as<double>() : nullptr;

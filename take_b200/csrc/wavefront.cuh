@@ -563,33 +563,60 @@ __device__ __forceinline__ void shade_raw(ShadeCtx &c, const RayRec &ray, const 
     c.depth += 1;
 }
 
-// One-sample MIS: src/integrator/path_tracing.h:161-271
-template <bool ENV>
+// light pdf with the light picked by power: get_light_pdf * d^2 * pmf / cos (path_tracing.h:309, :366)
+__device__ __forceinline__ bool nee_sample_power(const DevScene &sc, const TakeLightDesc &l, int light_id, const Isect &v, Rng &rng,
+                                                 D3 &light_dir, double &dist, double &lpdf) {
+    D3 lp, ln;
+    sample_on_light(sc, light_id, l.prim_id, v.pos, rng, lp, ln);
+    dist = length(sub(lp, v.pos));
+    light_dir = normalize(sub(lp, v.pos));
+    lpdf = light_pdf_area(sc, light_id, lp, v.pos) * (dist * dist) * sc.light_pmf[light_id] / (fmax(dot(neg(ln), light_dir), 0.0));
+    return !(lpdf <= 0);
+}
+__device__ __forceinline__ bool hit_light_pdf_power(const DevScene &sc, const Isect &nv, D3 prev_pos, double &lpdf) {
+    double d = length(sub(nv.pos, prev_pos));
+    D3 light_dir = normalize(sub(nv.pos, prev_pos));
+    lpdf = light_pdf_area(sc, nv.light, nv.pos, prev_pos) * (d * d) * sc.light_pmf[nv.light] / fmax(dot(neg(nv.gn), light_dir), 0.0);
+    return !(lpdf <= 0);
+}
+
+// One-sample MIS: src/integrator/path_tracing.h:161-271.  POWER = true is its sibling that picks the light in proportion to its
+// power, path_tracing_one_sample_MIS_power (:274-380): same structure; the light comes from the power CDF (light.cpp:9-17),
+// the pmf stands where 1 / N stood, and the light-aimed ray is checked on arrival -- a miss adds the background, a
+// non-emissive hit ends the path, and only then is the throughput updated (:326-335).
+template <bool ENV, bool POWER>
 __device__ __forceinline__ void shade_one_sample(ShadeCtx &c, const RayRec &ray, const HitRec &hit, const PathRec &path, const PendRec &pend) {
     const DevScene &sc = c.sc;
     const D3 o = mk3(ray.ox, ray.oy, ray.oz), d = mk3(ray.dx, ray.dy, ray.dz);
-    const int nl = ENV ? sc.pick_count : sc.num_lights;
+    const int nl = (ENV && !POWER) ? sc.pick_count : sc.num_lights;
     Isect v;
     if (path.flags == PEND_PRIMARY) {
         if (hit.prim < 0) { c.rad = miss_rad<ENV>(sc, d); return; }
         fill_isect<ENV>(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
     } else if (path.flags & PEND_LIGHT) {
-        if (ENV && hit.prim < 0 && (path.flags & PEND_ENV)) {  // EXTENSION: reached the environment we aimed at
-            c.rad = add(c.rad, mulv(c.thr, env_radiance(sc, d)));
-            return;
+        if (POWER) {
+            if (hit.prim < 0) { c.rad = add(c.rad, mulv(c.thr, miss_rad<ENV>(sc, d))); return; }   // :326-330
+            fill_isect<ENV>(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
+            if (v.light == -1) return;                                                              // :332-334
+            c.thr = mulv(c.thr, divs(mk3(pend.fg[0], pend.fg[1], pend.fg[2]), pend.bpdf));          // :335 (bpdf slot: 0.5 lpdf + 0.5 bpdf)
+        } else {
+            if (ENV && hit.prim < 0 && (path.flags & PEND_ENV)) {  // EXTENSION: reached the environment we aimed at
+                c.rad = add(c.rad, mulv(c.thr, env_radiance(sc, d)));
+                return;
+            }
+            if (hit.prim < 0) {
+                // the reference dereferences an empty optional here (:220, undefined behaviour): terminate and count
+                atomicAdd(&c.w.totals->miss_after_light_sample, 1ULL);
+                return;
+            }
+            fill_isect<ENV>(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
         }
-        if (hit.prim < 0) {
-            // the reference dereferences an empty optional here (:220, undefined behaviour): terminate and count
-            atomicAdd(&c.w.totals->miss_after_light_sample, 1ULL);
-            return;
-        }
-        fill_isect<ENV>(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
     } else {
         const D3 FG = mk3(pend.fg[0], pend.fg[1], pend.fg[2]);
         const bool spec = (path.flags & PEND_SPECULAR) != 0;
         double pdf = (nl == 0 || spec) ? pend.bpdf : 0.5 * pend.bpdf;  // :245
         if (hit.prim < 0) {  // :247-252
-            if (ENV && sc.env_light && !spec) pdf += 0.5 * (env_pdf(sc, d) / nl);  // EXTENSION: mixture pdf, as :255-265 for emitters
+            if (ENV && !POWER && sc.env_light && !spec) pdf += 0.5 * (env_pdf(sc, d) / nl);  // EXTENSION: mixture pdf, as :255-265 for emitters
             c.thr = mulv(c.thr, divs(FG, pdf));
             c.rad = add(c.rad, mulv(c.thr, miss_rad<ENV>(sc, d)));
             return;
@@ -597,7 +624,7 @@ __device__ __forceinline__ void shade_one_sample(ShadeCtx &c, const RayRec &ray,
         fill_isect<ENV>(sc, o, d, hit.prim, hit.t, hit.u, hit.v, v);
         if (!spec && v.light != -1) {  // :253-265
             double lpdf;
-            if (!hit_light_pdf(sc, v, o, lpdf)) return;
+            if (!(POWER ? hit_light_pdf_power(sc, v, o, lpdf) : hit_light_pdf(sc, v, o, lpdf))) return;
             pdf += 0.5 * lpdf;
         }
         c.thr = mulv(c.thr, divs(FG, pdf));
@@ -613,8 +640,14 @@ __device__ __forceinline__ void shade_one_sample(ShadeCtx &c, const RayRec &ray,
         const bool spec = is_specular(m.type);
         c.org = v.pos;
         if (nl > 0 && !spec && c.rng.next() <= 0.5) {  // :187
-            const int light_id = (int)floor(c.rng.next() * nl);
-            if (ENV && sc.env_light && light_id == sc.num_lights) {  // EXTENSION: the environment as a light
+            int light_id;
+            if (POWER) {   // sample_light_power, light.cpp:9-17
+                const double u = c.rng.next();
+                light_id = min(max(upper_bound_idx(sc.light_cdf, nl + 1, u) - 1, 0), nl - 1);
+            } else {
+                light_id = (int)floor(c.rng.next() * nl);
+            }
+            if (ENV && !POWER && sc.env_light && light_id == sc.num_lights) {  // EXTENSION: the environment as a light
                 const double u1 = c.rng.next();
                 const double u2 = c.rng.next();
                 D3 light_dir;
@@ -638,14 +671,19 @@ __device__ __forceinline__ void shade_one_sample(ShadeCtx &c, const RayRec &ray,
             if (l.kind != TAKE_LIGHT_AREA) continue;  // a point light: the iteration does nothing (:190)
             D3 light_dir;
             double dist, lpdf;
-            if (!nee_sample(sc, l, light_id, v, c.rng, light_dir, dist, lpdf)) return;
+            if (!(POWER ? nee_sample_power(sc, l, light_id, v, c.rng, light_dir, dist, lpdf) : nee_sample(sc, l, light_id, v, c.rng, light_dir, dist, lpdf)))
+                return;
             const double bpdf = bsdf_pdf(m, dir_in, light_dir, v);
             if (bpdf <= 0) return;
             D3 FG = bsdf_eval(sc, m, dir_in, light_dir, 0.0, v);
-            c.thr = mulv(c.thr, divs(FG, 0.5 * lpdf + 0.5 * bpdf));  // :225
+            if (POWER) {
+                c.pend_pdf = 0.5 * lpdf + 0.5 * bpdf;   // applied when the ray has arrived at an emitter (:335)
+            } else {
+                c.thr = mulv(c.thr, divs(FG, 0.5 * lpdf + 0.5 * bpdf));  // :225
+                c.pend_pdf = bpdf;
+            }
             c.ext_dir = light_dir;
             c.pend_fg = FG;
-            c.pend_pdf = bpdf;
             c.pend_flags = PEND_LIGHT;
             c.emit_extend = true;
             c.depth += 1;
@@ -740,7 +778,9 @@ __global__ void __launch_bounds__(128, TAKE_SHADE_MIN_BLOCKS) k_shade(DevScene s
                 else { ray = w.ray[slot]; path = w.path[slot]; }
 #endif
 #if TAKE_SHADE_EARLY < 2
-                if (!primary && INTEGRATOR != TAKE_INTEGRATOR_RAW && (path.flags & PEND_BSDF)) pend = w.pend[slot];
+                if (!primary && INTEGRATOR != TAKE_INTEGRATOR_RAW &&
+                    ((path.flags & PEND_BSDF) || (INTEGRATOR == TAKE_INTEGRATOR_ONE_SAMPLE_MIS_POWER && (path.flags & PEND_LIGHT))))
+                    pend = w.pend[slot];
 #endif
                 uint32_t pixel;
                 uint64_t sample;
@@ -756,7 +796,8 @@ __global__ void __launch_bounds__(128, TAKE_SHADE_MIN_BLOCKS) k_shade(DevScene s
                 c.org = mk3(ray.ox, ray.oy, ray.oz);
                 if (INTEGRATOR == TAKE_INTEGRATOR_MIS) shade_mis<ENV>(c, ray, hit, path, pend);
                 else if (INTEGRATOR == TAKE_INTEGRATOR_RAW) shade_raw<ENV>(c, ray, hit, path, pend);
-                else shade_one_sample<ENV>(c, ray, hit, path, pend);
+                else if (INTEGRATOR == TAKE_INTEGRATOR_ONE_SAMPLE_MIS) shade_one_sample<ENV, false>(c, ray, hit, path, pend);
+                else shade_one_sample<ENV, true>(c, ray, hit, path, pend);
                 emit_extend = c.emit_extend;
                 emit_shadow = c.emit_shadow;
                 shaded = c.shaded;
@@ -774,7 +815,8 @@ __global__ void __launch_bounds__(128, TAKE_SHADE_MIN_BLOCKS) k_shade(DevScene s
                     r.dx = c.ext_dir.x; r.dy = c.ext_dir.y; r.dz = c.ext_dir.z;
                     r.tmax = INFINITY;
                     // the coin of the vertex this ray will reach is the stream's next draw (see TAKE_KEY_BITS)
-                    r.aux0 = (INTEGRATOR == TAKE_INTEGRATOR_ONE_SAMPLE_MIS && w.sort_branch && emit_extend) ? peek_branch(c.rng) : 0;
+                    r.aux0 = ((INTEGRATOR == TAKE_INTEGRATOR_ONE_SAMPLE_MIS || INTEGRATOR == TAKE_INTEGRATOR_ONE_SAMPLE_MIS_POWER) && w.sort_branch &&
+                              emit_extend) ? peek_branch(c.rng) : 0;
                     r.aux1 = 0;
                     w.ray[slot] = r;
                 }

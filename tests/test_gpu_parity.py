@@ -110,7 +110,7 @@ def test_occluded(pair):
     assert np.array_equal(gs.occluded(seg), sc.occluded(seg))
 
 
-@pytest.mark.parametrize("integrator", ["mis", "raw", "one_sample_mis"])
+@pytest.mark.parametrize("integrator", ["mis", "raw", "one_sample_mis", "one_sample_mis_power"])
 def test_per_sample_radiance(pair, integrator):
     name, flat, gs, sc = pair
     H, W = flat.height, flat.width
@@ -127,7 +127,7 @@ def test_per_sample_radiance(pair, integrator):
         assert (err > REL).mean() <= 1e-3, (name, integrator, float(err.max()))
 
 
-@pytest.mark.parametrize("integrator", ["mis", "raw", "one_sample_mis"])
+@pytest.mark.parametrize("integrator", ["mis", "raw", "one_sample_mis", "one_sample_mis_power"])
 def test_image_sums_same_streams(pair, integrator):
     name, flat, gs, sc = pair
     for max_depth, lo, hi in ((5, 0, 3), (0, 2, 4), (-1, 0, 1)):
@@ -143,7 +143,7 @@ def test_image_sums_same_streams(pair, integrator):
         assert st["samples"] == flat.width * flat.height * (hi - lo)
 
 
-@pytest.mark.parametrize("integrator", ["mis", "raw", "one_sample_mis"])
+@pytest.mark.parametrize("integrator", ["mis", "raw", "one_sample_mis", "one_sample_mis_power"])
 def test_statistical_gate_independent_seeds(pair, integrator):
     """The north star's image gate, with DIFFERENT seeds on the two sides (independent estimates), calibrated as in
     SURVEY.md 8(c), for each of the three integrators (parity is per integrator: they truncate paths differently,
