@@ -102,7 +102,7 @@ struct TakeScene {
     cudaEvent_t ev_acc[2] = {nullptr, nullptr}, ev_begin = nullptr;
     int64_t wave_capacity = 0;
     int wave_sets = 0, wave_passes = 0;
-    int blocks_extend = 0, blocks_shadow = 0, blocks_isect = 0, blocks_occl = 0;
+    int blocks_extend = 0, blocks_shadow = 0, blocks_isect = 0, blocks_occl = 0, blocks_extend_primary = 0;
     int blocks_extend2 = 0, blocks_shadow2 = 0, blocks_isect2 = 0, blocks_occl2 = 0, blocks_extend2w = 0, blocks_shadow2w = 0;
     int persist_from_pass = 1, persist_shadow = 0;
     bool wide = true;   // 4-wide nodes (TAKE_BVH_WIDTH=4, default) or binary nodes (TAKE_BVH_WIDTH=2)
@@ -122,6 +122,7 @@ struct TakeScene {
     // diagnostics
     double build_ms_ref = 0, build_ms_fast = 0;
     int fast_depth = 0;
+    int wide_depth = 0;     // levels of the 4-wide tree (bounds the packet traversal's shared stack)
     double sah_cost = 0;
     int64_t num_fast_nodes = 0;
     ~TakeScene() {
@@ -428,6 +429,10 @@ int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, d
     for (int b = 0; b < n_passes; ++b) {
         tm.cur_pass = b;
         tm.begin(ST_EXTEND);
+        if (b == 0 && w.packet) {
+            if (count) k_extend_primary<true><<<s->blocks_extend_primary, 128, 0, st>>>(s->dev, w);
+            else k_extend_primary<false><<<s->blocks_extend_primary, 128, 0, st>>>(s->dev, w);
+        } else
 #if TAKE_EXPERIMENTAL
         if (s->traversal == 2) {
             if (count) k_extend2<true, false><<<s->blocks_extend2, 128, 0, st>>>(s->dev, w, b);
@@ -525,6 +530,9 @@ void fill_wave_ptrs(TakeScene *s, Wave &w, const TakeRenderOpts *o, int set = 0)
     // camera rays that miss are finished inside k_extend (the environment-map extension needs their direction in the
     // shade kernel, and the unsorted debugging mode walks every slot, so both keep the general path)
     w.miss_fast = (w.fused_primary && w.sort_enabled && s->dev.env_rgb == nullptr && !env_int("TAKE_NO_MISS_FAST", 0)) ? 1 : 0;
+    // camera rays as warp packets (traverse.cuh: trace_packet4): needs the 4-wide tree and a tree shallow enough for the shared
+    // per-warp stack; TAKE_PACKET=0 keeps one ray per thread in pass 0 (A/B runs, and the test that both give the same image)
+    w.packet = (w.fused_primary && s->wide && 3 * s->wide_depth + 1 <= TAKE_PACKET_STACK && env_int("TAKE_PACKET", 1)) ? 1 : 0;
 }
 
 // Keep the 4-wide tree resident in L2: the wavefront kernels stream gigabytes of per-path records through the cache
@@ -677,7 +685,7 @@ static int device_build_fast_tree(TakeScene *s, int max_leaf, double &abs_max) {
         CU(s->wide_nodes.ensure(sizeof(WideNode)));
         CU(cudaMemcpyAsync(s->wide_nodes.p, wide_tmp.p, sizeof(WideNode), cudaMemcpyDeviceToDevice, st));
         CU(cudaStreamSynchronize(st));
-        s->fast_depth = 1; s->num_fast_nodes = 1;
+        s->fast_depth = s->wide_depth = 1; s->num_fast_nodes = 1;
         return TAKE_OK;
     }
     const unsigned gb = (unsigned)((n + TAKE_DB_BLOCK - 1) / TAKE_DB_BLOCK);
@@ -807,7 +815,7 @@ static int device_build_fast_tree(TakeScene *s, int max_leaf, double &abs_max) {
     CU(cudaMemcpyAsync(&hg, glob.p, sizeof(hg), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     memcpy(&abs_max, &hg.abs_max_bits, 8);
-    s->fast_depth = depth;
+    s->fast_depth = s->wide_depth = depth;
     s->num_fast_nodes = n_wide;
     return TAKE_OK;
 }
@@ -846,6 +854,7 @@ static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild *hb, 
         s->build_ms_ref = hb->ms_ref;
         s->build_ms_fast = hb->ms_fast;
         s->fast_depth = hb->fast.depth;
+        s->wide_depth = hb->fast.wide_depth;
         s->sah_cost = hb->fast.sah_cost;
         s->num_fast_nodes = (int64_t)hb->fast.nodes.size();
 #if TAKE_EXPERIMENTAL
@@ -1064,6 +1073,7 @@ static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild *hb, 
         return per_sm * s->sm_count;
     };
     s->blocks_extend = blocks_for((const void *)k_extend<false, true>);
+    s->blocks_extend_primary = blocks_for((const void *)k_extend_primary<false>);
     s->blocks_shadow = blocks_for((const void *)k_shadow<false, true>);
     s->blocks_isect = blocks_for((const void *)k_intersect_fast<false, true>);
     s->blocks_occl = blocks_for((const void *)k_intersect_fast<true, true>);

@@ -425,6 +425,120 @@ __device__ __forceinline__ void trace_fast4(const DevScene &sc, D3 o, D3 d, doub
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Packet traversal for camera rays: the 32 rays of a warp walk the tree TOGETHER.
+//
+// Pass 0 of a wave gives every warp the samples of one pixel (or of an 8x4 pixel tile): rays that differ by sub-pixel
+// jitter.  Traced one ray per thread they visit almost the same nodes, yet each lane keeps its own stack and its own node
+// pointer, the warp runs until its longest lane is done (21.7 of 32 lanes active per instruction in the ncu capture of
+// config 2) and every node is requested by up to 32 lanes.  Here the warp has ONE node pointer and ONE stack (in shared
+// memory): a node is loaded once (same address in all lanes: a broadcast), every lane tests the four children against its
+// own ray, a child is entered when ANY lane enters it, the children are ordered by the nearest entry distance over the
+// lanes (redux), and a stacked entry is dropped when it is beyond every lane's current hit.  Every lane therefore sees a
+// superset of the leaves its own traversal would have seen and applies the same FP64 leaf test and tie rule, whose
+// outcome does not depend on the visiting order: the result is bit-identical to trace_fast4.
+// `valid` = false marks a lane without a ray (it takes part in the warp-wide operations with an empty interval).
+// ---------------------------------------------------------------------------------------------------------
+#define TAKE_PACKET_STACK 64   // entries of the shared per-warp stack (3 per level of the 4-wide tree + 1; checked on the host)
+
+template <bool COUNT>
+__device__ __forceinline__ void trace_packet4(const DevScene &sc, D3 o, D3 d, double tmin, double tmax, bool valid, uint2 *wstack,
+                                              HitOut &out, TravCounters *cnt) {
+    out.prim = -1; out.rank = -1; out.t = 0; out.u = 0; out.v = 0;
+    if (sc.num_prims <= 0) return;
+    if (!valid) tmax = -1.0;   // empty interval: no box and no primitive can be hit
+    const float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
+    const float idx = safe_rcp((float)d.x), idy = safe_rcp((float)d.y), idz = safe_rcp((float)d.z);
+    const float delta = 1.9073486e-6f * fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fmaxf(fabsf(oz), sc.abs_max));  // 2^-19
+    const float olx = -(ox + delta) * idx, ohx = -(ox - delta) * idx;
+    const float oly = -(oy + delta) * idy, ohy = -(oy - delta) * idy;
+    const float olz = -(oz + delta) * idz, ohz = -(oz - delta) * idz;
+    const float tmin_f = __double2float_rd(tmin);
+    float tbest_f = __double2float_ru(tmax);
+    double best_t = tmax;
+    int sp = 0;          // warp-uniform
+    int32_t node = 0;    // warp-uniform
+    for (;;) {
+        while (node >= 0) {
+            const float4 *N = sc.wide_nodes + 8 * (int64_t)node;
+            const F8 nx = ldg_f8(N), ny = ldg_f8(N + 2), nz = ldg_f8(N + 4);
+            const float4 lox = nx.a, hix = nx.b, loy = ny.a, hiy = ny.b, loz = nz.a, hiz = nz.b;
+            const int4 ch = __ldg((const int4 *)(N + 6));
+            if (COUNT && valid) cnt->box += 4;
+            uint32_t key[4];
+#define TAKE_PACKET_CHILD(K, LX, HX, LY, HY, LZ, HZ, C)                                          \
+            {                                                                                      \
+                float a = fmaf(LX, idx, olx), b = fmaf(HX, idx, ohx);                              \
+                float tn = fminf(a, b), tf = fmaxf(a, b);                                          \
+                a = fmaf(LY, idy, oly); b = fmaf(HY, idy, ohy);                                    \
+                tn = fmaxf(tn, fminf(a, b)); tf = fminf(tf, fmaxf(a, b));                          \
+                a = fmaf(LZ, idz, olz); b = fmaf(HZ, idz, ohz);                                    \
+                tn = fmaxf(tn, fminf(a, b)); tf = fminf(tf, fmaxf(a, b));                          \
+                tn = fmaxf(tn, tmin_f); tf = fminf(tf, tbest_f);                                   \
+                const bool h = (tn <= tf * TAKE_SLACK) && (C != TAKE_WIDE_EMPTY);                  \
+                /* tn >= tmin > 0: the bit pattern orders like the value; nearest entry over the lanes that enter */ \
+                const uint32_t m = __reduce_min_sync(0xffffffffu, h ? (__float_as_uint(tn) & 0xfffffffcu) : 0xffffffffu); \
+                key[K] = m == 0xffffffffu ? m : (m | (uint32_t)K);                                 \
+            }
+            TAKE_PACKET_CHILD(0, lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x, ch.x)
+            TAKE_PACKET_CHILD(1, lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, ch.y)
+            TAKE_PACKET_CHILD(2, lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, ch.z)
+            TAKE_PACKET_CHILD(3, lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, ch.w)
+#undef TAKE_PACKET_CHILD
+            cswap(key[0], key[1]); cswap(key[2], key[3]); cswap(key[0], key[2]); cswap(key[1], key[3]); cswap(key[1], key[2]);
+#define TAKE_WIDE_PICK(KEY) (((KEY) & 2u) ? (((KEY) & 1u) ? ch.w : ch.z) : (((KEY) & 1u) ? ch.y : ch.x))
+            // (all lanes hold the same keys and store the same words to the same addresses)
+            if (key[3] != 0xffffffffu) wstack[sp++] = make_uint2((uint32_t)TAKE_WIDE_PICK(key[3]), key[3] & 0xfffffffcu);
+            if (key[2] != 0xffffffffu) wstack[sp++] = make_uint2((uint32_t)TAKE_WIDE_PICK(key[2]), key[2] & 0xfffffffcu);
+            if (key[1] != 0xffffffffu) wstack[sp++] = make_uint2((uint32_t)TAKE_WIDE_PICK(key[1]), key[1] & 0xfffffffcu);
+            __syncwarp();
+            if (key[0] != 0xffffffffu) {
+                node = TAKE_WIDE_PICK(key[0]);
+            } else {
+                for (;;) {
+                    if (sp == 0) return;
+                    const uint2 e = wstack[--sp];
+                    node = (int32_t)e.x;
+                    if (__any_sync(0xffffffffu, __uint_as_float(e.y) <= tbest_f * TAKE_SLACK)) break;
+                }
+            }
+#undef TAKE_WIDE_PICK
+        }
+        {
+            const int32_t code = ~node;
+            const int64_t first = code >> 3;
+            const int count = (code & 7) + 1;
+            for (int k = 0; k < count; ++k) {
+                const double2 *T = sc.tris + 6 * (first + k);
+                const D4 t01 = ldg_d4(T), t23 = ldg_d4(T + 2), t45 = ldg_d4(T + 4);
+                const double2 a0 = t01.a, a1 = t01.b, a2 = t23.a, a3 = t23.b, a4 = t45.a, a5 = t45.b;
+                if (COUNT && valid) cnt->tri += 1;
+                double t, bu = 0, bv = 0;
+                bool ok;
+                if (a5.y == 0.0)
+                    ok = hit_triangle(mk3(a0.x, a0.y, a1.x), mk3(a2.x, a2.y, a3.x), mk3(a4.x, a4.y, a5.x), o, d, tmin, best_t, t, bu, bv);
+                else
+                    ok = hit_sphere(mk3(a0.x, a0.y, a1.x), a3.y, o, d, tmin, best_t, t);
+                if (ok) {
+                    const long long bits = __double_as_longlong(a1.y);
+                    const int32_t prim = (int32_t)(bits & 0xffffffffLL), rank = (int32_t)(bits >> 32);
+                    if (t < best_t || out.prim < 0 || rank > out.rank) {
+                        out.prim = prim; out.rank = rank; out.t = t; out.u = bu; out.v = bv;
+                        best_t = t;
+                        tbest_f = __double2float_ru(t);
+                    }
+                }
+            }
+        }
+        for (;;) {
+            if (sp == 0) return;
+            const uint2 e = wstack[--sp];
+            node = (int32_t)e.x;
+            if (__any_sync(0xffffffffu, __uint_as_float(e.y) <= tbest_f * TAKE_SLACK)) break;
+        }
+    }
+}
+
 #if TAKE_EXPERIMENTAL
 // ---------------------------------------------------------------------------------------------------------
 // Speculative 4-wide traversal (warp-cooperative schedule, same results as trace_fast4).

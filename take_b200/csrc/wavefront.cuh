@@ -121,6 +121,7 @@ struct Wave {
     int32_t sort_branch;    // 1: the sort key carries the one-sample integrator's light/BSDF coin (RayRec.aux0)
     int32_t fused_primary;  // 1: no k_generate -- pass 0 of extend and shade compute the camera ray themselves
     int32_t miss_fast;      // 1: camera rays that leave the scene are finished by k_extend itself (see k_extend)
+    int32_t packet;         // 1: pass 0 runs k_extend_primary (the warp's camera rays traverse as a packet)
     int32_t tile_w;  // > 0: image width, pixels are enumerated in 8x4 tiles (one warp = one tile); 0: row-major
     uint64_t seed;
 };
@@ -286,6 +287,58 @@ struct WorkCursor {
 };
 
 // ---- extend: closest hit for every queued ray + histogram of the shading sort key ------------------------
+// What happens to a traced ray (shared by the per-thread kernel and the camera-ray packet kernel); called by whole warps.
+__device__ __forceinline__ void extend_finish(const DevScene &sc, const Wave &w, PassCounters &pc, int lane, bool valid, int slot, const HitOut &h,
+                                              int32_t branch, bool primary, bool miss_fast) {
+    uint32_t key = 0;
+    bool rec = false;  // this lane has a hit record for the sort
+    if (valid) {
+        if (miss_fast && h.prim < 0) {
+            // A camera ray that left the scene: the sample is the background colour (path_tracing.h:8, :117, :164 -- the same
+            // line of the other two integrators).  Finishing it here keeps it out of the sort and the shade pass --
+            // on an open scene most camera rays end this way, and streaming their records through two more kernels
+            // was the larger part of the pass-0 shade time.
+            // (only the radiance sector of the record: nothing reads the rest of a finished path)
+            int4 *ps = reinterpret_cast<int4 *>(w.path + slot);
+            __stcs(ps, make_int4(__double2loint(sc.background.x), __double2hiint(sc.background.x), __double2loint(sc.background.y),
+                                 __double2hiint(sc.background.y)));
+            __stcs(ps + 1, make_int4(__double2loint(sc.background.z), __double2hiint(sc.background.z), 2, 0));
+        } else {
+            rec = true;
+            if (primary && w.sort_branch) {  // the coin of the first vertex: draw number 2 of the sample's stream
+                Rng rng;
+                uint32_t pixel;
+                uint64_t sample;
+                slot_identity(w, slot, pixel, sample);
+                rng.seed = w.seed; rng.sample = sample; rng.pixel = pixel; rng.k = 2;
+                branch = peek_branch(rng);
+            }
+            key = sort_key(h.prim, sc.prim_mtype, branch);
+        }
+    }
+    // warp-aggregated histogram: lanes with the same key elect a leader that bumps the bin once
+    const unsigned vmask = __ballot_sync(0xffffffffu, rec);
+    if (rec) {
+        const unsigned peers = __match_any_sync(vmask, key);
+        const int leader = __ffs(peers) - 1;
+        uint32_t rbase = 0;
+        if (lane == leader) rbase = atomicAdd(&pc.bins[key], (uint32_t)__popc(peers));
+        rbase = __shfl_sync(peers, rbase, leader);
+        const uint32_t rank = rbase + __popc(peers & ((1u << lane) - 1u));
+        HitRec hr;
+        hr.prim = h.prim;
+        hr.keyrank = (key << TAKE_RANK_BITS) | rank;
+        hr.t = h.t; hr.u = h.u; hr.v = h.v;
+        st_stream(w.hit + slot, hr);
+    }
+    if (miss_fast && vmask) {  // list the surviving slots for the sort (one atomic per warp)
+        uint32_t qb = 0;
+        if (lane == __ffs(vmask) - 1) qb = atomicAdd(&pc.n_extend, (uint32_t)__popc(vmask));
+        qb = __shfl_sync(0xffffffffu, qb, __ffs(vmask) - 1);
+        if (rec) w.q_extend[0][qb + __popc(vmask & ((1u << lane) - 1u))] = slot;
+    }
+}
+
 template <bool COUNT, bool WIDE>
 __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_extend(DevScene sc, Wave w, int pass) {
     TAKE_DECLARE_STACK(st);
@@ -303,13 +356,11 @@ __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_extend(DevScene sc,
         const uint32_t i = base + lane;
         const bool valid = i < n;
         int slot = -1;
-        uint32_t key = 0;
+        int32_t branch = 0;
         HitOut h;
-        bool rec = false;  // this lane has a hit record for the sort
         if (valid) {
             D3 o, d;
             double tmax = INFINITY;
-            int32_t branch = 0;
             if (primary) {
                 slot = (int)i;
                 primary_ray(sc, w, slot, o, d);
@@ -320,50 +371,36 @@ __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_extend(DevScene sc,
                 branch = r.aux0;
             }
             trace_any<false, COUNT, WIDE>(sc, o, d, TAKE_EPS, tmax, st, h, &cnt);
-            if (miss_fast && h.prim < 0) {
-                // A camera ray that left the scene: the sample is the background colour (path_tracing.h:8, :117, :164 -- the same
-                // line of the other two integrators).  Finishing it here keeps it out of the sort and the shade pass --
-                // on an open scene most camera rays end this way, and streaming their records through two more kernels
-                // was the larger part of the pass-0 shade time.
-                // (only the radiance sector of the record: nothing reads the rest of a finished path)
-                int4 *ps = reinterpret_cast<int4 *>(w.path + slot);
-                __stcs(ps, make_int4(__double2loint(sc.background.x), __double2hiint(sc.background.x), __double2loint(sc.background.y),
-                                     __double2hiint(sc.background.y)));
-                __stcs(ps + 1, make_int4(__double2loint(sc.background.z), __double2hiint(sc.background.z), 2, 0));
-            } else {
-                rec = true;
-                if (primary && w.sort_branch) {  // the coin of the first vertex: draw number 2 of the sample's stream
-                    Rng rng;
-                    uint32_t pixel;
-                    uint64_t sample;
-                    slot_identity(w, slot, pixel, sample);
-                    rng.seed = w.seed; rng.sample = sample; rng.pixel = pixel; rng.k = 2;
-                    branch = peek_branch(rng);
-                }
-                key = sort_key(h.prim, sc.prim_mtype, branch);
-            }
         }
-        // warp-aggregated histogram: lanes with the same key elect a leader that bumps the bin once
-        const unsigned vmask = __ballot_sync(0xffffffffu, rec);
-        if (rec) {
-            const unsigned peers = __match_any_sync(vmask, key);
-            const int leader = __ffs(peers) - 1;
-            uint32_t rbase = 0;
-            if (lane == leader) rbase = atomicAdd(&pc.bins[key], (uint32_t)__popc(peers));
-            rbase = __shfl_sync(peers, rbase, leader);
-            const uint32_t rank = rbase + __popc(peers & ((1u << lane) - 1u));
-            HitRec hr;
-            hr.prim = h.prim;
-            hr.keyrank = (key << TAKE_RANK_BITS) | rank;
-            hr.t = h.t; hr.u = h.u; hr.v = h.v;
-            st_stream(w.hit + slot, hr);
-        }
-        if (miss_fast && vmask) {  // list the surviving slots for the sort (one atomic per warp)
-            uint32_t qb = 0;
-            if (lane == __ffs(vmask) - 1) qb = atomicAdd(&pc.n_extend, (uint32_t)__popc(vmask));
-            qb = __shfl_sync(0xffffffffu, qb, __ffs(vmask) - 1);
-            if (rec) w.q_extend[0][qb + __popc(vmask & ((1u << lane) - 1u))] = slot;
-        }
+        extend_finish(sc, w, pc, lane, valid, slot, h, branch, primary, miss_fast);
+    }
+    if (COUNT) {
+        atomicAdd(&w.totals->box_tests, cnt.box);
+        atomicAdd(&w.totals->tri_tests, cnt.tri);
+    }
+}
+
+// Pass 0 with fused camera rays: the warp's 32 rays (the samples of one pixel, or of one 8x4 tile) traverse as a packet.
+template <bool COUNT>
+__global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_extend_primary(DevScene sc, Wave w) {
+    __shared__ uint2 pstack[128 / 32][TAKE_PACKET_STACK];
+    PassCounters &pc = w.pass[0];
+    const uint32_t n = (uint32_t)w.n_slots;
+    const bool miss_fast = w.miss_fast != 0;
+    const int lane = threadIdx.x & 31;
+    uint2 *wstack = pstack[threadIdx.x >> 5];
+    TravCounters cnt = {0, 0};
+    WorkCursor wc = {0, 0};
+    for (;;) {
+        uint32_t base;
+        if (!wc.next(&pc.fetch_extend, n, lane, base, TAKE_FETCH_BATCHES)) break;
+        const uint32_t i = base + lane;
+        const bool valid = i < n;
+        D3 o = mk3(0, 0, 0), d = mk3(0, 0, 0);
+        if (valid) primary_ray(sc, w, (int)i, o, d);
+        HitOut h;
+        trace_packet4<COUNT>(sc, o, d, TAKE_EPS, INFINITY, valid, wstack, h, &cnt);
+        extend_finish(sc, w, pc, lane, valid, (int)i, h, 0, true, miss_fast);
     }
     if (COUNT) {
         atomicAdd(&w.totals->box_tests, cnt.box);

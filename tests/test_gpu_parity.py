@@ -213,6 +213,14 @@ def test_render_properties(pair, monkeypatch):
         assert np.array_equal(f, g) and np.array_equal(f2, g2)
         for k in ("samples", "extend_rays", "shadow_rays", "shaded"):
             assert st_f[k] == st_g[k], (integ, k)
+    for integ in ("mis", "one_sample_mis"):                                      # camera rays as warp packets vs one ray per thread
+        f, f2, st_f = gs.render_sums(integ, 5, 0, 4, seed=5)
+        monkeypatch.setenv("TAKE_PACKET", "0")
+        g, g2, st_g = gs.render_sums(integ, 5, 0, 4, seed=5)
+        monkeypatch.delenv("TAKE_PACKET")
+        assert np.array_equal(f, g) and np.array_equal(f2, g2)
+        for k in ("samples", "extend_rays", "shadow_rays", "shaded"):
+            assert st_f[k] == st_g[k], (integ, k)
     monkeypatch.setenv("TAKE_WAVE_SLOTS", "1500")                                # force pixel chunking + many waves
     d, d2, _ = gs.render_sums("mis", 5, 0, 4, seed=5)
     assert np.array_equal(a, d) and np.array_equal(a2, d2)
