@@ -58,24 +58,6 @@ __device__ __forceinline__ D3 to_world(D3 n, D3 v) {  // :314-326 (Frisvad ONB)
     }
     return add(add(mul(x, v.x), mul(y, v.y)), mul(n, v.z));
 }
-// pow / sin / cos in the shade kernels.  CUDA inlines its FP64 pow (~350 SASS instructions) and sin / cos at every call site,
-// and the BSDF code has dozens of them after eval / sample / pdf are inlined into the integrators: the multi-sample shade
-// kernel was 16 k instructions (256 KB), far beyond the instruction caches, and 12-17 % of its stall samples were
-// `no_instructions`.  Routing them through ONE out-of-line copy each shrinks the kernels; the arithmetic is the same routine,
-// so results do not change.  TAKE_NOINLINE_MATH=0 restores the inlined calls (A/B).
-#ifndef TAKE_NOINLINE_MATH
-#define TAKE_NOINLINE_MATH 1
-#endif
-#if TAKE_NOINLINE_MATH
-__device__ __noinline__ double m_pow(double a, double b) { return pow(a, b); }
-__device__ __noinline__ double m_sin(double x) { return sin(x); }
-__device__ __noinline__ double m_cos(double x) { return cos(x); }
-#else
-__device__ __forceinline__ double m_pow(double a, double b) { return pow(a, b); }
-__device__ __forceinline__ double m_sin(double x) { return sin(x); }
-__device__ __forceinline__ double m_cos(double x) { return cos(x); }
-#endif
-
 __device__ __forceinline__ double clampd(double v, double lo, double hi) { return (v < lo) ? lo : (hi < v) ? hi : v; }
 __device__ __forceinline__ double modulo1(double a) { double r = fmod(a, 1.0); return (r < 0.0) ? r + 1.0 : r; }  // take.h:66-69
 

@@ -191,7 +191,7 @@ __device__ __forceinline__ void env_texel(const DevScene &sc, D3 d, int &i, int 
 }
 __device__ __forceinline__ D3 env_rgb_at(const DevScene &sc, int i, int j) { return ld3(sc.env_rgb + 3 * ((int64_t)j * sc.env_w + i)); }
 __device__ __forceinline__ double env_func(const DevScene &sc, int i, int j) {
-    return luminance(env_rgb_at(sc, i, j)) * m_sin(TAKE_PI * (j + 0.5) / sc.env_h);
+    return luminance(env_rgb_at(sc, i, j)) * sin(TAKE_PI * (j + 0.5) / sc.env_h);
 }
 __device__ __forceinline__ D3 env_radiance(const DevScene &sc, D3 d) {
     int i, j;
@@ -204,7 +204,7 @@ __device__ __forceinline__ double env_pdf(const DevScene &sc, D3 d) {
     int i, j;
     double theta;
     env_texel(sc, d, i, j, theta);
-    double st = m_sin(theta);
+    double st = sin(theta);
     if (!(st > 0) || !(sc.env_total > 0)) return 0;
     return env_func(sc, i, j) / sc.env_total * ((double)sc.env_w * sc.env_h) / (2 * TAKE_PI * TAKE_PI * st);
 }
@@ -236,8 +236,8 @@ __device__ __forceinline__ void env_sample_dir(const DevScene &sc, double u1, do
     double du = (y - c[i]) / cell;
     double u = (i + du) / W, v = (j + dv) / H;
     double theta = v * TAKE_PI, phi = u * (2 * TAKE_PI) - TAKE_PI;
-    double st = m_sin(theta);
-    dir = mk3(st * m_cos(phi), m_cos(theta), -(st * m_sin(phi)));
+    double st = sin(theta);
+    dir = mk3(st * cos(phi), cos(theta), -(st * sin(phi)));
     if (!(st > 0)) return;
     pdf = env_func(sc, i, j) / sc.env_total * ((double)W * H) / (2 * TAKE_PI * TAKE_PI * st);
 }
@@ -248,7 +248,7 @@ __device__ __forceinline__ D3 sample_hemisphere_cos(Rng &rng) {
     double u2 = rng.next();
     double phi = TAKE_TWOPI * u2;
     double sqrt_u1 = sqrt(clampd(u1, 0, 1));
-    return mk3(m_cos(phi) * sqrt_u1, m_sin(phi) * sqrt_u1, sqrt(clampd(1 - u1, 0, 1)));
+    return mk3(cos(phi) * sqrt_u1, sin(phi) * sqrt_u1, sqrt(clampd(1 - u1, 0, 1)));
 }
 __device__ __forceinline__ double blinn_G_hat(D3 omega, D3 n, double alpha) {
     double odn = dot(omega, n);
@@ -280,8 +280,8 @@ __device__ __forceinline__ D3 sample_power_cos_lobe(double exponent, Rng &rng) {
     double u2 = rng.next();
     double ra1 = 1 / (exponent + 1);
     double phi = TAKE_TWOPI * u2;
-    double sqrt_u1 = sqrt(clampd(1 - m_pow(u1, 2 * ra1), 0, 1));
-    return normalize(mk3(m_cos(phi) * sqrt_u1, m_sin(phi) * sqrt_u1, clampd(m_pow(u1, ra1), 0, 1)));
+    double sqrt_u1 = sqrt(clampd(1 - pow(u1, 2 * ra1), 0, 1));
+    return normalize(mk3(cos(phi) * sqrt_u1, sin(phi) * sqrt_u1, clampd(pow(u1, ra1), 0, 1)));
 }
 
 // sample_bsdf (src/material.cpp:76-82 + materials/*.inl); false == std::nullopt
@@ -302,8 +302,8 @@ __device__ __forceinline__ bool sample_bsdf(const TakeMaterialDesc &m, D3 dir_in
     if (t == TAKE_MAT_PLASTIC) {  // plastic.inl:1-27
         D3 rd = reflect(dir_in, n);
         double eta = m.p[0];
-        double F0 = m_pow((eta - 1) / (eta + 1), 2.0);
-        double F = F0 + (1 - F0) * m_pow(1 - dot(n, rd), 5.0);
+        double F0 = pow((eta - 1) / (eta + 1), 2.0);
+        double F = F0 + (1 - F0) * pow(1 - dot(n, rd), 5.0);
         double u = rng.next();
         if (u <= F) {
             dir_out = rd;
@@ -321,7 +321,7 @@ __device__ __forceinline__ bool sample_bsdf(const TakeMaterialDesc &m, D3 dir_in
         double phi = TAKE_TWOPI * u2;
         double cos_t = sqrt(clampd((1 - u1) / (1 + (alpha * alpha - 1) * u1), 0, 1));
         double sin_t = sqrt(clampd(1 - cos_t * cos_t, 0, 1));
-        D3 h = normalize(to_world(n, mk3(m_cos(phi) * sin_t, m_sin(phi) * sin_t, cos_t)));
+        D3 h = normalize(to_world(n, mk3(cos(phi) * sin_t, sin(phi) * sin_t, cos_t)));
         dir_out = normalize(add(neg(dir_in), mul(h, 2 * dot(dir_in, h))));
         if (dot(v.gn, dir_out) <= 0 || dot(h, n) <= 0 || dot(dir_out, h) <= 0) pdf = 0;
         else pdf = ggx_D(clampd(dot(n, h), 0, 1), alpha) * dot(n, h) * 0.25 / dot(dir_out, h);
@@ -332,7 +332,7 @@ __device__ __forceinline__ bool sample_bsdf(const TakeMaterialDesc &m, D3 dir_in
         D3 local = sample_power_cos_lobe(ex, rng);
         D3 rd = normalize(reflect(dir_in, n));
         dir_out = normalize(to_world(rd, local));
-        pdf = dot(v.gn, dir_out) < 0 ? 0.0 : fmax(0.0, (ex + 1) / TAKE_TWOPI * m_pow(dot(rd, dir_out), ex));
+        pdf = dot(v.gn, dir_out) < 0 ? 0.0 : fmax(0.0, (ex + 1) / TAKE_TWOPI * pow(dot(rd, dir_out), ex));
         return true;
     }
     // blinn_phong.inl:1-29 / blinn_phong_microfacet.inl:1-29
@@ -342,9 +342,9 @@ __device__ __forceinline__ bool sample_bsdf(const TakeMaterialDesc &m, D3 dir_in
     if (dot(v.gn, dir_out) <= 0 || dot(h, n) <= 0 || dot(dir_out, h) <= 0) {
         pdf = 0;
     } else if (t == TAKE_MAT_BLINN_PHONG) {
-        pdf = (ex + 1) * 0.25 * TAKE_INVTWOPI * m_pow(dot(n, h), ex) / dot(dir_out, h);
+        pdf = (ex + 1) * 0.25 * TAKE_INVTWOPI * pow(dot(n, h), ex) / dot(dir_out, h);
     } else {
-        pdf = (ex + 1) * 0.25 * TAKE_INVTWOPI * m_pow(clampd(dot(n, h), 0, 1), ex) / dot(dir_out, h);
+        pdf = (ex + 1) * 0.25 * TAKE_INVTWOPI * pow(clampd(dot(n, h), 0, 1), ex) / dot(dir_out, h);
     }
     return true;
 }
@@ -358,8 +358,8 @@ __device__ __forceinline__ double bsdf_pdf(const TakeMaterialDesc &m, D3 dir_in,
     if (is_lambert_like(t)) return fmax(dot(n, dir_out), 0.0) / TAKE_PI;  // diffuse.inl:16-21
     if (t == TAKE_MAT_PLASTIC) {  // plastic.inl:29-38
         double eta = m.p[0];
-        double F0 = m_pow((eta - 1) / (eta + 1), 2.0);
-        double F = F0 + (1 - F0) * m_pow(1 - dot(n, dir_out), 5.0);
+        double F0 = pow((eta - 1) / (eta + 1), 2.0);
+        double F = F0 + (1 - F0) * pow(1 - dot(n, dir_out), 5.0);
         return (1 - F) * fmax(dot(n, dir_out), 0.0) / TAKE_PI;
     }
     if (t == TAKE_MAT_GGX) {  // EXTENSION
@@ -370,12 +370,12 @@ __device__ __forceinline__ double bsdf_pdf(const TakeMaterialDesc &m, D3 dir_in,
     const double ex = m.p[0];
     if (t == TAKE_MAT_PHONG) {  // phong.inl:30-40
         D3 rd = normalize(reflect(dir_in, n));
-        return fmax(0.0, (ex + 1) / TAKE_TWOPI * m_pow(dot(rd, dir_out), ex));
+        return fmax(0.0, (ex + 1) / TAKE_TWOPI * pow(dot(rd, dir_out), ex));
     }
     D3 h = normalize(add(dir_out, dir_in));  // blinn_phong.inl:31-41, blinn_phong_microfacet.inl:31-41
     if (dot(v.gn, dir_out) <= 0 || dot(h, n) <= 0 || dot(dir_out, h) <= 0) return 0;
-    if (t == TAKE_MAT_BLINN_PHONG) return (ex + 1) * 0.25 * TAKE_INVTWOPI * m_pow(dot(n, h), ex) / dot(dir_out, h);
-    return (ex + 1) * 0.25 * TAKE_INVTWOPI * m_pow(clampd(dot(n, h), 0, 1), ex) / dot(dir_out, h);
+    if (t == TAKE_MAT_BLINN_PHONG) return (ex + 1) * 0.25 * TAKE_INVTWOPI * pow(dot(n, h), ex) / dot(dir_out, h);
+    return (ex + 1) * 0.25 * TAKE_INVTWOPI * pow(clampd(dot(n, h), 0, 1), ex) / dot(dir_out, h);
 }
 
 // eval (src/material.cpp:92-98 + materials/*.inl): BSDF * cos.  rec_pdf is SampleRecord::pdf, which Plastic::eval
@@ -394,7 +394,7 @@ __device__ __forceinline__ D3 bsdf_eval(const DevScene &sc, const TakeMaterialDe
     }
     if (t == TAKE_MAT_MIRROR) {  // mirror.inl:16-23
         D3 F0 = eval_texture(sc, m, v.uv);
-        return add(F0, mul(rsub(1, F0), m_pow(1 - dot(n, dir_out), 5.0)));
+        return add(F0, mul(rsub(1, F0), pow(1 - dot(n, dir_out), 5.0)));
     }
     if (t == TAKE_MAT_PLASTIC) {  // plastic.inl:40-52
         if (rec_pdf == 1.0) return mk3(1, 1, 1);
@@ -405,7 +405,7 @@ __device__ __forceinline__ D3 bsdf_eval(const DevScene &sc, const TakeMaterialDe
         D3 h = normalize(add(dir_out, dir_in));
         if (dot(n, dir_out) <= 0 || dot(dir_out, h) <= 0 || dot(dir_in, h) <= 0) return zero;
         D3 Ks = eval_texture(sc, m, v.uv);
-        D3 Fh = add(Ks, mul(rsub(1, Ks), m_pow(1 - dot(h, dir_out), 5.0)));
+        D3 Fh = add(Ks, mul(rsub(1, Ks), pow(1 - dot(h, dir_out), 5.0)));
         double Dh = ggx_D(clampd(dot(n, h), 0, 1), m.p[0]);
         double G = ggx_G1(dot(n, dir_out), m.p[0]) * ggx_G1(dot(n, dir_in), m.p[0]);
         return divs(mul(mul(mul(Fh, Dh), G), 0.25), dot(n, dir_in));
@@ -415,22 +415,22 @@ __device__ __forceinline__ D3 bsdf_eval(const DevScene &sc, const TakeMaterialDe
         D3 rd = normalize(reflect(dir_in, n));
         D3 Ks = eval_texture(sc, m, v.uv);
         if (dot(n, dir_out) <= 0) return zero;
-        return mul(divs(mul(Ks, ex + 1), TAKE_TWOPI), m_pow(fmax(dot(dir_out, rd), 0.0), ex));
+        return mul(divs(mul(Ks, ex + 1), TAKE_TWOPI), pow(fmax(dot(dir_out, rd), 0.0), ex));
     }
     if (t == TAKE_MAT_BLINN_PHONG) {  // blinn_phong.inl:43-56
         if (dot(n, dir_out) <= 0) return zero;
         D3 h = normalize(add(dir_out, dir_in));
         D3 Ks = eval_texture(sc, m, v.uv);
-        D3 Fh = add(Ks, mul(rsub(1, Ks), m_pow(1 - dot(h, dir_out), 5.0)));
-        double s = (ex + 2) * 0.25 * TAKE_INVPI / (2 - m_pow(2.0, -ex / 2));
-        return mul(mul(Fh, s), m_pow(fmax(0.0, dot(n, h)), ex));
+        D3 Fh = add(Ks, mul(rsub(1, Ks), pow(1 - dot(h, dir_out), 5.0)));
+        double s = (ex + 2) * 0.25 * TAKE_INVPI / (2 - pow(2.0, -ex / 2));
+        return mul(mul(Fh, s), pow(fmax(0.0, dot(n, h)), ex));
     }
     if (t == TAKE_MAT_BLINN_MICROFACET) {  // blinn_phong_microfacet.inl:43-60
         D3 h = normalize(add(dir_out, dir_in));
         if (dot(n, dir_out) <= 0 || dot(dir_out, h) <= 0 || dot(dir_in, h) <= 0) return zero;
         D3 Ks = eval_texture(sc, m, v.uv);
-        D3 Fh = add(Ks, mul(rsub(1, Ks), m_pow(1 - dot(h, dir_out), 5.0)));
-        double Dh = (ex + 2) * TAKE_INVTWOPI * m_pow(clampd(dot(n, h), 0, 1), ex);
+        D3 Fh = add(Ks, mul(rsub(1, Ks), pow(1 - dot(h, dir_out), 5.0)));
+        double Dh = (ex + 2) * TAKE_INVTWOPI * pow(clampd(dot(n, h), 0, 1), ex);
         double G = blinn_G_hat(dir_out, n, ex) * blinn_G_hat(dir_in, n, ex);
         return divs(mul(mul(mul(Fh, Dh), G), 0.25), dot(n, dir_in));
     }
@@ -439,7 +439,7 @@ __device__ __forceinline__ D3 bsdf_eval(const DevScene &sc, const TakeMaterialDe
     double hdout = dot(h, dir_out), ndout = dot(n, dir_out), ndin = dot(n, dir_in);
     D3 Kd = eval_texture(sc, m, v.uv);
     double rough = m.p[0], subsurface = m.p[1];
-    double p_in = m_pow(1 - dot(n, dir_in), 5.0), p_out = m_pow(1 - dot(n, dir_out), 5.0);
+    double p_in = pow(1 - dot(n, dir_in), 5.0), p_out = pow(1 - dot(n, dir_out), 5.0);
     double FD90 = 0.5 + 2 * rough * hdout * hdout;
     D3 f_base = mul(mul(mul(mul(Kd, TAKE_INVPI), 1 + (FD90 - 1) * p_in), 1 + (FD90 - 1) * p_out), ndout);
     double FSS90 = rough * hdout * hdout;
@@ -518,7 +518,7 @@ __device__ __forceinline__ void sample_on_light(const DevScene &sc, int light_id
         double z = 1 + u1 * (r / d - 1);
         double z2 = z * z;
         double sin_theta = sqrt(clampd(1 - z2, 0, 1));
-        D3 local_p = normalize(mk3(m_cos(2 * TAKE_PI * u2) * sin_theta, m_sin(2 * TAKE_PI * u2) * sin_theta, z));
+        D3 local_p = normalize(mk3(cos(2 * TAKE_PI * u2) * sin_theta, sin(2 * TAKE_PI * u2) * sin_theta, z));
         nrm = normalize(to_world(normalize(sub(ref_pos, c)), local_p));
         pos = add(c, mul(nrm, r));
         return;
@@ -548,7 +548,7 @@ __device__ __forceinline__ void sample_on_light(const DevScene &sc, int light_id
         double z = 1 + u1 * (r / d - 1);
         double z2 = z * z;
         double sin_theta = sqrt(clampd(1 - z2, 0, 1));
-        D3 local_p = normalize(mk3(m_cos(2 * TAKE_PI * u2) * sin_theta, m_sin(2 * TAKE_PI * u2) * sin_theta, z));
+        D3 local_p = normalize(mk3(cos(2 * TAKE_PI * u2) * sin_theta, sin(2 * TAKE_PI * u2) * sin_theta, z));
         nrm = normalize(to_world(normalize(sub(ref_pos, c)), local_p));
         pos = add(c, mul(nrm, r));
         return;

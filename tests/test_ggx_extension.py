@@ -58,6 +58,10 @@ def test_ggx_gpu_matches_restatement(gpu_lib, oracle_lib):
         px, py = rng.integers(0, flat.width, n), rng.integers(0, flat.height, n)
         s = rng.integers(0, 1 << 16, n)
         for integ in api.INTEGRATORS:
+            if integ == "one_sample_mis_power" and flat.env is not None and flat.env_sample:
+                with pytest.raises(api.TakeGpuError):      # the power pick has no entry for a sampled environment map
+                    gs.render_sums(integ, 4, 0, 1, seed=2)
+                continue
             a = sc.radiance_samples(px, py, s, integ, 4, seed=5)
             b = gs.radiance_samples(px, py, s, integ, 4, seed=5)
             err = np.abs(a - b).max(axis=1) / (np.abs(a).max(axis=1) + 1e-30)
