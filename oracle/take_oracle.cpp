@@ -950,7 +950,7 @@ inline int sample_light_power(const Scene &sc, Rng &rng) {  // light.cpp:9-17
 
 V3 path_tracing_one_sample_mis_power(const Scene &sc, Ray r, Rng &rng, int max_depth, Counters &cn) {
     Isect v;
-    if (!scene_intersect(sc, r, v, cn)) return sc.background;                                   // :277
+    if (!scene_intersect(sc, r, v, cn)) return miss_radiance(sc, r.d);                                   // :277
     V3 radiance = {0, 0, 0}, throughput = {1, 1, 1};
     for (int i = 0; i <= max_depth; ++i) {
         if (v.light != -1 && sc.lights[v.light].kind == TAKE_LIGHT_AREA) {                       // :284-291
@@ -977,7 +977,7 @@ V3 path_tracing_one_sample_mis_power(const Scene &sc, Ray r, Rng &rng, int max_d
                 r = {v.pos, light_dir, EPS, INFINITY};
                 Isect nv;
                 if (!scene_intersect(sc, r, nv, cn)) {                                            // :326-330 (checked here, unlike :220)
-                    radiance = add(radiance, mulv(throughput, sc.background));
+                    radiance = add(radiance, mulv(throughput, miss_radiance(sc, light_dir)));
                     break;
                 }
                 v = nv;
@@ -998,7 +998,7 @@ V3 path_tracing_one_sample_mis_power(const Scene &sc, Ray r, Rng &rng, int max_d
             double pdf = (sc.lights.empty() || spec) ? bpdf : 0.5 * bpdf;
             if (!hit) {
                 throughput = mulv(throughput, divs(FG, pdf));
-                radiance = add(radiance, mulv(throughput, sc.background));
+                radiance = add(radiance, mulv(throughput, miss_radiance(sc, dir_out)));
                 break;
             }
             if (!spec && nv.light != -1) {                                                        // :363-373

@@ -35,6 +35,8 @@ def test_env_scene_matches_oracle(gpu_lib, oracle_lib, name):
         px, py = rng.integers(0, flat.width, n), rng.integers(0, flat.height, n)
         s = rng.integers(0, 1 << 16, n)
         for integ in api.INTEGRATORS:
+            if integ == "one_sample_mis_power" and flat.env_sample:
+                continue      # the power pick has no entry for a sampled environment map (refused: test_ggx_extension)
             a = sc.radiance_samples(px, py, s, integ, 4, seed=3)
             b = gs.radiance_samples(px, py, s, integ, 4, seed=3)
             err = np.abs(a - b).max(axis=1) / (np.abs(a).max(axis=1) + 1e-30)
