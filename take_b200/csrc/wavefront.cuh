@@ -193,6 +193,9 @@ __device__ __forceinline__ void queue_push(bool want, int32_t *queue, uint32_t *
 #ifndef TAKE_V1_MIN_BLOCKS
 #define TAKE_V1_MIN_BLOCKS 1
 #endif
+#ifndef TAKE_BOUNCE_MIN_BLOCKS   // resident blocks (-> register cap) of the one-ray-per-thread traversal kernels (bounce / shadow passes)
+#define TAKE_BOUNCE_MIN_BLOCKS TAKE_V1_MIN_BLOCKS
+#endif
 
 // Camera ray of a slot: src/render.cpp:69-75 (jittered pinhole; first draw -> x, second -> y).  Consumes 2 draws.
 // The coin the one-sample integrator will flip first at the vertex this stream reaches next: draw number rng.k.
@@ -340,7 +343,7 @@ __device__ __forceinline__ void extend_finish(const DevScene &sc, const Wave &w,
 }
 
 template <bool COUNT, bool WIDE>
-__global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_extend(DevScene sc, Wave w, int pass) {
+__global__ void __launch_bounds__(128, TAKE_BOUNCE_MIN_BLOCKS) k_extend(DevScene sc, Wave w, int pass) {
     TAKE_DECLARE_STACK(st);
     PassCounters &pc = w.pass[pass];
     const uint32_t n = pass_count(w, pass);
@@ -882,7 +885,7 @@ __global__ void __launch_bounds__(128, TAKE_SHADE_MIN_BLOCKS) k_shade(DevScene s
 
 // ---- shadow-connect: any-hit query; unoccluded connections add throughput * C1 (path_tracing.h:53-60) ----------
 template <bool COUNT, bool WIDE>
-__global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_shadow(DevScene sc, Wave w, int pass) {
+__global__ void __launch_bounds__(128, TAKE_BOUNCE_MIN_BLOCKS) k_shadow(DevScene sc, Wave w, int pass) {
     TAKE_DECLARE_STACK(st);
     PassCounters &pc = w.pass[pass];
     const uint32_t n = pc.n_shadow;
