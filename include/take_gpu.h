@@ -275,6 +275,12 @@ int take_gpu_scene_info(TakeScene *scene, double *out);
  * fast tree was built on the device, 1 if the reference-order tree is still being built in the background (it is joined by
  * the first call that traces rays: take_gpu_scene_create itself does not wait for it). */
 int take_gpu_scene_create_timings(TakeScene *scene, double *out8);
+/* take_gpu_render / take_gpu_render_device do not wait for that background tree either: its only product the render needs
+ * are the ranks that decide EQUAL-t ties, so they render at once, count the leaf tests in which a rank decided anything
+ * (practically none with jittered rays), and only if that count is not zero restore the outputs and repeat the call after
+ * joining the tree -- the result is always the one with the ranks in place.  out[0] = renders that ran ahead of the tree,
+ * out[1] = how many had to be repeated.  (TAKE_PROVISIONAL=0 in the environment makes every render wait instead.) */
+int take_gpu_scene_provisional_stats(TakeScene *scene, int64_t *out2);
 /* Copies the fast tree out of the device for inspection: 128-byte 4-wide nodes (take_b200/csrc/bvh_build.h: WideNode) and
  * the primitive id of every leaf slot (device-built scenes only; pass NULL otherwise).  Returns the number of wide nodes
  * (either pointer may be NULL). */

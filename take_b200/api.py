@@ -35,6 +35,7 @@ EXPORTS = [
     "take_gpu_builder_create", "take_gpu_builder_destroy", "take_gpu_builder_add_ply", "take_gpu_builder_add_mesh",
     "take_gpu_builder_add_sphere", "take_gpu_builder_add_point_light", "take_gpu_builder_finish", "take_gpu_builder_timings",
     "take_gpu_scene_desc_save", "take_gpu_scene_create_timings", "take_gpu_scene_debug_tree",
+    "take_gpu_scene_provisional_stats",
 ]
 
 RAY_DTYPE = np.dtype([("origin", "<f8", 3), ("dir", "<f8", 3), ("tmin", "<f8"), ("tmax", "<f8")])
@@ -104,6 +105,7 @@ def load_library(path: str = LIB_PATH):
     L.take_gpu_scene_stream.argtypes = [vp]
     L.take_gpu_scene_info.argtypes = [vp, vp]
     L.take_gpu_scene_create_timings.argtypes = [vp, vp]
+    L.take_gpu_scene_provisional_stats.argtypes = [vp, vp]
     L.take_gpu_scene_debug_tree.restype = i64
     L.take_gpu_scene_debug_tree.argtypes = [vp, vp, vp]
     L.take_gpu_render_async.argtypes = [vp, C.POINTER(TakeRenderOpts), vp, vp, C.POINTER(i64)]
@@ -224,6 +226,12 @@ class GpuScene:
         _check(self.lib.take_gpu_scene_create_timings(self.h, out))
         keys = ["validate_ms", "upload_ms", "host_boxes_ms", "device_build_ms", "records_ms", "total_ms", "device_built", "reference_tree_pending"]
         return dict(zip(keys, out))
+
+    def provisional_stats(self) -> dict:
+        """Renders that ran before the background reference-order tree had arrived, and how many of them were repeated."""
+        out = (C.c_int64 * 2)()
+        _check(self.lib.take_gpu_scene_provisional_stats(self.h, out))
+        return {"provisional_renders": int(out[0]), "provisional_reruns": int(out[1])}
 
     def debug_tree(self, leaf_prims=True):
         """(wide nodes as a structured array, primitive id per leaf slot or None): the fast tree as it sits on the device."""

@@ -135,6 +135,9 @@ struct DevScene {
     const double *env_rgb, *env_marg, *env_cond;  // texels [h][w][3]; marginal CDF [h+1]; conditional CDFs [h][w+1]
     double env_total;
     int32_t env_w, env_h;
+    // Counts closest-hit leaf tests whose outcome depended on the tie-break rank (equal t with the current hit).  A render that
+    // runs before the reference-order tree -- the source of the ranks -- has arrived is valid iff this stays 0 (take_gpu.cu).
+    unsigned long long *tie_count;
     int32_t env_light;   // 1: the environment is entry number num_lights of the uniform light pick
     int32_t pick_count;  // num_lights + env_light: the N of sample_light (src/light.cpp:5-7) and of the 1/N in the light pdfs
 };

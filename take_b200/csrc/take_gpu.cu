@@ -8,8 +8,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <new>
 #include <string>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -71,6 +74,21 @@ struct DeviceBuffer {
 
 }  // namespace
 
+// The reference-order tree of a device-built scene: built by a host thread from its own copy of the primitive boxes, shared
+// by all replicas of a multi-GPU handle, joined by the first call that traces rays.
+struct RefJob {
+    std::thread th;
+    std::once_flag joined;
+    RefTree tree;
+    std::vector<Aabb> boxes;
+    double t0 = 0, ms = 0;
+    std::atomic<bool> done{false};
+    void wait() {
+        std::call_once(joined, [this] { if (th.joinable()) th.join(); });
+    }
+    ~RefJob() { if (th.joinable()) th.join(); }
+};
+
 struct TakeScene {
     int device = 0;
     int sm_count = 0;
@@ -110,11 +128,10 @@ struct TakeScene {
                         // with dynamic re-fetch (TAKE_TRAVERSAL=2)
     // Device-built scenes: the reference-order tree (tie-break ranks, exact mode) is built by a host thread while the device
     // builds the fast tree and while the caller goes on; finish_reference_tree() joins it before the first query.
-    std::thread ref_thread;
+    std::shared_ptr<RefJob> ref_job;
     bool ref_pending = false;
-    RefTree ref_host;
-    std::vector<Aabb> ref_boxes;
-    double ref_t0 = 0;
+    DeviceBuffer tie_count, snap_sum, snap_sq;   // rank-decided ties of a render; output snapshots of a provisional render
+    int64_t provisional_renders = 0, provisional_reruns = 0;
     DeviceBuffer leaf_prims;
     bool device_built = false;
     bool power_ok = false;   // the scene has emitters with non-zero total power (the power-sampling integrator needs them)
@@ -126,7 +143,7 @@ struct TakeScene {
     double sah_cost = 0;
     int64_t num_fast_nodes = 0;
     ~TakeScene() {
-        if (ref_thread.joinable()) ref_thread.join();
+        if (ref_job) ref_job->wait();
         for (auto *b : tex_data) delete b;
         for (auto e : ev_acc) if (e) cudaEventDestroy(e);
         if (ev_begin) cudaEventDestroy(ev_begin);
@@ -621,7 +638,45 @@ int take_gpu_device_count(int *count) {
     return TAKE_OK;
 }
 
-static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild *hb, TakeScene **out);
+static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild *hb, TakeScene **out, std::shared_ptr<RefJob> job = nullptr);
+
+// primitive boxes exactly as build_bvh (src/scene.cpp:4-23), then the reference-order tree on a host thread that works on ITS
+// OWN copy (the caller's arrays are not touched after the creating call returns)
+static std::shared_ptr<RefJob> start_reference_tree(const TakeSceneDesc *d, int threads) {
+    auto job = std::make_shared<RefJob>();
+    const int64_t n = d->num_prims;
+    job->boxes.resize((size_t)n);
+    RefJob *j = job.get();
+    parallel_chunks(n, threads, [&](int64_t a0, int64_t a1) {
+        for (int64_t i = a0; i < a1; ++i) {
+            Aabb &b = j->boxes[i];
+            const int32_t *id = d->indices + 3 * i;
+            if (d->prim_flags[i] & TAKE_PRIM_SPHERE) {
+                const double *sp = d->spheres + 4 * (int64_t)id[0];
+                for (int a = 0; a < 3; ++a) { b.lo[a] = sp[a] - sp[3]; b.hi[a] = sp[a] + sp[3]; }
+            } else {
+                const double *p0 = d->positions + 3 * (int64_t)id[0], *p1 = d->positions + 3 * (int64_t)id[1],
+                             *p2 = d->positions + 3 * (int64_t)id[2];
+                for (int a = 0; a < 3; ++a) {
+                    b.lo[a] = std::min(std::min(p0[a], p1[a]), p2[a]);
+                    b.hi[a] = std::max(std::max(p0[a], p1[a]), p2[a]);
+                }
+            }
+        }
+    });
+    job->t0 = now_ms();
+    // (leaves a core to the caller: the device build and the first waves need the launching thread)
+    const int ref_threads = std::max(1, threads - 1);
+    const int delay_ms = env_int("TAKE_REF_DELAY_MS", 0);   // test knob: keeps the tree "still being built" for a while
+    job->th = std::thread([j, n, ref_threads, delay_ms] {
+        if (delay_ms > 0) std::this_thread::sleep_for(std::chrono::milliseconds(delay_ms));
+        build_reference_tree(j->boxes.data(), n, ref_threads, j->tree);
+        std::vector<Aabb>().swap(j->boxes);
+        j->ms = now_ms() - j->t0;
+        j->done.store(true);
+    });
+    return job;
+}
 
 // The fast tree is built on the device (bvh_device.cuh) unless TAKE_DEVICE_BUILD=0 asks for the host's binned-SAH builder
 // (the A/B baseline for tree quality; also what the prebuilt / saved-build paths use).
@@ -648,9 +703,10 @@ int take_gpu_scene_create(int device, const TakeSceneDesc *d, TakeScene **out) {
 static int finish_reference_tree(TakeScene *s) {
     if (!s->ref_pending) return TAKE_OK;
     s->ref_pending = false;
-    if (s->ref_thread.joinable()) s->ref_thread.join();
+    s->ref_job->wait();
+    s->build_ms_ref = s->ref_job->ms;
     CU(cudaSetDevice(s->device));
-    RefTree &ref = s->ref_host;
+    RefTree &ref = s->ref_job->tree;
     if (int rc = upload(s->ref_nodes, ref.nodes.data(), ref.nodes.size(), s->stream)) return rc;
     if (int rc = upload(s->dfs_rank, ref.dfs_rank.data(), ref.dfs_rank.size(), s->stream)) return rc;
     s->dev.ref_nodes = s->ref_nodes.as<RefNode>();
@@ -661,9 +717,8 @@ static int finish_reference_tree(TakeScene *s) {
         devbuild::k_patch_ranks<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(n, s->dfs_rank.as<int32_t>(), s->tris.as<double>());
         CU(cudaGetLastError());
     }
-    CU(cudaStreamSynchronize(s->stream));   // the host copies are released below
-    std::vector<RefNode>().swap(ref.nodes);
-    std::vector<int32_t>().swap(ref.dfs_rank);
+    CU(cudaStreamSynchronize(s->stream));
+    s->ref_job.reset();                     // the host copy goes with the last scene that used it
     return TAKE_OK;
 }
 
@@ -823,7 +878,7 @@ static int device_build_fast_tree(TakeScene *s, int max_leaf, double &abs_max) {
 // Upload a scene to `device`.  hb != nullptr: acceleration structures built on the host (shared by all replicas of a
 // multi-GPU render, or loaded from a file); hb == nullptr: the fast tree is built on the device and the reference-order
 // tree on a background host thread.
-static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild *hb, TakeScene **out) {
+static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild *hb, TakeScene **out, std::shared_ptr<RefJob> job) {
     *out = nullptr;
     CU(cudaSetDevice(device));
     TakeScene *s = new TakeScene;
@@ -865,36 +920,10 @@ static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild *hb, 
         if ((rc = upload(s->ref_nodes, hb->ref.nodes.data(), hb->ref.nodes.size(), st))) return rc;
         if ((rc = upload(s->dfs_rank, hb->ref.dfs_rank.data(), hb->ref.dfs_rank.size(), st))) return rc;
     } else {
-        // primitive boxes exactly as build_bvh (src/scene.cpp:4-23) for the reference-order tree, which a host thread builds
-        // from ITS OWN copy while everything else goes on (the caller's arrays are not touched after this call returns)
-        s->ref_boxes.resize((size_t)n);
-        parallel_chunks(n, threads, [&](int64_t a0, int64_t a1) {
-            for (int64_t i = a0; i < a1; ++i) {
-                Aabb &b = s->ref_boxes[i];
-                const int32_t *id = d->indices + 3 * i;
-                if (d->prim_flags[i] & TAKE_PRIM_SPHERE) {
-                    const double *sp = d->spheres + 4 * (int64_t)id[0];
-                    for (int a = 0; a < 3; ++a) { b.lo[a] = sp[a] - sp[3]; b.hi[a] = sp[a] + sp[3]; }
-                } else {
-                    const double *p0 = d->positions + 3 * (int64_t)id[0], *p1 = d->positions + 3 * (int64_t)id[1],
-                                 *p2 = d->positions + 3 * (int64_t)id[2];
-                    for (int a = 0; a < 3; ++a) {
-                        b.lo[a] = std::min(std::min(p0[a], p1[a]), p2[a]);
-                        b.hi[a] = std::max(std::max(p0[a], p1[a]), p2[a]);
-                    }
-                }
-            }
-        });
-        s->create_ms[2] = now_ms() - t_mark;
-        s->ref_t0 = now_ms();
+        // the reference-order tree goes on in the background (one job for all replicas of a multi-GPU handle)
+        s->ref_job = job ? job : start_reference_tree(d, threads);
         s->ref_pending = true;
-        // (leaves a core or two to the caller: the device build and the first waves need the launching thread)
-        const int ref_threads = std::max(1, threads - 1);
-        s->ref_thread = std::thread([s, n, ref_threads] {
-            build_reference_tree(s->ref_boxes.data(), n, ref_threads, s->ref_host);
-            std::vector<Aabb>().swap(s->ref_boxes);
-            s->build_ms_ref = now_ms() - s->ref_t0;
-        });
+        s->create_ms[2] = now_ms() - t_mark;
         CU(s->ref_nodes.ensure(64));
         CU(s->dfs_rank.ensure(16));
     }
@@ -992,6 +1021,9 @@ static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild *hb, 
     v.materials = s->materials.as<TakeMaterialDesc>();
     v.lights = s->lights.as<TakeLightDesc>();
     v.textures = s->textures.as<DevTexture>();
+    CU(s->tie_count.ensure(16));
+    CU(cudaMemsetAsync(s->tie_count.p, 0, 16, st));
+    v.tie_count = s->tie_count.as<unsigned long long>();
     v.num_lights = d->num_lights; v.num_materials = d->num_materials;
     v.light_pmf = s->light_pmf.as<double>(); v.light_cdf = s->light_cdf.as<double>();
     v.env_rgb = has_env ? s->env_rgb.as<double>() : nullptr;
@@ -1132,6 +1164,14 @@ int take_gpu_scene_create_timings(TakeScene *s, double *out) {
     for (int i = 0; i < 6; ++i) out[i] = s->create_ms[i];
     out[6] = s->device_built ? 1 : 0;
     out[7] = s->ref_pending ? 1 : 0;
+    return TAKE_OK;
+}
+
+// out[0] = renders that ran before the reference-order tree had arrived, out[1] = how many of them had to be repeated because
+// a tie-break rank mattered
+int take_gpu_scene_provisional_stats(TakeScene *s, int64_t *out) {
+    if (!s || !out) return fail(TAKE_E_INVALID, "null argument");
+    out[0] = s->provisional_renders; out[1] = s->provisional_reruns;
     return TAKE_OK;
 }
 
@@ -1410,9 +1450,15 @@ int take_gpu_occluded(TakeScene *s, const TakeRay *rays, int64_t n, uint8_t *occ
 namespace {
 // Queue one render call on the scene's streams: everything up to (and including) an event `e1` on s->stream that
 // orders all of its work.  No host synchronisation; `d_totals` receives the counters.
+// `provisional`: the caller can cope with a render whose tie-break ranks are not in place yet (it checks the tie counter
+// afterwards and repeats the call if a rank ever mattered); otherwise the reference-order tree is waited for here.
 int render_enqueue(TakeScene *s, const TakeRenderOpts *o, double *d_sum, double *d_sumsq, Totals *d_totals, StageTimer &tm,
-                   cudaEvent_t e0, cudaEvent_t e1, int64_t &launches, int64_t &waves) {
-    if (int rc = finish_reference_tree(s)) return rc;   // tie-break ranks must be in the leaf records before the first ray
+                   cudaEvent_t e0, cudaEvent_t e1, int64_t &launches, int64_t &waves, bool provisional = false) {
+    if (!provisional) {
+        if (int rc = finish_reference_tree(s)) return rc;   // tie-break ranks must be in the leaf records before the first ray
+    } else {
+        CU(cudaMemsetAsync(s->tie_count.p, 0, 8, s->stream));
+    }
     const int64_t npix = (int64_t)s->width * s->height;
     const int64_t spp = o->spp_end - o->spp_begin;
     const int64_t cap_env = std::max<int64_t>(1024, (int64_t)env_int("TAKE_WAVE_SLOTS", 1 << 25));
@@ -1501,10 +1547,45 @@ int take_gpu_render_device(TakeScene *s, const TakeRenderOpts *o, double *d_sum,
     CU(cudaEventCreate(&e1));
     int64_t launches = 0, waves = 0;
     CU(s->totals.ensure(sizeof(Totals)));
-    int rc = render_enqueue(s, o, d_sum, d_sumsq, s->totals.as<Totals>(), tm, e0, e1, launches, waves);
+    // The reference-order tree (the source of the equal-t tie-break ranks) may still be under construction on its host thread
+    // (device-built scenes).  Instead of waiting, render now and count the leaf tests in which a rank decided anything: with
+    // jittered rays that is almost always zero, and then the image is exactly what it would have been with the ranks in
+    // place.  If the count is not zero the outputs are restored from a snapshot and the call is repeated after the join.
+    bool provisional = false;
+    const size_t out_bytes = (size_t)s->width * s->height * 3 * sizeof(double);
+    if (s->ref_pending) {
+        if (s->ref_job->done.load() || !env_int("TAKE_PROVISIONAL", 1) || tm.on) {
+            if (int rc0 = finish_reference_tree(s)) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc0; }
+        } else {
+            provisional = true;
+            CU(s->snap_sum.ensure(out_bytes));
+            CU(cudaMemcpyAsync(s->snap_sum.p, d_sum, out_bytes, cudaMemcpyDeviceToDevice, s->stream));
+            if (d_sumsq) {
+                CU(s->snap_sq.ensure(out_bytes));
+                CU(cudaMemcpyAsync(s->snap_sq.p, d_sumsq, out_bytes, cudaMemcpyDeviceToDevice, s->stream));
+            }
+        }
+    }
+    int rc = render_enqueue(s, o, d_sum, d_sumsq, s->totals.as<Totals>(), tm, e0, e1, launches, waves, provisional);
     if (rc == TAKE_OK) {
         cudaError_t e = cudaStreamSynchronize(s->stream);
         if (e != cudaSuccess) rc = fail(TAKE_E_CUDA, std::string("render: ") + cudaGetErrorString(e));
+    }
+    if (rc == TAKE_OK && provisional) {
+        s->provisional_renders++;
+        unsigned long long ties = 0;
+        CU(cudaMemcpy(&ties, s->tie_count.p, 8, cudaMemcpyDeviceToHost));
+        if (ties != 0) {   // a rank mattered: take the outputs back and do it again with the ranks in place
+            s->provisional_reruns++;
+            CU(cudaMemcpyAsync(d_sum, s->snap_sum.p, out_bytes, cudaMemcpyDeviceToDevice, s->stream));
+            if (d_sumsq) CU(cudaMemcpyAsync(d_sumsq, s->snap_sq.p, out_bytes, cudaMemcpyDeviceToDevice, s->stream));
+            rc = finish_reference_tree(s);
+            if (rc == TAKE_OK) rc = render_enqueue(s, o, d_sum, d_sumsq, s->totals.as<Totals>(), tm, e0, e1, launches, waves, false);
+            if (rc == TAKE_OK) {
+                cudaError_t e = cudaStreamSynchronize(s->stream);
+                if (e != cudaSuccess) rc = fail(TAKE_E_CUDA, std::string("render: ") + cudaGetErrorString(e));
+            }
+        }
     }
     float ms = 0;
     if (rc == TAKE_OK) cudaEventElapsedTime(&ms, e0, e1);
@@ -1663,8 +1744,13 @@ int take_gpu_multi_create(int ndev, const int *devices, const TakeSceneDesc *d, 
             if (devices[i] == devices[j]) return fail(TAKE_E_INVALID, "a device is listed twice");
     if (int rc = validate(d)) return rc;
     if (ndev > 1 && !g_nccl().ok) return fail(TAKE_E_CUDA, "libnccl.so.2 could not be loaded (needed to combine the partial images)");
+    // every replica builds its fast tree on its own device; the reference-order tree is built ONCE, in the background, and
+    // shared (TAKE_DEVICE_BUILD=0: both trees on the host, once, as before)
+    const bool device_build = env_int("TAKE_DEVICE_BUILD", 1) && !TAKE_EXPERIMENTAL;
     HostBuild hb;
-    if (int rc = host_build(d, host_threads(), hb)) return rc;
+    std::shared_ptr<RefJob> job;
+    if (device_build) job = start_reference_tree(d, host_threads());
+    else if (int rc = host_build(d, host_threads(), hb)) return rc;
     TakeMulti *m = new TakeMulti;
     m->ndev = ndev;
     m->devices.assign(devices, devices + ndev);
@@ -1682,7 +1768,7 @@ int take_gpu_multi_create(int ndev, const int *devices, const TakeSceneDesc *d, 
     for (int i = 0; i < ndev; ++i) {
         pool.emplace_back([&, i]() {
             auto body = [&]() -> int {
-                if (int rc = scene_create_from(devices[i], d, &hb, &m->scenes[i])) return rc;
+                if (int rc = scene_create_from(devices[i], d, device_build ? nullptr : &hb, &m->scenes[i], job)) return rc;
                 CU(cudaMalloc((void **)&m->d_sum[i], bytes));
                 CU(cudaMalloc((void **)&m->d_sq[i], bytes));
                 CU(cudaEventCreate(&m->e0[i]));

@@ -407,6 +407,8 @@ __device__ __forceinline__ void trace_fast4(const DevScene &sc, D3 o, D3 d, doub
                 if (ok) {
                     const long long bits = __double_as_longlong(a1.y);
                     const int32_t prim = (int32_t)(bits & 0xffffffffLL), rank = (int32_t)(bits >> 32);
+                    // (an accepted t equal to the current hit's: the only place the rank decides anything -- counted, see DevScene)
+                    if (!ANY_HIT && out.prim >= 0 && !(t < best_t)) atomicAdd(sc.tie_count, 1ULL);
                     if (t < best_t || out.prim < 0 || rank > out.rank) {
                         out.prim = prim; out.rank = rank; out.t = t; out.u = bu; out.v = bv;
                         best_t = t;
@@ -522,6 +524,7 @@ __device__ __forceinline__ void trace_packet4(const DevScene &sc, D3 o, D3 d, do
                 if (ok) {
                     const long long bits = __double_as_longlong(a1.y);
                     const int32_t prim = (int32_t)(bits & 0xffffffffLL), rank = (int32_t)(bits >> 32);
+                    if (out.prim >= 0 && !(t < best_t)) atomicAdd(sc.tie_count, 1ULL);   // the rank decides: counted (DevScene)
                     if (t < best_t || out.prim < 0 || rank > out.rank) {
                         out.prim = prim; out.rank = rank; out.t = t; out.u = bu; out.v = bv;
                         best_t = t;

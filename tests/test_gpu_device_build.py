@@ -192,3 +192,53 @@ def test_scene_create_does_not_wait_for_the_reference_tree(gpu_lib):
               "; reference-order tree", round(info["build_ms_reference_tree"], 1), "ms in the background")
     finally:
         gs.close()
+
+
+def test_render_ahead_of_the_reference_tree(gpu_lib, monkeypatch):
+    """take_gpu_render does not wait for the background reference-order tree: it renders at once, counts the leaf tests in which
+    a tie-break rank decided anything, and repeats the call after the join only if there were any.  TAKE_REF_DELAY_MS keeps the
+    tree 'under construction' long enough to observe both outcomes."""
+    import time
+    # (a) an ordinary scene: no exact ties -> the provisional image stands, and it is the image of a host-built scene
+    flat = scenes.cornell_box(64, 64, 4, materials="mixed").flat()
+    monkeypatch.setenv("TAKE_DEVICE_BUILD", "0")
+    host = api.GpuScene(flat)
+    monkeypatch.delenv("TAKE_DEVICE_BUILD")
+    want = {integ: host.render_sums(integ, 5, 0, 4, seed=11) for integ in ("mis", "one_sample_mis")}
+    host.close()
+    monkeypatch.setenv("TAKE_REF_DELAY_MS", "1500")
+    gs = api.GpuScene(flat)
+    t0 = time.perf_counter()
+    got = {integ: gs.render_sums(integ, 5, 0, 4, seed=11) for integ in ("mis", "one_sample_mis")}
+    dt = time.perf_counter() - t0
+    st = gs.provisional_stats()
+    assert gs.create_timings()["reference_tree_pending"] == 1 and dt < 1.0        # still pending: nothing waited for it
+    assert st == {"provisional_renders": 2, "provisional_reruns": 0}
+    for integ in want:
+        assert np.array_equal(got[integ][0], want[integ][0]) and np.array_equal(got[integ][1], want[integ][1])
+        assert got[integ][2]["extend_rays"] == want[integ][2]["extend_rays"]
+    # accumulating entry point: the snapshot / restore must leave earlier contents alone
+    p, _, _ = gs.intersect(api.make_rays([[0, 1, 3.8]], [[0.01, 0.02, -1.0]]), exact=True)   # joins the tree
+    assert gs.create_timings()["reference_tree_pending"] == 0
+    again = gs.render_sums("mis", 5, 0, 4, seed=11)
+    assert np.array_equal(again[0], want["mis"][0]) and gs.provisional_stats()["provisional_renders"] == 2
+    gs.close()
+    # (b) 37 coincident triangles: every hit is an exact tie -> the provisional render is thrown away and repeated
+    b = scenes.SceneBuilder(16, 16, (0, 0, 5), (0, 0, 0), background=(0.1, 0.1, 0.1))
+    m = b.material(sceneio.MAT_DIFFUSE, (0.5, 0.5, 0.5))
+    black = b.material(sceneio.MAT_DIFFUSE, (0, 0, 0))
+    b.mesh([(-1, -1, 0), (1, -1, 0), (0, 1, 0)], [[0, 1, 2]] * 37, [(0, 0, 1)] * 3, None, m)
+    b.quad((-1, 3, -1), (1, 3, -1), (1, 3, 1), (-1, 3, 1), black, radiance=(5, 5, 5))
+    flat = b.flat()
+    monkeypatch.delenv("TAKE_REF_DELAY_MS")
+    monkeypatch.setenv("TAKE_DEVICE_BUILD", "0")
+    host = api.GpuScene(flat)
+    monkeypatch.delenv("TAKE_DEVICE_BUILD")
+    want = host.render_sums("mis", 5, 0, 3, seed=2)
+    host.close()
+    monkeypatch.setenv("TAKE_REF_DELAY_MS", "300")
+    gs = api.GpuScene(flat)
+    got = gs.render_sums("mis", 5, 0, 3, seed=2)
+    assert gs.provisional_stats() == {"provisional_renders": 1, "provisional_reruns": 1}
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    gs.close()

@@ -30,7 +30,7 @@ try:
     d = json.load(open("gpurun_out/bench_n1.json"))
     print({k: d[k] for k in ("value", "ms_per_step", "scene_create_ms")}, "e2e", d["e2e"]["value"], "frac", d["roofline"]["frac"])
     for r in d.get("scenes", []):
-        print({k: (round(v, 1) if isinstance(v, float) else v) for k, v in r.items() if k in ("key", "job_ms", "mrays_per_s", "samples_per_s", "scene_create_ms", "scene_ready_ms", "e2e_job_ms", "error")})
+        print({k: (round(v, 1) if isinstance(v, float) else v) for k, v in r.items() if k in ("key", "job_ms", "mrays_per_s", "samples_per_s", "scene_create_ms", "e2e_job_ms", "e2e_job_cold_ms", "provisional", "error")})
 except Exception as e:
     print("bench line unreadable:", e)
 EOF
