@@ -35,7 +35,7 @@ EXPORTS = [
     "take_gpu_builder_create", "take_gpu_builder_destroy", "take_gpu_builder_add_ply", "take_gpu_builder_add_mesh",
     "take_gpu_builder_add_sphere", "take_gpu_builder_add_point_light", "take_gpu_builder_finish", "take_gpu_builder_timings",
     "take_gpu_scene_desc_save", "take_gpu_scene_create_timings", "take_gpu_scene_debug_tree",
-    "take_gpu_scene_provisional_stats",
+    "take_gpu_scene_provisional_stats", "take_gpu_release_cached_memory",
 ]
 
 RAY_DTYPE = np.dtype([("origin", "<f8", 3), ("dir", "<f8", 3), ("tmin", "<f8"), ("tmax", "<f8")])

@@ -6,6 +6,23 @@ from take_b200 import api, scenes
 
 SCENES = {"c1": scenes.cornell_box, "c2": scenes.heightfield, "c3": scenes.ibl_scene, "c4": scenes.multi_light, "c5": scenes.instanced_spheres}
 want = [a for a in sys.argv[1:] if a in SCENES] or list(SCENES)
+if "--cold" in sys.argv:
+    # what a process that renders one scene after another sees: every scene created ONCE, rendered (wave buffers allocated),
+    # destroyed; TAKE_MEMPOOL=0 / 1 in the environment selects plain cudaMalloc or the cached pool
+    for key in want:
+        flat = SCENES[key]().flat()
+        t0 = time.perf_counter()
+        gs = api.GpuScene(flat)
+        t_create = time.perf_counter() - t0
+        ph = gs.create_timings()
+        gs.render_sums("mis", 5, 0, 2, seed=1, sumsq=False)
+        t_first = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        gs.close()
+        print(json.dumps({"scene": key, "mempool": os.environ.get("TAKE_MEMPOOL", "1"), "create_ms": round(1e3 * t_create, 1),
+                          "create_plus_2spp_ms": round(1e3 * t_first, 1), "destroy_ms": round(1e3 * (time.perf_counter() - t1), 1),
+                          "phases_ms": {k: round(v, 1) for k, v in ph.items() if k.endswith("_ms")}}), flush=True)
+    sys.exit(0)
 warm = api.GpuScene(scenes.cornell_box(16, 16, 1).flat()); warm.close()     # CUDA context + module load
 for key in want:
     flat = SCENES[key]().flat()
