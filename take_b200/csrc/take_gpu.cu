@@ -931,14 +931,27 @@ static int device_build_fast_tree(TakeScene *s, int max_leaf, double &abs_max) {
 // tree on a background host thread.
 static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild *hb, TakeScene **out, std::shared_ptr<RefJob> job) {
     *out = nullptr;
+    // TAKE_TIMING=1: every step of the call on stderr (development aid)
+    const bool timing = env_int("TAKE_TIMING", 0) != 0;
+    const double t_begin = now_ms();
+    double t_last = t_begin;
+    auto mark = [&](const char *what) {
+        if (!timing) return;
+        const double t = now_ms();
+        fprintf(stderr, "[take_gpu] scene_create %-28s %8.2f ms (at %8.2f)\n", what, t - t_last, t - t_begin);
+        t_last = t;
+    };
     CU(cudaSetDevice(device));
     TakeScene *s = new TakeScene;
     struct Guard { TakeScene *&p; bool ok = false; ~Guard() { if (!ok) { delete p; p = nullptr; } } } guard{s};
     s->device = device;
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
-    s->sm_count = prop.multiProcessorCount;
+    mark("set device");
+    int sm_count = 0;   // (cudaGetDeviceProperties fills ~1 KB of fields through dozens of driver queries: one attribute is enough)
+    CU(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+    s->sm_count = sm_count;
+    mark("device attribute");
     CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    mark("stream");
     cudaStream_t st = s->stream;
     const int64_t n = d->num_prims;
     const int threads = host_threads();
@@ -972,9 +985,11 @@ static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild *hb, 
         if ((rc = upload(s->dfs_rank, hb->ref.dfs_rank.data(), hb->ref.dfs_rank.size(), st))) return rc;
     } else {
         // the reference-order tree goes on in the background (one job for all replicas of a multi-GPU handle)
+        mark("material types");
         s->ref_job = job ? job : start_reference_tree(d, threads);
         s->ref_pending = true;
         s->create_ms[2] = now_ms() - t_mark;
+        mark("boxes + reference thread");
         CU(s->ref_nodes.ensure(64));
         CU(s->dfs_rank.ensure(16));
     }
@@ -1064,6 +1079,7 @@ static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild *hb, 
     v.ref_nodes = s->ref_nodes.as<RefNode>();
     v.ref_root = hb ? hb->ref.root : -1;
     s->create_ms[1] = now_ms() - t_mark;
+    mark("uploads");
     v.positions = s->positions.as<double>(); v.normals = s->normals.as<double>(); v.uvs = s->uvs.as<double>();
     v.indices = s->indices.as<int32_t>(); v.prim_material = s->prim_material.as<int32_t>();
     v.prim_light = s->prim_light.as<int32_t>(); v.dfs_rank = s->dfs_rank.as<int32_t>();
@@ -1123,6 +1139,7 @@ static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild *hb, 
         v.tris = s->tris.as<double2>();
         s->device_built = true;
         s->build_ms_fast = s->create_ms[3] = now_ms() - t_mark;
+        mark("device build");
     }
     v.fast_depth = s->fast_depth;
     v.abs_max = (float)abs_max;
@@ -1148,6 +1165,7 @@ static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild *hb, 
         CU(cudaStreamSynchronize(st));
     }
     s->create_ms[4] = now_ms() - t_mark;
+    mark("records");
 
     // persistent-kernel launch widths: every SM filled to the occupancy the kernel allows
     auto blocks_for = [&](const void *fn) {
@@ -1182,8 +1200,10 @@ static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild *hb, 
         s->persist_shadow = env_int("TAKE_PERSIST_SHADOW", 0);
     }
 #endif
+    mark("occupancy queries");
     CU(s->fetch.ensure(256));
     apply_l2_policy(s, s->stream);
+    mark("tail");
     guard.ok = true;
     *out = s;
     return TAKE_OK;
