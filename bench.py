@@ -545,6 +545,8 @@ def scene_job(key, entry, sr, local, world, rank, barrier, allmax, allsum, peak,
         phases = sr.gs.create_timings()
         sr.submit(integ, MAX_DEPTH, 0, spp_job, seed=SEED, to_host=True).wait()
         cold_ms = 1e3 * allmax(time.perf_counter() - t0)
+        prov = sr.gs.provisional_stats()
+        sr.gs.info()        # joins the reference-order tree and uploads it, so that the warm job below does not contain that
     try:
         if not own:   # warm-up with the wave capacity of the real job (wave buffers and pinned memory are allocated on first use)
             per_rank = -(-spp_job // world)
@@ -568,7 +570,7 @@ def scene_job(key, entry, sr, local, world, rank, barrier, allmax, allsum, peak,
             row["scene_create_phases_ms"] = {k: round(v, 2) for k, v in phases.items()}
             row["e2e_job_ms"] = create_ms + 1e3 * job_s      # create + render + reduce + read-back (the Amdahl term)
             row["e2e_job_cold_ms"] = cold_ms                 # the same measured cold in one go: + first-use allocations (wave buffers, pinned memory)
-            row["provisional"] = sr.gs.provisional_stats()   # renders that ran ahead of the background reference-order tree / repeated
+            row["provisional"] = prov                        # renders that ran ahead of the background reference-order tree / repeated
         if note:
             row["note"] = note
         if rank == 0 and world == 1:

@@ -406,6 +406,7 @@ int ensure_wave(TakeScene *s, int64_t capacity, int sets, int passes) {
     capacity = std::max(capacity, s->wave_capacity);
     sets = std::max(sets, s->wave_sets);
     passes = std::max(passes, s->wave_passes);
+    const double t_alloc = now_ms();
     for (int i = 0; i < sets; ++i) {
         TakeScene::WaveBuffers &b = s->wb[i];
         CU(b.ray.ensure(capacity * sizeof(RayRec)));
@@ -423,6 +424,9 @@ int ensure_wave(TakeScene *s, int64_t capacity, int sets, int passes) {
     s->wave_capacity = capacity;
     s->wave_sets = sets;
     s->wave_passes = passes;
+    if (env_int("TAKE_TIMING", 0))
+        fprintf(stderr, "[take_gpu] wave buffers: %d set(s) x %lld slots (%.2f GB) allocated in %.1f ms\n", sets, (long long)capacity,
+                sets * capacity * 332.0 / 1e9, now_ms() - t_alloc);
     return TAKE_OK;
 }
 
