@@ -158,14 +158,19 @@ typedef struct TakeRenderOpts {
     int64_t spp_end;      /* multi-GPU sharding.  Results depend only on (seed, pixel, index).     */
     uint64_t seed;
     int32_t flags;        /* TAKE_RENDER_* */
-    int32_t reserved;
+    int32_t reserved;     /* with TAKE_RENDER_RUSSIAN_ROULETTE: first loop iteration that plays (0 = the default, 3); else 0 */
 } TakeRenderOpts;
 
 enum {
     TAKE_RENDER_DEFAULT = 0,
     TAKE_RENDER_NO_SORT = 1,     /* disable the per-bounce material sort (A/B measurements)                    */
     TAKE_RENDER_STAGE_TIMES = 2, /* bracket every kernel with CUDA events and fill TakeStats::ms_<stage>       */
-    TAKE_RENDER_COUNT_TESTS = 4  /* run the instrumented traversal kernels and fill box_tests / tri_tests      */
+    TAKE_RENDER_COUNT_TESTS = 4, /* run the instrumented traversal kernels and fill box_tests / tri_tests      */
+    /* EXTENSION (the reference's README.md:19-24 lists Russian roulette as a goal; its integrators have none): from loop
+     * iteration `reserved` (default 3) on, a path survives with probability q = min(max component of its throughput, 0.95)
+     * and its throughput is divided by q -- unbiased, one extra random draw per iteration.  Off by default: without the flag
+     * every result is the reference's.  Parity unpinned (checked against our own CPU restatement and for unbiasedness). */
+    TAKE_RENDER_RUSSIAN_ROULETTE = 8
 };
 
 typedef struct TakeStats {

@@ -181,6 +181,11 @@ class OracleScene:
             self.lib.oracle_scene_free(self.h)
             self.h = None
 
+    def set_russian_roulette(self, rr_start: int):
+        """EXTENSION (no reference counterpart): Russian roulette from loop iteration rr_start on; 0 = off."""
+        self.lib.oracle_set_russian_roulette.argtypes = [C.c_void_p, C.c_int]
+        self.lib.oracle_set_russian_roulette(self.h, int(rr_start))
+
     def bvh(self):
         n = self.lib.oracle_bvh_size(self.h)
         box = np.empty((n, 6), np.float64)

@@ -124,6 +124,9 @@ struct Scene {
     // tables of the power-sampling integrator (path_tracing.h:274-380): pmf[i] = light_power(i) / total, cdf = N + 1 running
     // sums from 0 to exactly 1 -- the layout light.cpp:9-23 reads; nothing in the reference fills them (ref_harness.cpp does)
     std::vector<double> power_pmf, power_cdf;
+    // EXTENSION (README.md:19-24 lists Russian roulette as a goal; the reference has none): from loop iteration rr_start on,
+    // a path survives with probability q = min(max component of the throughput, 0.95) and is divided by q.  0 = off.
+    int rr_start = 0;
     // number of entries of the uniform light pick: the scene's lights plus, when it is sampled, the environment
     size_t pick_count() const { return lights.size() + ((has_env() && env_sample) ? 1 : 0); }
 };
@@ -719,6 +722,17 @@ inline double light_pdf_area(const Scene &sc, int light_id, V3 light_pos, V3 ref
 inline bool is_specular(const TakeMaterialDesc &m) { return m.type == TAKE_MAT_PLASTIC || m.type == TAKE_MAT_MIRROR; }
 inline V3 intensity(const TakeLightDesc &l) { return {l.intensity[0], l.intensity[1], l.intensity[2]}; }
 
+// EXTENSION: Russian roulette at the top of loop iteration i (one extra draw per iteration from rr_start on); false = the
+// path ends here.  Unbiased: the survivors are divided by their survival probability.
+inline bool rr_survives(const Scene &sc, int i, V3 &throughput, Rng &rng) {
+    if (sc.rr_start <= 0 || i < sc.rr_start) return true;
+    const double q = fmin(fmax(fmax(throughput.x, throughput.y), throughput.z), 0.95);
+    if (!(q > 0)) return false;
+    if (rng.next() >= q) return false;
+    throughput = divs(throughput, q);
+    return true;
+}
+
 // ---- src/integrator/path_tracing.h:5-111 ---------------------------------------------------------
 V3 path_tracing(const Scene &sc, Ray r, Rng &rng, int max_depth, Counters &cn) {
     Isect v;
@@ -729,6 +743,7 @@ V3 path_tracing(const Scene &sc, Ray r, Rng &rng, int max_depth, Counters &cn) {
     if (v.light != -1 && sc.lights[v.light].kind == TAKE_LIGHT_AREA)
         radiance = add(radiance, mulv(throughput, intensity(sc.lights[v.light])));
     for (int i = 0; i <= max_depth; ++i) {
+        if (!rr_survives(sc, i, throughput, rng)) break;
         cn.shaded++;
         V3 dir_in = neg(r.d);
         const TakeMaterialDesc &m = sc.mats[v.material];
@@ -822,6 +837,7 @@ V3 path_tracing_raw(const Scene &sc, Ray r, Rng &rng, int max_depth, Counters &c
             // `if (v.area_light_id != -1) {... get_if fails ...} else {...}`: a hit on a non-area light id does nothing
             continue;
         }
+        if (!rr_survives(sc, i, throughput, rng)) break;
         cn.shaded++;
         V3 dir_in = neg(r.d);
         const TakeMaterialDesc &m = sc.mats[v.material];
@@ -855,6 +871,7 @@ V3 path_tracing_one_sample_mis(const Scene &sc, Ray r, Rng &rng, int max_depth, 
             radiance = add(radiance, mulv(throughput, intensity(sc.lights[v.light])));
             break;
         }
+        if (!rr_survives(sc, i, throughput, rng)) break;
         cn.shaded++;
         V3 dir_in = neg(r.d);
         const TakeMaterialDesc &m = sc.mats[v.material];
@@ -957,6 +974,7 @@ V3 path_tracing_one_sample_mis_power(const Scene &sc, Ray r, Rng &rng, int max_d
             radiance = add(radiance, mulv(throughput, intensity(sc.lights[v.light])));
             break;
         }
+        if (!rr_survives(sc, i, throughput, rng)) break;
         cn.shaded++;
         V3 dir_in = neg(r.d);
         const TakeMaterialDesc &m = sc.mats[v.material];
@@ -1101,6 +1119,8 @@ void build_power_tables(Scene &sc) {
 }
 
 extern "C" {
+
+void oracle_set_russian_roulette(void *h, int rr_start) { ((Scene *)h)->rr_start = rr_start; }
 
 void *oracle_scene_create(const TakeSceneDesc *d) {
     Scene *sc = new Scene;

@@ -23,7 +23,7 @@ LIB_PATH = os.environ.get("TAKE_GPU_LIB") or os.path.join(_HERE, "libtake_gpu.so
 
 INTEGRATORS = {"mis": 0, "raw": 1, "one_sample_mis": 2, "one_sample_mis_power": 3}
 ISECT_FAST, ISECT_EXACT = 0, 1
-RENDER_NO_SORT, RENDER_STAGE_TIMES, RENDER_COUNT_TESTS = 1, 2, 4
+RENDER_NO_SORT, RENDER_STAGE_TIMES, RENDER_COUNT_TESTS, RENDER_RUSSIAN_ROULETTE = 1, 2, 4, 8
 
 EXPORTS = [
     "take_gpu_device_count", "take_gpu_scene_create", "take_gpu_scene_destroy", "take_gpu_intersect",
@@ -265,7 +265,8 @@ class GpuScene:
         return occ
 
     def _opts(self, integrator, max_depth, spp_begin, spp_end, seed, flags=0):
-        return TakeRenderOpts(INTEGRATORS[integrator], max_depth, spp_begin, spp_end, seed, flags, 0)
+        # (rr_start: first loop iteration of the Russian-roulette extension, used with RENDER_RUSSIAN_ROULETTE; 0 = default 3)
+        return TakeRenderOpts(INTEGRATORS[integrator], max_depth, spp_begin, spp_end, seed, flags, getattr(self, "rr_start", 0))
 
     # the tile loop of render() (src/render.cpp:59-82): sums of samples [spp_begin, spp_end) per pixel
     def render_sums(self, integrator="mis", max_depth=5, spp_begin=0, spp_end=1, seed=0, sumsq=True, flags=0):

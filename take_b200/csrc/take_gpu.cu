@@ -593,6 +593,7 @@ void fill_wave_ptrs(TakeScene *s, Wave &w, const TakeRenderOpts *o, int set = 0)
     w.sort_branch = (w.sort_enabled && (o->integrator == TAKE_INTEGRATOR_ONE_SAMPLE_MIS || o->integrator == TAKE_INTEGRATOR_ONE_SAMPLE_MIS_POWER) && n_pick > 0 &&
                      !env_int("TAKE_NO_SORT_BRANCH", 0)) ? 1 : 0;
     w.seed = o->seed;
+    w.rr_start = (o->flags & TAKE_RENDER_RUSSIAN_ROULETTE) ? (o->reserved > 0 ? o->reserved : 3) : 0;
 #if TAKE_EXPERIMENTAL
     w.fused_primary = (s->traversal != 2 && !env_int("TAKE_NO_FUSE", 0)) ? 1 : 0;
 #else

@@ -122,6 +122,7 @@ struct Wave {
     int32_t fused_primary;  // 1: no k_generate -- pass 0 of extend and shade compute the camera ray themselves
     int32_t miss_fast;      // 1: camera rays that leave the scene are finished by k_extend itself (see k_extend)
     int32_t packet;         // 1: pass 0 runs k_extend_primary (the warp's camera rays traverse as a packet)
+    int32_t rr_start;       // EXTENSION: Russian roulette from this loop iteration on (0 = off, the reference's behaviour)
     int32_t tile_w;  // > 0: image width, pixels are enumerated in 8x4 tiles (one warp = one tile); 0: row-major
     uint64_t seed;
 };
@@ -199,7 +200,11 @@ __device__ __forceinline__ void queue_push(bool want, int32_t *queue, uint32_t *
 
 // Camera ray of a slot: src/render.cpp:69-75 (jittered pinhole; first draw -> x, second -> y).  Consumes 2 draws.
 // The coin the one-sample integrator will flip first at the vertex this stream reaches next: draw number rng.k.
-__device__ __forceinline__ int32_t peek_branch(Rng rng) { return rng.next() <= 0.5 ? 1 : 0; }
+// (`skip`: the iteration the ray arrives in starts with a Russian-roulette draw, so the coin is the draw after it)
+__device__ __forceinline__ int32_t peek_branch(Rng rng, bool skip = false) {
+    if (skip) rng.next();
+    return rng.next() <= 0.5 ? 1 : 0;
+}
 
 __device__ __forceinline__ void primary_ray(const DevScene &sc, const Wave &w, int slot, D3 &o, D3 &dir, Rng &rng) {
     uint32_t pixel;
@@ -451,6 +456,18 @@ struct ShadeCtx {
     int shaded;    // integrator loop iterations entered (statistics)
 };
 
+// EXTENSION (README.md:19-24 of the reference lists Russian roulette as a goal; it has none): at the top of loop iteration
+// c.depth, from rr_start on, the path survives with probability q = min(max component of the throughput, 0.95) and is divided
+// by q -- one extra draw per iteration, the same in oracle/take_oracle.cpp (rr_survives).  false = the path ends here.
+__device__ __forceinline__ bool russian_roulette(ShadeCtx &c) {
+    if (c.w.rr_start <= 0 || c.depth < c.w.rr_start) return true;
+    const double q = fmin(fmax(fmax(c.thr.x, c.thr.y), c.thr.z), 0.95);
+    if (!(q > 0)) return false;
+    if (c.rng.next() >= q) return false;
+    c.thr = divs(c.thr, q);
+    return true;
+}
+
 // NEE light-sample geometry shared by the integrators: path_tracing.h:31-43 / :189-200.
 // Returns false when the reference `break`s (light_pdf <= 0).
 __device__ __forceinline__ bool nee_sample(const DevScene &sc, const TakeLightDesc &l, int light_id, const Isect &v, Rng &rng,
@@ -516,6 +533,7 @@ __device__ __forceinline__ void shade_mis(ShadeCtx &c, const RayRec &ray, const 
         c.thr = mulv(c.thr, divs(FG, bpdf));  // :107
     }
     if (c.depth > c.w.max_depth) return;  // loop bound :20
+    if (!russian_roulette(c)) return;
     c.shaded += 1;
     const D3 dir_in = neg(d);
     const TakeMaterialDesc &m = sc.materials[v.material];
@@ -585,6 +603,7 @@ __device__ __forceinline__ void shade_raw(ShadeCtx &c, const RayRec &ray, const 
         if (sc.lights[v.light].kind == TAKE_LIGHT_AREA) c.rad = add(c.rad, mulv(c.thr, light_intensity(sc.lights[v.light])));
         return;
     }
+    if (!russian_roulette(c)) return;
     c.shaded += 1;
     const D3 dir_in = neg(d);
     const TakeMaterialDesc &m = sc.materials[v.material];
@@ -675,6 +694,7 @@ __device__ __forceinline__ void shade_one_sample(ShadeCtx &c, const RayRec &ray,
             c.rad = add(c.rad, mulv(c.thr, light_intensity(sc.lights[v.light])));
             return;
         }
+        if (!russian_roulette(c)) return;
         c.shaded += 1;
         const TakeMaterialDesc &m = sc.materials[v.material];
         const bool spec = is_specular(m.type);
@@ -856,7 +876,7 @@ __global__ void __launch_bounds__(128, TAKE_SHADE_MIN_BLOCKS) k_shade(DevScene s
                     r.tmax = INFINITY;
                     // the coin of the vertex this ray will reach is the stream's next draw (see TAKE_KEY_BITS)
                     r.aux0 = ((INTEGRATOR == TAKE_INTEGRATOR_ONE_SAMPLE_MIS || INTEGRATOR == TAKE_INTEGRATOR_ONE_SAMPLE_MIS_POWER) && w.sort_branch &&
-                              emit_extend) ? peek_branch(c.rng) : 0;
+                              emit_extend) ? peek_branch(c.rng, w.rr_start > 0 && c.depth >= w.rr_start) : 0;
                     r.aux1 = 0;
                     w.ray[slot] = r;
                 }
