@@ -502,8 +502,11 @@ int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, d
         tm.cur_pass = b;
         tm.begin(ST_EXTEND);
         if (b == 0 && w.packet) {
-            if (count) k_extend_primary<true><<<s->blocks_extend_primary, 128, 0, st>>>(s->dev, w);
+            if (w.count_ties) k_extend_primary<false, true><<<s->blocks_extend_primary, 128, 0, st>>>(s->dev, w);
+            else if (count) k_extend_primary<true><<<s->blocks_extend_primary, 128, 0, st>>>(s->dev, w);
             else k_extend_primary<false><<<s->blocks_extend_primary, 128, 0, st>>>(s->dev, w);
+        } else if (w.count_ties && s->wide) {
+            k_extend<false, true, true><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
         } else
 #if TAKE_EXPERIMENTAL
         if (s->traversal == 2) {
@@ -531,7 +534,9 @@ int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, d
         }
         tm.begin(ST_SHADE);
         const bool env = s->dev.env_rgb != nullptr;
-#define TAKE_SHADE(I) (env ? k_shade<I, true><<<shade_blocks, 128, 0, st>>>(s->dev, w, b) : k_shade<I, false><<<shade_blocks, 128, 0, st>>>(s->dev, w, b))
+#define TAKE_SHADE(I) (env ? k_shade<I, true><<<shade_blocks, 128, 0, st>>>(s->dev, w, b)                         \
+                           : w.rr_start > 0 ? k_shade<I, false, true><<<shade_blocks, 128, 0, st>>>(s->dev, w, b) \
+                                            : k_shade<I, false><<<shade_blocks, 128, 0, st>>>(s->dev, w, b))
         if (o->integrator == TAKE_INTEGRATOR_MIS) TAKE_SHADE(TAKE_INTEGRATOR_MIS);
         else if (o->integrator == TAKE_INTEGRATOR_RAW) TAKE_SHADE(TAKE_INTEGRATOR_RAW);
         else if (o->integrator == TAKE_INTEGRATOR_ONE_SAMPLE_MIS) TAKE_SHADE(TAKE_INTEGRATOR_ONE_SAMPLE_MIS);
@@ -646,6 +651,8 @@ int check_opts(const TakeScene *s, const TakeRenderOpts *o) {
     if (o->max_depth < -1 || o->max_depth > TAKE_MAX_DEPTH)
         return fail(TAKE_E_INVALID, "max_depth out of range (-1 .. " + std::to_string(TAKE_MAX_DEPTH) + ")");
     if (o->spp_end < o->spp_begin) return fail(TAKE_E_INVALID, "spp_end < spp_begin");
+    if ((o->flags & TAKE_RENDER_RUSSIAN_ROULETTE) && s->dev.env_rgb)
+        return fail(TAKE_E_INVALID, "the Russian-roulette extension is not compiled for scenes with an environment map");
     return TAKE_OK;
 }
 
@@ -1587,6 +1594,7 @@ int render_enqueue(TakeScene *s, const TakeRenderOpts *o, double *d_sum, double 
     fill_wave_ptrs(s, w[0], o, 0);
     if (sets == 2) fill_wave_ptrs(s, w[1], o, 1);
     w[0].totals = w[1].totals = d_totals;
+    w[0].count_ties = w[1].count_ties = provisional ? 1 : 0;
     cudaEvent_t prev_acc = nullptr;
     for (int64_t base = 0; base < npix; base += chunk_pixels) {
         const int64_t cp = std::min(chunk_pixels, npix - base);

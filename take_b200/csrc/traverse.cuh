@@ -317,7 +317,9 @@ __device__ __forceinline__ void cswap(uint32_t &a, uint32_t &b) {
     a = lo; b = hi;
 }
 
-template <bool ANY_HIT, bool COUNT>
+// TIES: count the accepted leaf tests whose t equals the current hit's (DevScene::tie_count) -- only compiled into the kernels
+// of a render that runs ahead of the tie-break ranks (take_gpu.cu); elsewhere it would cost registers the kernels do not have.
+template <bool ANY_HIT, bool COUNT, bool TIES = false>
 __device__ __forceinline__ void trace_fast4(const DevScene &sc, D3 o, D3 d, double tmin, double tmax, TravStack &st,
                                             HitOut &out, TravCounters *cnt) {
     out.prim = -1; out.rank = -1; out.t = 0; out.u = 0; out.v = 0;
@@ -408,7 +410,7 @@ __device__ __forceinline__ void trace_fast4(const DevScene &sc, D3 o, D3 d, doub
                     const long long bits = __double_as_longlong(a1.y);
                     const int32_t prim = (int32_t)(bits & 0xffffffffLL), rank = (int32_t)(bits >> 32);
                     // (an accepted t equal to the current hit's: the only place the rank decides anything -- counted, see DevScene)
-                    if (!ANY_HIT && out.prim >= 0 && !(t < best_t)) atomicAdd(sc.tie_count, 1ULL);
+                    if (TIES && !ANY_HIT && out.prim >= 0 && !(t < best_t)) atomicAdd(sc.tie_count, 1ULL);
                     if (t < best_t || out.prim < 0 || rank > out.rank) {
                         out.prim = prim; out.rank = rank; out.t = t; out.u = bu; out.v = bv;
                         best_t = t;
@@ -443,7 +445,7 @@ __device__ __forceinline__ void trace_fast4(const DevScene &sc, D3 o, D3 d, doub
 // ---------------------------------------------------------------------------------------------------------
 #define TAKE_PACKET_STACK 64   // entries of the shared per-warp stack (3 per level of the 4-wide tree + 1; checked on the host)
 
-template <bool COUNT>
+template <bool COUNT, bool TIES = false>
 __device__ __forceinline__ void trace_packet4(const DevScene &sc, D3 o, D3 d, double tmin, double tmax, bool valid, uint2 *wstack,
                                               HitOut &out, TravCounters *cnt) {
     out.prim = -1; out.rank = -1; out.t = 0; out.u = 0; out.v = 0;
@@ -524,7 +526,7 @@ __device__ __forceinline__ void trace_packet4(const DevScene &sc, D3 o, D3 d, do
                 if (ok) {
                     const long long bits = __double_as_longlong(a1.y);
                     const int32_t prim = (int32_t)(bits & 0xffffffffLL), rank = (int32_t)(bits >> 32);
-                    if (out.prim >= 0 && !(t < best_t)) atomicAdd(sc.tie_count, 1ULL);   // the rank decides: counted (DevScene)
+                    if (TIES && out.prim >= 0 && !(t < best_t)) atomicAdd(sc.tie_count, 1ULL);   // the rank decides: counted (DevScene)
                     if (t < best_t || out.prim < 0 || rank > out.rank) {
                         out.prim = prim; out.rank = rank; out.t = t; out.u = bu; out.v = bv;
                         best_t = t;
@@ -672,18 +674,18 @@ __device__ __forceinline__ void trace_spec4(const DevScene &sc, D3 o, D3 d, doub
 #endif
 
 // Dispatch on the tree width chosen at scene creation (the shipped library only has the 4-wide tree).
-template <bool ANY_HIT, bool COUNT, bool WIDE>
+template <bool ANY_HIT, bool COUNT, bool WIDE, bool TIES = false>
 __device__ __forceinline__ void trace_any(const DevScene &sc, D3 o, D3 d, double tmin, double tmax, TravStack &st, HitOut &out,
                                           TravCounters *cnt) {
 #if TAKE_EXPERIMENTAL
     if (WIDE) {
         if (TAKE_SPECULATE) trace_spec4<ANY_HIT, COUNT>(sc, o, d, tmin, tmax, st, out, cnt);
-        else trace_fast4<ANY_HIT, COUNT>(sc, o, d, tmin, tmax, st, out, cnt);
+        else trace_fast4<ANY_HIT, COUNT, TIES>(sc, o, d, tmin, tmax, st, out, cnt);
     }
     else trace_fast<ANY_HIT, COUNT>(sc, o, d, tmin, tmax, st, out, cnt);
 #else
     static_assert(WIDE, "binary-node traversal needs -DTAKE_EXPERIMENTAL=1");
-    trace_fast4<ANY_HIT, COUNT>(sc, o, d, tmin, tmax, st, out, cnt);
+    trace_fast4<ANY_HIT, COUNT, TIES>(sc, o, d, tmin, tmax, st, out, cnt);
 #endif
 }
 

@@ -122,6 +122,7 @@ struct Wave {
     int32_t fused_primary;  // 1: no k_generate -- pass 0 of extend and shade compute the camera ray themselves
     int32_t miss_fast;      // 1: camera rays that leave the scene are finished by k_extend itself (see k_extend)
     int32_t packet;         // 1: pass 0 runs k_extend_primary (the warp's camera rays traverse as a packet)
+    int32_t count_ties;     // 1: a render ahead of the tie-break ranks: the extend kernels count rank-decided ties
     int32_t rr_start;       // EXTENSION: Russian roulette from this loop iteration on (0 = off, the reference's behaviour)
     int32_t tile_w;  // > 0: image width, pixels are enumerated in 8x4 tiles (one warp = one tile); 0: row-major
     uint64_t seed;
@@ -347,7 +348,7 @@ __device__ __forceinline__ void extend_finish(const DevScene &sc, const Wave &w,
     }
 }
 
-template <bool COUNT, bool WIDE>
+template <bool COUNT, bool WIDE, bool TIES = false>
 __global__ void __launch_bounds__(128, TAKE_BOUNCE_MIN_BLOCKS) k_extend(DevScene sc, Wave w, int pass) {
     TAKE_DECLARE_STACK(st);
     PassCounters &pc = w.pass[pass];
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(128, TAKE_BOUNCE_MIN_BLOCKS) k_extend(DevScene
                 o = mk3(r.ox, r.oy, r.oz); d = mk3(r.dx, r.dy, r.dz); tmax = r.tmax;
                 branch = r.aux0;
             }
-            trace_any<false, COUNT, WIDE>(sc, o, d, TAKE_EPS, tmax, st, h, &cnt);
+            trace_any<false, COUNT, WIDE, TIES>(sc, o, d, TAKE_EPS, tmax, st, h, &cnt);
         }
         extend_finish(sc, w, pc, lane, valid, slot, h, branch, primary, miss_fast);
     }
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(128, TAKE_BOUNCE_MIN_BLOCKS) k_extend(DevScene
 }
 
 // Pass 0 with fused camera rays: the warp's 32 rays (the samples of one pixel, or of one 8x4 tile) traverse as a packet.
-template <bool COUNT>
+template <bool COUNT, bool TIES = false>
 __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_extend_primary(DevScene sc, Wave w) {
     __shared__ uint2 pstack[128 / 32][TAKE_PACKET_STACK];
     PassCounters &pc = w.pass[0];
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(128, TAKE_V1_MIN_BLOCKS) k_extend_primary(DevS
         D3 o = mk3(0, 0, 0), d = mk3(0, 0, 0);
         if (valid) primary_ray(sc, w, (int)i, o, d);
         HitOut h;
-        trace_packet4<COUNT>(sc, o, d, TAKE_EPS, INFINITY, valid, wstack, h, &cnt);
+        trace_packet4<COUNT, TIES>(sc, o, d, TAKE_EPS, INFINITY, valid, wstack, h, &cnt);
         extend_finish(sc, w, pc, lane, valid, (int)i, h, 0, true, miss_fast);
     }
     if (COUNT) {
@@ -459,8 +460,11 @@ struct ShadeCtx {
 // EXTENSION (README.md:19-24 of the reference lists Russian roulette as a goal; it has none): at the top of loop iteration
 // c.depth, from rr_start on, the path survives with probability q = min(max component of the throughput, 0.95) and is divided
 // by q -- one extra draw per iteration, the same in oracle/take_oracle.cpp (rr_survives).  false = the path ends here.
+// RR = false compiles it out of the kernels that run the reference's integrators as they are (the check and its live state cost
+// the shade kernels 1-2 %).
+template <bool RR>
 __device__ __forceinline__ bool russian_roulette(ShadeCtx &c) {
-    if (c.w.rr_start <= 0 || c.depth < c.w.rr_start) return true;
+    if (!RR || c.w.rr_start <= 0 || c.depth < c.w.rr_start) return true;
     const double q = fmin(fmax(fmax(c.thr.x, c.thr.y), c.thr.z), 0.95);
     if (!(q > 0)) return false;
     if (c.rng.next() >= q) return false;
@@ -495,7 +499,7 @@ __device__ __forceinline__ D3 miss_rad(const DevScene &sc, D3 d) { return ENV ? 
 
 // Multi-sample MIS: src/integrator/path_tracing.h:5-111.  One call = "finish iteration depth-1 with the hit that
 // just arrived, then run iteration depth up to the point where it needs rays".
-template <bool ENV>
+template <bool ENV, bool RR>
 __device__ __forceinline__ void shade_mis(ShadeCtx &c, const RayRec &ray, const HitRec &hit, const PathRec &path, const PendRec &pend) {
     const DevScene &sc = c.sc;
     const D3 o = mk3(ray.ox, ray.oy, ray.oz), d = mk3(ray.dx, ray.dy, ray.dz);
@@ -533,7 +537,7 @@ __device__ __forceinline__ void shade_mis(ShadeCtx &c, const RayRec &ray, const 
         c.thr = mulv(c.thr, divs(FG, bpdf));  // :107
     }
     if (c.depth > c.w.max_depth) return;  // loop bound :20
-    if (!russian_roulette(c)) return;
+    if (!russian_roulette<RR>(c)) return;
     c.shaded += 1;
     const D3 dir_in = neg(d);
     const TakeMaterialDesc &m = sc.materials[v.material];
@@ -587,7 +591,7 @@ __device__ __forceinline__ void shade_mis(ShadeCtx &c, const RayRec &ray, const 
 }
 
 // No MIS: src/integrator/path_tracing.h:114-157
-template <bool ENV>
+template <bool ENV, bool RR>
 __device__ __forceinline__ void shade_raw(ShadeCtx &c, const RayRec &ray, const HitRec &hit, const PathRec &path, const PendRec &) {
     const DevScene &sc = c.sc;
     const D3 o = mk3(ray.ox, ray.oy, ray.oz), d = mk3(ray.dx, ray.dy, ray.dz);
@@ -603,7 +607,7 @@ __device__ __forceinline__ void shade_raw(ShadeCtx &c, const RayRec &ray, const 
         if (sc.lights[v.light].kind == TAKE_LIGHT_AREA) c.rad = add(c.rad, mulv(c.thr, light_intensity(sc.lights[v.light])));
         return;
     }
-    if (!russian_roulette(c)) return;
+    if (!russian_roulette<RR>(c)) return;
     c.shaded += 1;
     const D3 dir_in = neg(d);
     const TakeMaterialDesc &m = sc.materials[v.material];
@@ -643,7 +647,7 @@ __device__ __forceinline__ bool hit_light_pdf_power(const DevScene &sc, const Is
 // power, path_tracing_one_sample_MIS_power (:274-380): same structure; the light comes from the power CDF (light.cpp:9-17),
 // the pmf stands where 1 / N stood, and the light-aimed ray is checked on arrival -- a miss adds the background, a
 // non-emissive hit ends the path, and only then is the throughput updated (:326-335).
-template <bool ENV, bool POWER>
+template <bool ENV, bool POWER, bool RR>
 __device__ __forceinline__ void shade_one_sample(ShadeCtx &c, const RayRec &ray, const HitRec &hit, const PathRec &path, const PendRec &pend) {
     const DevScene &sc = c.sc;
     const D3 o = mk3(ray.ox, ray.oy, ray.oz), d = mk3(ray.dx, ray.dy, ray.dz);
@@ -694,7 +698,7 @@ __device__ __forceinline__ void shade_one_sample(ShadeCtx &c, const RayRec &ray,
             c.rad = add(c.rad, mulv(c.thr, light_intensity(sc.lights[v.light])));
             return;
         }
-        if (!russian_roulette(c)) return;
+        if (!russian_roulette<RR>(c)) return;
         c.shaded += 1;
         const TakeMaterialDesc &m = sc.materials[v.material];
         const bool spec = is_specular(m.type);
@@ -775,7 +779,7 @@ __device__ __forceinline__ void shade_one_sample(ShadeCtx &c, const RayRec &ray,
 #ifndef TAKE_SHADE_MIN_BLOCKS
 #define TAKE_SHADE_MIN_BLOCKS 1
 #endif
-template <int INTEGRATOR, bool ENV>
+template <int INTEGRATOR, bool ENV, bool RR = false>
 __global__ void __launch_bounds__(128, TAKE_SHADE_MIN_BLOCKS) k_shade(DevScene sc, Wave w, int pass) {
     PassCounters &pc = w.pass[pass];
     const uint32_t n = shade_count(w, pass);
@@ -854,10 +858,10 @@ __global__ void __launch_bounds__(128, TAKE_SHADE_MIN_BLOCKS) k_shade(DevScene s
                 c.pend_flags = 0;
                 c.shaded = 0;
                 c.org = mk3(ray.ox, ray.oy, ray.oz);
-                if (INTEGRATOR == TAKE_INTEGRATOR_MIS) shade_mis<ENV>(c, ray, hit, path, pend);
-                else if (INTEGRATOR == TAKE_INTEGRATOR_RAW) shade_raw<ENV>(c, ray, hit, path, pend);
-                else if (INTEGRATOR == TAKE_INTEGRATOR_ONE_SAMPLE_MIS) shade_one_sample<ENV, false>(c, ray, hit, path, pend);
-                else shade_one_sample<ENV, true>(c, ray, hit, path, pend);
+                if (INTEGRATOR == TAKE_INTEGRATOR_MIS) shade_mis<ENV, RR>(c, ray, hit, path, pend);
+                else if (INTEGRATOR == TAKE_INTEGRATOR_RAW) shade_raw<ENV, RR>(c, ray, hit, path, pend);
+                else if (INTEGRATOR == TAKE_INTEGRATOR_ONE_SAMPLE_MIS) shade_one_sample<ENV, false, RR>(c, ray, hit, path, pend);
+                else shade_one_sample<ENV, true, RR>(c, ray, hit, path, pend);
                 emit_extend = c.emit_extend;
                 emit_shadow = c.emit_shadow;
                 shaded = c.shaded;
@@ -876,7 +880,7 @@ __global__ void __launch_bounds__(128, TAKE_SHADE_MIN_BLOCKS) k_shade(DevScene s
                     r.tmax = INFINITY;
                     // the coin of the vertex this ray will reach is the stream's next draw (see TAKE_KEY_BITS)
                     r.aux0 = ((INTEGRATOR == TAKE_INTEGRATOR_ONE_SAMPLE_MIS || INTEGRATOR == TAKE_INTEGRATOR_ONE_SAMPLE_MIS_POWER) && w.sort_branch &&
-                              emit_extend) ? peek_branch(c.rng, w.rr_start > 0 && c.depth >= w.rr_start) : 0;
+                              emit_extend) ? peek_branch(c.rng, RR && w.rr_start > 0 && c.depth >= w.rr_start) : 0;
                     r.aux1 = 0;
                     w.ray[slot] = r;
                 }
