@@ -172,11 +172,9 @@ struct TakeScene {
     int64_t wave_capacity = 0;
     int wave_sets = 0, wave_passes = 0;
     int blocks_extend = 0, blocks_shadow = 0, blocks_isect = 0, blocks_occl = 0, blocks_extend_primary = 0;
-    int blocks_extend2 = 0, blocks_shadow2 = 0, blocks_isect2 = 0, blocks_occl2 = 0, blocks_extend2w = 0, blocks_shadow2w = 0;
-    int persist_from_pass = 1, persist_shadow = 0;
+    int blocks_extend_refill = 0, blocks_shadow_refill = 0;
+    int refill_extend = 0, refill_shadow = 0;   // bounce / shadow passes on the lane-refill kernels (TAKE_REFILL, see scene creation)
     bool wide = true;   // 4-wide nodes (TAKE_BVH_WIDTH=4, default) or binary nodes (TAKE_BVH_WIDTH=2)
-    int traversal = 1;  // 1: one ray per thread to completion (default, measured faster); 2: warp-persistent while-while
-                        // with dynamic re-fetch (TAKE_TRAVERSAL=2)
     // Device-built scenes: the reference-order tree (tie-break ranks, exact mode) is built by a host thread while the device
     // builds the fast tree and while the caller goes on; finish_reference_tree() joins it before the first query.
     std::shared_ptr<RefJob> ref_job;
@@ -505,18 +503,16 @@ int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, d
             if (w.count_ties) k_extend_primary<false, true><<<s->blocks_extend_primary, 128, 0, st>>>(s->dev, w);
             else if (count) k_extend_primary<true><<<s->blocks_extend_primary, 128, 0, st>>>(s->dev, w);
             else k_extend_primary<false><<<s->blocks_extend_primary, 128, 0, st>>>(s->dev, w);
+        } else if (b >= 1 && s->refill_extend && s->wide) {
+            // bounce rays have very different lengths: lanes are refilled as their rays finish (trace_refill4)
+            if (w.count_ties) k_extend_refill<false, true><<<s->blocks_extend_refill, 128, 0, st>>>(s->dev, w, b);
+            else if (count) k_extend_refill<true><<<s->blocks_extend_refill, 128, 0, st>>>(s->dev, w, b);
+            else k_extend_refill<false><<<s->blocks_extend_refill, 128, 0, st>>>(s->dev, w, b);
         } else if (w.count_ties && s->wide) {
             k_extend<false, true, true><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
         } else
 #if TAKE_EXPERIMENTAL
-        if (s->traversal == 2) {
-            if (count) k_extend2<true, false><<<s->blocks_extend2, 128, 0, st>>>(s->dev, w, b);
-            else k_extend2<false, false><<<s->blocks_extend2, 128, 0, st>>>(s->dev, w, b);
-        } else if (s->traversal == 3 && s->wide && b >= s->persist_from_pass) {
-            // hybrid: bounce passes (rays of very different lengths) on the warp-persistent kernel with lane refill
-            if (count) k_extend2<true, true><<<s->blocks_extend2w, 128, 0, st>>>(s->dev, w, b);
-            else k_extend2<false, true><<<s->blocks_extend2w, 128, 0, st>>>(s->dev, w, b);
-        } else if (!s->wide) {
+        if (!s->wide) {
             if (count) k_extend<true, false><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
             else k_extend<false, false><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
         } else
@@ -528,7 +524,9 @@ int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, d
         tm.end();
         if (w.sort_enabled) {
             tm.begin(ST_SORT);
-            k_scatter<<<scatter_blocks, 256, 0, st>>>(w, b);
+            // (pass 0 is traced one ray per thread or as packets: its hits already finish in slot order)
+            if (w.ordered_sort && b >= 1) k_scatter_ordered<<<s->sm_count * 4, 256, 0, st>>>(w, b);
+            else k_scatter<<<scatter_blocks, 256, 0, st>>>(w, b);
             tm.end();
             launches++;
         }
@@ -546,14 +544,12 @@ int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, d
         launches += 2;
         if (o->integrator == TAKE_INTEGRATOR_MIS && b <= o->max_depth) {
             tm.begin(ST_SHADOW);
+            if (s->refill_shadow && s->wide) {
+                if (count) k_shadow_refill<true><<<s->blocks_shadow_refill, 128, 0, st>>>(s->dev, w, b);
+                else k_shadow_refill<false><<<s->blocks_shadow_refill, 128, 0, st>>>(s->dev, w, b);
+            } else
 #if TAKE_EXPERIMENTAL
-            if (s->traversal == 2) {
-                if (count) k_shadow2<true, false><<<s->blocks_shadow2, 128, 0, st>>>(s->dev, w, b);
-                else k_shadow2<false, false><<<s->blocks_shadow2, 128, 0, st>>>(s->dev, w, b);
-            } else if (s->traversal == 3 && s->wide && s->persist_shadow) {
-                if (count) k_shadow2<true, true><<<s->blocks_shadow2w, 128, 0, st>>>(s->dev, w, b);
-                else k_shadow2<false, true><<<s->blocks_shadow2w, 128, 0, st>>>(s->dev, w, b);
-            } else if (!s->wide) {
+            if (!s->wide) {
                 if (count) k_shadow<true, false><<<s->blocks_shadow, 128, 0, st>>>(s->dev, w, b);
                 else k_shadow<false, false><<<s->blocks_shadow, 128, 0, st>>>(s->dev, w, b);
             } else
@@ -600,7 +596,7 @@ void fill_wave_ptrs(TakeScene *s, Wave &w, const TakeRenderOpts *o, int set = 0)
     w.seed = o->seed;
     w.rr_start = (o->flags & TAKE_RENDER_RUSSIAN_ROULETTE) ? (o->reserved > 0 ? o->reserved : 3) : 0;
 #if TAKE_EXPERIMENTAL
-    w.fused_primary = (s->traversal != 2 && !env_int("TAKE_NO_FUSE", 0)) ? 1 : 0;
+    w.fused_primary = env_int("TAKE_NO_FUSE", 0) ? 0 : 1;
 #else
     w.fused_primary = 1;  // pass 0 of extend / shade computes the camera ray itself (no generate pass)
 #endif
@@ -610,6 +606,12 @@ void fill_wave_ptrs(TakeScene *s, Wave &w, const TakeRenderOpts *o, int set = 0)
     w.miss_fast = (w.fused_primary && w.sort_enabled && s->dev.env_rgb == nullptr && !env_int("TAKE_NO_MISS_FAST", 0)) ? 1 : 0;
     // camera rays as warp packets (traverse.cuh: trace_packet4): needs the 4-wide tree and a tree shallow enough for the shared
     // per-warp stack; TAKE_PACKET=0 keeps one ray per thread in pass 0 (A/B runs, and the test that both give the same image)
+    {   // TAKE_REFILL: bit 0 = bounce passes, bit 1 = shadow passes on the lane-refill kernels (default: both)
+        const int r = env_int("TAKE_REFILL", 3);
+        s->refill_extend = r & 1;
+        s->refill_shadow = (r >> 1) & 1;
+    }
+    w.ordered_sort = env_int("TAKE_ORDERED_SORT", s->refill_extend) ? 1 : 0;
     w.packet = (w.fused_primary && s->wide && 3 * s->wide_depth + 1 <= TAKE_PACKET_STACK && env_int("TAKE_PACKET", 1)) ? 1 : 0;
 }
 
@@ -1198,20 +1200,9 @@ static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild *hb, 
         s->blocks_isect = blocks_for((const void *)k_intersect_fast<false, false>);
         s->blocks_occl = blocks_for((const void *)k_intersect_fast<true, false>);
     }
-    s->blocks_extend2 = blocks_for((const void *)k_extend2<false, false>);
-    s->blocks_shadow2 = blocks_for((const void *)k_shadow2<false, false>);
-    s->blocks_extend2w = blocks_for((const void *)k_extend2<false, true>);
-    s->blocks_shadow2w = blocks_for((const void *)k_shadow2<false, true>);
-    s->blocks_isect2 = blocks_for((const void *)k_intersect_fast2<false>);
-    s->blocks_occl2 = blocks_for((const void *)k_intersect_fast2<true>);
-    {   // 1: one ray per thread to completion; 2: warp-persistent with lane refill (binary tree, all passes);
-        // 3: hybrid -- pass 0 as in 1 (fused camera rays), passes >= TAKE_PERSIST_FROM as in 2 on the 4-wide tree
-        const int t = env_int("TAKE_TRAVERSAL", 1);
-        s->traversal = (t == 2 || t == 3) ? t : 1;
-        s->persist_from_pass = std::max(1, env_int("TAKE_PERSIST_FROM", 1));
-        s->persist_shadow = env_int("TAKE_PERSIST_SHADOW", 0);
-    }
 #endif
+    s->blocks_extend_refill = blocks_for((const void *)k_extend_refill<false>);
+    s->blocks_shadow_refill = blocks_for((const void *)k_shadow_refill<false>);
     mark("occupancy queries");
     CU(s->fetch.ensure(256));
     apply_l2_policy(s, s->stream);
@@ -1477,9 +1468,7 @@ int take_gpu_intersect_device(TakeScene *s, const TakeRay *d_rays, int64_t n, Ta
     } else if (flags == TAKE_ISECT_FAST) {
         CU(cudaMemsetAsync(s->fetch.p, 0, 4, s->stream));
 #if TAKE_EXPERIMENTAL
-        if (s->traversal == 2)
-            k_intersect_fast2<false><<<s->blocks_isect2, 128, 0, s->stream>>>(s->dev, d_rays, n, d_hits, nullptr, s->fetch.as<uint32_t>());
-        else if (!s->wide)
+        if (!s->wide)
             k_intersect_fast<false, false><<<s->blocks_isect, 128, 0, s->stream>>>(s->dev, d_rays, n, d_hits, nullptr, s->fetch.as<uint32_t>());
         else
 #endif
@@ -1522,10 +1511,7 @@ int take_gpu_occluded(TakeScene *s, const TakeRay *rays, int64_t n, uint8_t *occ
         CU(cudaMemcpyAsync(s->scratch_a.p, rays + off, m * sizeof(TakeRay), cudaMemcpyHostToDevice, s->stream));
         CU(cudaMemsetAsync(s->fetch.p, 0, 4, s->stream));
 #if TAKE_EXPERIMENTAL
-        if (s->traversal == 2)
-            k_intersect_fast2<true><<<s->blocks_occl2, 128, 0, s->stream>>>(s->dev, s->scratch_a.as<TakeRay>(), m, nullptr,
-                                                                           s->scratch_b.as<uint8_t>(), s->fetch.as<uint32_t>());
-        else if (!s->wide)
+        if (!s->wide)
             k_intersect_fast<true, false><<<s->blocks_occl, 128, 0, s->stream>>>(s->dev, s->scratch_a.as<TakeRay>(), m, nullptr,
                                                                                  s->scratch_b.as<uint8_t>(), s->fetch.as<uint32_t>());
         else

@@ -544,6 +544,215 @@ __device__ __forceinline__ void trace_packet4(const DevScene &sc, D3 o, D3 d, do
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Traversal with lane refill for the bounce and shadow passes (same results as trace_fast4, different schedule).
+//
+// One ray per thread to completion leaves a warp waiting for its longest ray: in the ncu capture of the first bounce
+// pass of config 2 the node loop runs with 8.6 and the leaf tests with 12.2 of 32 lanes (tools/ncu_lines.py) -- two thirds
+// of the lanes have FINISHED and idle.  Here a warp stays resident and works in rounds:
+//   * node phase: every lane with a ray descends until it holds a leaf or runs out of nodes;
+//   * leaf phase: the lanes holding a leaf run the FP64 test together and pop their next node;
+//   * a lane whose stack ran dry keeps its result in registers (state 2) -- nothing is handed over yet;
+//   * when at least TAKE_REFILL_MIN lanes are without a ray, ALL finished results are handed to `io.retire` in one
+//     convergent call and all free lanes take new rays from the queue with one atomicAdd.
+// The hand-over (hit record, material histogram, two atomic round trips) therefore always runs for many lanes at once.
+// What made it pay (each step measured on five scenes, tools/tune.py; a first version of round 1 -- node phase until every
+// lane holds a leaf, then leaf phase, rays retired one by one, FP64 ray re-read with six 8-byte loads -- was 8 % SLOWER):
+//   * the warp does one step at a time, a node visit or a leaf test, whichever more of its rays are waiting for: in
+//     "node phase until all lanes hold a leaf" the lanes that found their leaf after one or two visits wait for the one
+//     that descends eight levels (11 of 27 live lanes active in the node code, ncu);
+//   * the kernels are L1-bound once the lanes are busy (L1TEX 84 % of peak): every divergent load instruction costs one
+//     L1 wavefront per lane, so the FP64 origin / direction live in registers at 80 registers per thread (6 resident
+//     blocks) instead of being re-read per leaf;
+//   * the hits are put into queue order by the sort (k_scatter_ordered), not into the order in which the rays finished.
+// The closest hit and the tie rule do not depend on the order in which a ray's leaves are visited, and each ray is still
+// traced by one lane with trace_fast4's arithmetic: identical results.
+// ---------------------------------------------------------------------------------------------------------
+#ifndef TAKE_REFILL_MIN
+#define TAKE_REFILL_MIN 20   // measured 4 / 8 / 12 / 16 / 20 / 24 / 28 on five scenes: 20 is best or within 0.5 % of the best on all
+#endif
+#ifndef TAKE_REFILL_OD_REGS
+#define TAKE_REFILL_OD_REGS 0
+#endif
+#ifndef TAKE_REFILL_NODE_BIAS
+#define TAKE_REFILL_NODE_BIAS 4   // a node visit is taken when 4 * (rays at a leaf) <= BIAS * (rays at an inner node)
+#endif
+
+struct LaneRay {        // FP32 image of the ray for the box tests + the FP64 window for the leaf test
+    float idx, idy, idz, olx, ohx, oly, ohy, olz, ohz, tbest_f;
+    double best_t;
+#if TAKE_REFILL_OD_REGS
+    D3 o, d;
+#else
+    // The FP64 origin and direction stay in memory and are re-read per leaf test (registers): two 32-byte blocks, fetched
+    // with one 256-bit load each.  o = the first three doubles of *o4; d = the last double of *o4 and the first two of *d4
+    // (an extend ray: RayRec is ox oy oz dx | dy dz ...) or the first three of *d4 (a shadow ray: ShadowRec is dx dy dz tmax).
+    const double2 *o4, *d4;
+#endif
+};
+
+template <bool D_SPLIT>
+__device__ __forceinline__ void lane_ray_od(const double2 *o4, const double2 *d4, D3 &o, D3 &d) {
+    const D4 a = ldg_d4(o4), b = ldg_d4(d4);
+    o = mk3(a.a.x, a.a.y, a.b.x);
+    d = D_SPLIT ? mk3(a.b.y, b.a.x, b.a.y) : mk3(b.a.x, b.a.y, b.b.x);
+}
+
+template <bool D_SPLIT>
+__device__ __forceinline__ void lane_ray_setup(LaneRay &r, const DevScene &sc, const double2 *o4, const double2 *d4, double tmax) {
+    D3 o, d;
+    lane_ray_od<D_SPLIT>(o4, d4, o, d);
+    const float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
+    r.idx = safe_rcp((float)d.x); r.idy = safe_rcp((float)d.y); r.idz = safe_rcp((float)d.z);
+    const float delta = 1.9073486e-6f * fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fmaxf(fabsf(oz), sc.abs_max));  // 2^-19
+    r.olx = -(ox + delta) * r.idx; r.ohx = -(ox - delta) * r.idx;
+    r.oly = -(oy + delta) * r.idy; r.ohy = -(oy - delta) * r.idy;
+    r.olz = -(oz + delta) * r.idz; r.ohz = -(oz - delta) * r.idz;
+    r.tbest_f = __double2float_ru(tmax);
+    r.best_t = tmax;
+#if TAKE_REFILL_OD_REGS
+    r.o = o; r.d = d;
+#else
+    r.o4 = o4; r.d4 = d4;
+#endif
+}
+
+// One node visit (the body of trace_fast4's inner loop; every ray of the wavefront passes starts at tmin = TAKE_EPS):
+// tests the four children, pushes the farther hits and returns the nearest -- or the next live stack entry, or TAKE_NODE_DONE.
+template <bool ANY_HIT, bool COUNT>
+__device__ __forceinline__ int32_t visit_wide(const DevScene &sc, int32_t node, const LaneRay &r, float tmin_f, TravStack &st, TravCounters *cnt) {
+    const float4 *N = sc.wide_nodes + 8 * (int64_t)node;
+    const F8 nx = ldg_f8(N), ny = ldg_f8(N + 2), nz = ldg_f8(N + 4);
+    const float4 lox = nx.a, hix = nx.b, loy = ny.a, hiy = ny.b, loz = nz.a, hiz = nz.b;
+    const int4 ch = __ldg((const int4 *)(N + 6));
+    if (COUNT) cnt->box += 4;
+    uint32_t key[4];
+#define TAKE_WIDE_CHILD(K, LX, HX, LY, HY, LZ, HZ, C)                                            \
+    {                                                                                              \
+        float a = fmaf(LX, r.idx, r.olx), b = fmaf(HX, r.idx, r.ohx);                              \
+        float tn = fminf(a, b), tf = fmaxf(a, b);                                                  \
+        a = fmaf(LY, r.idy, r.oly); b = fmaf(HY, r.idy, r.ohy);                                    \
+        tn = fmaxf(tn, fminf(a, b)); tf = fminf(tf, fmaxf(a, b));                                  \
+        a = fmaf(LZ, r.idz, r.olz); b = fmaf(HZ, r.idz, r.ohz);                                    \
+        tn = fmaxf(tn, fminf(a, b)); tf = fminf(tf, fmaxf(a, b));                                  \
+        tn = fmaxf(tn, tmin_f); tf = fminf(tf, r.tbest_f);                                         \
+        const bool h = (tn <= tf * TAKE_SLACK) && (C != TAKE_WIDE_EMPTY);                          \
+        key[K] = h ? ((__float_as_uint(tn) & 0xfffffffcu) | (uint32_t)K) : 0xffffffffu;            \
+    }
+    TAKE_WIDE_CHILD(0, lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x, ch.x)
+    TAKE_WIDE_CHILD(1, lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, ch.y)
+    TAKE_WIDE_CHILD(2, lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, ch.z)
+    TAKE_WIDE_CHILD(3, lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, ch.w)
+#undef TAKE_WIDE_CHILD
+    if (!(ANY_HIT && TAKE_ANYHIT_UNSORTED)) {
+        cswap(key[0], key[1]); cswap(key[2], key[3]); cswap(key[0], key[2]); cswap(key[1], key[3]); cswap(key[1], key[2]);
+    }
+#define TAKE_WIDE_PICK(KEY) (((KEY) & 2u) ? (((KEY) & 1u) ? ch.w : ch.z) : (((KEY) & 1u) ? ch.y : ch.x))
+    if (key[3] != 0xffffffffu) st.push_bits(TAKE_WIDE_PICK(key[3]), key[3] & 0xfffffffcu);
+    if (key[2] != 0xffffffffu) st.push_bits(TAKE_WIDE_PICK(key[2]), key[2] & 0xfffffffcu);
+    if (key[1] != 0xffffffffu) st.push_bits(TAKE_WIDE_PICK(key[1]), key[1] & 0xfffffffcu);
+    if (key[0] != 0xffffffffu) return TAKE_WIDE_PICK(key[0]);
+#undef TAKE_WIDE_PICK
+    while (st.sp > 0) {
+        int32_t nn; float tn;
+        st.pop(nn, tn);
+        if ((ANY_HIT && TAKE_ANYHIT_UNSORTED) || tn <= r.tbest_f * TAKE_SLACK) return nn;
+    }
+    return TAKE_NODE_DONE;
+}
+
+// `IO` supplies  void load(uint32_t i, const DevScene&, LaneRay&)  (queue entry i -> this lane's ray) and
+// void retire(unsigned mask, bool mine, const HitOut&)  (called by the whole warp; `mask` = the lanes handing over a result).
+template <bool ANY_HIT, bool COUNT, bool TIES, typename IO>
+__device__ __forceinline__ void trace_refill4(const DevScene &sc, IO &io, uint32_t n, uint32_t *fetch, TravStack &st, TravCounters *cnt) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const float tmin_f = __double2float_rd(TAKE_EPS);
+    int state = 0;                 // 0: no ray, 1: tracing, 2: finished, result still in `out`
+    bool exhausted = n == 0;       // warp-uniform: the queue has nothing left for this warp
+    int32_t node = TAKE_NODE_DONE;
+    LaneRay r;
+    HitOut out;
+    out.prim = -1; out.rank = -1; out.t = 0; out.u = 0; out.v = 0;
+    st.sp = 0;
+    for (;;) {
+        const unsigned busy = __ballot_sync(0xffffffffu, state == 1);
+        const int n_free = 32 - __popc(busy);
+        if (n_free >= (exhausted ? 32 : TAKE_REFILL_MIN)) {
+            const unsigned dmask = __ballot_sync(0xffffffffu, state == 2);
+            if (dmask) io.retire(dmask, state == 2, out);
+            if (state == 2) state = 0;
+            if (exhausted) return;   // (only reached with all 32 lanes free)
+            const int leader = __ffs(~busy) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(fetch, (uint32_t)n_free);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base + (uint32_t)n_free >= n) exhausted = true;
+            if (state == 0) {
+                const uint32_t i = base + (uint32_t)__popc(~busy & lt_mask);
+                if (i < n) {
+                    io.load(i, sc, r);
+                    out.prim = -1; out.rank = -1; out.t = 0; out.u = 0; out.v = 0;
+                    st.sp = 0;
+                    node = 0;
+                    state = sc.num_prims > 0 ? 1 : 2;
+                }
+            }
+            continue;
+        }
+        // ---- one step: the warp does what most of its rays wait for -- a node visit or a leaf test ----
+        const bool want_node = state == 1 && node >= 0;
+        const bool want_leaf = state == 1 && node < 0 && node != TAKE_NODE_DONE;
+        const int n_node = __popc(__ballot_sync(0xffffffffu, want_node)), n_leaf = __popc(__ballot_sync(0xffffffffu, want_leaf));
+        if (n_node * TAKE_REFILL_NODE_BIAS >= n_leaf * 4) {
+            if (want_node) node = visit_wide<ANY_HIT, COUNT>(sc, node, r, tmin_f, st, cnt);
+        } else if (want_leaf) {
+            const int32_t code = ~node;
+            const int64_t first = code >> 3;
+            const int count = (code & 7) + 1;
+#if TAKE_REFILL_OD_REGS
+            const D3 o = r.o, d = r.d;
+#else
+            D3 o, d;
+            lane_ray_od<IO::D_SPLIT>(r.o4, r.d4, o, d);
+#endif
+            bool stop = false;
+            for (int k = 0; k < count && !stop; ++k) {
+                const double2 *T = sc.tris + 6 * (first + k);
+                const D4 t01 = ldg_d4(T), t23 = ldg_d4(T + 2), t45 = ldg_d4(T + 4);
+                const double2 a0 = t01.a, a1 = t01.b, a2 = t23.a, a3 = t23.b, a4 = t45.a, a5 = t45.b;
+                if (COUNT) cnt->tri += 1;
+                double t, bu = 0, bv = 0;
+                bool ok;
+                if (a5.y == 0.0)
+                    ok = hit_triangle(mk3(a0.x, a0.y, a1.x), mk3(a2.x, a2.y, a3.x), mk3(a4.x, a4.y, a5.x), o, d, TAKE_EPS, r.best_t, t, bu, bv);
+                else
+                    ok = hit_sphere(mk3(a0.x, a0.y, a1.x), a3.y, o, d, TAKE_EPS, r.best_t, t);
+                if (ok) {
+                    const long long bits = __double_as_longlong(a1.y);
+                    const int32_t prim = (int32_t)(bits & 0xffffffffLL), rank = (int32_t)(bits >> 32);
+                    if (TIES && !ANY_HIT && out.prim >= 0 && !(t < r.best_t)) atomicAdd(sc.tie_count, 1ULL);   // see trace_fast4
+                    if (t < r.best_t || out.prim < 0 || rank > out.rank) {
+                        out.prim = prim; out.rank = rank; out.t = t; out.u = bu; out.v = bv;
+                        r.best_t = t;
+                        r.tbest_f = __double2float_ru(t);
+                        if (ANY_HIT) stop = true;
+                    }
+                }
+            }
+            node = TAKE_NODE_DONE;
+            if (!(ANY_HIT && stop)) {
+                while (st.sp > 0) {
+                    int32_t nn; float tn;
+                    st.pop(nn, tn);
+                    if ((ANY_HIT && TAKE_ANYHIT_UNSORTED) || tn <= r.tbest_f * TAKE_SLACK) { node = nn; break; }
+                }
+            }
+        }
+        if (state == 1 && node == TAKE_NODE_DONE) state = 2;
+    }
+}
+
 #if TAKE_EXPERIMENTAL
 // ---------------------------------------------------------------------------------------------------------
 // Speculative 4-wide traversal (warp-cooperative schedule, same results as trace_fast4).
@@ -689,230 +898,5 @@ __device__ __forceinline__ void trace_any(const DevScene &sc, D3 o, D3 d, double
 #endif
 }
 
-#if TAKE_EXPERIMENTAL
-// ---------------------------------------------------------------------------------------------------------
-// Warp-persistent traversal ("while-while" with dynamic re-fetch).
-//
-// trace_fast above walks one ray to completion per thread; lanes whose rays end early idle until the slowest ray
-// of the warp is done, and the long FP64 leaf test of one lane stalls the 31 others in the middle of their node
-// loop (measured: 10 of 32 lanes active per issued instruction on primary rays).  This variant keeps a warp
-// resident and splits every round into convergent phases:
-//   1. re-fetch: lanes without a ray are counted with __ballot_sync / __popc; when enough are idle one lane reserves
-//      that many queue entries with a single atomicAdd, __shfl_sync broadcasts the base, and the idle lanes load new
-//      rays (ray compaction by replacement);
-//   2. node phase: every lane descends inner nodes until it holds a leaf (or runs out of nodes);
-//   3. leaf phase: all lanes holding a leaf run the FP64 leaf test together, then pop;
-//   4. retire: lanes whose stack ran dry hand their result to `io` at a convergent point.
-// Results are identical to trace_fast (same boxes, same leaf test, same tie rule) -- only the schedule differs.
-// `IO` supplies  bool load(i, lane state...)  and  void retire(mask, done, ...)  (see the kernels in wavefront.cuh).
-// ---------------------------------------------------------------------------------------------------------
-#ifndef TAKE_REFILL_MIN
-#define TAKE_REFILL_MIN 8
-#endif
-
-struct LaneRay {        // FP32 image of the ray for the box tests + the FP64 window for the leaf test
-    float idx, idy, idz, olx, ohx, oly, ohy, olz, ohz, tmin_f, tbest_f;
-    double tmin, best_t;
-    const double *o;    // FP64 origin (3 doubles) and direction (3 doubles) stay in memory and are re-read per leaf
-    const double *d;
-};
-
-__device__ __forceinline__ void lane_ray_setup(LaneRay &r, const DevScene &sc, const double *o, const double *d, double tmin,
-                                               double tmax) {
-    const float ox = (float)o[0], oy = (float)o[1], oz = (float)o[2];
-    r.idx = safe_rcp((float)d[0]); r.idy = safe_rcp((float)d[1]); r.idz = safe_rcp((float)d[2]);
-    const float delta = 1.9073486e-6f * fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fmaxf(fabsf(oz), sc.abs_max));
-    r.olx = -(ox + delta) * r.idx; r.ohx = -(ox - delta) * r.idx;
-    r.oly = -(oy + delta) * r.idy; r.ohy = -(oy - delta) * r.idy;
-    r.olz = -(oz + delta) * r.idz; r.ohz = -(oz - delta) * r.idz;
-    r.tmin_f = __double2float_rd(tmin);
-    r.tbest_f = __double2float_ru(tmax);
-    r.tmin = tmin;
-    r.best_t = tmax;
-    r.o = o;
-    r.d = d;
-}
-
-// One 4-wide node visit for the warp-persistent loop: tests the four children (same arithmetic as trace_fast4), pushes
-// the farther hits and returns the nearest one -- or the next live stack entry, or TAKE_NODE_DONE.
-template <bool COUNT>
-__device__ __forceinline__ int32_t visit_wide(const DevScene &sc, int32_t node, const LaneRay &r, TravStack &st, TravCounters *cnt) {
-    const float4 *N = sc.wide_nodes + 8 * (int64_t)node;
-    const F8 nx = ldg_f8(N), ny = ldg_f8(N + 2), nz = ldg_f8(N + 4);
-    const float4 lox = nx.a, hix = nx.b, loy = ny.a, hiy = ny.b, loz = nz.a, hiz = nz.b;
-    const int4 ch = __ldg((const int4 *)(N + 6));
-    if (COUNT) cnt->box += 4;
-    uint32_t key[4];
-#define TAKE_WIDE_CHILD(K, LX, HX, LY, HY, LZ, HZ, C)                                            \
-    {                                                                                              \
-        float a = fmaf(LX, r.idx, r.olx), b = fmaf(HX, r.idx, r.ohx);                              \
-        float tn = fminf(a, b), tf = fmaxf(a, b);                                                  \
-        a = fmaf(LY, r.idy, r.oly); b = fmaf(HY, r.idy, r.ohy);                                    \
-        tn = fmaxf(tn, fminf(a, b)); tf = fminf(tf, fmaxf(a, b));                                  \
-        a = fmaf(LZ, r.idz, r.olz); b = fmaf(HZ, r.idz, r.ohz);                                    \
-        tn = fmaxf(tn, fminf(a, b)); tf = fminf(tf, fmaxf(a, b));                                  \
-        tn = fmaxf(tn, r.tmin_f); tf = fminf(tf, r.tbest_f);                                       \
-        const bool h = (tn <= tf * TAKE_SLACK) && (C != TAKE_WIDE_EMPTY);                          \
-        key[K] = h ? ((__float_as_uint(tn) & 0xfffffffcu) | (uint32_t)K) : 0xffffffffu;            \
-    }
-    TAKE_WIDE_CHILD(0, lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x, ch.x)
-    TAKE_WIDE_CHILD(1, lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, ch.y)
-    TAKE_WIDE_CHILD(2, lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, ch.z)
-    TAKE_WIDE_CHILD(3, lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, ch.w)
-#undef TAKE_WIDE_CHILD
-    cswap(key[0], key[1]); cswap(key[2], key[3]); cswap(key[0], key[2]); cswap(key[1], key[3]); cswap(key[1], key[2]);
-#define TAKE_WIDE_PICK(KEY) (((KEY) & 2u) ? (((KEY) & 1u) ? ch.w : ch.z) : (((KEY) & 1u) ? ch.y : ch.x))
-    if (key[3] != 0xffffffffu) st.push_bits(TAKE_WIDE_PICK(key[3]), key[3] & 0xfffffffcu);
-    if (key[2] != 0xffffffffu) st.push_bits(TAKE_WIDE_PICK(key[2]), key[2] & 0xfffffffcu);
-    if (key[1] != 0xffffffffu) st.push_bits(TAKE_WIDE_PICK(key[1]), key[1] & 0xfffffffcu);
-    if (key[0] != 0xffffffffu) return TAKE_WIDE_PICK(key[0]);
-#undef TAKE_WIDE_PICK
-    while (st.sp > 0) {
-        int32_t nn; float tn;
-        st.pop(nn, tn);
-        if (tn <= r.tbest_f * TAKE_SLACK) return nn;
-    }
-    return TAKE_NODE_DONE;
-}
-
-template <bool ANY_HIT, bool COUNT, bool WIDE, typename IO>
-__device__ __forceinline__ void trace_warp_persistent(const DevScene &sc, IO &io, uint32_t n, uint32_t *fetch, TravStack &st,
-                                                      TravCounters *cnt) {
-    const int lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    bool active = false, exhausted = (n == 0) || sc.num_prims <= 0;
-    int32_t node = TAKE_NODE_DONE;
-    uint32_t item = 0;
-    LaneRay r;
-    HitOut out;
-    out.prim = -1; out.rank = -1; out.t = 0; out.u = 0; out.v = 0;
-    st.sp = 0;
-    if (sc.num_prims <= 0) {  // nothing to hit: every ray misses (still has to be retired)
-        for (uint32_t base = 0;; ) {
-            if (lane == 0) base = atomicAdd(fetch, 32u);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base >= n) return;
-            const uint32_t i = base + lane;
-            const bool v = i < n;
-            if (v) io.load(i, sc, r);
-            io.retire(__ballot_sync(0xffffffffu, v), v, i, out);
-        }
-    }
-    for (;;) {
-        // ---- 1. re-fetch ----
-        const unsigned idle = __ballot_sync(0xffffffffu, !active);
-        if (idle != 0u && !exhausted && (idle == 0xffffffffu || __popc(idle) >= TAKE_REFILL_MIN)) {
-            const int want = __popc(idle);
-            uint32_t base = 0;
-            if (lane == __ffs(idle) - 1) base = atomicAdd(fetch, (uint32_t)want);
-            base = __shfl_sync(0xffffffffu, base, __ffs(idle) - 1);
-            if (base + (uint32_t)want >= n) exhausted = true;
-            if (!active) {
-                const uint32_t i = base + (uint32_t)__popc(idle & lt_mask);
-                if (i < n) {
-                    item = i;
-                    io.load(i, sc, r);
-                    active = true;
-                    node = 0;
-                    st.sp = 0;
-                    out.prim = -1; out.rank = -1; out.t = 0; out.u = 0; out.v = 0;
-                }
-            }
-        }
-        if (__ballot_sync(0xffffffffu, active) == 0u) {
-            if (exhausted) return;
-            continue;
-        }
-        // ---- 2. node phase ----
-        if (WIDE) {
-            while (active && node >= 0) node = visit_wide<COUNT>(sc, node, r, st, cnt);
-        } else {
-        while (active && node >= 0) {
-                const float4 q0 = __ldg(sc.nodes + 4 * (int64_t)node);
-                const float4 q1 = __ldg(sc.nodes + 4 * (int64_t)node + 1);
-                const float4 q2 = __ldg(sc.nodes + 4 * (int64_t)node + 2);
-                const float4 q3 = __ldg(sc.nodes + 4 * (int64_t)node + 3);
-                if (COUNT) cnt->box += 2;
-                float a, b;
-                a = fmaf(q0.x, r.idx, r.olx); b = fmaf(q0.y, r.idx, r.ohx);
-                float tn0 = fminf(a, b), tf0 = fmaxf(a, b);
-                a = fmaf(q0.z, r.idy, r.oly); b = fmaf(q0.w, r.idy, r.ohy);
-                tn0 = fmaxf(tn0, fminf(a, b)); tf0 = fminf(tf0, fmaxf(a, b));
-                a = fmaf(q2.x, r.idz, r.olz); b = fmaf(q2.y, r.idz, r.ohz);
-                tn0 = fmaxf(tn0, fminf(a, b)); tf0 = fminf(tf0, fmaxf(a, b));
-                tn0 = fmaxf(tn0, r.tmin_f); tf0 = fminf(tf0, r.tbest_f);
-                a = fmaf(q1.x, r.idx, r.olx); b = fmaf(q1.y, r.idx, r.ohx);
-                float tn1 = fminf(a, b), tf1 = fmaxf(a, b);
-                a = fmaf(q1.z, r.idy, r.oly); b = fmaf(q1.w, r.idy, r.ohy);
-                tn1 = fmaxf(tn1, fminf(a, b)); tf1 = fminf(tf1, fmaxf(a, b));
-                a = fmaf(q2.z, r.idz, r.olz); b = fmaf(q2.w, r.idz, r.ohz);
-                tn1 = fmaxf(tn1, fminf(a, b)); tf1 = fminf(tf1, fmaxf(a, b));
-                tn1 = fmaxf(tn1, r.tmin_f); tf1 = fminf(tf1, r.tbest_f);
-                const bool h0 = tn0 <= tf0 * TAKE_SLACK, h1 = tn1 <= tf1 * TAKE_SLACK;
-                const int32_t c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
-                if (h0 && h1) {
-                    if (tn1 < tn0) { st.push(c0, tn0); node = c1; }
-                    else { st.push(c1, tn1); node = c0; }
-                } else if (h0) {
-                    node = c0;
-                } else if (h1) {
-                    node = c1;
-                } else {
-                    node = TAKE_NODE_DONE;
-                    while (st.sp > 0) {
-                        int32_t nn; float tn;
-                        st.pop(nn, tn);
-                        if (tn <= r.tbest_f * TAKE_SLACK) { node = nn; break; }
-                    }
-                }
-            }
-        }
-        // ---- 3. leaf phase ----
-        if (active && node != TAKE_NODE_DONE) {  // node < 0: a leaf
-            const int32_t code = ~node;
-            const int64_t first = code >> 3;
-            const int count = (code & 7) + 1;
-            const D3 o = mk3(r.o[0], r.o[1], r.o[2]), d = mk3(r.d[0], r.d[1], r.d[2]);
-            bool stop = false;
-            for (int k = 0; k < count && !stop; ++k) {
-                const double2 *T = sc.tris + 6 * (first + k);
-                const D4 t01 = ldg_d4(T), t23 = ldg_d4(T + 2), t45 = ldg_d4(T + 4);
-                const double2 a0 = t01.a, a1 = t01.b, a2 = t23.a, a3 = t23.b, a4 = t45.a, a5 = t45.b;
-                if (COUNT) cnt->tri += 1;
-                double t, bu = 0, bv = 0;
-                bool ok;
-                if (a5.y == 0.0)
-                    ok = hit_triangle(mk3(a0.x, a0.y, a1.x), mk3(a2.x, a2.y, a3.x), mk3(a4.x, a4.y, a5.x), o, d, r.tmin, r.best_t, t,
-                                      bu, bv);
-                else
-                    ok = hit_sphere(mk3(a0.x, a0.y, a1.x), a3.y, o, d, r.tmin, r.best_t, t);
-                if (ok) {
-                    const long long bits = __double_as_longlong(a1.y);
-                    const int32_t prim = (int32_t)(bits & 0xffffffffLL), rank = (int32_t)(bits >> 32);
-                    if (t < r.best_t || out.prim < 0 || rank > out.rank) {
-                        out.prim = prim; out.rank = rank; out.t = t; out.u = bu; out.v = bv;
-                        r.best_t = t;
-                        r.tbest_f = __double2float_ru(t);
-                        if (ANY_HIT) stop = true;
-                    }
-                }
-            }
-            node = TAKE_NODE_DONE;
-            if (!(ANY_HIT && stop)) {
-                while (st.sp > 0) {
-                    int32_t nn; float tn;
-                    st.pop(nn, tn);
-                    if (tn <= r.tbest_f * TAKE_SLACK) { node = nn; break; }
-                }
-            }
-        }
-        // ---- 4. retire ----
-        const bool done = active && node == TAKE_NODE_DONE;
-        const unsigned dmask = __ballot_sync(0xffffffffu, done);
-        if (dmask) io.retire(dmask, done, item, out);
-        if (done) active = false;
-    }
-}
-#endif  // TAKE_EXPERIMENTAL (warp-persistent traversal)
 
 }  // namespace take

@@ -221,6 +221,18 @@ def test_render_properties(pair, monkeypatch):
         assert np.array_equal(f, g) and np.array_equal(f2, g2)
         for k in ("samples", "extend_rays", "shadow_rays", "shaded"):
             assert st_f[k] == st_g[k], (integ, k)
+    for integ in ("mis", "one_sample_mis", "raw"):                               # bounce / shadow passes: lane refill vs one ray per thread
+        f, f2, st_f = gs.render_sums(integ, 5, 0, 4, seed=5, flags=api.RENDER_COUNT_TESTS)
+        for env in ({"TAKE_REFILL": "0"}, {"TAKE_REFILL": "1"}, {"TAKE_REFILL": "2"}, {"TAKE_ORDERED_SORT": "0"},
+                    {"TAKE_REFILL": "0", "TAKE_ORDERED_SORT": "1"}):
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            g, g2, st_g = gs.render_sums(integ, 5, 0, 4, seed=5, flags=api.RENDER_COUNT_TESTS)
+            for k in env:
+                monkeypatch.delenv(k)
+            assert np.array_equal(f, g) and np.array_equal(f2, g2), (integ, env)
+            for k in ("samples", "extend_rays", "shadow_rays", "shaded", "box_tests", "tri_tests", "shadow_box_tests", "shadow_tri_tests"):   # every ray walks the same nodes
+                assert st_f[k] == st_g[k], (integ, env, k)
     monkeypatch.setenv("TAKE_WAVE_SLOTS", "1500")                                # force pixel chunking + many waves
     d, d2, _ = gs.render_sums("mis", 5, 0, 4, seed=5)
     assert np.array_equal(a, d) and np.array_equal(a2, d2)
