@@ -449,7 +449,7 @@ __global__ void k_scatter(Wave w, int pass) {
 // 10 M-triangle scene, +41 % on the Cornell box).  Blocks take chunks of TAKE_SORT_CHUNK queue entries from a cursor, rank
 // them per key in shared memory and reserve each key's share of its bin with one global atomic per key and chunk, so a bin
 // is filled chunk by chunk in (nearly) queue order.  The order changes no result -- only where the records lie.
-#define TAKE_SORT_CHUNK 2048
+#define TAKE_SORT_CHUNK 1024
 __global__ void __launch_bounds__(256) k_scatter_ordered(Wave w, int pass) {
     __shared__ uint32_t offs[TAKE_NBINS], cnt[TAKE_NBINS], base_of[TAKE_NBINS];
     __shared__ uint32_t chunk_base;
@@ -470,14 +470,18 @@ __global__ void __launch_bounds__(256) k_scatter_ordered(Wave w, int pass) {
         __syncthreads();
         const uint32_t c0 = chunk_base;
         if (c0 >= n) break;
-        int slot[PER];
+        HitRec h[PER];
         uint32_t key[PER], lrank[PER];
+        int slot[PER];
 #pragma unroll
         for (int j = 0; j < PER; ++j) {   // entry c0 + j * 256 + thread: a warp's 32 entries are consecutive
             const uint32_t i = c0 + (uint32_t)j * 256u + threadIdx.x;
-            const bool valid = i < n;
-            slot[j] = valid ? (primary ? (int)i : queue[i]) : -1;
-            key[j] = valid ? (w.hit[slot[j]].keyrank >> TAKE_RANK_BITS) : 0xffffffffu;
+            slot[j] = i < n ? (primary ? (int)i : queue[i]) : -1;
+        }
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            if (slot[j] >= 0) h[j] = w.hit[slot[j]];
+            key[j] = slot[j] >= 0 ? (h[j].keyrank >> TAKE_RANK_BITS) : 0xffffffffu;
         }
 #pragma unroll
         for (int j = 0; j < PER; ++j) {   // rank inside the chunk: one shared atomic per distinct key and warp
@@ -497,10 +501,9 @@ __global__ void __launch_bounds__(256) k_scatter_ordered(Wave w, int pass) {
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
             if (slot[j] < 0) continue;
-            HitRec h = w.hit[slot[j]];
             const uint32_t dst = offs[key[j]] + base_of[key[j]] + lrank[j];
-            h.keyrank = (uint32_t)slot[j];
-            w.hit_sorted[dst] = h;
+            h[j].keyrank = (uint32_t)slot[j];
+            w.hit_sorted[dst] = h[j];
         }
     }
 }
@@ -1041,13 +1044,13 @@ struct ExtendRefillIO {
 #ifndef TAKE_REFILL_MIN_BLOCKS
 #define TAKE_REFILL_MIN_BLOCKS TAKE_BOUNCE_MIN_BLOCKS
 #endif
-template <bool COUNT, bool TIES = false>
+template <bool COUNT, bool TIES = false, bool QNODES = false>
 __global__ void __launch_bounds__(128, TAKE_REFILL_MIN_BLOCKS) k_extend_refill(DevScene sc, Wave w, int pass) {
     TAKE_DECLARE_STACK(st);
     PassCounters &pc = w.pass[pass];
     ExtendRefillIO io = {w, pc, w.q_extend[pass & 1], sc.prim_mtype, -1, 0};
     TravCounters cnt = {0, 0};
-    trace_refill4<false, COUNT, TIES>(sc, io, pc.n_extend, &pc.fetch_extend, st, &cnt);
+    trace_refill4<false, COUNT, TIES, QNODES>(sc, io, pc.n_extend, &pc.fetch_extend, st, &cnt);
     if (COUNT) {
         atomicAdd(&w.totals->box_tests, cnt.box);
         atomicAdd(&w.totals->tri_tests, cnt.tri);
@@ -1072,13 +1075,13 @@ struct ShadowRefillIO {
     }
 };
 
-template <bool COUNT>
+template <bool COUNT, bool QNODES = false>
 __global__ void __launch_bounds__(128, TAKE_REFILL_MIN_BLOCKS) k_shadow_refill(DevScene sc, Wave w, int pass) {
     TAKE_DECLARE_STACK(st);
     PassCounters &pc = w.pass[pass];
     ShadowRefillIO io = {w, -1};
     TravCounters cnt = {0, 0};
-    trace_refill4<true, COUNT, false>(sc, io, pc.n_shadow, &pc.fetch_shadow, st, &cnt);
+    trace_refill4<true, COUNT, false, QNODES>(sc, io, pc.n_shadow, &pc.fetch_shadow, st, &cnt);
     if (COUNT) {
         atomicAdd(&w.totals->shadow_box_tests, cnt.box);
         atomicAdd(&w.totals->shadow_tri_tests, cnt.tri);
