@@ -734,81 +734,5 @@ __global__ void k_patch_ranks(int64_t n, const int32_t *dfs_rank, double *tris) 
     T[3] = __longlong_as_double(((long long)dfs_rank[prim] << 32) | (long long)prim);
 }
 
-// ---- 5. quantised copy of the 4-wide nodes (traverse.cuh: visit_wide_q) ---------------------------------------------
-// 64 bytes per node: a grid  plane(q) = org + q * scale  per axis (scale a power of two), the six planes of each child as
-// grid indices, the four child links as they are.  Outward rounding, all in exact arithmetic (double holds the differences
-// of two floats of one node exactly enough; the divisor is a power of two):
-//   scale  >= extent / 250  and  >= 4 ulp of the node's largest coordinate (so that org = float(lo - scale), rounded down,
-//             lies between 1 and 1.5 steps below the node's lower plane);
-//   q_lo    = floor((lo - org) / scale) - 1  >= 0,     q_hi = ceil((hi - org) / scale) + 1  <= 253:
-// one step further out than the grid needs -- the traversal evaluates the planes with an error of up to half a step.
-// An unused child gets q_lo = 255 > q_hi = 0 (and keeps its TAKE_WIDE_EMPTY link).
-struct WideQ {
-    float org[3], scale[3];
-    uint32_t q[6];        // lox, hix, loy, hiy, loz, hiz: byte k = child k
-    int32_t child[4];
-};
-static_assert(sizeof(WideQ) == 64, "WideQ must be 64 bytes");
-
-__global__ void k_quantize_wide(int64_t n_nodes, const WideNode *wide, WideQ *out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_nodes) return;
-    const WideNode w = wide[i];
-    WideQ o;
-    for (int a = 0; a < 3; ++a) {
-        const float *lo = a == 0 ? w.lox : a == 1 ? w.loy : w.loz, *hi = a == 0 ? w.hix : a == 1 ? w.hiy : w.hiz;
-        float nlo = INFINITY, nhi = -INFINITY;
-        for (int k = 0; k < 4; ++k)
-            if (w.child[k] != TAKE_WIDE_EMPTY && lo[k] <= hi[k]) { nlo = fminf(nlo, lo[k]); nhi = fmaxf(nhi, hi[k]); }
-        if (!(nlo <= nhi)) nlo = nhi = 0.0f;
-        const double ext = (double)nhi - (double)nlo;
-        const double amax = fmax(fabs((double)nlo), fabs((double)nhi));
-        int e = ext > 0 ? ilogb(ext / 250.0) + 1 : -100;
-        if (amax > 0) e = max(e, ilogb(amax) - 21);
-        e = max(e, -100);
-        const double sc = ldexp(1.0, e);
-        const float org = __double2float_rd((double)nlo - sc);
-        o.org[a] = org;
-        o.scale[a] = (float)sc;
-        uint32_t ql = 0, qh = 0;
-        for (int k = 0; k < 4; ++k) {
-            int l = 255, h = 0;
-            if (w.child[k] != TAKE_WIDE_EMPTY && lo[k] <= hi[k]) {
-                l = (int)floor(((double)lo[k] - (double)org) / sc) - 1;
-                h = (int)ceil(((double)hi[k] - (double)org) / sc) + 1;
-                l = max(l, 0);      // (never below 0 / above 255 by construction; the clamps only guard the byte packing,
-                h = min(h, 255);    //  and k_check_wide_q verifies the planes against the FP32 boxes)
-            }
-            ql |= (uint32_t)l << (8 * k);
-            qh |= (uint32_t)h << (8 * k);
-        }
-        o.q[2 * a] = ql;
-        o.q[2 * a + 1] = qh;
-    }
-    for (int k = 0; k < 4; ++k) o.child[k] = w.child[k];
-    out[i] = o;
-}
-
-// Verification pass (scene creation): every quantised box, shrunk by the half step the traversal may lose, contains the FP32
-// box it stands for.  Counts violations (0 expected; a scene that has any keeps the 128-byte nodes).
-__global__ void k_check_wide_q(int64_t n_nodes, const WideNode *wide, const WideQ *q, unsigned long long *bad) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_nodes) return;
-    const WideNode w = wide[i];
-    const WideQ o = q[i];
-    int n_bad = 0;
-    for (int a = 0; a < 3; ++a) {
-        const float *lo = a == 0 ? w.lox : a == 1 ? w.loy : w.loz, *hi = a == 0 ? w.hix : a == 1 ? w.hiy : w.hiz;
-        const double sc = (double)o.scale[a], org = (double)o.org[a];
-        for (int k = 0; k < 4; ++k) {
-            if (w.child[k] == TAKE_WIDE_EMPTY || !(lo[k] <= hi[k])) continue;
-            const double pl = org + (double)((o.q[2 * a] >> (8 * k)) & 255u) * sc, ph = org + (double)((o.q[2 * a + 1] >> (8 * k)) & 255u) * sc;
-            if (!(pl + 0.5 * sc <= (double)lo[k]) || !(ph - 0.5 * sc >= (double)hi[k])) ++n_bad;
-        }
-        if (!(sc > 0) || !isfinite(sc) || !isfinite(org)) ++n_bad;
-    }
-    if (n_bad) atomicAdd(bad, (unsigned long long)n_bad);
-}
-
 }  // namespace devbuild
 }  // namespace take

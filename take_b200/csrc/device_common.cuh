@@ -105,7 +105,6 @@ struct DevScene {
     // fast tree
     const float4 *nodes;    // 4 float4 per FastNode
     const float4 *wide_nodes;  // 8 float4 per WideNode (4-wide collapse of the same tree)
-    const float4 *wide_q;      // 4 float4 per WideQ: the same nodes with 8-bit quantised child boxes (bvh_device.cuh), or null
     const double2 *tris;    // 6 double2 per leaf slot: v0.xy | v0.z,idbits | e1.xy | e1.z,aux | e2.xy | e2.z,kind
     // reference-order tree
     const RefNode *ref_nodes;

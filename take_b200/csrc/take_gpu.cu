@@ -148,7 +148,6 @@ struct TakeScene {
     int width = 0, height = 0;
     // scene storage
     DeviceBuffer env_rgb, env_marg, env_cond;
-    DeviceBuffer wide_q;   // quantised copy of the 4-wide nodes (bounce / shadow passes), empty if the scene keeps the 128-byte ones
     DeviceBuffer nodes, wide_nodes, tris, ref_nodes, positions, normals, uvs, indices, prim_material, prim_light, dfs_rank, prim_flags,
         prim_mtype, spheres, materials, lights, textures, shade_recs, light_recs, light_pmf, light_cdf;
     std::vector<DeviceBuffer *> tex_data;
@@ -174,7 +173,6 @@ struct TakeScene {
     int wave_sets = 0, wave_passes = 0;
     int blocks_extend = 0, blocks_shadow = 0, blocks_isect = 0, blocks_occl = 0, blocks_extend_primary = 0;
     int blocks_extend_refill = 0, blocks_shadow_refill = 0;
-    int use_qnodes = 1;                          // TAKE_QNODES=0: the refill kernels read the 128-byte nodes
     int refill_extend = 0, refill_shadow = 0;   // bounce / shadow passes on the lane-refill kernels (TAKE_REFILL, see scene creation)
     bool wide = true;   // 4-wide nodes (TAKE_BVH_WIDTH=4, default) or binary nodes (TAKE_BVH_WIDTH=2)
     // Device-built scenes: the reference-order tree (tie-break ranks, exact mode) is built by a host thread while the device
@@ -507,17 +505,9 @@ int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, d
             else k_extend_primary<false><<<s->blocks_extend_primary, 128, 0, st>>>(s->dev, w);
         } else if (b >= 1 && s->refill_extend && s->wide) {
             // bounce rays have very different lengths: lanes are refilled as their rays finish (trace_refill4)
-            const bool q = s->dev.wide_q != nullptr && s->use_qnodes;
-            if (w.count_ties) {
-                if (q) k_extend_refill<false, true, true><<<s->blocks_extend_refill, 128, 0, st>>>(s->dev, w, b);
-                else k_extend_refill<false, true, false><<<s->blocks_extend_refill, 128, 0, st>>>(s->dev, w, b);
-            } else if (count) {
-                if (q) k_extend_refill<true, false, true><<<s->blocks_extend_refill, 128, 0, st>>>(s->dev, w, b);
-                else k_extend_refill<true, false, false><<<s->blocks_extend_refill, 128, 0, st>>>(s->dev, w, b);
-            } else {
-                if (q) k_extend_refill<false, false, true><<<s->blocks_extend_refill, 128, 0, st>>>(s->dev, w, b);
-                else k_extend_refill<false, false, false><<<s->blocks_extend_refill, 128, 0, st>>>(s->dev, w, b);
-            }
+            if (w.count_ties) k_extend_refill<false, true><<<s->blocks_extend_refill, 128, 0, st>>>(s->dev, w, b);
+            else if (count) k_extend_refill<true><<<s->blocks_extend_refill, 128, 0, st>>>(s->dev, w, b);
+            else k_extend_refill<false><<<s->blocks_extend_refill, 128, 0, st>>>(s->dev, w, b);
         } else if (w.count_ties && s->wide) {
             k_extend<false, true, true><<<s->blocks_extend, 128, 0, st>>>(s->dev, w, b);
         } else
@@ -535,7 +525,7 @@ int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, d
         if (w.sort_enabled) {
             tm.begin(ST_SORT);
             // (pass 0 is traced one ray per thread or as packets: its hits already finish in slot order)
-            if (w.ordered_sort && b >= 1) k_scatter_ordered<<<s->sm_count * env_int("TAKE_SORT_BLOCKS", 8), 256, 0, st>>>(w, b);
+            if (w.ordered_sort && b >= 1) k_scatter_ordered<<<s->sm_count * 8, 256, 0, st>>>(w, b);
             else k_scatter<<<scatter_blocks, 256, 0, st>>>(w, b);
             tm.end();
             launches++;
@@ -555,9 +545,8 @@ int launch_wave(TakeScene *s, Wave &w, const TakeRenderOpts *o, double *d_sum, d
         if (o->integrator == TAKE_INTEGRATOR_MIS && b <= o->max_depth) {
             tm.begin(ST_SHADOW);
             if (s->refill_shadow && s->wide) {
-                const bool q = s->dev.wide_q != nullptr && s->use_qnodes;
-                if (count) { if (q) k_shadow_refill<true, true><<<s->blocks_shadow_refill, 128, 0, st>>>(s->dev, w, b); else k_shadow_refill<true, false><<<s->blocks_shadow_refill, 128, 0, st>>>(s->dev, w, b); }
-                else { if (q) k_shadow_refill<false, true><<<s->blocks_shadow_refill, 128, 0, st>>>(s->dev, w, b); else k_shadow_refill<false, false><<<s->blocks_shadow_refill, 128, 0, st>>>(s->dev, w, b); }
+                if (count) k_shadow_refill<true><<<s->blocks_shadow_refill, 128, 0, st>>>(s->dev, w, b);
+                else k_shadow_refill<false><<<s->blocks_shadow_refill, 128, 0, st>>>(s->dev, w, b);
             } else
 #if TAKE_EXPERIMENTAL
             if (!s->wide) {
@@ -622,7 +611,6 @@ void fill_wave_ptrs(TakeScene *s, Wave &w, const TakeRenderOpts *o, int set = 0)
         s->refill_extend = r & 1;
         s->refill_shadow = (r >> 1) & 1;
     }
-    s->use_qnodes = env_int("TAKE_QNODES", 1);
     w.ordered_sort = env_int("TAKE_ORDERED_SORT", s->refill_extend) ? 1 : 0;
     w.packet = (w.fused_primary && s->wide && 3 * s->wide_depth + 1 <= TAKE_PACKET_STACK && env_int("TAKE_PACKET", 1)) ? 1 : 0;
 }
@@ -1169,26 +1157,6 @@ static int scene_create_from(int device, const TakeSceneDesc *d, HostBuild *hb, 
     }
     v.fast_depth = s->fast_depth;
     v.abs_max = (float)abs_max;
-    // quantised copy of the 4-wide nodes for the lane-refill kernels (bvh_device.cuh, section 5).  Kept only if the check
-    // pass finds every quantised box around its FP32 box; a scene too large for the plane arithmetic (2^23 * scale * 1e18
-    // must stay finite) keeps the 128-byte nodes.
-    v.wide_q = nullptr;
-    {
-        const int64_t nw = s->device_built ? s->num_fast_nodes : (int64_t)(s->wide_nodes.bytes / sizeof(WideNode));
-        if (nw > 0 && abs_max < 1e12 && env_int("TAKE_QNODES_BUILD", 1)) {
-            CU(s->wide_q.ensure((size_t)nw * sizeof(devbuild::WideQ)));
-            CU(cudaMemsetAsync(s->tie_count.p, 0, 16, st));
-            devbuild::k_quantize_wide<<<(unsigned)((nw + 127) / 128), 128, 0, st>>>(nw, s->wide_nodes.as<WideNode>(), s->wide_q.as<devbuild::WideQ>());
-            devbuild::k_check_wide_q<<<(unsigned)((nw + 127) / 128), 128, 0, st>>>(nw, s->wide_nodes.as<WideNode>(), s->wide_q.as<devbuild::WideQ>(),
-                                                                          s->tie_count.as<unsigned long long>() + 1);
-            unsigned long long bad = 0;
-            CU(cudaMemcpyAsync(&bad, s->tie_count.as<unsigned long long>() + 1, sizeof(bad), cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-            CU(cudaMemsetAsync(s->tie_count.p, 0, 16, st));
-            if (bad == 0) v.wide_q = s->wide_q.as<float4>();
-            else if (env_int("TAKE_TIMING", 0)) fprintf(stderr, "[take_gpu] quantised nodes rejected: %llu planes inside their box\n", bad);
-        }
-    }
 
     // per-primitive shading records, derived on the device from the arrays uploaded above (shading.cuh: ShadeRec)
     t_mark = now_ms();

@@ -668,56 +668,9 @@ __device__ __forceinline__ int32_t visit_wide(const DevScene &sc, int32_t node, 
     return visit_finish<ANY_HIT>(key, ch, r, st);
 }
 
-// The same visit on the QUANTISED copy of the 4-wide nodes (bvh_device.cuh: WideQ, 64 bytes instead of 128): the child boxes
-// are stored as 8-bit plane indices on a per-node grid,  plane(q) = org + q * scale  (scale a power of two), rounded outward
-// by one step more than necessary.  With lanes refilled the bounce passes are bound by the L1 (84 % of its peak, ncu): a
-// divergent load instruction costs one L1 wavefront per lane, and a node now takes two 256-bit loads per lane instead of four.
-//   t(q) = (org + q * scale - (o +- delta)) * idir = q * a + b,   a = scale * idir (exact),  b = fma(org, idir, ol / oh)
-// The byte q becomes a float without a conversion instruction: PRMT builds the bit pattern of 2^23 + q, and the 2^23 is folded
-// into the constant, b' = fma(-2^23, a, b).  b' is rounded at the size of 2^23 * a, i.e. to half a grid step in t -- that is
-// the extra step the builder pads; everything else is the rounding the delta / TAKE_SLACK analysis of trace_fast4 covers (two
-// more FMA roundings of quantities no larger than the plane distances there).  The near / far plane of an axis is picked by
-// the sign of the direction, so no min / max per axis is needed.  Boxes only get LARGER than the FP32 boxes of the 128-byte
-// nodes: a ray may visit a few more nodes, never fewer, and its leaf tests decide as before -- identical results.
-template <bool ANY_HIT, bool COUNT>
-__device__ __forceinline__ int32_t visit_wide_q(const DevScene &sc, int32_t node, const LaneRay &r, float tmin_f, TravStack &st, TravCounters *cnt) {
-    const float4 *N = sc.wide_q + 4 * (int64_t)node;
-    const F8 A = ldg_f8(N), B = ldg_f8(N + 2);
-    const int4 ch = make_int4(__float_as_int(B.b.x), __float_as_int(B.b.y), __float_as_int(B.b.z), __float_as_int(B.b.w));
-    if (COUNT) cnt->box += 4;
-    const float ax = A.a.w * r.idx, ay = A.b.x * r.idy, az = A.b.y * r.idz;
-    const float cx = -8388608.0f * ax, cy = -8388608.0f * ay, cz = -8388608.0f * az;   // exact (power-of-two factor)
-    const float blx = fmaf(A.a.x, r.idx, r.olx) + cx, bhx = fmaf(A.a.x, r.idx, r.ohx) + cx;
-    const float bly = fmaf(A.a.y, r.idy, r.oly) + cy, bhy = fmaf(A.a.y, r.idy, r.ohy) + cy;
-    const float blz = fmaf(A.a.z, r.idz, r.olz) + cz, bhz = fmaf(A.a.z, r.idz, r.ohz) + cz;
-    const bool sx = r.idx < 0.0f, sy = r.idy < 0.0f, sz = r.idz < 0.0f;
-    const uint32_t qlx = __float_as_uint(A.b.z), qhx = __float_as_uint(A.b.w), qly = __float_as_uint(B.a.x), qhy = __float_as_uint(B.a.y),
-                   qlz = __float_as_uint(B.a.z), qhz = __float_as_uint(B.a.w);
-    const uint32_t nx = sx ? qhx : qlx, fx = sx ? qlx : qhx, ny = sy ? qhy : qly, fy = sy ? qly : qhy, nz = sz ? qhz : qlz, fz = sz ? qlz : qhz;
-    const float bnx = sx ? bhx : blx, bfx = sx ? blx : bhx, bny = sy ? bhy : bly, bfy = sy ? bly : bhy, bnz = sz ? bhz : blz, bfz = sz ? blz : bhz;
-    uint32_t key[4];
-#define TAKE_Q(W, K) __uint_as_float(__byte_perm(W, 0x4B000000u, 0x7540u + K))
-#define TAKE_WIDE_CHILD(K, C)                                                                      \
-    {                                                                                              \
-        const float tn = fmaxf(fmaxf(fmaf(TAKE_Q(nx, K), ax, bnx), fmaf(TAKE_Q(ny, K), ay, bny)),   \
-                               fmaxf(fmaf(TAKE_Q(nz, K), az, bnz), tmin_f));                       \
-        const float tf = fminf(fminf(fmaf(TAKE_Q(fx, K), ax, bfx), fmaf(TAKE_Q(fy, K), ay, bfy)),   \
-                               fminf(fmaf(TAKE_Q(fz, K), az, bfz), r.tbest_f));                    \
-        const bool h = (tn <= tf * TAKE_SLACK) && (C != TAKE_WIDE_EMPTY);                          \
-        key[K] = h ? ((__float_as_uint(tn) & 0xfffffffcu) | (uint32_t)K) : 0xffffffffu;            \
-    }
-    TAKE_WIDE_CHILD(0, ch.x)
-    TAKE_WIDE_CHILD(1, ch.y)
-    TAKE_WIDE_CHILD(2, ch.z)
-    TAKE_WIDE_CHILD(3, ch.w)
-#undef TAKE_WIDE_CHILD
-#undef TAKE_Q
-    return visit_finish<ANY_HIT>(key, ch, r, st);
-}
-
 // `IO` supplies  void load(uint32_t i, const DevScene&, LaneRay&)  (queue entry i -> this lane's ray) and
 // void retire(unsigned mask, bool mine, const HitOut&)  (called by the whole warp; `mask` = the lanes handing over a result).
-template <bool ANY_HIT, bool COUNT, bool TIES, bool QNODES, typename IO>
+template <bool ANY_HIT, bool COUNT, bool TIES, typename IO>
 __device__ __forceinline__ void trace_refill4(const DevScene &sc, IO &io, uint32_t n, uint32_t *fetch, TravStack &st, TravCounters *cnt) {
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -759,7 +712,7 @@ __device__ __forceinline__ void trace_refill4(const DevScene &sc, IO &io, uint32
         const bool want_leaf = state == 1 && node < 0 && node != TAKE_NODE_DONE;
         const int n_node = __popc(__ballot_sync(0xffffffffu, want_node)), n_leaf = __popc(__ballot_sync(0xffffffffu, want_leaf));
         if (n_node * TAKE_REFILL_NODE_BIAS >= n_leaf * 4) {
-            if (want_node) node = QNODES ? visit_wide_q<ANY_HIT, COUNT>(sc, node, r, tmin_f, st, cnt) : visit_wide<ANY_HIT, COUNT>(sc, node, r, tmin_f, st, cnt);
+            if (want_node) node = visit_wide<ANY_HIT, COUNT>(sc, node, r, tmin_f, st, cnt);
         } else if (want_leaf) {
             const int32_t code = ~node;
             const int64_t first = code >> 3;

@@ -1044,13 +1044,13 @@ struct ExtendRefillIO {
 #ifndef TAKE_REFILL_MIN_BLOCKS
 #define TAKE_REFILL_MIN_BLOCKS TAKE_BOUNCE_MIN_BLOCKS
 #endif
-template <bool COUNT, bool TIES = false, bool QNODES = false>
+template <bool COUNT, bool TIES = false>
 __global__ void __launch_bounds__(128, TAKE_REFILL_MIN_BLOCKS) k_extend_refill(DevScene sc, Wave w, int pass) {
     TAKE_DECLARE_STACK(st);
     PassCounters &pc = w.pass[pass];
     ExtendRefillIO io = {w, pc, w.q_extend[pass & 1], sc.prim_mtype, -1, 0};
     TravCounters cnt = {0, 0};
-    trace_refill4<false, COUNT, TIES, QNODES>(sc, io, pc.n_extend, &pc.fetch_extend, st, &cnt);
+    trace_refill4<false, COUNT, TIES>(sc, io, pc.n_extend, &pc.fetch_extend, st, &cnt);
     if (COUNT) {
         atomicAdd(&w.totals->box_tests, cnt.box);
         atomicAdd(&w.totals->tri_tests, cnt.tri);
@@ -1075,13 +1075,13 @@ struct ShadowRefillIO {
     }
 };
 
-template <bool COUNT, bool QNODES = false>
+template <bool COUNT>
 __global__ void __launch_bounds__(128, TAKE_REFILL_MIN_BLOCKS) k_shadow_refill(DevScene sc, Wave w, int pass) {
     TAKE_DECLARE_STACK(st);
     PassCounters &pc = w.pass[pass];
     ShadowRefillIO io = {w, -1};
     TravCounters cnt = {0, 0};
-    trace_refill4<true, COUNT, false, QNODES>(sc, io, pc.n_shadow, &pc.fetch_shadow, st, &cnt);
+    trace_refill4<true, COUNT, false>(sc, io, pc.n_shadow, &pc.fetch_shadow, st, &cnt);
     if (COUNT) {
         atomicAdd(&w.totals->shadow_box_tests, cnt.box);
         atomicAdd(&w.totals->shadow_tri_tests, cnt.tri);

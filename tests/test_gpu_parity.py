@@ -222,7 +222,6 @@ def test_render_properties(pair, monkeypatch):
         for k in ("samples", "extend_rays", "shadow_rays", "shaded"):
             assert st_f[k] == st_g[k], (integ, k)
     for integ in ("mis", "one_sample_mis", "raw"):                               # bounce / shadow passes: lane refill vs one ray per thread
-        monkeypatch.setenv("TAKE_QNODES", "0")                                   # (same node boxes, so the test counts must agree too)
         f, f2, st_f = gs.render_sums(integ, 5, 0, 4, seed=5, flags=api.RENDER_COUNT_TESTS)
         for env in ({"TAKE_REFILL": "0"}, {"TAKE_REFILL": "1"}, {"TAKE_REFILL": "2"}, {"TAKE_ORDERED_SORT": "0"},
                     {"TAKE_REFILL": "0", "TAKE_ORDERED_SORT": "1"}):
@@ -234,14 +233,6 @@ def test_render_properties(pair, monkeypatch):
             assert np.array_equal(f, g) and np.array_equal(f2, g2), (integ, env)
             for k in ("samples", "extend_rays", "shadow_rays", "shaded", "box_tests", "tri_tests", "shadow_box_tests", "shadow_tri_tests"):   # every ray walks the same nodes
                 assert st_f[k] == st_g[k], (integ, env, k)
-        monkeypatch.delenv("TAKE_QNODES")
-        # the quantised (64-byte) nodes: boxes a little larger -- a few more tests, the same image
-        q, q2, st_q = gs.render_sums(integ, 5, 0, 4, seed=5, flags=api.RENDER_COUNT_TESTS)
-        assert np.array_equal(f, q) and np.array_equal(f2, q2), integ
-        for k in ("samples", "extend_rays", "shadow_rays", "shaded"):
-            assert st_f[k] == st_q[k], (integ, k)
-        assert st_f["box_tests"] <= st_q["box_tests"] <= 1.25 * st_f["box_tests"] + 64, (st_f["box_tests"], st_q["box_tests"])
-        assert st_f["tri_tests"] <= st_q["tri_tests"] <= 1.25 * st_f["tri_tests"] + 64
     monkeypatch.setenv("TAKE_WAVE_SLOTS", "1500")                                # force pixel chunking + many waves
     d, d2, _ = gs.render_sums("mis", 5, 0, 4, seed=5)
     assert np.array_equal(a, d) and np.array_equal(a2, d2)
