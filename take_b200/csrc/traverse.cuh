@@ -565,6 +565,11 @@ __device__ __forceinline__ void trace_packet4(const DevScene &sc, D3 o, D3 d, do
 //     L1 wavefront per lane, so the FP64 origin / direction live in registers at 80 registers per thread (6 resident
 //     blocks) instead of being re-read per leaf;
 //   * the hits are put into queue order by the sort (k_scatter_ordered), not into the order in which the rays finished.
+// Measured and not kept: one primitive of a leaf per step instead of the loop over its 1 to 4 primitives (+2 ... +10 % slower
+// -- the loop keeps the loads of consecutive leaf records in flight together); a 64-byte copy of the nodes with 8-bit
+// quantised child boxes, i.e. two L1 wavefronts per visit instead of four (identical images, extend +3 ... +7 % slower: the
+// decode -- 24 byte-to-float conversions, a per-node grid to set up, near / far selection -- costs more issue slots than the
+// L1 gives back; any-hit passes -2 ... -4 %).
 // The closest hit and the tie rule do not depend on the order in which a ray's leaves are visited, and each ray is still
 // traced by one lane with trace_fast4's arithmetic: identical results.
 // ---------------------------------------------------------------------------------------------------------
