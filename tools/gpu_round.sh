@@ -38,7 +38,9 @@ fi
 
 capture() {  # capture <name> <ncu kernel regex> <count> <timeout> <prof_run args...>
   local name=$1 rx=$2 cnt=$3 to=$4; shift 4
-  timeout $to ncu --set full --clock-control none --import-source on -k "regex:$rx" -c $cnt -f -o $O/prof_$name \
+  # (TAKE_PROVISIONAL=0: the first render waits for the tie-break ranks, so the captured kernels are the regular ones and not
+  #  the tie-counting instantiations a render ahead of the reference tree uses)
+  TAKE_PROVISIONAL=0 timeout $to ncu --set full --clock-control none --import-source on -k "regex:$rx" -c $cnt -f -o $O/prof_$name \
       python tools/prof_run.py "$@" > $O/ncu_$name.log 2>&1
   echo "ncu $name exit $?"
   if [ -f $O/prof_$name.ncu-rep ]; then
