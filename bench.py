@@ -416,7 +416,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         e2e["c_abi_async_mrays_per_s"] = o_rays / (time.perf_counter() - t0) / 1e6
         t0 = time.perf_counter()
-        _, _, st = gs.render_sums(INTEGRATOR, MAX_DEPTH, 0, S, seed=SEED)
+        _, _, st = gs.render_sums(INTEGRATOR, MAX_DEPTH, 0, S, seed=SEED, out=h_bufs[0])
         e2e["c_abi_blocking_mrays_per_s"] = (st["extend_rays"] + st["shadow_rays"]) / (time.perf_counter() - t0) / 1e6
 
     # ---- roofline of the dominant kernels (N = 1): events inside the library on the launching stream --------------
@@ -533,8 +533,18 @@ def scene_job(key, entry, sr, local, world, rank, barrier, allmax, allsum, peak,
     own = sr is None
     builder = make()
     flat = builder.flat()
-    create_ms = cold_ms = phases = None
+    create_ms = cold_ms = phases = prov = None
     npix = flat.width * flat.height
+    if not own:
+        # the headline scene is already resident (its creation was the first thing this process did with the library: the
+        # top-level scene_create_ms carries module loading and the first growth of the memory pool); time a second replica
+        from take_b200 import api
+        barrier()
+        t0 = time.perf_counter()
+        g2 = api.GpuScene(flat, device=local)
+        create_ms = 1e3 * allmax(time.perf_counter() - t0)
+        phases = g2.create_timings()
+        g2.close()
     if own:
         # cold: scene creation and the whole job back to back, as a host that renders one image does -- the fast tree is built
         # on the device, the reference-order tree on a background host thread that the render does not wait for
@@ -569,8 +579,9 @@ def scene_job(key, entry, sr, local, world, rank, barrier, allmax, allsum, peak,
             row["scene_create_ms"] = create_ms               # take_gpu_scene_create: upload + fast tree built on the device
             row["scene_create_phases_ms"] = {k: round(v, 2) for k, v in phases.items()}
             row["e2e_job_ms"] = create_ms + 1e3 * job_s      # create + render + reduce + read-back (the Amdahl term)
-            row["e2e_job_cold_ms"] = cold_ms                 # the same measured cold in one go: + first-use allocations (wave buffers, pinned memory)
-            row["provisional"] = prov                        # renders that ran ahead of the background reference-order tree / repeated
+            if cold_ms is not None:
+                row["e2e_job_cold_ms"] = cold_ms             # the same measured cold in one go: + first-use allocations (wave buffers, pinned memory)
+                row["provisional"] = prov                    # renders that ran ahead of the background reference-order tree / repeated
         if note:
             row["note"] = note
         if rank == 0 and world == 1:

@@ -269,9 +269,15 @@ class GpuScene:
         return TakeRenderOpts(INTEGRATORS[integrator], max_depth, spp_begin, spp_end, seed, flags, getattr(self, "rr_start", 0))
 
     # the tile loop of render() (src/render.cpp:59-82): sums of samples [spp_begin, spp_end) per pixel
-    def render_sums(self, integrator="mis", max_depth=5, spp_begin=0, spp_end=1, seed=0, sumsq=True, flags=0):
-        s = np.empty((self.height, self.width, 3), np.float64)
-        s2 = np.empty_like(s) if sumsq else None
+    def render_sums(self, integrator="mis", max_depth=5, spp_begin=0, spp_end=1, seed=0, sumsq=True, flags=0, out=None):
+        """The blocking take_gpu_render.  `out` = (sum, sumsq) host arrays to fill (page-locked ones make the copy 3x faster)."""
+        if out is not None:
+            s, s2 = out
+            assert s.dtype == np.float64 and s.flags["C_CONTIGUOUS"] and s.size == self.height * self.width * 3
+            sumsq = s2 is not None
+        else:
+            s = np.empty((self.height, self.width, 3), np.float64)
+            s2 = np.empty_like(s) if sumsq else None
         st = TakeStats()
         o = self._opts(integrator, max_depth, spp_begin, spp_end, seed, flags)
         _check(self.lib.take_gpu_render(self.h, C.byref(o), s.ctypes.data, s2.ctypes.data if sumsq else None, C.byref(st)))
