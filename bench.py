@@ -269,6 +269,7 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        tdist.configure_nccl_for_overlap()         # few NCCL channels: the per-step reduce overlaps kernels, it does not race them
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
@@ -456,6 +457,7 @@ def run_ours(args):
             "config": base_config(flat),
             "run": {"spp_per_step_per_gpu": S, "parallelism": f"spp-range x{world}, scene replicated, one NCCL sum-reduce per step "
                                                               "(overlapped with the next step's kernels)",
+                    "nccl_max_nchannels": os.environ.get("NCCL_MAX_NCHANNELS") if world > 1 else None,
                     "l2": "inputs larger than L2: each wave streams up to 33.5 M path records (300 B/slot, 10 GB) besides 130 MB of "
                           "tree + leaf records (L2 is 126 MB); no explicit flush",
                     "bvh": {"wide_nodes": int(info["fast_nodes"]), "depth": int(info["fast_tree_depth"]), "sah_cost": info["sah_cost"],
