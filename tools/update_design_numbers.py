@@ -1,55 +1,94 @@
-"""Rewrite section 11 of DESIGN.md from the artefacts in profiles/ (run after copying a gpurun's results there)."""
-import json, os
+"""Rewrite section 11 of DESIGN.md from the artefacts in profiles/ (run after copying a gpurun's results there).
+usage: python tools/update_design_numbers.py [tag=r02]"""
+import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r02"
 P = lambda n: os.path.join(ROOT, "profiles", n)
-b = json.load(open(P("r01_bench_n1.json")))
+b = json.load(open(P(f"{TAG}_bench_n1.json")))
+ref = json.load(open(P(f"{TAG}_bench_reference_n1.json")))
 r = b["roofline"]
-rows = [json.loads(l) for l in open(P("r01_report_scenes.jsonl"))]
+n = r.get("ncu") or {}
+e = b["e2e"]
 sec = f"""
-## 11. Round-1 measurements (B200, SM clock {b['clocks']['sm_mhz']:.0f} MHz during the timed regions, throttle reasons: {b['clocks']['reasons'] or 'none'})
+## 11. Round-2 measurements (B200, SM clock {b['clocks']['sm_mhz']:.0f} MHz during the timed regions, throttle reasons: {b['clocks']['reasons'] or 'none'})
 
-`bench.py` at N = 1 (`profiles/r01_bench_n1.json`; the reference arm of the same run is `r01_bench_reference_n1.json`):
+`bench.py` at N = 1 (`profiles/{TAG}_bench_n1.json`; the reference arm of the same box is `{TAG}_bench_reference_n1.json`;
+round 1's line is `r01_bench_n1.json`: 4573 Mrays/s, 17.29 ms per step):
 
 | quantity | value |
 |---|---|
-| `value` — whole pipeline, buffers resident in HBM | **{b['value']:.0f} Mrays/s**, {b['samples_per_s']/1e6:.0f} M path samples/s, {b['ms_per_step']:.2f} ms per {b['config']['spp_per_step_per_gpu']}-spp step |
-| `e2e` — `take_gpu_render_async` / `_wait` with pinned host buffers (99.5 MB device→host per step, overlapped with the next step) | {b['e2e']['value']:.0f} Mrays/s (blocking `take_gpu_render`: {b['e2e']['blocking_call_mrays_per_s']:.0f}) |
-| `k_extend` alone | **{r['extend_grays_per_s']:.2f} Grays/s** (north-star target: ≥ 1 Grays/s on this scene) |
-| `roofline` — algorithmic bytes / launch time vs. measured HBM {r['peak']:.0f} GB/s | {r['achieved']:.0f} GB/s = {r['frac']:.2f}; measured DRAM traffic per launch {r['traffic']/1e6:.0f} MB vs {r['bytes_per_launch']/1e6:.0f} MB algorithmic (caches absorb the rest) |
+| `value` — whole pipeline, every step with its own reduce, buffers resident in HBM | **{b['value']:.0f} Mrays/s**, {b['samples_per_s']/1e6:.0f} M path samples/s, {b['ms_per_step']:.2f} ms per {b['run']['spp_per_step_per_gpu']}-spp step |
+| `e2e` — `ShardedRenderer.submit(to_host=True)`: the reduced Σx, Σx² images ({e['d2h_bytes_per_step']/1e6:.1f} MB) in pinned host memory every step | {e['value']:.0f} Mrays/s; pure C-ABI loops: `take_gpu_render_async` / `_wait` {e['c_abi_async_mrays_per_s']:.0f}, blocking `take_gpu_render` {e['c_abi_blocking_mrays_per_s']:.0f} |
+| reference arm (`--impl reference`: the reference's own integrator, {ref['cpu_baseline']['cores']} host cores, same config dict) | {ref['value']:.2f} Mrays/s → e2e ratio {e['value']/ref['value']:.0f}× |
+| extend kernels alone | **{r['extend_grays_per_s']:.2f} Grays/s** (north-star target: ≥ 1 Grays/s on this scene) |
+| `roofline` — algorithmic bytes / launch time vs. measured HBM {r['peak']:.0f} GB/s | {r['achieved']:.0f} GB/s = {r['frac']:.2f}; measured DRAM traffic per launch {(r['traffic'] or 0)/1e6:.0f} MB vs {r['bytes_per_launch']/1e6:.0f} MB algorithmic (caches absorb the rest) |
+| ncu, all 14 extend launches of a step (`profiles/ncu_metrics.json`, sources {json.load(open(P('ncu_metrics.json')))['source_hash']}) | L2→SM {n.get('l2_to_sm_gbps')} GB/s, DRAM {n.get('dram_gbps')} GB/s, issue slots used {n.get('issue_active_pct')} %, {n.get('lanes_per_instruction')} lanes per instruction, occupancy {n.get('achieved_occupancy_pct')} % |
 | box / leaf tests per ray (4-wide tree) | {r['box_tests_per_ray']:.1f} / {r['tri_tests_per_ray']:.2f} (reference tree and order: 224 / 6.7) |
-| test rate vs FP32 peak | {r['test_rate_tflops']:.2f} TFLOP/s of {r['fp32_peak_tflops']:.1f} = {100*r['test_rate_frac_fp32']:.1f} % |
+| `k_shade` (352 B per vertex) | {r['kernels']['k_shade']['achieved']:.0f} GB/s = {r['kernels']['k_shade']['frac']:.2f} of the HBM peak, {r['kernels']['k_shade']['vertices_per_s']/1e9:.2f} G vertices/s |
 | stage share of a step (CUDA events) | extend {100*r['stage_share']['extend']:.0f} %, shade {100*r['stage_share']['shade']:.0f} %, sort {100*r['stage_share']['sort']:.0f} %, accumulate {100*r['stage_share']['other']:.0f} % |
 | kernels launched in the timed region | {b['gpu_launches']} |
-| reference CPU renderer, same box, {b['cpu_baseline']['cores']} cores (`{b['cpu_baseline']['kind']}`) | {b['cpu_baseline']['value']:.2f} Mrays/s ({b['cpu_baseline']['samples_per_s']/1e6:.2f} M samples/s) on {b['cpu_baseline']['sample'].split(',')[0]}, …) |
-| `take_gpu_scene_create` (host BVH builds + upload), one-time | {b['scene_create_ms']:.0f} ms |
+| reference CPU renderer beside it, {b['cpu_baseline']['cores']} cores (`{b['cpu_baseline']['kind']}`) | {b['cpu_baseline']['value']:.2f} Mrays/s ({b['cpu_baseline']['samples_per_s']/1e6:.2f} M samples/s) on {b['cpu_baseline']['sample'].split(',')[0]}, …) |
+| `take_gpu_scene_create`, first call of the process / second replica | {b['scene_create_ms']:.0f} ms / {[x for x in b['scenes'] if x.get('key') == 'c2'][0].get('scene_create_ms', float('nan')):.0f} ms (device tree {b['run']['bvh']['build_ms_fast_tree_device']:.0f} ms; reference-order tree in the background {b['run']['bvh']['build_ms_reference_order_tree_host_background']:.0f} ms) |
 
-All five BASELINE.json configs (`tools/report_scenes.py`, `profiles/r01_report_scenes.jsonl`; GPU = best of 3 after a
-warm-up, CPU = the reference's own integrator through `oracle/_ref` on all host cores where it exists, our CPU
-restatement for the environment-map scene and the 10 M scene; ~5 s of CPU work each):
+All BASELINE.json configs as one job each (`scenes` of the same line; job = full spp range → reduced image on the host;
+CPU = the reference's own integrator through `oracle/_ref` on all host cores where it can parse the scene, our CPU
+restatement for the environment-map / GGX / 10 M scenes; bounded samples of ~5 s):
 
-| config | primitives | integrator | GPU Mrays/s | GPU M samples/s | CPU M samples/s | BVH build + upload |
-|---|---|---|---|---|---|---|
+| config | primitives | integrator, spp of the job | job ms | GPU Mrays/s | GPU M samples/s | CPU M samples/s | ratio | scene create ms | create + job ms (warm / cold process) |
+|---|---|---|---|---|---|---|---|---|---|
 """
-for x in rows:
-    sec += (f"| {x['config']} | {x['prims']:,} | {x['integrator']} | {x['gpu_mrays_s']:.0f} | {x['gpu_msamples_s']:.0f} | "
-            f"{x['cpu_msamples_s']:.2f} ({x['cpu_kind']}, {x['cpu_cores']} cores) | {x['scene_create_s']:.2f} s |\n")
-scale = [json.load(open(P(f"r01_scale_n{n}.json"))) for n in (1, 2, 4, 8) if os.path.exists(P(f"r01_scale_n{n}.json"))]
+for x in b["scenes"]:
+    if "error" in x:
+        continue
+    c = x.get("cpu_baseline") or {}
+    cs = c.get("samples_per_s")
+    sec += (f"| {x['key']} | {x['triangles']:,} | {x['integrator']}, {x['spp_job']} | {x['job_ms']:.1f} | {x['mrays_per_s']:.0f} | {x['samples_per_s']/1e6:.0f} | "
+            f"{(cs or 0)/1e6:.2f} ({c.get('kind')}, {c.get('cores')} cores) | {x['samples_per_s']/cs:.0f}× | {x.get('scene_create_ms', float('nan')):.1f} | "
+            f"{x.get('e2e_job_ms', float('nan')):.0f} / {('%.0f' % x['e2e_job_cold_ms']) if 'e2e_job_cold_ms' in x else '— (resident)'} |\n")
+c1 = [x for x in b["scenes"] if x.get("key") == "c1"]
+if c1 and c1[0].get("cpu_stock_cli"):
+    s = c1[0]["cpu_stock_cli"]
+    sec += (f"\nStock executable on config 1 as specified ({s['what']}): {s['seconds']:.2f} s = {s['samples_per_s']/1e6:.2f} M samples/s on {s['cores']} cores; "
+            f"the GPU job takes {c1[0]['job_ms']:.1f} ms ({c1[0]['samples_per_s']/s['samples_per_s']:.0f}×).\n")
+scale = [json.load(open(P(f"{TAG}_scale_n{k}.json"))) for k in (1, 2, 4, 8) if os.path.exists(P(f"{TAG}_scale_n{k}.json"))]
 if scale:
-    base = scale[0]["value"]
-    sec += ("\nMulti-GPU (weak scaling, one process per GPU, one NCCL all-reduce inside the timed region; `profiles/r01_scale_n*.json`):\n\n"
-            f"| GPUs | Mrays/s | e2e Mrays/s | M path samples/s | ms per step ({scale[0]['config']['spp_per_step_per_gpu']} spp per GPU) | efficiency vs N=1 |\n|---|---|---|---|---|---|\n")
+    base, ebase = scale[0]["value"], scale[0]["e2e"]["value"]
+    sec += (f"\nMulti-GPU, weak scaling of the headline (one process per GPU, `ShardedRenderer`, **one NCCL reduce per step** inside the timed "
+            f"region, NCCL limited to four channels; `profiles/{TAG}_scale_n*.json`):\n\n"
+            "| GPUs | Mrays/s | e2e Mrays/s | ms per step | efficiency (value / e2e) | in-run checks |\n|---|---|---|---|---|---|\n")
     for x in scale:
-        sec += f"| {x['n_gpus']} | {x['value']:.0f} | {x['e2e']['value']:.0f} | {x['samples_per_s']/1e6:.0f} | {x['ms_per_step']:.2f} | {100*x['value']/(base*x['n_gpus']):.1f} % |\n"
-    sec += ("\n(8×B200 box of the same pool; every rank renders its own sample range of every step, the two 49.8 MB buffers are\n"
-            "all-reduced once at the end; `e2e` = every rank's host loop at once, each reading 99.5 MB per step back into its own\n"
-            "pinned buffers -- the rays of all ranks over the slowest rank's time; `take_gpu_render_multi` was checked against the\n"
-            "single-GPU image on a 2-GPU box.)\n")
+        ck = x.get("checks") or {}
+        ok = ", ".join(f"{k.split('_vs_')[0]} {'ok' if v.get('ok') else 'FAILED'} ({v.get('max_rel_diff_sum', float('nan')):.1e})" for k, v in ck.items()) or "—"
+        sec += (f"| {x['n_gpus']} | {x['value']:.0f} | {x['e2e']['value']:.0f} | {x['ms_per_step']:.2f} | {100*x['value']/(base*x['n_gpus']):.1f} % / "
+                f"{100*x['e2e']['value']/(ebase*x['n_gpus']):.1f} % | {ok} |\n")
+    sec += "\nStrong scaling of the jobs above (same files; job ms, efficiency against N = 1):\n\n| config | " + " | ".join(f"N = {x['n_gpus']}" for x in scale) + " |\n|---|" + "---|" * len(scale) + "\n"
+    keys = [x["key"] for x in scale[0]["scenes"] if "error" not in x]
+    for k in keys:
+        row = f"| {k} |"
+        j1 = None
+        for x in scale:
+            m = [y for y in x["scenes"] if y.get("key") == k and "error" not in y]
+            if not m:
+                row += " — |"
+                continue
+            j = m[0]["job_ms"]
+            j1 = j1 or j
+            row += f" {j:.1f} ms ({100*j1/(j*x['n_gpus']):.0f} %) |"
+        sec += row + "\n"
+ml = P(f"{TAG}_mesh_load_10M.json")
+if os.path.exists(ml):
+    m = json.load(open(ml))
+    sec += (f"\nMesh loading (`profiles/{TAG}_mesh_load_10M.json`, {m['host_threads']} host threads, this container): {m['triangles']:,} triangles, "
+            f"{m['file_MB']:.0f} MB binary PLY without normals → flat arrays in **{m['builder_s']:.2f} s** (read {m['builder_ms']['ms_read']:.0f} ms, "
+            f"convert {m['builder_ms']['ms_convert']:.0f} ms, vertex normals {m['builder_ms']['ms_normals']:.0f} ms, append {m['builder_ms']['ms_append']:.0f} ms); "
+            f"the reference parser with its BVH: {m['reference_parse_and_bvh_s']:.1f} s; arrays identical: {m['identical']}.\n")
 sec += ("\n`compute-sanitizer` is closed on this pool (gpurun refuses it), so memory safety rests on the parity suite, the\n"
         "host-side validation of every index array in `take_gpu_scene_create`, and `tools/sanitize_run.py` (every kernel on\n"
         "tiny waves and chunked images) running clean.\n")
 p = os.path.join(ROOT, "DESIGN.md")
 s = open(p).read()
-if "\n## 11. Round-1 measurements" in s:
-    s = s[:s.index("\n## 11. Round-1 measurements")]
+for head in ("\n## 11. Round-1 measurements", "\n## 11. Round-2 measurements"):
+    if head in s:
+        s = s[:s.index(head)]
 open(p, "w").write(s.rstrip("\n") + "\n" + sec)
 print("DESIGN.md section 11 rewritten")
