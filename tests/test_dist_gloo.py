@@ -44,6 +44,16 @@ def _worker(rank, world, port, spp, out_path):
     dist.destroy_process_group()
 
 
+def test_nccl_overlap_setting_respects_the_user(monkeypatch):
+    """configure_nccl_for_overlap() limits NCCL's channels for the overlapped per-job reduce -- unless the user set them."""
+    monkeypatch.delenv("NCCL_MAX_NCHANNELS", raising=False)
+    tdist.configure_nccl_for_overlap()
+    assert os.environ["NCCL_MAX_NCHANNELS"] == "4"
+    monkeypatch.setenv("NCCL_MAX_NCHANNELS", "12")
+    tdist.configure_nccl_for_overlap(2)
+    assert os.environ["NCCL_MAX_NCHANNELS"] == "12"
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_sharded_render_equals_single_process(tmp_path, oracle_lib, world):
     from take_b200 import scenes
