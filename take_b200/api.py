@@ -65,14 +65,16 @@ class TakeGpuError(RuntimeError):
 
 
 def kernel_source_hash() -> str:
-    """Short hash of the sources libtake_gpu.so is built from: profile summaries under profiles/ carry it, so a number read
-    from a capture can be tied to the kernels it was captured from (bench.py quotes ncu figures only when it matches)."""
+    """Short hash of the sources the KERNELS of libtake_gpu.so are built from (*.cu, *.cuh, the headers they include and the
+    Makefile with its flags; not the host-only *.cpp files: mesh loading, EXR writing, host tree builders): profile summaries
+    under profiles/ carry it, so a number read from a capture can be tied to the kernels it was captured from (bench.py quotes
+    ncu figures only when it matches)."""
     import glob
     import hashlib
     h = hashlib.sha1()
     d = os.path.join(_HERE, "csrc")
     for p in sorted(glob.glob(os.path.join(d, "*.cu")) + glob.glob(os.path.join(d, "*.cuh")) + glob.glob(os.path.join(d, "*.h")) +
-                    glob.glob(os.path.join(d, "*.cpp")) + [os.path.join(d, "Makefile")]):
+                    [os.path.join(d, "Makefile")]):
         h.update(os.path.basename(p).encode())
         h.update(open(p, "rb").read())
     return h.hexdigest()[:12]
@@ -134,7 +136,7 @@ def load_library(path: str = LIB_PATH):
 
 def _check(rc):
     if rc != 0:
-        raise TakeGpuError(f"take_gpu error {rc}: {load_library().take_gpu_last_error().decode()}")
+        raise TakeGpuError(f"take_gpu error {rc}: {load_library().take_gpu_last_error().decode(errors='replace')}")
 
 
 def device_count() -> int:

@@ -303,6 +303,9 @@ int load_ply(const char *path, const double *to_world, const double *inv_to_worl
     if (ve->has_list) { err = std::string("list properties on vertices are not supported: ") + path; return TAKE_E_INVALID; }
     const int64_t nv = ve->count, nf = fe->count;
     if (nv < 0 || nf < 0 || nv >= ((int64_t)1 << 31)) { err = "bad PLY element counts"; return TAKE_E_INVALID; }
+    // (every vertex and every face takes at least one byte of the file, in every format: a header that promises more is
+    //  refused before anything is sized by it)
+    if (nv > size || nf > size) { err = std::string("PLY element counts exceed the file size: ") + path; return TAKE_E_INVALID; }
     if (!to_world) to_world = kIdentity;
     if (!inv_to_world) inv_to_world = kIdentity;
     try {
@@ -310,7 +313,7 @@ int load_ply(const char *path, const double *to_world, const double *inv_to_worl
         if (has_n) m.nrm.resize((size_t)nv * 3);
         if (has_uv) m.uv.resize((size_t)nv * 2);
         m.idx.resize((size_t)nf * 3);
-    } catch (const std::bad_alloc &) { err = "out of memory"; return TAKE_E_NOMEM; }
+    } catch (const std::exception &) { err = "out of memory"; return TAKE_E_NOMEM; }
     const double t1 = now_ms();
     std::atomic<int> bad(0);  // 1: face with != 3 indices, 2: truncated data
     auto put_vertex = [&](int64_t i, const double *xyz, const double *n3, const double *uv2) {
@@ -482,6 +485,7 @@ int take_gpu_builder_destroy(TakeDescBuilder *b) {
 int take_gpu_builder_add_ply(TakeDescBuilder *b, const char *path, const double *to_world, const double *inv_to_world,
                              int32_t material_id, int32_t face_normals, const double *radiance) {
     if (!b || !path) return fail(TAKE_E_INVALID, "null argument");
+    try {
     Mesh m;
     std::string err;
     double ms[2] = {0, 0};
@@ -497,6 +501,11 @@ int take_gpu_builder_add_ply(TakeDescBuilder *b, const char *path, const double 
     const int rc = append_mesh(b, m, material_id, radiance);
     b->ms_append = now_ms() - t0;
     return rc;
+    } catch (const std::bad_alloc &) {
+        return fail(TAKE_E_NOMEM, "out of memory");
+    } catch (const std::exception &e) {   // nothing may propagate through the C boundary
+        return fail(TAKE_E_INVALID, std::string("PLY loader: ") + e.what());
+    }
 }
 
 int take_gpu_builder_add_mesh(TakeDescBuilder *b, int64_t num_vertices, const double *positions, const double *normals, const double *uvs,

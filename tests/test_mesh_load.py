@@ -214,6 +214,41 @@ def test_builder_refuses_bad_files(tmp_path):
     b.close()
 
 
+def test_corrupted_files_are_refused_not_crashed_on(tmp_path):
+    """Nothing may propagate through the C boundary: a header that promises 10^11 faces (a std::length_error inside the
+    loader before the fix), truncations, flipped bytes, absurd counts -- every case is either refused with an error code or
+    accepted with all indices in range, in all three formats."""
+    rng = np.random.default_rng(5)
+    P, T = bumpy_mesh(2, 2)
+    for fmt in ("binary_little_endian", "binary_big_endian", "ascii"):
+        good = str(tmp_path / f"good_{fmt}.ply")
+        write_ply_variant(good, P, T, fmt=fmt)
+        data = open(good, "rb").read()
+        cases = [data.replace(b"element face %d" % len(T), b"element face 100000000000"),
+                 data.replace(b"element vertex %d" % len(P), b"element vertex 4000000000"),
+                 data.replace(b"element face %d" % len(T), b"element face -3")]
+        for _ in range(40):
+            b_ = bytearray(data)
+            if rng.random() < 0.5:
+                b_ = b_[:int(rng.integers(0, len(b_)))]
+            else:
+                for _ in range(int(rng.integers(1, 8))):
+                    b_[int(rng.integers(0, len(b_)))] = int(rng.integers(0, 256))
+            cases.append(bytes(b_))
+        for i, c in enumerate(cases):
+            p = str(tmp_path / f"case_{fmt}_{i}.ply")
+            open(p, "wb").write(c)
+            b = api.DescBuilder()
+            try:
+                b.add_ply(p, 0)
+                a = b.arrays()
+                assert a["indices"].size == 0 or (a["indices"].min() >= 0 and a["indices"].max() < len(a["positions"]))
+            except api.TakeGpuError:
+                pass
+            finally:
+                b.close()
+
+
 def test_large_mesh_parallel_paths_equal_small_path(tmp_path):
     """A mesh big enough for every loop to run in chunks on several threads gives the same arrays as the add_mesh route fed
     with numpy data (same code, single chunk sizes differ) -- and computed normals do not depend on the thread count."""
