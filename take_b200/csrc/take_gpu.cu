@@ -692,6 +692,15 @@ void read_totals(TakeScene *s, TakeStats *stats, const StageTimer &tm, double ms
 
 extern "C" {
 
+// Nothing may propagate through the C boundary: the entry points that size host containers by caller-supplied counts or do
+// file I/O are function-try-blocks ending in this.
+static int translate_exception() noexcept {
+    try { throw; }
+    catch (const std::bad_alloc &) { return fail(TAKE_E_NOMEM, "out of host memory"); }
+    catch (const std::exception &e) { return fail(TAKE_E_INVALID, std::string("internal error: ") + e.what()); }
+    catch (...) { return fail(TAKE_E_INVALID, "internal error"); }
+}
+
 const char *take_gpu_last_error(void) { return g_error.c_str(); }
 int take_exr_fail(int code, const std::string &msg) { return fail(code, msg); }  // for exr_write.cpp
 const char *take_gpu_version(void) { return "take_b200 0.1 (sm_100a)"; }
@@ -745,7 +754,7 @@ static std::shared_ptr<RefJob> start_reference_tree(const TakeSceneDesc *d, int 
 
 // The fast tree is built on the device (bvh_device.cuh) unless TAKE_DEVICE_BUILD=0 asks for the host's binned-SAH builder
 // (the A/B baseline for tree quality; also what the prebuilt / saved-build paths use).
-int take_gpu_scene_create(int device, const TakeSceneDesc *d, TakeScene **out) {
+int take_gpu_scene_create(int device, const TakeSceneDesc *d, TakeScene **out) try {
     if (!out) return fail(TAKE_E_INVALID, "null argument");
     *out = nullptr;
     const double t0 = now_ms();
@@ -761,7 +770,7 @@ int take_gpu_scene_create(int device, const TakeSceneDesc *d, TakeScene **out) {
     }
     if (rc == TAKE_OK) { (*out)->create_ms[0] = t_validate; (*out)->create_ms[5] = now_ms() - t0; }
     return rc;
-}
+} catch (...) { return translate_exception(); }
 
 // Join the background build of the reference-order tree (device-built scenes), upload it and write the tie-break ranks into
 // the leaf records.  Every entry point that traces rays calls this first; it is a no-op afterwards.
@@ -1233,13 +1242,13 @@ int take_gpu_release_cached_memory(int device) {
 }
 
 // diagnostics: out[0..5] = reference-tree build ms, fast-tree build ms, fast-tree depth, SAH cost, #fast nodes, #SMs
-int take_gpu_scene_info(TakeScene *s, double *out) {
+int take_gpu_scene_info(TakeScene *s, double *out) try {
     if (!s || !out) return fail(TAKE_E_INVALID, "null argument");
     if (int rc = finish_reference_tree(s)) return rc;   // (its build time is one of the figures)
     out[0] = s->build_ms_ref; out[1] = s->build_ms_fast; out[2] = s->fast_depth; out[3] = s->sah_cost;
     out[4] = (double)s->num_fast_nodes; out[5] = s->sm_count;
     return TAKE_OK;
-}
+} catch (...) { return translate_exception(); }
 
 // out[0..7] = ms of take_gpu_scene_create: validate, scene upload, primitive boxes for the reference-order tree (host), fast
 // tree (device build; 0 for host-built scenes), shading / light records, whole call, 1 if the fast tree was built on the
@@ -1281,7 +1290,7 @@ struct TakeHostBuild {
     HostBuild hb;
 };
 
-int take_gpu_host_build(const TakeSceneDesc *d, TakeHostBuild **out) {
+int take_gpu_host_build(const TakeSceneDesc *d, TakeHostBuild **out) try {
     if (!out) return fail(TAKE_E_INVALID, "null argument");
     *out = nullptr;
     if (int rc = validate(d)) return rc;
@@ -1289,7 +1298,7 @@ int take_gpu_host_build(const TakeSceneDesc *d, TakeHostBuild **out) {
     if (int rc = host_build(d, host_threads(), h->hb)) { delete h; return rc; }
     *out = h;
     return TAKE_OK;
-}
+} catch (...) { return translate_exception(); }
 // out[0..7] = #reference nodes, reference root, #fast nodes, #prims, fast depth, abs_max, build ms (ref), build ms (fast)
 int take_gpu_host_build_info(TakeHostBuild *h, double *out) {
     if (!h || !out) return fail(TAKE_E_INVALID, "null argument");
@@ -1394,7 +1403,7 @@ int take_gpu_host_build_save(TakeHostBuild *h, const char *path) {
     return TAKE_OK;
 }
 
-int take_gpu_host_build_load(const char *path, TakeHostBuild **out) {
+int take_gpu_host_build_load(const char *path, TakeHostBuild **out) try {
     if (!path || !out) return fail(TAKE_E_INVALID, "null argument");
     *out = nullptr;
     FILE *f = fopen(path, "rb");
@@ -1436,9 +1445,9 @@ int take_gpu_host_build_load(const char *path, TakeHostBuild **out) {
     b.fast.wide_depth = hd.wide_depth; b.fast.sah_cost = hd.sah_cost; b.abs_max = hd.abs_max; b.ms_ref = hd.ms_ref; b.ms_fast = hd.ms_fast;
     *out = h;
     return TAKE_OK;
-}
+} catch (...) { return translate_exception(); }
 
-int take_gpu_scene_create_prebuilt(int device, const TakeSceneDesc *d, TakeHostBuild *h, TakeScene **out) {
+int take_gpu_scene_create_prebuilt(int device, const TakeSceneDesc *d, TakeHostBuild *h, TakeScene **out) try {
     if (!out || !h) return fail(TAKE_E_INVALID, "null argument");
     *out = nullptr;
     if (int rc = validate(d)) return rc;
@@ -1448,9 +1457,9 @@ int take_gpu_scene_create_prebuilt(int device, const TakeSceneDesc *d, TakeHostB
         return fail(TAKE_E_INVALID, "the prebuilt acceleration structures do not belong to this scene");
     if (b.fast.depth > TAKE_STACK_SMEM + TAKE_STACK_LOCAL) return fail(TAKE_E_INVALID, "acceleration tree too deep");
     return scene_create_from(device, d, &h->hb, out);
-}
+} catch (...) { return translate_exception(); }
 
-int take_gpu_intersect_device(TakeScene *s, const TakeRay *d_rays, int64_t n, TakeHit *d_hits, int flags) {
+int take_gpu_intersect_device(TakeScene *s, const TakeRay *d_rays, int64_t n, TakeHit *d_hits, int flags) try {
     if (!s || (n > 0 && (!d_rays || !d_hits))) return fail(TAKE_E_INVALID, "null argument");
     if (n < 0) return fail(TAKE_E_INVALID, "negative ray count");
     if (n == 0) return TAKE_OK;
@@ -1479,9 +1488,9 @@ int take_gpu_intersect_device(TakeScene *s, const TakeRay *d_rays, int64_t n, Ta
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s->stream));
     return TAKE_OK;
-}
+} catch (...) { return translate_exception(); }
 
-int take_gpu_intersect(TakeScene *s, const TakeRay *rays, int64_t n, TakeHit *hits, int flags) {
+int take_gpu_intersect(TakeScene *s, const TakeRay *rays, int64_t n, TakeHit *hits, int flags) try {
     if (!s || (n > 0 && (!rays || !hits))) return fail(TAKE_E_INVALID, "null argument");
     if (n < 0) return fail(TAKE_E_INVALID, "negative ray count");
     CU(cudaSetDevice(s->device));
@@ -1496,9 +1505,9 @@ int take_gpu_intersect(TakeScene *s, const TakeRay *rays, int64_t n, TakeHit *hi
         CU(cudaStreamSynchronize(s->stream));
     }
     return TAKE_OK;
-}
+} catch (...) { return translate_exception(); }
 
-int take_gpu_occluded(TakeScene *s, const TakeRay *rays, int64_t n, uint8_t *occluded) {
+int take_gpu_occluded(TakeScene *s, const TakeRay *rays, int64_t n, uint8_t *occluded) try {
     if (!s || (n > 0 && (!rays || !occluded))) return fail(TAKE_E_INVALID, "null argument");
     if (n < 0) return fail(TAKE_E_INVALID, "negative ray count");
     CU(cudaSetDevice(s->device));
@@ -1523,7 +1532,7 @@ int take_gpu_occluded(TakeScene *s, const TakeRay *rays, int64_t n, uint8_t *occ
         CU(cudaStreamSynchronize(s->stream));
     }
     return TAKE_OK;
-}
+} catch (...) { return translate_exception(); }
 
 }  // extern "C"
 
@@ -1617,7 +1626,7 @@ int render_enqueue(TakeScene *s, const TakeRenderOpts *o, double *d_sum, double 
 
 extern "C" {
 
-int take_gpu_render_device(TakeScene *s, const TakeRenderOpts *o, double *d_sum, double *d_sumsq, TakeStats *stats) {
+int take_gpu_render_device(TakeScene *s, const TakeRenderOpts *o, double *d_sum, double *d_sumsq, TakeStats *stats) try {
     if (int rc = check_opts(s, o)) return rc;
     if (!d_sum) return fail(TAKE_E_INVALID, "null output buffer");
     CU(cudaSetDevice(s->device));
@@ -1677,10 +1686,10 @@ int take_gpu_render_device(TakeScene *s, const TakeRenderOpts *o, double *d_sum,
     tm.collect();
     read_totals(s, stats, tm, ms, launches, waves);
     return TAKE_OK;
-}
+} catch (...) { return translate_exception(); }
 
 // ---- asynchronous render: up to two calls in flight; the device->host copy of call k overlaps the kernels of call k+1 --
-int take_gpu_render_async(TakeScene *s, const TakeRenderOpts *o, double *sum_rgb, double *sumsq_rgb, int64_t *ticket) {
+int take_gpu_render_async(TakeScene *s, const TakeRenderOpts *o, double *sum_rgb, double *sumsq_rgb, int64_t *ticket) try {
     if (int rc = check_opts(s, o)) return rc;
     if (!sum_rgb || !ticket) return fail(TAKE_E_INVALID, "null argument");
     if ((o->flags & TAKE_RENDER_STAGE_TIMES) || env_int("TAKE_STAGE_TIMES", 0))
@@ -1716,9 +1725,9 @@ int take_gpu_render_async(TakeScene *s, const TakeRenderOpts *o, double *sum_rgb
     a.ticket = s->next_ticket;
     *ticket = s->next_ticket++;
     return TAKE_OK;
-}
+} catch (...) { return translate_exception(); }
 
-int take_gpu_render_wait(TakeScene *s, int64_t ticket, TakeStats *stats) {
+int take_gpu_render_wait(TakeScene *s, int64_t ticket, TakeStats *stats) try {
     if (!s) return fail(TAKE_E_INVALID, "null scene");
     TakeScene::AsyncSlot &a = s->async_slot[ticket & 1];
     if (!a.busy || a.ticket != ticket) return fail(TAKE_E_INVALID, "unknown or already collected ticket");
@@ -1730,9 +1739,9 @@ int take_gpu_render_wait(TakeScene *s, int64_t ticket, TakeStats *stats) {
     StageTimer tm;
     fill_stats(*a.h_totals, stats, tm, ms, a.launches, a.waves);
     return TAKE_OK;
-}
+} catch (...) { return translate_exception(); }
 
-int take_gpu_render(TakeScene *s, const TakeRenderOpts *o, double *sum_rgb, double *sumsq_rgb, TakeStats *stats) {
+int take_gpu_render(TakeScene *s, const TakeRenderOpts *o, double *sum_rgb, double *sumsq_rgb, TakeStats *stats) try {
     if (int rc = check_opts(s, o)) return rc;
     if (!sum_rgb) return fail(TAKE_E_INVALID, "null output buffer");
     CU(cudaSetDevice(s->device));
@@ -1749,7 +1758,7 @@ int take_gpu_render(TakeScene *s, const TakeRenderOpts *o, double *sum_rgb, doub
     if (sumsq_rgb) CU(cudaMemcpyAsync(sumsq_rgb, s->scratch_b.p, bytes, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     return TAKE_OK;
-}
+} catch (...) { return translate_exception(); }
 
 // ---- single-process multi-GPU render: scene replicated, sample ranges sharded, one NCCL sum-reduce ------------------
 }  // extern "C"
@@ -1816,7 +1825,7 @@ int take_gpu_multi_destroy(TakeMulti *m) {
     return TAKE_OK;
 }
 
-int take_gpu_multi_create(int ndev, const int *devices, const TakeSceneDesc *d, TakeMulti **out) {
+int take_gpu_multi_create(int ndev, const int *devices, const TakeSceneDesc *d, TakeMulti **out) try {
     if (!out) return fail(TAKE_E_INVALID, "null argument");
     *out = nullptr;
     if (ndev < 1 || ndev > 64 || !devices) return fail(TAKE_E_INVALID, "bad device list");
@@ -1875,11 +1884,11 @@ int take_gpu_multi_create(int ndev, const int *devices, const TakeSceneDesc *d, 
     }
     *out = m;
     return TAKE_OK;
-}
+} catch (...) { return translate_exception(); }
 
 // Device i renders a contiguous share of [spp_begin, spp_end) of every pixel; the partial sums are combined on
 // devices[0] with one grouped ncclReduce (the path's one exchange step) and copied to the host from there.
-int take_gpu_multi_render(TakeMulti *m, const TakeRenderOpts *o, double *sum_rgb, double *sumsq_rgb, TakeStats *stats) {
+int take_gpu_multi_render(TakeMulti *m, const TakeRenderOpts *o, double *sum_rgb, double *sumsq_rgb, TakeStats *stats) try {
     if (!m || !o || !sum_rgb) return fail(TAKE_E_INVALID, "null argument");
     if (int rc = check_opts(m->scenes[0], o)) return rc;
     const int ndev = m->ndev;
@@ -1938,11 +1947,11 @@ int take_gpu_multi_render(TakeMulti *m, const TakeRenderOpts *o, double *sum_rgb
         }
     }
     return TAKE_OK;
-}
+} catch (...) { return translate_exception(); }
 
 // One-shot form: create, render once, destroy.
 int take_gpu_render_multi(int ndev, const int *devices, const TakeSceneDesc *d, const TakeRenderOpts *o, double *sum_rgb,
-                          double *sumsq_rgb, TakeStats *stats) {
+                          double *sumsq_rgb, TakeStats *stats) try {
     if (ndev < 1 || !devices || !o || !sum_rgb) return fail(TAKE_E_INVALID, "bad arguments");
     TakeMulti *m = nullptr;
     if (int rc = take_gpu_multi_create(ndev, devices, d, &m)) return rc;
@@ -1951,10 +1960,10 @@ int take_gpu_render_multi(int ndev, const int *devices, const TakeSceneDesc *d, 
     take_gpu_multi_destroy(m);
     if (rc) g_error = e;
     return rc;
-}
+} catch (...) { return translate_exception(); }
 
 // ---- output step: mean, double -> float -> half, B/G/R planes, ZIP pre-filter on the device (exr_out.cuh) -----------
-int take_gpu_exr_pack_device(TakeScene *s, const double *d_sum_rgb, int64_t spp, uint8_t *packed) {
+int take_gpu_exr_pack_device(TakeScene *s, const double *d_sum_rgb, int64_t spp, uint8_t *packed) try {
     if (!s || !d_sum_rgb || !packed || spp <= 0) return fail(TAKE_E_INVALID, "take_gpu_exr_pack_device: bad arguments");
     CU(cudaSetDevice(s->device));
     const int64_t bytes = take_gpu_exr_packed_size(s->width, s->height);
@@ -1970,18 +1979,18 @@ int take_gpu_exr_pack_device(TakeScene *s, const double *d_sum_rgb, int64_t spp,
     CU(cudaMemcpyAsync(packed, s->exr_packed.p, (size_t)bytes, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     return TAKE_OK;
-}
+} catch (...) { return translate_exception(); }
 
-int take_gpu_exr_pack(TakeScene *s, const double *sum_rgb, int64_t spp, uint8_t *packed) {
+int take_gpu_exr_pack(TakeScene *s, const double *sum_rgb, int64_t spp, uint8_t *packed) try {
     if (!s || !sum_rgb) return fail(TAKE_E_INVALID, "take_gpu_exr_pack: bad arguments");
     CU(cudaSetDevice(s->device));
     const size_t bytes = (size_t)s->width * s->height * 3 * sizeof(double);
     CU(s->scratch_a.ensure(bytes));
     CU(cudaMemcpyAsync(s->scratch_a.p, sum_rgb, bytes, cudaMemcpyHostToDevice, s->stream));
     return take_gpu_exr_pack_device(s, s->scratch_a.as<double>(), spp, packed);
-}
+} catch (...) { return translate_exception(); }
 
-int take_gpu_render_to_exr(TakeScene *s, const TakeRenderOpts *o, const char *path, TakeStats *stats) {
+int take_gpu_render_to_exr(TakeScene *s, const TakeRenderOpts *o, const char *path, TakeStats *stats) try {
     if (int rc = check_opts(s, o)) return rc;
     if (!path) return fail(TAKE_E_INVALID, "null path");
     if (o->spp_end <= o->spp_begin) return fail(TAKE_E_INVALID, "empty sample range");
@@ -1993,10 +2002,10 @@ int take_gpu_render_to_exr(TakeScene *s, const TakeRenderOpts *o, const char *pa
     std::vector<uint8_t> packed((size_t)take_gpu_exr_packed_size(s->width, s->height));
     if (int rc = take_gpu_exr_pack_device(s, s->scratch_a.as<double>(), o->spp_end - o->spp_begin, packed.data())) return rc;
     return take_gpu_exr_write_packed(path, s->width, s->height, packed.data(), 0);
-}
+} catch (...) { return translate_exception(); }
 
 int take_gpu_radiance_samples(TakeScene *s, const TakeRenderOpts *o, int64_t n, const int32_t *px, const int32_t *py,
-                              const int64_t *smp, double *rgb) {
+                              const int64_t *smp, double *rgb) try {
     if (int rc = check_opts(s, o)) return rc;
     if (n < 0 || (n > 0 && (!px || !py || !smp || !rgb))) return fail(TAKE_E_INVALID, "bad sample list");
     if (n == 0) return TAKE_OK;
@@ -2033,6 +2042,6 @@ int take_gpu_radiance_samples(TakeScene *s, const TakeRenderOpts *o, int64_t n, 
         CU(cudaStreamSynchronize(s->stream));
     }
     return TAKE_OK;
-}
+} catch (...) { return translate_exception(); }
 
 }  // extern "C"
