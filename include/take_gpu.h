@@ -214,6 +214,16 @@ int take_gpu_occluded(TakeScene *scene, const TakeRay *rays, int64_t n, uint8_t 
  * followed by a stream synchronise). */
 int take_gpu_intersect_device(TakeScene *scene, const TakeRay *d_rays, int64_t n, TakeHit *d_hits, int flags);
 
+/* Schedule switches (environment variables, read per call; for A/B measurements and for the parity tests, which compare the
+ * schedules against each other -- NONE of them changes a result):
+ *   TAKE_PACKET=0        camera rays one per thread instead of one packet per warp (trace_packet4)
+ *   TAKE_REFILL=0..3     bit 0: bounce passes, bit 1: shadow passes traced with lane refill (trace_refill4); default 3
+ *   TAKE_ORDERED_SORT=0  the material sort keeps the order in which rays finished instead of queue order
+ *   TAKE_NO_MISS_FAST=1  camera rays that leave the scene go through sort and shade like any other
+ *   TAKE_OVERLAP=0       one wave at a time instead of two in flight;  TAKE_WAVE_SLOTS=n  path samples per wave
+ *   TAKE_PROVISIONAL=0   renders wait for the reference-order tree instead of running ahead of it
+ *   TAKE_DEVICE_BUILD=0  host tree builders;  TAKE_HOST_THREADS=n;  TAKE_MEMPOOL=0;  TAKE_TIMING=1 (creation phases to stderr) */
+
 /* The render loop (replaces the tile lambda of src/render.cpp:59-82 and the integrators of
  * src/integrator/path_tracing.h).  Adds, for every pixel, the radiance of samples
  * [spp_begin, spp_end) to sum_rgb and its square to sumsq_rgb (may be NULL): height*width*3 doubles in image
