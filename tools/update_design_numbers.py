@@ -82,6 +82,11 @@ if os.path.exists(ml):
             f"{m['file_MB']:.0f} MB binary PLY without normals → flat arrays in **{m['builder_s']:.2f} s** (read {m['builder_ms']['ms_read']:.0f} ms, "
             f"convert {m['builder_ms']['ms_convert']:.0f} ms, vertex normals {m['builder_ms']['ms_normals']:.0f} ms, append {m['builder_ms']['ms_append']:.0f} ms); "
             f"the reference parser with its BVH: {m['reference_parse_and_bvh_s']:.1f} s; arrays identical: {m['identical']}.\n")
+lg = P(f"{TAG}_bench_n1_256steps.json")
+if os.path.exists(lg):
+    g = json.load(open(lg))
+    sec += (f"\nSustained: the same command with `--steps 256` ({g['ms_per_step'] * g['steps'] / 1e3:.1f} s timed, `profiles/{TAG}_bench_n1_256steps.json`): "
+            f"{g['value']:.0f} Mrays/s, e2e {g['e2e']['value']:.0f}, SM clock {g['clocks']['sm_mhz']:.0f} MHz over {g['clocks']['samples']} samples, throttle reasons: {g['clocks']['reasons'] or 'none'}.\n")
 sec += ("\n`compute-sanitizer` is closed on this pool (gpurun refuses it), so memory safety rests on the parity suite, the\n"
         "host-side validation of every index array in `take_gpu_scene_create`, and `tools/sanitize_run.py` (every kernel on\n"
         "tiny waves and chunked images) running clean.\n")
