@@ -20,3 +20,5 @@ python tools/ncu_lines.py $T/refill.ncu-rep k_extend_refillILb0ELb0 0 40 > $O/li
 cap shade4 k_shade 1 1 $A4
 python tools/ncu_lines.py $T/shade4.ncu-rep k_shadeILi0ELb0ELb0 0 45 > $O/lines_shade_mis_config4_pass1.txt 2>&1
 head -3 $O/lines_*.txt
+cap primary k_extend_primary 1 1 $A2                              # the heavy half of the frame (wave 1)
+python tools/ncu_lines.py $T/primary.ncu-rep k_extend_primaryILb0ELb0 0 40 > $O/lines_extend_primary.txt 2>&1

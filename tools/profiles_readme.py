@@ -34,7 +34,7 @@ L = [f"# profiles/ — round 2 (`{TAG}_*`; `r01_*` are round 1's files, kept for
      f"| `{TAG}_ncu_extend.csv`, `{TAG}_ncu_shade.csv`, `{TAG}_ncu_shadow.csv` | key metrics + stall shares of EVERY launch of one bench step of config 2 (`tools/prof_run.py`: 32 spp x 1920x1080 = two waves of 33.2 M slots, 7 passes each -> 14 extend and 14 shade launches; the shadow kernel from a 16-spp multi-sample wave) |",
      "| `ncu_metrics.json` | per-kernel aggregates of those captures (DRAM bytes per launch, L2->SM GB/s, issue-active %, lanes per instruction), stamped with a hash of the kernel sources; `bench.py` quotes them under `roofline.ncu` / `roofline.traffic` only when the hash matches the sources it runs |",
      f"| `{TAG}_ncu_shade_mis_config4.csv`, `{TAG}_ncu_traversal_config5.csv` | the same for the multi-sample shade kernel on the config-4 scene (`--scene=multi_light --integrator=mis --spp=16`, passes 0-6 of a wave) and the traversal kernels on the 10 M-triangle scene (`--scene=instanced --spp=4`: `k_extend_primary`, then `k_extend_refill` / `k_shadow_refill` alternating) |",
-     f"| `{TAG}_lines_extend_pass2_one_ray_per_thread.txt`, `{TAG}_lines_extend_pass1_lane_refill.txt`, `{TAG}_lines_shade_mis_config4_pass1.txt` | `tools/lines_round.sh` / `tools/ncu_lines.py`: stall samples, instruction share and active lanes PER SOURCE LINE of a bounce pass of config 2 traced one ray per thread (`TAKE_REFILL=0`: 9 of 32 lanes) and with lane refill (17.5 lanes), and of the multi-sample shade kernel on the config-4 scene |",
+     f"| `{TAG}_lines_extend_pass2_one_ray_per_thread.txt`, `{TAG}_lines_extend_pass1_lane_refill.txt`, `{TAG}_lines_shade_mis_config4_pass1.txt`, `{TAG}_lines_extend_primary.txt` | `tools/lines_round.sh` / `tools/ncu_lines.py`: stall samples, instruction share and active lanes PER SOURCE LINE of a bounce pass of config 2 traced one ray per thread (`TAKE_REFILL=0`: 9 of 32 lanes) and with lane refill (17.5 lanes), of the multi-sample shade kernel on the config-4 scene, and of the camera-ray packet kernel (the four box tests per lane and node are 36 % of its instructions) |",
      f"| `{TAG}_prof_run_counts.txt` | box / leaf test counts of the profiled step (instrumented kernels) |",
      f"| `{TAG}_build_bench.jsonl` | `tools/build_bench.py`: `take_gpu_scene_create` per config with the device builder and with the host builders, phase by phase |",
      f"| `{TAG}_device_vs_host_tree.jsonl` | `tools/tune.py`: a 32-spp step on the device-built and on the host-built tree (three scenes) |",
