@@ -1044,8 +1044,11 @@ struct ExtendRefillIO {
 #ifndef TAKE_REFILL_MIN_BLOCKS
 #define TAKE_REFILL_MIN_BLOCKS TAKE_BOUNCE_MIN_BLOCKS
 #endif
+#ifndef TAKE_REFILL_EXTEND_MIN_BLOCKS
+#define TAKE_REFILL_EXTEND_MIN_BLOCKS TAKE_REFILL_MIN_BLOCKS
+#endif
 template <bool COUNT, bool TIES = false>
-__global__ void __launch_bounds__(128, TAKE_REFILL_MIN_BLOCKS) k_extend_refill(DevScene sc, Wave w, int pass) {
+__global__ void __launch_bounds__(128, TAKE_REFILL_EXTEND_MIN_BLOCKS) k_extend_refill(DevScene sc, Wave w, int pass) {
     TAKE_DECLARE_STACK(st);
     PassCounters &pc = w.pass[pass];
     ExtendRefillIO io = {w, pc, w.q_extend[pass & 1], sc.prim_mtype, -1, 0};

@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun call that produces everything profiles/ is built from (run from the repo root on the GPU box):
 #   gpurun --timeout 2400 -- 'bash tools/gpu_round.sh'
-# Each ncu pass runs only after its own command exited 0 without ncu.  Numbers printed under ncu are never bench values.
+# Each ncu pass runs only after its own command (tools/prof_run.py) exited 0 without ncu; the bench arms run last.  Numbers printed under ncu are never bench values.
 # The .ncu-rep files are turned into raw CSV pages ON THE BOX and deleted (gpurun_out/ may carry 64 MiB back); set
 # KEEP_REP=extend|shade|shadow to keep one report (for tools/ncu_lines.py's per-source-line view).
 # Switches: SKIP_TESTS=1, SKIP_BENCH=1, SKIP_NCU=1, EXTRA_NCU=1 (config-4 shade, config-5 traversal), TESTS="-k expr"
@@ -17,25 +17,6 @@ if [ "${SKIP_TESTS:-0}" != "1" ]; then
   tail -5 $O/pytest_gpu.log
 fi
 
-rc=0
-if [ "${SKIP_BENCH:-0}" != "1" ]; then
-  timeout 600 python bench.py --impl reference > $O/bench_reference_n1.json 2> $O/bench_reference_n1.err
-  echo "bench reference exit $?"
-  timeout 1200 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err
-  rc=$?
-  echo "bench exit $rc"
-  python - <<'EOF'
-import json
-try:
-    d = json.load(open("gpurun_out/bench_n1.json"))
-    print({k: d[k] for k in ("value", "ms_per_step", "scene_create_ms")}, "e2e", d["e2e"]["value"], "frac", d["roofline"]["frac"])
-    for r in d.get("scenes", []):
-        print({k: (round(v, 1) if isinstance(v, float) else v) for k, v in r.items() if k in ("key", "job_ms", "mrays_per_s", "samples_per_s", "scene_create_ms", "e2e_job_ms", "e2e_job_cold_ms", "provisional", "error")})
-except Exception as e:
-    print("bench line unreadable:", e)
-EOF
-fi
-
 capture() {  # capture <name> <ncu kernel regex> <count> <timeout> <prof_run args...>
   local name=$1 rx=$2 cnt=$3 to=$4; shift 4
   # (TAKE_PROVISIONAL=0: the first render waits for the tie-break ranks, so the captured kernels are the regular ones and not
@@ -49,7 +30,7 @@ capture() {  # capture <name> <ncu kernel regex> <count> <timeout> <prof_run arg
   fi
 }
 
-if [ $rc -eq 0 ] && [ "${SKIP_NCU:-0}" != "1" ]; then
+if [ "${SKIP_NCU:-0}" != "1" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/launches_bench.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline --scenes '' > $O/ncu_launches.log 2>&1
   echo "ncu launches exit $?"
@@ -72,5 +53,26 @@ if [ "${EXTRA_NCU:-0}" = "1" ]; then
     capture traversal_config5 'k_extend|k_shadow' 8 900 $A5
   fi
 fi
+# the bench arms come AFTER the captures: tools/ncu_summary.py stamps profiles/ncu_metrics.json with the hash of the kernel
+# sources on this box, and bench.py quotes ncu figures only from a capture of the sources it runs
+if [ "${SKIP_NCU:-0}" != "1" ]; then python tools/ncu_summary.py ${TAG:-r02} > $O/ncu_summary.log 2>&1; cp profiles/ncu_metrics.json $O/ 2>/dev/null; fi
+if [ "${SKIP_BENCH:-0}" != "1" ]; then
+  timeout 600 python bench.py --impl reference > $O/bench_reference_n1.json 2> $O/bench_reference_n1.err
+  echo "bench reference exit $?"
+  timeout 1200 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err
+  rc=$?
+  echo "bench exit $rc"
+  python - <<'EOF'
+import json
+try:
+    d = json.load(open("gpurun_out/bench_n1.json"))
+    print({k: d[k] for k in ("value", "ms_per_step", "scene_create_ms")}, "e2e", d["e2e"]["value"], "frac", d["roofline"]["frac"])
+    for r in d.get("scenes", []):
+        print({k: (round(v, 1) if isinstance(v, float) else v) for k, v in r.items() if k in ("key", "job_ms", "mrays_per_s", "samples_per_s", "scene_create_ms", "e2e_job_ms", "e2e_job_cold_ms", "provisional", "error")})
+except Exception as e:
+    print("bench line unreadable:", e)
+EOF
+fi
+
 ls -la $O | tail -30
 du -sh $O
