@@ -54,7 +54,8 @@ scale = [json.load(open(P(f"{TAG}_scale_n{k}.json"))) for k in (1, 2, 4, 8) if o
 if scale:
     base, ebase = scale[0]["value"], scale[0]["e2e"]["value"]
     sec += (f"\nMulti-GPU, weak scaling of the headline (one process per GPU, `ShardedRenderer`, **one NCCL reduce per step** inside the timed "
-            f"region, NCCL limited to four channels; `profiles/{TAG}_scale_n*.json`):\n\n"
+            f"region, NCCL limited to four channels; `profiles/{TAG}_scale_n*.json` -- the four runs are one set, taken at the commit before "
+            f"`k_extend_refill` went from 6 to 7 resident blocks, so their N = 1 line reads {scale[0]['value']:.0f} where the table above reads {b['value']:.0f}):\n\n"
             "| GPUs | Mrays/s | e2e Mrays/s | ms per step | efficiency (value / e2e) | in-run checks |\n|---|---|---|---|---|---|\n")
     for x in scale:
         ck = x.get("checks") or {}
